@@ -1,0 +1,215 @@
+"""Quick on-GPU kernel checks against torch's own CUDA ops (development aid, not the parity
+suite — that lives in tests/ and checks against oracle/). Usage:
+    python tools/gpu_selftest.py            # runs every group, each in its own subprocess
+    python tools/gpu_selftest.py --group gemm_bf16
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+GROUPS = {}
+
+
+def group(fn):
+    GROUPS[fn.__name__] = fn
+    return fn
+
+
+def rel_err(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item(), (a - b).abs().max().item()
+
+
+def report(name, got, ref, tol):
+    r, m = rel_err(got, ref)
+    ok = r <= tol and bool(got.isfinite().all().item())
+    print(f"  [{'PASS' if ok else 'FAIL'}] {name}: rel={r:.3e} maxabs={m:.3e} tol={tol:.1e}", flush=True)
+    return ok
+
+
+def _gemm_cases(dtype, tol):
+    import torch
+    from vyomai_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    shapes = [(128, 128, 64), (256, 256, 128), (384, 768, 768), (1024, 3072, 768), (1000, 520, 264),
+              (8192, 768, 3072), (300, 50265 if dtype == torch.bfloat16 else 1000, 768)]
+    for (M, N, K) in shapes:
+        a = torch.randn(M, K, device=dev, dtype=dtype)
+        b = torch.randn(N, K, device=dev, dtype=dtype) / K ** 0.5
+        bias = torch.randn(N, device=dev, dtype=dtype)
+        ref = (a.float() @ b.float().t()) + bias.float()
+        ldo = (N + 7) // 8 * 8
+        outbuf = torch.empty(M, ldo, device=dev, dtype=dtype)
+        out = ops.gemm(a, b, bias=bias, out=outbuf[:, :N])
+        ok &= report(f"NT {M}x{N}x{K} bias", out, ref, tol)
+        at = a.t().contiguous().t()  # logical (M,K) stored transposed -> MN-major
+        bt = b.t().contiguous().t()
+        if M % 8 == 0 and N % 8 == 0:
+            ok &= report(f"A_MN {M}x{N}x{K}", ops.gemm(at, b, bias=bias, out=outbuf[:, :N]), ref, tol)
+            ok &= report(f"B_MN {M}x{N}x{K}", ops.gemm(a, bt, bias=bias, out=outbuf[:, :N]), ref, tol)
+            ok &= report(f"AB_MN {M}x{N}x{K}", ops.gemm(at, bt, bias=bias, out=outbuf[:, :N]), ref, tol)
+    # epilogues
+    M, N, K = 512, 768, 768
+    a = torch.randn(M, K, device=dev, dtype=dtype)
+    b = torch.randn(N, K, device=dev, dtype=dtype) / K ** 0.5
+    bias = torch.randn(N, device=dev, dtype=dtype)
+    res = torch.randn(M, N, device=dev, dtype=dtype)
+    z = a.float() @ b.float().t() + bias.float()
+    aux = torch.empty(M, N, device=dev, dtype=dtype)
+    out = ops.gemm(a, b, bias=bias, act="gelu", aux=aux)
+    ok &= report("gelu_erf", out, torch.nn.functional.gelu(z), tol)
+    ok &= report("gelu aux(pre-act)", aux, z, tol)
+    out = ops.gemm(a, b, bias=bias, act="gelu_tanh")
+    ok &= report("gelu_tanh", out, torch.nn.functional.gelu(z, approximate="tanh"), tol)
+    out = ops.gemm(a, b, bias=bias, addend=res)
+    ok &= report("residual addend", out, z + res.float(), tol)
+    zz = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    out = ops.gemm(a, b, act="dgelu", aux=aux)
+    ok &= report("dgelu", out, (a.float() @ b.float().t()) * zz.grad, tol * 2)
+    other = torch.float32 if dtype == torch.bfloat16 else torch.bfloat16
+    ok &= report("cross out dtype", ops.gemm(a, b, bias=bias, out_dtype=other), z, max(tol, 4e-3))
+    # swap-AB (decode shapes)
+    for (M, N, K) in [(32, 768, 768), (32, 3072, 768), (32, 768, 3072), (3, 2304, 768), (64, 50265, 768), (1, 768, 768)]:
+        a = torch.randn(M, K, device=dev, dtype=dtype)
+        b = torch.randn(N, K, device=dev, dtype=dtype) / K ** 0.5
+        bias = torch.randn(N, device=dev, dtype=dtype)
+        res = torch.randn(M, N, device=dev, dtype=dtype)
+        ref = torch.nn.functional.gelu(a.float() @ b.float().t() + bias.float()) + res.float()
+        out = ops.gemm(a, b, bias=bias, act="gelu", addend=res, swap_ab=True)
+        ok &= report(f"swapAB {M}x{N}x{K} gelu+res", out, ref, tol)
+    # patch-embed style remap: rows grouped 196 -> 197 with offset 1, addend row mod, scale 2
+    Bn, P, Hd, Kp = 4, 196, 768, 768
+    a = torch.randn(Bn * P, Kp, device=dev, dtype=dtype)
+    w = torch.randn(Hd, Kp, device=dev, dtype=dtype) / Kp ** 0.5
+    bias = torch.randn(Hd, device=dev, dtype=dtype)
+    pos = torch.randn(P + 1, Hd, device=dev, dtype=dtype)
+    outb = torch.zeros(Bn * (P + 1), Hd, device=dev, dtype=dtype)
+    ops.gemm(a, w, bias=bias, addend=pos, addend_row_mod=P, addend_row_off=1, out=outb, out_scale=2.0,
+             out_row_group=P, out_row_group_stride=P + 1, out_row_off=1)
+    ref = 2 * ((a.float() @ w.float().t() + bias.float()).view(Bn, P, Hd) + pos.float()[1:])
+    ok &= report("patch remap", outb.view(Bn, P + 1, Hd)[:, 1:], ref, tol)
+    ok &= bool((outb.view(Bn, P + 1, Hd)[:, 0] == 0).all().item())
+    return ok
+
+
+@group
+def gemm_bf16():
+    import torch
+    return _gemm_cases(torch.bfloat16, 6e-3)
+
+
+@group
+def gemm_tf32():
+    import torch
+    return _gemm_cases(torch.float32, 2e-3)
+
+
+@group
+def qkv_rope():
+    import torch
+    from vyomai_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    for dtype, tol in ((torch.bfloat16, 8e-3), (torch.float32, 2e-3)):
+        for (B, S, hq, hkv, start, smax) in [(8, 128, 12, 4, 0, 128), (3, 17, 12, 12, 0, 32), (2, 5, 12, 4, 7, 40)]:
+            d, H = 64, 768
+            N = (hq + 2 * hkv) * d
+            x = torch.randn(B * S, H, device=dev, dtype=dtype)
+            w = torch.randn(N, H, device=dev, dtype=dtype) / H ** 0.5
+            bias = torch.randn(N, device=dev, dtype=dtype)
+            inv = 1.0 / (10000 ** (torch.arange(0, d, 2, device=dev).float() / d))
+            ang = torch.arange(smax, device=dev).float()[:, None] * inv[None]
+            cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+            q = torch.zeros(B, hq, S, d, device=dev, dtype=dtype)
+            kc = torch.zeros(B, hkv, smax, d, device=dev, dtype=dtype)
+            vc = torch.zeros(B, hkv, smax, d, device=dev, dtype=dtype)
+            ops.qkv_rope_gemm(x, w, bias, tokens_per_seq=S, start_pos=start, n_q_heads=hq, n_kv_heads=hkv,
+                              head_dim=d, rope_cos=cos, rope_sin=sin, q_out=q, k_out=kc, v_out=vc)
+            y = (x.float() @ w.float().t() + bias.float()).view(B, S, hq + 2 * hkv, d).permute(0, 2, 1, 3)
+            c = torch.cat([cos, cos], -1)[start:start + S][None, None]
+            s_ = torch.cat([sin, sin], -1)[start:start + S][None, None]
+
+            def rot(t):
+                t1, t2 = t.chunk(2, -1)
+                return t * c + torch.cat([-t2, t1], -1) * s_
+
+            ok &= report(f"q {dtype} B{B} S{S} start{start}", q, rot(y[:, :hq]), tol)
+            ok &= report("k cache", kc[:, :, start:start + S], rot(y[:, hq:hq + hkv]), tol)
+            ok &= report("v cache", vc[:, :, start:start + S], y[:, hq + hkv:], tol)
+            ok &= bool((kc[:, :, :start] == 0).all().item() and (kc[:, :, start + S:] == 0).all().item())
+    return ok
+
+
+@group
+def layernorm():
+    import torch
+    from vyomai_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    for dtype, tol in ((torch.float32, 2e-6), (torch.bfloat16, 4e-3)):
+        for rows, H in ((1024, 768), (51, 768), (333, 1152), (64, 2048), (7, 64)):
+            x = torch.randn(rows, H, device=dev, dtype=dtype)
+            r = torch.randn(rows, H, device=dev, dtype=dtype)
+            g = torch.randn(H, device=dev, dtype=dtype)
+            b = torch.randn(H, device=dev, dtype=dtype)
+            y, s, mean, rstd = ops.add_layernorm(x, r, g, b, 1e-5, save_stats=True, save_sum=True)
+            sref = s.float().clone().requires_grad_(True)  # grads at the (rounded) saved sum
+            gref = g.float().clone().requires_grad_(True)
+            bref = b.float().clone().requires_grad_(True)
+            yref = torch.nn.functional.layer_norm(sref, (H,), gref, bref, 1e-5)
+            ok &= report(f"ln sum {dtype} {rows}x{H}", s, x.float() + r.float(), tol)
+            ok &= report(f"ln fwd {dtype} {rows}x{H}", y, yref, tol)
+            dy = torch.randn(rows, H, device=dev, dtype=dtype)
+            yref.backward(dy.float())
+            dx, dg, db = ops.add_layernorm_bwd(dy, s, g, mean, rstd)
+            btol = tol if dtype == torch.bfloat16 else 2e-5
+            ok &= report("ln bwd dx", dx, sref.grad, btol)
+            ok &= report("ln bwd dgamma", dg, gref.grad, 2e-5)
+            ok &= report("ln bwd dbeta", db, bref.grad, 2e-5)
+        y2, _, _, _ = ops.add_layernorm(x, None, g, b, 1e-5)
+        ok &= report("ln no residual", y2, torch.nn.functional.layer_norm(x.float(), (H,), g.float(), b.float(), 1e-5), tol)
+    return ok
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--group", default=None)
+    ap.add_argument("--only", default=None, help="comma separated groups for the driver mode")
+    ap.add_argument("--timeout", type=int, default=240)
+    args = ap.parse_args()
+    if args.group:
+        import torch
+        t0 = time.time()
+        ok = GROUPS[args.group]()
+        torch.cuda.synchronize()
+        print(f"GROUP {args.group}: {'PASS' if ok else 'FAIL'} ({time.time() - t0:.1f}s)", flush=True)
+        sys.exit(0 if ok else 1)
+    names = args.only.split(",") if args.only else list(GROUPS)
+    results = {}
+    for n in names:
+        print(f"=== {n}", flush=True)
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--group", n], timeout=args.timeout)
+            results[n] = p.returncode
+        except subprocess.TimeoutExpired:
+            results[n] = "timeout"
+            print(f"GROUP {n}: TIMEOUT", flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(results, open("gpurun_out/selftest.json", "w"), indent=1)
+    print("SUMMARY", json.dumps(results))
+    sys.exit(0 if all(v == 0 for v in results.values()) else 1)
+
+
+if __name__ == "__main__":
+    main()

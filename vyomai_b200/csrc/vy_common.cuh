@@ -1,0 +1,122 @@
+// Shared host/device helpers for the vyom_b200 C-ABI library.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/vyom_b200.h"
+
+namespace vy {
+
+// ---- host: error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);  // thread-local, defined in api.cu
+
+#define VY_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::vy::set_error(__VA_ARGS__);        \
+      return VY_ERR_INVALID_ARG;           \
+    }                                      \
+  } while (0)
+
+#define VY_CUDA_OK(expr)                                                               \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::vy::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                      __LINE__);                                                       \
+      return VY_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+#define VY_LAUNCH_OK()                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      ::vy::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                      __LINE__);                                                        \
+      return VY_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+inline size_t dtype_size(int dt) { return dt == VY_BF16 ? 2 : 4; }
+inline bool dtype_ok(int dt) { return dt == VY_F32 || dt == VY_BF16; }
+
+int num_sms();  // cached, current device
+
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// TMA descriptor creation (tensormap.cu). dims/strides innermost first; strides in BYTES for
+// dims 1..rank-1 (dim 0 is contiguous). Returns 0 or VY_ERR_*.
+int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+
+// ---- device: dtype-generic element access ---------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float ld_as_float(const void* p, int dt, int64_t i) {
+  return dt == VY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                       : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_from_float(void* p, int dt, int64_t i, float v) {
+  if (dt == VY_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+// 8 consecutive elements starting at element index i (i % 8 == 0, base 16B aligned)
+__device__ __forceinline__ void ld8_as_float(const void* p, int dt, int64_t i, float (&v)[8]) {
+  if (dt == VY_BF16) {
+    uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(h[k]);
+      v[2 * k] = f.x;
+      v[2 * k + 1] = f.y;
+    }
+  } else {
+    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+    float4 a = q[0], b = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+__device__ __forceinline__ void st8_from_float(void* p, int dt, int64_t i, const float (&v)[8]) {
+  if (dt == VY_BF16) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = raw;
+  } else {
+    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i);
+    q[0] = make_float4(v[0], v[1], v[2], v[3]);
+    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k = 0.7978845608028654f;
+  return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float dgelu_tanh(float x) {
+  const float k = 0.7978845608028654f;
+  const float u = k * (x + 0.044715f * x * x * x);
+  const float t = tanhf(u);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * (1.0f + 3.0f * 0.044715f * x * x);
+}
+#endif
+
+}  // namespace vy

@@ -1,0 +1,239 @@
+"""Tensor-level wrappers over the C ABI (include/vyom_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every function below
+passes raw pointers / sizes / strides to libvyom_b200.so through ctypes. Nothing in this module
+computes with torch ops, and nothing falls back to them.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import CONSTS as C
+
+_DT = {torch.float32: C["VY_F32"], torch.bfloat16: C["VY_BF16"]}
+
+ACT = {
+    None: C["VY_ACT_NONE"],
+    "none": C["VY_ACT_NONE"],
+    "gelu": C["VY_ACT_GELU_ERF"],
+    "gelu_erf": C["VY_ACT_GELU_ERF"],
+    "gelu_tanh": C["VY_ACT_GELU_TANH"],
+    "dgelu": C["VY_ACT_DGELU_ERF"],
+    "dgelu_erf": C["VY_ACT_DGELU_ERF"],
+    "dgelu_tanh": C["VY_ACT_DGELU_TANH"],
+}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise _lib.VyomError(f"unsupported dtype {t.dtype}: the sm_100a path takes float32 or bfloat16") from None
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.VyomError(
+                "vyomai_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device; got a "
+                f"{t.device} tensor"
+            )
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _major(t: torch.Tensor, what: str):
+    """(is_mn_major, leading stride) of a logical (rows, k) operand, from its torch strides."""
+    assert t.dim() == 2, what
+    if t.stride(1) == 1:
+        return 0, t.stride(0)
+    if t.stride(0) == 1:
+        return 1, t.stride(1)
+    raise _lib.VyomError(f"{what}: operand must have one unit stride, got strides {t.stride()}")
+
+
+def gemm(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    *,
+    bias: Optional[torch.Tensor] = None,
+    act: Optional[str] = None,
+    aux: Optional[torch.Tensor] = None,
+    addend: Optional[torch.Tensor] = None,
+    addend_row_mod: int = 0,
+    addend_row_off: int = 0,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    out_scale: float = 1.0,
+    out_row_group: int = 0,
+    out_row_group_stride: int = 0,
+    out_row_off: int = 0,
+    swap_ab: bool = False,
+) -> torch.Tensor:
+    """out = epilogue(a @ b.T). `a` is logical (M, K), `b` logical (N, K); each may be stored with
+    either index contiguous (K-major or MN-major — read off the torch strides, no copies).
+
+    swap_ab=True computes the same logical result by feeding `b` as the 128-row MMA operand and
+    writing the tile transposed — the decode-time path where M (tokens) is tiny and N large.
+    """
+    _need_cuda(a, b, bias, aux, addend, out)
+    M, K = a.shape
+    N, Kb = b.shape
+    if K != Kb:
+        raise _lib.VyomError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if a.dtype != b.dtype:
+        raise _lib.VyomError("gemm: a and b must share a dtype")
+    if out is None:
+        odt = out_dtype or a.dtype
+        rows = M if out_row_group == 0 else None
+        if rows is None:
+            raise _lib.VyomError("gemm: pass `out` when using a row-group remap")
+        out = torch.empty((M, N), device=a.device, dtype=odt)
+    if out.stride(-1) != 1:
+        raise _lib.VyomError("gemm: out must be row-major")
+    a_mn, lda = _major(a, "gemm a")
+    b_mn, ldb = _major(b, "gemm b")
+    kw = dict(
+        in_dtype=_dt(a),
+        epi=C["VY_EPI_LINEAR"],
+        act=ACT[act],
+        bias=_ptr(bias),
+        bias_dtype=_dt(bias) if bias is not None else 0,
+        addend=_ptr(addend),
+        ld_addend=addend.stride(0) if addend is not None else 0,
+        addend_dtype=_dt(addend) if addend is not None else 0,
+        addend_row_mod=addend_row_mod,
+        addend_row_off=addend_row_off,
+        aux=_ptr(aux),
+        ld_aux=aux.stride(0) if aux is not None else 0,
+        aux_dtype=_dt(aux) if aux is not None else 0,
+        out_scale=float(out_scale),
+        out=out.data_ptr(),
+        ld_out=out.stride(0),
+        out_dtype=_dt(out),
+        out_row_group=out_row_group,
+        out_row_group_stride=out_row_group_stride,
+        out_row_off=out_row_off,
+        stream=_stream(),
+    )
+    if not swap_ab:
+        kw.update(M=M, N=N, K=K, A=a.data_ptr(), lda=lda, a_mn_major=a_mn, B=b.data_ptr(), ldb=ldb,
+                  b_mn_major=b_mn, transposed_out=0)
+    else:
+        kw.update(M=N, N=M, K=K, A=b.data_ptr(), lda=ldb, a_mn_major=b_mn, B=a.data_ptr(), ldb=lda,
+                  b_mn_major=a_mn, transposed_out=1)
+    _lib.call("vy_gemm", "VyGemm", **kw)
+    return out
+
+
+def qkv_rope_gemm(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    *,
+    tokens_per_seq: int,
+    start_pos: int,
+    n_q_heads: int,
+    n_kv_heads: int,
+    head_dim: int,
+    rope_cos: Optional[torch.Tensor],
+    rope_sin: Optional[torch.Tensor],
+    q_out: torch.Tensor,
+    k_out: torch.Tensor,
+    v_out: torch.Tensor,
+) -> None:
+    """Fused q/k/v projection: bias + in-register RoPE + "b l (h d) -> b h l d" scatter + kv-cache
+    append. q_out/k_out/v_out are 4-D [B, heads, tokens, head_dim] tensors (any batch/head/token
+    strides, head_dim contiguous); k/v rows land at token index start_pos + l.
+    """
+    _need_cuda(x, w, bias, rope_cos, rope_sin, q_out, k_out, v_out)
+    M, K = x.shape
+    N = w.shape[0]
+    a_mn, lda = _major(x, "qkv x")
+    b_mn, ldb = _major(w, "qkv w")
+    for t in (q_out, k_out, v_out):
+        if t.dim() != 4 or t.stride(3) != 1 or t.dtype != q_out.dtype:
+            raise _lib.VyomError("qkv_rope_gemm: outputs must be [B,h,S,d] with contiguous d and one dtype")
+    if rope_cos is not None and (rope_cos.dtype != torch.float32 or not rope_cos.is_contiguous()):
+        raise _lib.VyomError("qkv_rope_gemm: rope tables must be contiguous float32")
+    _lib.call(
+        "vy_gemm", "VyGemm",
+        M=M, N=N, K=K, in_dtype=_dt(x), A=x.data_ptr(), lda=lda, a_mn_major=a_mn,
+        B=w.data_ptr(), ldb=ldb, b_mn_major=b_mn,
+        epi=C["VY_EPI_QKV_ROPE"], bias=_ptr(bias), bias_dtype=_dt(bias) if bias is not None else 0,
+        out_dtype=_dt(q_out), tokens_per_seq=tokens_per_seq, start_pos=start_pos, head_dim=head_dim,
+        n_q_heads=n_q_heads, n_kv_heads=n_kv_heads, rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin),
+        q_out=q_out.data_ptr(), q_sb=q_out.stride(0), q_sh=q_out.stride(1), q_sl=q_out.stride(2),
+        k_out=k_out.data_ptr(), k_sb=k_out.stride(0), k_sh=k_out.stride(1), k_sl=k_out.stride(2),
+        v_out=v_out.data_ptr(), v_sb=v_out.stride(0), v_sh=v_out.stride(1), v_sl=v_out.stride(2),
+        stream=_stream(),
+    )
+
+
+def add_layernorm(
+    x: torch.Tensor,
+    residual: Optional[torch.Tensor],
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    eps: float,
+    *,
+    save_stats: bool = False,
+    save_sum: bool = False,
+):
+    """y = LayerNorm(x + residual). Returns (y, sum_or_None, mean_or_None, rstd_or_None)."""
+    _need_cuda(x, residual, gamma, beta)
+    H = x.shape[-1]
+    x2 = x.reshape(-1, H)
+    if not x2.is_contiguous():
+        raise _lib.VyomError("add_layernorm: x must be contiguous")
+    rows = x2.shape[0]
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, H)
+        if not r2.is_contiguous() or r2.dtype != x2.dtype:
+            raise _lib.VyomError("add_layernorm: residual must be contiguous and match x's dtype")
+    y = torch.empty_like(x2)
+    s = torch.empty_like(x2) if (save_sum and residual is not None) else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    _lib.call(
+        "vy_add_layernorm_fwd", "VyNorm",
+        rows=rows, H=H, x=x2.data_ptr(), residual=_ptr(r2), io_dtype=_dt(x2), gamma=gamma.data_ptr(),
+        beta=beta.data_ptr(), param_dtype=_dt(gamma), eps=float(eps), y=y.data_ptr(), sum_out=_ptr(s),
+        mean=_ptr(mean), rstd=_ptr(rstd), stream=_stream(),
+    )
+    if save_sum and residual is None:
+        s = x2
+    return y.view(x.shape), s, mean, rstd
+
+
+def add_layernorm_bwd(dy, s, gamma, mean, rstd):
+    """Returns (dx, dgamma_fp32, dbeta_fp32) for y = LayerNorm(s)."""
+    _need_cuda(dy, s, gamma, mean, rstd)
+    H = dy.shape[-1]
+    dy2 = dy.reshape(-1, H)
+    s2 = s.reshape(-1, H)
+    if not dy2.is_contiguous() or not s2.is_contiguous():
+        raise _lib.VyomError("add_layernorm_bwd: dy and s must be contiguous")
+    rows = dy2.shape[0]
+    dx = torch.empty_like(dy2)
+    dgamma = torch.empty(H, device=dy.device, dtype=torch.float32)
+    dbeta = torch.empty(H, device=dy.device, dtype=torch.float32)
+    nparts = _lib.lib().vy_norm_bwd_partial_rows()
+    partials = torch.empty(2 * nparts * H, device=dy.device, dtype=torch.float32)
+    _lib.call(
+        "vy_add_layernorm_bwd", "VyNorm",
+        rows=rows, H=H, io_dtype=_dt(dy2), gamma=gamma.data_ptr(), param_dtype=_dt(gamma),
+        mean=mean.data_ptr(), rstd=rstd.data_ptr(), dy=dy2.data_ptr(), s=s2.data_ptr(), dx=dx.data_ptr(),
+        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), partials=partials.data_ptr(), stream=_stream(),
+    )
+    return dx.view(dy.shape), dgamma, dbeta
