@@ -1,0 +1,482 @@
+"""CPU ORACLE — test infrastructure, not product code.
+
+A plain restatement, in explicit fp32 (or fp64) tensor arithmetic on the CPU, of the algorithm
+the reference (Ajax0564/VyomAI) runs on its transformer-block hot path. Every function cites the
+reference file:line it follows (paths relative to the reference checkout). Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference` legs may import
+this module, and only as the checker or the timed CPU baseline — never from `vyomai_b200/`.
+
+Parity pinning: the reference's own tests pin shapes only, so this oracle is
+pinned against outputs of the REAL reference run in the build container:
+`tests/golden/make_golden.py` imports /root/reference/VyomAI, runs it on seeded inputs and
+commits inputs + weights + outputs as fixtures; `tests/test_oracle_golden.py` checks every
+function here against them. PARITY: PINNED (against reference-generated fixtures).
+
+The oracle never calls F.scaled_dot_product_attention, nn.LayerNorm, nn.GELU or nn.Conv2d: it
+spells those out (softmax(QK^T/sqrt(d)+M)V, biased-variance normalisation, exact-erf GELU,
+unfold-as-matmul) so that it is an independent statement of the math, not a re-run of the
+same library kernels.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# ----------------------------------------------------------------------------------------------
+# primitives
+# ----------------------------------------------------------------------------------------------
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    """nn.Linear: y = x W^T + b, W:(out,in). (layers/attention.py:87-95, ffn.py:21,30)"""
+    y = x @ w.transpose(-1, -2)
+    return y if b is None else y + b
+
+
+def gelu_erf(x: Tensor) -> Tensor:
+    """nn.GELU() default = exact erf form (layers/ffn.py:8,29; models/decoder.py:269)."""
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def gelu_tanh(x: Tensor) -> Tensor:
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x**3)))
+
+
+_ACT = {
+    # layers/ffn.py:7-15 `_ACT_`
+    "gelu": gelu_erf,
+    "leaky_relu": lambda x: torch.where(x >= 0, x, 0.01 * x),
+    "relu6": lambda x: x.clamp(0.0, 6.0),
+    "sigmoid": torch.sigmoid,
+    "silu": lambda x: x * torch.sigmoid(x),
+    "swish": lambda x: x * torch.sigmoid(x),
+    "tanh": torch.tanh,
+}
+
+
+def act_fn(name: Optional[str]):
+    """FeedForward picks `_ACT_[config.hidden_act]`, else exact GELU (layers/ffn.py:26-29)."""
+    return _ACT.get(name, gelu_erf)
+
+
+def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
+    """nn.LayerNorm over the last dim, biased variance (layers/attention.py:52-54, ffn.py:25)."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * gamma + beta
+
+
+def rope_freqs(max_pos: int, head_dim: int, dtype=torch.float32) -> Tensor:
+    """RotaryEmbedding: angles theta[p,i] = p * 10000^(-2i/d), shape (1, max_pos, d/2)
+    (layers/positional_embeddings.py:127-137)."""
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, head_dim, 2).float() / head_dim))
+    t = torch.arange(max_pos).type_as(inv_freq)
+    return torch.einsum("i,j->ij", t, inv_freq)[None].to(dtype)
+
+
+def rotate_half(x: Tensor) -> Tensor:
+    """(layers/positional_embeddings.py:140-152): (-x2, x1) with x = (x1 | x2) split in halves."""
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rope(q: Tensor, k: Tensor, freqs: Tensor) -> Tuple[Tensor, Tensor]:
+    """apply_rotary_pos_emb (layers/positional_embeddings.py:155-182): cos/sin of cat(freqs,freqs)
+    are cast to q.dtype BEFORE the multiply (quirk Q6), broadcast over heads."""
+    emb = torch.cat((freqs, freqs), dim=-1)
+    cos = emb.cos().to(q.dtype)[:, None]
+    sin = emb.sin().to(q.dtype)[:, None]
+    return q * cos + rotate_half(q) * sin, k * cos + rotate_half(k) * sin
+
+
+def split_heads(x: Tensor, head_dim: int) -> Tensor:
+    """einops "b l (h d) -> b h l d" (layers/attention.py:118-120,194-196)."""
+    b, l, hd = x.shape
+    return x.view(b, l, hd // head_dim, head_dim).permute(0, 2, 1, 3)
+
+
+def merge_heads(x: Tensor) -> Tensor:
+    """einops "b h l d -> b l (h d)" (layers/attention.py:132,213)."""
+    b, h, l, d = x.shape
+    return x.permute(0, 2, 1, 3).reshape(b, l, h * d)
+
+
+def repeat_kv(x: Tensor, n_rep: int) -> Tensor:
+    """GQA head broadcast: q-head i reads kv-head i // n_rep (layers/attention.py:8-19)."""
+    if n_rep == 1:
+        return x
+    b, hkv, s, d = x.shape
+    return x[:, :, None].expand(b, hkv, n_rep, s, d).reshape(b, hkv * n_rep, s, d)
+
+
+def sdpa(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
+    """F.scaled_dot_product_attention(q,k,v,attn_mask=mask) spelled out
+    (layers/attention.py:128-130,209-211,283-285,373-375,464-466,567-569,619-621):
+    softmax over keys of q k^T / sqrt(d) + additive float mask, times v. The mask holds
+    finfo(dtype).min, not -inf, so a fully masked row is the uniform mean of v (quirk Q4)."""
+    d = q.shape[-1]
+    scores = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+    if mask is not None:
+        scores = scores + mask
+    return torch.softmax(scores.float(), dim=-1).to(q.dtype) @ v
+
+
+# ----------------------------------------------------------------------------------------------
+# masks
+# ----------------------------------------------------------------------------------------------
+def encoder_mask(attention_mask: Tensor, dtype) -> Tensor:
+    """(models/encoder.py:161-164, vision_encoder.py:138-141): (1-m)[:,None,None,:]*finfo.min."""
+    m = attention_mask[:, None, None, :].to(dtype)
+    return (1.0 - m) * torch.finfo(dtype).min
+
+
+def decoder_mask(bsz: int, seqlen: int, attention_mask: Optional[Tensor], start_pos: int, dtype) -> Tensor:
+    """create_mask_for_decoder + inversion (models/decoder.py:355-362,376-419;
+    models/multimodel.py:181-190,203-246): key k visible to query l iff k <= start_pos + l and
+    attention_mask[b,k] == 1; attention_mask defaults to ones(start_pos + seqlen)."""
+    if attention_mask is None:
+        attention_mask = torch.ones(bsz, seqlen + start_pos)
+    ids = torch.arange(seqlen)
+    causal = (ids[None, None, :].repeat(bsz, seqlen, 1) <= ids[None, :, None]).to(attention_mask.dtype)
+    if start_pos > 0:
+        causal = torch.cat([torch.ones(bsz, seqlen, start_pos, dtype=causal.dtype), causal], dim=-1)
+    ext = causal[:, None, :, :] * attention_mask[:, None, None, :]
+    return (1.0 - ext).to(dtype) * torch.finfo(dtype).min
+
+
+# ----------------------------------------------------------------------------------------------
+# kv caches (semantics of layers/kv_cache.py)
+# ----------------------------------------------------------------------------------------------
+class StaticCacheOneOracle:
+    """StaticCacheOne (layers/kv_cache.py:255-361): zeros (B, h_kv, max_len, d) per layer; update
+    writes [start_pos, start_pos+S) and returns the views [:B, :, :start_pos+S]."""
+
+    def __init__(self, layers: int, batch: int, heads: int, max_len: int, head_dim: int, dtype=torch.float32):
+        self.key_cache = [torch.zeros(batch, heads, max_len, head_dim, dtype=dtype) for _ in range(layers)]
+        self.value_cache = [torch.zeros(batch, heads, max_len, head_dim, dtype=dtype) for _ in range(layers)]
+
+    def update(self, index: int, k: Tensor, v: Tensor, start_pos: int = 0):
+        bsz, _, seqlen, _ = k.shape
+        if seqlen > self.key_cache[index].shape[2]:
+            raise ValueError("update longer than the cache")  # kv_cache.py:349-353
+        self.key_cache[index][:bsz, :, start_pos:start_pos + seqlen] = k
+        self.value_cache[index][:bsz, :, start_pos:start_pos + seqlen] = v
+        return (self.key_cache[index][:bsz, :, :start_pos + seqlen],
+                self.value_cache[index][:bsz, :, :start_pos + seqlen])
+
+
+class DynamicCacheOneOracle:
+    """DynamicCacheOne (layers/kv_cache.py:171-236): clone on first update, torch.cat after."""
+
+    def __init__(self, layers: int):
+        self.key_cache: List = [[] for _ in range(layers)]
+        self.value_cache: List = [[] for _ in range(layers)]
+
+    def update(self, index: int, k: Tensor, v: Tensor, start_pos: int = 0):
+        if len(self.key_cache[index]) == 0:
+            self.key_cache[index], self.value_cache[index] = k.clone(), v.clone()
+        else:
+            self.key_cache[index] = torch.cat([self.key_cache[index], k], dim=-2)
+            self.value_cache[index] = torch.cat([self.value_cache[index], v], dim=-2)
+        return self.key_cache[index], self.value_cache[index]
+
+
+# ----------------------------------------------------------------------------------------------
+# blocks
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Cfg:
+    hidden_size: int = 768
+    num_attention_heads: int = 12
+    num_key_value_heads: Optional[int] = None  # None -> attribute absent on the reference config
+    max_position_embeddings: int = 514
+    num_hidden_layers: int = 4
+    vocab_size: int = 50265
+    layer_norm_eps: float = 1e-5
+    hidden_act: str = "gelu"
+    # vision
+    image_size: Tuple[int, int] = (224, 224)
+    patch_size: Tuple[int, int] = (16, 16)
+    num_channels: int = 3
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
+
+    def kv_heads(self, attention_type: Optional[str]) -> int:
+        """GQA modules read getattr(config, 'num_key_value_heads', 4) (attention.py:150,306; Q7);
+        vanilla modules use num_attention_heads."""
+        if attention_type == "gqa":
+            return self.num_key_value_heads if self.num_key_value_heads is not None else 4
+        return self.num_attention_heads
+
+
+def attention_self_output(sd: SD, pre: str, attn: Tensor, residual: Tensor, eps: float) -> Tensor:
+    """AttentionSelfOutput.forward, dropout in eval (layers/attention.py:57-72):
+    LN(dense(attn) + residual)."""
+    y = linear(attn, sd[pre + "dense.weight"], sd.get(pre + "dense.bias"))
+    return layer_norm(y + residual, sd[pre + "layernorm.weight"], sd[pre + "layernorm.bias"], eps)
+
+
+def feed_forward(sd: SD, pre: str, hidden: Tensor, input_tensor: Tensor, cfg: Cfg) -> Tensor:
+    """FeedForward.forward (layers/ffn.py:32-40): LN(out(act(intermediate(h))) + input_tensor).
+    The residual is the LAYER INPUT, not the attention output (quirk Q2)."""
+    y = linear(hidden, sd[pre + "intermediate.weight"], sd[pre + "intermediate.bias"])
+    y = act_fn(cfg.hidden_act)(y)
+    y = linear(y, sd[pre + "out.weight"], sd[pre + "out.bias"])
+    return layer_norm(y + input_tensor, sd[pre + "layernorm.weight"], sd[pre + "layernorm.bias"], cfg.layer_norm_eps)
+
+
+def self_attention(
+    sd: SD,
+    pre: str,
+    x: Tensor,
+    mask: Optional[Tensor],
+    freqs: Optional[Tensor],
+    cfg: Cfg,
+    attention_type: Optional[str],
+    fused_qkv: bool = False,
+    cache=None,
+    layer_idx: int = 0,
+    start_pos: int = 0,
+) -> Tensor:
+    """Encoder/Decoder/Vision attention forward (layers/attention.py:99-133,175-215,245-289,
+    331-379,591-624; models/decoder.py:71-113,155-201): q/k/v Linear -> head split -> RoPE ->
+    cache.update -> repeat_kv -> SDPA(mask) -> merge -> AttentionSelfOutput."""
+    d = cfg.head_dim
+    if fused_qkv:  # VisionAttention: one Linear H -> 3H then chunk(3) (attention.py:587,607)
+        qkv = linear(x, sd[pre + "qkv.weight"], sd[pre + "qkv.bias"])
+        q, k, v = qkv.chunk(3, dim=-1)
+    else:
+        q = linear(x, sd[pre + "query.weight"], sd.get(pre + "query.bias"))
+        k = linear(x, sd[pre + "key.weight"], sd.get(pre + "key.bias"))
+        v = linear(x, sd[pre + "value.weight"], sd.get(pre + "value.bias"))
+    q, k, v = split_heads(q, d), split_heads(k, d), split_heads(v, d)
+    if freqs is not None:
+        q, k = apply_rope(q, k, freqs)
+    if cache is not None:
+        k, v = cache.update(layer_idx, k, v, start_pos)
+    n_rep = q.shape[1] // k.shape[1]
+    k, v = repeat_kv(k, n_rep), repeat_kv(v, n_rep)
+    out = merge_heads(sdpa(q, k, v, mask))
+    return attention_self_output(sd, pre + "out.", out, x, cfg.layer_norm_eps)
+
+
+def transformer_layer(sd, pre, x, mask, freqs, cfg, attention_type, fused_qkv=False, cache=None,
+                      layer_idx=0, start_pos=0) -> Tensor:
+    """EncoderLayer / DecoderLayer forward (models/encoder.py:45-64, decoder.py:222-250,
+    vision_encoder.py:34-53, multimodel.py:43-69): out = attention(h); out = feed_forward(out, h)."""
+    a = self_attention(sd, pre + "attention.", x, mask, freqs, cfg, attention_type, fused_qkv, cache,
+                       layer_idx, start_pos)
+    return feed_forward(sd, pre + "feed_forward.", a, x, cfg)
+
+
+def lm_head(sd: SD, pre: str, h: Tensor, eps: float) -> Tensor:
+    """LMHead.forward (models/decoder.py:267-275, encoder.py:81-90): decoder(LN(gelu(dense(h))))."""
+    x = gelu_erf(linear(h, sd[pre + "dense.weight"], sd[pre + "dense.bias"]))
+    x = layer_norm(x, sd[pre + "layer_norm.weight"], sd[pre + "layer_norm.bias"], eps)
+    # lm_head.bias and lm_head.decoder.bias are one Parameter under two state_dict keys (:263-265)
+    bias = sd[pre + "bias"] if (pre + "bias") in sd else sd[pre + "decoder.bias"]
+    return linear(x, sd[pre + "decoder.weight"], bias)
+
+
+def sinusoidal_table(max_pos: int, hidden: int) -> Tensor:
+    """SinusoidalEncoding table (layers/positional_embeddings.py:86-102): sin on even, cos on odd."""
+    pe = torch.zeros(1, max_pos, hidden)
+    pos = torch.arange(0, max_pos).unsqueeze(1).float()
+    div = torch.exp(torch.arange(0, hidden, 2, dtype=torch.float) * -(math.log(10000.0) / hidden))
+    pe[:, :, 0::2] = torch.sin(pos * div)
+    pe[:, :, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def _positions(sd: SD, pre: str, cfg: Cfg, pos_type: str, start: int, n: int, dtype) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """returns (additive position embedding or None, rope freqs or None) for positions
+    [start, start+n) (models/encoder.py:148-154, decoder.py:345-354)."""
+    if pos_type == "absolute":
+        return sd[pre + "position_embeddings.pos_embeddings.weight"][None, start:start + n], None
+    if pos_type == "sinusoidal":
+        return sinusoidal_table(cfg.max_position_embeddings, cfg.hidden_size)[:, start:start + n].to(dtype), None
+    return None, rope_freqs(cfg.max_position_embeddings, cfg.head_dim)[:, start:start + n]
+
+
+# ----------------------------------------------------------------------------------------------
+# models
+# ----------------------------------------------------------------------------------------------
+def encoder_forward(sd: SD, cfg: Cfg, input_ids: Tensor, attention_mask: Optional[Tensor],
+                    pos_type: str = "absolute", attention_type: Optional[str] = None, pre: str = "") -> Tensor:
+    """EncoderModel.forward (models/encoder.py:134-168)."""
+    h = sd[pre + "word_embeddings.weight"][input_ids]
+    bsz, seqlen = input_ids.shape
+    add, freqs = _positions(sd, pre, cfg, pos_type, 0, seqlen, h.dtype)
+    if add is not None:
+        h = h + add
+    if attention_mask is None:
+        attention_mask = torch.ones(bsz, seqlen)
+    mask = encoder_mask(attention_mask, h.dtype)
+    for i in range(cfg.num_hidden_layers):
+        h = transformer_layer(sd, f"{pre}all_layer.{i}.", h, mask, freqs, cfg, attention_type)
+    return h
+
+
+def encoder_mlm_forward(sd, cfg, input_ids, attention_mask, pos_type="absolute", attention_type=None):
+    """EncoderForMaskedLM.forward (models/encoder.py:192-206)."""
+    h = encoder_forward(sd, cfg, input_ids, attention_mask, pos_type, attention_type, pre="encoder.")
+    return h, lm_head(sd, "lm_head.", h, cfg.layer_norm_eps)
+
+
+def decoder_forward(sd: SD, cfg: Cfg, input_ids: Tensor, attention_mask: Optional[Tensor] = None,
+                    pos_type: str = "absolute", attention_type: Optional[str] = None, cache=None,
+                    start_pos: int = 0) -> Tuple[Tensor, Tensor]:
+    """DecoderModel.forward (models/decoder.py:324-374). Returns (hidden_state, logits). A mask is
+    only built when seqlen > 1: single-token decode attends to every cached slot (quirk Q3)."""
+    h = sd["word_embeddings.weight"][input_ids]
+    bsz, seqlen = input_ids.shape
+    add, freqs = _positions(sd, "", cfg, pos_type, start_pos, seqlen, h.dtype)
+    if add is not None:
+        h = h + add
+    mask = decoder_mask(bsz, seqlen, attention_mask, start_pos, h.dtype) if seqlen > 1 else None
+    for i in range(cfg.num_hidden_layers):
+        h = transformer_layer(sd, f"all_layer.{i}.", h, mask, freqs, cfg, attention_type, cache=cache,
+                              layer_idx=i, start_pos=start_pos)
+    return h, lm_head(sd, "lm_head.", h, cfg.layer_norm_eps)
+
+
+def decoder_generate(sd: SD, cfg: Cfg, input_ids: Tensor, attention_mask: Tensor, max_len: int = 5,
+                     pos_type="absolute", attention_type=None, cache_kind: Optional[str] = "static",
+                     pad_id: int = 1, eos_id: int = 2) -> Tensor:
+    """DecoderModel.generate, greedy (models/decoder.py:430-514): argmax (= topk(1), first index on
+    ties) of the last-position logits; prompt tokens are kept while cur_pos is inside a prompt."""
+    bsz, prompt = input_ids.shape
+    total = max_len + prompt
+    tokens = torch.full((bsz, total), pad_id, dtype=torch.long)
+    tokens[:, :prompt] = input_ids
+    cache = None
+    if cache_kind == "static":
+        cache = StaticCacheOneOracle(cfg.num_hidden_layers, bsz, cfg.kv_heads(attention_type), total, cfg.head_dim)
+    elif cache_kind == "dynamic":
+        cache = DynamicCacheOneOracle(cfg.num_hidden_layers)
+    prev = 0
+    eos = torch.zeros(bsz, dtype=torch.bool)
+    text_mask = tokens != pad_id
+    for cur in range(prompt, total):
+        _, logits = decoder_forward(sd, cfg, tokens[:, prev:cur], attention_mask, pos_type, attention_type,
+                                    cache, prev)
+        nxt = torch.topk(logits[:, -1], k=1, dim=-1)[1].reshape(-1)
+        nxt = torch.where(text_mask[:, cur], tokens[:, cur], nxt)
+        tokens[:, cur] = nxt
+        eos |= (~text_mask[:, cur]) & (nxt == eos_id)
+        if cache is not None:
+            prev = cur
+        attention_mask = torch.cat([attention_mask, torch.ones(bsz, 1, dtype=attention_mask.dtype)], dim=-1)
+        if bool(eos.all()):
+            break
+    return tokens
+
+
+def patch_embed(sd: SD, pixels: Tensor, cfg: Cfg, pre: str = "") -> Tensor:
+    """nn.Conv2d(C,H,kernel=p,stride=p) + "b d c1 c2 -> b (c1 c2) d" as an explicit unfold+matmul
+    (models/vision_encoder.py:83-88,114-115): tok[b, r*Wp+s, o] = sum_{c,i,j} W[o,c,i,j] *
+    img[b,c,p*r+i,p*s+j] + bias[o]."""
+    b, c, hh, ww = pixels.shape
+    ph, pw = cfg.patch_size
+    x = pixels.view(b, c, hh // ph, ph, ww // pw, pw).permute(0, 2, 4, 1, 3, 5).reshape(b, (hh // ph) * (ww // pw), c * ph * pw)
+    w = sd[pre + "pixel_seq.weight"].reshape(cfg.hidden_size, -1)
+    return x @ w.t() + sd[pre + "pixel_seq.bias"]
+
+
+def vit_forward(sd: SD, cfg: Cfg, pixels: Tensor, pre: str = "") -> Tensor:
+    """Vit.forward (models/vision_encoder.py:102-145). The position add is applied twice because
+    VitAbsoluteEncoding adds in place and returns its input (positional_embeddings.py:222-226 +
+    vision_encoder.py:125-127): h0 = 2 * (cat(cls, patches) + pos) (quirk Q1). Mask is all ones."""
+    tok = patch_embed(sd, pixels, cfg, pre)
+    bsz, n, _ = tok.shape
+    cls = sd[pre + "cls_token"].expand(bsz, 1, -1)
+    h = torch.cat([cls, tok], dim=1)
+    pos = sd[pre + "position_embeddings.pos_embeddings"][:, : n + 2]
+    h = 2.0 * (h + pos)
+    mask = encoder_mask(torch.ones(bsz, n + 1), h.dtype)
+    for i in range(cfg.num_hidden_layers):
+        h = transformer_layer(sd, f"{pre}all_layer.{i}.", h, mask, None, cfg, None, fused_qkv=True)
+    return h
+
+
+class PerLayerCacheAdapter:
+    """The VLM attaches one DynamicCache/StaticCache per layer (multimodel.py:306-309); both reduce
+    to "append at start_pos, attend to [0, start_pos+S)" for batch 1, which is what the whole-model
+    oracles above do per layer index."""
+
+    def __init__(self, inner):
+        self.inner = inner
+
+    def update(self, index, k, v, start_pos=0):
+        return self.inner.update(index, k, v, start_pos)
+
+
+def vlm_decoder_forward(sd: SD, cfg: Cfg, input_ids: Tensor, attention_mask: Optional[Tensor],
+                        encoder_hidden_state: Tensor, pos_type="absolute", attention_type=None,
+                        cache=None, start_pos: int = 0, pre: str = "decoder.") -> Tensor:
+    """VisionLanguageDecoderModel.forward (models/multimodel.py:142-201): the image vector is
+    prepended as token 0 only when start_pos == 0 (and the padding mask gets a leading 1)."""
+    h = sd[pre + "word_embeddings.weight"][input_ids]
+    bsz = input_ids.shape[0]
+    if start_pos == 0:
+        h = torch.cat([encoder_hidden_state[:, None, :], h], dim=1)
+        if attention_mask is not None:
+            attention_mask = torch.cat([torch.ones(bsz, 1, dtype=attention_mask.dtype), attention_mask], dim=1)
+    seqlen = h.shape[1]
+    add, freqs = _positions(sd, pre, cfg, pos_type, start_pos, seqlen, h.dtype)
+    if add is not None:
+        h = h + add
+    mask = decoder_mask(bsz, seqlen, attention_mask, start_pos, h.dtype) if seqlen > 1 else None
+    for i in range(cfg.num_hidden_layers):
+        h = transformer_layer(sd, f"{pre}all_layer.{i}.", h, mask, freqs, cfg, attention_type, cache=cache,
+                              layer_idx=i, start_pos=start_pos)
+    return lm_head(sd, pre + "lm_head.", h, cfg.layer_norm_eps)
+
+
+def vlm_forward(sd: SD, cfg: Cfg, vit_cfg: Cfg, pixels: Optional[Tensor], decoder_input_ids: Tensor,
+                decoder_attention_mask: Optional[Tensor], pos_type="absolute", attention_type=None,
+                encoder_output: Optional[Tensor] = None, cache=None, start_pos: int = 0) -> Tensor:
+    """VisionLanguageModel.forward (models/multimodel.py:276-298): encoder_output = ViT CLS row."""
+    if encoder_output is None:
+        encoder_output = vit_forward(sd, vit_cfg, pixels, pre="encoder.")[:, 0, :]
+    return vlm_decoder_forward(sd, cfg, decoder_input_ids, decoder_attention_mask, encoder_output, pos_type,
+                               attention_type, cache, start_pos)
+
+
+def vlm_generate(sd, cfg, encoder_output: Tensor, decoder_start: Tensor, max_new_tokens: int,
+                 pos_type="absolute", attention_type=None, use_cache: bool = False) -> Tensor:
+    """generate_multimodel, greedy (generation_utils.py:128-197): with the cache the next start_pos
+    is idx.size(1) because the image token occupies slot 0 (:195)."""
+    idx = decoder_start
+    idx_next = idx
+    index = 0
+    cache = DynamicCacheOneOracle(cfg.num_hidden_layers) if use_cache else None
+    for _ in range(max_new_tokens):
+        if use_cache:
+            logits = vlm_decoder_forward(sd, cfg, idx_next, None, encoder_output, pos_type, attention_type, cache, index)
+        else:
+            logits = vlm_decoder_forward(sd, cfg, idx, None, encoder_output, pos_type, attention_type, None, 0)
+        probs = torch.softmax(logits[:, -1], dim=-1)
+        idx_next = torch.topk(probs, k=1, dim=-1)[1]
+        idx = torch.cat((idx, idx_next), dim=1)
+        index = idx.shape[1]
+    return idx
+
+
+def cross_entropy_shifted(logits: Tensor, labels: Tensor, ignore_index: int = -100) -> Tensor:
+    """Training loss of the captioner notebook (Examples/vyom-ai-accelerate-multimodel-2t4.ipynb
+    cell 1 `loss_fn`): mean token cross-entropy of logits[:, :-1] against labels[:, 1:], pad
+    positions ignored."""
+    lg = logits[:, :-1].reshape(-1, logits.shape[-1]).float()
+    lb = labels[:, 1:].reshape(-1)
+    keep = lb != ignore_index
+    lse = torch.logsumexp(lg, dim=-1)
+    picked = lg.gather(1, lb.clamp(min=0)[:, None])[:, 0]
+    return ((lse - picked) * keep).sum() / keep.sum().clamp(min=1)

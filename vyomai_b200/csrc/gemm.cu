@@ -62,6 +62,11 @@ struct GemmCfg {
   static constexpr int MN_BOX_BYTES = BK * 128;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 2 * BN * 4 /*bias*/ + 256;
   static constexpr int FMT = sizeof(TIn) == 2 ? 1 : 2;  // bf16 : tf32
+  // MN-major operands: bf16 uses the plain 128B swizzle (8 k-rows per 1024-B group); tf32 must use
+  // SWIZZLE_128B_BASE32B (4 k-rows per 512-B group) and the matching TMA mode.
+  static constexpr int MN_SBO = sizeof(TIn) == 2 ? 1024 : 512;
+  static constexpr int MN_LAYOUT = sizeof(TIn) == 2 ? 2 : 1;
+  static constexpr int MN_TMA_SWIZZLE = sizeof(TIn) == 2 ? 1 : 2;
 };
 
 __device__ __forceinline__ float apply_act(int act, float x) {
@@ -380,9 +385,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
-            const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, 1024)
+            const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
                                      : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, 1024)
+            const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             if constexpr (sizeof(TIn) == 2) umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
             else umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
@@ -439,17 +444,17 @@ struct TmapKey {
   const void* base;
   uint64_t d0, d1, s1;
   uint32_t b0, b1;
-  int dtype;
+  int dtype, swz;
   bool operator==(const TmapKey& o) const {
     return base == o.base && d0 == o.d0 && d1 == o.d1 && s1 == o.s1 && b0 == o.b0 && b1 == o.b1 &&
-           dtype == o.dtype;
+           dtype == o.dtype && swz == o.swz;
   }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.base);
     auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.d0); mix(k.d1); mix(k.s1); mix(k.b0); mix(k.b1); mix(static_cast<uint64_t>(k.dtype));
+    mix(k.d0); mix(k.d1); mix(k.s1); mix(k.b0); mix(k.b1); mix(static_cast<uint64_t>(k.dtype * 4 + k.swz));
     return h;
   }
 };
@@ -457,10 +462,10 @@ struct TmapKeyHash {
 // 2-D tensor map cache. A descriptor depends only on its key, so reuse across calls is safe even
 // when the caching allocator hands the same address to a different tensor.
 static int get_tmap_2d(CUtensorMap* out, int dtype, const void* base, uint64_t d0, uint64_t d1,
-                       uint64_t stride1_bytes, uint32_t b0, uint32_t b1) {
+                       uint64_t stride1_bytes, uint32_t b0, uint32_t b1, int swz = 1) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{base, d0, d1, stride1_bytes, b0, b1, dtype};
+  TmapKey key{base, d0, d1, stride1_bytes, b0, b1, dtype, swz};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -472,7 +477,7 @@ static int get_tmap_2d(CUtensorMap* out, int dtype, const void* base, uint64_t d
   uint64_t dims[2] = {d0, d1};
   uint64_t strides[2] = {0, stride1_bytes};
   uint32_t box[2] = {b0, b1};
-  int rc = make_tensor_map(out, dtype, 2, base, dims, strides, box, 1);
+  int rc = make_tensor_map(out, dtype, 2, base, dims, strides, box, swz);
   if (rc != VY_OK) return rc;
   std::lock_guard<std::mutex> lk(mu);
   if (cache.size() > 8192) cache.clear();
@@ -490,12 +495,12 @@ static int launch_gemm(const VyGemm* p, const GemmDev& g) {
   if (!A_MN)
     rc = get_tmap_2d(&ta, dt, p->A, p->K, p->M, p->lda * es, Cfg::BK, Cfg::BM);
   else
-    rc = get_tmap_2d(&ta, dt, p->A, p->M, p->K, p->lda * es, Cfg::EPB, Cfg::BK);
+    rc = get_tmap_2d(&ta, dt, p->A, p->M, p->K, p->lda * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
   if (!B_MN)
     rc = get_tmap_2d(&tb, dt, p->B, p->K, p->N, p->ldb * es, Cfg::BK, BN);
   else
-    rc = get_tmap_2d(&tb, dt, p->B, p->N, p->K, p->ldb * es, Cfg::EPB, Cfg::BK);
+    rc = get_tmap_2d(&tb, dt, p->B, p->N, p->K, p->ldb * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
 
   auto kern = gemm_kernel<TIn, BN, A_MN, B_MN>;

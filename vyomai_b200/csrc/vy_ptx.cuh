@@ -149,13 +149,16 @@ VY_DEVINL void tc_fence_after() {
 // K-major tile (rows of 128 B, 8-row groups 1024 B apart): LBO unused (1), SBO = 1024.
 // MN-major tile (k-rows of 128 B holding 64 contiguous MN elements): LBO = bytes between
 // consecutive 128-B MN blocks, SBO = 1024 (8 k-rows).
-VY_DEVINL uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type 1 = SWIZZLE_128B_BASE32B: the only layout MN-major tf32 operands may use (32-B
+// swizzle atoms, 4 k-rows per 512-B group; pairs with TMA SWIZZLE_128B_ATOM_32B).
+VY_DEVINL uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                        uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 
