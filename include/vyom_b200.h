@@ -182,6 +182,85 @@ VY_API int vy_add_layernorm_fwd(const VyNorm* p);
 VY_API int vy_add_layernorm_bwd(const VyNorm* p);
 VY_API int vy_norm_bwd_partial_rows(void);
 
+/* ------------------------------------------------------------------------------------------
+ * vy_attn_fwd — flash-style fused attention forward (tcgen05 + TMEM + TMA), Sq >= 1.
+ * replaces repeat_kv + F.scaled_dot_product_attention(q, k, v, attn_mask) + "b h l d -> b l (h d)"
+ * at VyomAI/layers/attention.py:128-132 (EncoderAttention), :205-213 (EncoderAttentionGqa),
+ * :283-287, :368-377 (DecoderAttention[Gqa]), :464-468, :563-571 (cross attention), :619-623
+ * (VisionAttention) and VyomAI/models/decoder.py:107-111,190-199.
+ *   out[b, l, h*64 + :] = softmax_k( q[b,h,l,:] . k[b,h/n_rep,k,:] / 8 + M[b,l,k] ) v[b,h/n_rep,k,:]
+ * q/k/v are bf16 [B, heads, S, 64] through element strides (sb, sh, sl; head_dim contiguous) — so
+ * k/v may point straight into a kv-cache. The additive float mask of the reference is passed in
+ * factored form: key_padding_mask[b,k] (uint8, 1 = visible; the `attention_mask` of
+ * models/encoder.py:161-164) and `causal` with q_pos0 = start_pos (key k visible to query l iff
+ * k <= q_pos0 + l; models/decoder.py:376-419). Masked scores behave like "+ finfo.min": a row with
+ * no visible key returns the mean of v over ALL Skv keys.
+ * lse (optional, fp32 [B, n_q_heads, Sq]) receives log2-domain logsumexp for vy_attn_bwd.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VyAttn {
+  int32_t B, n_q_heads, n_kv_heads, head_dim;
+  int32_t Sq, Skv;
+  int32_t qkv_dtype; /* VY_BF16 */
+  const void* q;
+  int64_t q_sb, q_sh, q_sl;
+  const void* k;
+  int64_t k_sb, k_sh, k_sl;
+  const void* v;
+  int64_t v_sb, v_sh, v_sl;
+  int32_t causal, q_pos0;
+  const uint8_t* key_padding_mask; /* [B, Skv] or NULL */
+  int64_t kpm_stride;
+  void* out; /* [B, Sq, n_q_heads*64] through o_sb, o_sl */
+  int64_t o_sb, o_sl;
+  int32_t out_dtype;
+  float* lse;
+  void* stream;
+} VyAttn;
+
+VY_API int vy_attn_fwd(const VyAttn* p);
+
+/* ------------------------------------------------------------------------------------------
+ * vy_attn_decode — single-token attention over the contiguous kv-cache, fused with the new
+ * token's RoPE and cache append. Replaces, for seqlen == 1, the chain
+ *   apply_rotary_pos_emb (layers/positional_embeddings.py:155-182)
+ *   -> kv_cache.update(layer, k, v, start_pos)  (layers/kv_cache.py:323-361, 198-236; per-layer
+ *      variants :114-146, :31-59)
+ *   -> repeat_kv (layers/attention.py:8-19) -> F.scaled_dot_product_attention(mask=None)
+ *      (models/decoder.py:105-109,188-197; layers/attention.py:281-285,366-375)
+ *   -> "b h l d -> b l (h d)" (attention.py:287,377).
+ * qkv is the packed projection output [B, (n_q + 2 n_kv) * 64] (bias added, not rotated).
+ * The cache is [B, n_kv, cache_len, 64] through element strides (cache_sb, cache_sh, cache_sl);
+ * slots [0, start_pos) must already hold the context; slot start_pos is written by this call
+ * (rotated k, raw v — what the reference stores) and attention covers [0, start_pos]. No mask is
+ * applied (the reference passes mask=None at decode). head_dim must be 64.
+ * splits = 0 lets the library choose (vy_attn_decode_splits); workspace must hold
+ * B * n_kv * splits * (n_q/n_kv) * 66 floats, tickets B * n_kv zero-initialised uint32 (the kernel
+ * leaves them zero again).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VyDecode {
+  int32_t B, n_q_heads, n_kv_heads, head_dim;
+  int32_t start_pos, cache_len;
+  const void* qkv;
+  int64_t ld_qkv;
+  int32_t qkv_dtype;
+  const float* rope_cos; /* [cache_len][32] fp32 or NULL */
+  const float* rope_sin;
+  void* k_cache;
+  void* v_cache;
+  int64_t cache_sb, cache_sh, cache_sl;
+  int32_t cache_dtype;
+  void* out; /* [B, n_q * 64] */
+  int64_t ld_out;
+  int32_t out_dtype;
+  int32_t splits;
+  float* workspace;
+  uint32_t* tickets;
+  void* stream;
+} VyDecode;
+
+VY_API int vy_attn_decode(const VyDecode* p);
+VY_API int vy_attn_decode_splits(int B, int n_kv_heads, int start_pos);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 
 #include "vy_common.cuh"
 
@@ -87,6 +88,56 @@ int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, con
         rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
     return VY_ERR_CUDA;
   }
+  return VY_OK;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t d[5], s[5];
+  uint32_t b[5];
+  int dtype, swz, rank;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return h;
+  }
+};
+
+// A descriptor depends only on its key (pointer, geometry, box, swizzle), so reuse across calls is
+// safe even when the caching allocator hands the same address to a different tensor.
+int get_tensor_map_cached(CUtensorMap* out, int dtype, int rank, const void* base,
+                          const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                          int swizzle) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.dtype = dtype;
+  key.swz = swizzle;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) {
+    key.d[i] = dims[i];
+    key.s[i] = i > 0 ? strides_bytes[i] : 0;
+    key.b[i] = box[i];
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return VY_OK;
+    }
+  }
+  int rc = make_tensor_map(out, dtype, rank, base, dims, strides_bytes, box, swizzle);
+  if (rc != VY_OK) return rc;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
   return VY_OK;
 }
 

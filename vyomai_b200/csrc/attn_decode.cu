@@ -1,0 +1,347 @@
+// vy_attn_decode: single-token (Sq == 1) attention over a contiguous kv-cache, HBM-bound.
+//
+// One CTA per (kv-split, kv head, batch row). Fuses, for the new token, the half-split RoPE of q
+// and k, the kv-cache append at `start_pos`, and the attention over slots [0, start_pos] — with NO
+// mask, exactly like the reference's decode step (models/decoder.py:355-362: mask is None when
+// seqlen == 1; quirk Q3). GQA is a head-index map (q head i reads kv head i / n_rep), so the
+// cache is streamed once per kv head instead of being re-materialised by repeat_kv
+// (layers/attention.py:8-19, models/decoder.py:190-193).
+//
+// Data movement: a key/value row of 64 elements is read by 8 lanes x 8 elements (16-byte loads
+// for bf16, 2 x 16 B for fp32), 4 rows per warp per step, UNROLL steps in flight; dot products
+// are reduced with 3 xor-shuffles; softmax is online per lane-group and merged across lane
+// groups (shuffles), warps (smem) and kv-splits (fp32 workspace + last-CTA ticket).
+// Algorithmic bytes = 2 * B * Hkv * ctx * 64 * sizeof(cache dtype) per layer.
+#include "vy_common.cuh"
+#include "vy_ptx.cuh"
+
+namespace vy {
+
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_UNROLL = 4;
+constexpr int DEC_MAX_REP = 8;
+constexpr int HD = 64;
+
+struct DecodeDev {
+  int B, Hq, Hkv, n_rep, start_pos, splits;
+  const void* qkv;  // [B, (Hq + 2 Hkv) * 64]
+  long long ld_qkv;
+  int qkv_dtype;
+  const float* rope_cos;  // row for position start_pos: [32], or null
+  const float* rope_sin;
+  void* kcache;
+  void* vcache;
+  long long c_sb, c_sh, c_sl;  // element strides: batch, head, slot
+  int cache_dtype;
+  void* out;  // [B, Hq * 64]
+  long long ld_out;
+  int out_dtype;
+  float scale_log2;
+  float* ws;          // [B, Hkv, splits, n_rep, 66] partial (m, l, o[64])
+  unsigned int* tickets;  // [B * Hkv], zero on entry, self-resetting
+};
+
+template <typename TC>
+__device__ __forceinline__ void load_row8(const TC* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load_row8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_row8<float>(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <typename TC, int NREP>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+attn_decode_kernel(const DecodeDev g) {
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = lane & 7;   // which 8-element slice of the head dim
+  const int lk = lane >> 3;  // key sub-index within the warp step (0..3)
+  const int ctx = g.start_pos + 1;
+
+  __shared__ float s_newk[HD];
+  __shared__ float s_newv[HD];
+  __shared__ float s_q[DEC_MAX_REP][HD];
+  __shared__ float s_red[DEC_WARPS][DEC_MAX_REP][HD + 2];
+
+  // ---- new token: bias-added projections -> RoPE(q, k) -> smem; append k, v to the cache ----
+  {
+    const long long row = static_cast<long long>(b) * g.ld_qkv;
+    const int t = threadIdx.x;
+    for (int idx = t; idx < (NREP + 2) * HD; idx += blockDim.x) {
+      const int which = idx / HD;  // 0..NREP-1: q heads, NREP: k, NREP+1: v
+      const int j = idx % HD;
+      int col;
+      if (which < NREP) col = (kvh * NREP + which) * HD;
+      else if (which == NREP) col = (g.Hq + kvh) * HD;
+      else col = (g.Hq + g.Hkv + kvh) * HD;
+      float x = ld_as_float(g.qkv, g.qkv_dtype, row + col + j);
+      if (which <= NREP && g.rope_cos) {
+        const int jj = j & 31;
+        const float other = ld_as_float(g.qkv, g.qkv_dtype, row + col + (j < 32 ? j + 32 : j - 32));
+        const float c = g.rope_cos[jj], s = g.rope_sin[jj];
+        x = j < 32 ? x * c - other * s : x * c + other * s;
+      }
+      if (which < NREP) s_q[which][j] = x;
+      else if (which == NREP) s_newk[j] = x;
+      else s_newv[j] = x;
+    }
+  }
+  __syncthreads();
+  TC* kc = reinterpret_cast<TC*>(g.kcache) + b * g.c_sb + kvh * g.c_sh;
+  TC* vc = reinterpret_cast<TC*>(g.vcache) + b * g.c_sb + kvh * g.c_sh;
+  if (split == g.splits - 1 && threadIdx.x < HD) {
+    // the cache stores what the reference stores: rotated k and raw v, rounded to the cache dtype
+    st_from_float(kc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, g.start_pos * g.c_sl + threadIdx.x, s_newk[threadIdx.x]);
+    st_from_float(vc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, g.start_pos * g.c_sl + threadIdx.x, s_newv[threadIdx.x]);
+  }
+
+  float q[NREP][8];
+#pragma unroll
+  for (int r = 0; r < NREP; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[r][j] = s_q[r][ld * 8 + j] * g.scale_log2;
+
+  float m[NREP], l[NREP], o[NREP][8];
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[r][j] = 0.f;
+  }
+
+  // cached slots [0, start_pos) are split evenly; the new token (slot start_pos) is taken from
+  // smem by the last split so no CTA has to wait for the append to become visible.
+  const int per = (g.start_pos + g.splits - 1) / g.splits;
+  const int k_begin = split * per;
+  const int k_end = min(g.start_pos, k_begin + per);
+  constexpr int KEYS_PER_ITER = DEC_WARPS * 4 * DEC_UNROLL;
+
+  for (int k0 = k_begin; k0 < k_end; k0 += KEYS_PER_ITER) {
+    float kv[DEC_UNROLL][8], vv[DEC_UNROLL][8];
+    int kidx[DEC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      kidx[u] = k0 + (u * DEC_WARPS + warp) * 4 + lk;
+      if (kidx[u] < k_end) {
+        load_row8<TC>(kc + kidx[u] * g.c_sl + ld * 8, kv[u]);
+        load_row8<TC>(vc + kidx[u] * g.c_sl + ld * 8, vv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const bool valid = kidx[u] < k_end;
+#pragma unroll
+      for (int r = 0; r < NREP; ++r) {
+        float s = 0.f;
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += q[r][j] * kv[u][j];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (valid) {
+          const float mn = fmaxf(m[r], s);
+          const float a = exp2f(m[r] - mn);
+          const float p = exp2f(s - mn);
+          l[r] = l[r] * a + p;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[r][j] = o[r][j] * a + p * vv[u][j];
+          m[r] = mn;
+        }
+      }
+    }
+  }
+  // the new token
+  if (split == g.splits - 1 && warp == 0 && lk == 0) {
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += q[r][j] * s_newk[ld * 8 + j];
+      s += __shfl_xor_sync(0x000000ffu, s, 1);
+      s += __shfl_xor_sync(0x000000ffu, s, 2);
+      s += __shfl_xor_sync(0x000000ffu, s, 4);
+      const float mn = fmaxf(m[r], s);
+      const float a = exp2f(m[r] - mn);
+      const float p = exp2f(s - mn);
+      l[r] = l[r] * a + p;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[r][j] = o[r][j] * a + p * s_newv[ld * 8 + j];
+      m[r] = mn;
+    }
+  }
+  (void)ctx;
+
+  // ---- merge the 4 lane groups of each warp (xor 8, 16) ----
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m[r], off);
+      const float l2 = __shfl_xor_sync(0xffffffffu, l[r], off);
+      const float mn = fmaxf(m[r], m2);
+      const float a1 = (m[r] == -INFINITY) ? 0.f : exp2f(m[r] - mn);
+      const float a2 = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
+      l[r] = l[r] * a1 + l2 * a2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o2 = __shfl_xor_sync(0xffffffffu, o[r][j], off);
+        o[r][j] = o[r][j] * a1 + o2 * a2;
+      }
+      m[r] = mn;
+    }
+    if (lk == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[warp][r][ld * 8 + j] = o[r][j];
+      if (ld == 0) {
+        s_red[warp][r][HD] = m[r];
+        s_red[warp][r][HD + 1] = l[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- merge warps; thread t < NREP*64 owns (head r, dim j) ----
+  const int t = threadIdx.x;
+  float M = -INFINITY, L = 0.f, O = 0.f;
+  const int r_own = t / HD, j_own = t % HD;
+  for (int rr = r_own; rr < NREP; rr += (DEC_WARPS * 32) / HD) {
+    M = -INFINITY; L = 0.f; O = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) {
+      const float mw = s_red[w][rr][HD], lw = s_red[w][rr][HD + 1], ow = s_red[w][rr][j_own];
+      if (mw == -INFINITY) continue;
+      const float mn = fmaxf(M, mw);
+      const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
+      const float a2 = exp2f(mw - mn);
+      L = L * a1 + lw * a2;
+      O = O * a1 + ow * a2;
+      M = mn;
+    }
+    if (g.splits == 1) {
+      st_from_float(g.out, g.out_dtype, static_cast<long long>(b) * g.ld_out + (kvh * NREP + rr) * HD + j_own, O / L);
+    } else {
+      float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + split) * NREP + rr) * (HD + 2));
+      w[j_own] = O;
+      if (j_own == 0) {
+        w[HD] = M;
+        w[HD + 1] = L;
+      }
+    }
+  }
+  if (g.splits == 1) return;
+
+  // ---- last CTA of this (b, kv head) combines the splits ----
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int prev = atomicAdd(&g.tickets[b * g.Hkv + kvh], 1u);
+    s_last = (prev == static_cast<unsigned int>(g.splits - 1)) ? 1u : 0u;
+    if (s_last) g.tickets[b * g.Hkv + kvh] = 0u;  // self-reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int rr = r_own; rr < NREP; rr += (DEC_WARPS * 32) / HD) {
+    M = -INFINITY; L = 0.f; O = 0.f;
+    for (int sp = 0; sp < g.splits; ++sp) {
+      const float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + sp) * NREP + rr) * (HD + 2));
+      const float mw = __ldcg(w + HD), lw = __ldcg(w + HD + 1), ow = __ldcg(w + j_own);
+      if (mw == -INFINITY) continue;
+      const float mn = fmaxf(M, mw);
+      const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
+      const float a2 = exp2f(mw - mn);
+      L = L * a1 + lw * a2;
+      O = O * a1 + ow * a2;
+      M = mn;
+    }
+    st_from_float(g.out, g.out_dtype, static_cast<long long>(b) * g.ld_out + (kvh * NREP + rr) * HD + j_own, O / L);
+  }
+}
+
+template <typename TC>
+static int launch_decode(const DecodeDev& g, cudaStream_t st) {
+  dim3 grid(g.splits, g.Hkv, g.B);
+  dim3 block(DEC_WARPS * 32);
+  switch (g.n_rep) {
+    case 1: attn_decode_kernel<TC, 1><<<grid, block, 0, st>>>(g); break;
+    case 2: attn_decode_kernel<TC, 2><<<grid, block, 0, st>>>(g); break;
+    case 3: attn_decode_kernel<TC, 3><<<grid, block, 0, st>>>(g); break;
+    case 4: attn_decode_kernel<TC, 4><<<grid, block, 0, st>>>(g); break;
+    case 6: attn_decode_kernel<TC, 6><<<grid, block, 0, st>>>(g); break;
+    case 8: attn_decode_kernel<TC, 8><<<grid, block, 0, st>>>(g); break;
+    default:
+      set_error("vy_attn_decode: unsupported q-heads per kv-head %d (1,2,3,4,6,8)", g.n_rep);
+      return VY_ERR_UNSUPPORTED;
+  }
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+}  // namespace vy
+
+extern "C" int vy_attn_decode_splits(int B, int Hkv, int start_pos) {
+  // enough CTAs to cover the GPU ~4x, but keep >= 64 cached slots per split
+  const int sms = vy::num_sms();
+  int splits = (4 * sms + B * Hkv - 1) / (B * Hkv);
+  const int max_by_len = (start_pos + 63) / 64;
+  if (splits > max_by_len) splits = max_by_len;
+  if (splits < 1) splits = 1;
+  if (splits > 32) splits = 32;
+  return splits;
+}
+
+extern "C" int vy_attn_decode(const VyDecode* p) {
+  using namespace vy;
+  VY_CHECK_ARG(p != nullptr, "vy_attn_decode: null params");
+  if (!vy_device_ok()) {
+    set_error("vy_attn_decode: no sm_100 device (there is no CPU fallback)");
+    return VY_ERR_NO_DEVICE;
+  }
+  VY_CHECK_ARG(p->head_dim == 64, "vy_attn_decode: head_dim must be 64 (got %d)", p->head_dim);
+  VY_CHECK_ARG(p->B > 0 && p->n_q_heads > 0 && p->n_kv_heads > 0 && p->n_q_heads % p->n_kv_heads == 0,
+               "vy_attn_decode: bad head counts");
+  VY_CHECK_ARG(p->start_pos >= 0 && p->start_pos < p->cache_len, "vy_attn_decode: start_pos %d outside the cache (%d)",
+               p->start_pos, p->cache_len);
+  VY_CHECK_ARG(p->qkv && p->k_cache && p->v_cache && p->out, "vy_attn_decode: null pointer");
+  VY_CHECK_ARG(dtype_ok(p->qkv_dtype) && dtype_ok(p->cache_dtype) && dtype_ok(p->out_dtype), "vy_attn_decode: bad dtype");
+  VY_CHECK_ARG((p->rope_cos == nullptr) == (p->rope_sin == nullptr), "vy_attn_decode: rope tables must both be set or NULL");
+  const long long es = dtype_size(p->cache_dtype);
+  VY_CHECK_ARG((reinterpret_cast<uintptr_t>(p->k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->v_cache) & 15) == 0 &&
+                   (p->cache_sb * es) % 16 == 0 && (p->cache_sh * es) % 16 == 0 && (p->cache_sl * es) % 16 == 0,
+               "vy_attn_decode: cache pointers/strides must keep 16-byte alignment");
+  int splits = p->splits > 0 ? p->splits : vy_attn_decode_splits(p->B, p->n_kv_heads, p->start_pos);
+  if (splits > 1) VY_CHECK_ARG(p->workspace && p->tickets, "vy_attn_decode: split-kv needs workspace and tickets");
+
+  DecodeDev g;
+  g.B = p->B; g.Hq = p->n_q_heads; g.Hkv = p->n_kv_heads; g.n_rep = p->n_q_heads / p->n_kv_heads;
+  g.start_pos = p->start_pos; g.splits = splits;
+  g.qkv = p->qkv; g.ld_qkv = p->ld_qkv; g.qkv_dtype = p->qkv_dtype;
+  g.rope_cos = p->rope_cos ? p->rope_cos + static_cast<long long>(p->start_pos) * 32 : nullptr;
+  g.rope_sin = p->rope_sin ? p->rope_sin + static_cast<long long>(p->start_pos) * 32 : nullptr;
+  g.kcache = p->k_cache; g.vcache = p->v_cache;
+  g.c_sb = p->cache_sb; g.c_sh = p->cache_sh; g.c_sl = p->cache_sl; g.cache_dtype = p->cache_dtype;
+  g.out = p->out; g.ld_out = p->ld_out; g.out_dtype = p->out_dtype;
+  g.scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+  g.ws = p->workspace; g.tickets = reinterpret_cast<unsigned int*>(p->tickets);
+  cudaStream_t st = static_cast<cudaStream_t>(p->stream);
+  if (p->cache_dtype == VY_BF16) return launch_decode<__nv_bfloat16>(g, st);
+  return launch_decode<float>(g, st);
+}

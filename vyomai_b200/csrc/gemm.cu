@@ -440,49 +440,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
-struct TmapKey {
-  const void* base;
-  uint64_t d0, d1, s1;
-  uint32_t b0, b1;
-  int dtype, swz;
-  bool operator==(const TmapKey& o) const {
-    return base == o.base && d0 == o.d0 && d1 == o.d1 && s1 == o.s1 && b0 == o.b0 && b1 == o.b1 &&
-           dtype == o.dtype && swz == o.swz;
-  }
-};
-struct TmapKeyHash {
-  size_t operator()(const TmapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.base);
-    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.d0); mix(k.d1); mix(k.s1); mix(k.b0); mix(k.b1); mix(static_cast<uint64_t>(k.dtype * 4 + k.swz));
-    return h;
-  }
-};
-
-// 2-D tensor map cache. A descriptor depends only on its key, so reuse across calls is safe even
-// when the caching allocator hands the same address to a different tensor.
 static int get_tmap_2d(CUtensorMap* out, int dtype, const void* base, uint64_t d0, uint64_t d1,
                        uint64_t stride1_bytes, uint32_t b0, uint32_t b1, int swz = 1) {
-  static std::mutex mu;
-  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{base, d0, d1, stride1_bytes, b0, b1, dtype, swz};
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) {
-      *out = it->second;
-      return VY_OK;
-    }
-  }
   uint64_t dims[2] = {d0, d1};
   uint64_t strides[2] = {0, stride1_bytes};
   uint32_t box[2] = {b0, b1};
-  int rc = make_tensor_map(out, dtype, 2, base, dims, strides, box, swz);
-  if (rc != VY_OK) return rc;
-  std::lock_guard<std::mutex> lk(mu);
-  if (cache.size() > 8192) cache.clear();
-  cache.emplace(key, *out);
-  return VY_OK;
+  return get_tensor_map_cached(out, dtype, 2, base, dims, strides, box, swz);
 }
 
 template <typename TIn, int BN, bool A_MN, bool B_MN>

@@ -58,6 +58,11 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
 
+// Same, memoised on (pointer, geometry, box, swizzle).
+int get_tensor_map_cached(CUtensorMap* out, int dtype, int rank, const void* base,
+                          const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                          int swizzle);
+
 // ---- device: dtype-generic element access ---------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ float ld_as_float(const void* p, int dt, int64_t i) {

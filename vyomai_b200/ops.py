@@ -237,3 +237,98 @@ def add_layernorm_bwd(dy, s, gamma, mean, rstd):
         dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), partials=partials.data_ptr(), stream=_stream(),
     )
     return dx.view(dy.shape), dgamma, dbeta
+
+
+def attn_fwd(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    *,
+    causal: bool = False,
+    q_pos0: int = 0,
+    key_padding_mask: Optional[torch.Tensor] = None,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    need_lse: bool = False,
+):
+    """Flash attention forward. q [B,Hq,Sq,64], k/v [B,Hkv,Skv,64] (bf16, any batch/head/token
+    strides). Returns (out [B,Sq,Hq*64], lse [B,Hq,Sq] or None)."""
+    _need_cuda(q, k, v, key_padding_mask, out)
+    B, Hq, Sq, D = q.shape
+    _, Hkv, Skv, _ = k.shape
+    for t in (q, k, v):
+        if t.stride(3) != 1:
+            raise _lib.VyomError("attn_fwd: head_dim must be contiguous")
+    if out is None:
+        out = torch.empty((B, Sq, Hq * D), device=q.device, dtype=out_dtype or q.dtype)
+    lse = torch.empty((B, Hq, Sq), device=q.device, dtype=torch.float32) if need_lse else None
+    kpm = None
+    if key_padding_mask is not None:
+        kpm = key_padding_mask
+        if kpm.dtype != torch.uint8 or kpm.stride(1) != 1:
+            raise _lib.VyomError("attn_fwd: key_padding_mask must be uint8 [B, Skv] with unit inner stride")
+    _lib.call(
+        "vy_attn_fwd", "VyAttn",
+        B=B, n_q_heads=Hq, n_kv_heads=Hkv, head_dim=D, Sq=Sq, Skv=Skv, qkv_dtype=_dt(q),
+        q=q.data_ptr(), q_sb=q.stride(0), q_sh=q.stride(1), q_sl=q.stride(2),
+        k=k.data_ptr(), k_sb=k.stride(0), k_sh=k.stride(1), k_sl=k.stride(2),
+        v=v.data_ptr(), v_sb=v.stride(0), v_sh=v.stride(1), v_sl=v.stride(2),
+        causal=int(causal), q_pos0=q_pos0, key_padding_mask=_ptr(kpm),
+        kpm_stride=kpm.stride(0) if kpm is not None else 0,
+        out=out.data_ptr(), o_sb=out.stride(0), o_sl=out.stride(1), out_dtype=_dt(out), lse=_ptr(lse),
+        stream=_stream(),
+    )
+    return out, lse
+
+
+_TICKETS = {}
+
+
+def _tickets(device: torch.device, n: int) -> torch.Tensor:
+    t = _TICKETS.get(device)
+    if t is None or t.numel() < n:
+        t = torch.zeros(max(n, 4096), device=device, dtype=torch.int32)
+        _TICKETS[device] = t
+    return t
+
+
+def attn_decode(
+    qkv: torch.Tensor,
+    k_cache: torch.Tensor,
+    v_cache: torch.Tensor,
+    start_pos: int,
+    n_q_heads: int,
+    n_kv_heads: int,
+    rope_cos: Optional[torch.Tensor],
+    rope_sin: Optional[torch.Tensor],
+    *,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    splits: int = 0,
+) -> torch.Tensor:
+    """Single-token attention with fused RoPE and kv-cache append. qkv [B, (Hq+2Hkv)*64] packed
+    projections; caches [>=B, Hkv, cache_len, 64]; returns out [B, Hq*64]."""
+    _need_cuda(qkv, k_cache, v_cache, rope_cos, rope_sin, out)
+    B = qkv.shape[0]
+    D = 64
+    if k_cache.stride() != v_cache.stride() or k_cache.dtype != v_cache.dtype or k_cache.stride(3) != 1:
+        raise _lib.VyomError("attn_decode: k/v caches must share dtype and strides, head_dim contiguous")
+    if out is None:
+        out = torch.empty((B, n_q_heads * D), device=qkv.device, dtype=out_dtype or qkv.dtype)
+    L = _lib.lib()
+    if splits <= 0:
+        splits = L.vy_attn_decode_splits(B, n_kv_heads, start_pos)
+    ws = tk = None
+    if splits > 1:
+        ws = torch.empty(B * n_kv_heads * splits * (n_q_heads // n_kv_heads) * 66, device=qkv.device, dtype=torch.float32)
+        tk = _tickets(qkv.device, B * n_kv_heads)
+    _lib.call(
+        "vy_attn_decode", "VyDecode",
+        B=B, n_q_heads=n_q_heads, n_kv_heads=n_kv_heads, head_dim=D, start_pos=start_pos,
+        cache_len=k_cache.shape[2], qkv=qkv.data_ptr(), ld_qkv=qkv.stride(0), qkv_dtype=_dt(qkv),
+        rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin), k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),
+        cache_sb=k_cache.stride(0), cache_sh=k_cache.stride(1), cache_sl=k_cache.stride(2), cache_dtype=_dt(k_cache),
+        out=out.data_ptr(), ld_out=out.stride(0), out_dtype=_dt(out), splits=splits, workspace=_ptr(ws),
+        tickets=_ptr(tk), stream=_stream(),
+    )
+    return out
