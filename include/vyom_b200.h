@@ -64,6 +64,9 @@ VY_API const char* vy_last_error(void);
 VY_API int64_t vy_launch_count(void);
 /* 1 if the current device is sm_100 (B200), else 0 */
 VY_API int vy_device_ok(void);
+/* sizeof() of the parameter struct called `name` ("VyGemm", ...) as compiled into the library, or -1;
+ * bindings compare it with their own layout so a stale .so / header pair fails at load time. */
+VY_API int vy_abi_sizeof(const char* name);
 
 /* ------------------------------------------------------------------------------------------
  * vy_gemm — tcgen05/TMEM GEMM fed by TMA with a fused epilogue.
@@ -85,6 +88,7 @@ VY_API int vy_device_ok(void);
  *   if aux && act in {GELU_*}:  aux[r,c] = x        (pre-activation saved for backward)
  *   x = act(x)                  (D* variants: x = x * act'(aux[r,c]))
  *   if addend: x += addend[ar, c],  ar = addend_row_mod ? addend_row_off + r % addend_row_mod : r
+ *   if addend2: x += addend2[r, c]       (backward: the two residual gradients of a layer)
  *   out[orow, c] = out_scale * x,
  *       orow = out_row_group ? (r / out_row_group) * out_row_group_stride + r % out_row_group
  *                              + out_row_off : r
@@ -97,9 +101,10 @@ VY_API int vy_device_ok(void);
  * Adds bias, rotates q and k heads in registers with the half-split RoPE of
  * positional_embeddings.py:140-182 using rope_cos/rope_sin[pos][j] (fp32 tables of d/2 columns,
  * pass NULL for absolute/sinusoidal models), and scatters straight into q_out[b,h,l,:],
- * k_out[b,hk,start_pos+l,:], v_out[...] through the given element strides — i.e. the
+ * k_out[b,hk,kv_dst_pos0+l,:], v_out[...] through the given element strides — i.e. the
  * "b l (h d) -> b h l d" rearrange (attention.py:118-120) and the kv-cache append
- * (kv_cache.py:355-359) are fused into the projection.
+ * (kv_cache.py:355-359) are fused into the projection. k/v rows are written at token index
+ * kv_dst_pos0 + l (= start_pos for a cache, 0 for a fresh buffer); q rows at l.
  * ------------------------------------------------------------------------------------------ */
 typedef struct VyGemm {
   int32_t M, N, K;
@@ -120,6 +125,9 @@ typedef struct VyGemm {
   int64_t ld_addend;
   int32_t addend_dtype;
   int32_t addend_row_mod, addend_row_off;
+  const void* addend2; /* second residual stream (same row index as the output row), or NULL */
+  int64_t ld_addend2;
+  int32_t addend2_dtype;
   void* aux; /* pre-activation: written by GELU_*, read by DGELU_*; or NULL */
   int64_t ld_aux;
   int32_t aux_dtype;
@@ -130,7 +138,7 @@ typedef struct VyGemm {
   int32_t out_row_group, out_row_group_stride, out_row_off;
 
   /* VY_EPI_QKV_ROPE only */
-  int32_t tokens_per_seq, start_pos, head_dim, n_q_heads, n_kv_heads;
+  int32_t tokens_per_seq, start_pos, kv_dst_pos0, head_dim, n_q_heads, n_kv_heads;
   const float* rope_cos; /* [>= start_pos + tokens_per_seq][head_dim/2] */
   const float* rope_sin;
   void* q_out;
@@ -139,6 +147,7 @@ typedef struct VyGemm {
   int64_t k_sb, k_sh, k_sl;
   void* v_out;
   int64_t v_sb, v_sh, v_sl;
+  int32_t kv_out_dtype; /* dtype of k_out / v_out (a kv-cache may be fp32 while q_out is bf16) */
 
   void* stream;
 } VyGemm;
@@ -220,6 +229,75 @@ typedef struct VyAttn {
 VY_API int vy_attn_fwd(const VyAttn* p);
 
 /* ------------------------------------------------------------------------------------------
+ * vy_attn_bwd — flash-attention backward (tcgen05 + TMEM + TMA): the autograd of the SDPA call
+ * sites listed under vy_attn_fwd, of repeat_kv (dk/dv summed over the query heads of a group) and of
+ * apply_rotary_pos_emb (the rotation is undone on dq / dk before they are written).
+ * Inputs are the forward's bf16 q/k/v (post-RoPE, [B, heads, S, 64] via strides), its output o
+ * ([B, Sq, Hq*64] via o_sb/o_sl, any dtype), the bf16 output gradient dout (same layout through
+ * do_sb/do_sl) and lse from vy_attn_fwd. dsum is a [B, Hq, Sq] fp32 workspace. Results go to
+ * dq [B*Sq, >= Hq*64] (row stride ld_dq, head h at column h*64), dk / dv [B*Skv, >= Hkv*64] — pass
+ * three column offsets of one packed [tokens, (Hq+2Hkv)*64] buffer to get the gradient of the
+ * fused q|k|v projection directly. rope_cos/rope_sin are the forward's tables (NULL = no RoPE),
+ * rope_pos0 the table row of position 0 (normally 0).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VyAttnBwd {
+  int32_t B, n_q_heads, n_kv_heads, head_dim;
+  int32_t Sq, Skv;
+  const void* q;
+  int64_t q_sb, q_sh, q_sl;
+  const void* k;
+  int64_t k_sb, k_sh, k_sl;
+  const void* v;
+  int64_t v_sb, v_sh, v_sl;
+  const void* o;
+  int64_t o_sb, o_sl;
+  int32_t o_dtype;
+  const void* dout; /* bf16 */
+  int64_t do_sb, do_sl;
+  const float* lse;
+  float* dsum;
+  int32_t causal, q_pos0;
+  const uint8_t* key_padding_mask;
+  int64_t kpm_stride;
+  const float* rope_cos;
+  const float* rope_sin;
+  int32_t rope_pos0;
+  void* dq;
+  int64_t ld_dq;
+  void* dk;
+  int64_t ld_dk;
+  void* dv;
+  int64_t ld_dv;
+  int32_t out_dtype;
+  void* stream;
+} VyAttnBwd;
+
+VY_API int vy_attn_bwd(const VyAttnBwd* p);
+
+/* vy_rope_apply — stand-alone half-split RoPE for the public apply_rotary_pos_emb(q, k, freqs)
+ * helper (layers/positional_embeddings.py:155-182): out[b,h,l,:] = rotate(x[b,h,l,:], angle row
+ * pos0 + l). cos/sin are fp32 [rows][32]; inverse = 1 applies the transpose rotation. head_dim 64. */
+typedef struct VyRope {
+  int32_t B, H, S, head_dim;
+  const void* x;
+  int64_t x_sb, x_sh, x_sl;
+  int32_t dtype;
+  const float* cos;
+  const float* sin;
+  int32_t pos0, inverse;
+  void* out;
+  int64_t o_sb, o_sh, o_sl;
+  void* stream;
+} VyRope;
+
+VY_API int vy_rope_apply(const VyRope* p);
+
+/* vy_act_bwd — out[i] = dy[i] * act'(z[i]) (act = VY_ACT_GELU_ERF / VY_ACT_GELU_TANH): the GELU
+ * backward of the LM head (models/decoder.py:269), whose upstream gradient comes out of a LayerNorm
+ * backward rather than a GEMM (inside the FFN the same factor rides in the dgrad GEMM epilogue). */
+VY_API int vy_act_bwd(int64_t n, const void* dy, const void* z, int dtype, int act, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * vy_attn_decode — single-token attention over the contiguous kv-cache, fused with the new
  * token's RoPE and cache append. Replaces, for seqlen == 1, the chain
  *   apply_rotary_pos_emb (layers/positional_embeddings.py:155-182)
@@ -260,6 +338,129 @@ typedef struct VyDecode {
 
 VY_API int vy_attn_decode(const VyDecode* p);
 VY_API int vy_attn_decode_splits(int B, int n_kv_heads, int start_pos);
+
+/* ------------------------------------------------------------------------------------------
+ * vy_embed_fwd / vy_embed_bwd — row gather with fused positional add, scale and row remap.
+ * replaces nn.Embedding lookup + "hidden_state + pos_info" at VyomAI/models/encoder.py:146-152,
+ * models/decoder.py:343-350, models/multimodel.py:162-180 (the captioner writes its text rows
+ * after the prepended image row: out_group_stride = S+1, out_row_off = 1), and the cls-row
+ * "2 * (cls + pos[0])" of models/vision_encoder.py:119-127 (ids = NULL, ld_src = 0, out_scale = 2).
+ *   srow = ids ? ids[r] : r;  l = r % tokens_per_seq
+ *   out[(r / tokens_per_seq) * out_group_stride + l + out_row_off, :] =
+ *        out_scale * (src[srow * ld_src + :] + (pos ? pos[(pos_row_off + l) * H + :] : 0))
+ * bwd scatter-adds dout rows (same remap, times out_scale) into dtable[srow] and/or dpos[...]
+ * with atomics (the autograd of the lookups above). ids are int64. H % 8 == 0.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VyEmbed {
+  int32_t rows, H;
+  const int64_t* ids; /* [rows] or NULL */
+  const void* src;    /* table [vocab, H] (ld_src) or direct rows */
+  int64_t ld_src;
+  int32_t dtype; /* of src, pos, out, dout, dtable, dpos */
+  int32_t vocab;
+  int32_t tokens_per_seq, out_group_stride, out_row_off;
+  const void* pos; /* [>= pos_row_off + tokens_per_seq, H] or NULL */
+  int32_t pos_row_off;
+  float out_scale; /* 0 = 1 */
+  void* out;
+  int64_t ld_out; /* also the row stride of dout in bwd */
+  /* bwd only */
+  const void* dout;
+  void* dtable; /* or NULL */
+  void* dpos;   /* or NULL */
+  void* stream;
+} VyEmbed;
+
+VY_API int vy_embed_fwd(const VyEmbed* p);
+VY_API int vy_embed_bwd(const VyEmbed* p);
+
+/* vy_patchify — NCHW pixels -> [B * (H/ph) * (W/pw), C*ph*pw] patch rows, (c, i, j) order with j
+ * fastest: the im2col of the stride==kernel nn.Conv2d at VyomAI/models/vision_encoder.py:83-88,114
+ * so that the patch embedding is one vy_gemm against pixel_seq.weight viewed as [hidden, C*ph*pw]. */
+typedef struct VyPatchify {
+  int32_t B, C, H, W, patch_h, patch_w;
+  const void* pixels;
+  int32_t in_dtype;
+  void* out;
+  int32_t out_dtype;
+  void* stream;
+} VyPatchify;
+
+VY_API int vy_patchify(const VyPatchify* p);
+
+/* vy_argmax_rows — greedy token selection: out[r] = first index of the row maximum, the
+ * torch.topk(k=1) rule of VyomAI/models/decoder.py:489-496 and generation_utils.py:179-189
+ * (argmax of softmax(logits) == argmax of logits). out is int64 [rows]. */
+VY_API int vy_argmax_rows(int rows, int V, const void* x, int64_t ld, int dtype, int64_t* out, void* stream);
+
+/* vy_colsum — out[c] (+)= scale * sum_r x[r, c]: the bias gradient of every nn.Linear on the path.
+ * workspace: vy_colsum_workspace_floats(cols) floats. */
+VY_API int vy_colsum(int rows, int cols, const void* x, int64_t ld, int dtype, void* out, int out_dtype,
+                     int accumulate, float scale, float* workspace, void* stream);
+VY_API int vy_colsum_workspace_floats(int cols);
+
+/* vy_cast4d — strided 4-D copy with dtype conversion (inner dim contiguous on both sides), e.g.
+ * an fp32 StaticCacheOne prefix (layers/kv_cache.py:295-312) to the bf16 attention operands. */
+typedef struct VyCast4d {
+  int32_t n0, n1, n2, n3;
+  const void* src;
+  int32_t src_dtype;
+  int64_t s0, s1, s2;
+  void* dst;
+  int32_t dst_dtype;
+  int64_t d0, d1, d2;
+  void* stream;
+} VyCast4d;
+
+VY_API int vy_cast4d(const VyCast4d* p);
+
+/* vy_softmax_xent — fused softmax cross-entropy over the vocabulary, the training loss of the
+ * captioner / CLM notebooks (Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1 `loss_fn`:
+ * F.cross_entropy(logits.view(-1, V), labels.view(-1), ignore_index)). loss_rows[r] = logsumexp -
+ * logit[label] (0 for ignored rows). With write_grad the logits buffer is overwritten IN PLACE by
+ * d loss / d logits = (softmax - onehot) * grad_scale * (*grad_scale_ptr if given). */
+typedef struct VyXent {
+  int32_t rows, V;
+  void* logits;
+  int64_t ld;
+  int32_t dtype;
+  const int64_t* labels;
+  int64_t ignore_index;
+  const float* grad_scale_ptr; /* device scalar or NULL */
+  float grad_scale;
+  float* loss_rows; /* [rows] or NULL */
+  int32_t write_grad;
+  void* stream;
+} VyXent;
+
+VY_API int vy_softmax_xent(const VyXent* p);
+
+/* vy_sqnorm — *out += sum(g^2) over a flat gradient buffer (out must be zeroed by the caller);
+ * vy_adamw — fused AdamW over a flat parameter buffer (torch.optim.AdamW semantics: decoupled
+ * weight decay, bias correction), with the global-norm clip coefficient computed on device from
+ * *grad_sqnorm (clip_grad_norm_(…, max_grad_norm) of the notebooks' training loop) and grad_div
+ * dividing the gradient first (data-parallel mean). master (optional fp32 copy) is updated and the
+ * bf16/fp32 param rewritten from it. */
+VY_API int vy_sqnorm(int64_t n, const void* g, int dtype, float* out, void* stream);
+
+typedef struct VyAdamW {
+  int64_t n;
+  void* param;
+  int32_t param_dtype;
+  const void* grad;
+  int32_t grad_dtype;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* master; /* or NULL */
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step; /* 1-based */
+  const float* grad_sqnorm; /* device scalar or NULL */
+  float max_grad_norm;      /* <= 0: no clipping */
+  float grad_div;           /* 0 = 1 */
+  void* stream;
+} VyAdamW;
+
+VY_API int vy_adamw(const VyAdamW* p);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,193 @@
+"""-m gpu parity tests: the sm_100a path behind the reference's model classes vs (a) the golden
+fixtures produced by the REAL reference and (b) the CPU oracle on fresh seeded inputs.
+
+Stated tolerances (rel-L2 of the output tensor against the fp32 reference result):
+  fp32 modules  : GEMMs run in tf32 (10-bit mantissa) and attention operands in bf16 with fp32
+                  softmax / accumulation            -> hidden/logits <= 6e-3
+  bf16 modules  : bf16 storage everywhere, fp32 accumulation -> hidden/logits <= 2e-2
+                  (the reference's own bf16-vs-fp32 gap is 5e-3 on this shape)
+Integer results (kv-cache slot indexing, which slots are touched, greedy token ids) must be
+bit-exact; greedy ids are compared wherever the reference's top-1/top-2 logit margin exceeds the
+numeric tolerance of the path (margin rule of SURVEY.md §7).
+"""
+from dataclasses import make_dataclass
+
+import pytest
+import torch
+
+from tests.conftest import load_fixture, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 6e-3, torch.bfloat16: 2e-2}
+
+
+def _cfg_obj(meta, drop=("pos", "attn", "vit")):
+    fields = {k: (tuple(v) if isinstance(v, list) else v) for k, v in meta.items() if k not in drop}
+    fields["hidden_dropout_prob"] = 0.0
+    C = make_dataclass("Cfg", [(k, type(v), v) for k, v in fields.items()])
+    return C()
+
+
+def _load(model, sd, dtype):
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("position_ids" in m or "num_patches" in m or "inv_freq" in m for m in missing), missing
+    return model.to("cuda").to(dtype).eval()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["encoder_rope_gqa", "encoder_absolute_mha"])
+def test_encoder_forward_matches_reference(name, dtype):
+    from vyomai_b200 import EncoderModel
+    fx = load_fixture(name)
+    m = fx.meta
+    model = _load(EncoderModel(_cfg_obj(m), m["pos"], m["attn"]), fx.sd, dtype)
+    ids, mask = fx.inputs["input_ids"].cuda(), fx.inputs["attention_mask"].cuda()
+    with torch.no_grad():
+        out = model(ids, mask).logits
+    assert list(out.shape) == list(fx.outputs["logits"].shape)
+    assert rel_l2(out.float().cpu(), fx.outputs["logits"]) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_encoder_mlm_matches_reference(dtype):
+    from vyomai_b200 import EncoderForMaskedLM
+    fx = load_fixture("encoder_mlm_sinusoidal_mha")
+    m = fx.meta
+    model = _load(EncoderForMaskedLM(_cfg_obj(m), m["pos"], m["attn"]), fx.sd, dtype)
+    with torch.no_grad():
+        o = model(fx.inputs["input_ids"].cuda(), fx.inputs["attention_mask"].cuda())
+    assert rel_l2(o.hidden_state.float().cpu(), fx.outputs["hidden_state"]) <= TOL[dtype]
+    assert rel_l2(o.logits.float().cpu(), fx.outputs["logits"]) <= TOL[dtype]
+
+
+MARGIN = {torch.float32: 0.02, torch.bfloat16: 0.2}  # logit units; random-init logits have std ~0.6
+
+
+def _oracle_margins(fx, ref_tokens, prompt_len):
+    """top-1 / top-2 logit margin of the REFERENCE path at every generated position (teacher-forced
+    on the reference's own ids, fp32 CPU oracle)."""
+    from oracle import vyom_oracle as O
+    m = fx.meta
+    out = []
+    for cur in range(prompt_len, ref_tokens.shape[1]):
+        _, lg = O.decoder_forward(fx.sd, fx.cfg(), ref_tokens[:, :cur], None, m["pos"], m["attn"])
+        top2 = lg[:, -1].topk(2, dim=-1).values
+        out.append(float((top2[:, 0] - top2[:, 1]).min()))
+    return out
+
+
+def _ids_match_up_to_ambiguity(ours, ref, margins, prompt_len, tol):
+    """bit-exact ids wherever the reference's margin exceeds the path's numeric tolerance; after the
+    first ambiguous step the continuations are legitimately incomparable."""
+    assert torch.equal(ours[:, :prompt_len], ref[:, :prompt_len])
+    for i, mg in enumerate(margins):
+        if mg <= tol:
+            return i
+        assert torch.equal(ours[:, prompt_len + i], ref[:, prompt_len + i]), (i, mg, ours, ref)
+    return len(margins)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["decoder_rope_gqa", "decoder_absolute_mha", "decoder_rope_mha"])
+def test_decoder_forward_cache_and_generate(name, dtype):
+    from vyomai_b200 import DecoderModel, DynamicCacheOne, StaticCacheOne
+    fx = load_fixture(name)
+    m = fx.meta
+    cfg = _cfg_obj(m)
+    model = _load(DecoderModel(cfg, m["pos"], m["attn"]), fx.sd, dtype)
+    tol = TOL[dtype]
+    with torch.no_grad():
+        full = model(fx.inputs["input_ids"].cuda(), fx.inputs["attention_mask"].cuda())
+        assert rel_l2(full.logits.float().cpu(), fx.outputs["logits"]) <= tol
+        assert rel_l2(full.hidden_state.float().cpu(), fx.outputs["hidden_state"]) <= tol
+
+        prompt = fx.inputs["prompt"].cuda()
+        for cache_dtype in (dtype, torch.float32):
+            kv = StaticCacheOne(cfg, max_cache_len=12, batch_size=2, dtype=cache_dtype)
+            am = torch.ones(2, 4, dtype=torch.long, device="cuda")
+            o0 = model(prompt, am, use_cache=True, kv_cache=kv, start_pos=0)
+            assert rel_l2(o0.logits.float().cpu(), fx.outputs["prefill_logits"]) <= tol
+            steps = []
+            for t in range(3):
+                tok = fx.inputs["decode_tokens"][:, t:t + 1].cuda()
+                am = torch.cat([am, torch.ones(2, 1, dtype=torch.long, device="cuda")], dim=-1)
+                ot = model(tok, am, use_cache=True, kv_cache=kv, start_pos=4 + t)
+                steps.append(ot.logits)
+            assert rel_l2(torch.cat(steps, 1).float().cpu(), fx.outputs["decode_logits"]) <= tol
+            # kv-cache indexing is bit-exact: slots [0,7) written, the rest still exactly zero
+            k0 = kv.key_cache[0].float().cpu()
+            assert torch.equal(k0 == 0, fx.outputs["key_cache_l0"] == 0)
+            assert rel_l2(k0, fx.outputs["key_cache_l0"]) <= tol
+            assert rel_l2(kv.value_cache[1].float().cpu(), fx.outputs["value_cache_l1"]) <= tol
+
+        # greedy generation: all three cache modes agree with each other and with the reference ids
+        gp = fx.inputs["gen_prompt"].cuda()
+        gm = torch.ones(1, 4, dtype=torch.long, device="cuda")
+        g1 = model.generate(gp, gm, max_len=6, use_cache=False)
+        g2 = model.generate(gp, gm, max_len=6, use_cache=True)
+        g3 = model.generate(gp, gm, max_len=6, use_cache=True, use_static_cache=True)
+        ref = fx.outputs["generate"]
+        assert list(g3.shape) == list(ref.shape)
+        assert torch.equal(g2, g3)  # dynamic and static caches run the same kernels on the same values
+        margins = _oracle_margins(fx, ref, 4)
+        for g in (g1, g2, g3):
+            n_checked = _ids_match_up_to_ambiguity(g.cpu(), ref, margins, 4, MARGIN[dtype])
+        print(f"{name} {dtype}: greedy ids bit-exact for {n_checked}/{len(margins)} steps "
+              f"(margins {[round(x, 3) for x in margins]}); identical to reference: {torch.equal(g3.cpu(), ref)}")
+        # batch-2 static-cache generation (prompts of equal length)
+        gb = model.generate(prompt, torch.ones(2, 4, dtype=torch.long, device="cuda"), max_len=5, use_cache=True,
+                            use_static_cache=True)
+        refb = fx.outputs["generate_batch"]
+        mb = _oracle_margins(fx, refb, 4)
+        _ids_match_up_to_ambiguity(gb.cpu(), refb, mb, 4, MARGIN[dtype])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_vit_matches_reference(dtype):
+    from vyomai_b200 import Vit
+    fx = load_fixture("vit_small")
+    model = _load(Vit(_cfg_obj(fx.meta)), fx.sd, dtype)
+    with torch.no_grad():
+        out = model(fx.inputs["pixel_values"].cuda()).logits
+    assert list(out.shape) == list(fx.outputs["logits"].shape)
+    assert rel_l2(out.float().cpu(), fx.outputs["logits"]) <= TOL[dtype]
+
+
+def test_vit_accepts_cpu_model_and_input_like_the_reference_test():
+    """tests/test_vision_encoder.py builds model and input on the CPU; the build moves both to the GPU."""
+    from vyomai_b200 import Vit
+    fx = load_fixture("vit_small")
+    model = Vit(_cfg_obj(fx.meta))
+    model.load_state_dict(fx.sd, strict=False)
+    out = model.eval()(fx.inputs["pixel_values"]).logits
+    assert out.device.type == "cpu"
+    assert rel_l2(out.float(), fx.outputs["logits"]) <= TOL[torch.float32]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_vlm_forward_and_generate(dtype):
+    from vyomai_b200 import DynamicCache, StaticCache, VisionLanguageModel, Vit, generate_multimodel
+    fx = load_fixture("vlm_rope_gqa")
+    m = fx.meta
+    cfg = _cfg_obj(m)
+    vlm = _load(VisionLanguageModel(cfg, encoder=Vit(_cfg_obj(m["vit"])), pos_embedding_type=m["pos"],
+                                    attention_type=m["attn"]), fx.sd, dtype)
+    with torch.no_grad():
+        lg = vlm(pixel_values=fx.inputs["pixel_values"].cuda(), decoder_input_ids=fx.inputs["input_ids"].cuda(),
+                 decoder_attention_mask=fx.inputs["attention_mask"].cuda()).logits
+        assert list(lg.shape) == list(fx.outputs["logits"].shape)  # (3, 18, V): image token + 17 text tokens
+        assert rel_l2(lg.float().cpu(), fx.outputs["logits"]) <= TOL[dtype]
+        enc = vlm.get_encoder_output(fx.inputs["pixel_values"][:1].cuda())
+        assert rel_l2(enc.float().cpu(), fx.outputs["encoder_output"]) <= TOL[dtype]
+        start = fx.inputs["gen_start"].cuda()
+        g0 = generate_multimodel(vlm, enc, None, start, max_new_tokens=6, use_cache=False)
+        vlm._setup_cache(cfg, cls=DynamicCache)
+        g1 = generate_multimodel(vlm, enc, None, start, max_new_tokens=6, use_cache=True)
+        vlm._clean_cache()
+        vlm._setup_cache(cfg, cls=StaticCache)
+        g2 = generate_multimodel(vlm, enc, None, start, max_new_tokens=6, use_cache=True)
+        vlm._clean_cache()
+        assert torch.equal(g0, g1) and torch.equal(g0, g2)
+        assert list(g0.shape) == list(fx.outputs["generate"].shape)

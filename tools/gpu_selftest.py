@@ -300,6 +300,79 @@ def attn_decode():
     return ok
 
 
+@group
+def attn_bwd():
+    import torch
+    from vyomai_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    cases = [
+        (2, 2, 2, 128, False, None, False),
+        (3, 12, 4, 17, False, "right", True),
+        (2, 12, 12, 248, True, "right", True),
+        (2, 12, 4, 128, True, None, True),
+        (2, 4, 2, 300, False, "right", False),
+        (1, 6, 2, 197, False, None, False),
+        (2, 4, 4, 130, True, "left", True),
+    ]
+    for (B, Hq, Hkv, S, causal, pad, use_rope) in cases:
+        d = 64
+        n_rep = Hq // Hkv
+        # leaf tensors are the PRE-rope projections so the test also covers the fused inverse rotation
+        qp = torch.randn(B, Hq, S, d, device=dev).bfloat16().float().requires_grad_(True)
+        kp = torch.randn(B, Hkv, S, d, device=dev).bfloat16().float().requires_grad_(True)
+        vp = torch.randn(B, Hkv, S, d, device=dev).bfloat16().float().requires_grad_(True)
+        inv = 1.0 / (10000 ** (torch.arange(0, d, 2, device=dev).float() / d))
+        ang = torch.arange(S, device=dev).float()[:, None] * inv[None]
+        cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+        c = torch.cat([cos, cos], -1)[None, None]
+        s_ = torch.cat([sin, sin], -1)[None, None]
+
+        def rot(t):
+            if not use_rope:
+                return t
+            t1, t2 = t.chunk(2, -1)
+            return t * c + torch.cat([-t2, t1], -1) * s_
+
+        qr, kr = rot(qp), rot(kp)
+        kpm = None
+        if pad is not None:
+            kpm = torch.ones(B, S, device=dev, dtype=torch.uint8)
+            for bi in range(B):
+                n = max(1, S - 3 - 5 * bi)
+                if pad == "right":
+                    kpm[bi, n:] = 0
+                else:
+                    kpm[bi, : S - n] = 0
+        kf = kr.repeat_interleave(n_rep, 1)
+        vf = vp.repeat_interleave(n_rep, 1)
+        sc = qr @ kf.transpose(-1, -2) / 8.0
+        vis = torch.ones(B, 1, S, S, device=dev)
+        if causal:
+            vis = vis * torch.tril(torch.ones(S, S, device=dev))[None, None]
+        if kpm is not None:
+            vis = vis * kpm.float()[:, None, None, :]
+        sc = sc + (1.0 - vis) * torch.finfo(torch.float32).min
+        o_ref = (torch.softmax(sc, -1) @ vf).permute(0, 2, 1, 3).reshape(B, S, Hq * d)
+        dout = torch.randn(B, S, Hq * d, device=dev).bfloat16()
+        o_ref.backward(dout.float())
+
+        q16, k16, v16 = qr.detach().bfloat16(), kr.detach().bfloat16(), vp.detach().bfloat16()
+        o, lse = ops.attn_fwd(q16, k16, v16, causal=causal, q_pos0=0, key_padding_mask=kpm, need_lse=True)
+        N = (Hq + 2 * Hkv) * d
+        dqkv = torch.zeros(B * S, N, device=dev, dtype=torch.float32)
+        ops.attn_bwd(q16, k16, v16, o, dout, lse, causal=causal, q_pos0=0, key_padding_mask=kpm,
+                     rope_cos=cos if use_rope else None, rope_sin=sin if use_rope else None,
+                     dq=dqkv[:, : Hq * d], dk=dqkv[:, Hq * d:(Hq + Hkv) * d], dv=dqkv[:, (Hq + Hkv) * d:])
+        g = dqkv.view(B, S, Hq + 2 * Hkv, d).permute(0, 2, 1, 3)
+        tag = f"B{B} Hq{Hq} Hkv{Hkv} S{S} causal{int(causal)} pad={pad} rope{int(use_rope)}"
+        ok &= report(f"dq {tag}", g[:, :Hq], qp.grad, 2e-2)
+        ok &= report("   dk", g[:, Hq:Hq + Hkv], kp.grad, 2e-2)
+        ok &= report("   dv", g[:, Hq + Hkv:], vp.grad, 2e-2)
+    return ok
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", default=None)

@@ -112,9 +112,17 @@ def lib() -> ctypes.CDLL:
     for name, (ret, args) in FUNCS.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = _restype(ret)
-        fn.argtypes = [ctypes.c_void_p if "*" in a else _CTYPES[a.split()[0]] for a in args]
+        fn.argtypes = [(ctypes.c_char_p if "char" in a else ctypes.c_void_p) if "*" in a else _CTYPES[a.split()[0]]
+                       for a in args]
     if L.vy_version() != CONSTS["VY_ABI_VERSION"]:
         raise VyomError("libvyom_b200.so ABI version does not match include/vyom_b200.h")
+    for sname, cls in STRUCTS.items():
+        have = L.vy_abi_sizeof(sname.encode())
+        if have != ctypes.sizeof(cls):
+            raise VyomError(
+                f"libvyom_b200.so is stale: sizeof({sname}) is {have} in the library but {ctypes.sizeof(cls)} in "
+                "include/vyom_b200.h — rebuild with `make -C vyomai_b200/csrc`"
+            )
     _lib = L
     return L
 

@@ -1,0 +1,296 @@
+"""Backward passes of the fused blocks (training path).
+
+Every gradient below is a sequence of C-ABI kernel calls:
+  * input gradients  : vy_gemm with the weight read MN-major (no transposed copy), residual
+                       gradients folded in through the epilogue's addend / addend2;
+  * weight gradients : vy_gemm with BOTH operands MN-major (dW = dY^T X straight from row-major dY, X);
+  * bias gradients   : vy_colsum;   LayerNorm: vy_add_layernorm_bwd;   GELU': dgrad epilogue / vy_act_bwd;
+  * attention        : vy_attn_bwd (dq/dk/dv with RoPE undone, written into the packed dqkv);
+  * embeddings       : vy_embed_bwd scatter-add.
+torch.autograd only orders the calls and accumulates `.grad`.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from . import functional as F
+from .functional import MaskSpec
+
+
+def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, like: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """dW[out, in] = dY^T X: both operands are read MN-major from their row-major storage."""
+    return ops.gemm(dy2d.t(), x2d.t(), out_dtype=like.dtype, out_scale=scale)
+
+
+def _dgrad(dy2d: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
+    """dX = dY W: the nn.Linear weight [out, in] is the MN-major B operand."""
+    return ops.gemm(dy2d, w.t(), **kw)
+
+
+def _bgrad(dy2d: torch.Tensor, like: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if like is None:
+        return None
+    return ops.colsum(dy2d, out_dtype=like.dtype)
+
+
+class AttentionBlockFn(torch.autograd.Function):
+    """y = LN(dense(attention(x)) + x). Inputs after the non-tensor arguments: x2d, the 1 or 3
+    projection weights, their biases (if any), dense.weight, [dense.bias], ln.weight, ln.bias."""
+
+    @staticmethod
+    def forward(ctx, mod, B, S, mask: MaskSpec, rope, start_pos, x2d, *params):
+        lin = mod._packed()
+        dense, ln = mod.out.dense, mod.out.layernorm
+        w_qkv, b_qkv = F.pack_linears(lin)
+        attn, saved = F.attention_core(x2d, B, S, w_qkv, b_qkv, mod.num_attention_heads, mod._kv_heads, mask, rope,
+                                       None, False, need_lse=True, pos0=start_pos)
+        q, k, v, lse = saved
+        y, (s, mean, rstd) = F.self_output(attn, x2d, dense, ln, save=True)
+        ctx.mod, ctx.B, ctx.S, ctx.mask, ctx.rope, ctx.start_pos = mod, B, S, mask, rope, start_pos
+        ctx.n_w = len(lin)
+        ctx.has_qkv_bias = lin[0].bias is not None
+        ctx.has_dense_bias = dense.bias is not None
+        ctx.save_for_backward(x2d, q, k, v, attn, lse, s, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, q, k, v, attn, lse, s, mean, rstd = ctx.saved_tensors
+        mod, B, S, mask, rope = ctx.mod, ctx.B, ctx.S, ctx.mask, ctx.rope
+        lin = mod._packed()
+        dense, ln = mod.out.dense, mod.out.layernorm
+        w_qkv, _ = F.pack_linears(lin)
+        Hq, Hkv, d = mod.num_attention_heads, mod._kv_heads, F.HEAD_DIM
+        dy = dy.contiguous()
+        ds, dgamma, dbeta = ops.add_layernorm_bwd(dy, s, ln.weight, mean, rstd)
+        d_wo = _wgrad(ds, attn, dense.weight)
+        d_bo = _bgrad(ds, dense.bias)
+        d_attn = _dgrad(ds, dense.weight, out_dtype=torch.bfloat16)  # bf16: MMA operand of the attention backward
+        dqkv = torch.empty((B * S, (Hq + 2 * Hkv) * d), device=dy.device, dtype=x2d.dtype)
+        cos = sin = None
+        rope_pos0 = 0
+        if rope is not None:
+            cos, sin, base = rope
+            rope_pos0 = 0 if base is None else ctx.start_pos - base  # table row of the first token
+        ops.attn_bwd(q, k, v, attn, d_attn, lse, causal=mask.causal, q_pos0=mask.q_pos0, key_padding_mask=mask.key_padding,
+                     rope_cos=cos, rope_sin=sin, rope_pos0=rope_pos0, dq=dqkv[:, : Hq * d],
+                     dk=dqkv[:, Hq * d:(Hq + Hkv) * d], dv=dqkv[:, (Hq + Hkv) * d:])
+        d_wqkv = _wgrad(dqkv, x2d, w_qkv)
+        dx = _dgrad(dqkv, w_qkv, addend=ds)  # + the residual branch of LN(dense(.) + x)
+        grads = [dx]
+        r = 0
+        for l in lin:
+            n = l.weight.shape[0]
+            grads.append(d_wqkv[r:r + n])
+            r += n
+        if ctx.has_qkv_bias:
+            d_bqkv = ops.colsum(dqkv, out_dtype=lin[0].bias.dtype)
+            r = 0
+            for l in lin:
+                n = l.bias.shape[0]
+                grads.append(d_bqkv[r:r + n])
+                r += n
+        grads.append(d_wo)
+        if ctx.has_dense_bias:
+            grads.append(d_bo)
+        grads += [dgamma.to(ln.weight.dtype), dbeta.to(ln.bias.dtype)]
+        return (None, None, None, None, None, None, *grads)
+
+
+class SelfOutputFn(torch.autograd.Function):
+    """y = LN(dense(attn) + residual) (AttentionSelfOutput used stand-alone)."""
+
+    @staticmethod
+    def forward(ctx, attn2d, residual2d, w, b, gamma, beta, eps):
+        s = F._lin(attn2d, w, b, addend=residual2d)
+        y, _, mean, rstd = ops.add_layernorm(s, None, gamma, beta, eps, save_stats=True)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(attn2d, w, gamma, s, mean, rstd)
+        ctx.bdt = b.dtype if b is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        attn2d, w, gamma, s, mean, rstd = ctx.saved_tensors
+        ds, dgamma, dbeta = ops.add_layernorm_bwd(dy.contiguous(), s, gamma, mean, rstd)
+        d_w = _wgrad(ds, attn2d, w)
+        d_b = ops.colsum(ds, out_dtype=ctx.bdt) if ctx.has_bias else None
+        d_attn = _dgrad(ds, w)
+        return d_attn, ds, d_w, d_b, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None
+
+
+class FeedForwardFn(torch.autograd.Function):
+    """y = LN(W2 act(W1 h + b1) + b2 + input)."""
+
+    @staticmethod
+    def forward(ctx, act, eps, h2d, input2d, w1, b1, w2, b2, gamma, beta):
+        z = torch.empty((h2d.shape[0], w1.shape[0]), device=h2d.device, dtype=h2d.dtype)
+        a = F._lin(h2d, w1, b1, act=act, aux=z)
+        s = F._lin(a, w2, b2, addend=input2d)
+        y, _, mean, rstd = ops.add_layernorm(s, None, gamma, beta, eps, save_stats=True)
+        ctx.act = act
+        ctx.save_for_backward(h2d, w1, b1, w2, b2, gamma, z, a, s, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h2d, w1, b1, w2, b2, gamma, z, a, s, mean, rstd = ctx.saved_tensors
+        ds, dgamma, dbeta = ops.add_layernorm_bwd(dy.contiguous(), s, gamma, mean, rstd)
+        d_w2 = _wgrad(ds, a, w2)
+        d_b2 = _bgrad(ds, b2)
+        dz = _dgrad(ds, w2, act="d" + ctx.act, aux=z)  # (dS W2) * act'(z) in the dgrad epilogue
+        d_w1 = _wgrad(dz, h2d, w1)
+        d_b1 = _bgrad(dz, b1)
+        dh = _dgrad(dz, w1)
+        return None, None, dh, ds, d_w1, d_b1, d_w2, d_b2, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype)
+
+
+class LMHeadFn(torch.autograd.Function):
+    """logits = decoder(LN(gelu(dense(h))))."""
+
+    @staticmethod
+    def forward(ctx, eps, h2d, wd, bd, gamma, beta, wv, bv):
+        z = torch.empty((h2d.shape[0], wd.shape[0]), device=h2d.device, dtype=h2d.dtype)
+        a = F._lin(h2d, wd, bd, act="gelu", aux=z)
+        n, _, mean, rstd = ops.add_layernorm(a, None, gamma, beta, eps, save_stats=True)
+        V = wv.shape[0]
+        ld = (V + 7) // 8 * 8
+        buf = torch.empty((h2d.shape[0], ld), device=h2d.device, dtype=h2d.dtype)
+        logits = F._lin(n, wv, bv, out=buf[:, :V])
+        ctx.save_for_backward(h2d, wd, bd, gamma, wv, bv, z, a, n, mean, rstd)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        h2d, wd, bd, gamma, wv, bv, z, a, n, mean, rstd = ctx.saved_tensors
+        if dlogits.stride(1) != 1 or (dlogits.stride(0) * dlogits.element_size()) % 16 != 0:
+            V = dlogits.shape[1]
+            buf = torch.zeros((dlogits.shape[0], (V + 7) // 8 * 8), device=dlogits.device, dtype=dlogits.dtype)
+            buf[:, :V].copy_(dlogits)
+            dlogits = buf[:, :V]
+        d_wv = _wgrad(dlogits, n, wv)
+        d_bv = _bgrad(dlogits, bv)
+        dn = _dgrad(dlogits, wv)
+        da, dgamma, dbeta = ops.add_layernorm_bwd(dn, a, gamma, mean, rstd)
+        dz = ops.act_bwd(da, z, "gelu")
+        d_wd = _wgrad(dz, h2d, wd)
+        d_bd = _bgrad(dz, bd)
+        dh = _dgrad(dz, wd)
+        return None, dh, d_wd, d_bd, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), d_wv, d_bv
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """mean token cross-entropy over rows whose label != ignore_index. The backward recomputes the
+    softmax and OVERWRITES the logits buffer with d loss / d logits (the buffer is dead by then), so no
+    second [rows, V] tensor is ever allocated."""
+
+    @staticmethod
+    def forward(ctx, logits2d, labels, ignore_index):
+        labels = labels.contiguous()
+        loss_rows = ops.softmax_xent(logits2d, labels, ignore_index=ignore_index, write_grad=False)
+        n_valid = (labels != ignore_index).sum().clamp(min=1).to(torch.float32)
+        ctx.save_for_backward(logits2d, labels, n_valid)
+        ctx.ignore_index = ignore_index
+        return loss_rows.sum() / n_valid
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits2d, labels, n_valid = ctx.saved_tensors
+        scale = (gout.to(torch.float32) / n_valid).reshape(1).contiguous()
+        ops.softmax_xent(logits2d, labels, ignore_index=ctx.ignore_index, grad_scale_ptr=scale, write_grad=True)
+        return logits2d, None, None
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """F.cross_entropy(logits.view(-1, V), labels.view(-1), ignore_index=...) on the fused kernel. `logits`
+    must be the (possibly row-padded) tensor returned by the LM head; it is consumed by backward."""
+    V = logits.shape[-1]
+    if logits.dim() == 3:
+        B, S, _ = logits.shape
+        if logits.stride(2) != 1 or logits.stride(0) != S * logits.stride(1):
+            raise ValueError("cross_entropy: logits must be the LM head's output (rows with one stride)")
+        logits2d = torch.as_strided(logits, (B * S, V), (logits.stride(1), 1), logits.storage_offset())
+    else:
+        logits2d = logits
+    return CrossEntropyFn.apply(logits2d, labels.reshape(-1), ignore_index)
+
+
+class EmbedFn(torch.autograd.Function):
+    """hidden rows = table[ids] (+ pos rows), optionally with one extra leading row per sequence taken
+    from `extra` (the captioner's image vector, models/multimodel.py:163-166)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, pos_table, pos_row_off, tokens_per_seq, extra):
+        B = ids.numel() // tokens_per_seq
+        e = 0 if extra is None else 1
+        seq = tokens_per_seq + e
+        out = torch.empty((B * seq, table.shape[1]), device=table.device, dtype=table.dtype)
+        idsf = ids.reshape(-1).contiguous()
+        ops.embed(idsf, table, out=out, tokens_per_seq=tokens_per_seq, out_group_stride=seq, out_row_off=e, pos=pos_table,
+                  pos_row_off=pos_row_off + e)
+        if extra is not None:
+            ops.embed(None, extra, out=out, rows=B, tokens_per_seq=1, out_group_stride=seq, out_row_off=0, pos=pos_table,
+                      pos_row_off=pos_row_off)
+        ctx.save_for_backward(idsf, table, pos_table if pos_table is not None else table.new_empty(0))
+        ctx.has_pos = pos_table is not None
+        ctx.args = (pos_row_off, tokens_per_seq, e, seq, B)
+        ctx.extra_shape = None if extra is None else (extra.shape, extra.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        idsf, table, pos_table = ctx.saved_tensors
+        pos_row_off, tps, e, seq, B = ctx.args
+        dout = dout.contiguous()
+        H = table.shape[1]
+        d_table = d_pos = d_extra = None
+        need_pos = ctx.has_pos and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            d_table = torch.zeros_like(table)
+        if need_pos:
+            d_pos = torch.zeros_like(pos_table)
+        if d_table is not None or d_pos is not None:
+            ops.embed_bwd(idsf, dout, rows=idsf.numel(), H=H, tokens_per_seq=tps, out_group_stride=seq, out_row_off=e,
+                          dtable=d_table, dpos=d_pos, pos_row_off=pos_row_off + e)
+        if e:
+            if d_pos is not None:  # the extra row's position gradient
+                ops.embed_bwd(None, dout, rows=B, H=H, tokens_per_seq=1, out_group_stride=seq, out_row_off=0,
+                              dtable=None, dpos=d_pos, pos_row_off=pos_row_off)
+            if ctx.needs_input_grad[5]:
+                shape, dt = ctx.extra_shape
+                d_extra = torch.empty(shape, device=dout.device, dtype=dout.dtype)
+                ops.embed(None, dout, out=d_extra, rows=B, tokens_per_seq=1, out_group_stride=1, out_row_off=0,
+                          src_row_stride=seq * dout.stride(0))
+                d_extra = d_extra.to(dt)
+        return None, d_table, d_pos, None, None, d_extra
+
+
+class VitStemFn(torch.autograd.Function):
+    """hidden = 2 * (cat(cls, conv(pixels)) + pos) (quirk Q1); gradients for the conv weight / bias,
+    cls_token and the position table (pixels get none — they are data)."""
+
+    @staticmethod
+    def forward(ctx, mod, pixels, w4, bias, cls, pos):
+        from .autograd import vit_stem
+        hidden, patches = vit_stem(mod, pixels)
+        ctx.mod = mod
+        ctx.B = pixels.shape[0]
+        ctx.save_for_backward(patches, w4, bias, cls, pos)
+        return hidden
+
+    @staticmethod
+    def backward(ctx, dh):
+        patches, w4, bias, cls, pos = ctx.saved_tensors
+        mod, B = ctx.mod, ctx.B
+        nP, H = mod.num_patches, w4.shape[0]
+        dh = dh.contiguous()
+        dh3 = dh.view(B, nP + 1, H)
+        dp = ops.cast4d(dh3[:, 1:, :].unsqueeze(0), dh.dtype).view(B * nP, H)  # patch rows, contiguous
+        d_w = _wgrad(dp, patches, w4, scale=2.0).view(w4.shape)
+        d_b = ops.colsum(dp, out_dtype=bias.dtype, scale=2.0) if bias is not None else None
+        d_pos = ops.colsum(dh.view(B, (nP + 1) * H), out_dtype=pos.dtype, scale=2.0).view(pos.shape)
+        d_cls = d_pos.view(nP + 1, H)[0].to(cls.dtype).view(cls.shape).clone()
+        return None, None, d_w, d_b, d_cls, d_pos

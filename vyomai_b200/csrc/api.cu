@@ -151,6 +151,24 @@ const char* vy_last_error(void) { return vy::g_err; }
 
 int64_t vy_launch_count(void) { return vy::g_launches.load(); }
 
+int vy_abi_sizeof(const char* name) {
+  if (!name) return -1;
+#define VY_SZ(T) if (strcmp(name, #T) == 0) return static_cast<int>(sizeof(T))
+  VY_SZ(VyGemm);
+  VY_SZ(VyNorm);
+  VY_SZ(VyAttn);
+  VY_SZ(VyAttnBwd);
+  VY_SZ(VyDecode);
+  VY_SZ(VyEmbed);
+  VY_SZ(VyPatchify);
+  VY_SZ(VyCast4d);
+  VY_SZ(VyXent);
+  VY_SZ(VyAdamW);
+  VY_SZ(VyRope);
+#undef VY_SZ
+  return -1;
+}
+
 int vy_device_ok(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

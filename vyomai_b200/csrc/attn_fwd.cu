@@ -24,7 +24,9 @@ constexpr int AT_D = 64;
 constexpr int AT_TILE = AT_BM * AT_D * 2;        // 16 KB: one [128 x 64] bf16 tile
 constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;    // 32 KB
 constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + 2 * AT_TILE /*V*/ + AT_P_BYTES + 256;
-constexpr float AT_MASKED = -1.0e30f;  // finite: emulates "+ finfo.min" of the reference masks
+// finite, and small enough that lse = masked + log2(n) keeps ~1e-3 absolute precision in fp32, so a
+// fully masked row is the uniform mean in forward AND backward (quirk Q4). exp2(masked - real) == 0.
+constexpr float AT_MASKED = -30000.0f;
 
 struct AttnDev {
   int B, Hq, Hkv, Sq, Skv, n_rep;

@@ -1,0 +1,504 @@
+// Bandwidth-bound helpers around the tensor-core kernels: embedding gather / scatter-add,
+// patch extraction, greedy argmax, column sums (bias gradients), strided casts, fused
+// softmax-cross-entropy, fused AdamW with global-norm clipping. All vectorised to 16-byte
+// accesses where the layout allows; grid sizes are multiples of the SM count.
+#include "vy_common.cuh"
+#include "vy_ptx.cuh"
+
+namespace vy {
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define VY_NEED_DEVICE(who)                                             \
+  do {                                                                  \
+    if (!vy_device_ok()) {                                              \
+      set_error("%s: no sm_100 device (there is no CPU fallback)", who); \
+      return VY_ERR_NO_DEVICE;                                          \
+    }                                                                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// rows gather (+ positional add, + scale, + row remap). One warp per output row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(int rows, int H, const long long* __restrict__ ids, const void* __restrict__ src,
+                 long long ld_src, int dt, int vocab, int tokens_per_seq, int out_group_stride,
+                 int out_row_off, const void* __restrict__ pos, int pos_row_off, float out_scale,
+                 void* __restrict__ out, long long ld_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = H >> 3;
+  for (int r = warp; r < rows; r += nwarps) {
+    long long srow = r;
+    if (ids) {
+      srow = ids[r];
+      if (srow < 0 || srow >= vocab) srow = 0;  // torch would raise; keep the kernel memory-safe
+    }
+    const int l = r % tokens_per_seq;
+    const long long orow = static_cast<long long>(r / tokens_per_seq) * out_group_stride + l + out_row_off;
+    for (int vi = lane; vi < nvec; vi += 32) {
+      float v[8];
+      ld8_as_float(src, dt, srow * ld_src + vi * 8, v);
+      if (pos) {
+        float p[8];
+        ld8_as_float(pos, dt, static_cast<long long>(pos_row_off + l) * H + vi * 8, p);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += p[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= out_scale;
+      st8_from_float(out, dt, orow * ld_out + vi * 8, v);
+    }
+  }
+}
+
+// scatter-add of output-row gradients into the embedding table / position table (fp32 atomics
+// for fp32 tables, packed bf16x2 atomics for bf16 tables).
+__device__ __forceinline__ void atomic_add_elem2(void* base, int dt, long long idx, float a, float b) {
+  if (dt == VY_BF16) {
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(base) + idx),
+              __floats2bfloat162_rn(a, b));
+  } else {
+    float* p = reinterpret_cast<float*>(base) + idx;
+    atomicAdd(p, a);
+    atomicAdd(p + 1, b);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(int rows, int H, const long long* __restrict__ ids, int vocab, int tokens_per_seq,
+                 int out_group_stride, int out_row_off, int pos_row_off, float scale,
+                 const void* __restrict__ dout, long long ld_dout, int dt, void* __restrict__ dtable,
+                 long long ld_table, void* __restrict__ dpos) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = H >> 3;
+  for (int r = warp; r < rows; r += nwarps) {
+    long long srow = ids ? ids[r] : r;
+    if (srow < 0 || srow >= vocab) continue;
+    const int l = r % tokens_per_seq;
+    const long long orow = static_cast<long long>(r / tokens_per_seq) * out_group_stride + l + out_row_off;
+    for (int vi = lane; vi < nvec; vi += 32) {
+      float v[8];
+      ld8_as_float(dout, dt, orow * ld_dout + vi * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        if (dtable) atomic_add_elem2(dtable, dt, srow * ld_table + vi * 8 + j, v[j] * scale, v[j + 1] * scale);
+        if (dpos) atomic_add_elem2(dpos, dt, static_cast<long long>(pos_row_off + l) * H + vi * 8 + j, v[j] * scale, v[j + 1] * scale);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// patch extraction: NCHW pixels -> [B * nP, C * p * p] rows (c, i, j fastest = j), any dtype pair
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __restrict__ px, int in_dt,
+                void* __restrict__ out, int out_dt) {
+  const int gw = Ww / pw, gh = Hh / ph;
+  const int K = C * ph * pw;
+  const long long total = static_cast<long long>(B) * gh * gw * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kk = static_cast<int>(i % K);
+    const long long prow = i / K;
+    const int s = static_cast<int>(prow % gw);
+    const int r = static_cast<int>((prow / gw) % gh);
+    const int b = static_cast<int>(prow / (static_cast<long long>(gw) * gh));
+    const int j = kk % pw, ii = (kk / pw) % ph, c = kk / (pw * ph);
+    const long long src = ((static_cast<long long>(b) * C + c) * Hh + (r * ph + ii)) * Ww + (s * pw + j);
+    st_from_float(out, out_dt, i, ld_as_float(px, in_dt, src));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// greedy next-token: argmax over the vocabulary, first index on ties (torch.topk(k=1) rule used
+// by models/decoder.py:489-496 and generation_utils.py:179-189). One CTA per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(int rows, int V, const void* __restrict__ x, long long ld, int dt, long long* __restrict__ out) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  const int r = blockIdx.x;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float v = ld_as_float(x, dt, static_cast<long long>(r) * ld + c);
+    if (v > best || (v == best && c < bi)) {
+      best = v;
+      bi = c;
+    }
+  }
+  if (bi == 0x7fffffff && threadIdx.x == 0) bi = 0;  // all -inf / NaN row: fall back to index 0
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (v2 > best || (v2 == best && i2 < bi)) {
+      best = v2;
+      bi = i2;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_v[threadIdx.x >> 5] = best;
+    s_i[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) {
+        best = s_v[w];
+        bi = s_i[w];
+      }
+    out[r] = bi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums (bias gradients): stage 1 partial sums over row chunks, stage 2 final reduce
+// ------------------------------------------------------------------------------------------
+constexpr int CS_CHUNKS = 64;
+__global__ void __launch_bounds__(128)
+colsum_partial_kernel(int R, int Cn, const void* __restrict__ x, long long ld, int dt, float* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y;
+  const int per = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = chunk * per, r1 = min(R, r0 + per);
+  if (c >= Cn) return;
+  float a = 0.f;
+  for (int r = r0; r < r1; ++r) a += ld_as_float(x, dt, static_cast<long long>(r) * ld + c);
+  part[static_cast<long long>(chunk) * Cn + c] = a;
+}
+__global__ void __launch_bounds__(128)
+colsum_final_kernel(int Cn, int chunks, const float* __restrict__ part, void* __restrict__ out, int out_dt, int accumulate,
+                    float scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cn) return;
+  float a = 0.f;
+  for (int k = 0; k < chunks; ++k) a += part[static_cast<long long>(k) * Cn + c];
+  a *= scale;
+  if (accumulate) a += ld_as_float(out, out_dt, c);
+  st_from_float(out, out_dt, c, a);
+}
+
+// ------------------------------------------------------------------------------------------
+// strided 4-D cast/copy (inner dim contiguous), e.g. fp32 kv-cache prefix -> bf16 operands
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cast4d_kernel(int n0, int n1, int n2, int n3, const void* __restrict__ src, int sdt, long long s0, long long s1,
+              long long s2, void* __restrict__ dst, int ddt, long long d0, long long d1, long long d2) {
+  const long long total = static_cast<long long>(n0) * n1 * n2 * n3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i3 = static_cast<int>(i % n3);
+    long long t = i / n3;
+    const int i2 = static_cast<int>(t % n2);
+    t /= n2;
+    const int i1 = static_cast<int>(t % n1);
+    const int i0 = static_cast<int>(t / n1);
+    st_from_float(dst, ddt, i0 * d0 + i1 * d1 + i2 * d2 + i3, ld_as_float(src, sdt, i0 * s0 + i1 * s1 + i2 * s2 + i3));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused softmax cross-entropy: per row loss (fp32) and, in place, dlogits = (softmax - onehot) *
+// grad_scale for rows whose label != ignore_index (0 elsewhere). One CTA per row, two passes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+xent_kernel(int rows, int V, void* __restrict__ logits, long long ld, int dt, const long long* __restrict__ labels,
+            long long ignore_index, const float* __restrict__ grad_scale_ptr, float grad_scale,
+            float* __restrict__ loss_rows, int write_grad) {
+  __shared__ float s_red[8];
+  const int r = blockIdx.x;
+  const long long base = static_cast<long long>(r) * ld;
+  const long long lab = labels[r];
+  const bool active = lab != ignore_index && lab >= 0 && lab < V;
+  if (!active) {
+    if (threadIdx.x == 0 && loss_rows) loss_rows[r] = 0.f;
+    if (write_grad)
+      for (int c = threadIdx.x; c < V; c += blockDim.x) st_from_float(logits, dt, base + c, 0.f);
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, ld_as_float(logits, dt, base + c));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) sum += __expf(ld_as_float(logits, dt, base + c) - mx);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += s_red[w];
+  const float lse = mx + __logf(sum);
+  if (threadIdx.x == 0 && loss_rows) loss_rows[r] = lse - ld_as_float(logits, dt, base + lab);
+  if (write_grad) {
+    const float gs = grad_scale_ptr ? *grad_scale_ptr * grad_scale : grad_scale;
+    const float inv = 1.f / sum;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) {
+      const float p = __expf(ld_as_float(logits, dt, base + c) - mx) * inv;
+      st_from_float(logits, dt, base + c, (p - (c == lab ? 1.f : 0.f)) * gs);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// sum of squares of a flat gradient buffer -> one fp32 (atomic per CTA), then AdamW that reads the
+// clip coefficient from device memory (no host sync): g' = g * min(1, max_norm / (norm + 1e-6)).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sqnorm_kernel(long long n, const void* __restrict__ g, int dt, float* __restrict__ out) {
+  __shared__ float s_red[8];
+  float a = 0.f;
+  const long long nvec = n >> 3;
+  for (long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi < nvec;
+       vi += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    ld8_as_float(g, dt, vi * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += v[j] * v[j];
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (nvec << 3) + threadIdx.x; i < n; i += blockDim.x) {
+      const float v = ld_as_float(g, dt, i);
+      a += v * v;
+    }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(long long n, void* __restrict__ p, int p_dt, const void* __restrict__ g, int g_dt,
+             float* __restrict__ m, float* __restrict__ v, float* __restrict__ master, float lr, float beta1,
+             float beta2, float eps, float wd, float bc1, float bc2, const float* __restrict__ sqnorm,
+             float max_norm, float grad_div) {
+  float clip = 1.f / grad_div;
+  if (sqnorm && max_norm > 0.f) {
+    const float norm = sqrtf(*sqnorm) / grad_div;
+    clip *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = ld_as_float(g, g_dt, i) * clip;
+    float w = master ? master[i] : ld_as_float(p, p_dt, i);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    w = w * (1.f - lr * wd) - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    if (master) master[i] = w;
+    st_from_float(p, p_dt, i, w);
+  }
+}
+
+// stand-alone half-split RoPE: one warp per (b, h, l) row, lane j <-> pair (j, j + 32)
+__global__ void __launch_bounds__(256)
+rope_kernel(int B, int H, int S, const void* __restrict__ x, long long xsb, long long xsh, long long xsl, int dt,
+            const float* __restrict__ cs, const float* __restrict__ sn, int pos0, int inverse, void* __restrict__ out,
+            long long osb, long long osh, long long osl) {
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long rows = static_cast<long long>(B) * H * S;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const int l = static_cast<int>(r % S);
+    const int h = static_cast<int>((r / S) % H);
+    const int b = static_cast<int>(r / (static_cast<long long>(S) * H));
+    const long long xi = b * xsb + h * xsh + l * xsl, oi = b * osb + h * osh + l * osl;
+    const float a = ld_as_float(x, dt, xi + lane), bb = ld_as_float(x, dt, xi + lane + 32);
+    const float c = cs[static_cast<long long>(pos0 + l) * 32 + lane];
+    float s = sn[static_cast<long long>(pos0 + l) * 32 + lane];
+    if (inverse) s = -s;
+    st_from_float(out, dt, oi + lane, a * c - bb * s);
+    st_from_float(out, dt, oi + lane + 32, bb * c + a * s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(long long n, const void* __restrict__ dy, const void* __restrict__ z, int dt, int act, void* __restrict__ out) {
+  const long long nvec = n >> 3;
+  for (long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi < nvec;
+       vi += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float g[8], zz[8];
+    ld8_as_float(dy, dt, vi * 8, g);
+    ld8_as_float(z, dt, vi * 8, zz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= (act == VY_ACT_GELU_TANH ? dgelu_tanh(zz[j]) : dgelu_erf(zz[j]));
+    st8_from_float(out, dt, vi * 8, g);
+  }
+}
+
+static int ew_grid(long long work_items, int per_block) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace vy
+
+using namespace vy;
+
+extern "C" int vy_embed_fwd(const VyEmbed* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_embed_fwd: null params");
+  VY_NEED_DEVICE("vy_embed_fwd");
+  VY_CHECK_ARG(p->rows > 0 && p->H > 0 && p->H % 8 == 0, "vy_embed_fwd: bad shape rows=%d H=%d", p->rows, p->H);
+  VY_CHECK_ARG(p->src && p->out && dtype_ok(p->dtype), "vy_embed_fwd: null pointer / bad dtype");
+  VY_CHECK_ARG(aligned16(p->src) && aligned16(p->out) && aligned16(p->pos) && (p->ld_src * (long long)dtype_size(p->dtype)) % 16 == 0 &&
+                   (p->ld_out * (long long)dtype_size(p->dtype)) % 16 == 0,
+               "vy_embed_fwd: 16-byte alignment required");
+  const int tps = p->tokens_per_seq > 0 ? p->tokens_per_seq : p->rows;
+  const int ogs = p->out_group_stride > 0 ? p->out_group_stride : tps;
+  embed_fwd_kernel<<<ew_grid(p->rows, 8), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+      p->rows, p->H, reinterpret_cast<const long long*>(p->ids), p->src, p->ld_src, p->dtype, p->vocab, tps, ogs,
+      p->out_row_off, p->pos, p->pos_row_off, p->out_scale == 0.f ? 1.f : p->out_scale, p->out, p->ld_out);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_embed_bwd(const VyEmbed* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_embed_bwd: null params");
+  VY_NEED_DEVICE("vy_embed_bwd");
+  VY_CHECK_ARG(p->rows > 0 && p->H > 0 && p->H % 8 == 0, "vy_embed_bwd: bad shape");
+  VY_CHECK_ARG(p->dout && (p->dtable || p->dpos) && dtype_ok(p->dtype), "vy_embed_bwd: null pointer / bad dtype");
+  const int tps = p->tokens_per_seq > 0 ? p->tokens_per_seq : p->rows;
+  const int ogs = p->out_group_stride > 0 ? p->out_group_stride : tps;
+  embed_bwd_kernel<<<ew_grid(p->rows, 8), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+      p->rows, p->H, reinterpret_cast<const long long*>(p->ids), p->vocab, tps, ogs, p->out_row_off, p->pos_row_off,
+      p->out_scale == 0.f ? 1.f : p->out_scale, p->dout, p->ld_out, p->dtype, p->dtable, p->ld_src, p->dpos);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_patchify(const VyPatchify* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_patchify: null params");
+  VY_NEED_DEVICE("vy_patchify");
+  VY_CHECK_ARG(p->B > 0 && p->C > 0 && p->patch_h > 0 && p->patch_w > 0 && p->H % p->patch_h == 0 && p->W % p->patch_w == 0,
+               "vy_patchify: image dimensions must be divisible by the patch size");
+  VY_CHECK_ARG(p->pixels && p->out && dtype_ok(p->in_dtype) && dtype_ok(p->out_dtype), "vy_patchify: null pointer / bad dtype");
+  const long long total = static_cast<long long>(p->B) * p->C * p->H * p->W;
+  patchify_kernel<<<ew_grid(total, 1024), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+      p->B, p->C, p->H, p->W, p->patch_h, p->patch_w, p->pixels, p->in_dtype, p->out, p->out_dtype);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_argmax_rows(int rows, int V, const void* x, int64_t ld, int dtype, int64_t* out, void* stream) {
+  VY_NEED_DEVICE("vy_argmax_rows");
+  VY_CHECK_ARG(rows > 0 && V > 0 && x && out && dtype_ok(dtype), "vy_argmax_rows: bad arguments");
+  argmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, V, x, ld, dtype, reinterpret_cast<long long*>(out));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_colsum(int rows, int cols, const void* x, int64_t ld, int dtype, void* out, int out_dtype,
+                         int accumulate, float scale, float* workspace, void* stream) {
+  VY_NEED_DEVICE("vy_colsum");
+  VY_CHECK_ARG(rows > 0 && cols > 0 && x && out && workspace && dtype_ok(dtype) && dtype_ok(out_dtype), "vy_colsum: bad arguments");
+  int chunks = (rows + 255) / 256;
+  if (chunks > CS_CHUNKS) chunks = CS_CHUNKS;
+  dim3 grid((cols + 127) / 128, chunks);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  colsum_partial_kernel<<<grid, 128, 0, st>>>(rows, cols, x, ld, dtype, workspace);
+  VY_LAUNCH_OK();
+  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, st>>>(cols, chunks, workspace, out, out_dtype, accumulate,
+                                                           scale == 0.f ? 1.f : scale);
+  VY_LAUNCH_OK();
+  count_launch(2);
+  return VY_OK;
+}
+
+extern "C" int vy_colsum_workspace_floats(int cols) { return CS_CHUNKS * cols; }
+
+extern "C" int vy_cast4d(const VyCast4d* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_cast4d: null params");
+  VY_NEED_DEVICE("vy_cast4d");
+  VY_CHECK_ARG(p->n0 > 0 && p->n1 > 0 && p->n2 > 0 && p->n3 > 0 && p->src && p->dst && dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype),
+               "vy_cast4d: bad arguments");
+  const long long total = static_cast<long long>(p->n0) * p->n1 * p->n2 * p->n3;
+  cast4d_kernel<<<ew_grid(total, 1024), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+      p->n0, p->n1, p->n2, p->n3, p->src, p->src_dtype, p->s0, p->s1, p->s2, p->dst, p->dst_dtype, p->d0, p->d1, p->d2);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_softmax_xent(const VyXent* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_softmax_xent: null params");
+  VY_NEED_DEVICE("vy_softmax_xent");
+  VY_CHECK_ARG(p->rows > 0 && p->V > 0 && p->logits && p->labels && dtype_ok(p->dtype), "vy_softmax_xent: bad arguments");
+  xent_kernel<<<p->rows, 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+      p->rows, p->V, p->logits, p->ld, p->dtype, reinterpret_cast<const long long*>(p->labels), p->ignore_index,
+      p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->write_grad);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_sqnorm(int64_t n, const void* g, int dtype, float* out, void* stream) {
+  VY_NEED_DEVICE("vy_sqnorm");
+  VY_CHECK_ARG(n > 0 && g && out && dtype_ok(dtype) && aligned16(g), "vy_sqnorm: bad arguments");
+  sqnorm_kernel<<<ew_grid(n, 8 * 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, g, dtype, out);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_adamw(const VyAdamW* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_adamw: null params");
+  VY_NEED_DEVICE("vy_adamw");
+  VY_CHECK_ARG(p->n > 0 && p->param && p->grad && p->exp_avg && p->exp_avg_sq && dtype_ok(p->param_dtype) && dtype_ok(p->grad_dtype),
+               "vy_adamw: bad arguments");
+  VY_CHECK_ARG(p->step >= 1, "vy_adamw: step must be >= 1");
+  const float bc1 = 1.f - powf(p->beta1, static_cast<float>(p->step));
+  const float bc2 = 1.f - powf(p->beta2, static_cast<float>(p->step));
+  adamw_kernel<<<ew_grid(p->n, 1024), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+      p->n, p->param, p->param_dtype, p->grad, p->grad_dtype, p->exp_avg, p->exp_avg_sq, p->master, p->lr, p->beta1,
+      p->beta2, p->eps, p->weight_decay, bc1, bc2, p->grad_sqnorm, p->max_grad_norm, p->grad_div == 0.f ? 1.f : p->grad_div);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_rope_apply(const VyRope* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_rope_apply: null params");
+  VY_NEED_DEVICE("vy_rope_apply");
+  VY_CHECK_ARG(p->head_dim == 64, "vy_rope_apply: head_dim must be 64 (got %d)", p->head_dim);
+  VY_CHECK_ARG(p->B > 0 && p->H > 0 && p->S > 0 && p->x && p->out && p->cos && p->sin && dtype_ok(p->dtype), "vy_rope_apply: bad arguments");
+  const long long rows = static_cast<long long>(p->B) * p->H * p->S;
+  rope_kernel<<<ew_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+      p->B, p->H, p->S, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_act_bwd(int64_t n, const void* dy, const void* z, int dtype, int act, void* out, void* stream) {
+  VY_NEED_DEVICE("vy_act_bwd");
+  VY_CHECK_ARG(n > 0 && n % 8 == 0 && dy && z && out && dtype_ok(dtype) && aligned16(dy) && aligned16(z) && aligned16(out),
+               "vy_act_bwd: bad arguments (n must be a multiple of 8, pointers 16-byte aligned)");
+  VY_CHECK_ARG(act == VY_ACT_GELU_ERF || act == VY_ACT_GELU_TANH, "vy_act_bwd: unsupported activation %d", act);
+  act_bwd_kernel<<<ew_grid(n, 8 * 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, dy, z, dtype, act, out);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}

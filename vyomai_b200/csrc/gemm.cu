@@ -27,6 +27,9 @@ struct GemmDev {
   const void* addend;
   long long ld_addend;
   int addend_dtype, addend_row_mod, addend_row_off;
+  const void* addend2;
+  long long ld_addend2;
+  int addend2_dtype;
   void* aux;
   long long ld_aux;
   int aux_dtype;
@@ -36,7 +39,7 @@ struct GemmDev {
   int out_dtype, out_row_group, out_row_group_stride, out_row_off;
   int vec_ok;  // all row strides / bases allow 8-element vector access
   // qkv rope
-  int tokens_per_seq, start_pos, n_q_heads, n_kv_heads;
+  int tokens_per_seq, start_pos, kv_dst_pos0, n_q_heads, n_kv_heads;
   const float* rope_cos;
   const float* rope_sin;
   void* q_out;
@@ -45,6 +48,7 @@ struct GemmDev {
   long long k_sb, k_sh, k_sl;
   void* v_out;
   long long v_sb, v_sh, v_sl;
+  int kv_out_dtype;
 };
 
 template <typename TIn, int BN_>
@@ -139,6 +143,12 @@ __device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] += a[j];
         }
+        if (g.addend2) {
+          float a[8];
+          ld8_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(grow) * g.ld_addend2 + col, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] += a[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] *= scale;
         st8_from_float(g.out, g.out_dtype, orow * g.ld_out + col, x);
@@ -155,6 +165,7 @@ __device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_
           x *= apply_dact(g.act, ld_as_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + col));
         }
         if (g.addend) x += ld_as_float(g.addend, g.addend_dtype, arow * g.ld_addend + col);
+        if (g.addend2) x += ld_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(grow) * g.ld_addend2 + col);
         st_from_float(g.out, g.out_dtype, orow * g.ld_out + col, x * scale);
       }
     }
@@ -195,6 +206,7 @@ __device__ __forceinline__ void epilogue_transposed(const GemmDev& g, uint32_t t
           x *= apply_dact(g.act, ld_as_float(g.aux, g.aux_dtype, static_cast<long long>(lr) * g.ld_aux + lc));
         }
         if (g.addend) x += ld_as_float(g.addend, g.addend_dtype, remap_add_row(g, lr) * g.ld_addend + lc);
+        if (g.addend2) x += ld_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(lr) * g.ld_addend2 + lc);
         st_from_float(g.out, g.out_dtype, remap_out_row(g, lr) * g.ld_out + lc, x * scale);
       }
     }
@@ -230,18 +242,20 @@ __device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tme
     void* dst;
     long long off;
     bool rotate;
+    int dst_dt = g.kv_out_dtype;
     if (head < g.n_q_heads) {
+      dst_dt = g.out_dtype;
       dst = g.q_out;
       off = b * g.q_sb + head * g.q_sh + l * g.q_sl;
       rotate = cs != nullptr;
     } else if (head < g.n_q_heads + g.n_kv_heads) {
       dst = g.k_out;
-      off = b * g.k_sb + (head - g.n_q_heads) * g.k_sh + static_cast<long long>(pos) * g.k_sl;
+      off = b * g.k_sb + (head - g.n_q_heads) * g.k_sh + static_cast<long long>(g.kv_dst_pos0 + l) * g.k_sl;
       rotate = cs != nullptr;
     } else {
       dst = g.v_out;
       off = b * g.v_sb + (head - g.n_q_heads - g.n_kv_heads) * g.v_sh +
-            static_cast<long long>(pos) * g.v_sl;
+            static_cast<long long>(g.kv_dst_pos0 + l) * g.v_sl;
       rotate = false;
     }
 #pragma unroll
@@ -271,8 +285,8 @@ __device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tme
           o2[j] = x2[j];
         }
       }
-      st8_from_float(dst, g.out_dtype, off + q * 8, o1);
-      st8_from_float(dst, g.out_dtype, off + 32 + q * 8, o2);
+      st8_from_float(dst, dst_dt, off + q * 8, o1);
+      st8_from_float(dst, dst_dt, off + 32 + q * 8, o2);
     }
   }
 }
@@ -527,6 +541,7 @@ extern "C" int vy_gemm(const VyGemm* p) {
   g.bias = p->bias; g.bias_dtype = p->bias_dtype;
   g.addend = p->addend; g.ld_addend = p->ld_addend; g.addend_dtype = p->addend_dtype;
   g.addend_row_mod = p->addend_row_mod; g.addend_row_off = p->addend_row_off;
+  g.addend2 = p->addend2; g.ld_addend2 = p->ld_addend2; g.addend2_dtype = p->addend2_dtype;
   g.aux = p->aux; g.ld_aux = p->ld_aux; g.aux_dtype = p->aux_dtype;
   g.out_scale = p->out_scale;
   g.out = p->out; g.ld_out = p->ld_out; g.out_dtype = p->out_dtype;
@@ -540,6 +555,7 @@ extern "C" int vy_gemm(const VyGemm* p) {
       VY_CHECK_ARG(p->aux != nullptr, "vy_gemm: DGELU epilogue needs aux (saved pre-activation)");
     if (p->bias) VY_CHECK_ARG(dtype_ok(p->bias_dtype), "vy_gemm: bad bias_dtype");
     if (p->addend) VY_CHECK_ARG(dtype_ok(p->addend_dtype), "vy_gemm: bad addend_dtype");
+    if (p->addend2) VY_CHECK_ARG(dtype_ok(p->addend2_dtype), "vy_gemm: bad addend2_dtype");
     if (p->aux) VY_CHECK_ARG(dtype_ok(p->aux_dtype), "vy_gemm: bad aux_dtype");
     auto vec = [](const void* ptr, long long ld, int dt) {
       if (!ptr) return true;
@@ -547,28 +563,33 @@ extern "C" int vy_gemm(const VyGemm* p) {
     };
     // fp32 vector access moves 8 floats = 32 B as two 16-B halves: 16-B alignment suffices.
     g.vec_ok = vec(p->out, p->ld_out, p->out_dtype) && vec(p->aux, p->ld_aux, p->aux_dtype) &&
-               vec(p->addend, p->ld_addend, p->addend_dtype);
+               vec(p->addend, p->ld_addend, p->addend_dtype) && vec(p->addend2, p->ld_addend2, p->addend2_dtype);
   } else if (p->epi == VY_EPI_QKV_ROPE) {
     VY_CHECK_ARG(!p->transposed_out, "vy_gemm: QKV_ROPE epilogue cannot be transposed");
     VY_CHECK_ARG(p->head_dim == 64, "vy_gemm: QKV_ROPE epilogue supports head_dim 64 (got %d)", p->head_dim);
     VY_CHECK_ARG(p->N == (p->n_q_heads + 2 * p->n_kv_heads) * 64, "vy_gemm: QKV_ROPE N mismatch");
     VY_CHECK_ARG(p->tokens_per_seq > 0 && p->M % p->tokens_per_seq == 0, "vy_gemm: M %% tokens_per_seq != 0");
-    VY_CHECK_ARG(p->q_out && p->k_out && p->v_out && dtype_ok(p->out_dtype), "vy_gemm: q/k/v outputs missing");
+    VY_CHECK_ARG((p->q_out || p->n_q_heads == 0) && ((p->k_out && p->v_out) || p->n_kv_heads == 0) && dtype_ok(p->out_dtype),
+                 "vy_gemm: q/k/v outputs missing");
+    VY_CHECK_ARG(p->start_pos >= 0 && p->kv_dst_pos0 >= 0, "vy_gemm: negative position");
     VY_CHECK_ARG((p->rope_cos == nullptr) == (p->rope_sin == nullptr), "vy_gemm: rope_cos/rope_sin must both be set or NULL");
-    const long long es_o = dtype_size(p->out_dtype);
-    auto okstr = [&](const void* ptr, long long sb, long long sh, long long sl) {
+    VY_CHECK_ARG(dtype_ok(p->kv_out_dtype), "vy_gemm: bad kv_out_dtype");
+    auto okstr = [&](const void* ptr, long long sb, long long sh, long long sl, int dt) {
+      const long long es_o = dtype_size(dt);
       return aligned16(ptr) && (sb * es_o) % 16 == 0 && (sh * es_o) % 16 == 0 && (sl * es_o) % 16 == 0;
     };
-    VY_CHECK_ARG(okstr(p->q_out, p->q_sb, p->q_sh, p->q_sl) && okstr(p->k_out, p->k_sb, p->k_sh, p->k_sl) &&
-                     okstr(p->v_out, p->v_sb, p->v_sh, p->v_sl),
+    VY_CHECK_ARG(okstr(p->q_out, p->q_sb, p->q_sh, p->q_sl, p->out_dtype) &&
+                     okstr(p->k_out, p->k_sb, p->k_sh, p->k_sl, p->kv_out_dtype) &&
+                     okstr(p->v_out, p->v_sb, p->v_sh, p->v_sl, p->kv_out_dtype),
                  "vy_gemm: q/k/v strides must keep 16-byte alignment");
     if (p->bias) VY_CHECK_ARG(dtype_ok(p->bias_dtype), "vy_gemm: bad bias_dtype");
-    g.tokens_per_seq = p->tokens_per_seq; g.start_pos = p->start_pos;
+    g.tokens_per_seq = p->tokens_per_seq; g.start_pos = p->start_pos; g.kv_dst_pos0 = p->kv_dst_pos0;
     g.n_q_heads = p->n_q_heads; g.n_kv_heads = p->n_kv_heads;
     g.rope_cos = p->rope_cos; g.rope_sin = p->rope_sin;
     g.q_out = p->q_out; g.q_sb = p->q_sb; g.q_sh = p->q_sh; g.q_sl = p->q_sl;
     g.k_out = p->k_out; g.k_sb = p->k_sb; g.k_sh = p->k_sh; g.k_sl = p->k_sl;
     g.v_out = p->v_out; g.v_sb = p->v_sb; g.v_sh = p->v_sh; g.v_sl = p->v_sl;
+    g.kv_out_dtype = p->kv_out_dtype;
   } else {
     set_error("vy_gemm: unknown epilogue %d", p->epi);
     return VY_ERR_INVALID_ARG;

@@ -6,7 +6,7 @@ computes with torch ops, and nothing falls back to them.
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 
@@ -71,6 +71,7 @@ def gemm(
     addend: Optional[torch.Tensor] = None,
     addend_row_mod: int = 0,
     addend_row_off: int = 0,
+    addend2: Optional[torch.Tensor] = None,
     out: Optional[torch.Tensor] = None,
     out_dtype: Optional[torch.dtype] = None,
     out_scale: float = 1.0,
@@ -85,7 +86,7 @@ def gemm(
     swap_ab=True computes the same logical result by feeding `b` as the 128-row MMA operand and
     writing the tile transposed — the decode-time path where M (tokens) is tiny and N large.
     """
-    _need_cuda(a, b, bias, aux, addend, out)
+    _need_cuda(a, b, bias, aux, addend, addend2, out)
     M, K = a.shape
     N, Kb = b.shape
     if K != Kb:
@@ -113,6 +114,9 @@ def gemm(
         addend_dtype=_dt(addend) if addend is not None else 0,
         addend_row_mod=addend_row_mod,
         addend_row_off=addend_row_off,
+        addend2=_ptr(addend2),
+        ld_addend2=addend2.stride(0) if addend2 is not None else 0,
+        addend2_dtype=_dt(addend2) if addend2 is not None else 0,
         aux=_ptr(aux),
         ld_aux=aux.stride(0) if aux is not None else 0,
         aux_dtype=_dt(aux) if aux is not None else 0,
@@ -150,6 +154,7 @@ def qkv_rope_gemm(
     q_out: torch.Tensor,
     k_out: torch.Tensor,
     v_out: torch.Tensor,
+    kv_dst_pos0: Optional[int] = None,
 ) -> None:
     """Fused q/k/v projection: bias + in-register RoPE + "b l (h d) -> b h l d" scatter + kv-cache
     append. q_out/k_out/v_out are 4-D [B, heads, tokens, head_dim] tensors (any batch/head/token
@@ -161,8 +166,10 @@ def qkv_rope_gemm(
     a_mn, lda = _major(x, "qkv x")
     b_mn, ldb = _major(w, "qkv w")
     for t in (q_out, k_out, v_out):
-        if t.dim() != 4 or t.stride(3) != 1 or t.dtype != q_out.dtype:
-            raise _lib.VyomError("qkv_rope_gemm: outputs must be [B,h,S,d] with contiguous d and one dtype")
+        if t.dim() != 4 or t.stride(3) != 1:
+            raise _lib.VyomError("qkv_rope_gemm: outputs must be [B,h,S,d] with contiguous d")
+    if k_out.dtype != v_out.dtype:
+        raise _lib.VyomError("qkv_rope_gemm: k_out and v_out must share a dtype")
     if rope_cos is not None and (rope_cos.dtype != torch.float32 or not rope_cos.is_contiguous()):
         raise _lib.VyomError("qkv_rope_gemm: rope tables must be contiguous float32")
     _lib.call(
@@ -170,12 +177,13 @@ def qkv_rope_gemm(
         M=M, N=N, K=K, in_dtype=_dt(x), A=x.data_ptr(), lda=lda, a_mn_major=a_mn,
         B=w.data_ptr(), ldb=ldb, b_mn_major=b_mn,
         epi=C["VY_EPI_QKV_ROPE"], bias=_ptr(bias), bias_dtype=_dt(bias) if bias is not None else 0,
-        out_dtype=_dt(q_out), tokens_per_seq=tokens_per_seq, start_pos=start_pos, head_dim=head_dim,
+        out_dtype=_dt(q_out), tokens_per_seq=tokens_per_seq, start_pos=start_pos,
+        kv_dst_pos0=start_pos if kv_dst_pos0 is None else kv_dst_pos0, head_dim=head_dim,
         n_q_heads=n_q_heads, n_kv_heads=n_kv_heads, rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin),
         q_out=q_out.data_ptr(), q_sb=q_out.stride(0), q_sh=q_out.stride(1), q_sl=q_out.stride(2),
         k_out=k_out.data_ptr(), k_sb=k_out.stride(0), k_sh=k_out.stride(1), k_sl=k_out.stride(2),
         v_out=v_out.data_ptr(), v_sb=v_out.stride(0), v_sh=v_out.stride(1), v_sl=v_out.stride(2),
-        stream=_stream(),
+        kv_out_dtype=_dt(k_out), stream=_stream(),
     )
 
 
@@ -332,3 +340,176 @@ def attn_decode(
         tickets=_ptr(tk), stream=_stream(),
     )
     return out
+
+
+def cast4d(src: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Strided 4-D copy with dtype conversion (inner dim contiguous)."""
+    _need_cuda(src, out)
+    if src.dim() != 4 or src.stride(3) != 1:
+        raise _lib.VyomError("cast4d: expects a 4-D tensor with a contiguous inner dim")
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=dtype)
+    _lib.call(
+        "vy_cast4d", "VyCast4d",
+        n0=src.shape[0], n1=src.shape[1], n2=src.shape[2], n3=src.shape[3], src=src.data_ptr(), src_dtype=_dt(src),
+        s0=src.stride(0), s1=src.stride(1), s2=src.stride(2), dst=out.data_ptr(), dst_dtype=_dt(out),
+        d0=out.stride(0), d1=out.stride(1), d2=out.stride(2), stream=_stream(),
+    )
+    return out
+
+
+def embed(ids: Optional[torch.Tensor], src: torch.Tensor, *, out: torch.Tensor, tokens_per_seq: int,
+          out_group_stride: int = 0, out_row_off: int = 0, pos: Optional[torch.Tensor] = None, pos_row_off: int = 0,
+          out_scale: float = 1.0, rows: Optional[int] = None, broadcast_src: bool = False,
+          src_row_stride: Optional[int] = None) -> torch.Tensor:
+    """Row gather + positional add + scale + row remap (see vy_embed_fwd). `out` is 2-D [rows_out, H]."""
+    _need_cuda(ids, src, out, pos)
+    H = src.shape[-1]
+    n = rows if rows is not None else (ids.numel() if ids is not None else src.shape[0])
+    if ids is not None and (ids.dtype != torch.int64 or not ids.is_contiguous()):
+        raise _lib.VyomError("embed: ids must be contiguous int64")
+    if pos is not None and (pos.dtype != src.dtype or not pos.is_contiguous()):
+        raise _lib.VyomError("embed: pos must be contiguous and share the table dtype")
+    _lib.call(
+        "vy_embed_fwd", "VyEmbed",
+        rows=n, H=H, ids=_ptr(ids), src=src.data_ptr(),
+        ld_src=0 if broadcast_src else (src_row_stride if src_row_stride is not None else src.stride(-2)), dtype=_dt(src),
+        vocab=src.shape[0] if src.dim() == 2 else 1, tokens_per_seq=tokens_per_seq, out_group_stride=out_group_stride,
+        out_row_off=out_row_off, pos=_ptr(pos), pos_row_off=pos_row_off, out_scale=float(out_scale), out=out.data_ptr(),
+        ld_out=out.stride(0), stream=_stream(),
+    )
+    return out
+
+
+def embed_bwd(ids: Optional[torch.Tensor], dout: torch.Tensor, *, rows: int, H: int, tokens_per_seq: int,
+              out_group_stride: int = 0, out_row_off: int = 0, dtable: Optional[torch.Tensor] = None,
+              dpos: Optional[torch.Tensor] = None, pos_row_off: int = 0, out_scale: float = 1.0) -> None:
+    _need_cuda(ids, dout, dtable, dpos)
+    _lib.call(
+        "vy_embed_bwd", "VyEmbed",
+        rows=rows, H=H, ids=_ptr(ids), dtype=_dt(dout), vocab=dtable.shape[0] if dtable is not None else rows,
+        tokens_per_seq=tokens_per_seq, out_group_stride=out_group_stride, out_row_off=out_row_off,
+        pos_row_off=pos_row_off, out_scale=float(out_scale), ld_out=dout.stride(0), dout=dout.data_ptr(),
+        dtable=_ptr(dtable), ld_src=dtable.stride(0) if dtable is not None else 0, dpos=_ptr(dpos), stream=_stream(),
+    )
+
+
+def patchify(pixels: torch.Tensor, patch: Tuple[int, int], dtype: torch.dtype) -> torch.Tensor:
+    """NCHW pixels -> [B * nP, C*ph*pw] patch rows in `dtype`."""
+    _need_cuda(pixels)
+    if not pixels.is_contiguous():
+        raise _lib.VyomError("patchify: pixels must be contiguous NCHW")
+    B, Cc, Hh, Ww = pixels.shape
+    ph, pw = patch
+    out = torch.empty((B * (Hh // ph) * (Ww // pw), Cc * ph * pw), device=pixels.device, dtype=dtype)
+    _lib.call("vy_patchify", "VyPatchify", B=B, C=Cc, H=Hh, W=Ww, patch_h=ph, patch_w=pw, pixels=pixels.data_ptr(),
+              in_dtype=_dt(pixels), out=out.data_ptr(), out_dtype=_dt(out), stream=_stream())
+    return out
+
+
+def argmax_rows(x: torch.Tensor) -> torch.Tensor:
+    """Greedy token ids: first index of each row's maximum. x is 2-D with unit inner stride."""
+    _need_cuda(x)
+    out = torch.empty(x.shape[0], device=x.device, dtype=torch.int64)
+    _lib.check(_lib.lib().vy_argmax_rows(x.shape[0], x.shape[1], x.data_ptr(), x.stride(0), _dt(x), out.data_ptr(), _stream()),
+               "vy_argmax_rows")
+    return out
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+           accumulate: bool = False, scale: float = 1.0) -> torch.Tensor:
+    """out[c] (+)= sum_r x[r, c] (bias gradients)."""
+    _need_cuda(x, out)
+    R, Cn = x.shape
+    if out is None:
+        out = torch.empty(Cn, device=x.device, dtype=out_dtype or x.dtype)
+    L = _lib.lib()
+    ws = torch.empty(L.vy_colsum_workspace_floats(Cn), device=x.device, dtype=torch.float32)
+    _lib.check(L.vy_colsum(R, Cn, x.data_ptr(), x.stride(0), _dt(x), out.data_ptr(), _dt(out), int(accumulate),
+                           float(scale), ws.data_ptr(), _stream()), "vy_colsum")
+    return out
+
+
+def softmax_xent(logits: torch.Tensor, labels: torch.Tensor, *, ignore_index: int = -100, grad_scale: float = 1.0,
+                 grad_scale_ptr: Optional[torch.Tensor] = None, write_grad: bool = True) -> torch.Tensor:
+    """Per-row cross-entropy (fp32 [rows]); overwrites `logits` with d loss/d logits when write_grad."""
+    _need_cuda(logits, labels, grad_scale_ptr)
+    rows, V = logits.shape
+    loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    _lib.call("vy_softmax_xent", "VyXent", rows=rows, V=V, logits=logits.data_ptr(), ld=logits.stride(0), dtype=_dt(logits),
+              labels=labels.data_ptr(), ignore_index=ignore_index, grad_scale_ptr=_ptr(grad_scale_ptr),
+              grad_scale=float(grad_scale), loss_rows=loss.data_ptr(), write_grad=int(write_grad), stream=_stream())
+    return loss
+
+
+def attn_bwd(q, k, v, o, dout, lse, *, causal: bool, q_pos0: int, key_padding_mask, rope_cos, rope_sin,
+             dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, rope_pos0: int = 0) -> None:
+    """Flash-attention backward. q [B,Hq,Sq,64], k/v [B,Hkv,Skv,64] bf16; o / dout [B,Sq,Hq*64] (dout bf16);
+    dq [B*Sq, >=Hq*64], dk/dv [B*Skv, >=Hkv*64] 2-D views (typically column slices of the packed dqkv)."""
+    _need_cuda(q, k, v, o, dout, lse, key_padding_mask, rope_cos, rope_sin, dq, dk, dv)
+    B, Hq, Sq, D = q.shape
+    Hkv, Skv = k.shape[1], k.shape[2]
+    if dout.dtype != torch.bfloat16 or q.dtype != torch.bfloat16:
+        raise _lib.VyomError("attn_bwd: q/k/v/dout must be bf16")
+    o3 = o.view(B, Sq, Hq * D)
+    do3 = dout.view(B, Sq, Hq * D)
+    dsum = torch.empty((B, Hq, Sq), device=q.device, dtype=torch.float32)
+    _lib.call(
+        "vy_attn_bwd", "VyAttnBwd",
+        B=B, n_q_heads=Hq, n_kv_heads=Hkv, head_dim=D, Sq=Sq, Skv=Skv,
+        q=q.data_ptr(), q_sb=q.stride(0), q_sh=q.stride(1), q_sl=q.stride(2),
+        k=k.data_ptr(), k_sb=k.stride(0), k_sh=k.stride(1), k_sl=k.stride(2),
+        v=v.data_ptr(), v_sb=v.stride(0), v_sh=v.stride(1), v_sl=v.stride(2),
+        o=o3.data_ptr(), o_sb=o3.stride(0), o_sl=o3.stride(1), o_dtype=_dt(o3),
+        dout=do3.data_ptr(), do_sb=do3.stride(0), do_sl=do3.stride(1), lse=lse.data_ptr(), dsum=dsum.data_ptr(),
+        causal=int(causal), q_pos0=q_pos0, key_padding_mask=_ptr(key_padding_mask),
+        kpm_stride=key_padding_mask.stride(0) if key_padding_mask is not None else 0,
+        rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin), rope_pos0=rope_pos0,
+        dq=dq.data_ptr(), ld_dq=dq.stride(0), dk=dk.data_ptr(), ld_dk=dk.stride(0), dv=dv.data_ptr(), ld_dv=dv.stride(0),
+        out_dtype=_dt(dq), stream=_stream(),
+    )
+
+
+def rope_apply(x: torch.Tensor, freqs: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """Half-split RoPE of x [B,h,S,64] with the reference's angle slice freqs (1,S,32); cos/sin are
+    rounded to x.dtype first like apply_rotary_pos_emb does."""
+    _need_cuda(x)
+    f = freqs[0].to(torch.float32).cpu()
+    cos = f.cos().to(x.dtype).to(torch.float32).contiguous().to(x.device)
+    sin = f.sin().to(x.dtype).to(torch.float32).contiguous().to(x.device)
+    if x.stride(3) != 1:
+        x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    _lib.call("vy_rope_apply", "VyRope", B=x.shape[0], H=x.shape[1], S=x.shape[2], head_dim=x.shape[3], x=x.data_ptr(),
+              x_sb=x.stride(0), x_sh=x.stride(1), x_sl=x.stride(2), dtype=_dt(x), cos=cos.data_ptr(), sin=sin.data_ptr(),
+              pos0=0, inverse=int(inverse), out=out.data_ptr(), o_sb=out.stride(0), o_sh=out.stride(1), o_sl=out.stride(2),
+              stream=_stream())
+    return out
+
+
+def act_bwd(dy: torch.Tensor, z: torch.Tensor, act: str = "gelu") -> torch.Tensor:
+    """dy * act'(z), elementwise (contiguous, same dtype)."""
+    _need_cuda(dy, z)
+    if not (dy.is_contiguous() and z.is_contiguous()) or dy.dtype != z.dtype:
+        raise _lib.VyomError("act_bwd: dy and z must be contiguous and share a dtype")
+    out = torch.empty_like(dy)
+    _lib.check(_lib.lib().vy_act_bwd(dy.numel(), dy.data_ptr(), z.data_ptr(), _dt(dy), ACT[act], out.data_ptr(), _stream()),
+               "vy_act_bwd")
+    return out
+
+
+def sqnorm(g: torch.Tensor, out: torch.Tensor) -> None:
+    """out (fp32 scalar tensor, pre-zeroed) += sum(g^2)."""
+    _need_cuda(g, out)
+    _lib.check(_lib.lib().vy_sqnorm(g.numel(), g.data_ptr(), _dt(g), out.data_ptr(), _stream()), "vy_sqnorm")
+
+
+def adamw(param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay, step, master=None,
+          grad_sqnorm=None, max_grad_norm=0.0, grad_div=1.0) -> None:
+    """Fused AdamW over flat buffers (see vy_adamw)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, master, grad_sqnorm)
+    _lib.call("vy_adamw", "VyAdamW", n=param.numel(), param=param.data_ptr(), param_dtype=_dt(param), grad=grad.data_ptr(),
+              grad_dtype=_dt(grad), exp_avg=exp_avg.data_ptr(), exp_avg_sq=exp_avg_sq.data_ptr(), master=_ptr(master),
+              lr=float(lr), beta1=float(beta1), beta2=float(beta2), eps=float(eps), weight_decay=float(weight_decay),
+              step=int(step), grad_sqnorm=_ptr(grad_sqnorm), max_grad_norm=float(max_grad_norm), grad_div=float(grad_div),
+              stream=_stream())
