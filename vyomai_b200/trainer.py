@@ -1,0 +1,190 @@
+"""Data-parallel training of the captioner on the fused sm_100a path.
+
+What the reference's notebooks get from `accelerate` (DDP + AdamW + clip_grad_norm_(1.0);
+Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1 `main()`) is rebuilt B200-first:
+
+  * one process per GPU; every parameter lives in ONE flat buffer and every gradient in ONE flat
+    buffer of the same layout (q|k|v projection weights adjacent, so the packed-QKV GEMM needs no
+    repacking), which makes the optimizer a single fused kernel and the gradient exchange a
+    handful of large NCCL all-reduces over NVLink / NVSwitch instead of one per tensor;
+  * gradient all-reduce runs bucket by bucket on a side stream as soon as backward has produced a
+    bucket (post-accumulate hooks), so the transfer overlaps the remaining backward kernels;
+  * AdamW (fp32 master weights + fp32 moments, bf16 or fp32 model weights), the global-norm clip
+    and the 1/world_size mean are fused into vy_sqnorm + vy_adamw; the clip coefficient never
+    leaves the device.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import functional as F
+from . import ops
+from .autograd_train import cross_entropy
+from .layers.attention import _SelfAttentionBase
+
+
+def _param_order(model: nn.Module) -> List[nn.Parameter]:
+    """Parameters in flat-buffer order: projection weights of an attention module adjacent (then their
+    biases adjacent), everything else in module order; shared Parameters appear once."""
+    seen, order = set(), []
+
+    def add(p):
+        if p is not None and id(p) not in seen:
+            seen.add(id(p))
+            order.append(p)
+
+    for mod in model.modules():
+        if isinstance(mod, _SelfAttentionBase):
+            lin = mod._packed()
+            for l in lin:
+                add(l.weight)
+            for l in lin:
+                add(l.bias)
+    for p in model.parameters():
+        add(p)
+    return order
+
+
+class FlatParams:
+    """Re-homes every parameter (and its .grad) of `model` inside two flat buffers."""
+
+    ALIGN = 8  # elements; keeps every tensor 16-byte aligned for bf16 and fp32
+
+    def __init__(self, model: nn.Module):
+        params = _param_order(model)
+        dtypes = {p.dtype for p in params}
+        if len(dtypes) != 1:
+            raise ValueError(f"FlatParams needs one parameter dtype, got {dtypes}")
+        self.dtype = params[0].dtype
+        dev = params[0].device
+        self.params = params
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.flat = torch.zeros(off, device=dev, dtype=self.dtype)
+        self.grad = torch.zeros(off, device=dev, dtype=self.dtype)
+        for p, o in zip(params, self.offsets):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):  # re-attach in case autograd replaced a .grad
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + o * self.grad.element_size():
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+class Trainer:
+    """AdamW + clip + data-parallel all-reduce around a model built from vyomai_b200 modules."""
+
+    def __init__(self, model: nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                 max_grad_norm: float = 1.0, bucket_mb: float = 64.0, overlap: bool = True):
+        self.model = model
+        self.fp = FlatParams(model)
+        n = self.fp.numel
+        dev = self.fp.flat.device
+        self.master = self.fp.flat.to(torch.float32).clone() if self.fp.dtype != torch.float32 else None
+        self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.step_count = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.overlap = overlap and self.world > 1
+        self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # buckets: contiguous slices of the flat gradient, walked from the END (backward order)
+        per = max(1, int(bucket_mb * 1024 * 1024 / self.fp.grad.element_size()))
+        self.buckets = []
+        end = n
+        while end > 0:
+            start = max(0, end - per)
+            self.buckets.append((start, end))
+            end = start
+        self._pending: Dict[int, int] = {}
+        self._bucket_of: Dict[int, int] = {}
+        self._handles = []
+        if self.overlap:
+            self._install_hooks()
+
+    # ---- gradient exchange -------------------------------------------------------------------
+    def _install_hooks(self) -> None:
+        sizes = [0] * len(self.buckets)
+        for p, o in zip(self.fp.params, self.fp.offsets):
+            b = next(i for i, (s, e) in enumerate(self.buckets) if s <= o < e)
+            self._bucket_of[id(p)] = b
+            sizes[b] += 1
+            p.register_post_accumulate_grad_hook(self._on_grad)
+        self._bucket_size = sizes
+
+    def _on_grad(self, p: nn.Parameter) -> None:
+        b = self._bucket_of[id(p)]
+        self._pending[b] = self._pending.get(b, 0) + 1
+        if self._pending[b] == self._bucket_size[b]:
+            self._launch_bucket(b)
+
+    def _launch_bucket(self, b: int) -> None:
+        s, e = self.buckets[b]
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            dist.all_reduce(self.fp.grad[s:e], op=dist.ReduceOp.SUM)
+        self._launched.add(b)
+
+    def _finish_allreduce(self) -> None:
+        if self.world == 1:
+            return
+        if self.overlap:
+            for b in range(len(self.buckets)):
+                if b not in self._launched:  # buckets whose params got no gradient this step
+                    self._launch_bucket(b)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        else:
+            for (s, e) in self.buckets:
+                dist.all_reduce(self.fp.grad[s:e], op=dist.ReduceOp.SUM)
+
+    # ---- one optimisation step ---------------------------------------------------------------
+    def zero_grad(self) -> None:
+        self.fp.zero_grad()
+        self._pending = {}
+        self._launched = set()
+
+    def optimizer_step(self) -> None:
+        self._finish_allreduce()
+        self.step_count += 1
+        self.sqnorm.zero_()
+        ops.sqnorm(self.fp.grad, self.sqnorm)
+        ops.adamw(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
+                  beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.step_count, master=self.master,
+                  grad_sqnorm=self.sqnorm, max_grad_norm=self.max_grad_norm, grad_div=float(self.world))
+
+    def caption_step(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor,
+                     labels_full: torch.Tensor) -> torch.Tensor:
+        """One captioner training step (VisionLanguageModel): forward, shifted token cross-entropy,
+        backward, gradient all-reduce, clip, AdamW. `labels_full` is [B, S+1] aligned with the logits rows
+        (image position and the last position carry ignore_index). Returns the (local) loss tensor."""
+        self.zero_grad()
+        logits = self.model(pixel_values=pixel_values, decoder_input_ids=input_ids, decoder_attention_mask=attention_mask).logits
+        loss = cross_entropy(logits, labels_full, ignore_index=-100)
+        loss.backward()
+        self.optimizer_step()
+        return loss.detach()
+
+
+def caption_labels(input_ids: torch.Tensor, attention_mask: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """labels aligned with the captioner's logits rows: the logits have one extra leading (image)
+    position, so row t (1 <= t <= S-1) predicts text token t; pads, row 0 and row S are ignored — the
+    `loss_fn` of Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1 (shifted CE over non-pad labels)."""
+    B, S = input_ids.shape
+    full = torch.full((B, S + 1), ignore_index, dtype=torch.long, device=input_ids.device)
+    lab = input_ids.masked_fill(attention_mask == 0, ignore_index)
+    full[:, 1:S] = lab[:, 1:]
+    return full
