@@ -1,0 +1,167 @@
+"""CPU-only checks of the drop-in boundary and the host logic (no kernel is launched here):
+the C-ABI library loads and exports every symbol include/vyom_b200.h declares, the ctypes struct
+layouts generated from the header equal what a C compiler lays out, compute entry points refuse to
+run without an sm_100 device (no CPU fallback), and the host-side pieces (mask factoring, weight
+packing, flat parameter buffers, gradient-exchange buckets over gloo) behave."""
+import ctypes
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from vyomai_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib()
+    lib = L.lib()
+    assert len(L.FUNCS) >= 20
+    for name in L.FUNCS:
+        assert hasattr(lib, name), name
+    assert lib.vy_version() == L.CONSTS["VY_ABI_VERSION"]
+
+
+def test_ctypes_struct_layouts_match_a_c_compiler():
+    L = _lib()
+    names = sorted(L.STRUCTS)
+    src = '#include <stdio.h>\n#include "vyom_b200.h"\nint main(void){\n'
+    for n in names:
+        src += f'  printf("{n} %zu\\n", sizeof({n}));\n'
+    src += "  return 0;\n}\n"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "sz.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "sz")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    for n in names:
+        assert int(sizes[n]) == ctypes.sizeof(L.STRUCTS[n]), n
+        assert L.lib().vy_abi_sizeof(n.encode()) == int(sizes[n]), n
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    L = _lib()
+    assert L.lib().vy_device_ok() == 0
+    st = L.STRUCTS["VyGemm"]()
+    rc = L.lib().vy_gemm(ctypes.byref(st))
+    assert rc != 0
+    with pytest.raises(L.VyomError):
+        from vyomai_b200 import EncoderConfig, EncoderModel
+        m = EncoderModel(EncoderConfig(), "rope", "gqa")
+        m(torch.zeros(1, 4, dtype=torch.long), None)
+
+
+def test_product_package_never_imports_the_oracle():
+    import re
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vyomai_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_mask_factoring_recovers_the_reference_masks():
+    from oracle import vyom_oracle as O
+    from vyomai_b200.functional import MaskSpec
+    am = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1]])
+    enc = O.encoder_mask(am, torch.float32)
+    ms = MaskSpec.from_dense(enc, 5)
+    assert not ms.causal and torch.equal(ms.key_padding, am.to(torch.uint8))
+    for start in (0, 3):
+        am2 = torch.ones(2, start + 5, dtype=torch.long)
+        am2[0, -2:] = 0
+        dec = O.decoder_mask(2, 5, am2, start, torch.float32)
+        ms = MaskSpec.from_dense(dec, 5)
+        assert ms.causal and ms.q_pos0 == start and torch.equal(ms.key_padding, am2.to(torch.uint8))
+    weird = enc.clone().expand(2, 1, 5, 5).clone()
+    weird[0, 0, 2, 0] = torch.finfo(torch.float32).min
+    with pytest.raises(Exception):
+        MaskSpec.from_dense(weird, 5)
+
+
+def test_qkv_packing_keeps_parameter_identity_and_values():
+    from vyomai_b200.functional import pack_linears
+    q, k, v = torch.nn.Linear(64, 64), torch.nn.Linear(64, 16), torch.nn.Linear(64, 16)
+    before = [p.detach().clone() for l in (q, k, v) for p in (l.weight, l.bias)]
+    ids = [id(l.weight) for l in (q, k, v)]
+    W, B = pack_linears([q, k, v])
+    assert W.shape == (96, 64) and B.shape == (96,)
+    assert [id(l.weight) for l in (q, k, v)] == ids
+    assert torch.equal(W[:64], before[0]) and torch.equal(W[64:80], before[2]) and torch.equal(B[80:], before[5])
+    assert q.weight.data_ptr() == W.data_ptr() and k.weight.data_ptr() == W[64:].data_ptr()
+    W2, _ = pack_linears([q, k, v])  # second call: nothing moves
+    assert W2.data_ptr() == W.data_ptr()
+    with torch.no_grad():
+        k.weight.add_(1.0)
+    assert torch.equal(W[64:80], before[2] + 1.0)
+
+
+def test_flat_params_layout_and_grad_views():
+    import io
+    from contextlib import redirect_stdout
+    from dataclasses import make_dataclass
+    from vyomai_b200 import EncoderModel
+    from vyomai_b200.trainer import FlatParams
+    C = make_dataclass("C", [("hidden_size", int, 128), ("num_attention_heads", int, 2), ("num_key_value_heads", int, 1),
+                             ("max_position_embeddings", int, 32), ("num_hidden_layers", int, 2), ("vocab_size", int, 50),
+                             ("hidden_dropout_prob", float, 0.0), ("layer_norm_eps", float, 1e-5), ("hidden_act", str, "gelu")])
+    with redirect_stdout(io.StringIO()):
+        m = EncoderModel(C(), "rope", "gqa")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    fp = FlatParams(m)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    att = m.all_layer[0].attention
+    assert att.key.weight.data_ptr() == att.query.weight.data_ptr() + att.query.weight.numel() * 4
+    assert att.value.bias.data_ptr() == att.key.bias.data_ptr() + att.key.bias.numel() * 4
+    n = sum(p.numel() for p in m.parameters())
+    assert n <= fp.numel < n + 8 * len(list(m.parameters()))
+    att.query.weight.grad.fill_(2.0)
+    assert float(fp.grad.sum()) == 2.0 * att.query.weight.numel()
+    fp.zero_grad()
+    assert float(fp.grad.abs().sum()) == 0.0
+
+
+def _exchange_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vyomai_b200.trainer import GradExchange
+    torch.manual_seed(rank)
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    ex = GradExchange(g, bucket_elems=300)
+    assert len(ex.buckets) == 4 and ex.buckets[0] == (700, 1000) and ex.buckets[-1] == (0, 100)
+    ex.begin_step()
+    ex.launch(0)          # a bucket that became ready during "backward"
+    ex.finish()           # the rest
+    want = torch.arange(1000, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    q.put((rank, bool(torch.equal(g, want))))
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

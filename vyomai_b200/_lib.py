@@ -136,6 +136,71 @@ def check(rc: int, what: str) -> None:
         raise VyomError(f"{what} failed ({rc}): {last_error()}")
 
 
+class KernelTimer:
+    """Optional per-call CUDA-event timing of the C-ABI entry points (bench.py's roofline leg).
+    Events are recorded on the stream the kernel is launched on; nothing synchronises until
+    `summary()`."""
+
+    def __init__(self):
+        self.records = []  # (fn_name, info dict, start event, end event)
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, info, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["calls"] += 1
+            d["ms"] += ms
+            d["flops"] += info.get("flops", 0.0)
+            d["bytes"] += info.get("bytes", 0.0)
+        return out
+
+
+TIMER: "KernelTimer | None" = None
+
+
+def _work(fn_name: str, kw: dict) -> dict:
+    """Algorithmic work of one call: GEMM FLOPs = 2 M N K; attention FLOPs =
+    4 B Hq Sq Skv 64 per matmul pair (halved when causal); the rest are byte counts."""
+    try:
+        if fn_name == "vy_gemm":
+            return {"flops": 2.0 * kw["M"] * kw["N"] * kw["K"]}
+        if fn_name in ("vy_attn_fwd", "vy_attn_bwd"):
+            f = 4.0 * kw["B"] * kw["n_q_heads"] * kw["Sq"] * kw["Skv"] * 64
+            if kw.get("causal"):
+                f *= 0.5
+            return {"flops": f * (3.5 if fn_name == "vy_attn_bwd" else 1.0)}
+        if fn_name == "vy_attn_decode":
+            es = 2 if kw["cache_dtype"] == CONSTS["VY_BF16"] else 4
+            return {"bytes": 2.0 * kw["B"] * kw["n_kv_heads"] * (kw["start_pos"] + 1) * 64 * es}
+        if fn_name in ("vy_add_layernorm_fwd", "vy_add_layernorm_bwd"):
+            es = 2 if kw["io_dtype"] == CONSTS["VY_BF16"] else 4
+            n = 2 + (1 if kw.get("residual") else 0) + (1 if kw.get("sum_out") else 0)
+            if fn_name.endswith("bwd"):
+                n = 3
+            return {"bytes": float(n) * kw["rows"] * kw["H"] * es}
+    except KeyError:
+        pass
+    return {}
+
+
+def _timed(fn_name: str, kw: dict, thunk):
+    t = TIMER
+    if t is None:
+        return thunk()
+    import torch
+    stream = torch.cuda.current_stream()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rc = thunk()
+    e1.record(stream)
+    t.records.append((fn_name, _work(fn_name, kw), e0, e1))
+    return rc
+
+
 def call(fn_name: str, struct_name: str, **kw) -> None:
     """Fills `struct_name` from keyword arguments and calls `fn_name(&struct)`."""
     st = STRUCTS[struct_name]()
@@ -143,5 +208,13 @@ def call(fn_name: str, struct_name: str, **kw) -> None:
         if v is None:
             continue
         setattr(st, k, v)
-    rc = getattr(lib(), fn_name)(ctypes.byref(st))
+    fn = getattr(lib(), fn_name)
+    rc = _timed(fn_name, kw, lambda: fn(ctypes.byref(st)))
+    check(rc, fn_name)
+
+
+def call_raw(fn_name: str, *args) -> None:
+    """Calls a scalar-argument entry point (vy_colsum, vy_argmax_rows, ...)."""
+    fn = getattr(lib(), fn_name)
+    rc = _timed(fn_name, {}, lambda: fn(*args))
     check(rc, fn_name)

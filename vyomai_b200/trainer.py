@@ -7,7 +7,7 @@ Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1 `main()`) is rebuilt B20
     buffer of the same layout (q|k|v projection weights adjacent, so the packed-QKV GEMM needs no
     repacking), which makes the optimizer a single fused kernel and the gradient exchange a
     handful of large NCCL all-reduces over NVLink / NVSwitch instead of one per tensor;
-  * gradient all-reduce runs bucket by bucket on a side stream as soon as backward has produced a
+  * the all-reduce runs bucket by bucket on a side stream as soon as backward has produced a
     bucket (post-accumulate hooks), so the transfer overlaps the remaining backward kernels;
   * AdamW (fp32 master weights + fp32 moments, bf16 or fp32 model weights), the global-norm clip
     and the 1/world_size mean are fused into vy_sqnorm + vy_adamw; the clip coefficient never
@@ -15,13 +15,12 @@ Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1 `main()`) is rebuilt B20
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Set, Tuple
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import functional as F
 from . import ops
 from .autograd_train import cross_entropy
 from .layers.attention import _SelfAttentionBase
@@ -78,9 +77,56 @@ class FlatParams:
 
     def zero_grad(self) -> None:
         self.grad.zero_()
+        es = self.grad.element_size()
+        base = self.grad.data_ptr()
         for p, o in zip(self.params, self.offsets):  # re-attach in case autograd replaced a .grad
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + o * self.grad.element_size():
+            if p.grad is None or p.grad.data_ptr() != base + o * es:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+class GradExchange:
+    """Bucketed sum all-reduce of one flat gradient buffer. Buckets are contiguous slices walked from
+    the END of the buffer (the order backward fills it); on CUDA the collectives run on a side
+    stream so they overlap the rest of backward. Works with any torch.distributed backend (NCCL on
+    the B200 box, gloo in the CPU tests)."""
+
+    def __init__(self, flat_grad: torch.Tensor, bucket_elems: int):
+        self.grad = flat_grad
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.buckets: List[Tuple[int, int]] = []
+        end = flat_grad.numel()
+        while end > 0:
+            start = max(0, end - bucket_elems)
+            self.buckets.append((start, end))
+            end = start
+        self._launched: Set[int] = set()
+        self._stream = torch.cuda.Stream(device=flat_grad.device) if (flat_grad.is_cuda and self.world > 1) else None
+
+    def bucket_of(self, offset: int) -> int:
+        return next(i for i, (s, e) in enumerate(self.buckets) if s <= offset < e)
+
+    def begin_step(self) -> None:
+        self._launched = set()
+
+    def launch(self, b: int) -> None:
+        if self.world == 1 or b in self._launched:
+            return
+        s, e = self.buckets[b]
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                dist.all_reduce(self.grad[s:e], op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(self.grad[s:e], op=dist.ReduceOp.SUM)
+        self._launched.add(b)
+
+    def finish(self) -> None:
+        if self.world == 1:
+            return
+        for b in range(len(self.buckets)):
+            self.launch(b)
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
 
 
 class Trainer:
@@ -98,67 +144,33 @@ class Trainer:
         self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.overlap = overlap and self.world > 1
-        self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
-        # buckets: contiguous slices of the flat gradient, walked from the END (backward order)
         per = max(1, int(bucket_mb * 1024 * 1024 / self.fp.grad.element_size()))
-        self.buckets = []
-        end = n
-        while end > 0:
-            start = max(0, end - per)
-            self.buckets.append((start, end))
-            end = start
+        self.exchange = GradExchange(self.fp.grad, per)
+        self.world = self.exchange.world
+        self.overlap = overlap and self.world > 1
         self._pending: Dict[int, int] = {}
         self._bucket_of: Dict[int, int] = {}
-        self._handles = []
+        self._bucket_size: List[int] = [0] * len(self.exchange.buckets)
         if self.overlap:
-            self._install_hooks()
-
-    # ---- gradient exchange -------------------------------------------------------------------
-    def _install_hooks(self) -> None:
-        sizes = [0] * len(self.buckets)
-        for p, o in zip(self.fp.params, self.fp.offsets):
-            b = next(i for i, (s, e) in enumerate(self.buckets) if s <= o < e)
-            self._bucket_of[id(p)] = b
-            sizes[b] += 1
-            p.register_post_accumulate_grad_hook(self._on_grad)
-        self._bucket_size = sizes
+            for p, o in zip(self.fp.params, self.fp.offsets):
+                b = self.exchange.bucket_of(o)
+                self._bucket_of[id(p)] = b
+                self._bucket_size[b] += 1
+                p.register_post_accumulate_grad_hook(self._on_grad)
 
     def _on_grad(self, p: nn.Parameter) -> None:
         b = self._bucket_of[id(p)]
         self._pending[b] = self._pending.get(b, 0) + 1
         if self._pending[b] == self._bucket_size[b]:
-            self._launch_bucket(b)
+            self.exchange.launch(b)
 
-    def _launch_bucket(self, b: int) -> None:
-        s, e = self.buckets[b]
-        cs = self._comm_stream
-        cs.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(cs):
-            dist.all_reduce(self.fp.grad[s:e], op=dist.ReduceOp.SUM)
-        self._launched.add(b)
-
-    def _finish_allreduce(self) -> None:
-        if self.world == 1:
-            return
-        if self.overlap:
-            for b in range(len(self.buckets)):
-                if b not in self._launched:  # buckets whose params got no gradient this step
-                    self._launch_bucket(b)
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
-        else:
-            for (s, e) in self.buckets:
-                dist.all_reduce(self.fp.grad[s:e], op=dist.ReduceOp.SUM)
-
-    # ---- one optimisation step ---------------------------------------------------------------
     def zero_grad(self) -> None:
         self.fp.zero_grad()
         self._pending = {}
-        self._launched = set()
+        self.exchange.begin_step()
 
     def optimizer_step(self) -> None:
-        self._finish_allreduce()
+        self.exchange.finish()
         self.step_count += 1
         self.sqnorm.zero_()
         ops.sqnorm(self.fp.grad, self.sqnorm)
