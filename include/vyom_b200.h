@@ -454,6 +454,8 @@ typedef struct VyAdamW {
   float* master; /* or NULL */
   float lr, beta1, beta2, eps, weight_decay;
   int32_t step; /* 1-based */
+  const int32_t* step_ptr; /* optional device copy of the step counter (wins over `step`): lets a
+                              captured CUDA graph of the whole training step be replayed */
   const float* grad_sqnorm; /* device scalar or NULL */
   float max_grad_norm;      /* <= 0: no clipping */
   float grad_div;           /* 0 = 1 */

@@ -36,6 +36,55 @@ def _bgrad(dy2d: torch.Tensor, like: Optional[torch.Tensor]) -> Optional[torch.T
     return ops.colsum(dy2d, out_dtype=like.dtype)
 
 
+# ---- gradient accumulation fused into the kernels -----------------------------------------------
+# A trainer that owns preallocated gradient buffers (trainer.FlatParams) marks its parameters with
+# `_vy_direct_grad`; weight / bias gradients are then accumulated straight into `param.grad` by the
+# wgrad GEMM epilogue (addend = the buffer itself) or vy_colsum(accumulate), autograd receives None for
+# them, and `_vy_grad_ready` (the trainer's bucket hook) is called by hand. Saves one read-modify-write
+# pass and one launch per parameter.
+def _direct(p: Optional[torch.Tensor]) -> bool:
+    return p is not None and getattr(p, "_vy_direct_grad", False) and p.grad is not None
+
+
+def _ready(p) -> None:
+    cb = getattr(p, "_vy_grad_ready", None)
+    if cb is not None:
+        cb(p)
+
+
+def _emit_wgrad(p: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor) -> Optional[torch.Tensor]:
+    if _direct(p):
+        g2 = p.grad.view(p.grad.shape[0], -1)
+        ops.gemm(dy2d.t(), x2d.t(), out=g2, addend=g2)
+        _ready(p)
+        return None
+    return _wgrad(dy2d, x2d, p).view(p.shape)
+
+
+def _emit_bgrad(p: Optional[torch.Tensor], dy2d: torch.Tensor) -> Optional[torch.Tensor]:
+    if p is None:
+        return None
+    if _direct(p):
+        ops.colsum(dy2d, out=p.grad, accumulate=True)
+        _ready(p)
+        return None
+    return ops.colsum(dy2d, out_dtype=p.dtype)
+
+
+def _packed_grads(params) -> Optional[torch.Tensor]:
+    """One 2-D (or 1-D) view over the adjacent .grad buffers of several parameters, or None."""
+    if not all(_direct(p) for p in params):
+        return None
+    gs = [p.grad for p in params]
+    if not F._adjacent(gs):
+        return None
+    g0 = gs[0]
+    n = sum(g.shape[0] for g in gs)
+    if g0.dim() == 2:
+        return torch.as_strided(g0, (n, g0.shape[1]), (g0.stride(0), 1), g0.storage_offset())
+    return torch.as_strided(g0, (n,), (1,), g0.storage_offset())
+
+
 class AttentionBlockFn(torch.autograd.Function):
     """y = LN(dense(attention(x)) + x). Inputs after the non-tensor arguments: x2d, the 1 or 3
     projection weights, their biases (if any), dense.weight, [dense.bias], ln.weight, ln.bias."""
@@ -66,8 +115,8 @@ class AttentionBlockFn(torch.autograd.Function):
         Hq, Hkv, d = mod.num_attention_heads, mod._kv_heads, F.HEAD_DIM
         dy = dy.contiguous()
         ds, dgamma, dbeta = ops.add_layernorm_bwd(dy, s, ln.weight, mean, rstd)
-        d_wo = _wgrad(ds, attn, dense.weight)
-        d_bo = _bgrad(ds, dense.bias)
+        d_wo = _emit_wgrad(dense.weight, ds, attn)
+        d_bo = _emit_bgrad(dense.bias, ds)
         d_attn = _dgrad(ds, dense.weight, out_dtype=torch.bfloat16)  # bf16: MMA operand of the attention backward
         dqkv = torch.empty((B * S, (Hq + 2 * Hkv) * d), device=dy.device, dtype=x2d.dtype)
         cos = sin = None
@@ -78,21 +127,35 @@ class AttentionBlockFn(torch.autograd.Function):
         ops.attn_bwd(q, k, v, attn, d_attn, lse, causal=mask.causal, q_pos0=mask.q_pos0, key_padding_mask=mask.key_padding,
                      rope_cos=cos, rope_sin=sin, rope_pos0=rope_pos0, dq=dqkv[:, : Hq * d],
                      dk=dqkv[:, Hq * d:(Hq + Hkv) * d], dv=dqkv[:, (Hq + Hkv) * d:])
-        d_wqkv = _wgrad(dqkv, x2d, w_qkv)
         dx = _dgrad(dqkv, w_qkv, addend=ds)  # + the residual branch of LN(dense(.) + x)
         grads = [dx]
-        r = 0
-        for l in lin:
-            n = l.weight.shape[0]
-            grads.append(d_wqkv[r:r + n])
-            r += n
-        if ctx.has_qkv_bias:
-            d_bqkv = ops.colsum(dqkv, out_dtype=lin[0].bias.dtype)
+        gw = _packed_grads([l.weight for l in lin])
+        if gw is not None:  # one wgrad GEMM accumulating into the adjacent q|k|v gradient buffers
+            ops.gemm(dqkv.t(), x2d.t(), out=gw, addend=gw)
+            for l in lin:
+                _ready(l.weight)
+                grads.append(None)
+        else:
+            d_wqkv = _wgrad(dqkv, x2d, w_qkv)
             r = 0
             for l in lin:
-                n = l.bias.shape[0]
-                grads.append(d_bqkv[r:r + n])
+                n = l.weight.shape[0]
+                grads.append(d_wqkv[r:r + n])
                 r += n
+        if ctx.has_qkv_bias:
+            gb = _packed_grads([l.bias for l in lin])
+            if gb is not None:
+                ops.colsum(dqkv, out=gb, accumulate=True)
+                for l in lin:
+                    _ready(l.bias)
+                    grads.append(None)
+            else:
+                d_bqkv = ops.colsum(dqkv, out_dtype=lin[0].bias.dtype)
+                r = 0
+                for l in lin:
+                    n = l.bias.shape[0]
+                    grads.append(d_bqkv[r:r + n])
+                    r += n
         grads.append(d_wo)
         if ctx.has_dense_bias:
             grads.append(d_bo)

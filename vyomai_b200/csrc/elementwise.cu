@@ -159,16 +159,48 @@ argmax_rows_kernel(int rows, int V, const void* __restrict__ x, long long ld, in
 // column sums (bias gradients): stage 1 partial sums over row chunks, stage 2 final reduce
 // ------------------------------------------------------------------------------------------
 constexpr int CS_CHUNKS = 64;
-__global__ void __launch_bounds__(128)
-colsum_partial_kernel(int R, int Cn, const void* __restrict__ x, long long ld, int dt, float* __restrict__ part) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int chunk = blockIdx.y;
+// One warp covers 256 consecutive columns (8 per lane, one 16-byte load per row); the 8 warps of a CTA
+// take interleaved rows of the CTA's row chunk, 4 rows in flight each, and are combined in smem.
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(int R, int Cn, const void* __restrict__ x, long long ld, int dt, float* __restrict__ part, int vec_ok) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
   const int per = (R + gridDim.y - 1) / gridDim.y;
-  const int r0 = chunk * per, r1 = min(R, r0 + per);
-  if (c >= Cn) return;
-  float a = 0.f;
-  for (int r = r0; r < r1; ++r) a += ld_as_float(x, dt, static_cast<long long>(r) * ld + c);
-  part[static_cast<long long>(chunk) * Cn + c] = a;
+  const int r0 = blockIdx.y * per, r1 = min(R, r0 + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (vec_ok && c0 + 8 <= Cn) {
+    int r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ld8_as_float(x, dt, static_cast<long long>(r + u * 8) * ld + c0, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; r < r1; r += 8) {
+      float v[8];
+      ld8_as_float(x, dt, static_cast<long long>(r) * ld + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  } else if (c0 < Cn) {
+    const int lim = min(8, Cn - c0);
+    for (int r = r0 + w; r < r1; r += 8)
+      for (int j = 0; j < lim; ++j) acc[j] += ld_as_float(x, dt, static_cast<long long>(r) * ld + c0 + j);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[w][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < Cn) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x];
+    part[static_cast<long long>(blockIdx.y) * Cn + c] = a;
+  }
 }
 __global__ void __launch_bounds__(128)
 colsum_final_kernel(int Cn, int chunks, const float* __restrict__ part, void* __restrict__ out, int out_dt, int accumulate,
@@ -208,43 +240,78 @@ cast4d_kernel(int n0, int n1, int n2, int n3, const void* __restrict__ src, int 
 __global__ void __launch_bounds__(256)
 xent_kernel(int rows, int V, void* __restrict__ logits, long long ld, int dt, const long long* __restrict__ labels,
             long long ignore_index, const float* __restrict__ grad_scale_ptr, float grad_scale,
-            float* __restrict__ loss_rows, int write_grad) {
-  __shared__ float s_red[8];
+            float* __restrict__ loss_rows, int write_grad, int vec_ok) {
+  __shared__ float s_m[8], s_s[8];
   const int r = blockIdx.x;
   const long long base = static_cast<long long>(r) * ld;
   const long long lab = labels[r];
   const bool active = lab != ignore_index && lab >= 0 && lab < V;
+  const int nvec = vec_ok ? (V >> 3) : 0;  // 8-element (16 B of bf16) chunks; the tail is scalar
   if (!active) {
     if (threadIdx.x == 0 && loss_rows) loss_rows[r] = 0.f;
-    if (write_grad)
-      for (int c = threadIdx.x; c < V; c += blockDim.x) st_from_float(logits, dt, base + c, 0.f);
+    if (write_grad) {
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) st8_from_float(logits, dt, base + vi * 8, z);
+      for (int c = nvec * 8 + threadIdx.x; c < V; c += blockDim.x) st_from_float(logits, dt, base + c, 0.f);
+    }
     return;
   }
-  float mx = -INFINITY;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, ld_as_float(logits, dt, base + c));
-  mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  mx = s_red[0];
+  // pass 1: online max / sum (one read of the row)
+  float mx = -INFINITY, sum = 0.f;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    float x[8];
+    ld8_as_float(logits, dt, base + vi * 8, x);
+    float cm = x[0];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+    for (int j = 1; j < 8; ++j) cm = fmaxf(cm, x[j]);
+    const float nm = fmaxf(mx, cm);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += __expf(x[j] - nm);
+    sum = sum * __expf(mx - nm) + acc;
+    mx = nm;
+  }
+  for (int c = nvec * 8 + threadIdx.x; c < V; c += blockDim.x) {
+    const float x = ld_as_float(logits, dt, base + c);
+    const float nm = fmaxf(mx, x);
+    sum = sum * __expf(mx - nm) + __expf(x - nm);
+    mx = nm;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, mx, o), s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+    const float nm = fmaxf(mx, m2);
+    sum = (mx == -INFINITY ? 0.f : sum * __expf(mx - nm)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - nm));
+    mx = nm;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_m[threadIdx.x >> 5] = mx;
+    s_s[threadIdx.x >> 5] = sum;
+  }
   __syncthreads();
-  float sum = 0.f;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) sum += __expf(ld_as_float(logits, dt, base + c) - mx);
-  sum = warp_sum(sum);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sum;
-  __syncthreads();
+  mx = s_m[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_m[w]);
   sum = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) sum += s_red[w];
+  for (int w = 0; w < 8; ++w) sum += (s_m[w] == -INFINITY ? 0.f : s_s[w] * __expf(s_m[w] - mx));
   const float lse = mx + __logf(sum);
   if (threadIdx.x == 0 && loss_rows) loss_rows[r] = lse - ld_as_float(logits, dt, base + lab);
   if (write_grad) {
+    // pass 2: the row is re-read (L2-resident: a row is <= ~200 KB) and overwritten with the gradient
     const float gs = grad_scale_ptr ? *grad_scale_ptr * grad_scale : grad_scale;
     const float inv = 1.f / sum;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-      const float p = __expf(ld_as_float(logits, dt, base + c) - mx) * inv;
-      st_from_float(logits, dt, base + c, (p - (c == lab ? 1.f : 0.f)) * gs);
+    for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+      float x[8];
+      ld8_as_float(logits, dt, base + vi * 8, x);
+      const int c0 = vi * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (__expf(x[j] - mx) * inv - (c0 + j == lab ? 1.f : 0.f)) * gs;
+      st8_from_float(logits, dt, base + c0, x);
+    }
+    for (int c = nvec * 8 + threadIdx.x; c < V; c += blockDim.x) {
+      const float pr = __expf(ld_as_float(logits, dt, base + c) - mx) * inv;
+      st_from_float(logits, dt, base + c, (pr - (c == lab ? 1.f : 0.f)) * gs);
     }
   }
 }
@@ -284,24 +351,54 @@ sqnorm_kernel(long long n, const void* __restrict__ g, int dt, float* __restrict
 __global__ void __launch_bounds__(256)
 adamw_kernel(long long n, void* __restrict__ p, int p_dt, const void* __restrict__ g, int g_dt,
              float* __restrict__ m, float* __restrict__ v, float* __restrict__ master, float lr, float beta1,
-             float beta2, float eps, float wd, float bc1, float bc2, const float* __restrict__ sqnorm,
-             float max_norm, float grad_div) {
+             float beta2, float eps, float wd, float bc1, float bc2, const int* __restrict__ step_ptr,
+             const float* __restrict__ sqnorm, float max_norm, float grad_div) {
   float clip = 1.f / grad_div;
   if (sqnorm && max_norm > 0.f) {
     const float norm = sqrtf(*sqnorm) / grad_div;
     clip *= fminf(1.f, max_norm / (norm + 1e-6f));
   }
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = ld_as_float(g, g_dt, i) * clip;
-    float w = master ? master[i] : ld_as_float(p, p_dt, i);
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    w = w * (1.f - lr * wd) - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
-    if (master) master[i] = w;
-    st_from_float(p, p_dt, i, w);
+  if (step_ptr) {  // device-side step counter: the launch can sit in a replayed CUDA graph
+    const float t = static_cast<float>(*step_ptr);
+    bc1 = 1.f - powf(beta1, t);
+    bc2 = 1.f - powf(beta2, t);
+  }
+  const float inv_bc1 = 1.f / bc1, inv_bc2 = 1.f / bc2, decay = 1.f - lr * wd;
+  // n is padded to a multiple of 8 by the flat-buffer layout; 8 elements (16 B of bf16) per thread
+  const long long nvec = n >> 3;
+  for (long long vi8 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi8 < nvec;
+       vi8 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = vi8 * 8;
+    float gi[8], w[8], mi[8], vv[8];
+    ld8_as_float(g, g_dt, i, gi);
+    if (master) ld8_as_float(master, VY_F32, i, w);
+    else ld8_as_float(p, p_dt, i, w);
+    ld8_as_float(m, VY_F32, i, mi);
+    ld8_as_float(v, VY_F32, i, vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gj = gi[j] * clip;
+      mi[j] = beta1 * mi[j] + (1.f - beta1) * gj;
+      vv[j] = beta2 * vv[j] + (1.f - beta2) * gj * gj;
+      w[j] = w[j] * decay - lr * (mi[j] * inv_bc1) / (sqrtf(vv[j] * inv_bc2) + eps);
+    }
+    st8_from_float(m, VY_F32, i, mi);
+    st8_from_float(v, VY_F32, i, vv);
+    if (master) st8_from_float(master, VY_F32, i, w);
+    st8_from_float(p, p_dt, i, w);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = (nvec << 3) + threadIdx.x; i < n; i += blockDim.x) {
+      const float gj = ld_as_float(g, g_dt, i) * clip;
+      float w = master ? master[i] : ld_as_float(p, p_dt, i);
+      const float mj = beta1 * m[i] + (1.f - beta1) * gj;
+      const float vj = beta2 * v[i] + (1.f - beta2) * gj * gj;
+      m[i] = mj;
+      v[i] = vj;
+      w = w * decay - lr * (mj * inv_bc1) / (sqrtf(vj * inv_bc2) + eps);
+      if (master) master[i] = w;
+      st_from_float(p, p_dt, i, w);
+    }
   }
 }
 
@@ -414,11 +511,15 @@ extern "C" int vy_colsum(int rows, int cols, const void* x, int64_t ld, int dtyp
                          int accumulate, float scale, float* workspace, void* stream) {
   VY_NEED_DEVICE("vy_colsum");
   VY_CHECK_ARG(rows > 0 && cols > 0 && x && out && workspace && dtype_ok(dtype) && dtype_ok(out_dtype), "vy_colsum: bad arguments");
-  int chunks = (rows + 255) / 256;
+  const int colgroups = (cols + 255) / 256;
+  int chunks = (4 * num_sms() + colgroups - 1) / colgroups;  // ~4 CTAs per SM in total
   if (chunks > CS_CHUNKS) chunks = CS_CHUNKS;
-  dim3 grid((cols + 127) / 128, chunks);
+  if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(colgroups, chunks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  colsum_partial_kernel<<<grid, 128, 0, st>>>(rows, cols, x, ld, dtype, workspace);
+  const int vec_ok = (aligned16(x) && (ld * static_cast<long long>(dtype_size(dtype))) % 16 == 0) ? 1 : 0;
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, dtype, workspace, vec_ok);
   VY_LAUNCH_OK();
   colsum_final_kernel<<<(cols + 127) / 128, 128, 0, st>>>(cols, chunks, workspace, out, out_dtype, accumulate,
                                                            scale == 0.f ? 1.f : scale);
@@ -448,7 +549,8 @@ extern "C" int vy_softmax_xent(const VyXent* p) {
   VY_CHECK_ARG(p->rows > 0 && p->V > 0 && p->logits && p->labels && dtype_ok(p->dtype), "vy_softmax_xent: bad arguments");
   xent_kernel<<<p->rows, 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
       p->rows, p->V, p->logits, p->ld, p->dtype, reinterpret_cast<const long long*>(p->labels), p->ignore_index,
-      p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->write_grad);
+      p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->write_grad,
+      (aligned16(p->logits) && (p->ld * static_cast<long long>(dtype_size(p->dtype))) % 16 == 0) ? 1 : 0);
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -468,12 +570,13 @@ extern "C" int vy_adamw(const VyAdamW* p) {
   VY_NEED_DEVICE("vy_adamw");
   VY_CHECK_ARG(p->n > 0 && p->param && p->grad && p->exp_avg && p->exp_avg_sq && dtype_ok(p->param_dtype) && dtype_ok(p->grad_dtype),
                "vy_adamw: bad arguments");
-  VY_CHECK_ARG(p->step >= 1, "vy_adamw: step must be >= 1");
+  VY_CHECK_ARG(p->step >= 1 || p->step_ptr, "vy_adamw: step must be >= 1 (or pass step_ptr)");
   const float bc1 = 1.f - powf(p->beta1, static_cast<float>(p->step));
   const float bc2 = 1.f - powf(p->beta2, static_cast<float>(p->step));
   adamw_kernel<<<ew_grid(p->n, 1024), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
       p->n, p->param, p->param_dtype, p->grad, p->grad_dtype, p->exp_avg, p->exp_avg_sq, p->master, p->lr, p->beta1,
-      p->beta2, p->eps, p->weight_decay, bc1, bc2, p->grad_sqnorm, p->max_grad_norm, p->grad_div == 0.f ? 1.f : p->grad_div);
+      p->beta2, p->eps, p->weight_decay, bc1, bc2, p->step_ptr, p->grad_sqnorm, p->max_grad_norm,
+      p->grad_div == 0.f ? 1.f : p->grad_div);
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -148,15 +148,24 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
   }
 }
 
-__global__ void norm_bwd_reduce_kernel(int nparts, int H, const float* __restrict__ partials,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  // one warp per 32 columns, lanes = columns (coalesced over the partial rows)
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * H) return;
+// column reduce of the per-block partials: 32 columns per block, 8 warps split the partial rows
+__global__ void __launch_bounds__(256)
+norm_bwd_reduce_kernel(int nparts, int H, const float* __restrict__ partials, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float a = 0.f;
-  for (int p = 0; p < nparts; ++p) a += partials[static_cast<size_t>(p) * 2 * H + c];
-  if (c < H) dgamma[c] = a;
-  else dbeta[c - H] = a;
+  if (c < 2 * H)
+    for (int p = w; p < nparts; p += 8) a += partials[static_cast<size_t>(p) * 2 * H + c];
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && c < 2 * H) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += red[k][lane];
+    if (c < H) dgamma[c] = a;
+    else dbeta[c - H] = a;
+  }
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -244,7 +253,7 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   }
 #undef VY_LN_BWD
   VY_LAUNCH_OK();
-  norm_bwd_reduce_kernel<<<(2 * p->H + 127) / 128, 128, 0, st>>>(grid, p->H, p->partials, p->dgamma, p->dbeta);
+  norm_bwd_reduce_kernel<<<(2 * p->H + 31) / 32, 256, 0, st>>>(grid, p->H, p->partials, p->dgamma, p->dbeta);
   VY_LAUNCH_OK();
   count_launch(2);
   return VY_OK;

@@ -505,11 +505,11 @@ def sqnorm(g: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def adamw(param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay, step, master=None,
-          grad_sqnorm=None, max_grad_norm=0.0, grad_div=1.0) -> None:
+          grad_sqnorm=None, max_grad_norm=0.0, grad_div=1.0, step_ptr=None) -> None:
     """Fused AdamW over flat buffers (see vy_adamw)."""
     _need_cuda(param, grad, exp_avg, exp_avg_sq, master, grad_sqnorm)
     _lib.call("vy_adamw", "VyAdamW", n=param.numel(), param=param.data_ptr(), param_dtype=_dt(param), grad=grad.data_ptr(),
               grad_dtype=_dt(grad), exp_avg=exp_avg.data_ptr(), exp_avg_sq=exp_avg_sq.data_ptr(), master=_ptr(master),
               lr=float(lr), beta1=float(beta1), beta2=float(beta2), eps=float(eps), weight_decay=float(weight_decay),
-              step=int(step), grad_sqnorm=_ptr(grad_sqnorm), max_grad_norm=float(max_grad_norm), grad_div=float(grad_div),
+              step=int(step), step_ptr=_ptr(step_ptr), grad_sqnorm=_ptr(grad_sqnorm), max_grad_norm=float(max_grad_norm), grad_div=float(grad_div),
               stream=_stream())

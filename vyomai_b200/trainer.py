@@ -133,8 +133,11 @@ class Trainer:
     """AdamW + clip + data-parallel all-reduce around a model built from vyomai_b200 modules."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
-                 max_grad_norm: float = 1.0, bucket_mb: float = 64.0, overlap: bool = True):
+                 max_grad_norm: float = 1.0, bucket_mb: float = 64.0, overlap: bool = True, use_graph: bool = False):
         self.model = model
+        self.use_graph = use_graph
+        self._graph = None
+        self._graph_key = None
         self.fp = FlatParams(model)
         n = self.fp.numel
         dev = self.fp.flat.device
@@ -142,6 +145,7 @@ class Trainer:
         self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
         self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
         per = max(1, int(bucket_mb * 1024 * 1024 / self.fp.grad.element_size()))
@@ -172,23 +176,55 @@ class Trainer:
     def optimizer_step(self) -> None:
         self.exchange.finish()
         self.step_count += 1
+        self.step_dev.add_(1)  # device-side step counter: the whole step can live in a replayed CUDA graph
         self.sqnorm.zero_()
         ops.sqnorm(self.fp.grad, self.sqnorm)
         ops.adamw(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
-                  beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.step_count, master=self.master,
-                  grad_sqnorm=self.sqnorm, max_grad_norm=self.max_grad_norm, grad_div=float(self.world))
+                  beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.step_count, step_ptr=self.step_dev,
+                  master=self.master, grad_sqnorm=self.sqnorm, max_grad_norm=self.max_grad_norm, grad_div=float(self.world))
 
-    def caption_step(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor,
-                     labels_full: torch.Tensor) -> torch.Tensor:
-        """One captioner training step (VisionLanguageModel): forward, shifted token cross-entropy,
-        backward, gradient all-reduce, clip, AdamW. `labels_full` is [B, S+1] aligned with the logits rows
-        (image position and the last position carry ignore_index). Returns the (local) loss tensor."""
+    def _caption_body(self, pixel_values, input_ids, attention_mask, labels_full) -> torch.Tensor:
         self.zero_grad()
         logits = self.model(pixel_values=pixel_values, decoder_input_ids=input_ids, decoder_attention_mask=attention_mask).logits
         loss = cross_entropy(logits, labels_full, ignore_index=-100)
         loss.backward()
         self.optimizer_step()
         return loss.detach()
+
+    def caption_step(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor,
+                     labels_full: torch.Tensor) -> torch.Tensor:
+        """One captioner training step (VisionLanguageModel): forward, shifted token cross-entropy,
+        backward, gradient all-reduce, clip, AdamW. `labels_full` is [B, S+1] aligned with the logits rows
+        (image position and the last position carry ignore_index). Returns the (local) loss tensor.
+
+        With use_graph the first call of a given input shape runs three eager warm-up steps and captures
+        the whole step (every kernel, the NCCL all-reduces on the side stream, the optimizer) into one CUDA
+        graph; later calls copy the inputs into the graph's static buffers and replay it, so the ~400
+        launches of a step cost one cudaGraphLaunch."""
+        if not self.use_graph:
+            return self._caption_body(pixel_values, input_ids, attention_mask, labels_full)
+        key = (tuple(pixel_values.shape), tuple(input_ids.shape))
+        if self._graph_key != key:
+            self._capture(key, pixel_values, input_ids, attention_mask, labels_full)
+        for dst, src in zip(self._static_in, (pixel_values, input_ids, attention_mask, labels_full)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
+
+    def _capture(self, key, pixel_values, input_ids, attention_mask, labels_full) -> None:
+        self._static_in = [t.clone() for t in (pixel_values, input_ids, attention_mask, labels_full)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):  # these are real optimisation steps (the caller's warm-up)
+                self._caption_body(*self._static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._caption_body(*self._static_in)
+        self._graph_key = key
 
 
 def caption_labels(input_ids: torch.Tensor, attention_mask: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
