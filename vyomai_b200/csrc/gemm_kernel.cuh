@@ -1,0 +1,719 @@
+// vy_gemm: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 0      TMEM allocator, then TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1      MMA issuer    (one thread, tcgen05.mma cta_group::1, fp32 accumulators in TMEM)
+//   warps 2..9  epilogue      (tcgen05.ld -> registers -> fused bias/act/residual/RoPE -> smem staging
+//                              -> coalesced global stores; two warps per TMEM lane quarter)
+//
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the mainloop of tile i+1; the row
+// operand an epilogue reads (residual, saved pre-activation) is prefetched before the accumulator is
+// awaited. Tile = 128 x BN x (128 bytes of K), BN in {32, 64, 128, 192, 256} chosen per shape to
+// minimise the number of waves over the 148 SMs: BK = 64 bf16 or 32 tf32 elements, so every smem stage has
+// the same byte geometry for both input types. Operands may be K-major (nn.Linear layout) or
+// MN-major (transposed storage, used by dgrad / wgrad) — only the TMA box and the UMMA
+// descriptor change.
+#pragma once
+#include "vy_common.cuh"
+#include "vy_ptx.cuh"
+
+namespace vy {
+
+struct GemmDev {
+  int M, N, K;
+  int epi, act, transposed_out;
+  const void* bias;
+  int bias_dtype;
+  const void* addend;
+  long long ld_addend;
+  int addend_dtype, addend_row_mod, addend_row_off;
+  const void* addend2;
+  long long ld_addend2;
+  int addend2_dtype;
+  void* aux;
+  long long ld_aux;
+  int aux_dtype;
+  float out_scale;
+  void* out;
+  long long ld_out;
+  int out_dtype, out_row_group, out_row_group_stride, out_row_off;
+  int vec_ok;  // all row strides / bases allow 8-element vector access
+  // qkv rope
+  int tokens_per_seq, start_pos, kv_dst_pos0, n_q_heads, n_kv_heads;
+  const float* rope_cos;
+  const float* rope_sin;
+  void* q_out;
+  long long q_sb, q_sh, q_sl;
+  void* k_out;
+  long long k_sb, k_sh, k_sl;
+  void* v_out;
+  long long v_sb, v_sh, v_sl;
+  int kv_out_dtype;
+};
+
+constexpr int GEMM_EPI_WARPS = 8;                        // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int GEMM_FIRST_EPI_WARP = 2;                   // warp 0: TMEM allocator + TMA producer, warp 1: MMA issuer
+constexpr int GEMM_THREADS = (GEMM_FIRST_EPI_WARP + GEMM_EPI_WARPS) * 32;  // 320 threads -> up to 200 registers each
+constexpr int GEMM_STAGE_OUT = 2048;                     // per-warp staging of one [32 rows x 32 bf16] chunk (x2: out and aux)
+
+template <typename TIn, int BN_>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BN = BN_;
+  static constexpr int EPB = 128 / sizeof(TIn);  // elements per 128-byte swizzle row
+  static constexpr int BK = EPB;
+  static constexpr int UMMA_K = 32 / sizeof(TIn);
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 192 ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
+  static constexpr int MN_BOX_BYTES = BK * 128;
+  static constexpr int EPI_STAGE_BYTES = GEMM_EPI_WARPS * 2 * GEMM_STAGE_OUT;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2 * BN * 4 /*bias*/ + 256;
+  static constexpr int FMT = sizeof(TIn) == 2 ? 1 : 2;  // bf16 : tf32
+  // MN-major operands: bf16 uses the plain 128B swizzle (8 k-rows per 1024-B group); tf32 must use
+  // SWIZZLE_128B_BASE32B (4 k-rows per 512-B group) and the matching TMA mode.
+  static constexpr int MN_SBO = sizeof(TIn) == 2 ? 1024 : 512;
+  static constexpr int MN_LAYOUT = sizeof(TIn) == 2 ? 2 : 1;
+  static constexpr int MN_TMA_SWIZZLE = sizeof(TIn) == 2 ? 1 : 2;
+  static_assert(SMEM_BYTES <= 232448, "tile does not fit the 227 KB of shared memory");
+};
+
+__device__ __forceinline__ float apply_act(int act, float x) {
+  if (act == VY_ACT_GELU_ERF) return gelu_erf(x);
+  if (act == VY_ACT_GELU_TANH) return gelu_tanh(x);
+  return x;
+}
+__device__ __forceinline__ float apply_dact(int act, float z) {
+  return act == VY_ACT_DGELU_ERF ? dgelu_erf(z) : dgelu_tanh(z);
+}
+
+__device__ __forceinline__ long long remap_out_row(const GemmDev& g, int r) {
+  if (g.out_row_group > 0)
+    return static_cast<long long>(r / g.out_row_group) * g.out_row_group_stride +
+           (r % g.out_row_group) + g.out_row_off;
+  return r;
+}
+__device__ __forceinline__ long long remap_add_row(const GemmDev& g, int r) {
+  if (g.addend_row_mod > 0) return g.addend_row_off + (r % g.addend_row_mod);
+  return r;
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& raw, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+
+// every epilogue warp releases its share of the accumulator buffer once its last tcgen05.ld retired
+__device__ __forceinline__ void release_acc(uint64_t* tmem_empty_bar, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tmem_empty_bar);
+}
+
+// --------------------------------------------------------------------------------------------
+// Coalesced write-back of one [32 rows x 32 cols] bf16 chunk. Thread `lane` holds row `lane` as 16
+// packed words; the chunk goes through this warp's 2 KB staging buffer (16-byte slots XOR-swizzled so
+// that both the row-wise writes and the 8-rows-per-instruction read-back are bank-conflict free) and
+// leaves as 64-byte row segments: 4 lanes per row, 8 rows per store instruction, every 32-byte sector
+// written whole. wb[i] = destination of row (i * 8 + lane / 4) at this lane's 8-column slot (nullptr =
+// skip the row).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_rows_bf16(uint8_t* stage, int lane, const uint32_t (&pk)[16]) {
+  uint8_t* rowp = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+}
+__device__ __forceinline__ uint4 staged_slot(const uint8_t* stage, int lane, int i) {
+  const int r = i * 8 + (lane >> 2);
+  return *reinterpret_cast<const uint4*>(stage + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
+}
+
+// --------------------------------------------------------------------------------------------
+// Epilogue bodies. Warp (q = TMEM lane quarter, half) owns accumulator rows [32q, 32q + 32) and, of
+// the tile's BN columns, the half [half * BN/2, (half + 1) * BN/2); thread <-> accumulator row.
+// --------------------------------------------------------------------------------------------
+// general per-thread handling of one 32-column chunk: any dtype mix / alignment, ragged N edge
+static __device__ __noinline__ void epilogue_chunk_general(const GemmDev& g, const uint32_t* raw, const float* bs, int grow,
+                                                    long long orow, long long arow, int gcol0, int lim) {
+  const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
+  const bool fwd_act = g.act == VY_ACT_GELU_ERF || g.act == VY_ACT_GELU_TANH;
+  const bool bwd_act = g.act == VY_ACT_DGELU_ERF || g.act == VY_ACT_DGELU_TANH;
+  if (g.vec_ok && lim == 32) {
+#pragma unroll 1
+    for (int j4 = 0; j4 < 4; ++j4) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(raw[j4 * 8 + j]) + bs[j4 * 8 + j];
+      const int col = gcol0 + j4 * 8;
+      if (fwd_act) {
+        if (g.aux) st8_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + col, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = apply_act(g.act, x[j]);
+      } else if (bwd_act) {
+        float z[8];
+        ld8_as_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + col, z);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= apply_dact(g.act, z[j]);
+      }
+      if (g.addend) {
+        float a[8];
+        ld8_as_float(g.addend, g.addend_dtype, arow * g.ld_addend + col, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += a[j];
+      }
+      if (g.addend2) {
+        float a[8];
+        ld8_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(grow) * g.ld_addend2 + col, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += a[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] *= scale;
+      st8_from_float(g.out, g.out_dtype, orow * g.ld_out + col, x);
+    }
+  } else {
+    for (int j = 0; j < lim; ++j) {
+      const int col = gcol0 + j;
+      float x = __uint_as_float(raw[j]) + bs[j];
+      if (fwd_act) {
+        if (g.aux) st_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + col, x);
+        x = apply_act(g.act, x);
+      } else if (bwd_act) {
+        x *= apply_dact(g.act, ld_as_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + col));
+      }
+      if (g.addend) x += ld_as_float(g.addend, g.addend_dtype, arow * g.ld_addend + col);
+      if (g.addend2) x += ld_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(grow) * g.ld_addend2 + col);
+      st_from_float(g.out, g.out_dtype, orow * g.ld_out + col, x * scale);
+    }
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
+                                                int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
+                                                uint64_t* tmem_empty_bar, uint8_t* stage) {
+  constexpr int WC = BN >= 64 ? BN / 2 : BN;  // columns per warp
+  constexpr int NCH = WC / 32;
+  if (BN < 64 && half) {  // narrow tiles: one warp per lane quarter does all the columns
+    release_acc(tmem_empty_bar, lane);
+    return;
+  }
+  const int wcol0 = BN >= 64 ? half * WC : 0;
+  const int grow = m0 + q * 32 + lane;
+  const bool row_ok = grow < g.M;
+  const long long orow = remap_out_row(g, grow);
+  const long long arow = remap_add_row(g, grow);
+  const int gc0 = n0 + wcol0;  // first global column of this warp
+  // fast path: bf16 in and out, 16-byte aligned rows (a chunk that crosses N falls back)
+  const bool fast = g.vec_ok && g.out_dtype == VY_BF16 && (!g.aux || g.aux_dtype == VY_BF16) &&
+                    (!g.addend || g.addend_dtype == VY_BF16) && !g.addend2;
+
+  if (!fast) {
+    mbar_wait(tfull_bar, tfull_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t raw[32];
+      tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
+      tmem_ld_wait();
+      if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
+      const int nvalid = g.N - (gc0 + c * 32);
+      if (row_ok && nvalid > 0)
+        epilogue_chunk_general(g, raw, bias_s + wcol0 + c * 32, grow, orow, arow, gc0 + c * 32, nvalid < 32 ? nvalid : 32);
+    }
+    return;
+  }
+
+  const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
+  const bool fwd_act = g.act == VY_ACT_GELU_ERF || g.act == VY_ACT_GELU_TANH;
+  const bool bwd_act = g.act == VY_ACT_DGELU_ERF || g.act == VY_ACT_DGELU_TANH;
+  const bool save_aux = fwd_act && g.aux != nullptr;
+  // The one row operand the hot epilogues read (the saved pre-activation for DGELU, otherwise the
+  // residual / gradient-accumulation addend) is fetched for ALL of this warp's columns before the
+  // accumulator is awaited, so its latency hides behind the mainloop of this very tile.
+  constexpr int NPF = NCH < 2 ? NCH : 2;  // chunks in flight (register budget: 16 per chunk)
+  uint4 pf[NPF][4];
+  const __nv_bfloat16* pf_src = nullptr;
+  if (row_ok) {
+    if (bwd_act) pf_src = reinterpret_cast<const __nv_bfloat16*>(g.aux) + static_cast<long long>(grow) * g.ld_aux + gc0;
+    else if (g.addend) pf_src = reinterpret_cast<const __nv_bfloat16*>(g.addend) + arow * g.ld_addend + gc0;
+  }
+#pragma unroll
+  for (int c = 0; c < NPF; ++c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pf[c][j] = make_uint4(0u, 0u, 0u, 0u);
+      if (pf_src && gc0 + c * 32 + j * 8 + 8 <= g.N) pf[c][j] = *reinterpret_cast<const uint4*>(pf_src + c * 32 + j * 8);
+    }
+  }
+  // rows this lane writes in the coalesced phase (4 lanes per row, 8 rows per store instruction)
+  __nv_bfloat16* wb_out[4];
+  long long wb_aux_delta[4];  // aux row address relative to the out row address (elements)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + q * 32 + i * 8 + (lane >> 2);
+    wb_out[i] = r < g.M ? reinterpret_cast<__nv_bfloat16*>(g.out) + remap_out_row(g, r) * g.ld_out + gc0 + (lane & 3) * 8 : nullptr;
+    wb_aux_delta[i] = 0;
+    if (save_aux && r < g.M)
+      wb_aux_delta[i] = (reinterpret_cast<__nv_bfloat16*>(g.aux) + static_cast<long long>(r) * g.ld_aux + gc0 + (lane & 3) * 8) - wb_out[i];
+  }
+
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[32];
+    tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
+    tmem_ld_wait();
+    if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
+    const int gcol0 = gc0 + c * 32;
+    const int nvalid = g.N - gcol0;
+    const float* bs = bias_s + wcol0 + c * 32;
+    // this chunk's prefetched operand; its registers are refilled with chunk c + NPF right away
+    uint4 pc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pc[j] = pf[c % NPF][j];
+      if (c + NPF < NCH) {
+        pf[c % NPF][j] = make_uint4(0u, 0u, 0u, 0u);
+        if (pf_src && gcol0 + NPF * 32 + j * 8 + 8 <= g.N)
+          pf[c % NPF][j] = *reinterpret_cast<const uint4*>(pf_src + (c + NPF) * 32 + j * 8);
+      }
+    }
+    if (nvalid >= 32) {
+      const int sw = (lane >> 1) & 3;
+      uint8_t* srow = stage + lane * 64;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        float x[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(bs + j4 * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bs + j4 * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(raw[j4 * 8 + j]) + bb[j];
+        if (fwd_act) {
+          if (save_aux)
+            *reinterpret_cast<uint4*>(srow + GEMM_STAGE_OUT + ((j4 ^ sw) << 4)) =
+                make_uint4(pack2_bf16(x[0], x[1]), pack2_bf16(x[2], x[3]), pack2_bf16(x[4], x[5]), pack2_bf16(x[6], x[7]));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = apply_act(g.act, x[j]);
+        } else if (bwd_act) {
+          float z[8];
+          unpack8_bf16(pc[j4], z);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] *= apply_dact(g.act, z[j]);
+        }
+        if (g.addend) {
+          float a[8];
+          if (!bwd_act) {
+            unpack8_bf16(pc[j4], a);
+          } else if (row_ok) {
+            ld8_as_float(g.addend, VY_BF16, arow * g.ld_addend + gcol0 + j4 * 8, a);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] += a[j];
+        }
+        *reinterpret_cast<uint4*>(srow + ((j4 ^ sw) << 4)) =
+            make_uint4(pack2_bf16(x[0] * scale, x[1] * scale), pack2_bf16(x[2] * scale, x[3] * scale),
+                       pack2_bf16(x[4] * scale, x[5] * scale), pack2_bf16(x[6] * scale, x[7] * scale));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (wb_out[i]) {
+          *reinterpret_cast<uint4*>(wb_out[i] + c * 32) = staged_slot(stage, lane, i);
+          if (save_aux) *reinterpret_cast<uint4*>(wb_out[i] + wb_aux_delta[i] + c * 32) = staged_slot(stage + GEMM_STAGE_OUT, lane, i);
+        }
+      }
+      __syncwarp();
+    } else if (nvalid > 0 && row_ok) {
+      epilogue_chunk_general(g, raw, bs, grow, orow, arow, gcol0, nvalid);
+    }
+  }
+}
+
+// swap-AB epilogue: accumulator row = logical output COLUMN (a weight row), accumulator column =
+// logical output ROW (a token). Stores are scalar per thread but coalesced across the warp.
+template <int BN>
+__device__ __forceinline__ void epilogue_transposed(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
+                                                    int lane, uint64_t* tfull_bar, uint32_t tfull_phase,
+                                                    uint64_t* tmem_empty_bar) {
+  constexpr int WC = BN >= 64 ? BN / 2 : BN;
+  constexpr int NCH = WC / 32;
+  if (BN < 64 && half) {
+    release_acc(tmem_empty_bar, lane);
+    return;
+  }
+  const int wcol0 = BN >= 64 ? half * WC : 0;
+  const int lc = m0 + q * 32 + lane;  // logical column
+  const bool ok = lc < g.M;
+  const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
+  const bool fwd_act = g.act == VY_ACT_GELU_ERF || g.act == VY_ACT_GELU_TANH;
+  const bool bwd_act = g.act == VY_ACT_DGELU_ERF || g.act == VY_ACT_DGELU_TANH;
+  const float b = (ok && g.bias) ? ld_as_float(g.bias, g.bias_dtype, lc) : 0.f;
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[32];
+    tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
+    tmem_ld_wait();
+    if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
+    if (!ok) continue;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int lr = n0 + wcol0 + c * 32 + j;  // logical row
+      if (lr < g.N) {
+        float x = __uint_as_float(raw[j]) + b;
+        if (fwd_act) {
+          if (g.aux) st_from_float(g.aux, g.aux_dtype, static_cast<long long>(lr) * g.ld_aux + lc, x);
+          x = apply_act(g.act, x);
+        } else if (bwd_act) {
+          x *= apply_dact(g.act, ld_as_float(g.aux, g.aux_dtype, static_cast<long long>(lr) * g.ld_aux + lc));
+        }
+        if (g.addend) x += ld_as_float(g.addend, g.addend_dtype, remap_add_row(g, lr) * g.ld_addend + lc);
+        if (g.addend2) x += ld_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(lr) * g.ld_addend2 + lc);
+        st_from_float(g.out, g.out_dtype, remap_out_row(g, lr) * g.ld_out + lc, x * scale);
+      }
+    }
+  }
+}
+
+// QKV projection epilogue: bias + in-register half-split RoPE + head-split scatter (+ kv-cache
+// append through k_out/v_out strides). head_dim == 64: one 64-column group is one head. Of every
+// head the warp with half = 0 rotates the pairs j in [0,16) (columns j and j + 32), the other warp
+// the pairs j in [16,32) — so both warps stay busy for any number of heads per tile and a thread
+// has both members of each pair. bf16 destinations leave through the staging buffer as full
+// 32-byte sectors; fp32 destinations (an fp32 kv-cache) are written directly.
+template <int BN>
+__device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
+                                                  int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
+                                                  uint64_t* tmem_empty_bar, uint8_t* stage) {
+  const int grow = m0 + q * 32 + lane;
+  const bool row_ok = grow < g.M;
+  const int b = row_ok ? grow / g.tokens_per_seq : 0;
+  const int l = row_ok ? grow % g.tokens_per_seq : 0;
+  const int j0 = half * 16;
+  float cs[16], sn[16];
+  if (g.rope_cos) {
+    const float* cp = g.rope_cos + static_cast<long long>(g.start_pos + l) * 32 + j0;
+    const float* sp = g.rope_sin + static_cast<long long>(g.start_pos + l) * 32 + j0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 c4 = *reinterpret_cast<const float4*>(cp + j * 4);
+      const float4 s4 = *reinterpret_cast<const float4*>(sp + j * 4);
+      cs[j * 4] = c4.x; cs[j * 4 + 1] = c4.y; cs[j * 4 + 2] = c4.z; cs[j * 4 + 3] = c4.w;
+      sn[j * 4] = s4.x; sn[j * 4 + 1] = s4.y; sn[j * 4 + 2] = s4.z; sn[j * 4 + 3] = s4.w;
+    }
+  }
+  // (batch, token) of the rows this lane writes in the coalesced phase
+  int wb_b[4], wb_l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + q * 32 + i * 8 + (lane >> 2);
+    wb_b[i] = r < g.M ? r / g.tokens_per_seq : -1;
+    wb_l[i] = r < g.M ? r % g.tokens_per_seq : 0;
+  }
+  // this lane's 16-byte slot of a staged row: slots 0,1 = first-half columns j0.., slots 2,3 = columns 32 + j0..
+  const int slot_col = ((lane & 2) ? 32 : 0) + j0 + (lane & 1) * 8;
+
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+
+#pragma unroll 1
+  for (int hgrp = 0; hgrp < BN / 64; ++hgrp) {
+    uint32_t lo[16], hi[16];
+    tmem_ld_x16(tmem_acc + hgrp * 64 + j0, lo);
+    tmem_ld_x16(tmem_acc + hgrp * 64 + 32 + j0, hi);
+    tmem_ld_wait();
+    if (hgrp == BN / 64 - 1) release_acc(tmem_empty_bar, lane);
+    const int gcol0 = n0 + hgrp * 64;
+    if (gcol0 >= g.N) continue;
+    const int head = gcol0 >> 6;
+    uint8_t* dst;
+    long long sb, sh, sl;
+    int hh, tok0, dst_dt;
+    bool rotate;
+    if (head < g.n_q_heads) {
+      dst = reinterpret_cast<uint8_t*>(g.q_out); sb = g.q_sb; sh = g.q_sh; sl = g.q_sl;
+      hh = head; tok0 = 0; dst_dt = g.out_dtype; rotate = g.rope_cos != nullptr;
+    } else if (head < g.n_q_heads + g.n_kv_heads) {
+      dst = reinterpret_cast<uint8_t*>(g.k_out); sb = g.k_sb; sh = g.k_sh; sl = g.k_sl;
+      hh = head - g.n_q_heads; tok0 = g.kv_dst_pos0; dst_dt = g.kv_out_dtype; rotate = g.rope_cos != nullptr;
+    } else {
+      dst = reinterpret_cast<uint8_t*>(g.v_out); sb = g.v_sb; sh = g.v_sh; sl = g.v_sl;
+      hh = head - g.n_q_heads - g.n_kv_heads; tok0 = g.kv_dst_pos0; dst_dt = g.kv_out_dtype; rotate = false;
+    }
+    float o1[16], o2[16];
+    const float* bs = bias_s + hgrp * 64 + j0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x1 = __uint_as_float(lo[j]) + bs[j];
+      const float x2 = __uint_as_float(hi[j]) + bs[32 + j];
+      if (rotate) {
+        o1[j] = x1 * cs[j] - x2 * sn[j];
+        o2[j] = x2 * cs[j] + x1 * sn[j];
+      } else {
+        o1[j] = x1;
+        o2[j] = x2;
+      }
+    }
+    if (dst_dt == VY_BF16) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        pk[j] = pack2_bf16(o1[2 * j], o1[2 * j + 1]);
+        pk[8 + j] = pack2_bf16(o2[2 * j], o2[2 * j + 1]);
+      }
+      stage_rows_bf16(stage, lane, pk);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (wb_b[i] >= 0) {
+          __nv_bfloat16* rowp = reinterpret_cast<__nv_bfloat16*>(dst) + wb_b[i] * sb + hh * sh +
+                                static_cast<long long>(tok0 + wb_l[i]) * sl;
+          *reinterpret_cast<uint4*>(rowp + slot_col) = staged_slot(stage, lane, i);
+        }
+      }
+      __syncwarp();
+    } else if (row_ok) {
+      const long long off = b * sb + hh * sh + static_cast<long long>(tok0 + l) * sl;
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        float a[8], c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] = o1[h8 * 8 + j];
+          c[j] = o2[h8 * 8 + j];
+        }
+        st8_from_float(dst, dst_dt, off + j0 + h8 * 8, a);
+        st8_from_float(dst, dst_dt, off + 32 + j0 + h8 * 8, c);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel
+// --------------------------------------------------------------------------------------------
+template <typename TIn, int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ GemmDev g) {
+  using Cfg = GemmCfg<TIn, BN>;
+  constexpr int BM = Cfg::BM;
+  constexpr int BK = Cfg::BK;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(epi_stage + Cfg::EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned base
+
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], GEMM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint8_t* a_dst = sA + s * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + s * Cfg::B_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tma_a, &full_bar[s], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / Cfg::EPB; ++i)
+              tma_load_2d(a_dst + i * Cfg::MN_BOX_BYTES, &tma_a, &full_bar[s], m0 + i * Cfg::EPB, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(b_dst, &tma_b, &full_bar[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / Cfg::EPB; ++i)
+              tma_load_2d(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, &full_bar[s], n0 + i * Cfg::EPB, kb * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Cfg::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      uint32_t it = 0;
+      uint32_t local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
+            const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            if constexpr (sizeof(TIn) == 2) umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            else umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= GEMM_FIRST_EPI_WARP) {
+    // ===================== epilogue =====================
+    const int e = warp - GEMM_FIRST_EPI_WARP;
+    const int q = warp & 3;  // warp % 4: the TMEM lane quarter this warp may access
+    const int half = e >> 2;
+    const int et = threadIdx.x - GEMM_FIRST_EPI_WARP * 32;
+    uint8_t* stage = epi_stage + e * 2 * GEMM_STAGE_OUT;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1;
+      const uint32_t acc_ph = (local >> 1) & 1;
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      float* bs = bias_s + acc * BN;
+      if (!g.transposed_out) {
+        for (int j = et; j < BN; j += GEMM_EPI_WARPS * 32) {
+          const int col = n0 + j;
+          bs[j] = (g.bias && col < g.N) ? ld_as_float(g.bias, g.bias_dtype, col) : 0.f;
+        }
+        named_bar_sync(1, GEMM_EPI_WARPS * 32);
+      }
+      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (g.epi == VY_EPI_QKV_ROPE) {
+        if constexpr (BN >= 64)
+          epilogue_qkv_rope<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+      } else if (g.transposed_out) {
+        epilogue_transposed<BN>(g, tmem_acc, m0, n0, q, half, lane, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
+      } else {
+        epilogue_linear<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+static inline int get_tmap_2d(CUtensorMap* out, int dtype, const void* base, uint64_t d0, uint64_t d1,
+                       uint64_t stride1_bytes, uint32_t b0, uint32_t b1, int swz = 1) {
+  uint64_t dims[2] = {d0, d1};
+  uint64_t strides[2] = {0, stride1_bytes};
+  uint32_t box[2] = {b0, b1};
+  return get_tensor_map_cached(out, dtype, 2, base, dims, strides, box, swz);
+}
+
+template <typename TIn, int BN, bool A_MN, bool B_MN>
+int launch_gemm(const VyGemm* p, const GemmDev& g) {
+  using Cfg = GemmCfg<TIn, BN>;
+  const int dt = p->in_dtype;
+  const size_t es = sizeof(TIn);
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN)
+    rc = get_tmap_2d(&ta, dt, p->A, p->K, p->M, p->lda * es, Cfg::BK, Cfg::BM);
+  else
+    rc = get_tmap_2d(&ta, dt, p->A, p->M, p->K, p->lda * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
+  if (rc != VY_OK) return rc;
+  if (!B_MN)
+    rc = get_tmap_2d(&tb, dt, p->B, p->K, p->N, p->ldb * es, Cfg::BK, BN);
+  else
+    rc = get_tmap_2d(&tb, dt, p->B, p->N, p->K, p->ldb * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
+  if (rc != VY_OK) return rc;
+
+  auto kern = gemm_kernel<TIn, BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (p->M + Cfg::BM - 1) / Cfg::BM;
+  const int n_tiles = (p->N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream)>>>(ta, tb, g);
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+}  // namespace vy

@@ -138,6 +138,8 @@ class Trainer:
         self.use_graph = use_graph
         self._graph = None
         self._graph_key = None
+        self.graph_kernels = 0       # kernels of this library inside the captured step
+        self.replayed_kernels = 0    # ... launched so far through graph replays (vy_launch_count only sees eager calls)
         self.fp = FlatParams(model)
         n = self.fp.numel
         dev = self.fp.flat.device
@@ -210,6 +212,7 @@ class Trainer:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
+        self.replayed_kernels += self.graph_kernels
         return self._static_loss
 
     def _capture(self, key, pixel_values, input_ids, attention_mask, labels_full) -> None:
@@ -221,9 +224,12 @@ class Trainer:
                 self._caption_body(*self._static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
+        n0 = _lib.lib().vy_launch_count()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss = self._caption_body(*self._static_in)
+        self.graph_kernels = int(_lib.lib().vy_launch_count() - n0)
         self._graph_key = key
 
 
