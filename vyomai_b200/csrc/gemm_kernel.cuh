@@ -200,10 +200,11 @@ static __device__ __noinline__ void epilogue_chunk_general(const GemmDev& g, con
   }
 }
 
+// general epilogue: any dtype mix / alignment / activation, one 32-column chunk at a time
 template <int BN>
-__device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
-                                                int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
-                                                uint64_t* tmem_empty_bar, uint8_t* stage) {
+__device__ __forceinline__ void epilogue_linear_general(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
+                                                        int lane, const float* bias_s, uint64_t* tfull_bar,
+                                                        uint32_t tfull_phase, uint64_t* tmem_empty_bar) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;  // columns per warp
   constexpr int NCH = WC / 32;
   if (BN < 64 && half) {  // narrow tiles: one warp per lane quarter does all the columns
@@ -215,49 +216,65 @@ __device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_
   const bool row_ok = grow < g.M;
   const long long orow = remap_out_row(g, grow);
   const long long arow = remap_add_row(g, grow);
-  const int gc0 = n0 + wcol0;  // first global column of this warp
-  // fast path: bf16 in and out, 16-byte aligned rows (a chunk that crosses N falls back)
-  const bool fast = g.vec_ok && g.out_dtype == VY_BF16 && (!g.aux || g.aux_dtype == VY_BF16) &&
-                    (!g.addend || g.addend_dtype == VY_BF16) && !g.addend2;
-
-  if (!fast) {
-    mbar_wait(tfull_bar, tfull_phase);
-    tc_fence_after();
+  const int gc0 = n0 + wcol0;
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
-      uint32_t raw[32];
-      tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
-      tmem_ld_wait();
-      if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
-      const int nvalid = g.N - (gc0 + c * 32);
-      if (row_ok && nvalid > 0)
-        epilogue_chunk_general(g, raw, bias_s + wcol0 + c * 32, grow, orow, arow, gc0 + c * 32, nvalid < 32 ? nvalid : 32);
-    }
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[32];
+    tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
+    tmem_ld_wait();
+    if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
+    const int nvalid = g.N - (gc0 + c * 32);
+    if (row_ok && nvalid > 0)
+      epilogue_chunk_general(g, raw, bias_s + wcol0 + c * 32, grow, orow, arow, gc0 + c * 32, nvalid < 32 ? nvalid : 32);
+  }
+}
+
+// Fast epilogues (bf16 output / aux / addend, 16-byte aligned rows), one instantiation per fused
+// operation so that the per-element code is branch-free and small enough to stay in the instruction cache:
+enum { EPI_PLAIN = 0, EPI_ADD = 1, EPI_GELU = 2, EPI_DGELU = 3 };
+//   EPI_PLAIN  out = scale * (acc + bias)
+//   EPI_ADD    out = scale * (acc + bias + addend)                   (residual add / gradient accumulation)
+//   EPI_GELU   aux = acc + bias (if aux);  out = scale * gelu_erf(acc + bias)
+//   EPI_DGELU  out = scale * (acc + bias) * gelu_erf'(aux)
+// The row operand (addend / aux) of the first two chunks is fetched before the accumulator is awaited
+// and each later chunk's while its predecessor is being processed, so the loads hide behind the
+// mainloop and the math.
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
+                                                     int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
+                                                     uint64_t* tmem_empty_bar, uint8_t* stage) {
+  constexpr int WC = BN >= 64 ? BN / 2 : BN;
+  constexpr int NCH = WC / 32;
+  if (BN < 64 && half) {
+    release_acc(tmem_empty_bar, lane);
     return;
   }
-
+  const int wcol0 = BN >= 64 ? half * WC : 0;
+  const int grow = m0 + q * 32 + lane;
+  const bool row_ok = grow < g.M;
+  const int gc0 = n0 + wcol0;  // first global column of this warp
   const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
-  const bool fwd_act = g.act == VY_ACT_GELU_ERF || g.act == VY_ACT_GELU_TANH;
-  const bool bwd_act = g.act == VY_ACT_DGELU_ERF || g.act == VY_ACT_DGELU_TANH;
-  const bool save_aux = fwd_act && g.aux != nullptr;
-  // The one row operand the hot epilogues read (the saved pre-activation for DGELU, otherwise the
-  // residual / gradient-accumulation addend) is fetched for ALL of this warp's columns before the
-  // accumulator is awaited, so its latency hides behind the mainloop of this very tile.
-  constexpr int NPF = NCH < 2 ? NCH : 2;  // chunks in flight (register budget: 16 per chunk)
-  uint4 pf[NPF][4];
+  const bool save_aux = MODE == EPI_GELU && g.aux != nullptr;
+
   const __nv_bfloat16* pf_src = nullptr;
   if (row_ok) {
-    if (bwd_act) pf_src = reinterpret_cast<const __nv_bfloat16*>(g.aux) + static_cast<long long>(grow) * g.ld_aux + gc0;
-    else if (g.addend) pf_src = reinterpret_cast<const __nv_bfloat16*>(g.addend) + arow * g.ld_addend + gc0;
+    if (MODE == EPI_DGELU) pf_src = reinterpret_cast<const __nv_bfloat16*>(g.aux) + static_cast<long long>(grow) * g.ld_aux + gc0;
+    if (MODE == EPI_ADD) pf_src = reinterpret_cast<const __nv_bfloat16*>(g.addend) + remap_add_row(g, grow) * g.ld_addend + gc0;
   }
-#pragma unroll
-  for (int c = 0; c < NPF; ++c) {
+  uint4 pf[2][4];
+  auto fetch = [&](uint4 (&dst)[4], int c) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      pf[c][j] = make_uint4(0u, 0u, 0u, 0u);
-      if (pf_src && gc0 + c * 32 + j * 8 + 8 <= g.N) pf[c][j] = *reinterpret_cast<const uint4*>(pf_src + c * 32 + j * 8);
+      dst[j] = make_uint4(0u, 0u, 0u, 0u);
+      if ((MODE == EPI_DGELU || MODE == EPI_ADD) && pf_src && c < NCH && gc0 + c * 32 + j * 8 + 8 <= g.N)
+        dst[j] = *reinterpret_cast<const uint4*>(pf_src + c * 32 + j * 8);
     }
-  }
+  };
+  fetch(pf[0], 0);
+  fetch(pf[1], 1);
+
   // rows this lane writes in the coalesced phase (4 lanes per row, 8 rows per store instruction)
   __nv_bfloat16* wb_out[4];
   long long wb_aux_delta[4];  // aux row address relative to the out row address (elements)
@@ -269,33 +286,25 @@ __device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_
     if (save_aux && r < g.M)
       wb_aux_delta[i] = (reinterpret_cast<__nv_bfloat16*>(g.aux) + static_cast<long long>(r) * g.ld_aux + gc0 + (lane & 3) * 8) - wb_out[i];
   }
+  const int sw = (lane >> 1) & 3;
+  uint8_t* srow = stage + lane * 64;
 
   mbar_wait(tfull_bar, tfull_phase);
   tc_fence_after();
 
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
+  auto chunk = [&](int c, uint4 (&pfc)[4]) {
     uint32_t raw[32];
     tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
+    uint4 pc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pc[j] = pfc[j];
+    fetch(pfc, c + 2);
     tmem_ld_wait();
     if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
     const int gcol0 = gc0 + c * 32;
     const int nvalid = g.N - gcol0;
     const float* bs = bias_s + wcol0 + c * 32;
-    // this chunk's prefetched operand; its registers are refilled with chunk c + NPF right away
-    uint4 pc[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      pc[j] = pf[c % NPF][j];
-      if (c + NPF < NCH) {
-        pf[c % NPF][j] = make_uint4(0u, 0u, 0u, 0u);
-        if (pf_src && gcol0 + NPF * 32 + j * 8 + 8 <= g.N)
-          pf[c % NPF][j] = *reinterpret_cast<const uint4*>(pf_src + (c + NPF) * 32 + j * 8);
-      }
-    }
     if (nvalid >= 32) {
-      const int sw = (lane >> 1) & 3;
-      uint8_t* srow = stage + lane * 64;
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         float x[8];
@@ -304,28 +313,20 @@ __device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(raw[j4 * 8 + j]) + bb[j];
-        if (fwd_act) {
+        if (MODE == EPI_GELU) {
           if (save_aux)
             *reinterpret_cast<uint4*>(srow + GEMM_STAGE_OUT + ((j4 ^ sw) << 4)) =
                 make_uint4(pack2_bf16(x[0], x[1]), pack2_bf16(x[2], x[3]), pack2_bf16(x[4], x[5]), pack2_bf16(x[6], x[7]));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = apply_act(g.act, x[j]);
-        } else if (bwd_act) {
+          for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+        } else if (MODE == EPI_DGELU) {
           float z[8];
           unpack8_bf16(pc[j4], z);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] *= apply_dact(g.act, z[j]);
-        }
-        if (g.addend) {
+          for (int j = 0; j < 8; ++j) x[j] *= dgelu_erf(z[j]);
+        } else if (MODE == EPI_ADD) {
           float a[8];
-          if (!bwd_act) {
-            unpack8_bf16(pc[j4], a);
-          } else if (row_ok) {
-            ld8_as_float(g.addend, VY_BF16, arow * g.ld_addend + gcol0 + j4 * 8, a);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = 0.f;
-          }
+          unpack8_bf16(pc[j4], a);
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] += a[j];
         }
@@ -343,8 +344,14 @@ __device__ __forceinline__ void epilogue_linear(const GemmDev& g, uint32_t tmem_
       }
       __syncwarp();
     } else if (nvalid > 0 && row_ok) {
-      epilogue_chunk_general(g, raw, bs, grow, orow, arow, gcol0, nvalid);
+      epilogue_chunk_general(g, raw, bs, grow, remap_out_row(g, grow), remap_add_row(g, grow), gcol0, nvalid);
     }
+  };
+
+#pragma unroll 1
+  for (int c = 0; c < NCH; c += 2) {
+    chunk(c, pf[0]);
+    if (c + 1 < NCH) chunk(c + 1, pf[1]);
   }
 }
 
@@ -637,6 +644,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int half = e >> 2;
     const int et = threadIdx.x - GEMM_FIRST_EPI_WARP * 32;
     uint8_t* stage = epi_stage + e * 2 * GEMM_STAGE_OUT;
+    // which fused fast epilogue applies (-1: the general one)
+    int fast_mode = -1;
+    if (g.epi == VY_EPI_LINEAR && !g.transposed_out && g.vec_ok && g.out_dtype == VY_BF16 && !g.addend2) {
+      const bool aux16 = !g.aux || g.aux_dtype == VY_BF16;
+      if (g.act == VY_ACT_NONE) fast_mode = !g.addend ? EPI_PLAIN : (g.addend_dtype == VY_BF16 ? EPI_ADD : -1);
+      else if (g.act == VY_ACT_GELU_ERF && !g.addend && aux16) fast_mode = EPI_GELU;
+      else if (g.act == VY_ACT_DGELU_ERF && !g.addend && aux16) fast_mode = EPI_DGELU;
+    }
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const uint32_t acc = local & 1;
@@ -657,8 +672,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           epilogue_qkv_rope<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
       } else if (g.transposed_out) {
         epilogue_transposed<BN>(g, tmem_acc, m0, n0, q, half, lane, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
+      } else if (fast_mode == EPI_PLAIN) {
+        epilogue_linear_fast<BN, EPI_PLAIN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+      } else if (fast_mode == EPI_ADD) {
+        epilogue_linear_fast<BN, EPI_ADD>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+      } else if (fast_mode == EPI_GELU) {
+        epilogue_linear_fast<BN, EPI_GELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+      } else if (fast_mode == EPI_DGELU) {
+        epilogue_linear_fast<BN, EPI_DGELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
       } else {
-        epilogue_linear<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+        epilogue_linear_general<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
       }
     }
   }
