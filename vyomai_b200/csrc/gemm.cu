@@ -1,5 +1,7 @@
 // vy_gemm host side: argument checking, tile-width choice and dispatch to the kernel instantiations
 // (gemm_kernel.cuh; instantiated in gemm_inst_*.cu so the translation units build in parallel).
+#include <stdlib.h>
+
 #include "gemm_kernel.cuh"
 
 namespace vy {
@@ -101,6 +103,8 @@ extern "C" int vy_gemm(const VyGemm* p) {
 
   GemmDev g;
   memset(&g, 0, sizeof(g));
+  static const int dbg = getenv("VY_GEMM_DEBUG") ? atoi(getenv("VY_GEMM_DEBUG")) : 0;
+  g.debug = dbg;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.epi = p->epi; g.act = p->act; g.transposed_out = p->transposed_out;
   g.bias = p->bias; g.bias_dtype = p->bias_dtype;

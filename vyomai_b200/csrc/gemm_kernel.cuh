@@ -48,7 +48,15 @@ struct GemmDev {
   void* v_out;
   long long v_sb, v_sh, v_sl;
   int kv_out_dtype;
+  int debug;  // development switches (VY_GEMM_DEBUG): 1 = epilogue drains TMEM only, 2 = producer skips TMA after the first ring fill
 };
+
+#ifdef VY_GEMM_TRACE
+static __device__ long long vy_trace[10 * 16 * 4];  // [warp][tile][field] clock64 stamps of CTA 0
+#define VY_TRACE(w, t, f) do { if (blockIdx.x == 0 && (t) < 16 && (threadIdx.x & 31) == 0) vy_trace[((w) * 16 + (t)) * 4 + (f)] = clock64(); } while (0)
+#else
+#define VY_TRACE(w, t, f) do { } while (0)
+#endif
 
 constexpr int GEMM_EPI_WARPS = 8;                        // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int GEMM_FIRST_EPI_WARP = 2;                   // warp 0: TMEM allocator + TMA producer, warp 1: MMA issuer
@@ -238,13 +246,21 @@ enum { EPI_PLAIN = 0, EPI_ADD = 1, EPI_GELU = 2, EPI_DGELU = 3 };
 //   EPI_ADD    out = scale * (acc + bias + addend)                   (residual add / gradient accumulation)
 //   EPI_GELU   aux = acc + bias (if aux);  out = scale * gelu_erf(acc + bias)
 //   EPI_DGELU  out = scale * (acc + bias) * gelu_erf'(aux)
-// The row operand (addend / aux) of the first two chunks is fetched before the accumulator is awaited
-// and each later chunk's while its predecessor is being processed, so the loads hide behind the
-// mainloop and the math.
+// Software pipeline per warp: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed; the
+// row operand (addend / aux) of the first two chunks is fetched before the accumulator is awaited and
+// each later chunk's while its predecessor is processed; the two staging buffers alternate so one
+// __syncwarp per chunk suffices. (With EPI_GELU + aux both buffers are used by every chunk.)
+__device__ __forceinline__ void store_ragged8(__nv_bfloat16* dst, const uint4& v, int n) {
+  const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < n) dst[k] = e[k];
+}
+
 template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
                                                      int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
-                                                     uint64_t* tmem_empty_bar, uint8_t* stage) {
+                                                     uint64_t* tmem_empty_bar, uint8_t* stage, int trace_tile) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;
   constexpr int NCH = WC / 32;
   if (BN < 64 && half) {
@@ -265,11 +281,12 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
   }
   uint4 pf[2][4];
   auto fetch = [&](uint4 (&dst)[4], int c) {
+    if (MODE == EPI_DGELU || MODE == EPI_ADD) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dst[j] = make_uint4(0u, 0u, 0u, 0u);
-      if ((MODE == EPI_DGELU || MODE == EPI_ADD) && pf_src && c < NCH && gc0 + c * 32 + j * 8 + 8 <= g.N)
-        dst[j] = *reinterpret_cast<const uint4*>(pf_src + c * 32 + j * 8);
+      for (int j = 0; j < 4; ++j) {
+        dst[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (pf_src && c < NCH && gc0 + c * 32 + j * 8 + 8 <= g.N) dst[j] = *reinterpret_cast<const uint4*>(pf_src + c * 32 + j * 8);
+      }
     }
   };
   fetch(pf[0], 0);
@@ -287,72 +304,99 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
       wb_aux_delta[i] = (reinterpret_cast<__nv_bfloat16*>(g.aux) + static_cast<long long>(r) * g.ld_aux + gc0 + (lane & 3) * 8) - wb_out[i];
   }
   const int sw = (lane >> 1) & 3;
-  uint8_t* srow = stage + lane * 64;
 
   mbar_wait(tfull_bar, tfull_phase);
   tc_fence_after();
+  VY_TRACE(2 + half * 4 + ((q + 2) & 3), trace_tile, 1);
 
-  auto chunk = [&](int c, uint4 (&pfc)[4]) {
-    uint32_t raw[32];
-    tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
+  auto process = [&](int c, const uint32_t (&raw)[32], uint4 (&pfc)[4], uint8_t* stg) {
     uint4 pc[4];
+    if (MODE == EPI_DGELU || MODE == EPI_ADD) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pc[j] = pfc[j];
-    fetch(pfc, c + 2);
-    tmem_ld_wait();
-    if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
-    const int gcol0 = gc0 + c * 32;
-    const int nvalid = g.N - gcol0;
+      for (int j = 0; j < 4; ++j) pc[j] = pfc[j];
+      fetch(pfc, c + 2);
+    }
+    const int nvalid = g.N - (gc0 + c * 32);
+    if (nvalid <= 0) return;
     const float* bs = bias_s + wcol0 + c * 32;
-    if (nvalid >= 32) {
+    uint8_t* srow = stg + lane * 64;
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        float x[8];
-        const float4 b0 = *reinterpret_cast<const float4*>(bs + j4 * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bs + j4 * 8 + 4);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int j4 = 0; j4 < 4; ++j4) {
+      float x[8];
+      const float4 b0 = *reinterpret_cast<const float4*>(bs + j4 * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bs + j4 * 8 + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(raw[j4 * 8 + j]) + bb[j];
-        if (MODE == EPI_GELU) {
-          if (save_aux)
-            *reinterpret_cast<uint4*>(srow + GEMM_STAGE_OUT + ((j4 ^ sw) << 4)) =
-                make_uint4(pack2_bf16(x[0], x[1]), pack2_bf16(x[2], x[3]), pack2_bf16(x[4], x[5]), pack2_bf16(x[6], x[7]));
+      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(raw[j4 * 8 + j]) + bb[j];
+      if (MODE == EPI_GELU) {
+        if (save_aux)
+          *reinterpret_cast<uint4*>(stage + GEMM_STAGE_OUT + lane * 64 + ((j4 ^ sw) << 4)) =
+              make_uint4(pack2_bf16(x[0], x[1]), pack2_bf16(x[2], x[3]), pack2_bf16(x[4], x[5]), pack2_bf16(x[6], x[7]));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
-        } else if (MODE == EPI_DGELU) {
-          float z[8];
-          unpack8_bf16(pc[j4], z);
+        for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+      } else if (MODE == EPI_DGELU) {
+        float z[8];
+        unpack8_bf16(pc[j4], z);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] *= dgelu_erf(z[j]);
-        } else if (MODE == EPI_ADD) {
-          float a[8];
-          unpack8_bf16(pc[j4], a);
+        for (int j = 0; j < 8; ++j) x[j] *= dgelu_erf(z[j]);
+      } else if (MODE == EPI_ADD) {
+        float a[8];
+        unpack8_bf16(pc[j4], a);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] += a[j];
-        }
-        *reinterpret_cast<uint4*>(srow + ((j4 ^ sw) << 4)) =
-            make_uint4(pack2_bf16(x[0] * scale, x[1] * scale), pack2_bf16(x[2] * scale, x[3] * scale),
-                       pack2_bf16(x[4] * scale, x[5] * scale), pack2_bf16(x[6] * scale, x[7] * scale));
+        for (int j = 0; j < 8; ++j) x[j] += a[j];
       }
-      __syncwarp();
+      *reinterpret_cast<uint4*>(srow + ((j4 ^ sw) << 4)) =
+          make_uint4(pack2_bf16(x[0] * scale, x[1] * scale), pack2_bf16(x[2] * scale, x[3] * scale),
+                     pack2_bf16(x[4] * scale, x[5] * scale), pack2_bf16(x[6] * scale, x[7] * scale));
+    }
+    __syncwarp();
+    if (nvalid >= 32) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (wb_out[i]) {
-          *reinterpret_cast<uint4*>(wb_out[i] + c * 32) = staged_slot(stage, lane, i);
+          *reinterpret_cast<uint4*>(wb_out[i] + c * 32) = staged_slot(stg, lane, i);
           if (save_aux) *reinterpret_cast<uint4*>(wb_out[i] + wb_aux_delta[i] + c * 32) = staged_slot(stage + GEMM_STAGE_OUT, lane, i);
         }
       }
-      __syncwarp();
-    } else if (nvalid > 0 && row_ok) {
-      epilogue_chunk_general(g, raw, bs, grow, remap_out_row(g, grow), remap_add_row(g, grow), gcol0, nvalid);
+    } else {  // the chunk crosses N: element-wise predicated stores
+      const int n = nvalid - (lane & 3) * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (wb_out[i]) {
+          store_ragged8(wb_out[i] + c * 32, staged_slot(stg, lane, i), n);
+          if (save_aux) store_ragged8(wb_out[i] + wb_aux_delta[i] + c * 32, staged_slot(stage + GEMM_STAGE_OUT, lane, i), n);
+        }
+      }
     }
+    if (save_aux) __syncwarp();  // the aux buffer is reused by the very next chunk
   };
 
+  uint32_t raw_a[32], raw_b[32];
+  const uint32_t taddr = tmem_acc + wcol0;
+  const int trace_w = 2 + half * 4 + ((q + 2) & 3);
+  (void)trace_w;
+  tmem_ld_x32(taddr, raw_a);
 #pragma unroll 1
-  for (int c = 0; c < NCH; c += 2) {
-    chunk(c, pf[0]);
-    if (c + 1 < NCH) chunk(c + 1, pf[1]);
+  for (int c = 0; c + 1 < NCH; c += 2) {  // chunk pairs (c -> buffer 0, c + 1 -> buffer 1)
+    tmem_ld_wait();
+    tmem_ld_x32(taddr + (c + 1) * 32, raw_b);
+    process(c, raw_a, pf[0], stage);
+    tmem_ld_wait();
+    if (c + 2 < NCH) {
+      tmem_ld_x32(taddr + (c + 2) * 32, raw_a);
+    } else {
+      release_acc(tmem_empty_bar, lane);
+      VY_TRACE(trace_w, trace_tile, 2);
+    }
+    process(c + 1, raw_b, pf[1], save_aux ? stage : stage + GEMM_STAGE_OUT);
   }
+  if (NCH & 1) {  // odd chunk count: the last one is alone
+    tmem_ld_wait();
+    release_acc(tmem_empty_bar, lane);
+    VY_TRACE(trace_w, trace_tile, 2);
+    process(NCH - 1, raw_a, pf[0], stage);
+  }
+  __syncwarp();  // the next tile's first chunk reuses stage buffer 0
 }
 
 // swap-AB epilogue: accumulator row = logical output COLUMN (a weight row), accumulator column =
@@ -584,6 +628,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if ((g.debug & 2) && it >= STAGES) {
+            mbar_arrive(&full_bar[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           uint8_t* a_dst = sA + s * Cfg::A_BYTES;
           uint8_t* b_dst = sB + s * Cfg::B_BYTES;
@@ -613,8 +661,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const uint32_t acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
+        VY_TRACE(1, local, 0);
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
+        VY_TRACE(1, local, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -635,6 +685,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[acc]);
+        VY_TRACE(1, local, 2);
       }
     }
   } else if (warp >= GEMM_FIRST_EPI_WARP) {
@@ -648,9 +699,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int fast_mode = -1;
     if (g.epi == VY_EPI_LINEAR && !g.transposed_out && g.vec_ok && g.out_dtype == VY_BF16 && !g.addend2) {
       const bool aux16 = !g.aux || g.aux_dtype == VY_BF16;
-      if (g.act == VY_ACT_NONE) fast_mode = !g.addend ? EPI_PLAIN : (g.addend_dtype == VY_BF16 ? EPI_ADD : -1);
+      const bool n8 = (g.N & 7) == 0;  // the prefetched row operand is read in 8-column vectors
+      if (g.act == VY_ACT_NONE) fast_mode = !g.addend ? EPI_PLAIN : ((g.addend_dtype == VY_BF16 && n8) ? EPI_ADD : -1);
       else if (g.act == VY_ACT_GELU_ERF && !g.addend && aux16) fast_mode = EPI_GELU;
-      else if (g.act == VY_ACT_DGELU_ERF && !g.addend && aux16) fast_mode = EPI_DGELU;
+      else if (g.act == VY_ACT_DGELU_ERF && !g.addend && aux16 && n8) fast_mode = EPI_DGELU;
     }
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
@@ -659,6 +711,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
       float* bs = bias_s + acc * BN;
+      VY_TRACE(2 + e, local, 0);
       if (!g.transposed_out) {
         for (int j = et; j < BN; j += GEMM_EPI_WARPS * 32) {
           const int col = n0 + j;
@@ -667,22 +720,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         named_bar_sync(1, GEMM_EPI_WARPS * 32);
       }
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if (g.epi == VY_EPI_QKV_ROPE) {
+      if (g.debug & 1) {
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        release_acc(&tempty_bar[acc], lane);
+      } else if (g.epi == VY_EPI_QKV_ROPE) {
         if constexpr (BN >= 64)
           epilogue_qkv_rope<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
       } else if (g.transposed_out) {
         epilogue_transposed<BN>(g, tmem_acc, m0, n0, q, half, lane, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
       } else if (fast_mode == EPI_PLAIN) {
-        epilogue_linear_fast<BN, EPI_PLAIN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+        epilogue_linear_fast<BN, EPI_PLAIN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
       } else if (fast_mode == EPI_ADD) {
-        epilogue_linear_fast<BN, EPI_ADD>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+        epilogue_linear_fast<BN, EPI_ADD>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
       } else if (fast_mode == EPI_GELU) {
-        epilogue_linear_fast<BN, EPI_GELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+        epilogue_linear_fast<BN, EPI_GELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
       } else if (fast_mode == EPI_DGELU) {
-        epilogue_linear_fast<BN, EPI_DGELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+        epilogue_linear_fast<BN, EPI_DGELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
       } else {
         epilogue_linear_general<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
       }
+      VY_TRACE(2 + e, local, 3);
     }
   }
 
@@ -692,6 +750,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+#ifdef VY_GEMM_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t0 = vy_trace[(1 * 16 + 0) * 4 + 0];
+    for (int t = 0; t < 9; ++t) {
+      printf("tile %d MMA: start %lld tempty_ok %lld issued %lld\n", t, vy_trace[(16 + t) * 4] - t0, vy_trace[(16 + t) * 4 + 1] - t0, vy_trace[(16 + t) * 4 + 2] - t0);
+      for (int w = 2; w < 10; w += 3)
+        printf("   epi w%d: top %lld tfull %lld released %lld end %lld\n", w, vy_trace[(w * 16 + t) * 4] - t0, vy_trace[(w * 16 + t) * 4 + 1] - t0,
+               vy_trace[(w * 16 + t) * 4 + 2] - t0, vy_trace[(w * 16 + t) * 4 + 3] - t0);
+    }
+  }
+#endif
 }
 
 // --------------------------------------------------------------------------------------------
