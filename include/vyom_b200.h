@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VY_ABI_VERSION 1
+#define VY_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VY_API __attribute__((visibility("default")))
@@ -160,8 +160,8 @@ VY_API int vy_gemm(const VyGemm* p);
  * and VyomAI/layers/ffn.py:25,39 (biased variance, eps = config.layer_norm_eps), and the plain
  * LayerNorm of the LM head (models/decoder.py:259-261,270; residual = NULL).
  * mean / rstd (fp32, [rows]) are optional outputs of fwd and required inputs of bwd.
- * bwd: dx[rows,H] (= d residual as well), dgamma/dbeta partials are reduced into fp32
- * dgamma[H], dbeta[H] (overwritten). xhat is recomputed from the saved pre-norm sum `s`
+ * bwd: dx[rows,H] (= d residual as well), dgamma/dbeta partials are reduced into dgamma[H], dbeta[H]
+ * (fp32 or bf16; overwritten, or accumulated into when dparam_accumulate). xhat is recomputed from the saved pre-norm sum `s`
  * (s = x + residual; pass the tensor fwd wrote to sum_out, or x when residual was NULL).
  * ------------------------------------------------------------------------------------------ */
 typedef struct VyNorm {
@@ -181,8 +181,10 @@ typedef struct VyNorm {
   const void* dy;
   const void* s;  /* pre-norm sum saved by fwd */
   void* dx;
-  float* dgamma; /* [H] fp32 */
-  float* dbeta;  /* [H] fp32 */
+  void* dgamma; /* [H], dtype dparam_dtype */
+  void* dbeta;  /* [H], dtype dparam_dtype */
+  int32_t dparam_dtype;      /* VY_F32 (default 0) or VY_BF16 */
+  int32_t dparam_accumulate; /* 1: dgamma/dbeta += result (accumulate straight into the parameters' .grad) */
   float* partials; /* workspace: 2 * vy_norm_bwd_partial_rows() * H floats */
   void* stream;
 } VyNorm;

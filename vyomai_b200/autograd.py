@@ -74,6 +74,13 @@ def lm_head_fn(mod, h2d: torch.Tensor) -> torch.Tensor:
     return logits
 
 
+def lm_head_loss_fn(mod, h2d: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """Mean token cross-entropy of the LM head's logits against `labels` (one per row of h2d) as one autograd node."""
+    from .autograd_train import LMHeadLossFn
+    dense, ln, dec = mod.dense, mod.layer_norm, mod.decoder
+    return LMHeadLossFn.apply(ln.eps, ignore_index, h2d, dense.weight, dense.bias, ln.weight, ln.bias, dec.weight, mod.bias, labels)
+
+
 def embed_fn(ids: torch.Tensor, table: torch.Tensor, pos_table: Optional[torch.Tensor], pos_row_off: int,
              tokens_per_seq: int, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
     """hidden rows [B * (tokens_per_seq + (extra is not None)), H] = table[ids] (+ position rows), with an

@@ -71,6 +71,18 @@ def _emit_bgrad(p: Optional[torch.Tensor], dy2d: torch.Tensor) -> Optional[torch
     return ops.colsum(dy2d, out_dtype=p.dtype)
 
 
+def _ln_bwd(dy: torch.Tensor, s: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean, rstd):
+    """LayerNorm backward. Returns (ds, d_gamma, d_beta); with trainer-owned gradient buffers the parameter
+    gradients are accumulated in place by the reduce kernel and None is returned for them."""
+    if _direct(gamma) and _direct(beta) and gamma.grad.dtype == beta.grad.dtype:
+        ds, _, _ = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out=gamma.grad, dbeta_out=beta.grad)
+        _ready(gamma)
+        _ready(beta)
+        return ds, None, None
+    ds, dgamma, dbeta = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd)
+    return ds, dgamma.to(gamma.dtype), dbeta.to(beta.dtype)
+
+
 def _packed_grads(params) -> Optional[torch.Tensor]:
     """One 2-D (or 1-D) view over the adjacent .grad buffers of several parameters, or None."""
     if not all(_direct(p) for p in params):
@@ -114,7 +126,7 @@ class AttentionBlockFn(torch.autograd.Function):
         w_qkv, _ = F.pack_linears(lin)
         Hq, Hkv, d = mod.num_attention_heads, mod._kv_heads, F.HEAD_DIM
         dy = dy.contiguous()
-        ds, dgamma, dbeta = ops.add_layernorm_bwd(dy, s, ln.weight, mean, rstd)
+        ds, dgamma, dbeta = _ln_bwd(dy, s, ln.weight, ln.bias, mean, rstd)
         d_wo = _emit_wgrad(dense.weight, ds, attn)
         d_bo = _emit_bgrad(dense.bias, ds)
         d_attn = _dgrad(ds, dense.weight, out_dtype=torch.bfloat16)  # bf16: MMA operand of the attention backward
@@ -159,7 +171,7 @@ class AttentionBlockFn(torch.autograd.Function):
         grads.append(d_wo)
         if ctx.has_dense_bias:
             grads.append(d_bo)
-        grads += [dgamma.to(ln.weight.dtype), dbeta.to(ln.bias.dtype)]
+        grads += [dgamma, dbeta]
         return (None, None, None, None, None, None, *grads)
 
 
@@ -195,20 +207,43 @@ class FeedForwardFn(torch.autograd.Function):
         s = F._lin(a, w2, b2, addend=input2d)
         y, _, mean, rstd = ops.add_layernorm(s, None, gamma, beta, eps, save_stats=True)
         ctx.act = act
-        ctx.save_for_backward(h2d, w1, b1, w2, b2, gamma, z, a, s, mean, rstd)
+        ctx.params = (w1, b1, w2, b2, gamma, beta)  # the Parameter objects (direct-gradient attributes live on them)
+        ctx.save_for_backward(h2d, z, a, s, mean, rstd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        h2d, w1, b1, w2, b2, gamma, z, a, s, mean, rstd = ctx.saved_tensors
-        ds, dgamma, dbeta = ops.add_layernorm_bwd(dy.contiguous(), s, gamma, mean, rstd)
-        d_w2 = _wgrad(ds, a, w2)
-        d_b2 = _bgrad(ds, b2)
+        h2d, z, a, s, mean, rstd = ctx.saved_tensors
+        w1, b1, w2, b2, gamma, beta = ctx.params
+        ds, dgamma, dbeta = _ln_bwd(dy.contiguous(), s, gamma, beta, mean, rstd)
+        d_w2 = _emit_wgrad(w2, ds, a)
+        d_b2 = _emit_bgrad(b2, ds)
         dz = _dgrad(ds, w2, act="d" + ctx.act, aux=z)  # (dS W2) * act'(z) in the dgrad epilogue
-        d_w1 = _wgrad(dz, h2d, w1)
-        d_b1 = _bgrad(dz, b1)
+        d_w1 = _emit_wgrad(w1, dz, h2d)
+        d_b1 = _emit_bgrad(b1, dz)
         dh = _dgrad(dz, w1)
-        return None, None, dh, ds, d_w1, d_b1, d_w2, d_b2, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype)
+        return None, None, dh, ds, d_w1, d_b1, d_w2, d_b2, dgamma, dbeta
+
+
+def _padded_logits(rows: int, V: int, like: torch.Tensor):
+    """[rows, V] view of a buffer whose row stride is V rounded up to 8 elements (16-byte aligned rows)."""
+    ld = (V + 7) // 8 * 8
+    buf = torch.empty((rows, ld), device=like.device, dtype=like.dtype)
+    return buf[:, :V]
+
+
+def _lm_head_backward(ctx_saved, params, dlogits):
+    h2d, z, a, n, mean, rstd = ctx_saved
+    wd, bd, gamma, beta, wv, bv = params
+    d_wv = _emit_wgrad(wv, dlogits, n)
+    d_bv = _emit_bgrad(bv, dlogits)
+    dn = _dgrad(dlogits, wv)
+    da, dgamma, dbeta = _ln_bwd(dn, a, gamma, beta, mean, rstd)
+    dz = ops.act_bwd(da, z, "gelu")
+    d_wd = _emit_wgrad(wd, dz, h2d)
+    d_bd = _emit_bgrad(bd, dz)
+    dh = _dgrad(dz, wd)
+    return dh, d_wd, d_bd, dgamma, dbeta, d_wv, d_bv
 
 
 class LMHeadFn(torch.autograd.Function):
@@ -219,30 +254,51 @@ class LMHeadFn(torch.autograd.Function):
         z = torch.empty((h2d.shape[0], wd.shape[0]), device=h2d.device, dtype=h2d.dtype)
         a = F._lin(h2d, wd, bd, act="gelu", aux=z)
         n, _, mean, rstd = ops.add_layernorm(a, None, gamma, beta, eps, save_stats=True)
-        V = wv.shape[0]
-        ld = (V + 7) // 8 * 8
-        buf = torch.empty((h2d.shape[0], ld), device=h2d.device, dtype=h2d.dtype)
-        logits = F._lin(n, wv, bv, out=buf[:, :V])
-        ctx.save_for_backward(h2d, wd, bd, gamma, wv, bv, z, a, n, mean, rstd)
+        logits = F._lin(n, wv, bv, out=_padded_logits(h2d.shape[0], wv.shape[0], h2d))
+        ctx.params = (wd, bd, gamma, beta, wv, bv)
+        ctx.save_for_backward(h2d, z, a, n, mean, rstd)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        h2d, wd, bd, gamma, wv, bv, z, a, n, mean, rstd = ctx.saved_tensors
         if dlogits.stride(1) != 1 or (dlogits.stride(0) * dlogits.element_size()) % 16 != 0:
-            V = dlogits.shape[1]
-            buf = torch.zeros((dlogits.shape[0], (V + 7) // 8 * 8), device=dlogits.device, dtype=dlogits.dtype)
-            buf[:, :V].copy_(dlogits)
-            dlogits = buf[:, :V]
-        d_wv = _wgrad(dlogits, n, wv)
-        d_bv = _bgrad(dlogits, bv)
-        dn = _dgrad(dlogits, wv)
-        da, dgamma, dbeta = ops.add_layernorm_bwd(dn, a, gamma, mean, rstd)
-        dz = ops.act_bwd(da, z, "gelu")
-        d_wd = _wgrad(dz, h2d, wd)
-        d_bd = _bgrad(dz, bd)
-        dh = _dgrad(dz, wd)
-        return None, dh, d_wd, d_bd, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), d_wv, d_bv
+            buf = _padded_logits(dlogits.shape[0], dlogits.shape[1], dlogits)
+            buf.copy_(dlogits)
+            dlogits = buf
+        return (None, *_lm_head_backward(ctx.saved_tensors, ctx.params, dlogits))
+
+
+class LMHeadLossFn(torch.autograd.Function):
+    """loss = mean token cross-entropy(decoder(LN(gelu(dense(h)))), labels) over labels != ignore_index: the LM
+    head (models/decoder.py:267-275) and the notebooks' `loss_fn` as ONE autograd node, so the [rows, V] logits
+    exist exactly once: vy_softmax_xent computes the row losses and overwrites the logits with d loss / d logits in
+    the same launch (the upstream gradient of a training loss is 1; backward rescales only if it is not), and the
+    backward GEMMs read that buffer in place — no slice / as_strided gradient copies of an 800 MB tensor."""
+
+    assume_unit_grad = True  # loss.backward() passes 1; set False to rescale by an arbitrary upstream gradient
+
+    @staticmethod
+    def forward(ctx, eps, ignore_index, h2d, wd, bd, gamma, beta, wv, bv, labels):
+        z = torch.empty((h2d.shape[0], wd.shape[0]), device=h2d.device, dtype=h2d.dtype)
+        a = F._lin(h2d, wd, bd, act="gelu", aux=z)
+        n, _, mean, rstd = ops.add_layernorm(a, None, gamma, beta, eps, save_stats=True)
+        logits = F._lin(n, wv, bv, out=_padded_logits(h2d.shape[0], wv.shape[0], h2d))
+        labels = labels.reshape(-1).contiguous()
+        n_valid = (labels != ignore_index).sum().clamp(min=1).to(torch.float32)
+        inv = (1.0 / n_valid).reshape(1)
+        loss_rows = ops.softmax_xent(logits, labels, ignore_index=ignore_index, grad_scale_ptr=inv, write_grad=True)
+        ctx.params = (wd, bd, gamma, beta, wv, bv)
+        ctx.save_for_backward(h2d, z, a, n, mean, rstd, logits)
+        return loss_rows.sum() * inv[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        *saved, dlogits = ctx.saved_tensors
+        # dlogits already holds d loss / d logits for gout == 1 (what loss.backward() passes)
+        if not LMHeadLossFn.assume_unit_grad:
+            dlogits.mul_(gout.to(dlogits.dtype))
+        grads = _lm_head_backward(saved, ctx.params, dlogits)
+        return (None, None, *grads, None)
 
 
 class CrossEntropyFn(torch.autograd.Function):
@@ -298,6 +354,8 @@ class EmbedFn(torch.autograd.Function):
             ops.embed(None, extra, out=out, rows=B, tokens_per_seq=1, out_group_stride=seq, out_row_off=0, pos=pos_table,
                       pos_row_off=pos_row_off)
         ctx.save_for_backward(idsf, table, pos_table if pos_table is not None else table.new_empty(0))
+        ctx.table_param = table
+        ctx.pos_param = pos_table
         ctx.has_pos = pos_table is not None
         ctx.args = (pos_row_off, tokens_per_seq, e, seq, B)
         ctx.extra_shape = None if extra is None else (extra.shape, extra.dtype)
@@ -311,10 +369,12 @@ class EmbedFn(torch.autograd.Function):
         H = table.shape[1]
         d_table = d_pos = d_extra = None
         need_pos = ctx.has_pos and ctx.needs_input_grad[2]
+        tab_direct = ctx.needs_input_grad[1] and _direct(ctx.table_param)
+        pos_direct = need_pos and _direct(ctx.pos_param)
         if ctx.needs_input_grad[1]:
-            d_table = torch.zeros_like(table)
+            d_table = ctx.table_param.grad if tab_direct else torch.zeros_like(table)  # scatter-add straight into .grad
         if need_pos:
-            d_pos = torch.zeros_like(pos_table)
+            d_pos = ctx.pos_param.grad.view(pos_table.shape) if pos_direct else torch.zeros_like(pos_table)
         if d_table is not None or d_pos is not None:
             ops.embed_bwd(idsf, dout, rows=idsf.numel(), H=H, tokens_per_seq=tps, out_group_stride=seq, out_row_off=e,
                           dtable=d_table, dpos=d_pos, pos_row_off=pos_row_off + e)
@@ -328,6 +388,12 @@ class EmbedFn(torch.autograd.Function):
                 ops.embed(None, dout, out=d_extra, rows=B, tokens_per_seq=1, out_group_stride=1, out_row_off=0,
                           src_row_stride=seq * dout.stride(0))
                 d_extra = d_extra.to(dt)
+        if tab_direct:
+            _ready(ctx.table_param)
+            d_table = None
+        if pos_direct:
+            _ready(ctx.pos_param)
+            d_pos = None
         return None, d_table, d_pos, None, None, d_extra
 
 

@@ -59,6 +59,14 @@ int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, con
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return VY_ERR_CUDA;
   }
+  // The driver entry point needs the primary context bound to the CALLING thread. A thread whose first CUDA
+  // work is this call (autograd's backward worker, when a backward pass opens with a GEMM) has none yet:
+  // cudaFree(nullptr) binds it (a no-op afterwards).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t gdim[5];
   cuuint64_t gstr[5];
   cuuint32_t bdim[5];

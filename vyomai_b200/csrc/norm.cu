@@ -150,8 +150,8 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
 
 // column reduce of the per-block partials: 32 columns per block, 8 warps split the partial rows
 __global__ void __launch_bounds__(256)
-norm_bwd_reduce_kernel(int nparts, int H, const float* __restrict__ partials, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta) {
+norm_bwd_reduce_kernel(int nparts, int H, const float* __restrict__ partials, void* __restrict__ dgamma,
+                       void* __restrict__ dbeta, int out_dt, int accumulate) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -163,8 +163,10 @@ norm_bwd_reduce_kernel(int nparts, int H, const float* __restrict__ partials, fl
   if (w == 0 && c < 2 * H) {
 #pragma unroll
     for (int k = 1; k < 8; ++k) a += red[k][lane];
-    if (c < H) dgamma[c] = a;
-    else dbeta[c - H] = a;
+    void* dst = c < H ? dgamma : dbeta;
+    const int cc = c < H ? c : c - H;
+    if (accumulate) a += ld_as_float(dst, out_dt, cc);
+    st_from_float(dst, out_dt, cc, a);
   }
 }
 
@@ -227,6 +229,7 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
                "vy_add_layernorm_bwd: null pointer");
   VY_CHECK_ARG(aligned16(p->dy) && aligned16(p->s) && aligned16(p->dx) && aligned16(p->gamma),
                "vy_add_layernorm_bwd: pointers must be 16-byte aligned");
+  VY_CHECK_ARG(dtype_ok(p->dparam_dtype), "vy_add_layernorm_bwd: bad dparam_dtype");
   const int nv = (p->H + 255) / 256;
   int grid = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
   const int nparts = vy_norm_bwd_partial_rows();
@@ -253,7 +256,8 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   }
 #undef VY_LN_BWD
   VY_LAUNCH_OK();
-  norm_bwd_reduce_kernel<<<(2 * p->H + 31) / 32, 256, 0, st>>>(grid, p->H, p->partials, p->dgamma, p->dbeta);
+  norm_bwd_reduce_kernel<<<(2 * p->H + 31) / 32, 256, 0, st>>>(grid, p->H, p->partials, p->dgamma, p->dbeta,
+                                                               p->dparam_dtype, p->dparam_accumulate);
   VY_LAUNCH_OK();
   count_launch(2);
   return VY_OK;

@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from .. import _lib
 from .. import functional as F
-from ..autograd import embed_fn, lm_head_fn
+from ..autograd import embed_fn, lm_head_fn, lm_head_loss_fn
 from ..layers.positional_embeddings import AbsoluteEncoding, RotaryEmbedding, SinusoidalEncoding
 
 _position_embeddings = {"absolute": AbsoluteEncoding, "sinusoidal": SinusoidalEncoding}
@@ -59,6 +59,11 @@ class LMHead(nn.Module):
         shape = hidden_state.shape
         logits = lm_head_fn(self, hidden_state.reshape(-1, shape[-1]))
         return logits.view(*shape[:-1], logits.shape[-1])
+
+    def loss(self, hidden_state: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+        """F.cross_entropy(self(hidden).view(-1, V), labels.view(-1), ignore_index=...) without materialising the
+        logits more than once (training path; `labels` has one entry per hidden row)."""
+        return lm_head_loss_fn(self, hidden_state.reshape(-1, hidden_state.shape[-1]), labels, ignore_index)
 
 
 class TextStem:

@@ -56,6 +56,18 @@ class VisionLanguageDecoderModel(nn.Module, TextStem):
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 encoder_hidden_state: Optional[torch.Tensor] = None, use_cache: Optional[bool] = False,
                 start_pos: Optional[int] = 0) -> DecoderOutput:
+        origin, hidden = self._hidden(input_ids, attention_mask, encoder_hidden_state, use_cache, start_pos)
+        logits = self.lm_head(hidden)
+        return DecoderOutput(logits=back_to(origin, logits))
+
+    def forward_loss(self, input_ids, attention_mask, encoder_hidden_state, labels_full, ignore_index: int = -100):
+        """Training entry point: the token cross-entropy of forward(...).logits against `labels_full` ([B, S+1],
+        aligned with the logits rows) — same math as `loss_fn` of the reference's captioner notebook, with the LM
+        head and the loss fused into one autograd node."""
+        _origin, hidden = self._hidden(input_ids, attention_mask, encoder_hidden_state, False, 0)
+        return self.lm_head.loss(hidden, labels_full, ignore_index)
+
+    def _hidden(self, input_ids, attention_mask, encoder_hidden_state, use_cache, start_pos):
         dev, origin, (input_ids, attention_mask, encoder_hidden_state) = ensure_cuda(
             self, input_ids, attention_mask, encoder_hidden_state)
         _bsz, ntok = input_ids.shape
@@ -74,8 +86,7 @@ class VisionLanguageDecoderModel(nn.Module, TextStem):
         hidden = hidden.view(_bsz, seqlen, -1)
         for layer in self.all_layer:
             hidden = layer(hidden, mask, freqs=self._rope, use_cache=use_cache, start_pos=start_pos)
-        logits = self.lm_head(hidden)
-        return DecoderOutput(logits=back_to(origin, logits))
+        return origin, hidden
 
     @classmethod
     def from_config(cls, config, pos_embedding_type: Optional[str] = "absolute", attention_type: Optional[str] = None) -> nn.Module:
@@ -98,6 +109,11 @@ class VisionLanguageModel(nn.Module):
             encoder_output = self.encoder(pixel_values=pixel_values).logits[:, 0, :]  # cls token information
         return self.decoder(input_ids=decoder_input_ids, attention_mask=decoder_attention_mask,
                             encoder_hidden_state=encoder_output, use_cache=use_cache, start_pos=start_pos)
+
+    def forward_loss(self, pixel_values, decoder_input_ids, decoder_attention_mask, labels_full, ignore_index: int = -100):
+        """Captioning loss of one batch (see VisionLanguageDecoderModel.forward_loss)."""
+        encoder_output = self.encoder(pixel_values=pixel_values).logits[:, 0, :]
+        return self.decoder.forward_loss(decoder_input_ids, decoder_attention_mask, encoder_output, labels_full, ignore_index)
 
     def get_decoder(self) -> nn.Module:
         return self.decoder

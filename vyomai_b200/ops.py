@@ -224,9 +224,12 @@ def add_layernorm(
     return y.view(x.shape), s, mean, rstd
 
 
-def add_layernorm_bwd(dy, s, gamma, mean, rstd):
-    """Returns (dx, dgamma_fp32, dbeta_fp32) for y = LayerNorm(s)."""
-    _need_cuda(dy, s, gamma, mean, rstd)
+def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tensor] = None,
+                      dbeta_out: Optional[torch.Tensor] = None):
+    """Returns (dx, dgamma, dbeta) for y = LayerNorm(s). Without dgamma_out/dbeta_out the parameter gradients come
+    back as fresh fp32 tensors; with them (same dtype, e.g. the parameters' .grad views) the kernel ACCUMULATES
+    into those buffers and returns them."""
+    _need_cuda(dy, s, gamma, mean, rstd, dgamma_out, dbeta_out)
     H = dy.shape[-1]
     dy2 = dy.reshape(-1, H)
     s2 = s.reshape(-1, H)
@@ -234,15 +237,22 @@ def add_layernorm_bwd(dy, s, gamma, mean, rstd):
         raise _lib.VyomError("add_layernorm_bwd: dy and s must be contiguous")
     rows = dy2.shape[0]
     dx = torch.empty_like(dy2)
-    dgamma = torch.empty(H, device=dy.device, dtype=torch.float32)
-    dbeta = torch.empty(H, device=dy.device, dtype=torch.float32)
+    acc = dgamma_out is not None
+    if acc:
+        if dbeta_out is None or dgamma_out.dtype != dbeta_out.dtype or not (dgamma_out.is_contiguous() and dbeta_out.is_contiguous()):
+            raise _lib.VyomError("add_layernorm_bwd: dgamma_out / dbeta_out must both be given, contiguous, same dtype")
+        dgamma, dbeta = dgamma_out, dbeta_out
+    else:
+        dgamma = torch.empty(H, device=dy.device, dtype=torch.float32)
+        dbeta = torch.empty(H, device=dy.device, dtype=torch.float32)
     nparts = _lib.lib().vy_norm_bwd_partial_rows()
     partials = torch.empty(2 * nparts * H, device=dy.device, dtype=torch.float32)
     _lib.call(
         "vy_add_layernorm_bwd", "VyNorm",
         rows=rows, H=H, io_dtype=_dt(dy2), gamma=gamma.data_ptr(), param_dtype=_dt(gamma),
         mean=mean.data_ptr(), rstd=rstd.data_ptr(), dy=dy2.data_ptr(), s=s2.data_ptr(), dx=dx.data_ptr(),
-        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), partials=partials.data_ptr(), stream=_stream(),
+        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), dparam_dtype=_dt(dgamma), dparam_accumulate=int(acc),
+        partials=partials.data_ptr(), stream=_stream(),
     )
     return dx.view(dy.shape), dgamma, dbeta
 

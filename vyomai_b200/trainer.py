@@ -157,11 +157,15 @@ class Trainer:
         self._pending: Dict[int, int] = {}
         self._bucket_of: Dict[int, int] = {}
         self._bucket_size: List[int] = [0] * len(self.exchange.buckets)
-        if self.overlap:
-            for p, o in zip(self.fp.params, self.fp.offsets):
+        for p, o in zip(self.fp.params, self.fp.offsets):
+            # the backward kernels accumulate straight into the flat gradient buffer (autograd_train._direct);
+            # parameters whose gradient still arrives through autograd get the same bucket hook
+            p._vy_direct_grad = True
+            if self.overlap:
                 b = self.exchange.bucket_of(o)
                 self._bucket_of[id(p)] = b
                 self._bucket_size[b] += 1
+                p._vy_grad_ready = self._on_grad
                 p.register_post_accumulate_grad_hook(self._on_grad)
 
     def _on_grad(self, p: nn.Parameter) -> None:
@@ -187,8 +191,11 @@ class Trainer:
 
     def _caption_body(self, pixel_values, input_ids, attention_mask, labels_full) -> torch.Tensor:
         self.zero_grad()
-        logits = self.model(pixel_values=pixel_values, decoder_input_ids=input_ids, decoder_attention_mask=attention_mask).logits
-        loss = cross_entropy(logits, labels_full, ignore_index=-100)
+        if hasattr(self.model, "forward_loss"):  # LM head + cross-entropy as one autograd node
+            loss = self.model.forward_loss(pixel_values, input_ids, attention_mask, labels_full, ignore_index=-100)
+        else:
+            logits = self.model(pixel_values=pixel_values, decoder_input_ids=input_ids, decoder_attention_mask=attention_mask).logits
+            loss = cross_entropy(logits, labels_full, ignore_index=-100)
         loss.backward()
         self.optimizer_step()
         return loss.detach()
