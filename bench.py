@@ -22,6 +22,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own version / debug prints go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 WORKLOAD = "captioner_train_vit224p16L4_dec768L8gqa4_rope_rpad_S128"
 PER_GPU_BATCH = 64
@@ -293,7 +295,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators that were captured into CUDA graphs do not always tear down cleanly
+        # (destroy_process_group was seen to hang after the result line was out): synchronise, then leave.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
