@@ -315,6 +315,9 @@ def attn_bwd():
         (2, 4, 2, 300, False, "right", False),
         (1, 6, 2, 197, False, None, False),
         (2, 4, 4, 130, True, "left", True),
+        (2, 12, 12, 197, False, None, False),
+        (2, 3, 3, 256, True, "right", True),
+        (3, 6, 2, 100, True, "right", True),
     ]
     for (B, Hq, Hkv, S, causal, pad, use_rope) in cases:
         d = 64

@@ -14,6 +14,8 @@
 // The epilogues multiply by 1/sqrt(d), undo the RoPE rotation of q / k (transpose rotation) and
 // write straight into the packed [tokens, (Hq + 2 Hkv) * 64] gradient of the fused q|k|v projection.
 // Masks follow vy_attn_fwd exactly (finite "finfo.min" scores, -inf beyond Skv).
+#include <stdlib.h>
+
 #include "vy_common.cuh"
 #include "vy_ptx.cuh"
 
@@ -535,6 +537,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   }
 }
 
+int attn_bwd_fused_launch(const VyAttnBwd* p);  // attn_bwd_fused.cu: 1 = handled, 0 = shape not covered, < 0 = error
+
 static int make_map4(CUtensorMap* out, const void* base, int S, int H, int B, long long sb, long long sh, long long sl) {
   uint64_t dims[4] = {static_cast<uint64_t>(AB_D), static_cast<uint64_t>(S), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
   uint64_t strides[4] = {0, static_cast<uint64_t>(sl) * 2, static_cast<uint64_t>(sh) * 2, static_cast<uint64_t>(sb) * 2};
@@ -578,6 +582,19 @@ extern "C" int vy_attn_bwd(const VyAttnBwd* p) {
     attn_dsum_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(p->B, p->n_q_heads, p->Sq, p->o, p->o_sb, p->o_sl, p->o_dtype,
                                                                p->dout, p->do_sb, p->do_sl, VY_BF16, p->dsum);
     VY_LAUNCH_OK();
+  }
+
+  {
+    // short sequences: one fused kernel per (batch row, kv head); VY_ATTN_BWD_FUSED=0 forces the two-kernel path
+    static const bool fused_on = !(getenv("VY_ATTN_BWD_FUSED") && atoi(getenv("VY_ATTN_BWD_FUSED")) == 0);
+    if (fused_on) {
+      const int f = attn_bwd_fused_launch(p);
+      if (f < 0) return f;
+      if (f == 1) {
+        count_launch(2);
+        return VY_OK;
+      }
+    }
   }
 
   CUtensorMap tq, tk, tv, tdo;
