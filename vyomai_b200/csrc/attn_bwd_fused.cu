@@ -69,9 +69,27 @@ __device__ __forceinline__ void af_store_chunk(uint8_t* base, int row, int c4, c
   }
 }
 
+// rotation factors of one token for the pairs j0 .. j0+16 (four 16-byte loads per table)
+struct AfRope {
+  float cs[16], sn[16];
+  int row;  // table row held, -1 = none
+};
+__device__ __forceinline__ void af_load_rope(AfRope& r, const float* cos_t, const float* sin_t, int row, int j0) {
+  if (!cos_t || r.row == row) return;
+  const float4* cp = reinterpret_cast<const float4*>(cos_t + static_cast<long long>(row) * 32 + j0);
+  const float4* sp = reinterpret_cast<const float4*>(sin_t + static_cast<long long>(row) * 32 + j0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 c4 = cp[j], s4 = sp[j];
+    r.cs[j * 4] = c4.x; r.cs[j * 4 + 1] = c4.y; r.cs[j * 4 + 2] = c4.z; r.cs[j * 4 + 3] = c4.w;
+    r.sn[j * 4] = s4.x; r.sn[j * 4 + 1] = s4.y; r.sn[j * 4 + 2] = s4.z; r.sn[j * 4 + 3] = s4.w;
+  }
+  r.row = row;
+}
+
 // One warp writes its 16 rotation pairs (columns j0..j0+16 and 32+j0..) of a 64-wide gradient row held in TMEM.
 __device__ __forceinline__ void af_store_half_row(uint32_t taddr, int j0, void* dst, int dt, long long off, bool row_ok,
-                                                  float scale, const float* cs, const float* sn) {
+                                                  float scale, bool rotate, const AfRope& r) {
   uint32_t lo[16], hi[16];
   tmem_ld_x16(taddr + j0, lo);
   tmem_ld_x16(taddr + 32 + j0, hi);
@@ -83,8 +101,8 @@ __device__ __forceinline__ void af_store_half_row(uint32_t taddr, int j0, void* 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float a = __uint_as_float(lo[h8 * 8 + j]) * scale, b = __uint_as_float(hi[h8 * 8 + j]) * scale;
-      if (cs) {
-        const float c = cs[j0 + h8 * 8 + j], s = sn[j0 + h8 * 8 + j];
+      if (rotate) {
+        const float c = r.cs[h8 * 8 + j], s = r.sn[h8 * 8 + j];
         o1[j] = a * c + b * s;  // transpose of the forward rotation
         o2[j] = b * c - a * s;
       } else {
@@ -277,10 +295,21 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const int et = threadIdx.x - 64;
     const int j0 = half * 16;
     int dq_flushes = 0, dkdv_flushes = 0;
+    const bool rotate = g.rope_cos != nullptr;
+    AfRope rope;
+    rope.row = -1;
+    const int rope_max = (g.Sq > g.Skv ? g.Sq : g.Skv) - 1;  // rows beyond the sequences are never stored: clamp their loads
 
     for (int it = 0; it < n_it; ++it) {
       const int head = it_head(it), kt = it_kt(it), qt = it_qt(it);
       const int key = kt * AF_T + row;
+      {
+        // rotation factors of the row this iteration's flush needs (query row first), fetched before the softmax so
+        // the loads are long done when the accumulators arrive
+        const bool dq_done_ = mode_b ? (kt == KT - 1) : true;
+        const int need = dq_done_ ? qt * AF_T + row : key;
+        af_load_rope(rope, g.rope_cos, g.rope_sin, g.rope_pos0 + (need < rope_max ? need : rope_max), j0);
+      }
       const bool key_in = key < g.Skv;
       const bool key_vis = key_in && (!g.kpm || g.kpm[b * g.kpm_sb + key] != 0);
       const int q0 = qt * AF_T;
@@ -345,11 +374,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         tc_fence_after();
         const int qrow = q0 + row;
         const bool q_in = qrow < g.Sq;
-        const float* cs = g.rope_cos ? g.rope_cos + static_cast<long long>(g.rope_pos0 + qrow) * 32 : nullptr;
-        const float* sn = g.rope_sin ? g.rope_sin + static_cast<long long>(g.rope_pos0 + qrow) * 32 : nullptr;
+        af_load_rope(rope, g.rope_cos, g.rope_sin, g.rope_pos0 + (qrow < rope_max ? qrow : rope_max), j0);
         af_store_half_row(tm_dQ + (mode_b ? qt * AF_D : 0) + lane_off, j0, g.dq, g.out_dtype,
-                          (static_cast<long long>(b) * g.Sq + qrow) * g.ld_dq + head * AF_D, q_in, g.scale, q_in ? cs : nullptr,
-                          q_in ? sn : nullptr);
+                          (static_cast<long long>(b) * g.Sq + qrow) * g.ld_dq + head * AF_D, q_in, g.scale, rotate, rope);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);
@@ -359,11 +386,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         ++dkdv_flushes;
         tc_fence_after();
         const long long tok = static_cast<long long>(b) * g.Skv + key;
-        const float* cs = g.rope_cos ? g.rope_cos + static_cast<long long>(g.rope_pos0 + key) * 32 : nullptr;
-        const float* sn = g.rope_sin ? g.rope_sin + static_cast<long long>(g.rope_pos0 + key) * 32 : nullptr;
-        af_store_half_row(tm_dV + lane_off, j0, g.dv, g.out_dtype, tok * g.ld_dv + kvh * AF_D, key_in, 1.f, nullptr, nullptr);
-        af_store_half_row(tm_dK + lane_off, j0, g.dk, g.out_dtype, tok * g.ld_dk + kvh * AF_D, key_in, g.scale,
-                          key_in ? cs : nullptr, key_in ? sn : nullptr);
+        af_store_half_row(tm_dV + lane_off, j0, g.dv, g.out_dtype, tok * g.ld_dv + kvh * AF_D, key_in, 1.f, false, rope);
+        af_load_rope(rope, g.rope_cos, g.rope_sin, g.rope_pos0 + (key < rope_max ? key : rope_max), j0);
+        af_store_half_row(tm_dK + lane_off, j0, g.dk, g.out_dtype, tok * g.ld_dk + kvh * AF_D, key_in, g.scale, rotate, rope);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dkdv_empty);
