@@ -149,6 +149,13 @@ typedef struct VyGemm {
   int64_t v_sb, v_sh, v_sl;
   int32_t kv_out_dtype; /* dtype of k_out / v_out (a kv-cache may be fp32 while q_out is bf16) */
 
+  /* optional split-K scratch (fp32). When a GEMM has too few output tiles to fill the SMs and a long K (the
+   * weight gradients dW = dY^T X, K = tokens), the library splits K over several CTAs per tile, writes fp32
+   * partial tiles here and finishes with a reduce kernel that applies bias / addend / scale. It uses as many
+   * splits as fit in workspace_bytes (>= splits * M * N * 4); NULL / 0 disables split-K. */
+  void* workspace;
+  int64_t workspace_bytes;
+
   void* stream;
 } VyGemm;
 

@@ -67,6 +67,7 @@ def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=
             k2["addend"] = adds[i]
         if epi == "accum":
             k2["addend"] = outs[i]
+            k2["allow_split_k"] = True
         ops.gemm(a, b, out=outs[i], **k2)
 
     def qkv(i):

@@ -98,6 +98,19 @@ def _gemm_cases(dtype, tol):
     ref = 2 * ((a.float() @ w.float().t() + bias.float()).view(Bn, P, Hd) + pos.float()[1:])
     ok &= report("patch remap", outb.view(Bn, P + 1, Hd)[:, 1:], ref, tol)
     ok &= bool((outb.view(Bn, P + 1, Hd)[:, 0] == 0).all().item())
+    # split-K (weight-gradient shapes: few output tiles, K = tokens), accumulating into the output buffer
+    for (M, N, K) in [(768, 768, 8192), (1280, 768, 8192), (2304, 768, 12608), (768, 3072, 4096), (520, 264, 5000)]:
+        K8 = (K + 7) // 8 * 8
+        at = torch.randn(K8, M, device=dev, dtype=dtype) / K8 ** 0.5   # logical A = at.t() (MN-major)
+        bt = torch.randn(K8, N, device=dev, dtype=dtype)
+        acc0 = torch.randn(M, N, device=dev, dtype=dtype)
+        ref = acc0.float() + 0.5 * (at.float().t() @ bt.float())
+        out = acc0.clone()
+        ops.gemm(at.t(), bt.t(), out=out, addend=None, out_scale=1.0, allow_split_k=True)
+        ok &= report(f"splitK {M}x{N}x{K8} plain", out, at.float().t() @ bt.float(), tol * 2)
+        out = (2 * acc0).clone()
+        ops.gemm(at.t(), bt.t(), out=out, addend=out, out_scale=0.5, allow_split_k=True)
+        ok &= report(f"splitK {M}x{N}x{K8} accum*0.5", out, ref, tol * 2)
     return ok
 
 

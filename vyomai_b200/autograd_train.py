@@ -22,7 +22,7 @@ from .functional import MaskSpec
 
 def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, like: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     """dW[out, in] = dY^T X: both operands are read MN-major from their row-major storage."""
-    return ops.gemm(dy2d.t(), x2d.t(), out_dtype=like.dtype, out_scale=scale)
+    return ops.gemm(dy2d.t(), x2d.t(), out_dtype=like.dtype, out_scale=scale, allow_split_k=True)
 
 
 def _dgrad(dy2d: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
@@ -55,7 +55,7 @@ def _ready(p) -> None:
 def _emit_wgrad(p: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor) -> Optional[torch.Tensor]:
     if _direct(p):
         g2 = p.grad.view(p.grad.shape[0], -1)
-        ops.gemm(dy2d.t(), x2d.t(), out=g2, addend=g2)
+        ops.gemm(dy2d.t(), x2d.t(), out=g2, addend=g2, allow_split_k=True)
         _ready(p)
         return None
     return _wgrad(dy2d, x2d, p).view(p.shape)
@@ -143,7 +143,7 @@ class AttentionBlockFn(torch.autograd.Function):
         grads = [dx]
         gw = _packed_grads([l.weight for l in lin])
         if gw is not None:  # one wgrad GEMM accumulating into the adjacent q|k|v gradient buffers
-            ops.gemm(dqkv.t(), x2d.t(), out=gw, addend=gw)
+            ops.gemm(dqkv.t(), x2d.t(), out=gw, addend=gw, allow_split_k=True)
             for l in lin:
                 _ready(l.weight)
                 grads.append(None)

@@ -53,16 +53,22 @@ static int dispatch_gemm(const VyGemm* p, const GemmDev& g, int bn) {
 #undef VY_GEMM_CASE
 }
 
-// Tile width: the persistent grid walks ceil(tiles / SMs) waves of 128 x BN tiles, so the cost of a
-// candidate is waves * BN, weighted by how well a tile of that width feeds the tensor pipe (at BN <= 128
-// the A + B shared-memory reads per MMA reach the 128 B/clk of the SM; narrow tiles also amortise the
-// fixed per-tile cost worse). Ties go to the wider tile.
-static int choose_bn(int M, int N, bool mn_major, bool qkv) {
+// Tile width and K split. The persistent grid walks ceil(units / SMs) waves of 128 x BN x (K / splits) units; a
+// candidate is scored with a small time model calibrated on B200 (tools/gemm_bench.py): a 128 x 256 x 64 k-block
+// costs ~0.6 us of an SM at the sustained rate, a unit pays ~6 k-blocks for pipeline fill + epilogue, tiles of
+// BN <= 128 feed the tensor pipe worse (A + B shared-memory reads per MMA reach the SM's 128 B/clk), and split-K
+// adds a reduce pass over the fp32 slabs (launch gap + bytes at ~3 TB/s). Ties go to the wider tile / fewer splits.
+struct Tiling {
+  int bn, splits;
+};
+static Tiling choose_tiling(int M, int N, int num_kb, bool mn_major, bool qkv, int max_splits) {
   static const int cand[5] = {256, 192, 128, 64, 32};
   static const double pen[5] = {1.0, 1.0, 1.12, 1.6, 2.6};
+  static const int split_cand[6] = {1, 2, 3, 4, 6, 8};
   const int m_tiles = (M + 127) / 128;
   const int sms = num_sms();
-  int best = 256;
+  const double unit_fixed = 6.0;  // k-blocks' worth of fill + epilogue per unit
+  Tiling best = {256, 1};
   double best_cost = 1e30;
   for (int i = 0; i < 5; ++i) {
     const int bn = cand[i];
@@ -70,14 +76,60 @@ static int choose_bn(int M, int N, bool mn_major, bool qkv) {
     if (qkv && bn < 64) continue;
     if (bn > 32 && bn / 2 >= N) continue;  // more than half of the tile would be padding
     const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
-    const long long waves = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * bn * pen[i];
-    if (cost < best_cost * 0.999) {
-      best_cost = cost;
-      best = bn;
+    for (int si = 0; si < 6; ++si) {
+      const int sp = split_cand[si];
+      if (sp > max_splits) break;
+      if (sp > 1 && num_kb / sp < 16) break;  // keep the mainloop of a unit long enough to amortise its epilogue
+      const int kb_per = (num_kb + sp - 1) / sp;
+      if (sp > 1 && static_cast<long long>(sp - 1) * kb_per >= num_kb) continue;  // an empty last split
+      const long long waves = (tiles * sp + sms - 1) / sms;
+      double cost = static_cast<double>(waves) * (kb_per + unit_fixed) * 0.6 * (bn / 256.0) * pen[i];  // us
+      if (sp > 1) cost += 4.0 + (static_cast<double>(sp) * 8.0 + 4.0) * M * N / 3.0e6;
+      if (cost < best_cost * 0.999) {
+        best_cost = cost;
+        best.bn = bn;
+        best.splits = sp;
+      }
     }
   }
   return best;
+}
+
+// out[r, c] = scale * (sum_s ws[s][r][c] + bias[c] + addend[r, c]) — finishes a split-K GEMM. 8 columns per thread.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ ws, const void* __restrict__ bias, int bias_dt,
+                     const void* __restrict__ addend, long long ld_addend, int addend_dt, float scale, void* __restrict__ out,
+                     long long ld_out, int out_dt) {
+  const long long nvec = static_cast<long long>(M) * (N >> 3);
+  const long long slab = static_cast<long long>(M) * N;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(v / (N >> 3));
+    const int c = static_cast<int>(v % (N >> 3)) * 8;
+    float acc[8];
+    ld8_as_float(ws, VY_F32, static_cast<long long>(r) * N + c, acc);
+    for (int s = 1; s < splits; ++s) {
+      float t[8];
+      ld8_as_float(ws, VY_F32, s * slab + static_cast<long long>(r) * N + c, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += t[j];
+    }
+    if (bias) {
+      float t[8];
+      ld8_as_float(bias, bias_dt, c, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += t[j];
+    }
+    if (addend) {
+      float t[8];
+      ld8_as_float(addend, addend_dt, static_cast<long long>(r) * ld_addend + c, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= scale;
+    st8_from_float(out, out_dt, static_cast<long long>(r) * ld_out + c, acc);
+  }
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -164,7 +216,35 @@ extern "C" int vy_gemm(const VyGemm* p) {
     return VY_ERR_INVALID_ARG;
   }
 
-  const int bn = choose_bn(p->M, p->N, p->a_mn_major || p->b_mn_major, p->epi == VY_EPI_QKV_ROPE);
+  const int bk = p->in_dtype == VY_BF16 ? 64 : 32;
+  const int num_kb = (p->K + bk - 1) / bk;
+  // split-K is offered for plain linear epilogues (what the weight gradients use) when the caller lent scratch space
+  int max_splits = 1;
+  if (p->workspace && p->epi == VY_EPI_LINEAR && p->act == VY_ACT_NONE && !p->transposed_out && !p->addend2 && !p->aux &&
+      p->out_row_group == 0 && p->addend_row_mod == 0 && (p->N & 7) == 0 && g.vec_ok && aligned16(p->workspace) &&
+      (!p->bias || aligned16(p->bias))) {
+    const long long per = static_cast<long long>(p->M) * p->N * 4;
+    max_splits = static_cast<int>(p->workspace_bytes / per < 8 ? p->workspace_bytes / per : 8);
+    if (max_splits < 1) max_splits = 1;
+  }
+  const Tiling tl = choose_tiling(p->M, p->N, num_kb, p->a_mn_major || p->b_mn_major, p->epi == VY_EPI_QKV_ROPE, max_splits);
+  const int bn = tl.bn;
+  g.k_splits = tl.splits;
+  g.kb_per_split = (num_kb + tl.splits - 1) / tl.splits;
+  g.ws = static_cast<float*>(p->workspace);
+  if (tl.splits > 1) {
+    const int rc = p->in_dtype == VY_BF16 ? dispatch_gemm<__nv_bfloat16>(p, g, bn) : dispatch_gemm<float>(p, g, bn);
+    if (rc != VY_OK) return rc;
+    const long long nvec = static_cast<long long>(p->M) * (p->N >> 3);
+    long long blocks = (nvec + 255) / 256;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+        p->M, p->N, tl.splits, g.ws, p->bias, p->bias_dtype, p->addend, p->ld_addend, p->addend_dtype,
+        p->out_scale == 0.f ? 1.f : p->out_scale, p->out, p->ld_out, p->out_dtype);
+    VY_LAUNCH_OK();
+    count_launch();
+    return VY_OK;
+  }
 
   if (p->in_dtype == VY_BF16) return dispatch_gemm<__nv_bfloat16>(p, g, bn);
   return dispatch_gemm<float>(p, g, bn);

@@ -48,6 +48,8 @@ struct GemmDev {
   void* v_out;
   long long v_sb, v_sh, v_sl;
   int kv_out_dtype;
+  int k_splits, kb_per_split;  // split-K: unit = (tile, split); raw fp32 partial tiles go to ws[split][M][N]
+  float* ws;
   int debug;  // development switches (VY_GEMM_DEBUG): 1 = epilogue drains TMEM only, 2 = producer skips TMA after the first ring fill
 };
 
@@ -399,6 +401,37 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
   __syncwarp();  // the next tile's first chunk reuses stage buffer 0
 }
 
+// split-K epilogue: the raw fp32 accumulators of this (tile, split) unit go to the workspace slab of the split;
+// vy_gemm's reduce kernel sums the slabs and applies bias / addend / scale.
+template <int BN>
+__device__ __forceinline__ void epilogue_splitk(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half, int lane,
+                                                int split, uint64_t* tfull_bar, uint32_t tfull_phase, uint64_t* tmem_empty_bar) {
+  constexpr int WC = BN >= 64 ? BN / 2 : BN;
+  constexpr int NCH = WC / 32;
+  if (BN < 64 && half) {
+    release_acc(tmem_empty_bar, lane);
+    return;
+  }
+  const int wcol0 = BN >= 64 ? half * WC : 0;
+  const int grow = m0 + q * 32 + lane;
+  float* dst = g.ws + (static_cast<long long>(split) * g.M + grow) * g.N + n0 + wcol0;
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[32];
+    tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
+    tmem_ld_wait();
+    if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
+    if (grow < g.M) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n0 + wcol0 + c * 32 + j * 4 + 4 <= g.N)  // N % 8 == 0 on this path
+          *reinterpret_cast<uint4*>(dst + c * 32 + j * 4) = make_uint4(raw[j * 4], raw[j * 4 + 1], raw[j * 4 + 2], raw[j * 4 + 3]);
+    }
+  }
+}
+
 // swap-AB epilogue: accumulator row = logical output COLUMN (a weight row), accumulator column =
 // logical output ROW (a token). Stores are scalar per thread but coalesced across the warp.
 template <int BN>
@@ -592,6 +625,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int n_tiles = (g.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (g.K + BK - 1) / BK;
+  const int num_units = num_tiles * g.k_splits;  // unit = (tile, k-split); k_splits == 1 unless split-K
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -621,10 +655,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit % num_tiles;
         const int m0 = (tile / n_tiles) * BM;
         const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int kb0 = (unit / num_tiles) * g.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -658,7 +695,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       constexpr uint32_t idesc = make_idesc(Cfg::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0;
       uint32_t local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local) {
+        const int kb0 = (unit / num_tiles) * g.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + g.kb_per_split);
         const uint32_t acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         VY_TRACE(1, local, 0);
@@ -666,7 +705,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tc_fence_after();
         VY_TRACE(1, local, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -679,8 +718,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                      : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            if constexpr (sizeof(TIn) == 2) umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            else umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            if constexpr (sizeof(TIn) == 2) umma_f16(d_tmem, ad, bd, idesc, kb != kb0 || k != 0);
+            else umma_tf32(d_tmem, ad, bd, idesc, kb != kb0 || k != 0);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -705,7 +744,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       else if (g.act == VY_ACT_DGELU_ERF && !g.addend && aux16 && n8) fast_mode = EPI_DGELU;
     }
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local) {
+      const int tile = unit % num_tiles;
       const uint32_t acc = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
       const int m0 = (tile / n_tiles) * BM;
@@ -724,6 +764,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         mbar_wait(&tfull_bar[acc], acc_ph);
         tc_fence_after();
         release_acc(&tempty_bar[acc], lane);
+      } else if (g.k_splits > 1) {
+        epilogue_splitk<BN>(g, tmem_acc, m0, n0, q, half, lane, unit / num_tiles, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
       } else if (g.epi == VY_EPI_QKV_ROPE) {
         if constexpr (BN >= 64)
           epilogue_qkv_rope<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
@@ -800,7 +842,7 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   }
   const int m_tiles = (p->M + Cfg::BM - 1) / Cfg::BM;
   const int n_tiles = (p->N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles;
+  const int tiles = m_tiles * n_tiles * (g.k_splits > 1 ? g.k_splits : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream)>>>(ta, tb, g);
   VY_LAUNCH_OK();

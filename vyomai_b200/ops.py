@@ -61,6 +61,20 @@ def _major(t: torch.Tensor, what: str):
     raise _lib.VyomError(f"{what}: operand must have one unit stride, got strides {t.stride()}")
 
 
+_SPLITK_WS = {}
+SPLITK_WORKSPACE_BYTES = 64 << 20
+
+
+def _splitk_workspace(device: torch.device) -> torch.Tensor:
+    """Per-device fp32 scratch lent to vy_gemm for split-K (persistent, so captured CUDA graphs stay valid).
+    All GEMMs of this process run on one stream at a time, which is what sharing one buffer requires."""
+    t = _SPLITK_WS.get(device)
+    if t is None:
+        t = torch.empty(SPLITK_WORKSPACE_BYTES // 4, device=device, dtype=torch.float32)
+        _SPLITK_WS[device] = t
+    return t
+
+
 def gemm(
     a: torch.Tensor,
     b: torch.Tensor,
@@ -79,6 +93,7 @@ def gemm(
     out_row_group_stride: int = 0,
     out_row_off: int = 0,
     swap_ab: bool = False,
+    allow_split_k: bool = False,
 ) -> torch.Tensor:
     """out = epilogue(a @ b.T). `a` is logical (M, K), `b` logical (N, K); each may be stored with
     either index contiguous (K-major or MN-major — read off the torch strides, no copies).
@@ -129,6 +144,9 @@ def gemm(
         out_row_off=out_row_off,
         stream=_stream(),
     )
+    if allow_split_k:
+        ws = _splitk_workspace(a.device)
+        kw.update(workspace=ws.data_ptr(), workspace_bytes=ws.numel() * 4)
     if not swap_ab:
         kw.update(M=M, N=N, K=K, A=a.data_ptr(), lda=lda, a_mn_major=a_mn, B=b.data_ptr(), ldb=ldb,
                   b_mn_major=b_mn, transposed_out=0)
