@@ -168,7 +168,8 @@ VY_API int vy_gemm(const VyGemm* p);
  * LayerNorm of the LM head (models/decoder.py:259-261,270; residual = NULL).
  * mean / rstd (fp32, [rows]) are optional outputs of fwd and required inputs of bwd.
  * bwd: dx[rows,H] (= d residual as well), dgamma/dbeta partials are reduced into dgamma[H], dbeta[H]
- * (fp32 or bf16; overwritten, or accumulated into when dparam_accumulate). xhat is recomputed from the saved pre-norm sum `s`
+ * (fp32 or bf16; overwritten, or accumulated into when dparam_accumulate); dbias (optional) receives the column
+ * sums of dx, i.e. the gradient of the bias of the Linear whose output x was (attention.py:69, ffn.py:37). xhat is recomputed from the saved pre-norm sum `s`
  * (s = x + residual; pass the tensor fwd wrote to sum_out, or x when residual was NULL).
  * ------------------------------------------------------------------------------------------ */
 typedef struct VyNorm {
@@ -190,9 +191,10 @@ typedef struct VyNorm {
   void* dx;
   void* dgamma; /* [H], dtype dparam_dtype */
   void* dbeta;  /* [H], dtype dparam_dtype */
+  void* dbias;  /* optional [H]: column sums of dx = the bias gradient of the Linear that produced x */
   int32_t dparam_dtype;      /* VY_F32 (default 0) or VY_BF16 */
   int32_t dparam_accumulate; /* 1: dgamma/dbeta += result (accumulate straight into the parameters' .grad) */
-  float* partials; /* workspace: 2 * vy_norm_bwd_partial_rows() * H floats */
+  float* partials; /* workspace: 2 * vy_norm_bwd_partial_rows() * H floats (holds the per-strip column partials) */
   void* stream;
 } VyNorm;
 

@@ -71,16 +71,25 @@ def _emit_bgrad(p: Optional[torch.Tensor], dy2d: torch.Tensor) -> Optional[torch
     return ops.colsum(dy2d, out_dtype=p.dtype)
 
 
-def _ln_bwd(dy: torch.Tensor, s: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean, rstd):
-    """LayerNorm backward. Returns (ds, d_gamma, d_beta); with trainer-owned gradient buffers the parameter
-    gradients are accumulated in place by the reduce kernel and None is returned for them."""
-    if _direct(gamma) and _direct(beta) and gamma.grad.dtype == beta.grad.dtype:
-        ds, _, _ = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out=gamma.grad, dbeta_out=beta.grad)
+def _ln_bwd(dy: torch.Tensor, s: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean, rstd,
+            bias: Optional[torch.Tensor] = None):
+    """LayerNorm backward. Returns (ds, d_gamma, d_beta, d_bias); `bias` is the bias of the Linear whose output was
+    normalised (its gradient = column sums of ds, produced by the same kernels). With trainer-owned gradient buffers
+    the parameter gradients are accumulated in place by the reduce kernel and None is returned for them."""
+    direct = _direct(gamma) and _direct(beta) and gamma.grad.dtype == beta.grad.dtype
+    if direct and (bias is None or (_direct(bias) and bias.grad.dtype == gamma.grad.dtype)):
+        ds = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out=gamma.grad, dbeta_out=beta.grad,
+                                   dbias_out=bias.grad if bias is not None else None)[0]
         _ready(gamma)
         _ready(beta)
-        return ds, None, None
+        if bias is not None:
+            _ready(bias)
+        return ds, None, None, None
+    if bias is not None:
+        ds, dgamma, dbeta, dbias = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, want_dbias=True)
+        return ds, dgamma.to(gamma.dtype), dbeta.to(beta.dtype), dbias.to(bias.dtype)
     ds, dgamma, dbeta = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd)
-    return ds, dgamma.to(gamma.dtype), dbeta.to(beta.dtype)
+    return ds, dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None
 
 
 def _packed_grads(params) -> Optional[torch.Tensor]:
@@ -126,9 +135,8 @@ class AttentionBlockFn(torch.autograd.Function):
         w_qkv, _ = F.pack_linears(lin)
         Hq, Hkv, d = mod.num_attention_heads, mod._kv_heads, F.HEAD_DIM
         dy = dy.contiguous()
-        ds, dgamma, dbeta = _ln_bwd(dy, s, ln.weight, ln.bias, mean, rstd)
+        ds, dgamma, dbeta, d_bo = _ln_bwd(dy, s, ln.weight, ln.bias, mean, rstd, bias=dense.bias)
         d_wo = _emit_wgrad(dense.weight, ds, attn)
-        d_bo = _emit_bgrad(dense.bias, ds)
         d_attn = _dgrad(ds, dense.weight, out_dtype=torch.bfloat16)  # bf16: MMA operand of the attention backward
         dqkv = torch.empty((B * S, (Hq + 2 * Hkv) * d), device=dy.device, dtype=x2d.dtype)
         cos = sin = None
@@ -215,9 +223,8 @@ class FeedForwardFn(torch.autograd.Function):
     def backward(ctx, dy):
         h2d, z, a, s, mean, rstd = ctx.saved_tensors
         w1, b1, w2, b2, gamma, beta = ctx.params
-        ds, dgamma, dbeta = _ln_bwd(dy.contiguous(), s, gamma, beta, mean, rstd)
+        ds, dgamma, dbeta, d_b2 = _ln_bwd(dy.contiguous(), s, gamma, beta, mean, rstd, bias=b2)
         d_w2 = _emit_wgrad(w2, ds, a)
-        d_b2 = _emit_bgrad(b2, ds)
         dz = _dgrad(ds, w2, act="d" + ctx.act, aux=z)  # (dS W2) * act'(z) in the dgrad epilogue
         d_w1 = _emit_wgrad(w1, dz, h2d)
         d_b1 = _emit_bgrad(b1, dz)
@@ -238,7 +245,7 @@ def _lm_head_backward(ctx_saved, params, dlogits):
     d_wv = _emit_wgrad(wv, dlogits, n)
     d_bv = _emit_bgrad(bv, dlogits)
     dn = _dgrad(dlogits, wv)
-    da, dgamma, dbeta = _ln_bwd(dn, a, gamma, beta, mean, rstd)
+    da, dgamma, dbeta, _ = _ln_bwd(dn, a, gamma, beta, mean, rstd)
     dz = ops.act_bwd(da, z, "gelu")
     d_wd = _emit_wgrad(wd, dz, h2d)
     d_bd = _emit_bgrad(bd, dz)

@@ -69,47 +69,48 @@ add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void
   }
 }
 
-// backward: persistent blocks stride over rows; per-lane dgamma/dbeta partials stay in registers,
-// are combined across the block's warps in smem and written to partials[block][H].
+// backward, three light kernels instead of one register-heavy one (154 registers, 8 warps per SM, ~1 TB/s):
+//   1. dx:       warp per row, statistics of dy*gamma and dy*gamma*xhat, dx written — no per-column accumulators,
+//                so occupancy (and bytes in flight) is like the forward kernel's;
+//   2. columns:  dgamma = sum_r dy*xhat, dbeta = sum_r dy and, if asked, dbias = sum_r dx (the bias gradient of the
+//                Linear whose output fed this LayerNorm: attention.py:69-71, ffn.py:37-39) over row strips; the three
+//                inputs were just touched, so they stream from L2;
+//   3. final:    strips reduced and written as fp32 / bf16, overwriting or accumulating into the parameters' .grad.
 template <int NV>
-__global__ void __launch_bounds__(NORM_WARPS * 32)
-add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s,
-                         int io_dt, const void* __restrict__ gamma, int p_dt,
-                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                         void* __restrict__ dx, float* __restrict__ partials) {
-  extern __shared__ float red[];  // [NORM_WARPS][2][H]
+__global__ void __launch_bounds__(NORM_WARPS * 32, 2)
+add_layernorm_bwd_dx_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s, int io_dt,
+                            const void* __restrict__ gamma, int p_dt, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, void* __restrict__ dx) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H >> 3;
-  float dg[NV][8], db[NV][8], g[NV][8];
+  float g[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) ld8_as_float(gamma, p_dt, vi * 8, g[i]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dg[i][j] = 0.f;
-      db[i][j] = 0.f;
-    }
   }
   for (int row = blockIdx.x * NORM_WARPS + warp; row < rows; row += gridDim.x * NORM_WARPS) {
     const long long base = static_cast<long long>(row) * H;
     const float mu = mean[row], rs = rstd[row];
-    float xh[NV][8], dyv[NV][8];
+    float xh[NV][8], t[NV][8];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        ld8_as_float(dy, io_dt, base + vi * 8, dyv[i]);
+        ld8_as_float(dy, io_dt, base + vi * 8, t[i]);
         ld8_as_float(s, io_dt, base + vi * 8, xh[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (xh[i][j] - mu) * rs;
-          const float t = dyv[i][j] * g[i][j];
-          c1 += t;
-          c2 += t * xh[i][j];
-          dg[i][j] += dyv[i][j] * xh[i][j];
-          db[i][j] += dyv[i][j];
+          t[i][j] *= g[i][j];
+          c1 += t[i][j];
+          c2 += t[i][j] * xh[i][j];
         }
       }
     }
@@ -121,53 +122,99 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
       if (vi < nvec) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (dyv[i][j] * g[i][j] - c1 - xh[i][j] * c2);
+        for (int j = 0; j < 8; ++j) o[j] = rs * (t[i][j] - c1 - xh[i][j] * c2);
         st8_from_float(dx, io_dt, base + vi * 8, o);
       }
     }
   }
-  float* my = red + static_cast<size_t>(warp) * 2 * H;
+}
+
+constexpr int NORM_MAX_STRIPS = 128;
+
+// grid (ceil(H / 256), strips): a warp covers 256 consecutive columns (8 per lane), the 8 warps of the CTA take
+// interleaved rows of the strip, 4 rows in flight each; partials[strip][3][H].
+__global__ void __launch_bounds__(256)
+norm_bwd_columns_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s, const void* __restrict__ dx,
+                        int io_dt, const float* __restrict__ mean, const float* __restrict__ rstd, int want_dbias,
+                        float* __restrict__ partials) {
+  __shared__ float red[8][3][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float ag[8], ab[8], ax[8];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = ax[j] = 0.f;
+  if (c0 < H) {
+    int r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      float vd[4][8], vs[4][8], vx[4][8];
+      float mu[4], rs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long off = static_cast<long long>(r + u * 8) * H + c0;
+        ld8_as_float(dy, io_dt, off, vd[u]);
+        ld8_as_float(s, io_dt, off, vs[u]);
+        if (want_dbias) ld8_as_float(dx, io_dt, off, vx[u]);
+        mu[u] = mean[r + u * 8];
+        rs[u] = rstd[r + u * 8];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ag[j] += vd[u][j] * ((vs[u][j] - mu[u]) * rs[u]);
+          ab[j] += vd[u][j];
+          if (want_dbias) ax[j] += vx[u][j];
+        }
+    }
+    for (; r < r1; r += 8) {
+      float vd[8], vs[8], vx[8];
+      const long long off = static_cast<long long>(r) * H + c0;
+      ld8_as_float(dy, io_dt, off, vd);
+      ld8_as_float(s, io_dt, off, vs);
+      const float mu = mean[r], rs = rstd[r];
+      if (want_dbias) ld8_as_float(dx, io_dt, off, vx);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        my[vi * 8 + j] = dg[i][j];
-        my[H + vi * 8 + j] = db[i][j];
+        ag[j] += vd[j] * ((vs[j] - mu) * rs);
+        ab[j] += vd[j];
+        if (want_dbias) ax[j] += vx[j];
       }
     }
   }
-  __syncthreads();
-  float* outp = partials + static_cast<size_t>(blockIdx.x) * 2 * H;
-  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
-    float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < NORM_WARPS; ++w) a += red[static_cast<size_t>(w) * 2 * H + c];
-    outp[c] = a;
+  for (int j = 0; j < 8; ++j) {
+    red[w][0][lane * 8 + j] = ag[j];
+    red[w][1][lane * 8 + j] = ab[j];
+    red[w][2][lane * 8 + j] = ax[j];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < H) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[k][v][threadIdx.x];
+      partials[(static_cast<size_t>(blockIdx.y) * 3 + v) * H + c] = a;
+    }
   }
 }
 
-// column reduce of the per-block partials: 32 columns per block, 8 warps split the partial rows
+// final reduce over the strips: thread <-> (vector v, column c)
 __global__ void __launch_bounds__(256)
-norm_bwd_reduce_kernel(int nparts, int H, const float* __restrict__ partials, void* __restrict__ dgamma,
-                       void* __restrict__ dbeta, int out_dt, int accumulate) {
-  __shared__ float red[8][33];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+norm_bwd_reduce_kernel(int strips, int H, const float* __restrict__ partials, void* __restrict__ dgamma,
+                       void* __restrict__ dbeta, void* __restrict__ dbias, int out_dt, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = dbias ? 3 : 2;
+  if (idx >= nv * H) return;
+  const int v = idx / H, c = idx % H;
   float a = 0.f;
-  if (c < 2 * H)
-    for (int p = w; p < nparts; p += 8) a += partials[static_cast<size_t>(p) * 2 * H + c];
-  red[w][lane] = a;
-  __syncthreads();
-  if (w == 0 && c < 2 * H) {
-#pragma unroll
-    for (int k = 1; k < 8; ++k) a += red[k][lane];
-    void* dst = c < H ? dgamma : dbeta;
-    const int cc = c < H ? c : c - H;
-    if (accumulate) a += ld_as_float(dst, out_dt, cc);
-    st_from_float(dst, out_dt, cc, a);
-  }
+  for (int p = 0; p < strips; ++p) a += partials[(static_cast<size_t>(p) * 3 + v) * H + c];
+  void* dst = v == 0 ? dgamma : (v == 1 ? dbeta : dbias);
+  if (accumulate) a += ld_as_float(dst, out_dt, c);
+  st_from_float(dst, out_dt, c, a);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -232,18 +279,12 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   VY_CHECK_ARG(dtype_ok(p->dparam_dtype), "vy_add_layernorm_bwd: bad dparam_dtype");
   const int nv = (p->H + 255) / 256;
   int grid = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
-  const int nparts = vy_norm_bwd_partial_rows();
-  if (grid > nparts) grid = nparts;
-  const size_t smem = static_cast<size_t>(NORM_WARPS) * 2 * p->H * sizeof(float);
+  const int maxgrid = num_sms() * 8;
+  if (grid > maxgrid) grid = maxgrid;
   cudaStream_t st = static_cast<cudaStream_t>(p->stream);
-#define VY_LN_BWD(NV)                                                                               \
-  do {                                                                                              \
-    auto kern = add_layernorm_bwd_kernel<NV>;                                                       \
-    if (smem > 48 * 1024)                                                                           \
-      VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, NORM_WARPS * 32, smem, st>>>(p->rows, p->H, p->dy, p->s, p->io_dtype, p->gamma,    \
-                                              p->param_dtype, p->mean, p->rstd, p->dx, p->partials); \
-  } while (0)
+#define VY_LN_BWD(NV)                                                                                         \
+  add_layernorm_bwd_dx_kernel<NV><<<grid, NORM_WARPS * 32, 0, st>>>(p->rows, p->H, p->dy, p->s, p->io_dtype, \
+                                                                     p->gamma, p->param_dtype, p->mean, p->rstd, p->dx)
   switch (nv) {
     case 1: VY_LN_BWD(1); break;
     case 2: VY_LN_BWD(2); break;
@@ -256,9 +297,17 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   }
 #undef VY_LN_BWD
   VY_LAUNCH_OK();
-  norm_bwd_reduce_kernel<<<(2 * p->H + 31) / 32, 256, 0, st>>>(grid, p->H, p->partials, p->dgamma, p->dbeta,
-                                                               p->dparam_dtype, p->dparam_accumulate);
+  int strips = (p->rows + 63) / 64;
+  if (strips > NORM_MAX_STRIPS) strips = NORM_MAX_STRIPS;
+  if (strips < 1) strips = 1;
+  dim3 cgrid((p->H + 255) / 256, strips);
+  norm_bwd_columns_kernel<<<cgrid, 256, 0, st>>>(p->rows, p->H, p->dy, p->s, p->dx, p->io_dtype, p->mean, p->rstd,
+                                                 p->dbias != nullptr, p->partials);
   VY_LAUNCH_OK();
-  count_launch(2);
+  const int nvec = p->dbias ? 3 : 2;
+  norm_bwd_reduce_kernel<<<(nvec * p->H + 255) / 256, 256, 0, st>>>(strips, p->H, p->partials, p->dgamma, p->dbeta, p->dbias,
+                                                                    p->dparam_dtype, p->dparam_accumulate);
+  VY_LAUNCH_OK();
+  count_launch(3);
   return VY_OK;
 }

@@ -243,11 +243,13 @@ def add_layernorm(
 
 
 def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tensor] = None,
-                      dbeta_out: Optional[torch.Tensor] = None):
-    """Returns (dx, dgamma, dbeta) for y = LayerNorm(s). Without dgamma_out/dbeta_out the parameter gradients come
-    back as fresh fp32 tensors; with them (same dtype, e.g. the parameters' .grad views) the kernel ACCUMULATES
-    into those buffers and returns them."""
-    _need_cuda(dy, s, gamma, mean, rstd, dgamma_out, dbeta_out)
+                      dbeta_out: Optional[torch.Tensor] = None, dbias_out: Optional[torch.Tensor] = None,
+                      want_dbias: bool = False):
+    """Returns (dx, dgamma, dbeta[, dbias]) for y = LayerNorm(s). Without dgamma_out/dbeta_out the parameter
+    gradients come back as fresh fp32 tensors; with them (same dtype, e.g. the parameters' .grad views) the kernel
+    ACCUMULATES into those buffers and returns them. dbias (want_dbias / dbias_out) = column sums of dx: the bias
+    gradient of the Linear that produced the normalised sum."""
+    _need_cuda(dy, s, gamma, mean, rstd, dgamma_out, dbeta_out, dbias_out)
     H = dy.shape[-1]
     dy2 = dy.reshape(-1, H)
     s2 = s.reshape(-1, H)
@@ -260,18 +262,26 @@ def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tenso
         if dbeta_out is None or dgamma_out.dtype != dbeta_out.dtype or not (dgamma_out.is_contiguous() and dbeta_out.is_contiguous()):
             raise _lib.VyomError("add_layernorm_bwd: dgamma_out / dbeta_out must both be given, contiguous, same dtype")
         dgamma, dbeta = dgamma_out, dbeta_out
+        dbias = dbias_out
+        if dbias is not None and (dbias.dtype != dgamma.dtype or not dbias.is_contiguous()):
+            raise _lib.VyomError("add_layernorm_bwd: dbias_out must be contiguous and share dgamma_out's dtype")
     else:
+        if dbias_out is not None:
+            raise _lib.VyomError("add_layernorm_bwd: dbias_out needs dgamma_out / dbeta_out as well")
         dgamma = torch.empty(H, device=dy.device, dtype=torch.float32)
         dbeta = torch.empty(H, device=dy.device, dtype=torch.float32)
+        dbias = torch.empty(H, device=dy.device, dtype=torch.float32) if want_dbias else None
     nparts = _lib.lib().vy_norm_bwd_partial_rows()
     partials = torch.empty(2 * nparts * H, device=dy.device, dtype=torch.float32)
     _lib.call(
         "vy_add_layernorm_bwd", "VyNorm",
         rows=rows, H=H, io_dtype=_dt(dy2), gamma=gamma.data_ptr(), param_dtype=_dt(gamma),
         mean=mean.data_ptr(), rstd=rstd.data_ptr(), dy=dy2.data_ptr(), s=s2.data_ptr(), dx=dx.data_ptr(),
-        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), dparam_dtype=_dt(dgamma), dparam_accumulate=int(acc),
-        partials=partials.data_ptr(), stream=_stream(),
+        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), dbias=_ptr(dbias), dparam_dtype=_dt(dgamma),
+        dparam_accumulate=int(acc), partials=partials.data_ptr(), stream=_stream(),
     )
+    if want_dbias or dbias_out is not None:
+        return dx.view(dy.shape), dgamma, dbeta, dbias
     return dx.view(dy.shape), dgamma, dbeta
 
 
