@@ -69,13 +69,118 @@ add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void
   }
 }
 
-// backward, three light kernels instead of one register-heavy one (154 registers, 8 warps per SM, ~1 TB/s):
-//   1. dx:       warp per row, statistics of dy*gamma and dy*gamma*xhat, dx written — no per-column accumulators,
-//                so occupancy (and bytes in flight) is like the forward kernel's;
-//   2. columns:  dgamma = sum_r dy*xhat, dbeta = sum_r dy and, if asked, dbias = sum_r dx (the bias gradient of the
-//                Linear whose output fed this LayerNorm: attention.py:69-71, ffn.py:37-39) over row strips; the three
-//                inputs were just touched, so they stream from L2;
-//   3. final:    strips reduced and written as fp32 / bf16, overwriting or accumulating into the parameters' .grad.
+// backward: one pass over dy and s. Persistent CTAs (one per SM, 8 warps) stride over rows, warp per row; the raw
+// 16-byte loads of the NEXT row are issued before the current row is processed, so every warp keeps two rows in
+// flight (~7 MB over the chip: enough to cover HBM latency at full bandwidth with only 8 warps per SM). Per-lane
+// column accumulators stay in registers: dgamma += dy*xhat, dbeta += dy and — when asked — dbias += dx (the bias
+// gradient of the Linear whose output fed this LayerNorm: attention.py:69-71, ffn.py:37-39, saving a separate
+// column-sum pass over dx). They are combined across the CTA's warps in smem and written to partials[cta][3][H].
+template <int NV, bool IO_BF16>
+__global__ void __launch_bounds__(NORM_WARPS * 32, 1)
+add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s,
+                         const void* __restrict__ gamma, int p_dt, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, void* __restrict__ dx, int want_dbias, float* __restrict__ partials) {
+  extern __shared__ float red[];  // [NORM_WARPS][3][H]
+  constexpr int IO_DT = IO_BF16 ? VY_BF16 : VY_F32;
+  constexpr int RAW = IO_BF16 ? 1 : 2;  // uint4 per 8 elements
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = H >> 3;
+  float g[NV][8], dg[NV][8], db[NV][8], dbi[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[i][j] = dg[i][j] = db[i][j] = dbi[i][j] = 0.f;
+    if (vi < nvec) ld8_as_float(gamma, p_dt, vi * 8, g[i]);
+  }
+  const int stride = gridDim.x * NORM_WARPS;
+  uint4 ndy[NV][RAW], ns[NV][RAW];  // next row, raw
+  auto fetch = [&](int row) {
+    const uint4* pd = reinterpret_cast<const uint4*>(dy) + static_cast<long long>(row) * nvec * RAW;
+    const uint4* ps = reinterpret_cast<const uint4*>(s) + static_cast<long long>(row) * nvec * RAW;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int k = 0; k < RAW; ++k) {
+          ndy[i][k] = pd[vi * RAW + k];
+          ns[i][k] = ps[vi * RAW + k];
+        }
+      }
+    }
+  };
+  int row = blockIdx.x * NORM_WARPS + warp;
+  if (row < rows) fetch(row);
+  for (; row < rows; row += stride) {
+    const long long base = static_cast<long long>(row) * H;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][8], dyv[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        ld8_as_float(&ndy[i][0], IO_DT, 0, dyv[i]);  // unpack the prefetched registers
+        ld8_as_float(&ns[i][0], IO_DT, 0, xh[i]);
+      }
+    }
+    if (row + stride < rows) fetch(row + stride);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          const float t = dyv[i][j] * g[i][j];
+          c1 += t;
+          c2 += t * xh[i][j];
+          dg[i][j] += dyv[i][j] * xh[i][j];
+          db[i][j] += dyv[i][j];
+        }
+      }
+    }
+    c1 = warp_sum(c1) / H;
+    c2 = warp_sum(c2) / H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rs * (dyv[i][j] * g[i][j] - c1 - xh[i][j] * c2);
+          dbi[i][j] += o[j];
+        }
+        st8_from_float(dx, IO_DT, base + vi * 8, o);
+      }
+    }
+  }
+  float* my = red + static_cast<size_t>(warp) * 3 * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        my[vi * 8 + j] = dg[i][j];
+        my[H + vi * 8 + j] = db[i][j];
+        my[2 * H + vi * 8 + j] = dbi[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  float* outp = partials + static_cast<size_t>(blockIdx.x) * 3 * H;
+  const int nout = want_dbias ? 3 * H : 2 * H;
+  for (int c = threadIdx.x; c < nout; c += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < NORM_WARPS; ++w) a += red[static_cast<size_t>(w) * 3 * H + c];
+    outp[c] = a;
+  }
+}
+
+// Wide rows (H > 1024) do not fit the register accumulators above: dx by a light warp-per-row kernel, then the column
+// sums over row strips (partials[strip][3][H]).
 template <int NV>
 __global__ void __launch_bounds__(NORM_WARPS * 32, 2)
 add_layernorm_bwd_dx_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s, int io_dt,
@@ -279,35 +384,57 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   VY_CHECK_ARG(dtype_ok(p->dparam_dtype), "vy_add_layernorm_bwd: bad dparam_dtype");
   const int nv = (p->H + 255) / 256;
   int grid = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
-  const int maxgrid = num_sms() * 8;
-  if (grid > maxgrid) grid = maxgrid;
+  if (grid > num_sms()) grid = num_sms();  // persistent: one CTA per SM (partials hold up to 2 * SMs * 2 * H floats)
+  const size_t smem = static_cast<size_t>(NORM_WARPS) * 3 * p->H * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(p->stream);
-#define VY_LN_BWD(NV)                                                                                         \
-  add_layernorm_bwd_dx_kernel<NV><<<grid, NORM_WARPS * 32, 0, st>>>(p->rows, p->H, p->dy, p->s, p->io_dtype, \
-                                                                     p->gamma, p->param_dtype, p->mean, p->rstd, p->dx)
+#define VY_LN_BWD2(NV, BF)                                                                            \
+  do {                                                                                               \
+    auto kern = add_layernorm_bwd_kernel<NV, BF>;                                                    \
+    if (smem > 48 * 1024)                                                                            \
+      VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, NORM_WARPS * 32, smem, st>>>(p->rows, p->H, p->dy, p->s, p->gamma, p->param_dtype, p->mean, p->rstd, \
+                                              p->dx, p->dbias != nullptr, p->partials);               \
+  } while (0)
+#define VY_LN_BWD(NV)                     \
+  do {                                    \
+    if (p->io_dtype == VY_BF16) VY_LN_BWD2(NV, true); \
+    else VY_LN_BWD2(NV, false);           \
+  } while (0)
   switch (nv) {
     case 1: VY_LN_BWD(1); break;
     case 2: VY_LN_BWD(2); break;
     case 3: VY_LN_BWD(3); break;
     case 4: VY_LN_BWD(4); break;
-    case 5: VY_LN_BWD(5); break;
-    case 6: VY_LN_BWD(6); break;
-    case 7: VY_LN_BWD(7); break;
-    default: VY_LN_BWD(8); break;
+    default: break;
   }
 #undef VY_LN_BWD
-  VY_LAUNCH_OK();
-  int strips = (p->rows + 63) / 64;
-  if (strips > NORM_MAX_STRIPS) strips = NORM_MAX_STRIPS;
-  if (strips < 1) strips = 1;
-  dim3 cgrid((p->H + 255) / 256, strips);
-  norm_bwd_columns_kernel<<<cgrid, 256, 0, st>>>(p->rows, p->H, p->dy, p->s, p->dx, p->io_dtype, p->mean, p->rstd,
-                                                 p->dbias != nullptr, p->partials);
+#undef VY_LN_BWD2
+  int strips = grid;
+  if (nv > 4) {
+    int g2 = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
+    if (g2 > num_sms() * 8) g2 = num_sms() * 8;
+#define VY_LN_DX(NV)                                                                                        \
+  add_layernorm_bwd_dx_kernel<NV><<<g2, NORM_WARPS * 32, 0, st>>>(p->rows, p->H, p->dy, p->s, p->io_dtype, \
+                                                                   p->gamma, p->param_dtype, p->mean, p->rstd, p->dx)
+    switch (nv) {
+      case 5: VY_LN_DX(5); break;
+      case 6: VY_LN_DX(6); break;
+      case 7: VY_LN_DX(7); break;
+      default: VY_LN_DX(8); break;
+    }
+#undef VY_LN_DX
+    VY_LAUNCH_OK();
+    strips = (p->rows + 63) / 64;
+    if (strips > NORM_MAX_STRIPS) strips = NORM_MAX_STRIPS;
+    dim3 cgrid((p->H + 255) / 256, strips);
+    norm_bwd_columns_kernel<<<cgrid, 256, 0, st>>>(p->rows, p->H, p->dy, p->s, p->dx, p->io_dtype, p->mean, p->rstd,
+                                                   p->dbias != nullptr, p->partials);
+  }
   VY_LAUNCH_OK();
   const int nvec = p->dbias ? 3 : 2;
   norm_bwd_reduce_kernel<<<(nvec * p->H + 255) / 256, 256, 0, st>>>(strips, p->H, p->partials, p->dgamma, p->dbeta, p->dbias,
                                                                     p->dparam_dtype, p->dparam_accumulate);
   VY_LAUNCH_OK();
-  count_launch(3);
+  count_launch(2);
   return VY_OK;
 }
