@@ -1,6 +1,7 @@
 // Library-level entry points: version, error string, launch counter, device probe, TMA
 // descriptor encoding through the driver entry point (no link-time libcuda dependency).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -18,6 +19,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("VY_PDL") && atoi(getenv("VY_PDL")) != 0;  // measured: no gain inside the captured step, so opt-in
+  return on;
 }
 
 int num_sms() {

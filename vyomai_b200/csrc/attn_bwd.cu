@@ -54,6 +54,8 @@ struct AttnBwdDev {
 __global__ void __launch_bounds__(256)
 attn_dsum_kernel(int B, int Hq, int Sq, const void* __restrict__ o, long long o_sb, long long o_sl, int o_dt,
                  const void* __restrict__ dout, long long do_sb, long long do_sl, int do_dt, float* __restrict__ dsum) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nchunks = Hq * 8;  // 8-element chunks per row
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(256, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                      const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
                      const AttnBwdDev g) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + AB_TILE;
@@ -179,6 +182,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // everything above is independent of the predecessor grid's output
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
 
   const int q_tiles = (g.Sq + AB_T - 1) / AB_T;
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(256, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                    const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
                    const AttnBwdDev g) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + AB_TILE;
@@ -399,6 +404,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // everything above is independent of the predecessor grid's output
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256;
 
   const int total = (g.Skv + AB_T - 1) / AB_T;
@@ -579,8 +585,8 @@ extern "C" int vy_attn_bwd(const VyAttnBwd* p) {
     long long blocks = (rows + 7) / 8;
     const long long cap = static_cast<long long>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
-    attn_dsum_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(p->B, p->n_q_heads, p->Sq, p->o, p->o_sb, p->o_sl, p->o_dtype,
-                                                               p->dout, p->do_sb, p->do_sl, VY_BF16, p->dsum);
+    VY_CUDA_OK(launch_kernel(attn_dsum_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, st, p->B, p->n_q_heads, p->Sq, p->o, p->o_sb, p->o_sl, p->o_dtype,
+                                                               p->dout, p->do_sb, p->do_sl, VY_BF16, p->dsum));
     VY_LAUNCH_OK();
   }
 
@@ -625,10 +631,10 @@ extern "C" int vy_attn_bwd(const VyAttnBwd* p) {
     attr_set = true;
   }
   dim3 grid_kv((p->Skv + AB_T - 1) / AB_T, p->n_kv_heads, p->B);
-  attn_bwd_dkdv_kernel<<<grid_kv, 256, AB_SMEM_DKDV, st>>>(tq, tk, tv, tdo, g);
+  VY_CUDA_OK(launch_kernel(attn_bwd_dkdv_kernel, dim3(grid_kv), dim3(256), AB_SMEM_DKDV, st, tq, tk, tv, tdo, g));
   VY_LAUNCH_OK();
   dim3 grid_q((p->Sq + AB_T - 1) / AB_T, p->n_q_heads, p->B);
-  attn_bwd_dq_kernel<<<grid_q, 256, AB_SMEM_DQ, st>>>(tq, tk, tv, tdo, g);
+  VY_CUDA_OK(launch_kernel(attn_bwd_dq_kernel, dim3(grid_q), dim3(256), AB_SMEM_DQ, st, tq, tk, tv, tdo, g));
   VY_LAUNCH_OK();
   count_launch(3);
   return VY_OK;

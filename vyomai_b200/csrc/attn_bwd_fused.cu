@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
                       const __grid_constant__ AttnBwdFusedDev g) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;                   // [2] key tiles
   uint8_t* sV = smem + 2 * AF_TILE;     // [2]
@@ -175,6 +176,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // everything above is independent of the predecessor grid's output
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320,
                  tm_dQ = tmem_base + 384;
 
@@ -448,7 +450,7 @@ int attn_bwd_fused_launch(const VyAttnBwd* p) {
     attr_set = true;
   }
   dim3 grid(p->n_kv_heads, p->B);
-  attn_bwd_fused_kernel<<<grid, AF_THREADS, AF_SMEM, static_cast<cudaStream_t>(p->stream)>>>(tq, tk, tv, tdo, g);
+  VY_CUDA_OK(launch_kernel(attn_bwd_fused_kernel, dim3(grid), dim3(AF_THREADS), AF_SMEM, static_cast<cudaStream_t>(p->stream), tq, tk, tv, tdo, g));
   VY_LAUNCH_OK();
   return 1;
 }

@@ -65,6 +65,8 @@ __device__ __forceinline__ void load_row8<float>(const float* p, float (&v)[8]) 
 template <typename TC, int NREP>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 attn_decode_kernel(const DecodeDev g) {
+  pdl_trigger();
+  pdl_wait();
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = lane & 7;   // which 8-element slice of the head dim
@@ -280,12 +282,12 @@ static int launch_decode(const DecodeDev& g, cudaStream_t st) {
   dim3 grid(g.splits, g.Hkv, g.B);
   dim3 block(DEC_WARPS * 32);
   switch (g.n_rep) {
-    case 1: attn_decode_kernel<TC, 1><<<grid, block, 0, st>>>(g); break;
-    case 2: attn_decode_kernel<TC, 2><<<grid, block, 0, st>>>(g); break;
-    case 3: attn_decode_kernel<TC, 3><<<grid, block, 0, st>>>(g); break;
-    case 4: attn_decode_kernel<TC, 4><<<grid, block, 0, st>>>(g); break;
-    case 6: attn_decode_kernel<TC, 6><<<grid, block, 0, st>>>(g); break;
-    case 8: attn_decode_kernel<TC, 8><<<grid, block, 0, st>>>(g); break;
+    case 1: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 1>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 2: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 2>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 3: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 3>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 4: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 4>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 6: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 6>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 8: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 8>, dim3(grid), dim3(block), 0, st, g)); break;
     default:
       set_error("vy_attn_decode: unsupported q-heads per kv-head %d (1,2,3,4,6,8)", g.n_rep);
       return VY_ERR_UNSUPPORTED;

@@ -54,6 +54,7 @@ __device__ __forceinline__ int attn_num_kv_tiles(const AttnDev& g, int b, int q0
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_v, const AttnDev g) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_TILE;
@@ -102,6 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // everything above is independent of the predecessor grid's output
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
 
@@ -339,7 +341,7 @@ extern "C" int vy_attn_fwd(const VyAttn* p) {
     attr_set = true;
   }
   dim3 grid((p->Sq + AT_BM - 1) / AT_BM, p->n_q_heads, p->B);
-  attn_fwd_kernel<<<grid, 256, AT_SMEM, static_cast<cudaStream_t>(p->stream)>>>(tq, tk, tv, g);
+  VY_CUDA_OK(launch_kernel(attn_fwd_kernel, dim3(grid), dim3(256), AT_SMEM, static_cast<cudaStream_t>(p->stream), tq, tk, tv, g));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -25,6 +25,8 @@ embed_fwd_kernel(int rows, int H, const long long* __restrict__ ids, const void*
                  long long ld_src, int dt, int vocab, int tokens_per_seq, int out_group_stride,
                  int out_row_off, const void* __restrict__ pos, int pos_row_off, float out_scale,
                  void* __restrict__ out, long long ld_out) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = H >> 3;
@@ -70,6 +72,8 @@ embed_bwd_kernel(int rows, int H, const long long* __restrict__ ids, int vocab, 
                  int out_group_stride, int out_row_off, int pos_row_off, float scale,
                  const void* __restrict__ dout, long long ld_dout, int dt, void* __restrict__ dtable,
                  long long ld_table, void* __restrict__ dpos) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = H >> 3;
@@ -96,6 +100,8 @@ embed_bwd_kernel(int rows, int H, const long long* __restrict__ ids, int vocab, 
 __global__ void __launch_bounds__(256)
 patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __restrict__ px, int in_dt,
                 void* __restrict__ out, int out_dt) {
+  pdl_trigger();
+  pdl_wait();
   const int gw = Ww / pw, gh = Hh / ph;
   const int K = C * ph * pw;
   const long long total = static_cast<long long>(B) * gh * gw * K;
@@ -118,6 +124,8 @@ patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __rest
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 argmax_rows_kernel(int rows, int V, const void* __restrict__ x, long long ld, int dt, long long* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   const int r = blockIdx.x;
@@ -163,6 +171,8 @@ constexpr int CS_CHUNKS = 64;
 // take interleaved rows of the CTA's row chunk, 4 rows in flight each, and are combined in smem.
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(int R, int Cn, const void* __restrict__ x, long long ld, int dt, float* __restrict__ part, int vec_ok) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -205,6 +215,8 @@ colsum_partial_kernel(int R, int Cn, const void* __restrict__ x, long long ld, i
 __global__ void __launch_bounds__(128)
 colsum_final_kernel(int Cn, int chunks, const float* __restrict__ part, void* __restrict__ out, int out_dt, int accumulate,
                     float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
   float a = 0.f;
@@ -220,6 +232,8 @@ colsum_final_kernel(int Cn, int chunks, const float* __restrict__ part, void* __
 __global__ void __launch_bounds__(256)
 cast4d_kernel(int n0, int n1, int n2, int n3, const void* __restrict__ src, int sdt, long long s0, long long s1,
               long long s2, void* __restrict__ dst, int ddt, long long d0, long long d1, long long d2) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(n0) * n1 * n2 * n3;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -241,6 +255,8 @@ __global__ void __launch_bounds__(256)
 xent_kernel(int rows, int V, void* __restrict__ logits, long long ld, int dt, const long long* __restrict__ labels,
             long long ignore_index, const float* __restrict__ grad_scale_ptr, float grad_scale,
             float* __restrict__ loss_rows, int write_grad, int vec_ok) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_m[8], s_s[8];
   const int r = blockIdx.x;
   const long long base = static_cast<long long>(r) * ld;
@@ -322,6 +338,8 @@ xent_kernel(int rows, int V, void* __restrict__ logits, long long ld, int dt, co
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 sqnorm_kernel(long long n, const void* __restrict__ g, int dt, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_red[8];
   float a = 0.f;
   const long long nvec = n >> 3;
@@ -353,6 +371,8 @@ adamw_kernel(long long n, void* __restrict__ p, int p_dt, const void* __restrict
              float* __restrict__ m, float* __restrict__ v, float* __restrict__ master, float lr, float beta1,
              float beta2, float eps, float wd, float bc1, float bc2, const int* __restrict__ step_ptr,
              const float* __restrict__ sqnorm, float max_norm, float grad_div) {
+  pdl_trigger();
+  pdl_wait();
   float clip = 1.f / grad_div;
   if (sqnorm && max_norm > 0.f) {
     const float norm = sqrtf(*sqnorm) / grad_div;
@@ -407,6 +427,8 @@ __global__ void __launch_bounds__(256)
 rope_kernel(int B, int H, int S, const void* __restrict__ x, long long xsb, long long xsh, long long xsl, int dt,
             const float* __restrict__ cs, const float* __restrict__ sn, int pos0, int inverse, void* __restrict__ out,
             long long osb, long long osh, long long osl) {
+  pdl_trigger();
+  pdl_wait();
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -427,6 +449,8 @@ rope_kernel(int B, int H, int S, const void* __restrict__ x, long long xsb, long
 
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(long long n, const void* __restrict__ dy, const void* __restrict__ z, int dt, int act, void* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long nvec = n >> 3;
   for (long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi < nvec;
        vi += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -461,9 +485,9 @@ extern "C" int vy_embed_fwd(const VyEmbed* p) {
                "vy_embed_fwd: 16-byte alignment required");
   const int tps = p->tokens_per_seq > 0 ? p->tokens_per_seq : p->rows;
   const int ogs = p->out_group_stride > 0 ? p->out_group_stride : tps;
-  embed_fwd_kernel<<<ew_grid(p->rows, 8), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+  VY_CUDA_OK(launch_kernel(embed_fwd_kernel, dim3(ew_grid(p->rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->rows, p->H, reinterpret_cast<const long long*>(p->ids), p->src, p->ld_src, p->dtype, p->vocab, tps, ogs,
-      p->out_row_off, p->pos, p->pos_row_off, p->out_scale == 0.f ? 1.f : p->out_scale, p->out, p->ld_out);
+      p->out_row_off, p->pos, p->pos_row_off, p->out_scale == 0.f ? 1.f : p->out_scale, p->out, p->ld_out));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -476,9 +500,9 @@ extern "C" int vy_embed_bwd(const VyEmbed* p) {
   VY_CHECK_ARG(p->dout && (p->dtable || p->dpos) && dtype_ok(p->dtype), "vy_embed_bwd: null pointer / bad dtype");
   const int tps = p->tokens_per_seq > 0 ? p->tokens_per_seq : p->rows;
   const int ogs = p->out_group_stride > 0 ? p->out_group_stride : tps;
-  embed_bwd_kernel<<<ew_grid(p->rows, 8), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+  VY_CUDA_OK(launch_kernel(embed_bwd_kernel, dim3(ew_grid(p->rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->rows, p->H, reinterpret_cast<const long long*>(p->ids), p->vocab, tps, ogs, p->out_row_off, p->pos_row_off,
-      p->out_scale == 0.f ? 1.f : p->out_scale, p->dout, p->ld_out, p->dtype, p->dtable, p->ld_src, p->dpos);
+      p->out_scale == 0.f ? 1.f : p->out_scale, p->dout, p->ld_out, p->dtype, p->dtable, p->ld_src, p->dpos));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -491,8 +515,8 @@ extern "C" int vy_patchify(const VyPatchify* p) {
                "vy_patchify: image dimensions must be divisible by the patch size");
   VY_CHECK_ARG(p->pixels && p->out && dtype_ok(p->in_dtype) && dtype_ok(p->out_dtype), "vy_patchify: null pointer / bad dtype");
   const long long total = static_cast<long long>(p->B) * p->C * p->H * p->W;
-  patchify_kernel<<<ew_grid(total, 1024), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
-      p->B, p->C, p->H, p->W, p->patch_h, p->patch_w, p->pixels, p->in_dtype, p->out, p->out_dtype);
+  VY_CUDA_OK(launch_kernel(patchify_kernel, dim3(ew_grid(total, 1024)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
+      p->B, p->C, p->H, p->W, p->patch_h, p->patch_w, p->pixels, p->in_dtype, p->out, p->out_dtype));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -501,7 +525,7 @@ extern "C" int vy_patchify(const VyPatchify* p) {
 extern "C" int vy_argmax_rows(int rows, int V, const void* x, int64_t ld, int dtype, int64_t* out, void* stream) {
   VY_NEED_DEVICE("vy_argmax_rows");
   VY_CHECK_ARG(rows > 0 && V > 0 && x && out && dtype_ok(dtype), "vy_argmax_rows: bad arguments");
-  argmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, V, x, ld, dtype, reinterpret_cast<long long*>(out));
+  VY_CUDA_OK(launch_kernel(argmax_rows_kernel, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, V, x, ld, dtype, reinterpret_cast<long long*>(out)));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -519,10 +543,10 @@ extern "C" int vy_colsum(int rows, int cols, const void* x, int64_t ld, int dtyp
   dim3 grid(colgroups, chunks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int vec_ok = (aligned16(x) && (ld * static_cast<long long>(dtype_size(dtype))) % 16 == 0) ? 1 : 0;
-  colsum_partial_kernel<<<grid, 256, 0, st>>>(rows, cols, x, ld, dtype, workspace, vec_ok);
+  VY_CUDA_OK(launch_kernel(colsum_partial_kernel, dim3(grid), dim3(256), 0, st, rows, cols, x, ld, dtype, workspace, vec_ok));
   VY_LAUNCH_OK();
-  colsum_final_kernel<<<(cols + 127) / 128, 128, 0, st>>>(cols, chunks, workspace, out, out_dtype, accumulate,
-                                                           scale == 0.f ? 1.f : scale);
+  VY_CUDA_OK(launch_kernel(colsum_final_kernel, dim3((cols + 127) / 128), dim3(128), 0, st, cols, chunks, workspace, out, out_dtype, accumulate,
+                                                           scale == 0.f ? 1.f : scale));
   VY_LAUNCH_OK();
   count_launch(2);
   return VY_OK;
@@ -536,8 +560,8 @@ extern "C" int vy_cast4d(const VyCast4d* p) {
   VY_CHECK_ARG(p->n0 > 0 && p->n1 > 0 && p->n2 > 0 && p->n3 > 0 && p->src && p->dst && dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype),
                "vy_cast4d: bad arguments");
   const long long total = static_cast<long long>(p->n0) * p->n1 * p->n2 * p->n3;
-  cast4d_kernel<<<ew_grid(total, 1024), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
-      p->n0, p->n1, p->n2, p->n3, p->src, p->src_dtype, p->s0, p->s1, p->s2, p->dst, p->dst_dtype, p->d0, p->d1, p->d2);
+  VY_CUDA_OK(launch_kernel(cast4d_kernel, dim3(ew_grid(total, 1024)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
+      p->n0, p->n1, p->n2, p->n3, p->src, p->src_dtype, p->s0, p->s1, p->s2, p->dst, p->dst_dtype, p->d0, p->d1, p->d2));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -547,10 +571,10 @@ extern "C" int vy_softmax_xent(const VyXent* p) {
   VY_CHECK_ARG(p != nullptr, "vy_softmax_xent: null params");
   VY_NEED_DEVICE("vy_softmax_xent");
   VY_CHECK_ARG(p->rows > 0 && p->V > 0 && p->logits && p->labels && dtype_ok(p->dtype), "vy_softmax_xent: bad arguments");
-  xent_kernel<<<p->rows, 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+  VY_CUDA_OK(launch_kernel(xent_kernel, dim3(p->rows), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->rows, p->V, p->logits, p->ld, p->dtype, reinterpret_cast<const long long*>(p->labels), p->ignore_index,
       p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->write_grad,
-      (aligned16(p->logits) && (p->ld * static_cast<long long>(dtype_size(p->dtype))) % 16 == 0) ? 1 : 0);
+      (aligned16(p->logits) && (p->ld * static_cast<long long>(dtype_size(p->dtype))) % 16 == 0) ? 1 : 0));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -559,7 +583,7 @@ extern "C" int vy_softmax_xent(const VyXent* p) {
 extern "C" int vy_sqnorm(int64_t n, const void* g, int dtype, float* out, void* stream) {
   VY_NEED_DEVICE("vy_sqnorm");
   VY_CHECK_ARG(n > 0 && g && out && dtype_ok(dtype) && aligned16(g), "vy_sqnorm: bad arguments");
-  sqnorm_kernel<<<ew_grid(n, 8 * 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, g, dtype, out);
+  VY_CUDA_OK(launch_kernel(sqnorm_kernel, dim3(ew_grid(n, 8 * 256 * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), n, g, dtype, out));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -573,10 +597,10 @@ extern "C" int vy_adamw(const VyAdamW* p) {
   VY_CHECK_ARG(p->step >= 1 || p->step_ptr, "vy_adamw: step must be >= 1 (or pass step_ptr)");
   const float bc1 = 1.f - powf(p->beta1, static_cast<float>(p->step));
   const float bc2 = 1.f - powf(p->beta2, static_cast<float>(p->step));
-  adamw_kernel<<<ew_grid(p->n, 1024), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+  VY_CUDA_OK(launch_kernel(adamw_kernel, dim3(ew_grid(p->n, 1024)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->n, p->param, p->param_dtype, p->grad, p->grad_dtype, p->exp_avg, p->exp_avg_sq, p->master, p->lr, p->beta1,
       p->beta2, p->eps, p->weight_decay, bc1, bc2, p->step_ptr, p->grad_sqnorm, p->max_grad_norm,
-      p->grad_div == 0.f ? 1.f : p->grad_div);
+      p->grad_div == 0.f ? 1.f : p->grad_div));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -588,8 +612,8 @@ extern "C" int vy_rope_apply(const VyRope* p) {
   VY_CHECK_ARG(p->head_dim == 64, "vy_rope_apply: head_dim must be 64 (got %d)", p->head_dim);
   VY_CHECK_ARG(p->B > 0 && p->H > 0 && p->S > 0 && p->x && p->out && p->cos && p->sin && dtype_ok(p->dtype), "vy_rope_apply: bad arguments");
   const long long rows = static_cast<long long>(p->B) * p->H * p->S;
-  rope_kernel<<<ew_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
-      p->B, p->H, p->S, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl);
+  VY_CUDA_OK(launch_kernel(rope_kernel, dim3(ew_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
+      p->B, p->H, p->S, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -600,7 +624,7 @@ extern "C" int vy_act_bwd(int64_t n, const void* dy, const void* z, int dtype, i
   VY_CHECK_ARG(n > 0 && n % 8 == 0 && dy && z && out && dtype_ok(dtype) && aligned16(dy) && aligned16(z) && aligned16(out),
                "vy_act_bwd: bad arguments (n must be a multiple of 8, pointers 16-byte aligned)");
   VY_CHECK_ARG(act == VY_ACT_GELU_ERF || act == VY_ACT_GELU_TANH, "vy_act_bwd: unsupported activation %d", act);
-  act_bwd_kernel<<<ew_grid(n, 8 * 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, dy, z, dtype, act, out);
+  VY_CUDA_OK(launch_kernel(act_bwd_kernel, dim3(ew_grid(n, 8 * 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), n, dy, z, dtype, act, out));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ ws, const void* __restrict__ bias, int bias_dt,
                      const void* __restrict__ addend, long long ld_addend, int addend_dt, float scale, void* __restrict__ out,
                      long long ld_out, int out_dt) {
+  pdl_trigger();
+  pdl_wait();
   const long long nvec = static_cast<long long>(M) * (N >> 3);
   const long long slab = static_cast<long long>(M) * N;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
@@ -238,9 +240,9 @@ extern "C" int vy_gemm(const VyGemm* p) {
     const long long nvec = static_cast<long long>(p->M) * (p->N >> 3);
     long long blocks = (nvec + 255) / 256;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(p->stream)>>>(
+    VY_CUDA_OK(launch_kernel(splitk_reduce_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
         p->M, p->N, tl.splits, g.ws, p->bias, p->bias_dtype, p->addend, p->ld_addend, p->addend_dtype,
-        p->out_scale == 0.f ? 1.f : p->out_scale, p->out, p->ld_out, p->out_dtype);
+        p->out_scale == 0.f ? 1.f : p->out_scale, p->out, p->ld_out, p->out_dtype));
     VY_LAUNCH_OK();
     count_launch();
     return VY_OK;

@@ -600,6 +600,7 @@ template <typename TIn, int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ GemmDev g) {
+  pdl_trigger();
   using Cfg = GemmCfg<TIn, BN>;
   constexpr int BM = Cfg::BM;
   constexpr int BK = Cfg::BK;
@@ -650,6 +651,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // everything above is independent of the predecessor grid's output
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -844,7 +846,7 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   const int n_tiles = (p->N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles * (g.k_splits > 1 ? g.k_splits : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream)>>>(ta, tb, g);
+  VY_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream), ta, tb, g));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -15,6 +15,8 @@ add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void
                          int io_dt, const void* __restrict__ gamma, const void* __restrict__ beta,
                          int p_dt, float eps, void* __restrict__ y, void* __restrict__ sum_out,
                          float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H >> 3;
   for (int row = blockIdx.x * NORM_WARPS + warp; row < rows; row += gridDim.x * NORM_WARPS) {
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(NORM_WARPS * 32, 1)
 add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s,
                          const void* __restrict__ gamma, int p_dt, const float* __restrict__ mean,
                          const float* __restrict__ rstd, void* __restrict__ dx, int want_dbias, float* __restrict__ partials) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];  // [NORM_WARPS][3][H]
   constexpr int IO_DT = IO_BF16 ? VY_BF16 : VY_F32;
   constexpr int RAW = IO_BF16 ? 1 : 2;  // uint4 per 8 elements
@@ -186,6 +190,8 @@ __global__ void __launch_bounds__(NORM_WARPS * 32, 2)
 add_layernorm_bwd_dx_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s, int io_dt,
                             const void* __restrict__ gamma, int p_dt, const float* __restrict__ mean,
                             const float* __restrict__ rstd, void* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H >> 3;
   float g[NV][8];
@@ -242,6 +248,8 @@ __global__ void __launch_bounds__(256)
 norm_bwd_columns_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s, const void* __restrict__ dx,
                         int io_dt, const float* __restrict__ mean, const float* __restrict__ rstd, int want_dbias,
                         float* __restrict__ partials) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][3][256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -311,6 +319,8 @@ norm_bwd_columns_kernel(int rows, int H, const void* __restrict__ dy, const void
 __global__ void __launch_bounds__(256)
 norm_bwd_reduce_kernel(int strips, int H, const float* __restrict__ partials, void* __restrict__ dgamma,
                        void* __restrict__ dbeta, void* __restrict__ dbias, int out_dt, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = dbias ? 3 : 2;
   if (idx >= nv * H) return;
@@ -354,9 +364,9 @@ extern "C" int vy_add_layernorm_fwd(const VyNorm* p) {
   if (grid > maxgrid) grid = maxgrid;
   cudaStream_t st = static_cast<cudaStream_t>(p->stream);
 #define VY_LN_FWD(NV)                                                                              \
-  add_layernorm_fwd_kernel<NV><<<grid, NORM_WARPS * 32, 0, st>>>(                                  \
+  VY_CUDA_OK(launch_kernel(add_layernorm_fwd_kernel<NV>, dim3(grid), dim3(NORM_WARPS * 32), 0, st,                                   \
       p->rows, p->H, p->x, p->residual, p->io_dtype, p->gamma, p->beta, p->param_dtype, p->eps, p->y, \
-      p->sum_out, p->mean, p->rstd)
+      p->sum_out, p->mean, p->rstd))
   switch (nv) {
     case 1: VY_LN_FWD(1); break;
     case 2: VY_LN_FWD(2); break;
@@ -392,8 +402,8 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
     auto kern = add_layernorm_bwd_kernel<NV, BF>;                                                    \
     if (smem > 48 * 1024)                                                                            \
       VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, NORM_WARPS * 32, smem, st>>>(p->rows, p->H, p->dy, p->s, p->gamma, p->param_dtype, p->mean, p->rstd, \
-                                              p->dx, p->dbias != nullptr, p->partials);               \
+    VY_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(NORM_WARPS * 32), smem, st, p->rows, p->H, p->dy, p->s, p->gamma, p->param_dtype, p->mean, p->rstd, \
+                                              p->dx, p->dbias != nullptr, p->partials));               \
   } while (0)
 #define VY_LN_BWD(NV)                     \
   do {                                    \
@@ -414,8 +424,8 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
     int g2 = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
     if (g2 > num_sms() * 8) g2 = num_sms() * 8;
 #define VY_LN_DX(NV)                                                                                        \
-  add_layernorm_bwd_dx_kernel<NV><<<g2, NORM_WARPS * 32, 0, st>>>(p->rows, p->H, p->dy, p->s, p->io_dtype, \
-                                                                   p->gamma, p->param_dtype, p->mean, p->rstd, p->dx)
+  VY_CUDA_OK(launch_kernel(add_layernorm_bwd_dx_kernel<NV>, dim3(g2), dim3(NORM_WARPS * 32), 0, st, p->rows, p->H, p->dy, p->s, p->io_dtype, \
+                                                                   p->gamma, p->param_dtype, p->mean, p->rstd, p->dx))
     switch (nv) {
       case 5: VY_LN_DX(5); break;
       case 6: VY_LN_DX(6); break;
@@ -427,13 +437,13 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
     strips = (p->rows + 63) / 64;
     if (strips > NORM_MAX_STRIPS) strips = NORM_MAX_STRIPS;
     dim3 cgrid((p->H + 255) / 256, strips);
-    norm_bwd_columns_kernel<<<cgrid, 256, 0, st>>>(p->rows, p->H, p->dy, p->s, p->dx, p->io_dtype, p->mean, p->rstd,
-                                                   p->dbias != nullptr, p->partials);
+    VY_CUDA_OK(launch_kernel(norm_bwd_columns_kernel, dim3(cgrid), dim3(256), 0, st, p->rows, p->H, p->dy, p->s, p->dx, p->io_dtype, p->mean, p->rstd,
+                                                   p->dbias != nullptr, p->partials));
   }
   VY_LAUNCH_OK();
   const int nvec = p->dbias ? 3 : 2;
-  norm_bwd_reduce_kernel<<<(nvec * p->H + 255) / 256, 256, 0, st>>>(strips, p->H, p->partials, p->dgamma, p->dbeta, p->dbias,
-                                                                    p->dparam_dtype, p->dparam_accumulate);
+  VY_CUDA_OK(launch_kernel(norm_bwd_reduce_kernel, dim3((nvec * p->H + 255) / 256), dim3(256), 0, st, strips, p->H, p->partials, p->dgamma, p->dbeta, p->dbias,
+                                                                    p->dparam_dtype, p->dparam_accumulate));
   VY_LAUNCH_OK();
   count_launch(2);
   return VY_OK;
