@@ -44,6 +44,14 @@ def main():
         name = name.split("(CUtensorMap")[0][:90]
         agg[name][0] += 1
         agg[name][1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+    if os.environ.get("VY_PROFILE_SEQUENCE"):
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda e: e.time_range.start)
+        n = len(evs) // steps
+        print("kernel sequence of the last step (us):")
+        for e in evs[-n:]:
+            nm = e.name.replace("void ", "").replace("vy::", "").replace("__nv_bfloat16", "bf16").split("(")[0][:60]
+            print(f"  {e.device_time_total:8.1f}  {nm}")
     total = sum(v[1] for v in agg.values())
     lines = [f"in-situ kernel time per training step (graph replay, {steps} steps averaged): {total / steps / 1e3:.2f} ms of kernels",
              "", "| kernel | launches/step | us/step | mean us | share |", "|---|---:|---:|---:|---:|"]
