@@ -347,9 +347,12 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] += a[j];
       }
+      if (scale != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= scale;
+      }
       *reinterpret_cast<uint4*>(srow + ((j4 ^ sw) << 4)) =
-          make_uint4(pack2_bf16(x[0] * scale, x[1] * scale), pack2_bf16(x[2] * scale, x[3] * scale),
-                     pack2_bf16(x[4] * scale, x[5] * scale), pack2_bf16(x[6] * scale, x[7] * scale));
+          make_uint4(pack2_bf16(x[0], x[1]), pack2_bf16(x[2], x[3]), pack2_bf16(x[4], x[5]), pack2_bf16(x[6], x[7]));
     }
     __syncwarp();
     if (nvalid >= 32) {
@@ -373,30 +376,46 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
     if (save_aux) __syncwarp();  // the aux buffer is reused by the very next chunk
   };
 
-  uint32_t raw_a[32], raw_b[32];
   const uint32_t taddr = tmem_acc + wcol0;
   const int trace_w = 2 + half * 4 + ((q + 2) & 3);
   (void)trace_w;
-  tmem_ld_x32(taddr, raw_a);
+  if (MODE == EPI_PLAIN || MODE == EPI_GELU) {
+    // no row operand to rotate: one rolled loop body per chunk keeps the hot code small (instruction cache); the
+    // tcgen05.ld latency is covered by the other epilogue warp of this SM sub-partition
+    uint32_t raw[32];
 #pragma unroll 1
-  for (int c = 0; c + 1 < NCH; c += 2) {  // chunk pairs (c -> buffer 0, c + 1 -> buffer 1)
-    tmem_ld_wait();
-    tmem_ld_x32(taddr + (c + 1) * 32, raw_b);
-    process(c, raw_a, pf[0], stage);
-    tmem_ld_wait();
-    if (c + 2 < NCH) {
-      tmem_ld_x32(taddr + (c + 2) * 32, raw_a);
-    } else {
+    for (int c = 0; c < NCH; ++c) {
+      tmem_ld_x32(taddr + c * 32, raw);
+      tmem_ld_wait();
+      if (c == NCH - 1) {
+        release_acc(tmem_empty_bar, lane);
+        VY_TRACE(trace_w, trace_tile, 2);
+      }
+      process(c, raw, pf[0], (save_aux || !(c & 1)) ? stage : stage + GEMM_STAGE_OUT);
+    }
+  } else {
+    uint32_t raw_a[32], raw_b[32];
+    tmem_ld_x32(taddr, raw_a);
+#pragma unroll 1
+    for (int c = 0; c + 1 < NCH; c += 2) {  // chunk pairs (c -> buffer 0, c + 1 -> buffer 1)
+      tmem_ld_wait();
+      tmem_ld_x32(taddr + (c + 1) * 32, raw_b);
+      process(c, raw_a, pf[0], stage);
+      tmem_ld_wait();
+      if (c + 2 < NCH) {
+        tmem_ld_x32(taddr + (c + 2) * 32, raw_a);
+      } else {
+        release_acc(tmem_empty_bar, lane);
+        VY_TRACE(trace_w, trace_tile, 2);
+      }
+      process(c + 1, raw_b, pf[1], stage + GEMM_STAGE_OUT);
+    }
+    if (NCH & 1) {  // odd chunk count: the last one is alone
+      tmem_ld_wait();
       release_acc(tmem_empty_bar, lane);
       VY_TRACE(trace_w, trace_tile, 2);
+      process(NCH - 1, raw_a, pf[0], stage);
     }
-    process(c + 1, raw_b, pf[1], save_aux ? stage : stage + GEMM_STAGE_OUT);
-  }
-  if (NCH & 1) {  // odd chunk count: the last one is alone
-    tmem_ld_wait();
-    release_acc(tmem_empty_bar, lane);
-    VY_TRACE(trace_w, trace_tile, 2);
-    process(NCH - 1, raw_a, pf[0], stage);
   }
   __syncwarp();  // the next tile's first chunk reuses stage buffer 0
 }

@@ -156,12 +156,12 @@ __device__ __forceinline__ float gauss_tail(float x, float& e) {
   p = fmaf(t, p, 0.5f * 1.421413741f);
   p = fmaf(t, p, 0.5f * -0.284496736f);
   p = fmaf(t, p, 0.5f * 0.254829592f);
-  return p * t * e;
+  return p * (t * e);
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float e;
-  const float xq = x * gauss_tail(x, e);  // x * (1 - Phi(|x|))
-  return x >= 0.f ? x - xq : xq;
+  const float q = gauss_tail(x, e);       // 1 - Phi(|x|)
+  return fmaf(-fabsf(x), q, fmaxf(x, 0.f));  // x >= 0: x - x q;  x < 0: x q = -|x| q
 }
 __device__ __forceinline__ float dgelu_erf(float x) {
   float e;
