@@ -1,0 +1,99 @@
+"""Config 3 of BASELINE.json: DecoderModel (GPT-style CLM, RoPE) prefill 512 + greedy decode 256, batch 32, bf16,
+StaticCacheOne. Prints prefill tok/s, decode tok/s (device-timed forward + argmax per step), the HBM roofline of a
+decode step (weights + kv-cache bytes over the measured copy bandwidth) and generate()'s own wall clock.
+    python tools/decode_bench.py [--attn gqa|mha] [--layers 4] [--batch 32]"""
+import argparse
+import io
+import json
+import os
+import sys
+import time
+from contextlib import redirect_stdout
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vyomai_b200 import DecoderModel, StaticCacheOne, ops  # noqa: E402
+
+
+class Cfg:
+    hidden_size = 768
+    num_attention_heads = 12
+    num_key_value_heads = 4
+    max_position_embeddings = 1024
+    num_hidden_layers = 4
+    vocab_size = 50265
+    hidden_dropout_prob = 0.0
+    initializer_range = 0.02
+    intermediate_size = 3072
+    layer_norm_eps = 1e-05
+    hidden_act = "gelu"
+    pad_token_id = 1
+    eos_token_id = 2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--attn", default="gqa")
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--prefill", type=int, default=512)
+    ap.add_argument("--decode", type=int, default=256)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    cfg = Cfg()
+    cfg.num_hidden_layers = args.layers
+    if args.attn != "gqa":
+        del Cfg.num_key_value_heads
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        model = DecoderModel(cfg, "rope", "gqa" if args.attn == "gqa" else None)
+    model = model.to(dev).to(torch.bfloat16).eval()
+    B, P, N = args.batch, args.prefill, args.decode
+    ids = torch.randint(3, cfg.vocab_size, (B, P), device=dev)
+    mask = torch.ones((B, P), device=dev, dtype=torch.long)
+    hkv = 4 if args.attn == "gqa" else 12
+
+    def run(timed):
+        cache = StaticCacheOne(cfg, max_cache_len=P + N, batch_size=B, dtype=torch.bfloat16)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        with torch.no_grad():
+            ev[0].record()
+            out = model(ids, mask, use_cache=True, kv_cache=cache, start_pos=0, _logits_last_only=True)
+            tok = ops.argmax_rows(out.logits[:, -1])
+            ev[1].record()
+            toks = [tok]
+            for t in range(N - 1):
+                out = model(tok.view(B, 1), None, use_cache=True, kv_cache=out.kv_cache, start_pos=P + t, _logits_last_only=True)
+                tok = ops.argmax_rows(out.logits[:, -1])
+                toks.append(tok)
+            ev[2].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), torch.stack(toks, 1)
+
+    run(False)
+    pre_ms, dec_ms, toks = run(True)
+    n_params = sum(p.numel() for n, p in model.named_parameters() if "word_embeddings" not in n)
+    mean_ctx = P + N / 2
+    step_bytes = 2.0 * n_params + 2.0 * B * args.layers * 2 * hkv * mean_ctx * 64
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    step_us = dec_ms * 1e3 / (N - 1)
+    t0 = time.perf_counter()
+    full = model.generate(ids, mask, max_len=N, use_cache=True, use_static_cache=True)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    res = {
+        "workload": f"decoder_clm_L{args.layers}_{args.attn}_B{B}_prefill{P}_decode{N}_bf16_staticcache",
+        "prefill_tok_per_s": B * P / (pre_ms / 1e3), "prefill_ms": pre_ms,
+        "decode_tok_per_s": B * (N - 1) / (dec_ms / 1e3), "decode_us_per_step": step_us,
+        "decode_step_algorithmic_MB": step_bytes / 1e6,
+        "decode_hbm_frac_of_measured": step_bytes / (step_us * 1e-6) / 1e9 / peaks["hbm_gbs"],
+        "generate_wall_s": gen_s, "generate_tok_per_s": B * N / gen_s,
+        "ids_match_generate": bool((full[:, P:P + N] == toks).all().item()),
+    }
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

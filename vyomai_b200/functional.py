@@ -70,9 +70,13 @@ class MaskSpec:
 # flat packing of q/k/v projection weights
 # ----------------------------------------------------------------------------------------------
 def _adjacent(ts) -> bool:
+    """True if the tensors are back-to-back slices of ONE storage (so a single strided view can span them).
+    Address adjacency alone is not enough: the caching allocator happily places separate small allocations
+    (e.g. three bias vectors) next to each other."""
     p = ts[0].data_ptr()
+    base = ts[0].untyped_storage().data_ptr()
     for t in ts:
-        if not t.is_contiguous() or t.data_ptr() != p:
+        if not t.is_contiguous() or t.data_ptr() != p or t.untyped_storage().data_ptr() != base:
             return False
         p += t.numel() * t.element_size()
     return True
