@@ -329,6 +329,9 @@ VY_API int vy_act_bwd(int64_t n, const void* dy, const void* z, int dtype, int a
 typedef struct VyDecode {
   int32_t B, n_q_heads, n_kv_heads, head_dim;
   int32_t start_pos, cache_len;
+  const int32_t* start_pos_ptr; /* optional device copy of start_pos (wins over the host value; start_pos is then
+                                   only the upper bound used to size the kv-split): a captured CUDA graph of one
+                                   decode step can be replayed for every token */
   const void* qkv;
   int64_t ld_qkv;
   int32_t qkv_dtype;

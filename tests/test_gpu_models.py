@@ -191,3 +191,40 @@ def test_vlm_forward_and_generate(dtype):
         vlm._clean_cache()
         assert torch.equal(g0, g1) and torch.equal(g0, g2)
         assert list(g0.shape) == list(fx.outputs["generate"].shape)
+
+
+@pytest.mark.parametrize("name", ["decoder_rope_gqa", "decoder_rope_mha"])
+def test_graph_decode_matches_python_loop(name):
+    """generate() with a static cache replays one captured CUDA graph per token (position read from device memory by
+    vy_attn_decode); ids and kv-cache contents must be bit-identical to the reference-style per-token loop, including
+    the early stop when every sequence has produced eos."""
+    from vyomai_b200 import DecoderModel
+    fx = load_fixture(name)
+    m = fx.meta
+    cfg = _cfg_obj(m)
+    model = _load(DecoderModel(cfg, m["pos"], m["attn"]), fx.sd, torch.bfloat16).eval()
+    torch.manual_seed(1)
+    B, P, N = 3, 9, 12
+    ids = torch.randint(3, cfg.vocab_size, (B, P), device="cuda")
+    mask = torch.ones((B, P), dtype=torch.long, device="cuda")
+    try:
+        DecoderModel.use_decode_graph = False
+        ref = model.generate(ids, mask, max_len=N, use_cache=True, use_static_cache=True)
+        DecoderModel.use_decode_graph = True
+        got = model.generate(ids, mask, max_len=N, use_cache=True, use_static_cache=True)
+        assert torch.equal(ref, got)
+        # force an early stop: declare the third generated token of every row an eos token
+        cfg.eos_token_id = [int(t) for t in ref[:, P + 2].tolist()]
+        DecoderModel.use_decode_graph = False
+        ref2 = model.generate(ids, mask, max_len=N, use_cache=True, use_static_cache=True)
+        DecoderModel.use_decode_graph = True
+        got2 = model.generate(ids, mask, max_len=N, use_cache=True, use_static_cache=True)
+        assert torch.equal(ref2, got2)
+        assert bool((ref2[:, P + 3:] == getattr(cfg, "pad_token_id", 1)).all())
+    finally:
+        DecoderModel.use_decode_graph = True
+        if hasattr(cfg, "eos_token_id"):
+            try:
+                del cfg.eos_token_id
+            except AttributeError:
+                pass

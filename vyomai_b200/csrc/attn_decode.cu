@@ -24,10 +24,11 @@ constexpr int HD = 64;
 
 struct DecodeDev {
   int B, Hq, Hkv, n_rep, start_pos, splits;
+  const int* start_pos_ptr;  // device copy of start_pos (wins when set): lets a captured CUDA graph be replayed per token
   const void* qkv;  // [B, (Hq + 2 Hkv) * 64]
   long long ld_qkv;
   int qkv_dtype;
-  const float* rope_cos;  // row for position start_pos: [32], or null
+  const float* rope_cos;  // table [cache_len][32] (row = position), or null
   const float* rope_sin;
   void* kcache;
   void* vcache;
@@ -71,7 +72,7 @@ attn_decode_kernel(const DecodeDev g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = lane & 7;   // which 8-element slice of the head dim
   const int lk = lane >> 3;  // key sub-index within the warp step (0..3)
-  const int ctx = g.start_pos + 1;
+  const int sp = g.start_pos_ptr ? *g.start_pos_ptr : g.start_pos;  // slot / position of the new token
 
   __shared__ float s_newk[HD];
   __shared__ float s_newv[HD];
@@ -93,7 +94,7 @@ attn_decode_kernel(const DecodeDev g) {
       if (which <= NREP && g.rope_cos) {
         const int jj = j & 31;
         const float other = ld_as_float(g.qkv, g.qkv_dtype, row + col + (j < 32 ? j + 32 : j - 32));
-        const float c = g.rope_cos[jj], s = g.rope_sin[jj];
+        const float c = g.rope_cos[sp * 32 + jj], s = g.rope_sin[sp * 32 + jj];
         x = j < 32 ? x * c - other * s : x * c + other * s;
       }
       if (which < NREP) s_q[which][j] = x;
@@ -106,8 +107,8 @@ attn_decode_kernel(const DecodeDev g) {
   TC* vc = reinterpret_cast<TC*>(g.vcache) + b * g.c_sb + kvh * g.c_sh;
   if (split == g.splits - 1 && threadIdx.x < HD) {
     // the cache stores what the reference stores: rotated k and raw v, rounded to the cache dtype
-    st_from_float(kc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, g.start_pos * g.c_sl + threadIdx.x, s_newk[threadIdx.x]);
-    st_from_float(vc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, g.start_pos * g.c_sl + threadIdx.x, s_newv[threadIdx.x]);
+    st_from_float(kc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, sp * g.c_sl + threadIdx.x, s_newk[threadIdx.x]);
+    st_from_float(vc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, sp * g.c_sl + threadIdx.x, s_newv[threadIdx.x]);
   }
 
   float q[NREP][8];
@@ -127,9 +128,9 @@ attn_decode_kernel(const DecodeDev g) {
 
   // cached slots [0, start_pos) are split evenly; the new token (slot start_pos) is taken from
   // smem by the last split so no CTA has to wait for the append to become visible.
-  const int per = (g.start_pos + g.splits - 1) / g.splits;
+  const int per = (sp + g.splits - 1) / g.splits;
   const int k_begin = split * per;
-  const int k_end = min(g.start_pos, k_begin + per);
+  const int k_end = min(sp, k_begin + per);
   constexpr int KEYS_PER_ITER = DEC_WARPS * 4 * DEC_UNROLL;
 
   for (int k0 = k_begin; k0 < k_end; k0 += KEYS_PER_ITER) {
@@ -187,7 +188,6 @@ attn_decode_kernel(const DecodeDev g) {
       m[r] = mn;
     }
   }
-  (void)ctx;
 
   // ---- merge the 4 lane groups of each warp (xor 8, 16) ----
 #pragma unroll
@@ -335,9 +335,10 @@ extern "C" int vy_attn_decode(const VyDecode* p) {
   DecodeDev g;
   g.B = p->B; g.Hq = p->n_q_heads; g.Hkv = p->n_kv_heads; g.n_rep = p->n_q_heads / p->n_kv_heads;
   g.start_pos = p->start_pos; g.splits = splits;
+  g.start_pos_ptr = p->start_pos_ptr;
   g.qkv = p->qkv; g.ld_qkv = p->ld_qkv; g.qkv_dtype = p->qkv_dtype;
-  g.rope_cos = p->rope_cos ? p->rope_cos + static_cast<long long>(p->start_pos) * 32 : nullptr;
-  g.rope_sin = p->rope_sin ? p->rope_sin + static_cast<long long>(p->start_pos) * 32 : nullptr;
+  g.rope_cos = p->rope_cos;
+  g.rope_sin = p->rope_sin;
   g.kcache = p->k_cache; g.vcache = p->v_cache;
   g.c_sb = p->cache_sb; g.c_sh = p->cache_sh; g.c_sl = p->cache_sl; g.cache_dtype = p->cache_dtype;
   g.out = p->out; g.ld_out = p->ld_out; g.out_dtype = p->out_dtype;

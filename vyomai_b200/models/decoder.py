@@ -108,6 +108,35 @@ class DecoderModel(nn.Module, TextStem):
     def from_config(cls, config, pos_embedding_type: Optional[str] = "absolute", attention_type: Optional[str] = None) -> nn.Module:
         return cls(config, pos_embedding_type, attention_type)
 
+    use_decode_graph = True  # class-level switch: False forces the per-token Python loop of the reference
+
+    def _generate_graph(self, tokens, attention_mask, kv_cache, prompt_len: int, max_len: int, pad_id: int) -> torch.Tensor:
+        """Greedy continuation of full-length prompts with a static cache: eager prefill, then one CUDA-graph replay
+        per token (decode_graph.GreedyDecodeGraph). Token ids, cache contents and the early stop are those of the
+        reference loop (decoder.py:470-513): the reference stops after the first step at which every sequence has
+        produced an eos token and leaves the remaining positions at pad_id, which is applied here after the fact."""
+        from ..decode_graph import GreedyDecodeGraph
+        bsz = tokens.shape[0]
+        dev = tokens.device
+        out = self.forward(input_ids=tokens[:, :prompt_len].contiguous(), attention_mask=attention_mask, use_cache=True,
+                           kv_cache=kv_cache, start_pos=0, _logits_last_only=True)
+        first = ops.argmax_rows(out.logits[:, -1])
+        tokens[:, prompt_len] = first
+        steps = max_len - prompt_len - 1
+        if steps > 0:
+            g = getattr(self, "_decode_graph", None)
+            if g is None or g.cache is not kv_cache:
+                g = self._decode_graph = GreedyDecodeGraph(self, kv_cache, bsz, max_len)
+            g.run(first, prompt_len, steps)
+            tokens[:, prompt_len + 1:] = g.tokens[:, prompt_len + 1:]
+        stop_tokens = torch.as_tensor(getattr(self.config, "eos_token_id", 2), device=dev)
+        gen = tokens[:, prompt_len:]
+        hit = torch.isin(gen, stop_tokens).to(torch.int32).cummax(dim=1).values.bool()  # eos seen at or before step t
+        all_hit = hit.all(dim=0)                                                          # the reference breaks after step t
+        after = torch.cat([torch.zeros(1, dtype=torch.bool, device=dev), all_hit[:-1]]).to(torch.int32).cummax(dim=0).values.bool()
+        gen[:, after] = pad_id
+        return tokens
+
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, max_len: int = 5, temperature: float = 1.0,
                  use_cache: bool = True, do_sample: bool = False, use_static_cache: bool = False) -> torch.Tensor:
@@ -123,13 +152,27 @@ class DecoderModel(nn.Module, TextStem):
         bsz, _ = input_ids.size()
         tokens = torch.full((bsz, max_len), pad_id, dtype=torch.long, device=dev)
         kv_cache = None
+        graph_path = (self.use_decode_graph and use_cache and use_static_cache and not do_sample and self._rope is not None
+                      and min_prompt_len == input_ids.shape[1] and bool((input_ids != pad_id).all()))
         if use_cache:
-            if use_static_cache:
+            if use_static_cache and graph_path:
+                # the captured step is bound to its cache buffers: keep both and reuse them for calls of the same shape
+                # (slots beyond the current position are never read, so a stale cache needs no clearing)
+                key = (bsz, max_len, self.word_embeddings.weight.dtype, dev)
+                if getattr(self, "_decode_graph_key", None) != key:
+                    self._decode_graph_key = key
+                    self._decode_graph_cache = StaticCacheOne(self.config, max_cache_len=max_len, batch_size=bsz,
+                                                              dtype=self.word_embeddings.weight.dtype)
+                    self._decode_graph = None
+                kv_cache = self._decode_graph_cache
+            elif use_static_cache:
                 kv_cache = StaticCacheOne(self.config, max_cache_len=max_len, batch_size=bsz,
                                           dtype=self.word_embeddings.weight.dtype)
             else:
                 kv_cache = DynamicCacheOne(self.config)
         tokens[:, : input_ids.shape[1]] = input_ids
+        if graph_path:
+            return back_to(origin, self._generate_graph(tokens, attention_mask, kv_cache, min_prompt_len, max_len, pad_id))
         prev_pos = 0
         eos_reached = torch.zeros(bsz, dtype=torch.bool, device=dev)
         input_text_mask = tokens != pad_id

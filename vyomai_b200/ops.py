@@ -351,8 +351,11 @@ def attn_decode(
     out: Optional[torch.Tensor] = None,
     out_dtype: Optional[torch.dtype] = None,
     splits: int = 0,
+    start_pos_dev: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """Single-token attention with fused RoPE and kv-cache append. qkv [B, (Hq+2Hkv)*64] packed
+    """Single-token attention with fused RoPE and kv-cache append. With `start_pos_dev` (int32 [1] on the device) the
+    kernel takes the position from device memory and `start_pos` is only the upper bound that sizes the kv-split —
+    the form a captured decode step uses. qkv [B, (Hq+2Hkv)*64] packed
     projections; caches [>=B, Hkv, cache_len, 64]; returns out [B, Hq*64]."""
     _need_cuda(qkv, k_cache, v_cache, rope_cos, rope_sin, out)
     B = qkv.shape[0]
@@ -375,7 +378,7 @@ def attn_decode(
         rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin), k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),
         cache_sb=k_cache.stride(0), cache_sh=k_cache.stride(1), cache_sl=k_cache.stride(2), cache_dtype=_dt(k_cache),
         out=out.data_ptr(), ld_out=out.stride(0), out_dtype=_dt(out), splits=splits, workspace=_ptr(ws),
-        tickets=_ptr(tk), stream=_stream(),
+        tickets=_ptr(tk), start_pos_ptr=_ptr(start_pos_dev), stream=_stream(),
     )
     return out
 
@@ -445,10 +448,13 @@ def patchify(pixels: torch.Tensor, patch: Tuple[int, int], dtype: torch.dtype) -
     return out
 
 
-def argmax_rows(x: torch.Tensor) -> torch.Tensor:
+def argmax_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Greedy token ids: first index of each row's maximum. x is 2-D with unit inner stride."""
-    _need_cuda(x)
-    out = torch.empty(x.shape[0], device=x.device, dtype=torch.int64)
+    _need_cuda(x, out)
+    if out is None:
+        out = torch.empty(x.shape[0], device=x.device, dtype=torch.int64)
+    elif out.dtype != torch.int64 or not out.is_contiguous() or out.numel() != x.shape[0]:
+        raise _lib.VyomError("argmax_rows: out must be a contiguous int64 tensor with one entry per row")
     _lib.check(_lib.lib().vy_argmax_rows(x.shape[0], x.shape[1], x.data_ptr(), x.stride(0), _dt(x), out.data_ptr(), _stream()),
                "vy_argmax_rows")
     return out
