@@ -94,6 +94,15 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     graph_step_us = e0.elapsed_time(e1) * 1e3 / (N - 1)
+    if os.environ.get("VY_PROFILE_SEQUENCE"):
+        g.pos.fill_(P + N // 2)
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            g.graph.replay()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda e: e.time_range.start)
+        for e in evs:
+            print(f"  {e.device_time_total:8.1f}  {e.name[:100]}", file=sys.stderr)
     res = {
         "workload": f"decoder_clm_L{args.layers}_{args.attn}_B{B}_prefill{P}_decode{N}_bf16_staticcache",
         "prefill_tok_per_s": B * P / (pre_ms / 1e3), "prefill_ms": pre_ms,

@@ -122,23 +122,58 @@ patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __rest
 // greedy next-token: argmax over the vocabulary, first index on ties (torch.topk(k=1) rule used
 // by models/decoder.py:489-496 and generation_utils.py:179-189). One CTA per row.
 // ------------------------------------------------------------------------------------------
+// Rows are long (a vocabulary) and few (a decode batch), so a row is split over several CTAs: each finds the (max,
+// first index) of its slice and folds it into out[r] with a 64-bit atomicMax on the packed key
+// (order-preserving float bits << 32 | ~index): larger value wins, equal values keep the SMALLER index — the
+// torch.topk(k=1) rule. out[] must be zero on entry (vy_argmax_rows clears it); a second tiny kernel unpacks.
+__device__ __forceinline__ unsigned int float_order_bits(float v) {
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 __global__ void __launch_bounds__(256)
-argmax_rows_kernel(int rows, int V, const void* __restrict__ x, long long ld, int dt, long long* __restrict__ out) {
+argmax_rows_kernel(int rows, int V, int per, const void* __restrict__ x, long long ld, int dt,
+                   unsigned long long* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_v[8];
   __shared__ int s_i[8];
-  const int r = blockIdx.x;
+  const int r = blockIdx.y;
+  const int c0 = blockIdx.x * per, c1 = min(V, c0 + per);
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float v = ld_as_float(x, dt, static_cast<long long>(r) * ld + c);
-    if (v > best || (v == best && c < bi)) {
-      best = v;
-      bi = c;
+  const long long base = static_cast<long long>(r) * ld;
+  const bool vec = dt == VY_BF16 && (ld & 7) == 0 && (c0 & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  int c = c0 + threadIdx.x * 8;
+  if (vec) {
+    for (; c + 8 <= c1; c += blockDim.x * 8) {
+      float v[8];
+      ld8_as_float(x, dt, base + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[j] > best) {  // ascending index within a thread: strict > keeps the first maximum
+          best = v[j];
+          bi = c + j;
+        }
+    }
+    // ragged tail of the slice (at most 7 + misaligned leftovers): thread 0..7 scalar
+    const int tail0 = c0 + ((c1 - c0) / 8) * 8;
+    if (threadIdx.x < c1 - tail0) {
+      const int ct = tail0 + threadIdx.x;
+      const float v = ld_as_float(x, dt, base + ct);
+      if (v > best || (v == best && ct < bi)) {
+        best = v;
+        bi = ct;
+      }
+    }
+  } else {
+    for (int cc = c0 + threadIdx.x; cc < c1; cc += blockDim.x) {
+      const float v = ld_as_float(x, dt, base + cc);
+      if (v > best || (v == best && cc < bi)) {
+        best = v;
+        bi = cc;
+      }
     }
   }
-  if (bi == 0x7fffffff && threadIdx.x == 0) bi = 0;  // all -inf / NaN row: fall back to index 0
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
@@ -159,8 +194,22 @@ argmax_rows_kernel(int rows, int V, const void* __restrict__ x, long long ld, in
         best = s_v[w];
         bi = s_i[w];
       }
-    out[r] = bi;
+    if (bi != 0x7fffffff) {  // a slice of only -inf / NaN contributes nothing (an all -inf / NaN row ends as index 0)
+      const unsigned long long key = (static_cast<unsigned long long>(float_order_bits(best)) << 32) |
+                                     static_cast<unsigned long long>(0xffffffffu - static_cast<unsigned int>(bi));
+      atomicMax(out + r, key);
+    }
   }
+}
+__global__ void __launch_bounds__(256)
+argmax_unpack_kernel(int rows, unsigned long long* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const unsigned long long key = out[r];
+  const long long idx = key == 0ull ? 0ll : static_cast<long long>(0xffffffffu - static_cast<unsigned int>(key & 0xffffffffull));
+  reinterpret_cast<long long*>(out)[r] = idx;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -525,9 +574,22 @@ extern "C" int vy_patchify(const VyPatchify* p) {
 extern "C" int vy_argmax_rows(int rows, int V, const void* x, int64_t ld, int dtype, int64_t* out, void* stream) {
   VY_NEED_DEVICE("vy_argmax_rows");
   VY_CHECK_ARG(rows > 0 && V > 0 && x && out && dtype_ok(dtype), "vy_argmax_rows: bad arguments");
-  VY_CUDA_OK(launch_kernel(argmax_rows_kernel, dim3(rows), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, V, x, ld, dtype, reinterpret_cast<long long*>(out)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int slices = (2 * num_sms() + rows - 1) / rows;  // ~2 CTAs per SM over all rows
+  const int max_slices = (V + 2047) / 2048;         // at least 2048 columns per slice
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  int per = (V + slices - 1) / slices;
+  per = (per + 7) / 8 * 8;  // slices start on 16-byte boundaries of a bf16 row
+  slices = (V + per - 1) / per;
+  VY_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(int64_t) * rows, st));
+  VY_CUDA_OK(launch_kernel(argmax_rows_kernel, dim3(slices, rows), dim3(256), 0, st, rows, V, per, x, ld, dtype,
+                           reinterpret_cast<unsigned long long*>(out)));
   VY_LAUNCH_OK();
-  count_launch();
+  VY_CUDA_OK(launch_kernel(argmax_unpack_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, rows,
+                           reinterpret_cast<unsigned long long*>(out)));
+  VY_LAUNCH_OK();
+  count_launch(2);
   return VY_OK;
 }
 
