@@ -451,50 +451,52 @@ __device__ __forceinline__ void epilogue_splitk(const GemmDev& g, uint32_t tmem_
   }
 }
 
-// swap-AB epilogue: accumulator row = logical output COLUMN (a weight row), accumulator column =
-// logical output ROW (a token). Stores are scalar per thread but coalesced across the warp.
+// swap-AB epilogue: accumulator row = logical output COLUMN (a weight row), accumulator column = logical output ROW
+// (a token). Decode-shaped GEMMs run one tile per CTA, so every instruction of the epilogue is executed once and
+// fetched cold: the code is kept SMALL instead of unrolled — each 32-column chunk is transposed through the
+// staging buffer (fp32 [32 tokens][128 + 1 features], conflict-free) and finished by one rolled loop in which
+// consecutive threads own consecutive features of a token, so bias / addend / aux / out accesses are coalesced.
 template <int BN>
-__device__ __forceinline__ void epilogue_transposed(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
-                                                    int lane, uint64_t* tfull_bar, uint32_t tfull_phase,
-                                                    uint64_t* tmem_empty_bar) {
-  constexpr int WC = BN >= 64 ? BN / 2 : BN;
-  constexpr int NCH = WC / 32;
-  if (BN < 64 && half) {
-    release_acc(tmem_empty_bar, lane);
-    return;
-  }
-  const int wcol0 = BN >= 64 ? half * WC : 0;
-  const int lc = m0 + q * 32 + lane;  // logical column
-  const bool ok = lc < g.M;
+__device__ __forceinline__ void epilogue_transposed(const GemmDev& g, uint32_t tmem_base_acc, int m0, int n0, int q, int half,
+                                                    int lane, int et, uint64_t* tfull_bar, uint32_t tfull_phase,
+                                                    uint64_t* tmem_empty_bar, float* stage_f) {
+  constexpr int NCH = BN >= 32 ? BN / 32 : 1;
+  constexpr int LDT = 128 + 1;
   const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
   const bool fwd_act = g.act == VY_ACT_GELU_ERF || g.act == VY_ACT_GELU_TANH;
   const bool bwd_act = g.act == VY_ACT_DGELU_ERF || g.act == VY_ACT_DGELU_TANH;
-  const float b = (ok && g.bias) ? ld_as_float(g.bias, g.bias_dtype, lc) : 0.f;
   mbar_wait(tfull_bar, tfull_phase);
   tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
-    uint32_t raw[32];
-    tmem_ld_x32(tmem_acc + wcol0 + c * 32, raw);
-    tmem_ld_wait();
-    if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
-    if (!ok) continue;
+    if (half == 0) {  // one warp per lane quarter moves the chunk; all eight finish it
+      uint32_t raw[32];
+      tmem_ld_x32(tmem_base_acc + (static_cast<uint32_t>(q * 32) << 16) + c * 32, raw);
+      tmem_ld_wait();
+      float* col0 = stage_f + q * 32 + lane;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int lr = n0 + wcol0 + c * 32 + j;  // logical row
-      if (lr < g.N) {
-        float x = __uint_as_float(raw[j]) + b;
-        if (fwd_act) {
-          if (g.aux) st_from_float(g.aux, g.aux_dtype, static_cast<long long>(lr) * g.ld_aux + lc, x);
-          x = apply_act(g.act, x);
-        } else if (bwd_act) {
-          x *= apply_dact(g.act, ld_as_float(g.aux, g.aux_dtype, static_cast<long long>(lr) * g.ld_aux + lc));
-        }
-        if (g.addend) x += ld_as_float(g.addend, g.addend_dtype, remap_add_row(g, lr) * g.ld_addend + lc);
-        if (g.addend2) x += ld_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(lr) * g.ld_addend2 + lc);
-        st_from_float(g.out, g.out_dtype, remap_out_row(g, lr) * g.ld_out + lc, x * scale);
-      }
+      for (int j = 0; j < 32; ++j) col0[j * LDT] = __uint_as_float(raw[j]);
     }
+    if (c == NCH - 1) release_acc(tmem_empty_bar, lane);
+    named_bar_sync(2, GEMM_EPI_WARPS * 32);
+#pragma unroll 1
+    for (int idx = et; idx < 32 * 128; idx += GEMM_EPI_WARPS * 32) {
+      const int j = idx >> 7, r = idx & 127;
+      const int lc = m0 + r;             // logical column (feature)
+      const int lr = n0 + c * 32 + j;    // logical row (token)
+      if (lc >= g.M || lr >= g.N) continue;
+      float x = stage_f[j * LDT + r] + (g.bias ? ld_as_float(g.bias, g.bias_dtype, lc) : 0.f);
+      if (fwd_act) {
+        if (g.aux) st_from_float(g.aux, g.aux_dtype, static_cast<long long>(lr) * g.ld_aux + lc, x);
+        x = apply_act(g.act, x);
+      } else if (bwd_act) {
+        x *= apply_dact(g.act, ld_as_float(g.aux, g.aux_dtype, static_cast<long long>(lr) * g.ld_aux + lc));
+      }
+      if (g.addend) x += ld_as_float(g.addend, g.addend_dtype, remap_add_row(g, lr) * g.ld_addend + lc);
+      if (g.addend2) x += ld_as_float(g.addend2, g.addend2_dtype, static_cast<long long>(lr) * g.ld_addend2 + lc);
+      st_from_float(g.out, g.out_dtype, remap_out_row(g, lr) * g.ld_out + lc, x * scale);
+    }
+    named_bar_sync(2, GEMM_EPI_WARPS * 32);  // the staging buffer is reused by the next chunk / tile
   }
 }
 
@@ -791,7 +793,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if constexpr (BN >= 64)
           epilogue_qkv_rope<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
       } else if (g.transposed_out) {
-        epilogue_transposed<BN>(g, tmem_acc, m0, n0, q, half, lane, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
+        epilogue_transposed<BN>(g, tmem_base + acc * BN, m0, n0, q, half, lane, et, &tfull_bar[acc], acc_ph, &tempty_bar[acc],
+                                reinterpret_cast<float*>(epi_stage));
       } else if (fast_mode == EPI_PLAIN) {
         epilogue_linear_fast<BN, EPI_PLAIN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
       } else if (fast_mode == EPI_ADD) {
