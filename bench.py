@@ -257,13 +257,18 @@ def run_ours(args):
     prof = _lib.TIMER.summary()
     _lib.TIMER = None
     hbm, tf_burst, tf_sust, src = peaks()
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_mean")
     total_ms = sum(d["ms"] for d in prof.values())
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     name, d = dom
     if d["flops"] > 0:
         achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
-                "frac": achieved / tf_sust, "traffic": None, "peak_source": f"{src} (sustained bf16 GEMM)",
+                "frac": achieved / tf_sust, "traffic": traffic if name == "vy_gemm" else None,
+                "peak_source": f"{src} (sustained bf16 GEMM)",
                 "launches_per_step": d["calls"], "share_of_kernel_time": d["ms"] / total_ms}
     else:
         achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
