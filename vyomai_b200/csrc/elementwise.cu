@@ -99,12 +99,31 @@ embed_bwd_kernel(int rows, int H, const long long* __restrict__ ids, int vocab, 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __restrict__ px, int in_dt,
-                void* __restrict__ out, int out_dt) {
+                void* __restrict__ out, int out_dt, int vec) {
   pdl_trigger();
   pdl_wait();
   const int gw = Ww / pw, gh = Hh / ph;
   const int K = C * ph * pw;
   const long long total = static_cast<long long>(B) * gh * gw * K;
+  if (vec) {
+    // 8 consecutive outputs = 8 consecutive pixels of one patch row (pw % 8 == 0): one 16/32-byte load and store
+    const long long nvec = total >> 3;
+    for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
+         v += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long i = v << 3;
+      const int kk = static_cast<int>(i % K);
+      const long long prow = i / K;
+      const int s = static_cast<int>(prow % gw);
+      const int r = static_cast<int>((prow / gw) % gh);
+      const int b = static_cast<int>(prow / (static_cast<long long>(gw) * gh));
+      const int j = kk % pw, ii = (kk / pw) % ph, c = kk / (pw * ph);
+      const long long src = ((static_cast<long long>(b) * C + c) * Hh + (r * ph + ii)) * Ww + (s * pw + j);
+      float x[8];
+      ld8_as_float(px, in_dt, src, x);
+      st8_from_float(out, out_dt, i, x);
+    }
+    return;
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int kk = static_cast<int>(i % K);
@@ -280,19 +299,28 @@ colsum_final_kernel(int Cn, int chunks, const float* __restrict__ part, void* __
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 cast4d_kernel(int n0, int n1, int n2, int n3, const void* __restrict__ src, int sdt, long long s0, long long s1,
-              long long s2, void* __restrict__ dst, int ddt, long long d0, long long d1, long long d2) {
+              long long s2, void* __restrict__ dst, int ddt, long long d0, long long d1, long long d2, int vec) {
   pdl_trigger();
   pdl_wait();
-  const long long total = static_cast<long long>(n0) * n1 * n2 * n3;
+  const int w = vec ? 8 : 1;  // elements per thread along the contiguous inner dim
+  const int n3v = n3 / w;
+  const long long total = static_cast<long long>(n0) * n1 * n2 * n3v;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int i3 = static_cast<int>(i % n3);
-    long long t = i / n3;
+    const int i3 = static_cast<int>(i % n3v) * w;
+    long long t = i / n3v;
     const int i2 = static_cast<int>(t % n2);
     t /= n2;
     const int i1 = static_cast<int>(t % n1);
     const int i0 = static_cast<int>(t / n1);
-    st_from_float(dst, ddt, i0 * d0 + i1 * d1 + i2 * d2 + i3, ld_as_float(src, sdt, i0 * s0 + i1 * s1 + i2 * s2 + i3));
+    const long long so = i0 * s0 + i1 * s1 + i2 * s2 + i3, dof = i0 * d0 + i1 * d1 + i2 * d2 + i3;
+    if (vec) {
+      float x[8];
+      ld8_as_float(src, sdt, so, x);
+      st8_from_float(dst, ddt, dof, x);
+    } else {
+      st_from_float(dst, ddt, dof, ld_as_float(src, sdt, so));
+    }
   }
 }
 
@@ -564,8 +592,10 @@ extern "C" int vy_patchify(const VyPatchify* p) {
                "vy_patchify: image dimensions must be divisible by the patch size");
   VY_CHECK_ARG(p->pixels && p->out && dtype_ok(p->in_dtype) && dtype_ok(p->out_dtype), "vy_patchify: null pointer / bad dtype");
   const long long total = static_cast<long long>(p->B) * p->C * p->H * p->W;
-  VY_CUDA_OK(launch_kernel(patchify_kernel, dim3(ew_grid(total, 1024)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
-      p->B, p->C, p->H, p->W, p->patch_h, p->patch_w, p->pixels, p->in_dtype, p->out, p->out_dtype));
+  const int vec = (p->patch_w % 8 == 0 && p->W % 8 == 0 && aligned16(p->pixels) && aligned16(p->out)) ? 1 : 0;
+  VY_CUDA_OK(launch_kernel(patchify_kernel, dim3(ew_grid(vec ? total / 8 : total, 1024)), dim3(256), 0,
+                           static_cast<cudaStream_t>(p->stream), p->B, p->C, p->H, p->W, p->patch_h, p->patch_w, p->pixels,
+                           p->in_dtype, p->out, p->out_dtype, vec));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -622,8 +652,14 @@ extern "C" int vy_cast4d(const VyCast4d* p) {
   VY_CHECK_ARG(p->n0 > 0 && p->n1 > 0 && p->n2 > 0 && p->n3 > 0 && p->src && p->dst && dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype),
                "vy_cast4d: bad arguments");
   const long long total = static_cast<long long>(p->n0) * p->n1 * p->n2 * p->n3;
-  VY_CUDA_OK(launch_kernel(cast4d_kernel, dim3(ew_grid(total, 1024)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
-      p->n0, p->n1, p->n2, p->n3, p->src, p->src_dtype, p->s0, p->s1, p->s2, p->dst, p->dst_dtype, p->d0, p->d1, p->d2));
+  auto ok8 = [](const void* ptr, long long a, long long b_, long long c, int dt) {
+    const long long es = static_cast<long long>(dtype_size(dt));
+    return aligned16(ptr) && (a * es) % 16 == 0 && (b_ * es) % 16 == 0 && (c * es) % 16 == 0;
+  };
+  const int vec = (p->n3 % 8 == 0 && ok8(p->src, p->s0, p->s1, p->s2, p->src_dtype) && ok8(p->dst, p->d0, p->d1, p->d2, p->dst_dtype)) ? 1 : 0;
+  VY_CUDA_OK(launch_kernel(cast4d_kernel, dim3(ew_grid(vec ? total / 8 : total, 1024)), dim3(256), 0,
+                           static_cast<cudaStream_t>(p->stream), p->n0, p->n1, p->n2, p->n3, p->src, p->src_dtype, p->s0, p->s1,
+                           p->s2, p->dst, p->dst_dtype, p->d0, p->d1, p->d2, vec));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -315,21 +315,31 @@ norm_bwd_columns_kernel(int rows, int H, const void* __restrict__ dy, const void
   }
 }
 
-// final reduce over the strips: thread <-> (vector v, column c)
+// final reduce over the strips. CTA = 32 consecutive entries of the flattened [3][H] result; its 8 warps split the
+// strips (coalesced 128-byte reads per warp and strip) and are combined in smem — ~70 CTAs of short loops instead of
+// 9 CTAs each walking every strip.
 __global__ void __launch_bounds__(256)
 norm_bwd_reduce_kernel(int strips, int H, const float* __restrict__ partials, void* __restrict__ dgamma,
                        void* __restrict__ dbeta, void* __restrict__ dbias, int out_dt, int accumulate) {
   pdl_trigger();
   pdl_wait();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nv = dbias ? 3 : 2;
-  if (idx >= nv * H) return;
-  const int v = idx / H, c = idx % H;
+  const int idx = blockIdx.x * 32 + lane;  // entry of the flattened [nv][H] result
   float a = 0.f;
-  for (int p = 0; p < strips; ++p) a += partials[(static_cast<size_t>(p) * 3 + v) * H + c];
-  void* dst = v == 0 ? dgamma : (v == 1 ? dbeta : dbias);
-  if (accumulate) a += ld_as_float(dst, out_dt, c);
-  st_from_float(dst, out_dt, c, a);
+  if (idx < nv * H)
+    for (int p = w; p < strips; p += 8) a += partials[static_cast<size_t>(p) * 3 * H + idx];
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && idx < nv * H) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += red[k][lane];
+    const int v = idx / H, c = idx % H;
+    void* dst = v == 0 ? dgamma : (v == 1 ? dbeta : dbias);
+    if (accumulate) a += ld_as_float(dst, out_dt, c);
+    st_from_float(dst, out_dt, c, a);
+  }
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -442,7 +452,7 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   }
   VY_LAUNCH_OK();
   const int nvec = p->dbias ? 3 : 2;
-  VY_CUDA_OK(launch_kernel(norm_bwd_reduce_kernel, dim3((nvec * p->H + 255) / 256), dim3(256), 0, st, strips, p->H, p->partials, p->dgamma, p->dbeta, p->dbias,
+  VY_CUDA_OK(launch_kernel(norm_bwd_reduce_kernel, dim3((nvec * p->H + 31) / 32), dim3(256), 0, st, strips, p->H, p->partials, p->dgamma, p->dbeta, p->dbias,
                                                                     p->dparam_dtype, p->dparam_accumulate));
   VY_LAUNCH_OK();
   count_launch(2);
