@@ -87,7 +87,8 @@ int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, con
       dtype == VY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 == 2   ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                  swizzle128 == 3   ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                   : swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
                                     : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

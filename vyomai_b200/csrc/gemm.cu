@@ -218,6 +218,12 @@ extern "C" int vy_gemm(const VyGemm* p) {
     return VY_ERR_INVALID_ARG;
   }
 
+  // TMA-store write-back for the fast (all-bf16, 16-byte aligned, no row remap) epilogues; VY_GEMM_TMA_STORE=0 keeps st.global
+  static const bool tma_store_on = !(getenv("VY_GEMM_TMA_STORE") && atoi(getenv("VY_GEMM_TMA_STORE")) == 0);
+  g.tma_store = 0;
+  if (tma_store_on && p->epi == VY_EPI_LINEAR && !p->transposed_out && g.vec_ok && p->out_dtype == VY_BF16 && !p->addend2 &&
+      p->out_row_group == 0 && (!p->aux || p->aux_dtype == VY_BF16) && (!p->addend || p->addend_dtype == VY_BF16))
+    g.tma_store = 1;
   const int bk = p->in_dtype == VY_BF16 ? 64 : 32;
   const int num_kb = (p->K + bk - 1) / bk;
   // split-K is offered for plain linear epilogues (what the weight gradients use) when the caller lent scratch space

@@ -50,6 +50,7 @@ struct GemmDev {
   int kv_out_dtype;
   int k_splits, kb_per_split;  // split-K: unit = (tile, split); raw fp32 partial tiles go to ws[split][M][N]
   float* ws;
+  int tma_store;  // fast epilogues write back with TMA stores (tma_out / tma_aux of the launch)
   int debug;  // development switches (VY_GEMM_DEBUG): 1 = epilogue drains TMEM only, 2 = producer skips TMA after the first ring fill
 };
 
@@ -259,10 +260,11 @@ __device__ __forceinline__ void store_ragged8(__nv_bfloat16* dst, const uint4& v
     if (k < n) dst[k] = e[k];
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool TMA>
 __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
                                                      int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
-                                                     uint64_t* tmem_empty_bar, uint8_t* stage, int trace_tile) {
+                                                     uint64_t* tmem_empty_bar, uint8_t* stage, int trace_tile,
+                                                     const CUtensorMap* tma_out, const CUtensorMap* tma_aux) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;
   constexpr int NCH = WC / 32;
   if (BN < 64 && half) {
@@ -299,6 +301,11 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
   long long wb_aux_delta[4];  // aux row address relative to the out row address (elements)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+    if (TMA) {  // the bulk tensor store needs no per-row pointers
+      wb_out[i] = nullptr;
+      wb_aux_delta[i] = 0;
+      continue;
+    }
     const int r = m0 + q * 32 + i * 8 + (lane >> 2);
     wb_out[i] = r < g.M ? reinterpret_cast<__nv_bfloat16*>(g.out) + remap_out_row(g, r) * g.ld_out + gc0 + (lane & 3) * 8 : nullptr;
     wb_aux_delta[i] = 0;
@@ -322,6 +329,15 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
     if (nvalid <= 0) return;
     const float* bs = bias_s + wcol0 + c * 32;
     uint8_t* srow = stg + lane * 64;
+    if (TMA) {
+      // the buffer about to be overwritten must have been read by its bulk store: the out buffers alternate per chunk,
+      // so only the store before the last has to be done — except with GELU + aux, where both buffers are used every chunk
+      if (lane == 0) {
+        if (save_aux) tma_store_wait_read<0>();
+        else tma_store_wait_read<1>();
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
       float x[8];
@@ -353,6 +369,17 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
       }
       *reinterpret_cast<uint4*>(srow + ((j4 ^ sw) << 4)) =
           make_uint4(pack2_bf16(x[0], x[1]), pack2_bf16(x[2], x[3]), pack2_bf16(x[4], x[5]), pack2_bf16(x[6], x[7]));
+    }
+    if (TMA) {
+      // [32 rows x 32 cols] bf16 box, SWIZZLE_64B == the staging swizzle; rows >= M / columns >= N are clipped by TMA
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tma_out, stg, gc0 + c * 32, m0 + q * 32);
+        if (save_aux) tma_store_2d(tma_aux, stage + GEMM_STAGE_OUT, gc0 + c * 32, m0 + q * 32);
+        tma_store_commit();
+      }
+      return;
     }
     __syncwarp();
     if (nvalid >= 32) {
@@ -394,31 +421,33 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
       process(c, raw, pf[0], (save_aux || !(c & 1)) ? stage : stage + GEMM_STAGE_OUT);
     }
   } else {
-    uint32_t raw_a[32], raw_b[32];
-    tmem_ld_x32(taddr, raw_a);
+    // the row operand rotates through two register sets (static indices => the chunk loop is unrolled by two); the
+    // accumulator chunk itself needs no double buffering: tcgen05.ld + wait measured ~75 cycles
+    uint32_t raw[32];
 #pragma unroll 1
-    for (int c = 0; c + 1 < NCH; c += 2) {  // chunk pairs (c -> buffer 0, c + 1 -> buffer 1)
+    for (int c = 0; c + 1 < NCH; c += 2) {
+      tmem_ld_x32(taddr + c * 32, raw);
       tmem_ld_wait();
-      tmem_ld_x32(taddr + (c + 1) * 32, raw_b);
-      process(c, raw_a, pf[0], stage);
+      process(c, raw, pf[0], stage);
+      tmem_ld_x32(taddr + (c + 1) * 32, raw);
       tmem_ld_wait();
-      if (c + 2 < NCH) {
-        tmem_ld_x32(taddr + (c + 2) * 32, raw_a);
-      } else {
+      if (c + 2 >= NCH) {
         release_acc(tmem_empty_bar, lane);
         VY_TRACE(trace_w, trace_tile, 2);
       }
-      process(c + 1, raw_b, pf[1], stage + GEMM_STAGE_OUT);
+      process(c + 1, raw, pf[1], stage + GEMM_STAGE_OUT);
     }
     if (NCH & 1) {  // odd chunk count: the last one is alone
+      tmem_ld_x32(taddr + (NCH - 1) * 32, raw);
       tmem_ld_wait();
       release_acc(tmem_empty_bar, lane);
       VY_TRACE(trace_w, trace_tile, 2);
-      process(NCH - 1, raw_a, pf[0], stage);
+      process(NCH - 1, raw, pf[0], stage);
     }
   }
   __syncwarp();  // the next tile's first chunk reuses stage buffer 0
 }
+
 
 // split-K epilogue: the raw fp32 accumulators of this (tile, split) unit go to the workspace slab of the split;
 // vy_gemm's reduce kernel sums the slabs and applies bias / addend / scale.
@@ -620,6 +649,7 @@ __device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tme
 template <typename TIn, int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
             const __grid_constant__ GemmDev g) {
   pdl_trigger();
   using Cfg = GemmCfg<TIn, BN>;
@@ -652,6 +682,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (g.tma_store) {
+      tma_prefetch_desc(&tma_out);
+      tma_prefetch_desc(&tma_aux);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -796,18 +830,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         epilogue_transposed<BN>(g, tmem_base + acc * BN, m0, n0, q, half, lane, et, &tfull_bar[acc], acc_ph, &tempty_bar[acc],
                                 reinterpret_cast<float*>(epi_stage));
       } else if (fast_mode == EPI_PLAIN) {
-        epilogue_linear_fast<BN, EPI_PLAIN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
+        if (g.tma_store)
+          epilogue_linear_fast<BN, EPI_PLAIN, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                    local, &tma_out, &tma_aux);
+        else
+          epilogue_linear_fast<BN, EPI_PLAIN, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                     local, &tma_out, &tma_aux);
       } else if (fast_mode == EPI_ADD) {
-        epilogue_linear_fast<BN, EPI_ADD>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
+        if (g.tma_store)
+          epilogue_linear_fast<BN, EPI_ADD, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                    local, &tma_out, &tma_aux);
+        else
+          epilogue_linear_fast<BN, EPI_ADD, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                     local, &tma_out, &tma_aux);
       } else if (fast_mode == EPI_GELU) {
-        epilogue_linear_fast<BN, EPI_GELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
+        if (g.tma_store)
+          epilogue_linear_fast<BN, EPI_GELU, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                    local, &tma_out, &tma_aux);
+        else
+          epilogue_linear_fast<BN, EPI_GELU, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                     local, &tma_out, &tma_aux);
       } else if (fast_mode == EPI_DGELU) {
-        epilogue_linear_fast<BN, EPI_DGELU>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage, local);
+        if (g.tma_store)
+          epilogue_linear_fast<BN, EPI_DGELU, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                    local, &tma_out, &tma_aux);
+        else
+          epilogue_linear_fast<BN, EPI_DGELU, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+                                                     local, &tma_out, &tma_aux);
       } else {
         epilogue_linear_general<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
       }
       VY_TRACE(2 + e, local, 3);
     }
+    if (g.tma_store && lane == 0) tma_store_wait<0>();  // the staged tiles must have left smem (and landed) before exit
   }
 
   tc_fence_before();
@@ -858,6 +913,15 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
     rc = get_tmap_2d(&tb, dt, p->B, p->N, p->K, p->ldb * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
 
+  // write-back tensor maps of the fast epilogues: [32 cols x 32 rows] bf16 boxes, SWIZZLE_64B (the staging layout)
+  CUtensorMap tout = ta, taux = ta;
+  GemmDev gl = g;
+  if (g.tma_store) {
+    rc = get_tmap_2d(&tout, VY_BF16, p->out, p->N, p->M, p->ld_out * 2, 32, 32, 3);
+    if (rc == VY_OK && p->aux && (p->act == VY_ACT_GELU_ERF))
+      rc = get_tmap_2d(&taux, VY_BF16, p->aux, p->N, p->M, p->ld_aux * 2, 32, 32, 3);
+    if (rc != VY_OK) gl.tma_store = 0;  // fall back to the staged st.global write-back
+  }
   auto kern = gemm_kernel<TIn, BN, A_MN, B_MN>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -868,7 +932,7 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   const int n_tiles = (p->N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles * (g.k_splits > 1 ? g.k_splits : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  VY_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream), ta, tb, g));
+  VY_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream), ta, tb, tout, taux, gl));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -54,7 +54,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 // TMA descriptor creation (tensormap.cu). dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1 (dim 0 is contiguous). swizzle128: 0 none, 1 = SWIZZLE_128B (16-B atoms),
-// 2 = SWIZZLE_128B_ATOM_32B (what MN-major tf32 UMMA operands need). Returns 0 or VY_ERR_*.
+// 2 = SWIZZLE_128B_ATOM_32B (what MN-major tf32 UMMA operands need), 3 = SWIZZLE_64B (the epilogue's 64-byte staged
+// rows). Returns 0 or VY_ERR_*.
 int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
 
