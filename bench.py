@@ -176,7 +176,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from vyomai_b200 import _lib, VisionLanguageModel, Vit
-    from vyomai_b200.trainer import Trainer, caption_labels
+    from vyomai_b200.trainer import HostPrefetcher, Trainer, caption_labels
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,9 +208,12 @@ def run_ours(args):
     def step_resident():
         return trainer.caption_step(px_d, ids_d, mask_d, labels_d)
 
+    # end to end: every step's batch comes from pinned host memory (copied on a side stream one step ahead, like a
+    # pin_memory DataLoader) and the step's loss is read back to the host before the next step starts
+    feeder = HostPrefetcher(host, dev)
+
     def step_e2e(i):
-        px, ids, mask = host[i % 2]
-        px, ids, mask = px.to(dev, non_blocking=True), ids.to(dev, non_blocking=True), mask.to(dev, non_blocking=True)
+        px, ids, mask = feeder.next()  # this step's inputs; issues the H2D copy of the next step's batch
         loss = trainer.caption_step(px, ids, mask, caption_labels(ids, mask))
         return float(loss)  # device -> host read of the step's result
 

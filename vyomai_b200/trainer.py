@@ -240,6 +240,37 @@ class Trainer:
         self._graph_key = key
 
 
+class HostPrefetcher:
+    """Feeds pinned host batches to the device one step ahead: the host->device copy of batch i+1 runs on a copy
+    stream while step i computes (what a DataLoader with pin_memory + non_blocking copies gives the reference's
+    notebooks). `next()` returns device tensors of the batch whose copy was issued by the previous call and
+    immediately issues the copy of the following batch; the compute stream waits on the copy's event, never the host."""
+
+    def __init__(self, batches, device: torch.device):
+        self.batches = batches  # indexable / cyclic source of tuples of pinned CPU tensors
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._i = 0
+        self._pending = self._issue()
+
+    def _issue(self):
+        host = self.batches[self._i % len(self.batches)]
+        self._i += 1
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(self.device, non_blocking=True) for t in host)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def next(self):
+        dev, ev = self._pending
+        torch.cuda.current_stream().wait_event(ev)
+        for t in dev:
+            t.record_stream(torch.cuda.current_stream())
+        self._pending = self._issue()
+        return dev
+
+
 def caption_labels(input_ids: torch.Tensor, attention_mask: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
     """labels aligned with the captioner's logits rows: the logits have one extra leading (image)
     position, so row t (1 <= t <= S-1) predicts text token t; pads, row 0 and row S are ignored — the
