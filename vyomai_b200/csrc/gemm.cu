@@ -236,7 +236,8 @@ extern "C" int vy_gemm(const VyGemm* p) {
     if (max_splits < 1) max_splits = 1;
   }
   const Tiling tl = choose_tiling(p->M, p->N, num_kb, p->a_mn_major || p->b_mn_major, p->epi == VY_EPI_QKV_ROPE, max_splits);
-  const int bn = tl.bn;
+  static const int force_bn = getenv("VY_GEMM_FORCE_BN") ? atoi(getenv("VY_GEMM_FORCE_BN")) : 0;  // development: pin the tile width
+  const int bn = force_bn ? force_bn : tl.bn;
   g.k_splits = tl.splits;
   g.kb_per_split = (num_kb + tl.splits - 1) / tl.splits;
   g.ws = static_cast<float*>(p->workspace);

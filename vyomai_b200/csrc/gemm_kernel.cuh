@@ -13,6 +13,7 @@
 // MN-major (transposed storage, used by dgrad / wgrad) — only the TMA box and the UMMA
 // descriptor change.
 #pragma once
+#include <stdlib.h>
 #include "vy_common.cuh"
 #include "vy_ptx.cuh"
 
@@ -50,6 +51,7 @@ struct GemmDev {
   int kv_out_dtype;
   int k_splits, kb_per_split;  // split-K: unit = (tile, split); raw fp32 partial tiles go to ws[split][M][N]
   float* ws;
+  int cluster2;   // launched as 2-CTA clusters: the pair computes two m-tiles of one n-tile and multicasts the shared B tile
   int tma_store;  // fast epilogues write back with TMA stores (tma_out / tma_aux of the launch)
   int debug;  // development switches (VY_GEMM_DEBUG): 1 = epilogue drains TMEM only, 2 = producer skips TMA after the first ring fill
 };
@@ -673,11 +675,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned base
 
+  // Work distribution. Plain launch: CTA b walks units b, b + grid, ... (unit = (tile, k-split); k_splits == 1 unless
+  // split-K). Cluster launch (g.cluster2): the two CTAs of a cluster walk the same units, a unit covers the m-tile PAIR
+  // (2p, 2p + 1) of one n-tile and CTA rank r computes m-tile 2p + r — both need the same B tile, so each loads half of
+  // it and multicasts it to the pair: L2 -> SM operand traffic per tile drops from (128 + BN) to (128 + BN / 2) rows,
+  // which is what bounds these GEMMs (~12 TB/s of L2 -> SM bandwidth, measured).
+  const bool cl2 = g.cluster2 != 0;
+  const int rank = cl2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = cl2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nworkers = cl2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int m_tiles = (g.M + BM - 1) / BM;
+  const int m_slots = cl2 ? (m_tiles + 1) / 2 : m_tiles;
+  const int m_mul = cl2 ? 2 : 1;
   const int n_tiles = (g.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = m_slots * n_tiles;
   const int num_kb = (g.K + BK - 1) / BK;
-  const int num_units = num_tiles * g.k_splits;  // unit = (tile, k-split); k_splits == 1 unless split-K
+  const int num_units = num_tiles * g.k_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -690,7 +703,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], cl2 ? 2 : 1);  // a multicast stage is free when BOTH CTAs' MMAs have consumed it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -703,18 +716,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (cl2) cluster_sync();  // the peer's barriers must be initialised before anything can arrive on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   pdl_wait();  // everything above is independent of the predecessor grid's output
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    {
       uint32_t it = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int unit = worker; unit < num_units; unit += nworkers) {
         const int tile = unit % num_tiles;
-        const int m0 = (tile / n_tiles) * BM;
+        const int m0 = ((tile / n_tiles) * m_mul + rank) * BM;  // may lie beyond M for the odd m-tile of the last pair: TMA zero-fills
         const int n0 = (tile % n_tiles) * BN;
         const int kb0 = (unit / num_tiles) * g.kb_per_split;
         const int kb1 = min(num_kb, kb0 + g.kb_per_split);
@@ -722,10 +736,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (elect_one_sync()) {
           if ((g.debug & 2) && it >= STAGES) {
             mbar_arrive(&full_bar[s]);
-            continue;
-          }
+          } else {
           mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           uint8_t* a_dst = sA + s * Cfg::A_BYTES;
           uint8_t* b_dst = sB + s * Cfg::B_BYTES;
@@ -736,23 +750,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int i = 0; i < BM / Cfg::EPB; ++i)
               tma_load_2d(a_dst + i * Cfg::MN_BOX_BYTES, &tma_a, &full_bar[s], m0 + i * Cfg::EPB, kb * BK);
           }
-          if constexpr (!B_MN) {
-            tma_load_2d(b_dst, &tma_b, &full_bar[s], kb * BK, n0);
-          } else {
+          if (!cl2) {
+            if constexpr (!B_MN) {
+              tma_load_2d(b_dst, &tma_b, &full_bar[s], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / Cfg::EPB; ++i)
-              tma_load_2d(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, &full_bar[s], n0 + i * Cfg::EPB, kb * BK);
+              for (int i = 0; i < BN / Cfg::EPB; ++i)
+                tma_load_2d(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, &full_bar[s], n0 + i * Cfg::EPB, kb * BK);
+            }
+          } else {
+            // this CTA's share of the B tile, multicast into both CTAs (same smem offset, each CTA's own full barrier)
+            if constexpr (!B_MN) {  // tma_b was built with a box of BN / 2 rows
+              tma_load_2d_mc(b_dst + rank * (BN / 2) * 128, &tma_b, &full_bar[s], kb * BK, n0 + rank * (BN / 2), 3);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / Cfg::EPB; ++i)
+                if ((i & 1) == rank)
+                  tma_load_2d_mc(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, &full_bar[s], n0 + i * Cfg::EPB, kb * BK, 3);
+            }
           }
+          }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc(Cfg::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0;
       uint32_t local = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local) {
+      for (int unit = worker; unit < num_units; unit += nworkers, ++local) {
         const int kb0 = (unit / num_tiles) * g.kb_per_split;
         const int kb1 = min(num_kb, kb0 + g.kb_per_split);
         const uint32_t acc = local & 1;
@@ -769,6 +798,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
             const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
@@ -778,9 +808,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if constexpr (sizeof(TIn) == 2) umma_f16(d_tmem, ad, bd, idesc, kb != kb0 || k != 0);
             else umma_tf32(d_tmem, ad, bd, idesc, kb != kb0 || k != 0);
           }
-          umma_commit(&empty_bar[s]);
+          if (cl2) umma_commit_mc(&empty_bar[s], 3);
+          else umma_commit(&empty_bar[s]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
         }
-        umma_commit(&tfull_bar[acc]);
         VY_TRACE(1, local, 2);
       }
     }
@@ -801,11 +834,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       else if (g.act == VY_ACT_DGELU_ERF && !g.addend && aux16 && n8) fast_mode = EPI_DGELU;
     }
     uint32_t local = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local) {
+    for (int unit = worker; unit < num_units; unit += nworkers, ++local) {
       const int tile = unit % num_tiles;
       const uint32_t acc = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
-      const int m0 = (tile / n_tiles) * BM;
+      const int m0 = ((tile / n_tiles) * m_mul + rank) * BM;
       const int n0 = (tile % n_tiles) * BN;
       float* bs = bias_s + acc * BN;
       VY_TRACE(2 + e, local, 0);
@@ -866,7 +899,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (cl2) cluster_sync();  // the peer may still multicast-arrive on this CTA's barriers until it is done too
+  else __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -907,8 +941,12 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   else
     rc = get_tmap_2d(&ta, dt, p->A, p->M, p->K, p->lda * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
+  // 2-CTA clusters (see gemm_kernel): worth it when there are m-tile pairs to share a B tile; VY_GEMM_CLUSTER=0 disables
+  static const bool cluster_on = !(getenv("VY_GEMM_CLUSTER") && atoi(getenv("VY_GEMM_CLUSTER")) == 0);
+  const int m_tiles_h = (p->M + Cfg::BM - 1) / Cfg::BM;
+  const bool cl2 = cluster_on && BN >= 128 && m_tiles_h >= 2 && (m_tiles_h % 2 == 0 || m_tiles_h >= 9);
   if (!B_MN)
-    rc = get_tmap_2d(&tb, dt, p->B, p->K, p->N, p->ldb * es, Cfg::BK, BN);
+    rc = get_tmap_2d(&tb, dt, p->B, p->K, p->N, p->ldb * es, Cfg::BK, cl2 ? BN / 2 : BN);
   else
     rc = get_tmap_2d(&tb, dt, p->B, p->N, p->K, p->ldb * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
@@ -930,9 +968,14 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   }
   const int m_tiles = (p->M + Cfg::BM - 1) / Cfg::BM;
   const int n_tiles = (p->N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles * (g.k_splits > 1 ? g.k_splits : 1);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  VY_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream), ta, tb, tout, taux, gl));
+  const int m_slots = cl2 ? (m_tiles + 1) / 2 : m_tiles;
+  const int units = m_slots * n_tiles * (g.k_splits > 1 ? g.k_splits : 1);
+  const int max_workers = cl2 ? num_sms() / 2 : num_sms();
+  const int workers = units < max_workers ? units : max_workers;
+  const int grid = cl2 ? 2 * workers : workers;
+  gl.cluster2 = cl2 ? 1 : 0;
+  VY_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream),
+                                   cl2 ? 2 : 1, ta, tb, tout, taux, gl));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

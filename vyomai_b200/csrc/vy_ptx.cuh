@@ -80,6 +80,15 @@ VY_DEVINL void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset in every CTA of `cta_mask` and completes bytes on the
+// mbarrier at the same offset in each of them
+VY_DEVINL void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 VY_DEVINL void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -202,6 +211,29 @@ VY_DEVINL void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// same, arriving on the barrier at this offset in every CTA of `cta_mask` (a smem stage filled by multicast TMA is
+// free only when all the CTAs that received it have consumed it)
+VY_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters
+// ----------------------------------------------------------------------------------------------
+VY_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+VY_DEVINL void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM -> registers. 32x32b shape: lane i of the warp reads TMEM lane (base_lane + i),
 // N consecutive 32-bit columns. A warp may only touch lanes [32*(warp_id%4), +32).
@@ -234,6 +266,23 @@ VY_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::
 // ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
+// One lane of a converged warp. The single-thread roles (TMA producer, tcgen05.mma issuer) run their loops with the
+// WHOLE warp and elect a lane only around the issuing instructions: control flow and descriptor arithmetic then stay
+// warp-uniform, so the compiler keeps them in uniform registers. Inside an `if (lane == 0)` region it cannot, and wraps
+// every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall (~25 instructions and ~200 cycles per MMA,
+// measured — enough to make the issue loop, not the tensor pipe, the bottleneck of long-K GEMMs).
+VY_DEVINL bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " elect.sync _|p, 0xffffffff;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 VY_DEVINL void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
