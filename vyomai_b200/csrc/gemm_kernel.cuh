@@ -941,8 +941,10 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   else
     rc = get_tmap_2d(&ta, dt, p->A, p->M, p->K, p->lda * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
-  // 2-CTA clusters (see gemm_kernel): worth it when there are m-tile pairs to share a B tile; VY_GEMM_CLUSTER=0 disables
-  static const bool cluster_on = !(getenv("VY_GEMM_CLUSTER") && atoi(getenv("VY_GEMM_CLUSTER")) == 0);
+  // 2-CTA clusters with a multicast B tile (see gemm_kernel). Opt-in (VY_GEMM_CLUSTER=1): measured on the captured
+  // training step it changes nothing (12.00 vs 12.01 ms) — at cluster size 2 the L2 already de-duplicates the two CTAs'
+  // unicast requests, and the mainloop is tensor-pipe bound (136 cycles per M128 N192 K16 MMA), not operand-bound.
+  static const bool cluster_on = getenv("VY_GEMM_CLUSTER") && atoi(getenv("VY_GEMM_CLUSTER")) != 0;
   const int m_tiles_h = (p->M + Cfg::BM - 1) / Cfg::BM;
   const bool cl2 = cluster_on && BN >= 128 && m_tiles_h >= 2 && (m_tiles_h % 2 == 0 || m_tiles_h >= 9);
   if (!B_MN)
