@@ -165,3 +165,21 @@ def test_gradient_exchange_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_vyomai_import_name_is_a_drop_in_for_the_hot_path():
+    """`from VyomAI import ...` (what the reference's tests and notebooks write) resolves to this package for the
+    in-scope names, keeps the sub-module import paths, and refuses the out-of-scope names loudly."""
+    import VyomAI
+    import vyomai_b200
+    from VyomAI import DecoderModel, EncoderConfig, EncoderModel, StaticCacheOne, VisionLanguageModel, Vit  # noqa: F401
+    from VyomAI.layers.kv_cache import DynamicCacheOne  # noqa: F401
+    from VyomAI.models.decoder import DecoderModel as D2
+    from VyomAI.utils import EncoderConfig as C2
+    assert D2 is vyomai_b200.DecoderModel and C2 is vyomai_b200.EncoderConfig
+    cfg = EncoderConfig()
+    assert (cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size) == (768, 12, 50265)  # reference defaults (utils.py:90-100)
+    with pytest.raises(ImportError):
+        from VyomAI import LoraLinear  # noqa: F401
+    with pytest.raises(ImportError):
+        VyomAI.speculative_generate
