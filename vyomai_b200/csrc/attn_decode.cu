@@ -17,7 +17,8 @@
 
 namespace vy {
 
-constexpr int DEC_WARPS = 4;
+constexpr int DEC_WARPS = 4;       // warps per CTA when the context is split over several CTAs
+constexpr int DEC_WARPS_WIDE = 8;  // ... when one CTA owns a whole (batch row, kv head): no split, no workspace, no ticket
 constexpr int DEC_UNROLL = 4;
 constexpr int DEC_MAX_REP = 8;
 constexpr int HD = 64;
@@ -63,8 +64,8 @@ __device__ __forceinline__ void load_row8<float>(const float* p, float (&v)[8]) 
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-template <typename TC, int NREP>
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+template <typename TC, int NREP, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
 attn_decode_kernel(const DecodeDev g) {
   pdl_trigger();
   pdl_wait();
@@ -77,7 +78,7 @@ attn_decode_kernel(const DecodeDev g) {
   __shared__ float s_newk[HD];
   __shared__ float s_newv[HD];
   __shared__ float s_q[DEC_MAX_REP][HD];
-  __shared__ float s_red[DEC_WARPS][DEC_MAX_REP][HD + 2];
+  __shared__ float s_red[NWARPS][DEC_MAX_REP][HD + 2];
 
   // ---- new token: bias-added projections -> RoPE(q, k) -> smem; append k, v to the cache ----
   {
@@ -131,14 +132,14 @@ attn_decode_kernel(const DecodeDev g) {
   const int per = (sp + g.splits - 1) / g.splits;
   const int k_begin = split * per;
   const int k_end = min(sp, k_begin + per);
-  constexpr int KEYS_PER_ITER = DEC_WARPS * 4 * DEC_UNROLL;
+  constexpr int KEYS_PER_ITER = NWARPS * 4 * DEC_UNROLL;
 
   for (int k0 = k_begin; k0 < k_end; k0 += KEYS_PER_ITER) {
     float kv[DEC_UNROLL][8], vv[DEC_UNROLL][8];
     int kidx[DEC_UNROLL];
 #pragma unroll
     for (int u = 0; u < DEC_UNROLL; ++u) {
-      kidx[u] = k0 + (u * DEC_WARPS + warp) * 4 + lk;
+      kidx[u] = k0 + (u * NWARPS + warp) * 4 + lk;
       if (kidx[u] < k_end) {
         load_row8<TC>(kc + kidx[u] * g.c_sl + ld * 8, kv[u]);
         load_row8<TC>(vc + kidx[u] * g.c_sl + ld * 8, vv[u]);
@@ -222,10 +223,10 @@ attn_decode_kernel(const DecodeDev g) {
   const int t = threadIdx.x;
   float M = -INFINITY, L = 0.f, O = 0.f;
   const int r_own = t / HD, j_own = t % HD;
-  for (int rr = r_own; rr < NREP; rr += (DEC_WARPS * 32) / HD) {
+  for (int rr = r_own; rr < NREP; rr += (NWARPS * 32) / HD) {
     M = -INFINITY; L = 0.f; O = 0.f;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) {
+    for (int w = 0; w < NWARPS; ++w) {
       const float mw = s_red[w][rr][HD], lw = s_red[w][rr][HD + 1], ow = s_red[w][rr][j_own];
       if (mw == -INFINITY) continue;
       const float mn = fmaxf(M, mw);
@@ -260,10 +261,10 @@ attn_decode_kernel(const DecodeDev g) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int rr = r_own; rr < NREP; rr += (DEC_WARPS * 32) / HD) {
+  for (int rr = r_own; rr < NREP; rr += (NWARPS * 32) / HD) {
     M = -INFINITY; L = 0.f; O = 0.f;
-    for (int sp = 0; sp < g.splits; ++sp) {
-      const float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + sp) * NREP + rr) * (HD + 2));
+    for (int si = 0; si < g.splits; ++si) {
+      const float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + si) * NREP + rr) * (HD + 2));
       const float mw = __ldcg(w + HD), lw = __ldcg(w + HD + 1), ow = __ldcg(w + j_own);
       if (mw == -INFINITY) continue;
       const float mn = fmaxf(M, mw);
@@ -277,17 +278,17 @@ attn_decode_kernel(const DecodeDev g) {
   }
 }
 
-template <typename TC>
-static int launch_decode(const DecodeDev& g, cudaStream_t st) {
+template <typename TC, int NWARPS>
+static int launch_decode_w(const DecodeDev& g, cudaStream_t st) {
   dim3 grid(g.splits, g.Hkv, g.B);
-  dim3 block(DEC_WARPS * 32);
+  dim3 block(NWARPS * 32);
   switch (g.n_rep) {
-    case 1: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 1>, dim3(grid), dim3(block), 0, st, g)); break;
-    case 2: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 2>, dim3(grid), dim3(block), 0, st, g)); break;
-    case 3: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 3>, dim3(grid), dim3(block), 0, st, g)); break;
-    case 4: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 4>, dim3(grid), dim3(block), 0, st, g)); break;
-    case 6: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 6>, dim3(grid), dim3(block), 0, st, g)); break;
-    case 8: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 8>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 1: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 1, NWARPS>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 2: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 2, NWARPS>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 3: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 3, NWARPS>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 4: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 4, NWARPS>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 6: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 6, NWARPS>, dim3(grid), dim3(block), 0, st, g)); break;
+    case 8: VY_CUDA_OK(launch_kernel(attn_decode_kernel<TC, 8, NWARPS>, dim3(grid), dim3(block), 0, st, g)); break;
     default:
       set_error("vy_attn_decode: unsupported q-heads per kv-head %d (1,2,3,4,6,8)", g.n_rep);
       return VY_ERR_UNSUPPORTED;
@@ -296,12 +297,21 @@ static int launch_decode(const DecodeDev& g, cudaStream_t st) {
   count_launch();
   return VY_OK;
 }
+template <typename TC>
+static int launch_decode(const DecodeDev& g, cudaStream_t st) {
+  // one CTA per (batch row, kv head) gets 8 warps (its context is not split); split contexts use 4-warp CTAs
+  if (g.splits == 1) return launch_decode_w<TC, DEC_WARPS_WIDE>(g, st);
+  return launch_decode_w<TC, DEC_WARPS>(g, st);
+}
 
 }  // namespace vy
 
 extern "C" int vy_attn_decode_splits(int B, int Hkv, int start_pos) {
   // enough CTAs to cover the GPU ~4x, but keep >= 64 cached slots per split
   const int sms = vy::num_sms();
+  // enough (batch row, kv head) pairs to occupy most SMs on their own: no split — one 8-warp CTA per pair streams the
+  // whole context (no workspace round trip, no ticket, a single wave)
+  if (3 * B * Hkv >= 2 * sms) return 1;
   int splits = (4 * sms + B * Hkv - 1) / (B * Hkv);
   const int max_by_len = (start_pos + 63) / 64;
   if (splits > max_by_len) splits = max_by_len;
