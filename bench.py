@@ -193,7 +193,8 @@ def run_ours(args):
     with redirect_stdout(io.StringIO()):
         model = VisionLanguageModel(TextCfg(), encoder=Vit(VitCfg()), pos_embedding_type="rope", attention_type="gqa")
     model = model.to(dev).to(torch.bfloat16).train()
-    trainer = Trainer(model, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, use_graph=not args.no_graph)
+    trainer = Trainer(model, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, use_graph=not args.no_graph,
+                      grad_overwrite=not args.no_grad_overwrite)
 
     B = PER_GPU_BATCH
     host = [synth_batch(B, 17 + 1000 * rank + i, True) for i in range(2)]
@@ -296,7 +297,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "seq_len": TEXT_LEN + 1,
                        "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2",
                        "dropout": 0.0, "optimizer": "AdamW fp32 master + clip 1.0",
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": not args.no_graph, "grad_overwrite": bool(trainer.grad_overwrite)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof, "cpu_baseline": cpu,
             "kernel_breakdown_ms": breakdown, "final_loss": float(loss), "e2e_last_loss": last,
@@ -319,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-grad-overwrite", action="store_true", help="zero + accumulate every gradient instead of overwrite mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

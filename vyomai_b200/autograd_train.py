@@ -46,6 +46,12 @@ def _direct(p: Optional[torch.Tensor]) -> bool:
     return p is not None and getattr(p, "_vy_direct_grad", False) and p.grad is not None
 
 
+def _overwrite(p: Optional[torch.Tensor]) -> bool:
+    """The trainer guarantees this parameter's gradient is produced exactly once per step by one of the kernels below,
+    so it may be WRITTEN instead of accumulated (no zero fill of the buffer, no read-modify-write in the epilogue)."""
+    return p is not None and getattr(p, "_vy_grad_overwrite", False)
+
+
 def _ready(p) -> None:
     cb = getattr(p, "_vy_grad_ready", None)
     if cb is not None:
@@ -55,7 +61,7 @@ def _ready(p) -> None:
 def _emit_wgrad(p: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor) -> Optional[torch.Tensor]:
     if _direct(p):
         g2 = p.grad.view(p.grad.shape[0], -1)
-        ops.gemm(dy2d.t(), x2d.t(), out=g2, addend=g2, allow_split_k=True)
+        ops.gemm(dy2d.t(), x2d.t(), out=g2, addend=None if _overwrite(p) else g2, allow_split_k=True)
         _ready(p)
         return None
     return _wgrad(dy2d, x2d, p).view(p.shape)
@@ -65,7 +71,7 @@ def _emit_bgrad(p: Optional[torch.Tensor], dy2d: torch.Tensor) -> Optional[torch
     if p is None:
         return None
     if _direct(p):
-        ops.colsum(dy2d, out=p.grad, accumulate=True)
+        ops.colsum(dy2d, out=p.grad, accumulate=not _overwrite(p))
         _ready(p)
         return None
     return ops.colsum(dy2d, out_dtype=p.dtype)
@@ -78,8 +84,11 @@ def _ln_bwd(dy: torch.Tensor, s: torch.Tensor, gamma: torch.Tensor, beta: torch.
     the parameter gradients are accumulated in place by the reduce kernel and None is returned for them."""
     direct = _direct(gamma) and _direct(beta) and gamma.grad.dtype == beta.grad.dtype
     if direct and (bias is None or (_direct(bias) and bias.grad.dtype == gamma.grad.dtype)):
+        over = _overwrite(gamma) and _overwrite(beta) and (bias is None or _overwrite(bias))
+        if not over and (_overwrite(gamma) or _overwrite(beta) or _overwrite(bias)):
+            raise RuntimeError("a LayerNorm's weight / bias and the preceding Linear's bias must share the gradient write mode")
         ds = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out=gamma.grad, dbeta_out=beta.grad,
-                                   dbias_out=bias.grad if bias is not None else None)[0]
+                                   dbias_out=bias.grad if bias is not None else None, accumulate=not over)[0]
         _ready(gamma)
         _ready(beta)
         if bias is not None:
@@ -150,8 +159,8 @@ class AttentionBlockFn(torch.autograd.Function):
         dx = _dgrad(dqkv, w_qkv, addend=ds)  # + the residual branch of LN(dense(.) + x)
         grads = [dx]
         gw = _packed_grads([l.weight for l in lin])
-        if gw is not None:  # one wgrad GEMM accumulating into the adjacent q|k|v gradient buffers
-            ops.gemm(dqkv.t(), x2d.t(), out=gw, addend=gw, allow_split_k=True)
+        if gw is not None:  # one wgrad GEMM into the adjacent q|k|v gradient buffers
+            ops.gemm(dqkv.t(), x2d.t(), out=gw, addend=None if all(_overwrite(l.weight) for l in lin) else gw, allow_split_k=True)
             for l in lin:
                 _ready(l.weight)
                 grads.append(None)
@@ -165,7 +174,7 @@ class AttentionBlockFn(torch.autograd.Function):
         if ctx.has_qkv_bias:
             gb = _packed_grads([l.bias for l in lin])
             if gb is not None:
-                ops.colsum(dqkv, out=gb, accumulate=True)
+                ops.colsum(dqkv, out=gb, accumulate=not all(_overwrite(l.bias) for l in lin))
                 for l in lin:
                     _ready(l.bias)
                     grads.append(None)

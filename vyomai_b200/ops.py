@@ -244,10 +244,10 @@ def add_layernorm(
 
 def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tensor] = None,
                       dbeta_out: Optional[torch.Tensor] = None, dbias_out: Optional[torch.Tensor] = None,
-                      want_dbias: bool = False):
+                      want_dbias: bool = False, accumulate: bool = True):
     """Returns (dx, dgamma, dbeta[, dbias]) for y = LayerNorm(s). Without dgamma_out/dbeta_out the parameter
     gradients come back as fresh fp32 tensors; with them (same dtype, e.g. the parameters' .grad views) the kernel
-    ACCUMULATES into those buffers and returns them. dbias (want_dbias / dbias_out) = column sums of dx: the bias
+    ACCUMULATES into those buffers (or, with accumulate=False, overwrites them) and returns them. dbias (want_dbias / dbias_out) = column sums of dx: the bias
     gradient of the Linear that produced the normalised sum."""
     _need_cuda(dy, s, gamma, mean, rstd, dgamma_out, dbeta_out, dbias_out)
     H = dy.shape[-1]
@@ -278,7 +278,7 @@ def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tenso
         rows=rows, H=H, io_dtype=_dt(dy2), gamma=gamma.data_ptr(), param_dtype=_dt(gamma),
         mean=mean.data_ptr(), rstd=rstd.data_ptr(), dy=dy2.data_ptr(), s=s2.data_ptr(), dx=dx.data_ptr(),
         dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), dbias=_ptr(dbias), dparam_dtype=_dt(dgamma),
-        dparam_accumulate=int(acc), partials=partials.data_ptr(), stream=_stream(),
+        dparam_accumulate=int(acc and accumulate), partials=partials.data_ptr(), stream=_stream(),
     )
     if want_dbias or dbias_out is not None:
         return dx.view(dy.shape), dgamma, dbeta, dbias

@@ -67,6 +67,7 @@ class FlatParams:
             self.offsets.append(off)
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
+        self.zero_ranges = None  # None: zero_grad clears everything; else the [start, end) slices it must clear
         self.flat = torch.zeros(off, device=dev, dtype=self.dtype)
         self.grad = torch.zeros(off, device=dev, dtype=self.dtype)
         for p, o in zip(params, self.offsets):
@@ -76,7 +77,11 @@ class FlatParams:
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
 
     def zero_grad(self) -> None:
-        self.grad.zero_()
+        if self.zero_ranges is None:
+            self.grad.zero_()
+        else:  # overwrite-mode parameters need no clearing: zero only the slices that are accumulated into
+            for a, b in self.zero_ranges:
+                self.grad[a:b].zero_()
         es = self.grad.element_size()
         base = self.grad.data_ptr()
         for p, o in zip(self.params, self.offsets):  # re-attach in case autograd replaced a .grad
@@ -133,7 +138,8 @@ class Trainer:
     """AdamW + clip + data-parallel all-reduce around a model built from vyomai_b200 modules."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
-                 max_grad_norm: float = 1.0, bucket_mb: float = 64.0, overlap: bool = True, use_graph: bool = False):
+                 max_grad_norm: float = 1.0, bucket_mb: float = 64.0, overlap: bool = True, use_graph: bool = False,
+                 grad_overwrite: bool = True):
         self.model = model
         self.use_graph = use_graph
         self._graph = None
@@ -167,6 +173,56 @@ class Trainer:
                 self._bucket_size[b] += 1
                 p._vy_grad_ready = self._on_grad
                 p.register_post_accumulate_grad_hook(self._on_grad)
+        self.grad_overwrite = False
+        if grad_overwrite:
+            self._enable_grad_overwrite()
+
+    def _enable_grad_overwrite(self) -> None:
+        """Linear / LayerNorm parameters of the fused blocks get their gradient from exactly one kernel per step
+        (wgrad GEMM, column sum, LayerNorm reduce): those kernels may write instead of accumulate, which removes the
+        zero fill of ~3/4 of the gradient buffer and the read-modify-write in the wgrad epilogues. Everything else
+        (embeddings: scatter-add; ViT stem: autograd accumulation) keeps zero + accumulate. `_verify_grad_overwrite`
+        checks the "exactly once" premise on the first step by poisoning the buffer."""
+        from .layers.ffn import FeedForward
+        from .models._common import LMHead
+        marked = set()
+
+        def mark(*ps):
+            for q in ps:
+                if q is not None:
+                    q._vy_grad_overwrite = True
+                    marked.add(id(q))
+
+        for mod in self.model.modules():
+            if isinstance(mod, _SelfAttentionBase):
+                for l in mod._packed():
+                    mark(l.weight, l.bias)
+                mark(mod.out.dense.weight, mod.out.dense.bias, mod.out.layernorm.weight, mod.out.layernorm.bias)
+            elif isinstance(mod, FeedForward):
+                mark(mod.intermediate.weight, mod.intermediate.bias, mod.out.weight, mod.out.bias, mod.layernorm.weight,
+                     mod.layernorm.bias)
+            elif isinstance(mod, LMHead):
+                mark(mod.dense.weight, mod.dense.bias, mod.layer_norm.weight, mod.layer_norm.bias, mod.decoder.weight, mod.bias)
+        ranges = []
+        for p, o in zip(self.fp.params, self.fp.offsets):
+            end = o + (p.numel() + FlatParams.ALIGN - 1) // FlatParams.ALIGN * FlatParams.ALIGN
+            start = o + p.numel() if id(p) in marked else o  # a written parameter still has its alignment padding cleared
+            if start == end:
+                continue
+            if ranges and ranges[-1][1] == start:
+                ranges[-1][1] = end
+            else:
+                ranges.append([start, end])
+        self.fp.zero_ranges = [tuple(r) for r in ranges]
+        self.grad_overwrite = True
+        self._overwrite_verified = False
+
+    def _disable_grad_overwrite(self) -> None:
+        for p in self.fp.params:
+            if getattr(p, "_vy_grad_overwrite", False):
+                p._vy_grad_overwrite = False
+        self.fp.zero_ranges = None
+        self.grad_overwrite = False
 
     def _on_grad(self, p: nn.Parameter) -> None:
         b = self._bucket_of[id(p)]
@@ -190,15 +246,32 @@ class Trainer:
                   master=self.master, grad_sqnorm=self.sqnorm, max_grad_norm=self.max_grad_norm, grad_div=float(self.world))
 
     def _caption_body(self, pixel_values, input_ids, attention_mask, labels_full) -> torch.Tensor:
+        if self.grad_overwrite and not self._overwrite_verified:
+            # first step: poison the buffer; any overwrite-mode slice that no kernel wrote would stay NaN
+            self._overwrite_verified = True
+            if not torch.cuda.is_current_stream_capturing():
+                self.fp.grad.fill_(float("nan"))
+                self.zero_grad()
+                loss = self._forward_backward(pixel_values, input_ids, attention_mask, labels_full)
+                if not bool(torch.isfinite(self.fp.grad).all()):
+                    self._disable_grad_overwrite()  # some parameter is not written exactly once per step: accumulate instead
+                    self.zero_grad()
+                    loss = self._forward_backward(pixel_values, input_ids, attention_mask, labels_full)
+                self.optimizer_step()
+                return loss.detach()
         self.zero_grad()
+        loss = self._forward_backward(pixel_values, input_ids, attention_mask, labels_full)
+        self.optimizer_step()
+        return loss.detach()
+
+    def _forward_backward(self, pixel_values, input_ids, attention_mask, labels_full) -> torch.Tensor:
         if hasattr(self.model, "forward_loss"):  # LM head + cross-entropy as one autograd node
             loss = self.model.forward_loss(pixel_values, input_ids, attention_mask, labels_full, ignore_index=-100)
         else:
             logits = self.model(pixel_values=pixel_values, decoder_input_ids=input_ids, decoder_attention_mask=attention_mask).logits
             loss = cross_entropy(logits, labels_full, ignore_index=-100)
         loss.backward()
-        self.optimizer_step()
-        return loss.detach()
+        return loss
 
     def caption_step(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor,
                      labels_full: torch.Tensor) -> torch.Tensor:
