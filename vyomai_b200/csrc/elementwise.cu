@@ -249,12 +249,12 @@ colsum_partial_kernel(int R, int Cn, const void* __restrict__ x, long long ld, i
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (vec_ok && c0 + 8 <= Cn) {
     int r = r0 + w;
-    for (; r + 56 < r1; r += 64) {  // 8 rows (16-byte loads) in flight per lane
-      float v[8][8];
+    for (; r + 24 < r1; r += 32) {  // 4 rows in flight per lane (8 measured slower: 22 vs 16 us per call in the step)
+      float v[4][8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) ld8_as_float(x, dt, static_cast<long long>(r + u * 8) * ld + c0, v[u]);
+      for (int u = 0; u < 4; ++u) ld8_as_float(x, dt, static_cast<long long>(r + u * 8) * ld + c0, v[u]);
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
     }
