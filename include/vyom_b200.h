@@ -160,6 +160,13 @@ typedef struct VyGemm {
 } VyGemm;
 
 VY_API int vy_gemm(const VyGemm* p);
+/* Self-check of the GEMM kernels' barrier protocol: a wait inside a kernel that times out raises a device flag instead
+ * of faulting, and the launch finishes with undefined results. Returns the flag (0 = every vy_gemm so far ran its
+ * protocol to completion, 1 = some launch did not, -1 = the flag could not be read). Synchronises the device. */
+VY_API int vy_gemm_poisoned(void);
+/* Development hook (tools/gemm_sweep.py): pin the kernel flavour (pair: -1 auto, 0 single CTA, 1 CTA pair), the tile
+ * width (bn: 0 auto) and the K split (splits: 0 auto) of subsequent vy_gemm calls of this process. */
+VY_API int vy_gemm_tune_override(int pair, int bn, int splits);
 
 /* ------------------------------------------------------------------------------------------
  * vy_add_layernorm_fwd / _bwd — y = LayerNorm(x + residual) * gamma + beta, warp per row.

@@ -33,7 +33,7 @@ def timeit(fn, iters, nbuf):
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
 
-def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=BF):
+def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=BF, cublas_too=True, quiet=False):
     """A logical (M,K), B logical (N,K). a_mn/b_mn: stored transposed."""
     bytes_per = (M * K + N * K + M * N) * 2
     nbuf = max(1, min(8, int(160e6 // bytes_per) + 1))
@@ -94,6 +94,8 @@ def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=
         torch.matmul(a, b.t())
 
     t = timeit(fn, iters, nbuf)
+    if not cublas_too:
+        return dict(name=name, us=t)
     tc = timeit(cublas, iters, nbuf)
     fl = 2.0 * M * N * K
     r = dict(name=name, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, epi=epi, us=round(t, 1), tflops=round(fl / t / 1e6, 1),
@@ -104,14 +106,10 @@ def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=
     return r
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--json", default=None)
-    ap.add_argument("--only", default=None)
-    args = ap.parse_args()
+def bench_cases():
+    """(role, M, N, K, A stored transposed, B stored transposed, epilogue) of every GEMM shape of one captioner step."""
     T, Tv = 64 * 128, 64 * 197  # decoder / ViT token rows of the bench batch
-    cases = [
+    return [
         # forward
         ("dec.qkv_rope", T, 1280, 768, False, False, "qkv"),
         ("vit.qkv", Tv, 2304, 768, False, False, "bias"),
@@ -140,6 +138,15 @@ def main():
         ("vit.w ffn2", 768, 3072, Tv, True, True, "accum"),
         ("lm_head wgrad", 50272, 768, T, True, True, "accum"),
     ]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    cases = bench_cases()
     res = []
     for c in cases:
         if args.only and args.only not in c[0]:

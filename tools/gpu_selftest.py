@@ -400,6 +400,11 @@ def main():
         t0 = time.time()
         ok = GROUPS[args.group]()
         torch.cuda.synchronize()
+        from vyomai_b200 import _lib
+        poisoned = _lib.lib().vy_gemm_poisoned()
+        if poisoned != 0:
+            print(f"  [FAIL] vy_gemm_poisoned() = {poisoned}", flush=True)
+            ok = False
         print(f"GROUP {args.group}: {'PASS' if ok else 'FAIL'} ({time.time() - t0:.1f}s)", flush=True)
         sys.exit(0 if ok else 1)
     names = args.only.split(",") if args.only else list(GROUPS)

@@ -6,28 +6,46 @@
 
 namespace vy {
 
-#define VY_GEMM_EXTERN(T, BN, A, B) extern template int launch_gemm<T, BN, A, B>(const VyGemm*, const GemmDev&);
+#define VY_GEMM_EXTERN(T, BN, A, B, P) extern template int launch_gemm<T, BN, A, B, P>(const VyGemm*, const GemmDev&);
 #define VY_GEMM_EXTERN_ALL(T)                                                                                   \
-  VY_GEMM_EXTERN(T, 32, false, false) VY_GEMM_EXTERN(T, 64, false, false) VY_GEMM_EXTERN(T, 128, false, false) \
-  VY_GEMM_EXTERN(T, 192, false, false) VY_GEMM_EXTERN(T, 256, false, false)                                    \
-  VY_GEMM_EXTERN(T, 128, false, true) VY_GEMM_EXTERN(T, 192, false, true) VY_GEMM_EXTERN(T, 256, false, true)  \
-  VY_GEMM_EXTERN(T, 128, true, false) VY_GEMM_EXTERN(T, 192, true, false) VY_GEMM_EXTERN(T, 256, true, false)  \
-  VY_GEMM_EXTERN(T, 128, true, true) VY_GEMM_EXTERN(T, 192, true, true) VY_GEMM_EXTERN(T, 256, true, true)
+  VY_GEMM_EXTERN(T, 32, false, false, false) VY_GEMM_EXTERN(T, 64, false, false, false) VY_GEMM_EXTERN(T, 128, false, false, false) \
+  VY_GEMM_EXTERN(T, 192, false, false, false) VY_GEMM_EXTERN(T, 256, false, false, false)                                    \
+  VY_GEMM_EXTERN(T, 128, false, true, false) VY_GEMM_EXTERN(T, 192, false, true, false) VY_GEMM_EXTERN(T, 256, false, true, false)  \
+  VY_GEMM_EXTERN(T, 128, true, false, false) VY_GEMM_EXTERN(T, 192, true, false, false) VY_GEMM_EXTERN(T, 256, true, false, false)  \
+  VY_GEMM_EXTERN(T, 128, true, true, false) VY_GEMM_EXTERN(T, 192, true, true, false) VY_GEMM_EXTERN(T, 256, true, true, false)
 VY_GEMM_EXTERN_ALL(__nv_bfloat16)
 VY_GEMM_EXTERN_ALL(float)
+// CTA-pair (cta_group::2) kernels: bf16 only; an MN-major B half must be whole 64-column boxes, so no 192 there
+#define VY_GEMM_EXTERN_PAIR(A, B, BN) VY_GEMM_EXTERN(__nv_bfloat16, BN, A, B, true)
+VY_GEMM_EXTERN_PAIR(false, false, 128) VY_GEMM_EXTERN_PAIR(false, false, 192) VY_GEMM_EXTERN_PAIR(false, false, 256)
+VY_GEMM_EXTERN_PAIR(true, false, 128) VY_GEMM_EXTERN_PAIR(true, false, 192) VY_GEMM_EXTERN_PAIR(true, false, 256)
+VY_GEMM_EXTERN_PAIR(false, true, 128) VY_GEMM_EXTERN_PAIR(false, true, 256)
+VY_GEMM_EXTERN_PAIR(true, true, 128) VY_GEMM_EXTERN_PAIR(true, true, 256)
+
+static int dispatch_gemm_pair(const VyGemm* p, const GemmDev& g, int bn) {
+  using T = __nv_bfloat16;
+  const bool amn = p->a_mn_major != 0, bmn = p->b_mn_major != 0;
+  if (!bmn) {
+    if (bn == 128) return amn ? launch_gemm<T, 128, true, false, true>(p, g) : launch_gemm<T, 128, false, false, true>(p, g);
+    if (bn == 192) return amn ? launch_gemm<T, 192, true, false, true>(p, g) : launch_gemm<T, 192, false, false, true>(p, g);
+    return amn ? launch_gemm<T, 256, true, false, true>(p, g) : launch_gemm<T, 256, false, false, true>(p, g);
+  }
+  if (bn == 128) return amn ? launch_gemm<T, 128, true, true, true>(p, g) : launch_gemm<T, 128, false, true, true>(p, g);
+  return amn ? launch_gemm<T, 256, true, true, true>(p, g) : launch_gemm<T, 256, false, true, true>(p, g);
+}
 
 template <typename TIn>
 static int dispatch_gemm(const VyGemm* p, const GemmDev& g, int bn) {
   const bool amn = p->a_mn_major != 0, bmn = p->b_mn_major != 0;
 #define VY_GEMM_CASE(BN_, A_, B_) \
-  case BN_: return launch_gemm<TIn, BN_, A_, B_>(p, g)
+  case BN_: return launch_gemm<TIn, BN_, A_, B_, false>(p, g)
   if (!amn && !bmn) {
     switch (bn) {
       VY_GEMM_CASE(32, false, false);
       VY_GEMM_CASE(64, false, false);
       VY_GEMM_CASE(128, false, false);
       VY_GEMM_CASE(192, false, false);
-      default: return launch_gemm<TIn, 256, false, false>(p, g);
+      default: return launch_gemm<TIn, 256, false, false, false>(p, g);
     }
   }
   if (bn < 128) bn = 128;  // MN-major operands arrive in 64-element (bf16) / 32-element (tf32) boxes
@@ -35,60 +53,64 @@ static int dispatch_gemm(const VyGemm* p, const GemmDev& g, int bn) {
     switch (bn) {
       VY_GEMM_CASE(128, false, true);
       VY_GEMM_CASE(192, false, true);
-      default: return launch_gemm<TIn, 256, false, true>(p, g);
+      default: return launch_gemm<TIn, 256, false, true, false>(p, g);
     }
   }
   if (amn && !bmn) {
     switch (bn) {
       VY_GEMM_CASE(128, true, false);
       VY_GEMM_CASE(192, true, false);
-      default: return launch_gemm<TIn, 256, true, false>(p, g);
+      default: return launch_gemm<TIn, 256, true, false, false>(p, g);
     }
   }
   switch (bn) {
     VY_GEMM_CASE(128, true, true);
     VY_GEMM_CASE(192, true, true);
-    default: return launch_gemm<TIn, 256, true, true>(p, g);
+    default: return launch_gemm<TIn, 256, true, true, false>(p, g);
   }
 #undef VY_GEMM_CASE
 }
 
-// Tile width and K split. The persistent grid walks ceil(units / SMs) waves of 128 x BN x (K / splits) units; a
-// candidate is scored with a small time model calibrated on B200 (tools/gemm_bench.py): a 128 x 256 x 64 k-block
-// costs ~0.6 us of an SM at the sustained rate, a unit pays ~6 k-blocks for pipeline fill + epilogue, tiles of
-// BN <= 128 feed the tensor pipe worse (A + B shared-memory reads per MMA reach the SM's 128 B/clk), and split-K
-// adds a reduce pass over the fp32 slabs (launch gap + bytes at ~3 TB/s). Ties go to the wider tile / fewer splits.
+// Kernel flavour, tile width and K split. The persistent grid walks ceil(units / workers) waves of units — 128 x BN x
+// (K / splits) on one SM, or 256 x BN x (K / splits) on a CTA pair — and every candidate is scored with a small time
+// model fitted to a sweep of all candidates over the GEMM shapes of the captioner step on B200 (tools/gemm_sweep.py,
+// profiles/r01_gemm_sweep.txt; rms error 7%, total time of its choices within 1% of the per-shape best):
+//   t [us] = 12 + 8 * a + waves * (k-blocks per unit * a + e * BN / 256) (+ 3 + 0.165 * (4 * splits + 4) * M * N / 1e6)
+// a = time of one 64-wide k-block of a unit (CTA pairs halve the B rows each SM reads from shared memory, which is what
+// holds single-CTA tiles below the tensor pipe's rate), e = epilogue time per 256 columns of a unit, the last term the
+// fp32 slab traffic of the split-K reduce pass.
 struct Tiling {
-  int bn, splits;
+  int pair, bn, splits;
+  double cost;  // modelled time, us
 };
-static Tiling choose_tiling(int M, int N, int num_kb, bool mn_major, bool qkv, int max_splits) {
+static Tiling choose_tiling(int M, int N, int num_kb, bool mn_major, bool b_mn, bool qkv, double epi_cost, int max_splits,
+                            int pair_lo, int pair_hi) {
   static const int cand[5] = {256, 192, 128, 64, 32};
-  static const double pen[5] = {1.0, 1.0, 1.12, 1.6, 2.6};
+  static const double kb_single[5] = {0.354, 0.32, 0.29, 0.24, 0.195};
+  static const double kb_pair[3] = {0.303, 0.256, 0.244};
   static const int split_cand[6] = {1, 2, 3, 4, 6, 8};
-  const int m_tiles = (M + 127) / 128;
-  const int sms = num_sms();
-  const double unit_fixed = 6.0;  // k-blocks' worth of fill + epilogue per unit
-  Tiling best = {256, 1};
-  double best_cost = 1e30;
-  for (int i = 0; i < 5; ++i) {
-    const int bn = cand[i];
-    if (mn_major && bn < 128) continue;
-    if (qkv && bn < 64) continue;
-    if (bn > 32 && bn / 2 >= N) continue;  // more than half of the tile would be padding
-    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
-    for (int si = 0; si < 6; ++si) {
-      const int sp = split_cand[si];
-      if (sp > max_splits) break;
-      if (sp > 1 && num_kb / sp < 16) break;  // keep the mainloop of a unit long enough to amortise its epilogue
-      const int kb_per = (num_kb + sp - 1) / sp;
-      if (sp > 1 && static_cast<long long>(sp - 1) * kb_per >= num_kb) continue;  // an empty last split
-      const long long waves = (tiles * sp + sms - 1) / sms;
-      double cost = static_cast<double>(waves) * (kb_per + unit_fixed) * 0.6 * (bn / 256.0) * pen[i];  // us
-      if (sp > 1) cost += 4.0 + (static_cast<double>(sp) * 8.0 + 4.0) * M * N / 3.0e6;
-      if (cost < best_cost * 0.999) {
-        best_cost = cost;
-        best.bn = bn;
-        best.splits = sp;
+  Tiling best = {0, 256, 1, 1e30};
+  for (int pair = pair_lo; pair <= pair_hi; ++pair) {
+    const int m_tiles = pair ? (M + 255) / 256 : (M + 127) / 128;
+    const int workers = pair ? num_sms() / 2 : num_sms();
+    for (int i = 0; i < (pair ? 3 : 5); ++i) {
+      const int bn = cand[i];
+      if (mn_major && bn < 128) continue;
+      if (pair && b_mn && bn == 192) continue;  // an MN-major B half must be whole 64-column boxes
+      if (qkv && bn < 64) continue;
+      if (bn > 32 && bn / 2 >= N) continue;  // more than half of the tile would be padding
+      const double a = pair ? kb_pair[i] : kb_single[i];
+      const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+      for (int si = 0; si < 6; ++si) {
+        const int sp = split_cand[si];
+        if (sp > max_splits) break;
+        if (sp > 1 && num_kb / sp < 16) break;  // keep the mainloop of a unit long enough to amortise its epilogue
+        const int kb_per = (num_kb + sp - 1) / sp;
+        if (sp > 1 && static_cast<long long>(sp - 1) * kb_per >= num_kb) continue;  // an empty last split
+        const long long waves = (tiles * sp + workers - 1) / workers;
+        double cost = 12.0 + 8.0 * a + static_cast<double>(waves) * (kb_per * a + epi_cost * bn / 256.0);
+        if (sp > 1) cost += 3.0 + 0.165 * (sp * 4.0 + 4.0) * M * N / 1.0e6;
+        if (cost < best.cost * 0.999) best = {pair, bn, sp, cost};
       }
     }
   }
@@ -136,7 +158,34 @@ splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ ws, con
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// one int of device memory that a timed-out wait inside a GEMM kernel raises (mbar_wait_soft)
+static int* poison_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
 }  // namespace vy
+
+// development hook (tools/gemm_sweep.py): pin the kernel flavour, tile width and K split of subsequent vy_gemm calls
+static int g_force_pair = -1, g_force_bn = 0, g_force_splits = 0;
+extern "C" int vy_gemm_tune_override(int pair, int bn, int splits) {
+  g_force_pair = pair;
+  g_force_bn = bn;
+  g_force_splits = splits;
+  return VY_OK;
+}
+
+extern "C" int vy_gemm_poisoned(void) {
+  using namespace vy;
+  int* f = poison_flag();
+  int v = -1;
+  if (!f || cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v;
+}
 
 extern "C" int vy_gemm(const VyGemm* p) {
   using namespace vy;
@@ -159,6 +208,8 @@ extern "C" int vy_gemm(const VyGemm* p) {
   memset(&g, 0, sizeof(g));
   static const int dbg = getenv("VY_GEMM_DEBUG") ? atoi(getenv("VY_GEMM_DEBUG")) : 0;
   g.debug = dbg;
+  g.poison = poison_flag();
+  VY_CHECK_ARG(g.poison != nullptr, "vy_gemm: could not allocate the poison flag");
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.epi = p->epi; g.act = p->act; g.transposed_out = p->transposed_out;
   g.bias = p->bias; g.bias_dtype = p->bias_dtype;
@@ -235,14 +286,33 @@ extern "C" int vy_gemm(const VyGemm* p) {
     max_splits = static_cast<int>(p->workspace_bytes / per < 8 ? p->workspace_bytes / per : 8);
     if (max_splits < 1) max_splits = 1;
   }
-  const Tiling tl = choose_tiling(p->M, p->N, num_kb, p->a_mn_major || p->b_mn_major, p->epi == VY_EPI_QKV_ROPE, max_splits);
-  static const int force_bn = getenv("VY_GEMM_FORCE_BN") ? atoi(getenv("VY_GEMM_FORCE_BN")) : 0;  // development: pin the tile width
-  const int bn = force_bn ? force_bn : tl.bn;
+  // CTA-pair kernels (cta_group::2): bf16, at least two m-tiles, row-major result. Both flavours are scored by the time
+  // model and the cheaper one runs; VY_GEMM_PAIR=0 / 1 pins the flavour.
+  static const int pair_env = getenv("VY_GEMM_PAIR") ? atoi(getenv("VY_GEMM_PAIR")) : -1;
+  const int pair_pin = g_force_pair >= 0 ? g_force_pair : pair_env;
+  const bool pair_ok = p->in_dtype == VY_BF16 && p->M > 128 && p->N >= 128 && !p->transposed_out;
+  const double epi_cost = p->act == VY_ACT_GELU_ERF || p->act == VY_ACT_GELU_TANH ? 3.4
+                          : (p->act == VY_ACT_DGELU_ERF || p->act == VY_ACT_DGELU_TANH ? 8.6 : 2.4);
+  Tiling tl = choose_tiling(p->M, p->N, num_kb, p->a_mn_major || p->b_mn_major, p->b_mn_major != 0, p->epi == VY_EPI_QKV_ROPE,
+                            epi_cost, max_splits, pair_ok && pair_pin == 1 ? 1 : 0, pair_ok && pair_pin != 0 ? 1 : 0);
+  const bool pair = tl.pair != 0;
+  static const int force_bn_env = getenv("VY_GEMM_FORCE_BN") ? atoi(getenv("VY_GEMM_FORCE_BN")) : 0;  // development: pin the tile width
+  const int force_bn = g_force_bn ? g_force_bn : force_bn_env;
+  int bn = force_bn ? force_bn : tl.bn;
+  if (pair && bn < 128) bn = 128;
+  if (pair && p->b_mn_major && bn == 192) bn = 256;
+  if (g_force_splits > 0) {
+    VY_CHECK_ARG(g_force_splits <= max_splits, "vy_gemm: forced split %d > %d allowed here", g_force_splits, max_splits);
+    VY_CHECK_ARG(static_cast<long long>(g_force_splits - 1) * ((num_kb + g_force_splits - 1) / g_force_splits) < num_kb,
+                 "vy_gemm: forced split %d leaves an empty slab", g_force_splits);
+    tl.splits = g_force_splits;
+  }
   g.k_splits = tl.splits;
   g.kb_per_split = (num_kb + tl.splits - 1) / tl.splits;
   g.ws = static_cast<float*>(p->workspace);
   if (tl.splits > 1) {
-    const int rc = p->in_dtype == VY_BF16 ? dispatch_gemm<__nv_bfloat16>(p, g, bn) : dispatch_gemm<float>(p, g, bn);
+    const int rc = pair ? dispatch_gemm_pair(p, g, bn)
+                        : (p->in_dtype == VY_BF16 ? dispatch_gemm<__nv_bfloat16>(p, g, bn) : dispatch_gemm<float>(p, g, bn));
     if (rc != VY_OK) return rc;
     const long long nvec = static_cast<long long>(p->M) * (p->N >> 3);
     long long blocks = (nvec + 255) / 256;
@@ -255,6 +325,7 @@ extern "C" int vy_gemm(const VyGemm* p) {
     return VY_OK;
   }
 
+  if (pair) return dispatch_gemm_pair(p, g, bn);
   if (p->in_dtype == VY_BF16) return dispatch_gemm<__nv_bfloat16>(p, g, bn);
   return dispatch_gemm<float>(p, g, bn);
 }

@@ -1,6 +1,6 @@
 // explicit instantiations of the vy_gemm kernel (see gemm_kernel.cuh)
 #include "gemm_kernel.cuh"
 namespace vy {
-template int launch_gemm<__nv_bfloat16, 192, false, false>(const VyGemm*, const GemmDev&);
-template int launch_gemm<__nv_bfloat16, 256, false, false>(const VyGemm*, const GemmDev&);
+template int launch_gemm<__nv_bfloat16, 192, false, false, false>(const VyGemm*, const GemmDev&);
+template int launch_gemm<__nv_bfloat16, 256, false, false, false>(const VyGemm*, const GemmDev&);
 }  // namespace vy

@@ -1,7 +1,7 @@
 // vy_gemm: persistent, warp-specialised tcgen05 GEMM for sm_100a.
 //
 //   warp 0      TMEM allocator, then TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
-//   warp 1      MMA issuer    (one thread, tcgen05.mma cta_group::1, fp32 accumulators in TMEM)
+//   warp 1      MMA issuer    (one thread, tcgen05.mma, fp32 accumulators in TMEM; cta_group::2 in PAIR kernels: see gemm_kernel)
 //   warps 2..9  epilogue      (tcgen05.ld -> registers -> fused bias/act/residual/RoPE -> smem staging
 //                              -> coalesced global stores; two warps per TMEM lane quarter)
 //
@@ -51,7 +51,7 @@ struct GemmDev {
   int kv_out_dtype;
   int k_splits, kb_per_split;  // split-K: unit = (tile, split); raw fp32 partial tiles go to ws[split][M][N]
   float* ws;
-  int cluster2;   // launched as 2-CTA clusters: the pair computes two m-tiles of one n-tile and multicasts the shared B tile
+  int* poison;    // raised by a wait that timed out (mbar_wait_soft); checked by the host through vy_gemm_poisoned()
   int tma_store;  // fast epilogues write back with TMA stores (tma_out / tma_aux of the launch)
   int debug;  // development switches (VY_GEMM_DEBUG): 1 = epilogue drains TMEM only, 2 = producer skips TMA after the first ring fill
 };
@@ -83,6 +83,11 @@ struct GemmCfg {
   static constexpr int MN_BOX_BYTES = BK * 128;
   static constexpr int EPI_STAGE_BYTES = GEMM_EPI_WARPS * 2 * GEMM_STAGE_OUT;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2 * BN * 4 /*bias*/ + 256;
+  // CTA pair (cta_group::2): each CTA stages its 128 rows of A and HALF of the B tile
+  static constexpr int PAIR_B_BYTES = B_BYTES / 2;
+  static constexpr int PAIR_STAGE_BYTES = A_BYTES + PAIR_B_BYTES;
+  static constexpr int PAIR_STAGES = BN >= 256 ? 6 : (BN >= 192 ? 6 : 8);
+  static constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + EPI_STAGE_BYTES + 2 * BN * 4 + 256;
   static constexpr int FMT = sizeof(TIn) == 2 ? 1 : 2;  // bf16 : tf32
   // MN-major operands: bf16 uses the plain 128B swizzle (8 k-rows per 1024-B group); tf32 must use
   // SWIZZLE_128B_BASE32B (4 k-rows per 512-B group) and the matching TMA mode.
@@ -90,6 +95,7 @@ struct GemmCfg {
   static constexpr int MN_LAYOUT = sizeof(TIn) == 2 ? 2 : 1;
   static constexpr int MN_TMA_SWIZZLE = sizeof(TIn) == 2 ? 1 : 2;
   static_assert(SMEM_BYTES <= 232448, "tile does not fit the 227 KB of shared memory");
+  static_assert(PAIR_SMEM_BYTES <= 232448, "pair tile does not fit the 227 KB of shared memory");
 };
 
 __device__ __forceinline__ float apply_act(int act, float x) {
@@ -127,10 +133,11 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& raw, float (&v)[8]) {
 }
 
 // every epilogue warp releases its share of the accumulator buffer once its last tcgen05.ld retired
-__device__ __forceinline__ void release_acc(uint64_t* tmem_empty_bar, int lane) {
+// (the barrier is named by a shared::cluster address: in a CTA pair it lives in the leader's shared memory)
+__device__ __forceinline__ void release_acc(uint32_t tmem_empty_bar, int lane) {
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(tmem_empty_bar);
+  if (lane == 0) mbar_arrive_cluster(tmem_empty_bar);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -217,7 +224,7 @@ static __device__ __noinline__ void epilogue_chunk_general(const GemmDev& g, con
 template <int BN>
 __device__ __forceinline__ void epilogue_linear_general(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
                                                         int lane, const float* bias_s, uint64_t* tfull_bar,
-                                                        uint32_t tfull_phase, uint64_t* tmem_empty_bar) {
+                                                        uint32_t tfull_phase, uint32_t tmem_empty_bar) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;  // columns per warp
   constexpr int NCH = WC / 32;
   if (BN < 64 && half) {  // narrow tiles: one warp per lane quarter does all the columns
@@ -230,7 +237,7 @@ __device__ __forceinline__ void epilogue_linear_general(const GemmDev& g, uint32
   const long long orow = remap_out_row(g, grow);
   const long long arow = remap_add_row(g, grow);
   const int gc0 = n0 + wcol0;
-  mbar_wait(tfull_bar, tfull_phase);
+  mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
   tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
@@ -265,7 +272,7 @@ __device__ __forceinline__ void store_ragged8(__nv_bfloat16* dst, const uint4& v
 template <int BN, int MODE, bool TMA>
 __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
                                                      int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
-                                                     uint64_t* tmem_empty_bar, uint8_t* stage, int trace_tile,
+                                                     uint32_t tmem_empty_bar, uint8_t* stage, int trace_tile,
                                                      const CUtensorMap* tma_out, const CUtensorMap* tma_aux) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;
   constexpr int NCH = WC / 32;
@@ -316,7 +323,7 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
   }
   const int sw = (lane >> 1) & 3;
 
-  mbar_wait(tfull_bar, tfull_phase);
+  mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
   tc_fence_after();
   VY_TRACE(2 + half * 4 + ((q + 2) & 3), trace_tile, 1);
 
@@ -455,7 +462,7 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
 // vy_gemm's reduce kernel sums the slabs and applies bias / addend / scale.
 template <int BN>
 __device__ __forceinline__ void epilogue_splitk(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half, int lane,
-                                                int split, uint64_t* tfull_bar, uint32_t tfull_phase, uint64_t* tmem_empty_bar) {
+                                                int split, uint64_t* tfull_bar, uint32_t tfull_phase, uint32_t tmem_empty_bar) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;
   constexpr int NCH = WC / 32;
   if (BN < 64 && half) {
@@ -465,7 +472,7 @@ __device__ __forceinline__ void epilogue_splitk(const GemmDev& g, uint32_t tmem_
   const int wcol0 = BN >= 64 ? half * WC : 0;
   const int grow = m0 + q * 32 + lane;
   float* dst = g.ws + (static_cast<long long>(split) * g.M + grow) * g.N + n0 + wcol0;
-  mbar_wait(tfull_bar, tfull_phase);
+  mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
   tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
@@ -490,13 +497,13 @@ __device__ __forceinline__ void epilogue_splitk(const GemmDev& g, uint32_t tmem_
 template <int BN>
 __device__ __forceinline__ void epilogue_transposed(const GemmDev& g, uint32_t tmem_base_acc, int m0, int n0, int q, int half,
                                                     int lane, int et, uint64_t* tfull_bar, uint32_t tfull_phase,
-                                                    uint64_t* tmem_empty_bar, float* stage_f) {
+                                                    uint32_t tmem_empty_bar, float* stage_f) {
   constexpr int NCH = BN >= 32 ? BN / 32 : 1;
   constexpr int LDT = 128 + 1;
   const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
   const bool fwd_act = g.act == VY_ACT_GELU_ERF || g.act == VY_ACT_GELU_TANH;
   const bool bwd_act = g.act == VY_ACT_DGELU_ERF || g.act == VY_ACT_DGELU_TANH;
-  mbar_wait(tfull_bar, tfull_phase);
+  mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
   tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
@@ -540,7 +547,7 @@ __device__ __forceinline__ void epilogue_transposed(const GemmDev& g, uint32_t t
 template <int BN>
 __device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
                                                   int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
-                                                  uint64_t* tmem_empty_bar, uint8_t* stage) {
+                                                  uint32_t tmem_empty_bar, uint8_t* stage) {
   const int grow = m0 + q * 32 + lane;
   const bool row_ok = grow < g.M;
   const int b = row_ok ? grow / g.tokens_per_seq : 0;
@@ -569,7 +576,7 @@ __device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tme
   // this lane's 16-byte slot of a staged row: slots 0,1 = first-half columns j0.., slots 2,3 = columns 32 + j0..
   const int slot_col = ((lane & 2) ? 32 : 0) + j0 + (lane & 1) * 8;
 
-  mbar_wait(tfull_bar, tfull_phase);
+  mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
   tc_fence_after();
 
 #pragma unroll 1
@@ -648,7 +655,7 @@ __device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tme
 // --------------------------------------------------------------------------------------------
 // kernel
 // --------------------------------------------------------------------------------------------
-template <typename TIn, int BN, bool A_MN, bool B_MN>
+template <typename TIn, int BN, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
@@ -657,12 +664,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   using Cfg = GemmCfg<TIn, BN>;
   constexpr int BM = Cfg::BM;
   constexpr int BK = Cfg::BK;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
+  constexpr int B_BYTES = PAIR ? Cfg::PAIR_B_BYTES : Cfg::B_BYTES;      // this CTA's part of the B tile
+  constexpr int STAGE_BYTES = Cfg::A_BYTES + B_BYTES;
+  constexpr int BN_CTA = PAIR ? BN / 2 : BN;                            // B rows (output columns) staged by this CTA
+  static_assert(!PAIR || !B_MN || BN_CTA % Cfg::EPB == 0, "an MN-major B half must be whole swizzle boxes");
+  static_assert(!PAIR || BN % 16 == 0, "cta_group::2 MMAs take N in steps of 16");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
   float* bias_s = reinterpret_cast<float*>(epi_stage + Cfg::EPI_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
   uint64_t* full_bar = bars;                 // [STAGES]
@@ -676,17 +688,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned base
 
   // Work distribution. Plain launch: CTA b walks units b, b + grid, ... (unit = (tile, k-split); k_splits == 1 unless
-  // split-K). Cluster launch (g.cluster2): the two CTAs of a cluster walk the same units, a unit covers the m-tile PAIR
-  // (2p, 2p + 1) of one n-tile and CTA rank r computes m-tile 2p + r — both need the same B tile, so each loads half of
-  // it and multicasts it to the pair: L2 -> SM operand traffic per tile drops from (128 + BN) to (128 + BN / 2) rows,
-  // which is what bounds these GEMMs (~12 TB/s of L2 -> SM bandwidth, measured).
-  const bool cl2 = g.cluster2 != 0;
-  const int rank = cl2 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int worker = cl2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int nworkers = cl2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // split-K). PAIR launch (2-CTA clusters, tcgen05 cta_group::2): the two CTAs of a cluster walk the same units, a unit
+  // covers the m-tile pair (2p, 2p + 1) of one n-tile as ONE 256 x BN MMA tile. CTA rank r stages A rows of m-tile
+  // 2p + r and B rows [r * BN/2, (r + 1) * BN/2) of the n-tile in its own shared memory, the leader (rank 0) issues the
+  // M = 256 MMAs, which read both CTAs' shared memory and leave m-tile 2p + r's accumulator in CTA r's TMEM. Per SM
+  // and MMA that is 128 + BN/2 operand rows out of shared memory instead of 128 + BN — the shared-memory read rate
+  // (128 B/clk) is what holds a single-CTA 128 x BN MMA at ~75% of the tensor pipe's rate.
+  //   full[s]    leader's: one arrive.expect_tx by the leader's producer, bytes of BOTH CTAs' loads complete on it
+  //   empty[s]   per CTA:  the leader's tcgen05.commit arrives on both (multicast)
+  //   tfull[a]   per CTA:  likewise
+  //   tempty[a]  leader's: 2 x 8 epilogue warps, the peer's arrive through the cluster address
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nworkers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int m_tiles = (g.M + BM - 1) / BM;
-  const int m_slots = cl2 ? (m_tiles + 1) / 2 : m_tiles;
-  const int m_mul = cl2 ? 2 : 1;
+  const int m_slots = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int m_mul = PAIR ? 2 : 1;
   const int n_tiles = (g.N + BN - 1) / BN;
   const int num_tiles = m_slots * n_tiles;
   const int num_kb = (g.K + BK - 1) / BK;
@@ -703,20 +720,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], cl2 ? 2 : 1);  // a multicast stage is free when BOTH CTAs' MMAs have consumed it
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], GEMM_EPI_WARPS);
+      mbar_init(&tempty_bar[a], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_ptr_s, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  if (cl2) cluster_sync();  // the peer's barriers must be initialised before anything can arrive on them
+  if constexpr (PAIR) cluster_sync();  // the peer's barriers must be initialised before anything can arrive on them
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
@@ -729,56 +751,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       for (int unit = worker; unit < num_units; unit += nworkers) {
         const int tile = unit % num_tiles;
         const int m0 = ((tile / n_tiles) * m_mul + rank) * BM;  // may lie beyond M for the odd m-tile of the last pair: TMA zero-fills
-        const int n0 = (tile % n_tiles) * BN;
+        const int n0 = (tile % n_tiles) * BN + rank * BN_CTA;   // first B row this CTA stages
         const int kb0 = (unit / num_tiles) * g.kb_per_split;
         const int kb1 = min(num_kb, kb0 + g.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait_soft(&empty_bar[s], ph ^ 1, g.poison);
           if (elect_one_sync()) {
-          if ((g.debug & 2) && it >= STAGES) {
-            mbar_arrive(&full_bar[s]);
-          } else {
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          uint8_t* a_dst = sA + s * Cfg::A_BYTES;
-          uint8_t* b_dst = sB + s * Cfg::B_BYTES;
-          if constexpr (!A_MN) {
-            tma_load_2d(a_dst, &tma_a, &full_bar[s], kb * BK, m0);
-          } else {
+            uint8_t* a_dst = sA + s * Cfg::A_BYTES;
+            uint8_t* b_dst = sB + s * B_BYTES;
+            if ((g.debug & 2) && it >= STAGES) {
+              if (rank == 0) mbar_arrive(&full_bar[s]);
+            } else if constexpr (!PAIR) {
+              mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+              if constexpr (!A_MN) {
+                tma_load_2d(a_dst, &tma_a, &full_bar[s], kb * BK, m0);
+              } else {
 #pragma unroll
-            for (int i = 0; i < BM / Cfg::EPB; ++i)
-              tma_load_2d(a_dst + i * Cfg::MN_BOX_BYTES, &tma_a, &full_bar[s], m0 + i * Cfg::EPB, kb * BK);
-          }
-          if (!cl2) {
-            if constexpr (!B_MN) {
-              tma_load_2d(b_dst, &tma_b, &full_bar[s], kb * BK, n0);
+                for (int i = 0; i < BM / Cfg::EPB; ++i)
+                  tma_load_2d(a_dst + i * Cfg::MN_BOX_BYTES, &tma_a, &full_bar[s], m0 + i * Cfg::EPB, kb * BK);
+              }
+              if constexpr (!B_MN) {
+                tma_load_2d(b_dst, &tma_b, &full_bar[s], kb * BK, n0);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BN / Cfg::EPB; ++i)
+                  tma_load_2d(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, &full_bar[s], n0 + i * Cfg::EPB, kb * BK);
+              }
             } else {
+              // both CTAs' bytes complete on the LEADER's full barrier, which gates the one MMA thread of the pair
+              const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+              if constexpr (!A_MN) {
+                tma_load_2d_pair(a_dst, &tma_a, full_leader, kb * BK, m0);
+              } else {
 #pragma unroll
-              for (int i = 0; i < BN / Cfg::EPB; ++i)
-                tma_load_2d(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, &full_bar[s], n0 + i * Cfg::EPB, kb * BK);
-            }
-          } else {
-            // this CTA's share of the B tile, multicast into both CTAs (same smem offset, each CTA's own full barrier)
-            if constexpr (!B_MN) {  // tma_b was built with a box of BN / 2 rows
-              tma_load_2d_mc(b_dst + rank * (BN / 2) * 128, &tma_b, &full_bar[s], kb * BK, n0 + rank * (BN / 2), 3);
-            } else {
+                for (int i = 0; i < BM / Cfg::EPB; ++i)
+                  tma_load_2d_pair(a_dst + i * Cfg::MN_BOX_BYTES, &tma_a, full_leader, m0 + i * Cfg::EPB, kb * BK);
+              }
+              if constexpr (!B_MN) {  // tma_b was built with a box of BN / 2 rows
+                tma_load_2d_pair(b_dst, &tma_b, full_leader, kb * BK, n0);
+              } else {
 #pragma unroll
-              for (int i = 0; i < BN / Cfg::EPB; ++i)
-                if ((i & 1) == rank)
-                  tma_load_2d_mc(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, &full_bar[s], n0 + i * Cfg::EPB, kb * BK, 3);
+                for (int i = 0; i < BN_CTA / Cfg::EPB; ++i)
+                  tma_load_2d_pair(b_dst + i * Cfg::MN_BOX_BYTES, &tma_b, full_leader, n0 + i * Cfg::EPB, kb * BK);
+              }
             }
-          }
-          }
           }
           __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-    {
-      constexpr uint32_t idesc = make_idesc(Cfg::FMT, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ===================== MMA issuer (whole warp, one elected lane issues; in a pair only the leader's) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(Cfg::FMT, PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0;
       uint32_t local = 0;
       for (int unit = worker; unit < num_units; unit += nworkers, ++local) {
@@ -787,30 +815,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const uint32_t acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         VY_TRACE(1, local, 0);
-        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        mbar_wait_soft<PAIR>(&tempty_bar[acc], acc_ph ^ 1, g.poison);
         tc_fence_after();
         VY_TRACE(1, local, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait_soft<PAIR>(&full_bar[s], ph, g.poison);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
           if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
-            const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            if constexpr (sizeof(TIn) == 2) umma_f16(d_tmem, ad, bd, idesc, kb != kb0 || k != 0);
-            else umma_tf32(d_tmem, ad, bd, idesc, kb != kb0 || k != 0);
-          }
-          if (cl2) umma_commit_mc(&empty_bar[s], 3);
-          else umma_commit(&empty_bar[s]);
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+            for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
+              const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                                       : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                                       : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              const uint32_t accum = kb != kb0 || k != 0;
+              if constexpr (PAIR) {
+                if constexpr (sizeof(TIn) == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum);
+                else umma_tf32_pair(d_tmem, ad, bd, idesc, accum);
+              } else {
+                if constexpr (sizeof(TIn) == 2) umma_f16(d_tmem, ad, bd, idesc, accum);
+                else umma_tf32(d_tmem, ad, bd, idesc, accum);
+              }
+            }
+            if constexpr (PAIR) {
+              umma_commit_pair(&empty_bar[s], 3);
+              if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc], 3);
+            } else {
+              umma_commit(&empty_bar[s]);
+              if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+            }
           }
           __syncwarp();
         }
@@ -841,6 +879,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int m0 = ((tile / n_tiles) * m_mul + rank) * BM;
       const int n0 = (tile % n_tiles) * BN;
       float* bs = bias_s + acc * BN;
+      // where this warp announces that it has drained the accumulator: the (leader's) MMA thread waits there
+      const uint32_t tempty_addr = PAIR ? mapa_u32(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
       VY_TRACE(2 + e, local, 0);
       if (!g.transposed_out) {
         for (int j = et; j < BN; j += GEMM_EPI_WARPS * 32) {
@@ -851,47 +891,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (g.debug & 1) {
-        mbar_wait(&tfull_bar[acc], acc_ph);
+        mbar_wait_soft(&tfull_bar[acc], acc_ph, g.poison);
         tc_fence_after();
-        release_acc(&tempty_bar[acc], lane);
+        release_acc(tempty_addr, lane);
       } else if (g.k_splits > 1) {
-        epilogue_splitk<BN>(g, tmem_acc, m0, n0, q, half, lane, unit / num_tiles, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
+        epilogue_splitk<BN>(g, tmem_acc, m0, n0, q, half, lane, unit / num_tiles, &tfull_bar[acc], acc_ph, tempty_addr);
       } else if (g.epi == VY_EPI_QKV_ROPE) {
         if constexpr (BN >= 64)
-          epilogue_qkv_rope<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage);
+          epilogue_qkv_rope<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage);
       } else if (g.transposed_out) {
-        epilogue_transposed<BN>(g, tmem_base + acc * BN, m0, n0, q, half, lane, et, &tfull_bar[acc], acc_ph, &tempty_bar[acc],
+        epilogue_transposed<BN>(g, tmem_base + acc * BN, m0, n0, q, half, lane, et, &tfull_bar[acc], acc_ph, tempty_addr,
                                 reinterpret_cast<float*>(epi_stage));
       } else if (fast_mode == EPI_PLAIN) {
         if (g.tma_store)
-          epilogue_linear_fast<BN, EPI_PLAIN, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_PLAIN, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                     local, &tma_out, &tma_aux);
         else
-          epilogue_linear_fast<BN, EPI_PLAIN, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_PLAIN, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                      local, &tma_out, &tma_aux);
       } else if (fast_mode == EPI_ADD) {
         if (g.tma_store)
-          epilogue_linear_fast<BN, EPI_ADD, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_ADD, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                     local, &tma_out, &tma_aux);
         else
-          epilogue_linear_fast<BN, EPI_ADD, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_ADD, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                      local, &tma_out, &tma_aux);
       } else if (fast_mode == EPI_GELU) {
         if (g.tma_store)
-          epilogue_linear_fast<BN, EPI_GELU, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_GELU, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                     local, &tma_out, &tma_aux);
         else
-          epilogue_linear_fast<BN, EPI_GELU, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_GELU, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                      local, &tma_out, &tma_aux);
       } else if (fast_mode == EPI_DGELU) {
         if (g.tma_store)
-          epilogue_linear_fast<BN, EPI_DGELU, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_DGELU, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                     local, &tma_out, &tma_aux);
         else
-          epilogue_linear_fast<BN, EPI_DGELU, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc], stage,
+          epilogue_linear_fast<BN, EPI_DGELU, false>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
                                                      local, &tma_out, &tma_aux);
       } else {
-        epilogue_linear_general<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, &tempty_bar[acc]);
+        epilogue_linear_general<BN>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr);
       }
       VY_TRACE(2 + e, local, 3);
     }
@@ -899,11 +939,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
 
   tc_fence_before();
-  if (cl2) cluster_sync();  // the peer may still multicast-arrive on this CTA's barriers until it is done too
+  if constexpr (PAIR) cluster_sync();  // the peer may still arrive on this CTA's barriers / read its smem until it is done too
   else __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 #ifdef VY_GEMM_TRACE
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -929,7 +970,7 @@ static inline int get_tmap_2d(CUtensorMap* out, int dtype, const void* base, uin
   return get_tensor_map_cached(out, dtype, 2, base, dims, strides, box, swz);
 }
 
-template <typename TIn, int BN, bool A_MN, bool B_MN>
+template <typename TIn, int BN, bool A_MN, bool B_MN, bool PAIR>
 int launch_gemm(const VyGemm* p, const GemmDev& g) {
   using Cfg = GemmCfg<TIn, BN>;
   const int dt = p->in_dtype;
@@ -941,14 +982,8 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   else
     rc = get_tmap_2d(&ta, dt, p->A, p->M, p->K, p->lda * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
-  // 2-CTA clusters with a multicast B tile (see gemm_kernel). Opt-in (VY_GEMM_CLUSTER=1): measured on the captured
-  // training step it changes nothing (12.00 vs 12.01 ms) — at cluster size 2 the L2 already de-duplicates the two CTAs'
-  // unicast requests, and the mainloop is tensor-pipe bound (136 cycles per M128 N192 K16 MMA), not operand-bound.
-  static const bool cluster_on = getenv("VY_GEMM_CLUSTER") && atoi(getenv("VY_GEMM_CLUSTER")) != 0;
-  const int m_tiles_h = (p->M + Cfg::BM - 1) / Cfg::BM;
-  const bool cl2 = cluster_on && BN >= 128 && m_tiles_h >= 2 && (m_tiles_h % 2 == 0 || m_tiles_h >= 9);
-  if (!B_MN)
-    rc = get_tmap_2d(&tb, dt, p->B, p->K, p->N, p->ldb * es, Cfg::BK, cl2 ? BN / 2 : BN);
+  if (!B_MN)  // a CTA of a pair stages half of the B tile
+    rc = get_tmap_2d(&tb, dt, p->B, p->K, p->N, p->ldb * es, Cfg::BK, PAIR ? BN / 2 : BN);
   else
     rc = get_tmap_2d(&tb, dt, p->B, p->N, p->K, p->ldb * es, Cfg::EPB, Cfg::BK, Cfg::MN_TMA_SWIZZLE);
   if (rc != VY_OK) return rc;
@@ -962,22 +997,22 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
       rc = get_tmap_2d(&taux, VY_BF16, p->aux, p->N, p->M, p->ld_aux * 2, 32, 32, 3);
     if (rc != VY_OK) gl.tma_store = 0;  // fall back to the staged st.global write-back
   }
-  auto kern = gemm_kernel<TIn, BN, A_MN, B_MN>;
+  auto kern = gemm_kernel<TIn, BN, A_MN, B_MN, PAIR>;
+  constexpr int smem_bytes = PAIR ? Cfg::PAIR_SMEM_BYTES : Cfg::SMEM_BYTES;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   const int m_tiles = (p->M + Cfg::BM - 1) / Cfg::BM;
   const int n_tiles = (p->N + BN - 1) / BN;
-  const int m_slots = cl2 ? (m_tiles + 1) / 2 : m_tiles;
+  const int m_slots = PAIR ? (m_tiles + 1) / 2 : m_tiles;
   const int units = m_slots * n_tiles * (g.k_splits > 1 ? g.k_splits : 1);
-  const int max_workers = cl2 ? num_sms() / 2 : num_sms();
+  const int max_workers = PAIR ? num_sms() / 2 : num_sms();
   const int workers = units < max_workers ? units : max_workers;
-  const int grid = cl2 ? 2 * workers : workers;
-  gl.cluster2 = cl2 ? 1 : 0;
-  VY_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, static_cast<cudaStream_t>(p->stream),
-                                   cl2 ? 2 : 1, ta, tb, tout, taux, gl));
+  const int grid = PAIR ? 2 * workers : workers;
+  VY_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(GEMM_THREADS), smem_bytes, static_cast<cudaStream_t>(p->stream),
+                                   PAIR ? 2 : 1, ta, tb, tout, taux, gl));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -50,6 +50,19 @@ VY_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+VY_DEVINL bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {  // local barrier, remote arrivals
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug (wrong descriptor, missing arrive) traps instead of hanging the GPU; the trap surfaces
 // as a launch failure on the host (vy_last_error). try_wait suspends the thread in hardware for a bounded time per
 // attempt, so the loop is a handful of instructions per microsecond-scale attempt (the single-thread producer / MMA
@@ -59,6 +72,23 @@ VY_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22)) __trap();
+  }
+}
+
+// GEMM flavour of the bounded wait: instead of trapping, a wait that times out raises a flag in global memory and
+// returns; every other wait of the grid notices the flag within 64 attempts and returns too, so a protocol bug ends the
+// kernel with wrong results and *poison != 0 (vy_gemm_poisoned() on the host) rather than with a fault or a hang.
+template <bool CLUSTER_SCOPE = false>
+VY_DEVINL void mbar_wait_soft(uint64_t* bar, uint32_t parity, int* poison) {
+  uint32_t spins = 0;
+  while (!(CLUSTER_SCOPE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
+    if ((++spins & 63u) == 0) {
+      if (*reinterpret_cast<volatile int*>(poison) != 0) return;
+      if (spins > (1u << 21)) {
+        atomicExch(poison, 1);
+        return;
+      }
+    }
   }
 }
 
@@ -78,15 +108,6 @@ VY_DEVINL void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// multicast variant: the box lands at the same smem offset in every CTA of `cta_mask` and completes bytes on the
-// mbarrier at the same offset in each of them
-VY_DEVINL void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
 VY_DEVINL void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -211,16 +232,6 @@ VY_DEVINL void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// same, arriving on the barrier at this offset in every CTA of `cta_mask` (a smem stage filled by multicast TMA is
-// free only when all the CTAs that received it have consumed it)
-VY_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
-
 // ----------------------------------------------------------------------------------------------
 // thread-block clusters
 // ----------------------------------------------------------------------------------------------
@@ -232,6 +243,72 @@ VY_DEVINL uint32_t cluster_ctarank() {
 VY_DEVINL void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// CTA pairs (tcgen05 cta_group::2): two CTAs of a cluster, on the two SMs of one TPC, run ONE M = 256 MMA. Each CTA
+// holds its own 128 rows of A and HALF of the B tile in its shared memory and receives its 128 accumulator rows in its
+// own TMEM; the even-ranked CTA (the leader) issues the MMAs for both. Every tcgen05 instruction of such a kernel carries
+// .cta_group::2. Barriers that gate the leader's MMA thread live in the leader's shared memory, so the peer signals
+// them through shared::cluster addresses (mapa).
+// ----------------------------------------------------------------------------------------------
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+VY_DEVINL uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier given by a shared::cluster address (this CTA's own shared::cta addresses are valid ones)
+VY_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// both CTAs of the pair execute these (one full warp each); the allocation is made in both TMEMs at the same columns
+VY_DEVINL void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+VY_DEVINL void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+VY_DEVINL void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes complete on an mbarrier of either CTA of the pair
+VY_DEVINL void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA] * B[N rows: N/2 from each CTA]; issued by ONE thread of the leader
+VY_DEVINL void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+VY_DEVINL void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `cta_mask` once the pair's MMAs issued so far are complete
+VY_DEVINL void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
