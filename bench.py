@@ -283,6 +283,9 @@ def run_ours(args):
                      "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["bytes"] else None}
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
+    poisoned = _lib.lib().vy_gemm_poisoned()
+    if poisoned != 0:
+        raise RuntimeError(f"vy_gemm_poisoned() = {poisoned}: a wait inside a GEMM kernel timed out, the numbers above are void")
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

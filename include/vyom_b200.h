@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VY_ABI_VERSION 2
+#define VY_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VY_API __attribute__((visibility("default")))
@@ -156,13 +156,22 @@ typedef struct VyGemm {
   void* workspace;
   int64_t workspace_bytes;
 
+  /* optional tiling hints (0 = let the library's time model decide). A caller that has timed the candidates on its own
+   * shapes (vyomai_b200/gemm_tune.py does, once per shape) passes the winner here; a hint that does not apply to the
+   * call (pair kernels need bf16 and M > 128, widths below 128 need K-major operands, a split needs workspace and must
+   * not leave an empty slab) is ignored. */
+  int32_t hint_flavour; /* 1 = single-CTA 128 x BN tiles, 2 = CTA-pair (cta_group::2) 256 x BN tiles */
+  int32_t hint_bn;      /* 32, 64, 128, 192 or 256 */
+  int32_t hint_splits;  /* K splits, 1..8 */
+
   void* stream;
 } VyGemm;
 
 VY_API int vy_gemm(const VyGemm* p);
 /* Self-check of the GEMM kernels' barrier protocol: a wait inside a kernel that times out raises a device flag instead
  * of faulting, and the launch finishes with undefined results. Returns the flag (0 = every vy_gemm so far ran its
- * protocol to completion, 1 = some launch did not, -1 = the flag could not be read). Synchronises the device. */
+ * protocol to completion, 1 = some launch did not, -1 = the flag could not be read); a raised flag is lowered by the
+ * read. Synchronises the device. */
 VY_API int vy_gemm_poisoned(void);
 /* Development hook (tools/gemm_sweep.py): pin the kernel flavour (pair: -1 auto, 0 single CTA, 1 CTA pair), the tile
  * width (bn: 0 auto) and the K split (splits: 0 auto) of subsequent vy_gemm calls of this process. */

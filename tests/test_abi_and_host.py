@@ -183,3 +183,34 @@ def test_vyomai_import_name_is_a_drop_in_for_the_hot_path():
         from VyomAI import LoraLinear  # noqa: F401
     with pytest.raises(ImportError):
         VyomAI.speculative_generate
+
+
+def test_gemm_tuner_candidates_respect_kernel_constraints():
+    """vyomai_b200/gemm_tune.py offers vy_gemm only tilings its kernels have: CTA pairs need bf16 and M > 128, widths
+    below 128 need K-major operands, an MN-major B half of a pair must be whole 64-column boxes (no 192), a split must
+    fit the lent workspace and leave no empty slab; decode (swap-AB, tiny N) shapes have nothing to tune."""
+    from vyomai_b200 import _lib as L
+    from vyomai_b200 import gemm_tune as T
+
+    bf16, f32, lin = L.CONSTS["VY_BF16"], L.CONSTS["VY_F32"], L.CONSTS["VY_EPI_LINEAR"]
+    base = dict(M=8192, N=3072, K=768, in_dtype=bf16, epi=lin, a_mn_major=0, b_mn_major=0, transposed_out=0)
+    c = T._candidates(base)
+    assert {x["hint_flavour"] for x in c} == {1, 2}
+    assert {x["hint_bn"] for x in c if x["hint_flavour"] == 2} == {128, 192, 256}
+    assert {x["hint_bn"] for x in c if x["hint_flavour"] == 1} == {32, 64, 128, 192, 256}
+    assert all(x["hint_splits"] == 1 for x in c)  # no workspace, no split
+    c = T._candidates(dict(base, b_mn_major=1))
+    assert all(x["hint_bn"] >= 128 for x in c)
+    assert not any(x["hint_flavour"] == 2 and x["hint_bn"] == 192 for x in c)
+    assert {x["hint_flavour"] for x in T._candidates(dict(base, in_dtype=f32))} == {1}
+    assert {x["hint_flavour"] for x in T._candidates(dict(base, M=128))} == {1}
+    # wgrad: K = 8192 tokens = 128 k-blocks, 64 MB of workspace for a 768 x 768 fp32 slab
+    c = T._candidates(dict(base, M=768, N=768, K=8192, a_mn_major=1, b_mn_major=1, workspace=1, workspace_bytes=64 << 20))
+    assert {x["hint_splits"] for x in c} == {1, 2, 3, 4, 6, 8}
+    c = T._candidates(dict(base, M=768, N=768, K=8192, workspace=1, workspace_bytes=5 * 768 * 768 * 4))
+    assert {x["hint_splits"] for x in c} == {1, 2, 3, 4}
+    # 79 k-blocks: 6 splits of 14 leave none for the last... (5 * 14 = 70 < 79 is fine, but 79 // 6 < 16 k-blocks per split)
+    c = T._candidates(dict(base, M=520, N=264, K=5000, a_mn_major=1, b_mn_major=1, workspace=1, workspace_bytes=64 << 20))
+    assert {x["hint_splits"] for x in c} == {1, 2, 3, 4}
+    # decode: swap-AB, N = 32 rows of the batch -> one 32-wide tile, nothing to choose
+    assert len(T._candidates(dict(base, M=768, N=32, transposed_out=1))) == 1

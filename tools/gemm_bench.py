@@ -54,7 +54,7 @@ def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=
     elif epi == "addend":
         adds = [torch.randn((M, ldo), device=DEV, dtype=BF)[:, :N] for _ in range(nbuf)]
         kw = dict(bias=bias)
-    elif epi == "accum":
+    elif epi in ("accum", "splitk_ok"):
         pass
 
     def ours(i):
@@ -67,6 +67,8 @@ def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=
             k2["addend"] = adds[i]
         if epi == "accum":
             k2["addend"] = outs[i]
+            k2["allow_split_k"] = True
+        if epi == "splitk_ok":
             k2["allow_split_k"] = True
         ops.gemm(a, b, out=outs[i], **k2)
 
@@ -127,7 +129,7 @@ def bench_cases():
         ("dec.d ffn2 dgelu", T, 3072, 768, False, True, "dgelu"),
         ("vit.d ffn2 dgelu", Tv, 3072, 768, False, True, "dgelu"),
         ("dec.d ffn1", T, 768, 3072, False, True, "none"),
-        ("lm_head dgrad", T, 768, 50272, False, True, "none"),
+        ("lm_head dgrad", T, 768, 50272, False, True, "splitk_ok"),
         # wgrad: dW = dY^T X, both MN-major, accumulated into the gradient buffer
         ("dec.w attn_out", 768, 768, T, True, True, "accum"),
         ("dec.w qkv", 1280, 768, T, True, True, "accum"),
@@ -152,6 +154,9 @@ def main():
         if args.only and args.only not in c[0]:
             continue
         res.append(case(*c, iters=args.iters))
+    from vyomai_b200 import gemm_tune
+    for key, best, us, model_us in gemm_tune.LOG:
+        print(f"tuned {key[:4]} mn={key[5:7]}: {best or 'model choice kept'} {us:.1f} us (model's choice {model_us:.1f} us)")
     if args.json:
         json.dump(res, open(args.json, "w"), indent=1)
 

@@ -16,7 +16,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gemm_bench  # noqa: E402
-from vyomai_b200 import _lib  # noqa: E402
+from vyomai_b200 import _lib, gemm_tune  # noqa: E402
+
+gemm_tune.ENABLED = False  # the sweep pins every candidate itself
 
 
 def main():
@@ -34,7 +36,7 @@ def main():
         lib.vy_gemm_tune_override(-1, 0, 0)
         auto = gemm_bench.case(*c, iters=args.iters, cublas_too=False)["us"]
         rows = []
-        splits = [0] if epi != "accum" else [1, 2, 3, 4, 6]
+        splits = [0] if epi not in ("accum", "splitk_ok") else [1, 2, 3, 4, 6]
         for pair in (0, 1):
             for bn in (128, 192, 256):
                 if pair and b_mn and bn == 192:

@@ -30,6 +30,10 @@ def report(name, got, ref, tol):
     r, m = rel_err(got, ref)
     ok = r <= tol and bool(got.isfinite().all().item())
     print(f"  [{'PASS' if ok else 'FAIL'}] {name}: rel={r:.3e} maxabs={m:.3e} tol={tol:.1e}", flush=True)
+    from vyomai_b200 import _lib, gemm_tune
+    if _lib.lib().vy_gemm_poisoned() != 0:  # a wait inside a GEMM kernel timed out (also during the tuning runs of this case)
+        print(f"  [FAIL] {name}: vy_gemm_poisoned; tuned so far: {gemm_tune.LOG[-3:]}", flush=True)
+        ok = False
     return ok
 
 
@@ -56,6 +60,18 @@ def _gemm_cases(dtype, tol):
             ok &= report(f"A_MN {M}x{N}x{K}", ops.gemm(at, b, bias=bias, out=outbuf[:, :N]), ref, tol)
             ok &= report(f"B_MN {M}x{N}x{K}", ops.gemm(a, bt, bias=bias, out=outbuf[:, :N]), ref, tol)
             ok &= report(f"AB_MN {M}x{N}x{K}", ops.gemm(at, bt, bias=bias, out=outbuf[:, :N]), ref, tol)
+    # narrow tiles walked many times by each CTA (pinned through the tuning hook; the time model never picks them here)
+    from vyomai_b200 import _lib
+    M, N, K = 2048, 3072, 256
+    a = torch.randn(M, K, device=dev, dtype=dtype)
+    b = torch.randn(N, K, device=dev, dtype=dtype) / K ** 0.5
+    bias = torch.randn(N, device=dev, dtype=dtype)
+    ref = (a.float() @ b.float().t()) + bias.float()
+    for bn in (32, 64):
+        _lib.lib().vy_gemm_tune_override(0, bn, 0)
+        ok &= report(f"NT {M}x{N}x{K} pinned BN={bn}", ops.gemm(a, b, bias=bias), ref, tol)
+        ok &= report(f"NT {M}x{N}x{K} pinned BN={bn} fp32 out", ops.gemm(a, b, bias=bias, out_dtype=torch.float32), ref, tol)
+    _lib.lib().vy_gemm_tune_override(-1, 0, 0)
     # epilogues
     M, N, K = 512, 768, 768
     a = torch.randn(M, K, device=dev, dtype=dtype)

@@ -26,8 +26,9 @@ def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, like: torch.Tensor, scale: flo
 
 
 def _dgrad(dy2d: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
-    """dX = dY W: the nn.Linear weight [out, in] is the MN-major B operand."""
-    return ops.gemm(dy2d, w.t(), **kw)
+    """dX = dY W: the nn.Linear weight [out, in] is the MN-major B operand. A long reduction (the LM head: K = vocabulary)
+    may be split over K when the output has too few tiles for the SMs."""
+    return ops.gemm(dy2d, w.t(), allow_split_k=dy2d.shape[1] >= 4096, **kw)
 
 
 def _bgrad(dy2d: torch.Tensor, like: Optional[torch.Tensor]) -> Optional[torch.Tensor]:

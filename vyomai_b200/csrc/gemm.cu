@@ -74,8 +74,9 @@ static int dispatch_gemm(const VyGemm* p, const GemmDev& g, int bn) {
 // Kernel flavour, tile width and K split. The persistent grid walks ceil(units / workers) waves of units — 128 x BN x
 // (K / splits) on one SM, or 256 x BN x (K / splits) on a CTA pair — and every candidate is scored with a small time
 // model fitted to a sweep of all candidates over the GEMM shapes of the captioner step on B200 (tools/gemm_sweep.py,
-// profiles/r01_gemm_sweep.txt; rms error 7%, total time of its choices within 1% of the per-shape best):
-//   t [us] = 12 + 8 * a + waves * (k-blocks per unit * a + e * BN / 256) (+ 3 + 0.165 * (4 * splits + 4) * M * N / 1e6)
+// profiles/r01_gemm_sweep.txt; rms error 10%, total time of its choices within 4% of the per-shape best — callers that
+// can afford to time the candidates themselves pass the winner as a hint instead, see VyGemm.hint_*):
+//   t [us] = 14 + 3 * a + waves * (k-blocks per unit * a + e * BN / 256) (+ 3 + 0.058 * (4 * splits + 4) * M * N / 1e6)
 // a = time of one 64-wide k-block of a unit (CTA pairs halve the B rows each SM reads from shared memory, which is what
 // holds single-CTA tiles below the tensor pipe's rate), e = epilogue time per 256 columns of a unit, the last term the
 // fp32 slab traffic of the split-K reduce pass.
@@ -86,8 +87,8 @@ struct Tiling {
 static Tiling choose_tiling(int M, int N, int num_kb, bool mn_major, bool b_mn, bool qkv, double epi_cost, int max_splits,
                             int pair_lo, int pair_hi) {
   static const int cand[5] = {256, 192, 128, 64, 32};
-  static const double kb_single[5] = {0.354, 0.32, 0.29, 0.24, 0.195};
-  static const double kb_pair[3] = {0.303, 0.256, 0.244};
+  static const double kb_single[5] = {0.303, 0.261, 0.19, 0.15, 0.13};
+  static const double kb_pair[3] = {0.27, 0.218, 0.162};
   static const int split_cand[6] = {1, 2, 3, 4, 6, 8};
   Tiling best = {0, 256, 1, 1e30};
   for (int pair = pair_lo; pair <= pair_hi; ++pair) {
@@ -108,8 +109,8 @@ static Tiling choose_tiling(int M, int N, int num_kb, bool mn_major, bool b_mn, 
         const int kb_per = (num_kb + sp - 1) / sp;
         if (sp > 1 && static_cast<long long>(sp - 1) * kb_per >= num_kb) continue;  // an empty last split
         const long long waves = (tiles * sp + workers - 1) / workers;
-        double cost = 12.0 + 8.0 * a + static_cast<double>(waves) * (kb_per * a + epi_cost * bn / 256.0);
-        if (sp > 1) cost += 3.0 + 0.165 * (sp * 4.0 + 4.0) * M * N / 1.0e6;
+        double cost = 14.0 + 3.0 * a + static_cast<double>(waves) * (kb_per * a + epi_cost * bn / 256.0);
+        if (sp > 1) cost += 3.0 + 0.058 * (sp * 4.0 + 4.0) * M * N / 1.0e6;
         if (cost < best.cost * 0.999) best = {pair, bn, sp, cost};
       }
     }
@@ -184,6 +185,7 @@ extern "C" int vy_gemm_poisoned(void) {
   int* f = poison_flag();
   int v = -1;
   if (!f || cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (v != 0) cudaMemset(f, 0, sizeof(int));  // reading a raised flag lowers it again
   return v;
 }
 
@@ -289,23 +291,43 @@ extern "C" int vy_gemm(const VyGemm* p) {
   // CTA-pair kernels (cta_group::2): bf16, at least two m-tiles, row-major result. Both flavours are scored by the time
   // model and the cheaper one runs; VY_GEMM_PAIR=0 / 1 pins the flavour.
   static const int pair_env = getenv("VY_GEMM_PAIR") ? atoi(getenv("VY_GEMM_PAIR")) : -1;
-  const int pair_pin = g_force_pair >= 0 ? g_force_pair : pair_env;
   const bool pair_ok = p->in_dtype == VY_BF16 && p->M > 128 && p->N >= 128 && !p->transposed_out;
-  const double epi_cost = p->act == VY_ACT_GELU_ERF || p->act == VY_ACT_GELU_TANH ? 3.4
-                          : (p->act == VY_ACT_DGELU_ERF || p->act == VY_ACT_DGELU_TANH ? 8.6 : 2.4);
-  Tiling tl = choose_tiling(p->M, p->N, num_kb, p->a_mn_major || p->b_mn_major, p->b_mn_major != 0, p->epi == VY_EPI_QKV_ROPE,
-                            epi_cost, max_splits, pair_ok && pair_pin == 1 ? 1 : 0, pair_ok && pair_pin != 0 ? 1 : 0);
+  // precedence: development override (vy_gemm_tune_override) > environment > the caller's hint > the time model
+  int pair_pin = g_force_pair >= 0 ? g_force_pair : pair_env;
+  if (pair_pin < 0 && p->hint_flavour == 1) pair_pin = 0;
+  if (pair_pin < 0 && p->hint_flavour == 2 && pair_ok) pair_pin = 1;
+  const bool mn_major = p->a_mn_major || p->b_mn_major;
+  const bool qkv = p->epi == VY_EPI_QKV_ROPE;
+  const double epi_cost = p->act == VY_ACT_GELU_ERF || p->act == VY_ACT_GELU_TANH ? 3.7
+                          : (p->act == VY_ACT_DGELU_ERF || p->act == VY_ACT_DGELU_TANH ? 6.2 : 2.5);
+  Tiling tl = choose_tiling(p->M, p->N, num_kb, mn_major, p->b_mn_major != 0, qkv, epi_cost, max_splits,
+                            pair_ok && pair_pin == 1 ? 1 : 0, pair_ok && pair_pin != 0 ? 1 : 0);
   const bool pair = tl.pair != 0;
   static const int force_bn_env = getenv("VY_GEMM_FORCE_BN") ? atoi(getenv("VY_GEMM_FORCE_BN")) : 0;  // development: pin the tile width
-  const int force_bn = g_force_bn ? g_force_bn : force_bn_env;
-  int bn = force_bn ? force_bn : tl.bn;
+  int bn = tl.bn;
+  if (g_force_bn || force_bn_env) {
+    bn = g_force_bn ? g_force_bn : force_bn_env;
+  } else if (p->hint_bn) {
+    const int hb = p->hint_bn;
+    const bool known = hb == 32 || hb == 64 || hb == 128 || hb == 192 || hb == 256;
+    const bool fits = (!mn_major || hb >= 128) && (!qkv || hb >= 64) && (!pair || hb >= 128) &&
+                      !(pair && p->b_mn_major && hb == 192) && (hb == 32 || hb / 2 < p->N);
+    if (known && fits) {
+      bn = hb;
+      if (p->hint_splits == 0) tl.splits = 1;  // the model's split belonged to the model's width
+    }
+  }
   if (pair && bn < 128) bn = 128;
   if (pair && p->b_mn_major && bn == 192) bn = 256;
+  auto split_ok = [&](int sp) {
+    return sp >= 1 && sp <= max_splits && (sp == 1 || static_cast<long long>(sp - 1) * ((num_kb + sp - 1) / sp) < num_kb);
+  };
   if (g_force_splits > 0) {
-    VY_CHECK_ARG(g_force_splits <= max_splits, "vy_gemm: forced split %d > %d allowed here", g_force_splits, max_splits);
-    VY_CHECK_ARG(static_cast<long long>(g_force_splits - 1) * ((num_kb + g_force_splits - 1) / g_force_splits) < num_kb,
-                 "vy_gemm: forced split %d leaves an empty slab", g_force_splits);
+    VY_CHECK_ARG(split_ok(g_force_splits), "vy_gemm: forced split %d not possible here (max %d, %d k-blocks)", g_force_splits,
+                 max_splits, num_kb);
     tl.splits = g_force_splits;
+  } else if (p->hint_splits > 0 && split_ok(p->hint_splits)) {
+    tl.splits = p->hint_splits;
   }
   g.k_splits = tl.splits;
   g.kb_per_split = (num_kb + tl.splits - 1) / tl.splits;

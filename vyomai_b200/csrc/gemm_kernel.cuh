@@ -228,6 +228,9 @@ __device__ __forceinline__ void epilogue_linear_general(const GemmDev& g, uint32
   constexpr int WC = BN >= 64 ? BN / 2 : BN;  // columns per warp
   constexpr int NCH = WC / 32;
   if (BN < 64 && half) {  // narrow tiles: one warp per lane quarter does all the columns
+    // an idle warp still arrives once per tile, and only once the tile exists: arriving unconditionally would let it run
+    // ahead and complete a LATER phase of the barrier together with the working warps' arrivals for this one
+    mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
     release_acc(tmem_empty_bar, lane);
     return;
   }
@@ -269,6 +272,28 @@ __device__ __forceinline__ void store_ragged8(__nv_bfloat16* dst, const uint4& v
     if (k < n) dst[k] = e[k];
 }
 
+// bias[col .. col + 8) as floats, straight from global memory: every lane reads the same 16 / 32 bytes (one L1
+// broadcast), so the fast epilogues need neither a staged copy of the tile's bias nor the CTA-wide barrier behind it
+__device__ __forceinline__ void load_bias8(const GemmDev& g, int col, float (&bb)[8]) {
+  if (!g.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = 0.f;
+  } else if (col + 8 <= g.N) {
+    if (g.bias_dtype == VY_BF16) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.bias) + col));
+      unpack8_bf16(raw, bb);
+    } else {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.bias) + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.bias) + col + 4));
+      bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+      bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = col + j < g.N ? ld_as_float(g.bias, g.bias_dtype, col + j) : 0.f;
+  }
+}
+
 template <int BN, int MODE, bool TMA>
 __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half,
                                                      int lane, const float* bias_s, uint64_t* tfull_bar, uint32_t tfull_phase,
@@ -276,7 +301,10 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
                                                      const CUtensorMap* tma_out, const CUtensorMap* tma_aux) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;
   constexpr int NCH = WC / 32;
-  if (BN < 64 && half) {
+  if (BN < 64 && half) {  // narrow tiles: one warp per lane quarter does all the columns
+    // an idle warp still arrives once per tile, and only once the tile exists: arriving unconditionally would let it run
+    // ahead and complete a LATER phase of the barrier together with the working warps' arrivals for this one
+    mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
     release_acc(tmem_empty_bar, lane);
     return;
   }
@@ -336,12 +364,11 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
     }
     const int nvalid = g.N - (gc0 + c * 32);
     if (nvalid <= 0) return;
-    const float* bs = bias_s + wcol0 + c * 32;
     uint8_t* srow = stg + lane * 64;
     if (TMA) {
       // the buffer about to be overwritten must have been read by its bulk store: the out buffers alternate per chunk,
       // so only the store before the last has to be done — except with GELU + aux, where both buffers are used every chunk
-      if (lane == 0) {
+      if (elect_one_sync()) {  // the lane that issued (and committed) the bulk stores: the same one is elected every time
         if (save_aux) tma_store_wait_read<0>();
         else tma_store_wait_read<1>();
       }
@@ -349,10 +376,8 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
     }
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
-      float x[8];
-      const float4 b0 = *reinterpret_cast<const float4*>(bs + j4 * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(bs + j4 * 8 + 4);
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float x[8], bb[8];
+      load_bias8(g, gc0 + c * 32 + j4 * 8, bb);
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(raw[j4 * 8 + j]) + bb[j];
       if (MODE == EPI_GELU) {
@@ -383,7 +408,7 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
       // [32 rows x 32 cols] bf16 box, SWIZZLE_64B == the staging swizzle; rows >= M / columns >= N are clipped by TMA
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one_sync()) {
         tma_store_2d(tma_out, stg, gc0 + c * 32, m0 + q * 32);
         if (save_aux) tma_store_2d(tma_aux, stage + GEMM_STAGE_OUT, gc0 + c * 32, m0 + q * 32);
         tma_store_commit();
@@ -465,7 +490,10 @@ __device__ __forceinline__ void epilogue_splitk(const GemmDev& g, uint32_t tmem_
                                                 int split, uint64_t* tfull_bar, uint32_t tfull_phase, uint32_t tmem_empty_bar) {
   constexpr int WC = BN >= 64 ? BN / 2 : BN;
   constexpr int NCH = WC / 32;
-  if (BN < 64 && half) {
+  if (BN < 64 && half) {  // narrow tiles: one warp per lane quarter does all the columns
+    // an idle warp still arrives once per tile, and only once the tile exists: arriving unconditionally would let it run
+    // ahead and complete a LATER phase of the barrier together with the working warps' arrivals for this one
+    mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
     release_acc(tmem_empty_bar, lane);
     return;
   }
@@ -683,7 +711,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast through a shuffle so that the compiler knows the warp index (and everything derived from it: role, TMEM
+  // lane quarter, staging buffer, store coordinates) is warp-uniform and keeps it in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned base
 
@@ -747,16 +777,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0) {
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
     {
-      uint32_t it = 0;
+      uint32_t it = 0, s = 0, ph = 0;  // k-blocks issued, ring position and its phase bit
       for (int unit = worker; unit < num_units; unit += nworkers) {
         const int tile = unit % num_tiles;
         const int m0 = ((tile / n_tiles) * m_mul + rank) * BM;  // may lie beyond M for the odd m-tile of the last pair: TMA zero-fills
         const int n0 = (tile % n_tiles) * BN + rank * BN_CTA;   // first B row this CTA stages
         const int kb0 = (unit / num_tiles) * g.kb_per_split;
         const int kb1 = min(num_kb, kb0 + g.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int kb = kb0; kb < kb1; ++kb, ++it, ph ^= (s + 1 == STAGES), s = (s + 1 == STAGES) ? 0 : s + 1) {
           mbar_wait_soft(&empty_bar[s], ph ^ 1, g.poison);
           if (elect_one_sync()) {
             uint8_t* a_dst = sA + s * Cfg::A_BYTES;
@@ -807,33 +835,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // ===================== MMA issuer (whole warp, one elected lane issues; in a pair only the leader's) =====================
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc(Cfg::FMT, PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      uint32_t it = 0;
+      // The issue loop is kept to a handful of instructions per MMA: it shares its SM sub-partition's issue slots with
+      // two epilogue warps, and at ~95 instructions per k-block (descriptors rebuilt from addresses, % and / for the
+      // ring position) the loop itself, not the tensor pipe, set the pace of tiles narrower than 256. The descriptors of
+      // stage 0 are built once; a stage adds its byte offset >> 4 to the 14-bit address field (the ring stays inside the
+      // field's 256 KB, so nothing carries into the neighbouring fields) and a k-step adds a constant.
+      const uint64_t a_desc0 = A_MN ? make_smem_desc_sw128(smem_u32(sA), Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                                    : make_smem_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = B_MN ? make_smem_desc_sw128(smem_u32(sB), Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                                    : make_smem_desc_sw128(smem_u32(sB), 16, 1024);
+      const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), b_lo0 = static_cast<uint32_t>(b_desc0);
+      constexpr uint32_t A_KSTEP = (A_MN ? Cfg::UMMA_K * 128 : 32) >> 4;  // one UMMA_K step inside a stage, in 16-byte units
+      constexpr uint32_t B_KSTEP = (B_MN ? Cfg::UMMA_K * 128 : 32) >> 4;
+      uint32_t s = 0, ph = 0;  // ring position and its phase bit
       uint32_t local = 0;
       for (int unit = worker; unit < num_units; unit += nworkers, ++local) {
         const int kb0 = (unit / num_tiles) * g.kb_per_split;
-        const int kb1 = min(num_kb, kb0 + g.kb_per_split);
+        const int nkb = min(num_kb, kb0 + g.kb_per_split) - kb0;
         const uint32_t acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         VY_TRACE(1, local, 0);
-        mbar_wait_soft<PAIR>(&tempty_bar[acc], acc_ph ^ 1, g.poison);
+        mbar_wait_soft(&tempty_bar[acc], acc_ph ^ 1, g.poison);
         tc_fence_after();
         VY_TRACE(1, local, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait_soft<PAIR>(&full_bar[s], ph, g.poison);
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait_soft(&full_bar[s], ph, g.poison);  // (cta-scope acquire: a cluster-scope one invalidates L1 on every k-block)
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
           if (elect_one_sync()) {
+            const uint32_t a_lo = a_lo0 + s * (Cfg::A_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + s * (B_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
-              const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                                       : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-              const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * Cfg::UMMA_K * 128, Cfg::MN_BOX_BYTES, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                                       : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-              const uint32_t accum = kb != kb0 || k != 0;
+              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * A_KSTEP);
+              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * B_KSTEP);
+              const uint32_t accum = (i | k) != 0;
               if constexpr (PAIR) {
                 if constexpr (sizeof(TIn) == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum);
                 else umma_tf32_pair(d_tmem, ad, bd, idesc, accum);
@@ -844,13 +881,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             if constexpr (PAIR) {
               umma_commit_pair(&empty_bar[s], 3);
-              if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc], 3);
+              if (i == nkb - 1) umma_commit_pair(&tfull_bar[acc], 3);
             } else {
               umma_commit(&empty_bar[s]);
-              if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+              if (i == nkb - 1) umma_commit(&tfull_bar[acc]);
             }
           }
           __syncwarp();
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
         VY_TRACE(1, local, 2);
       }
@@ -864,7 +905,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint8_t* stage = epi_stage + e * 2 * GEMM_STAGE_OUT;
     // which fused fast epilogue applies (-1: the general one)
     int fast_mode = -1;
-    if (g.epi == VY_EPI_LINEAR && !g.transposed_out && g.vec_ok && g.out_dtype == VY_BF16 && !g.addend2) {
+    if (g.epi == VY_EPI_LINEAR && !g.transposed_out && g.vec_ok && g.out_dtype == VY_BF16 && !g.addend2 &&
+        (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) {
       const bool aux16 = !g.aux || g.aux_dtype == VY_BF16;
       const bool n8 = (g.N & 7) == 0;  // the prefetched row operand is read in 8-column vectors
       if (g.act == VY_ACT_NONE) fast_mode = !g.addend ? EPI_PLAIN : ((g.addend_dtype == VY_BF16 && n8) ? EPI_ADD : -1);
@@ -882,7 +924,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // where this warp announces that it has drained the accumulator: the (leader's) MMA thread waits there
       const uint32_t tempty_addr = PAIR ? mapa_u32(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
       VY_TRACE(2 + e, local, 0);
-      if (!g.transposed_out) {
+      if (!g.transposed_out && g.k_splits <= 1 && fast_mode < 0) {  // the fast epilogues read the bias straight from global
         for (int j = et; j < BN; j += GEMM_EPI_WARPS * 32) {
           const int col = n0 + j;
           bs[j] = (g.bias && col < g.N) ? ld_as_float(g.bias, g.bias_dtype, col) : 0.f;
@@ -935,7 +977,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       VY_TRACE(2 + e, local, 3);
     }
-    if (g.tma_store && lane == 0) tma_store_wait<0>();  // the staged tiles must have left smem (and landed) before exit
+    if (g.tma_store && elect_one_sync()) tma_store_wait<0>();  // the staged tiles must have left smem (and landed) before exit
   }
 
   tc_fence_before();

@@ -10,7 +10,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, gemm_tune
 from ._lib import CONSTS as C
 
 _DT = {torch.float32: C["VY_F32"], torch.bfloat16: C["VY_BF16"]}
@@ -62,7 +62,7 @@ def _major(t: torch.Tensor, what: str):
 
 
 _SPLITK_WS = {}
-SPLITK_WORKSPACE_BYTES = 64 << 20
+SPLITK_WORKSPACE_BYTES = 128 << 20
 
 
 def _splitk_workspace(device: torch.device) -> torch.Tensor:
@@ -153,6 +153,12 @@ def gemm(
     else:
         kw.update(M=N, N=M, K=K, A=b.data_ptr(), lda=ldb, a_mn_major=b_mn, B=a.data_ptr(), ldb=lda,
                   b_mn_major=a_mn, transposed_out=1)
+    if gemm_tune.ENABLED:
+        key = ("gemm", kw["M"], kw["N"], K, kw["in_dtype"], kw["a_mn_major"], kw["b_mn_major"], kw["transposed_out"], act,
+               bias is not None, addend is not None, addend is not None and addend.data_ptr() == out.data_ptr(),
+               addend2 is not None, aux is not None, out.dtype, allow_split_k, out_row_group, addend_row_mod, out_scale != 1.0)
+        saves_aux = aux is not None and act in ("gelu", "gelu_tanh")
+        kw.update(gemm_tune.hints(key, kw, [("out", out), ("aux", aux if saves_aux else None)], a.device))
     _lib.call("vy_gemm", "VyGemm", **kw)
     return out
 
@@ -190,8 +196,7 @@ def qkv_rope_gemm(
         raise _lib.VyomError("qkv_rope_gemm: k_out and v_out must share a dtype")
     if rope_cos is not None and (rope_cos.dtype != torch.float32 or not rope_cos.is_contiguous()):
         raise _lib.VyomError("qkv_rope_gemm: rope tables must be contiguous float32")
-    _lib.call(
-        "vy_gemm", "VyGemm",
+    kw = dict(
         M=M, N=N, K=K, in_dtype=_dt(x), A=x.data_ptr(), lda=lda, a_mn_major=a_mn,
         B=w.data_ptr(), ldb=ldb, b_mn_major=b_mn,
         epi=C["VY_EPI_QKV_ROPE"], bias=_ptr(bias), bias_dtype=_dt(bias) if bias is not None else 0,
@@ -203,6 +208,11 @@ def qkv_rope_gemm(
         v_out=v_out.data_ptr(), v_sb=v_out.stride(0), v_sh=v_out.stride(1), v_sl=v_out.stride(2),
         kv_out_dtype=_dt(k_out), stream=_stream(),
     )
+    if gemm_tune.ENABLED:
+        key = ("qkv", M, N, K, kw["in_dtype"], a_mn, b_mn, bias is not None, rope_cos is not None, n_q_heads, n_kv_heads,
+               tokens_per_seq, q_out.dtype, k_out.dtype)
+        kw.update(gemm_tune.hints(key, kw, [("q_out", q_out), ("k_out", k_out), ("v_out", v_out)], x.device))
+    _lib.call("vy_gemm", "VyGemm", **kw)
 
 
 def add_layernorm(
