@@ -214,3 +214,24 @@ def test_gemm_tuner_candidates_respect_kernel_constraints():
     assert {x["hint_splits"] for x in c} == {1, 2, 3, 4}
     # decode: swap-AB, N = 32 rows of the batch -> one 32-wide tile, nothing to choose
     assert len(T._candidates(dict(base, M=768, N=32, transposed_out=1))) == 1
+
+
+def test_gradient_buckets_hold_whole_parameters():
+    """Overlapped all-reduce launches a bucket once every parameter STARTING in it has its gradient: that is only sound
+    if no parameter's tail lies in another bucket (trainer.GradExchange with param_starts)."""
+    from vyomai_b200.trainer import GradExchange
+    sizes = [40, 700, 16, 16, 250, 3000, 8, 120, 64]  # one parameter far larger than a bucket, several smaller
+    starts, o = [], 0
+    for n in sizes:
+        starts.append(o)
+        o += n
+    g = torch.zeros(o)
+    ex = GradExchange(g, bucket_elems=300, param_starts=starts)
+    assert ex.buckets[0][1] == o and ex.buckets[-1][0] == 0
+    assert all(a[0] == b[1] for a, b in zip(ex.buckets, ex.buckets[1:]))          # contiguous, walked from the end
+    assert all(s in starts for s, _ in ex.buckets)                                  # every boundary is a parameter start
+    for st, n in zip(starts, sizes):                                                # so each parameter sits in one bucket
+        b = ex.bucket_of(st)
+        assert ex.buckets[b][0] <= st and st + n <= ex.buckets[b][1]
+    small = [b for b in ex.buckets if b[1] - b[0] < 300]
+    assert len(small) <= 1 and (not small or small[0][0] == 0)                     # only the last-walked bucket may be short

@@ -413,11 +413,20 @@ xent_kernel(int rows, int V, void* __restrict__ logits, long long ld, int dt, co
 // sum of squares of a flat gradient buffer -> one fp32 (atomic per CTA), then AdamW that reads the
 // clip coefficient from device memory (no host sync): g' = g * min(1, max_norm / (norm + 1e-6)).
 // ------------------------------------------------------------------------------------------
+// Deterministic: every block stores its partial sum, the block that finishes last adds the partials up in index order
+// and updates *out once — two data-parallel replicas that hold identical gradients therefore compute bit-identical clip
+// coefficients and stay in lock step (a float atomicAdd per block would make the order, hence the rounding, vary).
+// The partial / ticket buffers are shared by all launches: vy_sqnorm calls must not overlap on different streams.
+constexpr int SQNORM_MAX_BLOCKS = 4096;
+static __device__ float sqnorm_partials[SQNORM_MAX_BLOCKS];
+static __device__ unsigned int sqnorm_ticket;
+
 __global__ void __launch_bounds__(256)
 sqnorm_kernel(long long n, const void* __restrict__ g, int dt, float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_red[8];
+  __shared__ bool s_last;
   float a = 0.f;
   const long long nvec = n >> 3;
   for (long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi < nvec;
@@ -439,7 +448,22 @@ sqnorm_kernel(long long n, const void* __restrict__ g, int dt, float* __restrict
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s_red[w];
-    atomicAdd(out, t);
+    sqnorm_partials[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(&sqnorm_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {  // fixed-order tree over the partials: lane-strided sums, then the warp butterfly
+    __threadfence();
+    float t = 0.f;
+    if (threadIdx.x < 32) {
+      for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 32) t += *const_cast<volatile float*>(&sqnorm_partials[i]);
+      t = warp_sum(t);
+      if (threadIdx.x == 0) {
+        *out += t;
+        sqnorm_ticket = 0;
+      }
+    }
   }
 }
 
@@ -681,7 +705,7 @@ extern "C" int vy_softmax_xent(const VyXent* p) {
 extern "C" int vy_sqnorm(int64_t n, const void* g, int dtype, float* out, void* stream) {
   VY_NEED_DEVICE("vy_sqnorm");
   VY_CHECK_ARG(n > 0 && g && out && dtype_ok(dtype) && aligned16(g), "vy_sqnorm: bad arguments");
-  VY_CUDA_OK(launch_kernel(sqnorm_kernel, dim3(ew_grid(n, 8 * 256 * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), n, g, dtype, out));
+  VY_CUDA_OK(launch_kernel(sqnorm_kernel, dim3(min(ew_grid(n, 8 * 256 * 4), SQNORM_MAX_BLOCKS)), dim3(256), 0, static_cast<cudaStream_t>(stream), n, g, dtype, out));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -15,6 +15,7 @@ Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1 `main()`) is rebuilt B20
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Set, Tuple
 
 import torch
@@ -89,19 +90,33 @@ class FlatParams:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
 
 
+_DP_TRACE = os.environ.get("VY_DP_TRACE", "0") != "0"  # development: log every gradient-ready event and bucket launch
+
+
 class GradExchange:
     """Bucketed sum all-reduce of one flat gradient buffer. Buckets are contiguous slices walked from
     the END of the buffer (the order backward fills it); on CUDA the collectives run on a side
     stream so they overlap the rest of backward. Works with any torch.distributed backend (NCCL on
     the B200 box, gloo in the CPU tests)."""
 
-    def __init__(self, flat_grad: torch.Tensor, bucket_elems: int):
+    def __init__(self, flat_grad: torch.Tensor, bucket_elems: int, param_starts: Optional[List[int]] = None):
+        """`param_starts`: offsets at which parameters begin in the flat buffer. Bucket boundaries then snap to them (a
+        bucket = whole parameters, at least `bucket_elems` elements unless a single parameter is larger), so that
+        "every parameter that starts in the bucket is ready" means every element of the bucket has been written — with
+        free-running boundaries the tail of a parameter lying in the next bucket would be reduced before backward has
+        produced it."""
         self.grad = flat_grad
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.buckets: List[Tuple[int, int]] = []
+        cuts = sorted(set(param_starts)) if param_starts else None
         end = flat_grad.numel()
         while end > 0:
             start = max(0, end - bucket_elems)
+            if cuts is not None:
+                import bisect
+                i = bisect.bisect_right(cuts, start) - 1  # the last parameter start at or before the free-running boundary
+                start = cuts[i] if i >= 0 else 0
+                assert start < end
             self.buckets.append((start, end))
             end = start
         self._launched: Set[int] = set()
@@ -157,10 +172,11 @@ class Trainer:
         self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
         per = max(1, int(bucket_mb * 1024 * 1024 / self.fp.grad.element_size()))
-        self.exchange = GradExchange(self.fp.grad, per)
+        self.exchange = GradExchange(self.fp.grad, per, param_starts=list(self.fp.offsets))
         self.world = self.exchange.world
         self.overlap = overlap and self.world > 1
         self._pending: Dict[int, int] = {}
+        self._ready_ids: Set[int] = set()
         self._bucket_of: Dict[int, int] = {}
         self._bucket_size: List[int] = [0] * len(self.exchange.buckets)
         for p, o in zip(self.fp.params, self.fp.offsets):
@@ -225,14 +241,26 @@ class Trainer:
         self.grad_overwrite = False
 
     def _on_grad(self, p: nn.Parameter) -> None:
+        # A parameter is counted once per step: the kernels that write a gradient straight into the flat buffer report
+        # it by hand (autograd_train._ready), and autograd's post-accumulate hook ALSO fires for such a parameter when
+        # its Function returns None for it — counted twice, a bucket would be reduced before its last writer has run.
+        if id(p) in self._ready_ids:
+            return
+        self._ready_ids.add(id(p))
         b = self._bucket_of[id(p)]
         self._pending[b] = self._pending.get(b, 0) + 1
+        if _DP_TRACE:
+            names = getattr(self, "_names", None) or {id(q): n for n, q in self.model.named_parameters()}
+            self._names = names
+            print(f"[dp-trace] ready {names.get(id(p), '?')} bucket {b} {self._pending[b]}/{self._bucket_size[b]}"
+                  f"{' -> all-reduce' if self._pending[b] == self._bucket_size[b] else ''}", flush=True)
         if self._pending[b] == self._bucket_size[b]:
             self.exchange.launch(b)
 
     def zero_grad(self) -> None:
         self.fp.zero_grad()
         self._pending = {}
+        self._ready_ids = set()
         self.exchange.begin_step()
 
     def optimizer_step(self) -> None:
@@ -254,6 +282,12 @@ class Trainer:
                 self.zero_grad()
                 loss = self._forward_backward(pixel_values, input_ids, attention_mask, labels_full)
                 if not bool(torch.isfinite(self.fp.grad).all()):
+                    import warnings
+                    names = {id(p): n for n, p in self.model.named_parameters()}
+                    bad = [f"{names.get(id(p), '?')}[{int((~torch.isfinite(p.grad)).sum())}/{p.numel()}]"
+                           for p in self.fp.params if not bool(torch.isfinite(p.grad).all())]
+                    warnings.warn("gradient overwrite mode switched off: after the poisoned first step these gradients still hold "
+                                  f"non-finite values: {bad[:6]}{' ...' if len(bad) > 6 else ''} (none listed = alignment padding)")
                     self._disable_grad_overwrite()  # some parameter is not written exactly once per step: accumulate instead
                     self.zero_grad()
                     loss = self._forward_backward(pixel_values, input_ids, attention_mask, labels_full)
