@@ -77,6 +77,21 @@ add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void
 // column accumulators stay in registers: dgamma += dy*xhat, dbeta += dy and — when asked — dbias += dx (the bias
 // gradient of the Linear whose output fed this LayerNorm: attention.py:69-71, ffn.py:37-39, saving a separate
 // column-sum pass over dx). They are combined across the CTA's warps in smem and written to partials[cta][3][H].
+// Row ring of the single-pass backward: every warp streams its rows of dy and s through LN_RING slots of shared memory
+// with 1-D bulk copies (cp.async.bulk, mbarrier tx-count), issued LN_RING rows ahead by one lane. In-flight bytes per SM
+// = 8 warps x LN_RING rows x 2 tensors x H x sizeof — what an HBM-bound kernel with one warp per row needs to cover the
+// memory latency (registers only held ONE row ahead: 2.0 TB/s; see profiles/). The ring is dead when the column
+// partials are staged, so `red` aliases it.
+template <bool IO_BF16>
+struct LnRing {
+  static constexpr int SLOTS = IO_BF16 ? 4 : 2;
+};
+__device__ __forceinline__ void bulk_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <int NV, bool IO_BF16>
 __global__ void __launch_bounds__(NORM_WARPS * 32, 1)
 add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s,
@@ -84,11 +99,22 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
                          const float* __restrict__ rstd, void* __restrict__ dx, int want_dbias, float* __restrict__ partials) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float red[];  // [NORM_WARPS][3][H]
+  extern __shared__ __align__(128) float red[];  // [NORM_WARPS][3][H] at the end; the row ring before that
   constexpr int IO_DT = IO_BF16 ? VY_BF16 : VY_F32;
   constexpr int RAW = IO_BF16 ? 1 : 2;  // uint4 per 8 elements
+  constexpr int D = LnRing<IO_BF16>::SLOTS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H >> 3;
+  const uint32_t row_bytes = static_cast<uint32_t>(H) * (IO_BF16 ? 2u : 4u);
+  // ring layout: [warp][slot][dy row | s row], then the mbarriers
+  uint8_t* ring = reinterpret_cast<uint8_t*>(red) + static_cast<size_t>(warp) * D * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + static_cast<size_t>(NORM_WARPS) * D * 2 * row_bytes) + warp * D;
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) mbar_init(&bars[d], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
   float g[NV][8], dg[NV][8], db[NV][8], dbi[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -98,67 +124,118 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
     if (vi < nvec) ld8_as_float(gamma, p_dt, vi * 8, g[i]);
   }
   const int stride = gridDim.x * NORM_WARPS;
-  uint4 ndy[NV][RAW], ns[NV][RAW];  // next row, raw
-  auto fetch = [&](int row) {
-    const uint4* pd = reinterpret_cast<const uint4*>(dy) + static_cast<long long>(row) * nvec * RAW;
-    const uint4* ps = reinterpret_cast<const uint4*>(s) + static_cast<long long>(row) * nvec * RAW;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-#pragma unroll
-        for (int k = 0; k < RAW; ++k) {
-          ndy[i][k] = pd[vi * RAW + k];
-          ns[i][k] = ps[vi * RAW + k];
-        }
-      }
+  float mu_r[D], rs_r[D];  // per-row statistics of the rows in flight (loaded when the row's copies are issued)
+  auto issue = [&](int d, int row) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[d], 2 * row_bytes);
+      uint8_t* slot = ring + static_cast<size_t>(d) * 2 * row_bytes;
+      bulk_load_row(slot, reinterpret_cast<const uint8_t*>(dy) + static_cast<size_t>(row) * row_bytes, row_bytes, &bars[d]);
+      bulk_load_row(slot + row_bytes, reinterpret_cast<const uint8_t*>(s) + static_cast<size_t>(row) * row_bytes, row_bytes, &bars[d]);
     }
   };
-  int row = blockIdx.x * NORM_WARPS + warp;
-  if (row < rows) fetch(row);
-  for (; row < rows; row += stride) {
-    const long long base = static_cast<long long>(row) * H;
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NV][8], dyv[NV][8];
+  const int first = blockIdx.x * NORM_WARPS + warp;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (lane + i * 32 < nvec) {
-        ld8_as_float(&ndy[i][0], IO_DT, 0, dyv[i]);  // unpack the prefetched registers
-        ld8_as_float(&ns[i][0], IO_DT, 0, xh[i]);
-      }
+  for (int d = 0; d < D; ++d) {
+    const int row = first + d * stride;
+    mu_r[d] = rs_r[d] = 0.f;
+    if (row < rows) {
+      issue(d, row);
+      mu_r[d] = mean[row];
+      rs_r[d] = rstd[row];
     }
-    if (row + stride < rows) fetch(row + stride);
-    float c1 = 0.f, c2 = 0.f;
+  }
+  // Two rows per step: their dependency chains (unpack -> row sums -> warp butterflies -> dx) are independent, and with
+  // only two warps per SM sub-partition it is this instruction-level parallelism, not more loads in flight, that fills
+  // the issue slots (one row per step: 18 us per call, latency-bound).
+  uint32_t ph = 0;
+  for (int base = first; base < rows; base += D * stride, ph ^= 1) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (lane + i * 32 < nvec) {
+    for (int d = 0; d < D; d += 2) {
+      const int row0 = base + d * stride;
+      if (row0 >= rows) break;
+      const int row1 = row0 + stride;
+      const bool two = row1 < rows;
+      const float mu[2] = {mu_r[d], mu_r[d + 1]}, rs[2] = {rs_r[d], rs_r[d + 1]};
+      float xh[2][NV][8], dyv[2][NV][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xh[i][j] - mu) * rs;
-          const float t = dyv[i][j] * g[i][j];
-          c1 += t;
-          c2 += t * xh[i][j];
-          dg[i][j] += dyv[i][j] * xh[i][j];
-          db[i][j] += dyv[i][j];
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        mbar_wait(&bars[d + u], ph);
+        const uint4* sd = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(d + u) * 2 * row_bytes);
+        const uint4* ss = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(d + u) * 2 * row_bytes + row_bytes);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int vi = lane + i * 32;
+          if (vi < nvec) {
+            uint4 rd[RAW], rx[RAW];
+#pragma unroll
+            for (int k = 0; k < RAW; ++k) {
+              rd[k] = sd[vi * RAW + k];
+              rx[k] = ss[vi * RAW + k];
+            }
+            ld8_as_float(&rd[0], IO_DT, 0, dyv[u][i]);
+            ld8_as_float(&rx[0], IO_DT, 0, xh[u][i]);
+          }
         }
       }
-    }
-    c1 = warp_sum(c1) / H;
-    c2 = warp_sum(c2) / H;
+      __syncwarp();  // every lane has read the slots: refill them with the rows LN_RING steps ahead
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = rs * (dyv[i][j] * g[i][j] - c1 - xh[i][j] * c2);
-          dbi[i][j] += o[j];
+      for (int u = 0; u < 2; ++u) {
+        const int next = row0 + u * stride + D * stride;
+        if (next < rows) {
+          issue(d + u, next);
+          mu_r[d + u] = mean[next];
+          rs_r[d + u] = rstd[next];
         }
-        st8_from_float(dx, IO_DT, base + vi * 8, o);
+      }
+      float c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if (lane + i * 32 < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              xh[u][i][j] = (xh[u][i][j] - mu[u]) * rs[u];
+              const float t = dyv[u][i][j] * g[i][j];
+              c1[u] += t;
+              c2[u] += t * xh[u][i][j];
+              dg[i][j] += dyv[u][i][j] * xh[u][i][j];
+              db[i][j] += dyv[u][i][j];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {  // the four butterflies interleaved
+        c1[0] += __shfl_xor_sync(0xffffffffu, c1[0], o);
+        c2[0] += __shfl_xor_sync(0xffffffffu, c2[0], o);
+        c1[1] += __shfl_xor_sync(0xffffffffu, c1[1], o);
+        c2[1] += __shfl_xor_sync(0xffffffffu, c2[1], o);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const float m1 = c1[u] / H, m2 = c2[u] / H;
+        const long long rbase = static_cast<long long>(row0 + u * stride) * H;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int vi = lane + i * 32;
+          if (vi < nvec) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[j] = rs[u] * (dyv[u][i][j] * g[i][j] - m1 - xh[u][i][j] * m2);
+              dbi[i][j] += o[j];
+            }
+            st8_from_float(dx, IO_DT, rbase + vi * 8, o);
+          }
+        }
       }
     }
   }
+  __syncthreads();  // all rings are drained (every issued row was consumed): the staging below reuses their memory
   float* my = red + static_cast<size_t>(warp) * 3 * H;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -405,7 +482,10 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   const int nv = (p->H + 255) / 256;
   int grid = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
   if (grid > num_sms()) grid = num_sms();  // persistent: one CTA per SM (partials hold up to 2 * SMs * 2 * H floats)
-  const size_t smem = static_cast<size_t>(NORM_WARPS) * 3 * p->H * sizeof(float);
+  const size_t red_bytes = static_cast<size_t>(NORM_WARPS) * 3 * p->H * sizeof(float);
+  const size_t ring_slots = p->io_dtype == VY_BF16 ? LnRing<true>::SLOTS : LnRing<false>::SLOTS;
+  const size_t ring_bytes = static_cast<size_t>(NORM_WARPS) * ring_slots * 2 * p->H * dtype_size(p->io_dtype) + NORM_WARPS * ring_slots * 8;
+  const size_t smem = red_bytes > ring_bytes ? red_bytes : ring_bytes;
   cudaStream_t st = static_cast<cudaStream_t>(p->stream);
 #define VY_LN_BWD2(NV, BF)                                                                            \
   do {                                                                                               \
