@@ -7,10 +7,12 @@ operands, with every buffer the GEMM WRITES redirected to scratch so that an acc
 twice — and from then on passes the winner through VyGemm.hint_*. Nothing is tuned while a CUDA graph is being
 captured (the capture gets the cached winner or, for a signature never seen eagerly, the model's choice).
 
-VY_GEMM_AUTOTUNE=0 turns this off.
+VY_GEMM_AUTOTUNE=0 turns this off. VY_GEMM_TUNE_CACHE=<file.json> keeps the winners across processes (read at import,
+appended to after every tuned signature): a second run — a profiler pass, a restarted job — launches no tuning kernels.
 """
 from __future__ import annotations
 
+import json
 import os
 from typing import Dict, List, Optional, Tuple
 
@@ -19,7 +21,15 @@ import torch
 from . import _lib
 
 ENABLED = os.environ.get("VY_GEMM_AUTOTUNE", "1") != "0"
+CACHE_FILE = os.environ.get("VY_GEMM_TUNE_CACHE") or None
 _CACHE: Dict[tuple, Dict[str, int]] = {}
+_FILE_CACHE: Dict[str, Dict[str, int]] = {}
+if CACHE_FILE and os.path.exists(CACHE_FILE):
+    try:
+        with open(CACHE_FILE) as _f:
+            _FILE_CACHE = json.load(_f)
+    except (OSError, ValueError):
+        _FILE_CACHE = {}
 _FLUSH: Dict[torch.device, torch.Tensor] = {}
 MAX_SCRATCH_BYTES = 4 << 30
 LOG: List[tuple] = []  # (key, winner, us, model_us) of every signature tuned in this process
@@ -93,6 +103,9 @@ def hints(key: tuple, kw: dict, written: List[Tuple[str, Optional[torch.Tensor]]
     hit = _CACHE.get(key)
     if hit is not None:
         return hit
+    if repr(key) in _FILE_CACHE:
+        _CACHE[key] = _FILE_CACHE[repr(key)]
+        return _CACHE[key]
     if torch.cuda.is_current_stream_capturing() or _lib.TIMER is not None:
         return {}
     cands = _candidates(kw)
@@ -125,4 +138,11 @@ def hints(key: tuple, kw: dict, written: List[Tuple[str, Optional[torch.Tensor]]
     del keep
     _CACHE[key] = best
     LOG.append((key, best, best_us if best else model_us, model_us))
+    if CACHE_FILE:
+        _FILE_CACHE[repr(key)] = best
+        try:
+            with open(CACHE_FILE, "w") as f:
+                json.dump(_FILE_CACHE, f, indent=0)
+        except OSError:
+            pass
     return best
