@@ -194,7 +194,7 @@ def run_ours(args):
         model = VisionLanguageModel(TextCfg(), encoder=Vit(VitCfg()), pos_embedding_type="rope", attention_type="gqa")
     model = model.to(dev).to(torch.bfloat16).train()
     trainer = Trainer(model, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, use_graph=not args.no_graph,
-                      grad_overwrite=not args.no_grad_overwrite)
+                      grad_overwrite=not args.no_grad_overwrite, overlap=not args.no_overlap, bucket_mb=args.bucket_mb)
 
     B = PER_GPU_BATCH
     host = [synth_batch(B, 17 + 1000 * rank + i, True) for i in range(2)]
@@ -325,6 +325,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-grad-overwrite", action="store_true", help="zero + accumulate every gradient instead of overwrite mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of bucketed overlap")
+    ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient bucket size of the overlapped all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VY_ABI_VERSION 3
+#define VY_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VY_API __attribute__((visibility("default")))
@@ -357,6 +357,17 @@ typedef struct VyDecode {
   void* v_cache;
   int64_t cache_sb, cache_sh, cache_sl;
   int32_t cache_dtype;
+  /* continuous batching / paged cache (Examples/simple_vllm.ipynb cell 2: PagedKVManager, the slot_mapping write
+   * `k_cache[slots // block_size, slots % block_size] = k` and flash_attn_with_kvcache(cache_seqlens, block_table)):
+   *   seqlens     optional device int32 [B]: row b's context length = the position of its new token (wins over
+   *               start_pos / start_pos_ptr, which then only bound the kv-split); a negative entry skips the row.
+   *   block_table optional device int32 [B, max_blocks_per_seq]: the caches are then [num_blocks, block_size, n_kv, 64]
+   *               pools — cache_sb is the BLOCK stride, cache_sl the slot stride, cache_sh the head stride — and slot p
+   *               of row b lives in block block_table[b][p / block_size] at offset p % block_size. The new token is
+   *               appended there too; its block must already be in the table. */
+  const int32_t* seqlens;
+  const int32_t* block_table;
+  int32_t max_blocks_per_seq, block_size;
   void* out; /* [B, n_q * 64] */
   int64_t ld_out;
   int32_t out_dtype;

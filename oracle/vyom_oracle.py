@@ -480,3 +480,42 @@ def cross_entropy_shifted(logits: Tensor, labels: Tensor, ignore_index: int = -1
     lse = torch.logsumexp(lg, dim=-1)
     picked = lg.gather(1, lb.clamp(min=0)[:, None])[:, 0]
     return ((lse - picked) * keep).sum() / keep.sum().clamp(min=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Paged kv-cache decode (Examples/simple_vllm.ipynb cell 2)
+# ---------------------------------------------------------------------------------------------
+def paged_slots(block_table_row: Tensor, start: int, end: int, block_size: int) -> Tensor:
+    """Pool slots of token positions [start, end) of one sequence (notebook SequenceState.update_metadata:
+    `slot_mapping[idx] = block_table[idx // block_size] * block_size + idx % block_size`)."""
+    idx = torch.arange(start, end)
+    return block_table_row[idx // block_size].long() * block_size + idx % block_size
+
+
+def paged_decode_attention(q: Tensor, k_new: Tensor, v_new: Tensor, k_pool: Tensor, v_pool: Tensor, block_table: Tensor,
+                           ctx_lens: Tensor, block_size: int) -> Tensor:
+    """One decode step of the notebook's GroupedQueryAttention.forward with `is_decoding`: the new token's (already
+    rotated) k / raw v are written at `k_cache[slots // block_size, slots % block_size]`, then
+    flash_attn_with_kvcache(q, k_cache, v_cache, cache_seqlens, block_table, causal=True) attends, per sequence, over the
+    first cache_seqlens = ctx_len + 1 tokens of the blocks its block-table row names (flash-attn 2.8.3 semantics:
+    row b reads block block_table[b][p // block_size], offset p % block_size, for p < cache_seqlens[b]; a single query
+    with causal=True sees all of them). PARITY: UNPINNED by the reference (the notebook needs a GPU and flash-attn);
+    pinned here by the equivalence with the contiguous-cache decode (`sdpa` over the gathered rows), which IS pinned.
+      q [B, Hq, d]; k_new, v_new [B, Hkv, d]; pools [num_blocks, block_size, Hkv, d] (modified in place);
+      block_table [B, max_blocks] int; ctx_lens [B] = tokens already cached = position of the new token.
+    Returns [B, Hq, d]."""
+    B, Hq, d = q.shape
+    Hkv = k_new.shape[1]
+    out = torch.empty_like(q)
+    kf, vf = k_pool.view(-1, Hkv, d), v_pool.view(-1, Hkv, d)
+    for b in range(B):
+        n = int(ctx_lens[b])
+        slot = paged_slots(block_table[b], n, n + 1, block_size)
+        kf[slot] = k_new[b].to(kf.dtype)
+        vf[slot] = v_new[b].to(vf.dtype)
+        rows = paged_slots(block_table[b], 0, n + 1, block_size)
+        k = kf[rows].float().permute(1, 0, 2).unsqueeze(0)  # [1, Hkv, n + 1, d]
+        v = vf[rows].float().permute(1, 0, 2).unsqueeze(0)
+        k, v = repeat_kv(k, Hq // Hkv), repeat_kv(v, Hq // Hkv)
+        out[b] = sdpa(q[b].float().view(1, Hq, 1, d), k, v, None)[0, :, 0].to(q.dtype)
+    return out

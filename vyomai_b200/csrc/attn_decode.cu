@@ -1,4 +1,4 @@
-// vy_attn_decode: single-token (Sq == 1) attention over a contiguous kv-cache, HBM-bound.
+// vy_attn_decode: single-token (Sq == 1) attention over a contiguous or paged kv-cache, HBM-bound.
 //
 // One CTA per (kv-split, kv head, batch row). Fuses, for the new token, the half-split RoPE of q
 // and k, the kv-cache append at `start_pos`, and the attention over slots [0, start_pos] — with NO
@@ -33,7 +33,10 @@ struct DecodeDev {
   const float* rope_sin;
   void* kcache;
   void* vcache;
-  long long c_sb, c_sh, c_sl;  // element strides: batch, head, slot
+  long long c_sb, c_sh, c_sl;  // element strides: batch (paged: block), head, slot
+  const int* seqlens;      // optional [B]: per-row position of the new token (wins over start_pos); negative = skip the row
+  const int* block_table;  // optional [B][table_stride]: paged cache, slot p of row b lives in block block_table[b][p / block_size]
+  int table_stride, block_size, block_shift;  // block_shift = log2(block_size) when it is a power of two, else -1
   int cache_dtype;
   void* out;  // [B, Hq * 64]
   long long ld_out;
@@ -73,7 +76,20 @@ attn_decode_kernel(const DecodeDev g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = lane & 7;   // which 8-element slice of the head dim
   const int lk = lane >> 3;  // key sub-index within the warp step (0..3)
-  const int sp = g.start_pos_ptr ? *g.start_pos_ptr : g.start_pos;  // slot / position of the new token
+  // slot / position of the new token: per row (continuous batching), from device memory (graph replay), or the host value
+  const int sp = g.seqlens ? g.seqlens[b] : (g.start_pos_ptr ? *g.start_pos_ptr : g.start_pos);
+  if (sp < 0) return;  // an idle batch slot
+  // element offset of cache slot `pos` of this (row, kv head): contiguous [B, Hkv, len, 64] through strides, or paged
+  // [blocks, block_size, Hkv, 64] through the row's block table (one int32 lookup per row, L1-resident)
+  const int* tbl = g.block_table ? g.block_table + static_cast<long long>(b) * g.table_stride : nullptr;
+  auto slot_off = [&](int pos) -> long long {
+    if (tbl) {
+      const int blk = g.block_shift >= 0 ? pos >> g.block_shift : pos / g.block_size;
+      const int off = g.block_shift >= 0 ? pos & (g.block_size - 1) : pos - blk * g.block_size;
+      return static_cast<long long>(__ldg(tbl + blk)) * g.c_sb + off * g.c_sl;
+    }
+    return pos * g.c_sl;
+  };
 
   __shared__ float s_newk[HD];
   __shared__ float s_newv[HD];
@@ -104,12 +120,12 @@ attn_decode_kernel(const DecodeDev g) {
     }
   }
   __syncthreads();
-  TC* kc = reinterpret_cast<TC*>(g.kcache) + b * g.c_sb + kvh * g.c_sh;
-  TC* vc = reinterpret_cast<TC*>(g.vcache) + b * g.c_sb + kvh * g.c_sh;
+  TC* kc = reinterpret_cast<TC*>(g.kcache) + (tbl ? 0 : b * g.c_sb) + kvh * g.c_sh;
+  TC* vc = reinterpret_cast<TC*>(g.vcache) + (tbl ? 0 : b * g.c_sb) + kvh * g.c_sh;
   if (split == g.splits - 1 && threadIdx.x < HD) {
     // the cache stores what the reference stores: rotated k and raw v, rounded to the cache dtype
-    st_from_float(kc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, sp * g.c_sl + threadIdx.x, s_newk[threadIdx.x]);
-    st_from_float(vc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, sp * g.c_sl + threadIdx.x, s_newv[threadIdx.x]);
+    st_from_float(kc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, slot_off(sp) + threadIdx.x, s_newk[threadIdx.x]);
+    st_from_float(vc, sizeof(TC) == 2 ? VY_BF16 : VY_F32, slot_off(sp) + threadIdx.x, s_newv[threadIdx.x]);
   }
 
   float q[NREP][8];
@@ -141,8 +157,9 @@ attn_decode_kernel(const DecodeDev g) {
     for (int u = 0; u < DEC_UNROLL; ++u) {
       kidx[u] = k0 + (u * NWARPS + warp) * 4 + lk;
       if (kidx[u] < k_end) {
-        load_row8<TC>(kc + kidx[u] * g.c_sl + ld * 8, kv[u]);
-        load_row8<TC>(vc + kidx[u] * g.c_sl + ld * 8, vv[u]);
+        const long long off = slot_off(kidx[u]) + ld * 8;
+        load_row8<TC>(kc + off, kv[u]);
+        load_row8<TC>(vc + off, vv[u]);
       }
     }
 #pragma unroll
@@ -332,6 +349,10 @@ extern "C" int vy_attn_decode(const VyDecode* p) {
                "vy_attn_decode: bad head counts");
   VY_CHECK_ARG(p->start_pos >= 0 && p->start_pos < p->cache_len, "vy_attn_decode: start_pos %d outside the cache (%d)",
                p->start_pos, p->cache_len);
+  if (p->block_table)
+    VY_CHECK_ARG(p->block_size > 0 && p->max_blocks_per_seq > 0 &&
+                     static_cast<long long>(p->max_blocks_per_seq) * p->block_size >= p->start_pos + 1,
+                 "vy_attn_decode: paged cache needs block_size > 0 and max_blocks_per_seq * block_size > start_pos");
   VY_CHECK_ARG(p->qkv && p->k_cache && p->v_cache && p->out, "vy_attn_decode: null pointer");
   VY_CHECK_ARG(dtype_ok(p->qkv_dtype) && dtype_ok(p->cache_dtype) && dtype_ok(p->out_dtype), "vy_attn_decode: bad dtype");
   VY_CHECK_ARG((p->rope_cos == nullptr) == (p->rope_sin == nullptr), "vy_attn_decode: rope tables must both be set or NULL");
@@ -351,6 +372,12 @@ extern "C" int vy_attn_decode(const VyDecode* p) {
   g.rope_sin = p->rope_sin;
   g.kcache = p->k_cache; g.vcache = p->v_cache;
   g.c_sb = p->cache_sb; g.c_sh = p->cache_sh; g.c_sl = p->cache_sl; g.cache_dtype = p->cache_dtype;
+  g.seqlens = p->seqlens;
+  g.block_table = p->block_table; g.table_stride = p->max_blocks_per_seq; g.block_size = p->block_size;
+  g.block_shift = -1;
+  if (p->block_size > 0 && (p->block_size & (p->block_size - 1)) == 0)
+    for (int sft = 0; sft < 31; ++sft)
+      if ((1 << sft) == p->block_size) g.block_shift = sft;
   g.out = p->out; g.ld_out = p->ld_out; g.out_dtype = p->out_dtype;
   g.scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
   g.ws = p->workspace; g.tickets = reinterpret_cast<unsigned int*>(p->tickets);

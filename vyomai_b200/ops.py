@@ -362,8 +362,13 @@ def attn_decode(
     out_dtype: Optional[torch.dtype] = None,
     splits: int = 0,
     start_pos_dev: Optional[torch.Tensor] = None,
+    seqlens: Optional[torch.Tensor] = None,
+    block_table: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """Single-token attention with fused RoPE and kv-cache append. With `start_pos_dev` (int32 [1] on the device) the
+    """Single-token attention with fused RoPE and kv-cache append. `seqlens` (int32 [B], device) gives every row its
+    own context length (continuous batching; negative = idle slot); `block_table` (int32 [B, max_blocks], device) makes
+    the caches paged pools [num_blocks, block_size, Hkv, 64] (Examples/simple_vllm.ipynb) — `start_pos` is then the
+    largest context length of the batch. With `start_pos_dev` (int32 [1] on the device) the
     kernel takes the position from device memory and `start_pos` is only the upper bound that sizes the kv-split —
     the form a captured decode step uses. qkv [B, (Hq+2Hkv)*64] packed
     projections; caches [>=B, Hkv, cache_len, 64]; returns out [B, Hq*64]."""
@@ -372,6 +377,19 @@ def attn_decode(
     D = 64
     if k_cache.stride() != v_cache.stride() or k_cache.dtype != v_cache.dtype or k_cache.stride(3) != 1:
         raise _lib.VyomError("attn_decode: k/v caches must share dtype and strides, head_dim contiguous")
+    _need_cuda(seqlens, block_table)
+    for t, name in ((seqlens, "seqlens"), (block_table, "block_table")):
+        if t is not None and (t.dtype != torch.int32 or not t.is_contiguous()):
+            raise _lib.VyomError(f"attn_decode: {name} must be a contiguous int32 tensor")
+    paged = block_table is not None
+    if paged:  # [num_blocks, block_size, Hkv, 64]
+        block_size = k_cache.shape[1]
+        cache_len = block_table.shape[1] * block_size
+        c_sb, c_sl, c_sh = k_cache.stride(0), k_cache.stride(1), k_cache.stride(2)
+    else:      # [>=B, Hkv, cache_len, 64]
+        block_size = 0
+        cache_len = k_cache.shape[2]
+        c_sb, c_sh, c_sl = k_cache.stride(0), k_cache.stride(1), k_cache.stride(2)
     if out is None:
         out = torch.empty((B, n_q_heads * D), device=qkv.device, dtype=out_dtype or qkv.dtype)
     L = _lib.lib()
@@ -384,9 +402,11 @@ def attn_decode(
     _lib.call(
         "vy_attn_decode", "VyDecode",
         B=B, n_q_heads=n_q_heads, n_kv_heads=n_kv_heads, head_dim=D, start_pos=start_pos,
-        cache_len=k_cache.shape[2], qkv=qkv.data_ptr(), ld_qkv=qkv.stride(0), qkv_dtype=_dt(qkv),
+        cache_len=cache_len, qkv=qkv.data_ptr(), ld_qkv=qkv.stride(0), qkv_dtype=_dt(qkv),
         rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin), k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),
-        cache_sb=k_cache.stride(0), cache_sh=k_cache.stride(1), cache_sl=k_cache.stride(2), cache_dtype=_dt(k_cache),
+        cache_sb=c_sb, cache_sh=c_sh, cache_sl=c_sl, cache_dtype=_dt(k_cache),
+        seqlens=_ptr(seqlens), block_table=_ptr(block_table),
+        max_blocks_per_seq=block_table.shape[1] if paged else 0, block_size=block_size,
         out=out.data_ptr(), ld_out=out.stride(0), out_dtype=_dt(out), splits=splits, workspace=_ptr(ws),
         tickets=_ptr(tk), start_pos_ptr=_ptr(start_pos_dev), stream=_stream(),
     )
