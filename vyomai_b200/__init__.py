@@ -10,3 +10,4 @@ from .models.decoder import DecoderModel  # noqa: F401
 from .models.vision_encoder import Vit  # noqa: F401
 from .models.multimodel import VisionLanguageModel  # noqa: F401
 from .generation_utils import generate, generate_multimodel  # noqa: F401
+from .paged import ContinuousBatchEngine, PagedKVManager, SequenceState  # noqa: F401  (Examples/simple_vllm.ipynb)
