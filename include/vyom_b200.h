@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VY_ABI_VERSION 4
+#define VY_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define VY_API __attribute__((visibility("default")))
@@ -53,7 +53,8 @@ enum {
   VY_ACT_GELU_ERF = 1,
   VY_ACT_GELU_TANH = 2,
   VY_ACT_DGELU_ERF = 3,
-  VY_ACT_DGELU_TANH = 4
+  VY_ACT_DGELU_TANH = 4,
+  VY_ACT_SWIGLU = 5 /* gated MLP: see VyGemm.act */
 };
 
 enum { VY_EPI_LINEAR = 0, VY_EPI_QKV_ROPE = 1 };
@@ -117,7 +118,11 @@ typedef struct VyGemm {
   int32_t b_mn_major;
 
   int32_t epi; /* VY_EPI_* */
-  int32_t act; /* VY_ACT_* */
+  int32_t act; /* VY_ACT_*. VY_ACT_SWIGLU: B holds the gate and up projections INTERLEAVED (row 2j = gate_j, row 2j+1 =
+                * up_j; N = 2 * intermediate), out has N / 2 columns: out[r, j] = silu(z[r, 2j]) * z[r, 2j+1] with z = A B^T
+                * + bias — `down_proj(act_fn(gate_proj(x)) * up_proj(x))`'s first half as ONE GEMM
+                * (VyomAI/models/custom_transformer.py:76-89; Examples/simple_vllm.ipynb FeedForward). aux (optional)
+                * receives z ([rows, N]) for vy_swiglu_bwd. No addend / transposed_out / split-K with it. */
   int32_t transposed_out;
   const void* bias; /* [cols] or NULL */
   int32_t bias_dtype;
@@ -188,6 +193,10 @@ VY_API int vy_gemm_tune_override(int pair, int bn, int splits);
  * sums of dx, i.e. the gradient of the bias of the Linear whose output x was (attention.py:69, ffn.py:37). xhat is recomputed from the saved pre-norm sum `s`
  * (s = x + residual; pass the tensor fwd wrote to sum_out, or x when residual was NULL).
  * ------------------------------------------------------------------------------------------ */
+#define VY_NORM_LAYER 0
+#define VY_NORM_RMS 1
+#define VY_NORM_RMS_GEMMA 2
+
 typedef struct VyNorm {
   int32_t rows, H;
   const void* x;
@@ -211,6 +220,12 @@ typedef struct VyNorm {
   int32_t dparam_dtype;      /* VY_F32 (default 0) or VY_BF16 */
   int32_t dparam_accumulate; /* 1: dgamma/dbeta += result (accumulate straight into the parameters' .grad) */
   float* partials; /* workspace: 2 * vy_norm_bwd_partial_rows() * H floats (holds the per-strip column partials) */
+  /* VY_NORM_LAYER (0, default): LayerNorm as above. VY_NORM_RMS: y = gamma * xhat, xhat = x * rsqrt(mean(x^2) + eps),
+   * with xhat rounded to the activation dtype before the multiply (VyomAI/models/custom_transformer.py:227-241;
+   * Examples/simple_vllm.ipynb cell 2 RMSNorm, whose optional `shift` is `beta`). VY_NORM_RMS_GEMMA: y = (1 + gamma) *
+   * xhat (Examples/paligemma.ipynb GemmaRMSNorm). For both, beta may be NULL, mean is unused, and bwd's dbeta
+   * receives the column sums of dy (meaningful only when a shift is trained). */
+  int32_t kind;
   void* stream;
 } VyNorm;
 
@@ -323,6 +338,11 @@ VY_API int vy_rope_apply(const VyRope* p);
  * backward of the LM head (models/decoder.py:269), whose upstream gradient comes out of a LayerNorm
  * backward rather than a GEMM (inside the FFN the same factor rides in the dgrad GEMM epilogue). */
 VY_API int vy_act_bwd(int64_t n, const void* dy, const void* z, int dtype, int act, void* out, void* stream);
+
+/* vy_swiglu_bwd — gradient of h[r, j] = silu(z[r, 2j]) * z[r, 2j+1] w.r.t. the interleaved pre-activations:
+ * dz[r, 2j] = dh[r, j] * z[r, 2j+1] * silu'(z[r, 2j]), dz[r, 2j+1] = dh[r, j] * silu(z[r, 2j]); dz then feeds the
+ * ordinary dgrad / wgrad GEMMs against the interleaved weight. dh [rows, I], z / dz [rows, 2 I], contiguous, I % 8 == 0. */
+VY_API int vy_swiglu_bwd(int64_t rows, int32_t inter, const void* dh, const void* z, int dtype, void* dz, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * vy_attn_decode — single-token attention over the contiguous kv-cache, fused with the new

@@ -519,3 +519,31 @@ def paged_decode_attention(q: Tensor, k_new: Tensor, v_new: Tensor, k_pool: Tens
         k, v = repeat_kv(k, Hq // Hkv), repeat_kv(v, Hq // Hkv)
         out[b] = sdpa(q[b].float().view(1, Hq, 1, d), k, v, None)[0, :, 0].to(q.dtype)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# RMSNorm / gated MLP family (models/custom_transformer.py; Examples/simple_vllm.ipynb, paligemma.ipynb)
+# ---------------------------------------------------------------------------------------------
+def rms_norm(x: Tensor, weight: Tensor, eps: float, gemma: bool = False, shift: Optional[Tensor] = None) -> Tensor:
+    """RMSNorm.forward (models/custom_transformer.py:236-241): fp32 `x * rsqrt(mean(x^2) + eps)`, cast back to the input
+    dtype, THEN times the weight. gemma=True: `(1 + weight)` (paligemma.ipynb GemmaRMSNorm, product taken in fp32 before
+    the cast); shift: the optional additive term of simple_vllm.ipynb's RMSNorm."""
+    dt = x.dtype
+    xf = x.to(torch.float32)
+    xhat = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    if gemma:
+        y = (xhat * (1.0 + weight.to(torch.float32))).to(dt)
+    else:
+        y = weight * xhat.to(dt)
+    return y if shift is None else y + shift
+
+
+def silu(x: Tensor) -> Tensor:
+    """ACT2FN["silu"]: x * sigmoid(x), spelled out."""
+    return x / (1.0 + torch.exp(-x))
+
+
+def gated_mlp(x: Tensor, w_gate: Tensor, w_up: Tensor, w_down: Tensor) -> Tensor:
+    """MLP.forward (models/custom_transformer.py:87-89): down_proj(act_fn(gate_proj(x)) * up_proj(x)), no biases,
+    act_fn = SiLU for the shipped configs."""
+    return linear(silu(linear(x, w_gate, None)) * linear(x, w_up, None), w_down, None)

@@ -11,7 +11,6 @@ for l in sys.stdin:
         d=json.loads(l); print('$label', round(d['ms_per_step'],3), 'ms/step', round(d['value']), 'samples/s')"
 }
 run "overlap(default)" X=1 --
-run "no-overlap" X=1 -- --no-overlap
-run "overlap bucket16" X=1 -- --bucket-mb 16
-run "overlap NCCL_MAX_CTAS=4" NCCL_MAX_CTAS=4 --
-run "overlap NCCL_MAX_CTAS=16" NCCL_MAX_CTAS=16 --
+run "overlap margin8" VY_GEMM_SM_MARGIN=8 --
+run "overlap margin16" VY_GEMM_SM_MARGIN=16 --
+run "overlap margin16 CTAS16" VY_GEMM_SM_MARGIN=16 NCCL_MAX_CTAS=16 --

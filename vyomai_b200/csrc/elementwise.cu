@@ -564,6 +564,34 @@ act_bwd_kernel(long long n, const void* __restrict__ dy, const void* __restrict_
   }
 }
 
+// dz of the gated MLP: 8 outputs of dh <-> 16 interleaved (gate, up) pre-activations
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(long long nvec, const void* __restrict__ dh, const void* __restrict__ z, int dt, void* __restrict__ dz) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi < nvec;
+       vi += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float d[8], lo[8], hi[8];
+    ld8_as_float(dh, dt, vi * 8, d);
+    ld8_as_float(z, dt, vi * 16, lo);
+    ld8_as_float(z, dt, vi * 16 + 8, hi);
+    float x[16], o[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x[j] = lo[j]; x[8 + j] = hi[j]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gte = x[2 * j], up = x[2 * j + 1];
+      const float sg = 1.f / (1.f + __expf(-gte));
+      o[2 * j] = d[j] * up * sg * (1.f + gte * (1.f - sg));  // silu'(g) = sigma(g) (1 + g (1 - sigma(g)))
+      o[2 * j + 1] = d[j] * gte * sg;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = o[j]; hi[j] = o[8 + j]; }
+    st8_from_float(dz, dt, vi * 16, lo);
+    st8_from_float(dz, dt, vi * 16 + 8, hi);
+  }
+}
+
 static int ew_grid(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(num_sms()) * 8;
@@ -697,6 +725,17 @@ extern "C" int vy_softmax_xent(const VyXent* p) {
       p->rows, p->V, p->logits, p->ld, p->dtype, reinterpret_cast<const long long*>(p->labels), p->ignore_index,
       p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->write_grad,
       (aligned16(p->logits) && (p->ld * static_cast<long long>(dtype_size(p->dtype))) % 16 == 0) ? 1 : 0));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_swiglu_bwd(int64_t rows, int32_t inter, const void* dh, const void* z, int dtype, void* dz, void* stream) {
+  VY_NEED_DEVICE("vy_swiglu_bwd");
+  VY_CHECK_ARG(rows > 0 && inter > 0 && inter % 8 == 0 && dh && z && dz && dtype_ok(dtype) && aligned16(dh) && aligned16(z) && aligned16(dz),
+               "vy_swiglu_bwd: bad arguments (intermediate size must be a multiple of 8, pointers 16-byte aligned)");
+  const long long nvec = rows * (inter / 8);
+  VY_CUDA_OK(launch_kernel(swiglu_bwd_kernel, dim3(ew_grid(nvec, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), nvec, dh, z, dtype, dz));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

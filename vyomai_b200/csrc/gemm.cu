@@ -226,7 +226,10 @@ extern "C" int vy_gemm(const VyGemm* p) {
 
   if (p->epi == VY_EPI_LINEAR) {
     VY_CHECK_ARG(p->out != nullptr && dtype_ok(p->out_dtype), "vy_gemm: out / out_dtype invalid");
-    VY_CHECK_ARG(p->act >= VY_ACT_NONE && p->act <= VY_ACT_DGELU_TANH, "vy_gemm: bad act %d", p->act);
+    VY_CHECK_ARG(p->act >= VY_ACT_NONE && p->act <= VY_ACT_SWIGLU, "vy_gemm: bad act %d", p->act);
+    if (p->act == VY_ACT_SWIGLU)
+      VY_CHECK_ARG((p->N & 1) == 0 && !p->addend && !p->addend2 && !p->transposed_out && p->out_row_group == 0,
+                   "vy_gemm: SWIGLU needs an even N (interleaved gate/up rows) and takes no addend / transpose / row remap");
     if (p->act == VY_ACT_DGELU_ERF || p->act == VY_ACT_DGELU_TANH)
       VY_CHECK_ARG(p->aux != nullptr, "vy_gemm: DGELU epilogue needs aux (saved pre-activation)");
     if (p->bias) VY_CHECK_ARG(dtype_ok(p->bias_dtype), "vy_gemm: bad bias_dtype");
@@ -274,7 +277,7 @@ extern "C" int vy_gemm(const VyGemm* p) {
   // TMA-store write-back for the fast (all-bf16, 16-byte aligned, no row remap) epilogues; VY_GEMM_TMA_STORE=0 keeps st.global
   static const bool tma_store_on = !(getenv("VY_GEMM_TMA_STORE") && atoi(getenv("VY_GEMM_TMA_STORE")) == 0);
   g.tma_store = 0;
-  if (tma_store_on && p->epi == VY_EPI_LINEAR && !p->transposed_out && g.vec_ok && p->out_dtype == VY_BF16 && !p->addend2 &&
+  if (tma_store_on && p->epi == VY_EPI_LINEAR && p->act != VY_ACT_SWIGLU && !p->transposed_out && g.vec_ok && p->out_dtype == VY_BF16 && !p->addend2 &&
       p->out_row_group == 0 && (!p->aux || p->aux_dtype == VY_BF16) && (!p->addend || p->addend_dtype == VY_BF16))
     g.tma_store = 1;
   const int bk = p->in_dtype == VY_BF16 ? 64 : 32;

@@ -170,6 +170,38 @@ static __device__ __noinline__ void epilogue_chunk_general(const GemmDev& g, con
   const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
   const bool fwd_act = g.act == VY_ACT_GELU_ERF || g.act == VY_ACT_GELU_TANH;
   const bool bwd_act = g.act == VY_ACT_DGELU_ERF || g.act == VY_ACT_DGELU_TANH;
+  if (g.act == VY_ACT_SWIGLU) {
+    // columns (2j, 2j+1) of the accumulator are (gate_j, up_j): 32 accumulator columns -> 16 outputs at column gcol0 / 2
+    const long long obase = orow * g.ld_out + (gcol0 >> 1);
+    if (g.vec_ok && lim == 32) {
+#pragma unroll 1
+      for (int j4 = 0; j4 < 2; ++j4) {
+        float x[16], h[8];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(raw[j4 * 16 + j]) + bs[j4 * 16 + j];
+        if (g.aux) {
+          float lo[8], hi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lo[j] = x[j]; hi[j] = x[8 + j]; }
+          st8_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + gcol0 + j4 * 16, lo);
+          st8_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + gcol0 + j4 * 16 + 8, hi);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = x[2 * j] / (1.f + __expf(-x[2 * j])) * x[2 * j + 1] * scale;
+        st8_from_float(g.out, g.out_dtype, obase + j4 * 8, h);
+      }
+    } else {
+      for (int j = 0; j + 1 < lim; j += 2) {
+        const float a = __uint_as_float(raw[j]) + bs[j], b = __uint_as_float(raw[j + 1]) + bs[j + 1];
+        if (g.aux) {
+          st_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + gcol0 + j, a);
+          st_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + gcol0 + j + 1, b);
+        }
+        st_from_float(g.out, g.out_dtype, obase + (j >> 1), a / (1.f + __expf(-a)) * b * scale);
+      }
+    }
+    return;
+  }
   if (g.vec_ok && lim == 32) {
 #pragma unroll 1
     for (int j4 = 0; j4 < 4; ++j4) {
@@ -1050,7 +1082,11 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   const int n_tiles = (p->N + BN - 1) / BN;
   const int m_slots = PAIR ? (m_tiles + 1) / 2 : m_tiles;
   const int units = m_slots * n_tiles * (g.k_splits > 1 ? g.k_splits : 1);
-  const int max_workers = PAIR ? num_sms() / 2 : num_sms();
+  // VY_GEMM_SM_MARGIN=n leaves n SMs to concurrently running kernels (the NCCL all-reduce of a data-parallel step): a
+  // persistent grid that assumes every SM is its own waits for the stragglers that could not be co-scheduled.
+  static const int sm_margin = getenv("VY_GEMM_SM_MARGIN") ? atoi(getenv("VY_GEMM_SM_MARGIN")) : 0;
+  const int usable_sms = num_sms() - sm_margin > 16 ? num_sms() - sm_margin : num_sms();
+  const int max_workers = PAIR ? usable_sms / 2 : usable_sms;
   const int workers = units < max_workers ? units : max_workers;
   const int grid = PAIR ? 2 * workers : workers;
   VY_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(GEMM_THREADS), smem_bytes, static_cast<cudaStream_t>(p->stream),

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(NORM_WARPS * 32)
 add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void* __restrict__ res,
                          int io_dt, const void* __restrict__ gamma, const void* __restrict__ beta,
                          int p_dt, float eps, void* __restrict__ y, void* __restrict__ sum_out,
-                         float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int kind) {
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -39,7 +39,8 @@ add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void
         for (int j = 0; j < 8; ++j) sum += v[i][j];
       }
     }
-    const float mean = warp_sum(sum) / H;
+    // kind 0: LayerNorm. kind 1 / 2: RMSNorm — no mean, y = w * xhat (2: Gemma's (1 + w) * xhat), optional shift beta
+    const float mean = kind == VY_NORM_LAYER ? warp_sum(sum) / H : 0.f;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -62,9 +63,25 @@ add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void
       if (vi < nvec) {
         float g[8], b[8], o[8];
         ld8_as_float(gamma, p_dt, vi * 8, g);
-        ld8_as_float(beta, p_dt, vi * 8, b);
+        if (beta) {
+          ld8_as_float(beta, p_dt, vi * 8, b);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+          for (int j = 0; j < 8; ++j) b[j] = 0.f;
+        }
+        if (kind == VY_NORM_LAYER) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+        } else {
+          // the reference rounds xhat to the activation dtype BEFORE the weight multiply
+          // (models/custom_transformer.py:236-240: `self.weight * hidden_states.to(input_dtype)`)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float xh = v[i][j] * rstd;
+            if (io_dt == VY_BF16) xh = __bfloat162float(__float2bfloat16_rn(xh));
+            o[j] = xh * (kind == VY_NORM_RMS_GEMMA ? 1.f + g[j] : g[j]) + b[j];
+          }
+        }
         st8_from_float(y, io_dt, base + vi * 8, o);
       }
     }
@@ -96,7 +113,8 @@ template <int NV, bool IO_BF16>
 __global__ void __launch_bounds__(NORM_WARPS * 32, 1)
 add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s,
                          const void* __restrict__ gamma, int p_dt, const float* __restrict__ mean,
-                         const float* __restrict__ rstd, void* __restrict__ dx, int want_dbias, float* __restrict__ partials) {
+                         const float* __restrict__ rstd, void* __restrict__ dx, int want_dbias, float* __restrict__ partials,
+                         int kind) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(128) float red[];  // [NORM_WARPS][3][H] at the end; the row ring before that
@@ -121,8 +139,15 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
     const int vi = lane + i * 32;
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[i][j] = dg[i][j] = db[i][j] = dbi[i][j] = 0.f;
-    if (vi < nvec) ld8_as_float(gamma, p_dt, vi * 8, g[i]);
+    if (vi < nvec) {
+      ld8_as_float(gamma, p_dt, vi * 8, g[i]);
+      if (kind == VY_NORM_RMS_GEMMA) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[i][j] += 1.f;
+      }
+    }
   }
+  const bool rms = kind != VY_NORM_LAYER;  // RMSNorm: xhat = x * rstd, dx = rstd * (dy g - xhat mean(dy g xhat))
   const int stride = gridDim.x * NORM_WARPS;
   float mu_r[D], rs_r[D];  // per-row statistics of the rows in flight (loaded when the row's copies are issued)
   auto issue = [&](int d, int row) {
@@ -140,7 +165,7 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
     mu_r[d] = rs_r[d] = 0.f;
     if (row < rows) {
       issue(d, row);
-      mu_r[d] = mean[row];
+      mu_r[d] = rms ? 0.f : mean[row];
       rs_r[d] = rstd[row];
     }
   }
@@ -184,7 +209,7 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
         const int next = row0 + u * stride + D * stride;
         if (next < rows) {
           issue(d + u, next);
-          mu_r[d + u] = mean[next];
+          mu_r[d + u] = rms ? 0.f : mean[next];
           rs_r[d + u] = rstd[next];
         }
       }
@@ -217,7 +242,7 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         if (u == 1 && !two) break;
-        const float m1 = c1[u] / H, m2 = c2[u] / H;
+        const float m1 = rms ? 0.f : c1[u] / H, m2 = c2[u] / H;
         const long long rbase = static_cast<long long>(row0 + u * stride) * H;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -441,7 +466,8 @@ extern "C" int vy_add_layernorm_fwd(const VyNorm* p) {
   using namespace vy;
   int rc = norm_common_checks(p, "vy_add_layernorm_fwd");
   if (rc != VY_OK) return rc;
-  VY_CHECK_ARG(p->x && p->y && p->gamma && p->beta, "vy_add_layernorm_fwd: null pointer");
+  VY_CHECK_ARG(p->x && p->y && p->gamma && (p->beta || p->kind != VY_NORM_LAYER), "vy_add_layernorm_fwd: null pointer");
+  VY_CHECK_ARG(p->kind >= VY_NORM_LAYER && p->kind <= VY_NORM_RMS_GEMMA, "vy_add_layernorm_fwd: bad kind %d", p->kind);
   VY_CHECK_ARG(aligned16(p->x) && aligned16(p->y) && aligned16(p->gamma) && aligned16(p->beta) &&
                    aligned16(p->residual) && aligned16(p->sum_out),
                "vy_add_layernorm_fwd: pointers must be 16-byte aligned");
@@ -453,7 +479,7 @@ extern "C" int vy_add_layernorm_fwd(const VyNorm* p) {
 #define VY_LN_FWD(NV)                                                                              \
   VY_CUDA_OK(launch_kernel(add_layernorm_fwd_kernel<NV>, dim3(grid), dim3(NORM_WARPS * 32), 0, st,                                   \
       p->rows, p->H, p->x, p->residual, p->io_dtype, p->gamma, p->beta, p->param_dtype, p->eps, p->y, \
-      p->sum_out, p->mean, p->rstd))
+      p->sum_out, p->mean, p->rstd, p->kind))
   switch (nv) {
     case 1: VY_LN_FWD(1); break;
     case 2: VY_LN_FWD(2); break;
@@ -474,8 +500,11 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   using namespace vy;
   int rc = norm_common_checks(p, "vy_add_layernorm_bwd");
   if (rc != VY_OK) return rc;
-  VY_CHECK_ARG(p->dy && p->s && p->dx && p->gamma && p->mean && p->rstd && p->dgamma && p->dbeta && p->partials,
+  VY_CHECK_ARG(p->dy && p->s && p->dx && p->gamma && (p->mean || p->kind != VY_NORM_LAYER) && p->rstd && p->dgamma && p->dbeta &&
+                   p->partials,
                "vy_add_layernorm_bwd: null pointer");
+  VY_CHECK_ARG(p->kind >= VY_NORM_LAYER && p->kind <= VY_NORM_RMS_GEMMA, "vy_add_layernorm_bwd: bad kind %d", p->kind);
+  VY_CHECK_ARG(p->kind == VY_NORM_LAYER || p->H <= 1024, "vy_add_layernorm_bwd: RMSNorm backward supports H <= 1024 (got %d)", p->H);
   VY_CHECK_ARG(aligned16(p->dy) && aligned16(p->s) && aligned16(p->dx) && aligned16(p->gamma),
                "vy_add_layernorm_bwd: pointers must be 16-byte aligned");
   VY_CHECK_ARG(dtype_ok(p->dparam_dtype), "vy_add_layernorm_bwd: bad dparam_dtype");
@@ -493,7 +522,7 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
     if (smem > 48 * 1024)                                                                            \
       VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     VY_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(NORM_WARPS * 32), smem, st, p->rows, p->H, p->dy, p->s, p->gamma, p->param_dtype, p->mean, p->rstd, \
-                                              p->dx, p->dbias != nullptr, p->partials));               \
+                                              p->dx, p->dbias != nullptr, p->partials, p->kind));      \
   } while (0)
 #define VY_LN_BWD(NV)                     \
   do {                                    \

@@ -15,10 +15,13 @@ from ._lib import CONSTS as C
 
 _DT = {torch.float32: C["VY_F32"], torch.bfloat16: C["VY_BF16"]}
 
+NORM_KIND = {"layernorm": C["VY_NORM_LAYER"], "rmsnorm": C["VY_NORM_RMS"], "gemma_rmsnorm": C["VY_NORM_RMS_GEMMA"]}
+
 ACT = {
     None: C["VY_ACT_NONE"],
     "none": C["VY_ACT_NONE"],
     "gelu": C["VY_ACT_GELU_ERF"],
+    "swiglu": C["VY_ACT_SWIGLU"],
     "gelu_erf": C["VY_ACT_GELU_ERF"],
     "gelu_tanh": C["VY_ACT_GELU_TANH"],
     "dgelu": C["VY_ACT_DGELU_ERF"],
@@ -113,7 +116,9 @@ def gemm(
         rows = M if out_row_group == 0 else None
         if rows is None:
             raise _lib.VyomError("gemm: pass `out` when using a row-group remap")
-        out = torch.empty((M, N), device=a.device, dtype=odt)
+        out = torch.empty((M, N // 2 if act == "swiglu" else N), device=a.device, dtype=odt)
+    if act == "swiglu" and (swap_ab or N % 2 or out.shape[-1] != N // 2):
+        raise _lib.VyomError("gemm: act='swiglu' takes interleaved gate/up rows (even N), writes N / 2 columns, no swap_ab")
     if out.stride(-1) != 1:
         raise _lib.VyomError("gemm: out must be row-major")
     a_mn, lda = _major(a, "gemm a")
@@ -157,7 +162,7 @@ def gemm(
         key = ("gemm", kw["M"], kw["N"], K, kw["in_dtype"], kw["a_mn_major"], kw["b_mn_major"], kw["transposed_out"], act,
                bias is not None, addend is not None, addend is not None and addend.data_ptr() == out.data_ptr(),
                addend2 is not None, aux is not None, out.dtype, allow_split_k, out_row_group, addend_row_mod, out_scale != 1.0)
-        saves_aux = aux is not None and act in ("gelu", "gelu_tanh")
+        saves_aux = aux is not None and act in ("gelu", "gelu_tanh", "swiglu")
         kw.update(gemm_tune.hints(key, kw, [("out", out), ("aux", aux if saves_aux else None)], a.device))
     _lib.call("vy_gemm", "VyGemm", **kw)
     return out
@@ -224,8 +229,11 @@ def add_layernorm(
     *,
     save_stats: bool = False,
     save_sum: bool = False,
+    kind: str = "layernorm",
 ):
-    """y = LayerNorm(x + residual). Returns (y, sum_or_None, mean_or_None, rstd_or_None)."""
+    """y = LayerNorm(x + residual). Returns (y, sum_or_None, mean_or_None, rstd_or_None).
+    kind="rmsnorm": y = gamma * xhat with xhat = s * rsqrt(mean(s^2) + eps) (custom_transformer.py:227-241; `beta`, the
+    optional shift of simple_vllm.ipynb's RMSNorm, may be None); kind="gemma_rmsnorm": y = (1 + gamma) * xhat."""
     _need_cuda(x, residual, gamma, beta)
     H = x.shape[-1]
     x2 = x.reshape(-1, H)
@@ -241,11 +249,13 @@ def add_layernorm(
     s = torch.empty_like(x2) if (save_sum and residual is not None) else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    if beta is None and kind == "layernorm":
+        raise _lib.VyomError("add_layernorm: LayerNorm needs beta")
     _lib.call(
         "vy_add_layernorm_fwd", "VyNorm",
         rows=rows, H=H, x=x2.data_ptr(), residual=_ptr(r2), io_dtype=_dt(x2), gamma=gamma.data_ptr(),
-        beta=beta.data_ptr(), param_dtype=_dt(gamma), eps=float(eps), y=y.data_ptr(), sum_out=_ptr(s),
-        mean=_ptr(mean), rstd=_ptr(rstd), stream=_stream(),
+        beta=_ptr(beta), param_dtype=_dt(gamma), eps=float(eps), y=y.data_ptr(), sum_out=_ptr(s),
+        mean=_ptr(mean), rstd=_ptr(rstd), kind=NORM_KIND[kind], stream=_stream(),
     )
     if save_sum and residual is None:
         s = x2
@@ -254,8 +264,9 @@ def add_layernorm(
 
 def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tensor] = None,
                       dbeta_out: Optional[torch.Tensor] = None, dbias_out: Optional[torch.Tensor] = None,
-                      want_dbias: bool = False, accumulate: bool = True):
-    """Returns (dx, dgamma, dbeta[, dbias]) for y = LayerNorm(s). Without dgamma_out/dbeta_out the parameter
+                      want_dbias: bool = False, accumulate: bool = True, kind: str = "layernorm"):
+    """Returns (dx, dgamma, dbeta[, dbias]) for y = LayerNorm(s) (or the RMSNorm kinds of add_layernorm; `mean` may then
+    be None and dbeta is the gradient of the optional shift). Without dgamma_out/dbeta_out the parameter
     gradients come back as fresh fp32 tensors; with them (same dtype, e.g. the parameters' .grad views) the kernel
     ACCUMULATES into those buffers (or, with accumulate=False, overwrites them) and returns them. dbias (want_dbias / dbias_out) = column sums of dx: the bias
     gradient of the Linear that produced the normalised sum."""
@@ -286,9 +297,9 @@ def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tenso
     _lib.call(
         "vy_add_layernorm_bwd", "VyNorm",
         rows=rows, H=H, io_dtype=_dt(dy2), gamma=gamma.data_ptr(), param_dtype=_dt(gamma),
-        mean=mean.data_ptr(), rstd=rstd.data_ptr(), dy=dy2.data_ptr(), s=s2.data_ptr(), dx=dx.data_ptr(),
+        mean=_ptr(mean), rstd=rstd.data_ptr(), dy=dy2.data_ptr(), s=s2.data_ptr(), dx=dx.data_ptr(),
         dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), dbias=_ptr(dbias), dparam_dtype=_dt(dgamma),
-        dparam_accumulate=int(acc and accumulate), partials=partials.data_ptr(), stream=_stream(),
+        dparam_accumulate=int(acc and accumulate), partials=partials.data_ptr(), kind=NORM_KIND[kind], stream=_stream(),
     )
     if want_dbias or dbias_out is not None:
         return dx.view(dy.shape), dgamma, dbeta, dbias
@@ -570,6 +581,18 @@ def act_bwd(dy: torch.Tensor, z: torch.Tensor, act: str = "gelu") -> torch.Tenso
     _lib.check(_lib.lib().vy_act_bwd(dy.numel(), dy.data_ptr(), z.data_ptr(), _dt(dy), ACT[act], out.data_ptr(), _stream()),
                "vy_act_bwd")
     return out
+
+
+def swiglu_bwd(dh: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """dz for h = silu(z[:, 0::2]) * z[:, 1::2] (the act="swiglu" epilogue of gemm): dh [rows, I], z [rows, 2 I]."""
+    _need_cuda(dh, z)
+    if not (dh.is_contiguous() and z.is_contiguous()) or dh.dtype != z.dtype or z.shape[-1] != 2 * dh.shape[-1]:
+        raise _lib.VyomError("swiglu_bwd: dh [rows, I] and z [rows, 2 I] must be contiguous and share a dtype")
+    dz = torch.empty_like(z)
+    inter = dh.shape[-1]
+    _lib.check(_lib.lib().vy_swiglu_bwd(dh.numel() // inter, inter, dh.data_ptr(), z.data_ptr(), _dt(dh), dz.data_ptr(), _stream()),
+               "vy_swiglu_bwd")
+    return dz
 
 
 def sqnorm(g: torch.Tensor, out: torch.Tensor) -> None:
