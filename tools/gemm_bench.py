@@ -56,12 +56,16 @@ def case(name, M, N, K, a_mn=False, b_mn=False, epi="none", iters=20, out_dtype=
         kw = dict(bias=bias)
     elif epi in ("accum", "splitk_ok"):
         pass
+    elif epi in ("swiglu", "swiglu_aux"):  # B rows are interleaved (gate, up): N = 2 * intermediate, N / 2 output columns
+        outs = [torch.empty((M, N // 2), device=DEV, dtype=out_dtype) for _ in range(nbuf)]
+        auxs = [torch.empty((M, N), device=DEV, dtype=BF) for _ in range(nbuf)]
+        kw = dict(act="swiglu")
 
     def ours(i):
         a = As[i].t() if a_mn else As[i]
         b = Bs[i].t() if b_mn else Bs[i]
         k2 = dict(kw)
-        if epi in ("gelu_aux", "dgelu"):
+        if epi in ("gelu_aux", "dgelu", "swiglu_aux"):
             k2["aux"] = auxs[i]
         if epi == "addend":
             k2["addend"] = adds[i]
@@ -139,6 +143,9 @@ def bench_cases():
         ("vit.w ffn1", 3072, 768, Tv, True, True, "accum"),
         ("vit.w ffn2", 768, 3072, Tv, True, True, "accum"),
         ("lm_head wgrad", 50272, 768, T, True, True, "accum"),
+        # gated MLP of the RMSNorm / SwiGLU family (hidden 1024, intermediate 3072: the notebooks' Qwen3-0.6B block)
+        ("gated gate|up swiglu", T, 6144, 1024, False, False, "swiglu"),
+        ("gated gate|up +save z", T, 6144, 1024, False, False, "swiglu_aux"),
     ]
 
 

@@ -93,6 +93,23 @@ def _gemm_cases(dtype, tol):
     ok &= report("dgelu", out, (a.float() @ b.float().t()) * zz.grad, tol * 2)
     other = torch.float32 if dtype == torch.bfloat16 else torch.bfloat16
     ok &= report("cross out dtype", ops.gemm(a, b, bias=bias, out_dtype=other), z, max(tol, 4e-3))
+    # gated MLP epilogue: interleaved gate / up rows -> silu(gate) * up; staged fast path (no save) and general path (save z)
+    if dtype == torch.bfloat16:
+        for (Mg, Kg, Ig) in [(300, 256, 320), (1024, 1024, 3072), (257, 128, 104)]:
+            xg = torch.randn(Mg, Kg, device=dev, dtype=dtype)
+            wg = torch.randn(Ig, Kg, device=dev, dtype=dtype) / Kg ** 0.5
+            wu = torch.randn(Ig, Kg, device=dev, dtype=dtype) / Kg ** 0.5
+            bg = torch.randn(2 * Ig, device=dev, dtype=dtype)
+            wi = torch.stack((wg, wu), 1).reshape(2 * Ig, Kg)
+            for bb in (None, bg):
+                zg = xg.float() @ wg.float().t() + (0 if bb is None else bb[0::2].float())
+                zu = xg.float() @ wu.float().t() + (0 if bb is None else bb[1::2].float())
+                refg = zg * torch.sigmoid(zg) * zu
+                ok &= report(f"swiglu {Mg}x{2 * Ig}x{Kg} bias={bb is not None}", ops.gemm(xg, wi, bias=bb, act="swiglu"), refg, tol * 2)
+                zsave = torch.empty(Mg, 2 * Ig, device=dev, dtype=dtype)
+                ok &= report("   + save z", ops.gemm(xg, wi, bias=bb, act="swiglu", aux=zsave), refg, tol * 2)
+                zi = torch.stack((zg, zu), 2).reshape(Mg, 2 * Ig)
+                ok &= report("   z", zsave, zi, tol)
     # swap-AB (decode shapes)
     for (M, N, K) in [(32, 768, 768), (32, 3072, 768), (32, 768, 3072), (3, 2304, 768), (64, 50265, 768), (1, 768, 768)]:
         a = torch.randn(M, K, device=dev, dtype=dtype)

@@ -277,7 +277,9 @@ extern "C" int vy_gemm(const VyGemm* p) {
   // TMA-store write-back for the fast (all-bf16, 16-byte aligned, no row remap) epilogues; VY_GEMM_TMA_STORE=0 keeps st.global
   static const bool tma_store_on = !(getenv("VY_GEMM_TMA_STORE") && atoi(getenv("VY_GEMM_TMA_STORE")) == 0);
   g.tma_store = 0;
-  if (tma_store_on && p->epi == VY_EPI_LINEAR && p->act != VY_ACT_SWIGLU && !p->transposed_out && g.vec_ok && p->out_dtype == VY_BF16 && !p->addend2 &&
+  // (SwiGLU: the staged write-back exists for the inference form only — no pre-activation save — and for bias pointers
+  //  the fast bias loader can vector-load)
+  if (tma_store_on && p->epi == VY_EPI_LINEAR && (p->act != VY_ACT_SWIGLU || (!p->aux && aligned16(p->bias))) && !p->transposed_out && g.vec_ok && p->out_dtype == VY_BF16 && !p->addend2 &&
       p->out_row_group == 0 && (!p->aux || p->aux_dtype == VY_BF16) && (!p->addend || p->addend_dtype == VY_BF16))
     g.tma_store = 1;
   const int bk = p->in_dtype == VY_BF16 ? 64 : 32;
@@ -322,6 +324,7 @@ extern "C" int vy_gemm(const VyGemm* p) {
   }
   if (pair && bn < 128) bn = 128;
   if (pair && p->b_mn_major && bn == 192) bn = 256;
+  if (p->act == VY_ACT_SWIGLU && g.tma_store && (bn == 192 || bn < 128)) bn = bn == 192 ? 256 : 128;  // whole chunk pairs per warp
   auto split_ok = [&](int sp) {
     return sp >= 1 && sp <= max_splits && (sp == 1 || static_cast<long long>(sp - 1) * ((num_kb + sp - 1) / sp) < num_kb);
   };

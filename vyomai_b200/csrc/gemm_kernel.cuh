@@ -515,6 +515,66 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
 }
 
 
+// SwiGLU, inference form (no pre-activation save): accumulator columns (2j, 2j+1) = (gate_j, up_j), so a PAIR of 32-column
+// chunks yields one [32 rows x 32 cols] bf16 output chunk, staged and written back like the other fast epilogues
+// (tma_out describes the N / 2 - column output). BN must be a multiple of 128 (an even number of chunks per warp).
+template <int BN>
+static __device__ __noinline__ void epilogue_swiglu_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half, int lane,
+                                                     uint64_t* tfull_bar, uint32_t tfull_phase, uint32_t tmem_empty_bar,
+                                                     uint8_t* stage, const CUtensorMap* tma_out) {
+  static_assert(BN % 128 == 0, "SwiGLU fast epilogue: an even number of 32-column chunks per warp");
+  constexpr int WC = BN / 2;
+  constexpr int NCH = WC / 32;
+  const int wcol0 = half * WC;
+  const int gc0 = n0 + wcol0;
+  const float scale = g.out_scale == 0.f ? 1.f : g.out_scale;
+  const int sw = (lane >> 1) & 3;
+  mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
+  tc_fence_after();
+  const uint32_t taddr = tmem_acc + wcol0;
+#pragma unroll 1
+  for (int c = 0; c < NCH; c += 2) {
+    const bool live = gc0 + c * 32 < g.N;
+    uint8_t* stg = (c & 2) ? stage + GEMM_STAGE_OUT : stage;
+    uint8_t* srow = stg + lane * 64;
+    if (live) {
+      if (elect_one_sync()) tma_store_wait_read<1>();  // the bulk store that last read this buffer (two pairs ago) is done
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {  // one 32-column chunk at a time: 16 outputs = half of the staged row
+      uint32_t raw[32];
+      tmem_ld_x32(taddr + (c + cc) * 32, raw);
+      tmem_ld_wait();
+      if (c + 2 >= NCH && cc == 1) release_acc(tmem_empty_bar, lane);
+      if (!live) continue;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {  // 16 accumulator columns -> 8 outputs
+        float b0[8], b1[8], h[8];
+        const int col = gc0 + (c + cc) * 32 + jj * 16;
+        load_bias8(g, col, b0);
+        load_bias8(g, col + 8, b1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gte = __uint_as_float(raw[jj * 16 + 2 * j]) + (j < 4 ? b0[2 * j] : b1[2 * j - 8]);
+          const float up = __uint_as_float(raw[jj * 16 + 2 * j + 1]) + (j < 4 ? b0[2 * j + 1] : b1[2 * j - 7]);
+          h[j] = gte / (1.f + __expf(-gte)) * up * scale;
+        }
+        *reinterpret_cast<uint4*>(srow + (((cc * 2 + jj) ^ sw) << 4)) =
+            make_uint4(pack2_bf16(h[0], h[1]), pack2_bf16(h[2], h[3]), pack2_bf16(h[4], h[5]), pack2_bf16(h[6], h[7]));
+      }
+    }
+    if (!live) continue;
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one_sync()) {
+      tma_store_2d(tma_out, stg, (gc0 + c * 32) >> 1, m0 + q * 32);
+      tma_store_commit();
+    }
+  }
+  __syncwarp();
+}
+
 // split-K epilogue: the raw fp32 accumulators of this (tile, split) unit go to the workspace slab of the split;
 // vy_gemm's reduce kernel sums the slabs and applies bias / addend / scale.
 template <int BN>
@@ -956,7 +1016,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // where this warp announces that it has drained the accumulator: the (leader's) MMA thread waits there
       const uint32_t tempty_addr = PAIR ? mapa_u32(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
       VY_TRACE(2 + e, local, 0);
-      if (!g.transposed_out && g.k_splits <= 1 && fast_mode < 0) {  // the fast epilogues read the bias straight from global
+      if (!g.transposed_out && g.k_splits <= 1 && fast_mode < 0 && !(g.act == VY_ACT_SWIGLU && g.tma_store && BN % 128 == 0)) {  // the fast epilogues read the bias straight from global
         for (int j = et; j < BN; j += GEMM_EPI_WARPS * 32) {
           const int col = n0 + j;
           bs[j] = (g.bias && col < g.N) ? ld_as_float(g.bias, g.bias_dtype, col) : 0.f;
@@ -976,6 +1036,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       } else if (g.transposed_out) {
         epilogue_transposed<BN>(g, tmem_base + acc * BN, m0, n0, q, half, lane, et, &tfull_bar[acc], acc_ph, tempty_addr,
                                 reinterpret_cast<float*>(epi_stage));
+      } else if (g.act == VY_ACT_SWIGLU && g.tma_store && BN % 128 == 0) {
+        if constexpr (BN % 128 == 0)
+          epilogue_swiglu_fast<BN>(g, tmem_acc, m0, n0, q, half, lane, &tfull_bar[acc], acc_ph, tempty_addr, stage, &tma_out);
       } else if (fast_mode == EPI_PLAIN) {
         if (g.tma_store)
           epilogue_linear_fast<BN, EPI_PLAIN, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
@@ -1066,7 +1129,7 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
   CUtensorMap tout = ta, taux = ta;
   GemmDev gl = g;
   if (g.tma_store) {
-    rc = get_tmap_2d(&tout, VY_BF16, p->out, p->N, p->M, p->ld_out * 2, 32, 32, 3);
+    rc = get_tmap_2d(&tout, VY_BF16, p->out, p->act == VY_ACT_SWIGLU ? p->N / 2 : p->N, p->M, p->ld_out * 2, 32, 32, 3);
     if (rc == VY_OK && p->aux && (p->act == VY_ACT_GELU_ERF))
       rc = get_tmap_2d(&taux, VY_BF16, p->aux, p->N, p->M, p->ld_aux * 2, 32, 32, 3);
     if (rc != VY_OK) gl.tma_store = 0;  // fall back to the staged st.global write-back
