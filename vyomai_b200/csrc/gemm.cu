@@ -22,6 +22,17 @@ VY_GEMM_EXTERN_PAIR(true, false, 128) VY_GEMM_EXTERN_PAIR(true, false, 192) VY_G
 VY_GEMM_EXTERN_PAIR(false, true, 128) VY_GEMM_EXTERN_PAIR(false, true, 256)
 VY_GEMM_EXTERN_PAIR(true, true, 128) VY_GEMM_EXTERN_PAIR(true, true, 256)
 
+// staged SwiGLU epilogue (inference form): bf16, both operands K-major, BN 128 | 256, either flavour
+extern template int launch_gemm<__nv_bfloat16, 128, false, false, false, true>(const VyGemm*, const GemmDev&);
+extern template int launch_gemm<__nv_bfloat16, 256, false, false, false, true>(const VyGemm*, const GemmDev&);
+extern template int launch_gemm<__nv_bfloat16, 128, false, false, true, true>(const VyGemm*, const GemmDev&);
+extern template int launch_gemm<__nv_bfloat16, 256, false, false, true, true>(const VyGemm*, const GemmDev&);
+static int dispatch_gemm_gated(const VyGemm* p, const GemmDev& g, int bn, bool pair) {
+  using T = __nv_bfloat16;
+  if (pair) return bn == 128 ? launch_gemm<T, 128, false, false, true, true>(p, g) : launch_gemm<T, 256, false, false, true, true>(p, g);
+  return bn == 128 ? launch_gemm<T, 128, false, false, false, true>(p, g) : launch_gemm<T, 256, false, false, false, true>(p, g);
+}
+
 static int dispatch_gemm_pair(const VyGemm* p, const GemmDev& g, int bn) {
   using T = __nv_bfloat16;
   const bool amn = p->a_mn_major != 0, bmn = p->b_mn_major != 0;
@@ -279,7 +290,9 @@ extern "C" int vy_gemm(const VyGemm* p) {
   g.tma_store = 0;
   // (SwiGLU: the staged write-back exists for the inference form only — no pre-activation save — and for bias pointers
   //  the fast bias loader can vector-load)
-  if (tma_store_on && p->epi == VY_EPI_LINEAR && (p->act != VY_ACT_SWIGLU || (!p->aux && aligned16(p->bias))) && !p->transposed_out && g.vec_ok && p->out_dtype == VY_BF16 && !p->addend2 &&
+  const bool gated_fast = p->act == VY_ACT_SWIGLU && !p->aux && aligned16(p->bias) && p->in_dtype == VY_BF16 && !p->a_mn_major &&
+                          !p->b_mn_major;
+  if (tma_store_on && p->epi == VY_EPI_LINEAR && (p->act != VY_ACT_SWIGLU || gated_fast) && !p->transposed_out && g.vec_ok && p->out_dtype == VY_BF16 && !p->addend2 &&
       p->out_row_group == 0 && (!p->aux || p->aux_dtype == VY_BF16) && (!p->addend || p->addend_dtype == VY_BF16))
     g.tma_store = 1;
   const int bk = p->in_dtype == VY_BF16 ? 64 : 32;
@@ -353,6 +366,7 @@ extern "C" int vy_gemm(const VyGemm* p) {
     return VY_OK;
   }
 
+  if (p->act == VY_ACT_SWIGLU && g.tma_store) return dispatch_gemm_gated(p, g, bn, pair);
   if (pair) return dispatch_gemm_pair(p, g, bn);
   if (p->in_dtype == VY_BF16) return dispatch_gemm<__nv_bfloat16>(p, g, bn);
   return dispatch_gemm<float>(p, g, bn);

@@ -519,7 +519,7 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
 // chunks yields one [32 rows x 32 cols] bf16 output chunk, staged and written back like the other fast epilogues
 // (tma_out describes the N / 2 - column output). BN must be a multiple of 128 (an even number of chunks per warp).
 template <int BN>
-static __device__ __noinline__ void epilogue_swiglu_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half, int lane,
+__device__ __forceinline__ void epilogue_swiglu_fast(const GemmDev& g, uint32_t tmem_acc, int m0, int n0, int q, int half, int lane,
                                                      uint64_t* tfull_bar, uint32_t tfull_phase, uint32_t tmem_empty_bar,
                                                      uint8_t* stage, const CUtensorMap* tma_out) {
   static_assert(BN % 128 == 0, "SwiGLU fast epilogue: an even number of 32-column chunks per warp");
@@ -775,7 +775,10 @@ __device__ __forceinline__ void epilogue_qkv_rope(const GemmDev& g, uint32_t tme
 // --------------------------------------------------------------------------------------------
 // kernel
 // --------------------------------------------------------------------------------------------
-template <typename TIn, int BN, bool A_MN, bool B_MN, bool PAIR>
+// GATED: the kernel's only epilogue is the staged SwiGLU one (epilogue_swiglu_fast). It is a separate instantiation so that
+// the register allocation of the other epilogues does not change with it (inlined next to them it cost the split-K /
+// plain paths a few spills and ~5 % on the weight-gradient GEMMs).
+template <typename TIn, int BN, bool A_MN, bool B_MN, bool PAIR, bool GATED = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
@@ -1016,7 +1019,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // where this warp announces that it has drained the accumulator: the (leader's) MMA thread waits there
       const uint32_t tempty_addr = PAIR ? mapa_u32(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
       VY_TRACE(2 + e, local, 0);
-      if (!g.transposed_out && g.k_splits <= 1 && fast_mode < 0 && !(g.act == VY_ACT_SWIGLU && g.tma_store && BN % 128 == 0)) {  // the fast epilogues read the bias straight from global
+      if (!GATED && !g.transposed_out && g.k_splits <= 1 && fast_mode < 0) {  // the fast epilogues read the bias straight from global
         for (int j = et; j < BN; j += GEMM_EPI_WARPS * 32) {
           const int col = n0 + j;
           bs[j] = (g.bias && col < g.N) ? ld_as_float(g.bias, g.bias_dtype, col) : 0.f;
@@ -1024,6 +1027,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         named_bar_sync(1, GEMM_EPI_WARPS * 32);
       }
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if constexpr (GATED) {
+        epilogue_swiglu_fast<BN>(g, tmem_acc, m0, n0, q, half, lane, &tfull_bar[acc], acc_ph, tempty_addr, stage, &tma_out);
+        continue;
+      }
       if (g.debug & 1) {
         mbar_wait_soft(&tfull_bar[acc], acc_ph, g.poison);
         tc_fence_after();
@@ -1036,9 +1043,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       } else if (g.transposed_out) {
         epilogue_transposed<BN>(g, tmem_base + acc * BN, m0, n0, q, half, lane, et, &tfull_bar[acc], acc_ph, tempty_addr,
                                 reinterpret_cast<float*>(epi_stage));
-      } else if (g.act == VY_ACT_SWIGLU && g.tma_store && BN % 128 == 0) {
-        if constexpr (BN % 128 == 0)
-          epilogue_swiglu_fast<BN>(g, tmem_acc, m0, n0, q, half, lane, &tfull_bar[acc], acc_ph, tempty_addr, stage, &tma_out);
       } else if (fast_mode == EPI_PLAIN) {
         if (g.tma_store)
           epilogue_linear_fast<BN, EPI_PLAIN, true>(g, tmem_acc, m0, n0, q, half, lane, bs, &tfull_bar[acc], acc_ph, tempty_addr, stage,
@@ -1107,7 +1111,7 @@ static inline int get_tmap_2d(CUtensorMap* out, int dtype, const void* base, uin
   return get_tensor_map_cached(out, dtype, 2, base, dims, strides, box, swz);
 }
 
-template <typename TIn, int BN, bool A_MN, bool B_MN, bool PAIR>
+template <typename TIn, int BN, bool A_MN, bool B_MN, bool PAIR, bool GATED = false>
 int launch_gemm(const VyGemm* p, const GemmDev& g) {
   using Cfg = GemmCfg<TIn, BN>;
   const int dt = p->in_dtype;
@@ -1134,7 +1138,7 @@ int launch_gemm(const VyGemm* p, const GemmDev& g) {
       rc = get_tmap_2d(&taux, VY_BF16, p->aux, p->N, p->M, p->ld_aux * 2, 32, 32, 3);
     if (rc != VY_OK) gl.tma_store = 0;  // fall back to the staged st.global write-back
   }
-  auto kern = gemm_kernel<TIn, BN, A_MN, B_MN, PAIR>;
+  auto kern = gemm_kernel<TIn, BN, A_MN, B_MN, PAIR, GATED>;
   constexpr int smem_bytes = PAIR ? Cfg::PAIR_SMEM_BYTES : Cfg::SMEM_BYTES;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
