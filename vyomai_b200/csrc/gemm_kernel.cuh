@@ -382,6 +382,16 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
       wb_aux_delta[i] = (reinterpret_cast<__nv_bfloat16*>(g.aux) + static_cast<long long>(r) * g.ld_aux + gc0 + (lane & 3) * 8) - wb_out[i];
   }
   const int sw = (lane >> 1) & 3;
+  // bias of chunk c (32 columns = one or two cache lines) is pulled into L1 one chunk ahead: the broadcast loads in
+  // process() then hit L1 instead of stalling every warp on L2 at the top of every chunk
+  const int bias_es = g.bias_dtype == VY_BF16 ? 2 : 4;
+  auto prefetch_bias = [&](int c) {
+    if (g.bias && c < NCH && lane < 2) {
+      const int col = gc0 + c * 32 + lane * 16;
+      if (col < g.N) prefetch_l1(reinterpret_cast<const uint8_t*>(g.bias) + static_cast<long long>(col) * bias_es);
+    }
+  };
+  prefetch_bias(0);
 
   mbar_wait_soft(tfull_bar, tfull_phase, g.poison);
   tc_fence_after();
@@ -394,6 +404,7 @@ __device__ __forceinline__ void epilogue_linear_fast(const GemmDev& g, uint32_t 
       for (int j = 0; j < 4; ++j) pc[j] = pfc[j];
       fetch(pfc, c + 2);
     }
+    prefetch_bias(c + 1);
     const int nvalid = g.N - (gc0 + c * 32);
     if (nvalid <= 0) return;
     uint8_t* srow = stg + lane * 64;

@@ -259,9 +259,14 @@ VY_DEVINL uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   return r;
 }
 // arrive on an mbarrier given by a shared::cluster address (this CTA's own shared::cta addresses are valid ones)
+// (default semantics — release at CTA scope — like every barrier arrive of a tcgen05 pipeline: what the waiter consumes
+//  are TMEM reads ordered by tcgen05.fence, not global memory. Asking for .release.cluster makes the compiler emit
+//  MEMBAR.ALL + ERRBAR in front of the arrive, which waits for the warp's outstanding TMA / global stores: ~10 % of
+//  the epilogue warps' time in the ncu stall samples.)
 VY_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+VY_DEVINL void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // both CTAs of the pair execute these (one full warp each); the allocation is made in both TMEMs at the same columns
 VY_DEVINL void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
