@@ -235,3 +235,61 @@ def test_gradient_buckets_hold_whole_parameters():
         assert ex.buckets[b][0] <= st and st + n <= ex.buckets[b][1]
     small = [b for b in ex.buckets if b[1] - b[0] < 300]
     assert len(small) <= 1 and (not small or small[0][0] == 0)                     # only the last-walked bucket may be short
+
+
+def _ready_count_worker(rank, world, port, q):
+    import io
+    from contextlib import redirect_stdout
+    from dataclasses import make_dataclass
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vyomai_b200 import DecoderModel
+    from vyomai_b200.trainer import Trainer
+    C = make_dataclass("C", [("hidden_size", int, 128), ("num_attention_heads", int, 2), ("num_key_value_heads", int, 1),
+                             ("max_position_embeddings", int, 32), ("num_hidden_layers", int, 2), ("vocab_size", int, 61),
+                             ("hidden_dropout_prob", float, 0.0), ("layer_norm_eps", float, 1e-5), ("hidden_act", str, "gelu")])
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        model = DecoderModel(C(), "rope", "gqa")
+    tr = Trainer(model, bucket_mb=0.03, overlap=True, use_graph=False, grad_overwrite=False)  # ~8k-element buckets, CPU tensors
+    launched = []
+    tr.exchange.launch = lambda b: launched.append(b)  # record instead of reducing
+    tr.zero_grad()
+    ok = len(tr.exchange.buckets) > 4
+    members = {}
+    for p in tr.fp.params:
+        members.setdefault(tr._bucket_of[id(p)], []).append(p)
+    # backward order: last parameter first; every parameter reports TWICE (kernel + post-accumulate hook)
+    seen = {b: 0 for b in members}
+    for p in reversed(tr.fp.params):
+        b = tr._bucket_of[id(p)]
+        tr._on_grad(p)
+        seen[b] += 1
+        ok &= (b in launched) == (seen[b] == len(members[b]))  # launched exactly when its last parameter reported
+        tr._on_grad(p)                                           # the duplicate event changes nothing
+        ok &= launched.count(b) <= 1
+    ok &= sorted(launched) == sorted(members)
+    # a new step starts from scratch
+    tr.zero_grad()
+    ok &= tr._pending == {} and not tr._ready_ids
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_bucket_launches_once_every_parameter_reported_once_two_ranks_gloo():
+    """The overlapped all-reduce launches a bucket when its LAST parameter has reported, although every directly written
+    parameter reports twice per step (kernel-side _ready + autograd's post-accumulate hook). Counting both events reduced
+    buckets before their last writer had run (found on 2 GPUs with tools/dp_check.py)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ready_count_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
