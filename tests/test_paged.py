@@ -172,3 +172,41 @@ def test_continuous_batch_engine_matches_generate():
     for i in range(5):  # same tokens up to and including the stop token (generate() pads the rest of its row)
         assert got[i] == want[i][: len(got[i])], (i, got[i], want[i])
         assert len(got[i]) == len(prompts[i]) + 6 or got[i][-1] == 2
+
+
+def test_engine_scheduling_and_retirement_on_the_host():
+    """ContinuousBatchEngine's bookkeeping with the two model calls stubbed out (no GPU): at most max_batch_size
+    sequences are active, a request waits while the pool cannot hold its prompt, block tables grow one block at a time
+    during decoding, eos / length retire a sequence and return its blocks (notebook: ContinuousBatchEngine.step)."""
+    import io
+    from contextlib import redirect_stdout
+    from vyomai_b200 import DecoderModel
+    from vyomai_b200.paged import ContinuousBatchEngine, PagedKVManager
+    with redirect_stdout(io.StringIO()):
+        model = DecoderModel(CFG(), "rope", "gqa")
+    mgr = PagedKVManager(model, max_blocks=8, block_size=4, dtype=torch.float32, device="cpu")
+
+    class Stub(ContinuousBatchEngine):
+        def _prefill(self, s):      # next token = 10 + sequence id
+            return 10 + s.id
+
+        def _decode(self, states):  # sequence 1 emits eos (2) on its second decode step, the others count up
+            return [2 if (s.id == 1 and s.num_tokens == 8) else 20 + s.num_tokens for s in states]
+
+    eng = Stub(model, mgr, max_batch_size=2, eos_token_ids=[2])
+    sid0 = eng.add_sequence([5, 6, 7], max_gen_len=3)             # 3 + 3 tokens: 2 blocks at most
+    sid1 = eng.add_sequence([5, 6, 7, 8, 9, 3], max_gen_len=6)    # stops at eos after 3 generated tokens
+    sid2 = eng.add_sequence(list(range(3, 16)), max_gen_len=2)    # 13-token prompt: 4 blocks
+    assert (sid0, sid1, sid2) == (0, 1, 2)
+    done, max_active, steps = {}, 0, 0
+    while eng.waiting_room or eng.active:
+        done.update(eng.step())
+        max_active = max(max_active, len(eng.active))
+        steps += 1
+        assert len(mgr.free_blocks) + sum(s.block_count for s in eng.active.values()) == 8  # no block is lost
+        assert steps < 50
+    assert max_active <= 2
+    assert done[0] == [5, 6, 7, 10, 24, 25]                       # prefill token, then two decode tokens -> length 6
+    assert done[1] == [5, 6, 7, 8, 9, 3, 11, 27, 2]               # ends with the eos token
+    assert done[2][:13] == list(range(3, 16)) and len(done[2]) == 15 and done[2][13] == 12
+    assert len(mgr.free_blocks) == 8 and not eng.active and not eng.waiting_room
