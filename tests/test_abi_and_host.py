@@ -293,3 +293,47 @@ def test_bucket_launches_once_every_parameter_reported_once_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_gemm_tuner_picks_by_measurement_redirects_written_buffers_and_persists(tmp_path, monkeypatch):
+    """gemm_tune.hints with the timing stubbed: every buffer the GEMM writes is replaced by scratch during the trials
+    (the caller's `out` is never touched), a candidate must beat the model's own choice by more than the noise margin,
+    the winner is cached per signature, and VY_GEMM_TUNE_CACHE round-trips through a file."""
+    import json
+    from vyomai_b200 import _lib as L
+    from vyomai_b200 import gemm_tune as T
+
+    bf16, lin = L.CONSTS["VY_BF16"], L.CONSTS["VY_EPI_LINEAR"]
+    out = torch.zeros(256, 512)
+    kw = dict(M=256, N=512, K=768, in_dtype=bf16, epi=lin, a_mn_major=0, b_mn_major=0, transposed_out=0, out=out.data_ptr())
+    seen_ptrs = []
+
+    def fake_time(k, device, runs=3):
+        seen_ptrs.append(k["out"])
+        if k.get("hint_flavour") == 2 and k.get("hint_bn") == 128:
+            return 40.0   # clearly the best
+        if k.get("hint_flavour") == 1 and k.get("hint_bn") == 256:
+            return 49.5   # 1 % better than the model's choice: inside the noise margin
+        return 50.0 if "hint_bn" not in k else 60.0
+
+    monkeypatch.setattr(T, "_time", fake_time)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)  # no CUDA runtime in the CPU suite
+    monkeypatch.setattr(T, "ENABLED", True)
+    cache_file = tmp_path / "tune.json"
+    monkeypatch.setattr(T, "CACHE_FILE", str(cache_file))
+    monkeypatch.setattr(T, "_FILE_CACHE", {})
+    T.clear()
+    best = T.hints(("sig", 1), kw, [("out", out)], torch.device("cpu"))
+    assert best == dict(hint_flavour=2, hint_bn=128, hint_splits=1)
+    assert out.data_ptr() not in seen_ptrs and len(set(seen_ptrs)) == 1     # all trials wrote to one scratch buffer
+    n_calls = len(seen_ptrs)
+    assert T.hints(("sig", 1), kw, [("out", out)], torch.device("cpu")) == best and len(seen_ptrs) == n_calls  # cached
+    assert json.load(open(cache_file)) == {repr(("sig", 1)): best}
+    # a fresh process that loads the file launches no trials
+    T.clear()
+    monkeypatch.setattr(T, "_FILE_CACHE", json.load(open(cache_file)))
+    assert T.hints(("sig", 1), kw, [("out", out)], torch.device("cpu")) == best and len(seen_ptrs) == n_calls
+    # nothing beats the model by the margin -> no hint, and that (empty) verdict is cached as well
+    monkeypatch.setattr(T, "_time", lambda k, device, runs=3: 50.0 if "hint_bn" not in k else 49.5)
+    assert T.hints(("sig", 2), kw, [("out", out)], torch.device("cpu")) == {}
+    T.clear()
