@@ -2,13 +2,15 @@
 //
 //   warp 0      TMEM allocator, then TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 //   warp 1      MMA issuer    (one thread, tcgen05.mma, fp32 accumulators in TMEM; cta_group::2 in PAIR kernels: see gemm_kernel)
-//   warps 2..9  epilogue      (tcgen05.ld -> registers -> fused bias/act/residual/RoPE -> smem staging
-//                              -> coalesced global stores; two warps per TMEM lane quarter)
+//   warps 2..9  epilogue      (tcgen05.ld -> registers -> fused bias/act/residual/RoPE/SwiGLU -> smem staging
+//                              -> per-warp TMA bulk tensor stores (fast epilogues) or coalesced global stores;
+//                              two warps per TMEM lane quarter)
 //
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the mainloop of tile i+1; the row
 // operand an epilogue reads (residual, saved pre-activation) is prefetched before the accumulator is
-// awaited. Tile = 128 x BN x (128 bytes of K), BN in {32, 64, 128, 192, 256} chosen per shape to
-// minimise the number of waves over the 148 SMs: BK = 64 bf16 or 32 tf32 elements, so every smem stage has
+// awaited. Tile = 128 x BN x (128 bytes of K) on one SM, or 256 x BN on a CTA pair (two SMs, one M = 256 MMA,
+// each CTA staging half of B: see gemm_kernel); BN in {32, 64, 128, 192, 256}. Flavour, BN and K split are chosen
+// per call (gemm.cu: choose_tiling, VyGemm.hint_*): BK = 64 bf16 or 32 tf32 elements, so every smem stage has
 // the same byte geometry for both input types. Operands may be K-major (nn.Linear layout) or
 // MN-major (transposed storage, used by dgrad / wgrad) — only the TMA box and the UMMA
 // descriptor change.
