@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VY_ABI_VERSION 5
+#define VY_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define VY_API __attribute__((visibility("default")))
@@ -153,6 +153,10 @@ typedef struct VyGemm {
   void* v_out;
   int64_t v_sb, v_sh, v_sl;
   int32_t kv_out_dtype; /* dtype of k_out / v_out (a kv-cache may be fp32 while q_out is bf16) */
+  int32_t kv_cap;       /* token slots of k_out / v_out (0 = unchecked): kv_dst_pos0 + tokens_per_seq must not exceed it —
+                         * the reference fails on the slice assignment (kv_cache.py:355-359), this call returns
+                         * VY_ERR_INVALID_ARG instead of writing past the cache */
+  int32_t rope_rows;    /* rows of rope_cos / rope_sin (0 = unchecked): start_pos + tokens_per_seq must not exceed it */
 
   /* optional split-K scratch (fp32). When a GEMM has too few output tiles to fill the SMs and a long K (the
    * weight gradients dW = dY^T X, K = tokens), the library splits K over several CTAs per tile, writes fp32
@@ -178,6 +182,10 @@ VY_API int vy_gemm(const VyGemm* p);
  * protocol to completion, 1 = some launch did not, -1 = the flag could not be read); a raised flag is lowered by the
  * read. Synchronises the device. */
 VY_API int vy_gemm_poisoned(void);
+/* Same flag without synchronising (a pinned host mirror the kernels write on a timeout): 1 once a GEMM of the current
+ * device has timed out and nobody has acknowledged it through vy_gemm_poisoned(), else 0. While it is raised every
+ * vy_gemm call on that device fails with VY_ERR_CUDA, so a corrupted result cannot feed later work silently. */
+VY_API int vy_gemm_poison_peek(void);
 /* Development hook (tools/gemm_sweep.py): pin the kernel flavour (pair: -1 auto, 0 single CTA, 1 CTA pair), the tile
  * width (bn: 0 auto) and the K split (splits: 0 auto) of subsequent vy_gemm calls of this process. */
 VY_API int vy_gemm_tune_override(int pair, int bn, int splits);
@@ -226,6 +234,20 @@ typedef struct VyNorm {
    * xhat (Examples/paligemma.ipynb GemmaRMSNorm). For both, beta may be NULL, mean is unused, and bwd's dbeta
    * receives the column sums of dy (meaningful only when a shift is trained). */
   int32_t kind;
+  /* Dropout on x before the residual add — `self.dropout(hidden_states)` at VyomAI/layers/attention.py:70 and
+   * VyomAI/layers/ffn.py:38, live in .train() with hidden_dropout_prob (0.1 in every reference config):
+   *   y = Norm(keep * x / (1 - p) + residual),  keep ~ Bernoulli(1 - p) per element.
+   * The mask is never stored: element e of the call is kept iff a 16-bit lane of Philox4x32-10(key = dropout_seed,
+   * counter = (e / 8, dropout_offset, step)) is >= round(p * 65536), so bwd regenerates it from the same
+   * (seed, offset, step). `step` is *dropout_step_ptr (device int32, e.g. the trainer's step counter, so a captured
+   * CUDA graph draws a fresh mask on every replay) or 0. dropout_p == 0 disables all of it.
+   * bwd: dx (= d residual) is the gradient of the pre-norm sum; dx_drop (required when dropout_p > 0) receives
+   * keep * dx / (1 - p) = the gradient of x, and dbias is then its column sum. */
+  float dropout_p;
+  uint64_t dropout_seed;
+  uint32_t dropout_offset;
+  const int32_t* dropout_step_ptr;
+  void* dx_drop;
   void* stream;
 } VyNorm;
 
@@ -339,6 +361,11 @@ VY_API int vy_rope_apply(const VyRope* p);
  * backward rather than a GEMM (inside the FFN the same factor rides in the dgrad GEMM epilogue). */
 VY_API int vy_act_bwd(int64_t n, const void* dy, const void* z, int dtype, int act, void* out, void* stream);
 
+/* vy_scale_by_ptr — x[i] *= *scale (device scalar, fp32) over a contiguous buffer; returns immediately on the device when
+ * *scale == 1. Applies an arbitrary upstream gradient to the d logits the fused LM-head + cross-entropy node has already
+ * written (loss.backward() passes 1, a scaled or accumulated loss does not). */
+VY_API int vy_scale_by_ptr(int64_t n, void* x, int dtype, const float* scale, void* stream);
+
 /* vy_swiglu_bwd — gradient of h[r, j] = silu(z[r, 2j]) * z[r, 2j+1] w.r.t. the interleaved pre-activations:
  * dz[r, 2j] = dh[r, j] * z[r, 2j+1] * silu'(z[r, 2j]), dz[r, 2j+1] = dh[r, j] * silu(z[r, 2j]); dz then feeds the
  * ordinary dgrad / wgrad GEMMs against the interleaved weight. dh [rows, I], z / dz [rows, 2 I], contiguous, I % 8 == 0. */
@@ -371,8 +398,11 @@ typedef struct VyDecode {
   const void* qkv;
   int64_t ld_qkv;
   int32_t qkv_dtype;
-  const float* rope_cos; /* [cache_len][32] fp32 or NULL */
+  const float* rope_cos; /* fp32 [rope_rows][32] or NULL; the new token's angles are row (position + rope_pos_off) */
   const float* rope_sin;
+  int32_t rope_pos_off;  /* table row of cache slot 0 (0 when the tables start at position 0; negative offsets are how
+                            a caller that only holds the angle rows of the CURRENT positions addresses them) */
+  int32_t rope_rows;     /* rows of the tables (0 = unchecked); start_pos + rope_pos_off must lie inside */
   void* k_cache;
   void* v_cache;
   int64_t cache_sb, cache_sh, cache_sl;
@@ -429,6 +459,12 @@ typedef struct VyEmbed {
   const void* dout;
   void* dtable; /* or NULL */
   void* dpos;   /* or NULL */
+  /* nn.Embedding(padding_idx=...) never receives a gradient for that row (models/encoder.py:100-104 word_embeddings;
+   * layers/positional_embeddings.py:20-24 builds the learned position table with padding_idx = pad_token_id too).
+   * Stored as index + 1 so that zero-initialised structs mean "no padding row": bwd skips ids[r] == padding_idx_plus1 - 1
+   * for dtable and position row == pos_padding_idx_plus1 - 1 for dpos. */
+  int64_t padding_idx_plus1;
+  int64_t pos_padding_idx_plus1;
   void* stream;
 } VyEmbed;
 

@@ -547,3 +547,47 @@ def gated_mlp(x: Tensor, w_gate: Tensor, w_up: Tensor, w_down: Tensor) -> Tensor
     """MLP.forward (models/custom_transformer.py:87-89): down_proj(act_fn(gate_proj(x)) * up_proj(x)), no biases,
     act_fn = SiLU for the shipped configs."""
     return linear(silu(linear(x, w_gate, None)) * linear(x, w_up, None), w_down, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# dropout (layers/attention.py:55,70; layers/ffn.py:24,38): nn.Dropout(hidden_dropout_prob) on the Linear output before
+# the residual add. The reference draws its mask from torch's global RNG stream, which no fused kernel can replay; the
+# CUDA path draws its own counter-based mask (Philox4x32-10, include/vyom_b200.h VyNorm.dropout_*). This is the CPU
+# restatement of THAT mask (integer arithmetic: bit-exact), so tests can pin which elements were dropped and then check
+# the surrounding floating-point math against layer_norm() above with the same mask.
+# ----------------------------------------------------------------------------------------------
+def philox4x32_10(ctr, key):
+    """ctr: uint32 array [..., 4], key: (k0, k1). Returns uint32 [..., 4] (Salmon et al. 2011, 10 rounds)."""
+    import numpy as np
+    c = [ctr[..., i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = m0 * c[0]
+        p1 = m1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [(hi1 ^ c[1] ^ k0) & mask, lo1, (hi0 ^ c[3] ^ k1) & mask, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def dropout_keep_mask(rows: int, H: int, p: float, seed: int, offset: int, step: int = 0) -> Tensor:
+    """[rows, H] bool: element (r, c) is kept iff 16-bit lane (c % 8) of Philox(counter = (vec lo, vec hi, offset, step),
+    key = seed) is >= round(p * 65536), vec = (r * H + c) // 8."""
+    import numpy as np
+    nvec = rows * H // 8
+    vec = np.arange(nvec, dtype=np.uint64)
+    ctr = np.stack([(vec & np.uint64(0xFFFFFFFF)).astype(np.uint32), (vec >> np.uint64(32)).astype(np.uint32),
+                    np.full(nvec, offset, dtype=np.uint32), np.full(nvec, step, dtype=np.uint32)], axis=-1)
+    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    lanes = np.stack([(r[:, j >> 1] >> np.uint32(16 * (j & 1))) & np.uint32(0xFFFF) for j in range(8)], axis=-1)
+    thresh = int(p * 65536.0 + 0.5)
+    return torch.from_numpy((lanes >= thresh).reshape(rows, H))
+
+
+def dropout_add_layer_norm(x: Tensor, residual: Tensor, keep: Tensor, p: float, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
+    """LN(dropout(x) + residual) with a given keep mask (attention.py:70-71, ffn.py:38-39)."""
+    return layer_norm(torch.where(keep, x / (1.0 - p), torch.zeros_like(x)) + residual, gamma, beta, eps)

@@ -68,3 +68,32 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor, floor: float = 0.0) -> float:
     gradient, which softmax shift-invariance makes exactly 0) from comparing rounding noise."""
     a, b = a.detach().double(), b.detach().double()
     return float((a - b).norm() / max(float(b.norm()), floor, 1e-30))
+
+
+def seeded_state_dict(shapes: dict, seed: int) -> dict:
+    """{key: shape} -> {key: tensor}: N(0, 0.02) matrices / embeddings / biases, 1 + N(0, 0.1) norm scales, drawn key by
+    key in sorted order from one CPU generator and rounded to bf16-representable fp32. The real-width fixtures
+    (tests/golden/make_golden_real.py) store no weights: generator and tests both rebuild them with this recipe."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        t = torch.randn(shp, generator=g)
+        if ("layernorm.weight" in k or "layer_norm.weight" in k) and len(shp) == 1:
+            t = 1.0 + 0.1 * t
+        else:
+            t = 0.02 * t
+        out[k] = t.bfloat16().float()
+    return out
+
+
+def real_state_dict(model_or_shapes, seed: int) -> dict:
+    """seeded_state_dict over the floating-point entries of a module's state_dict (or a {key: shape} dict), with the LM
+    head's shared bias present under both of its keys."""
+    shapes = model_or_shapes
+    if not isinstance(shapes, dict):
+        shapes = {k: tuple(v.shape) for k, v in model_or_shapes.state_dict().items() if v.dtype.is_floating_point}
+    sd = seeded_state_dict(shapes, seed)
+    if "lm_head.bias" in sd:
+        sd["lm_head.decoder.bias"] = sd["lm_head.bias"]
+    return sd

@@ -190,7 +190,47 @@ def test_vlm_forward_and_generate(dtype):
         g2 = generate_multimodel(vlm, enc, None, start, max_new_tokens=6, use_cache=True)
         vlm._clean_cache()
         assert torch.equal(g0, g1) and torch.equal(g0, g2)
-        assert list(g0.shape) == list(fx.outputs["generate"].shape)
+        ref = fx.outputs["generate"]
+        assert list(g0.shape) == list(ref.shape)
+        # ids against the REFERENCE's: bit-exact wherever its top-1 / top-2 margin exceeds the path's tolerance
+        from oracle import vyom_oracle as O
+        margins = []
+        for cur in range(1, ref.shape[1]):
+            lgt = O.vlm_decoder_forward(fx.sd, fx.cfg(), ref[:, :cur], None, fx.outputs["encoder_output"], m["pos"], m["attn"])
+            top2 = lgt[:, -1].topk(2, dim=-1).values
+            margins.append(float((top2[:, 0] - top2[:, 1]).min()))
+        n_checked = _ids_match_up_to_ambiguity(g0.cpu(), ref, margins, 1, MARGIN[dtype])
+        assert n_checked >= 1, margins
+        print(f"vlm {dtype}: greedy ids bit-exact for {n_checked}/{len(margins)} steps; identical to reference: {torch.equal(g0.cpu(), ref)}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["decoder_rope_gqa", "decoder_absolute_mha"])
+def test_generation_utils_generate(name, dtype):
+    """generation_utils.generate (reference: generation_utils.py:6-51) with the model its signature fits — DecoderModel
+    without a cache (the function never passes a kv_cache, so use_cache=True cannot work there either): greedy ids
+    against the oracle's decoder_forward, bit-exact up to the first ambiguous step (margin rule)."""
+    from vyomai_b200 import DecoderModel, generate
+    from oracle import vyom_oracle as O
+    fx = load_fixture(name)
+    m = fx.meta
+    model = _load(DecoderModel(_cfg_obj(m), m["pos"], m["attn"]), fx.sd, dtype)
+    start = fx.inputs["prompt"]
+    got = generate(model, start.cuda(), max_new_tokens=4, use_cache=False).cpu()
+    assert got.shape == (2, 8) and torch.equal(got[:, :4], start)
+    idx = start.clone()
+    checked = 0
+    for i in range(4):
+        _, lg = O.decoder_forward(fx.sd, fx.cfg(), idx, None, m["pos"], m["attn"])
+        top2 = lg[:, -1].topk(2, dim=-1)
+        if float((top2.values[:, 0] - top2.values[:, 1]).min()) <= MARGIN[dtype]:
+            break  # ambiguous step: continuations are incomparable from here on
+        idx = torch.cat([idx, top2.indices[:, :1]], dim=1)
+        assert torch.equal(got[:, : idx.shape[1]], idx), (i, got, idx)
+        checked += 1
+    print(f"generate {name} {dtype}: {checked}/4 steps bit-exact")
+    with pytest.raises(ValueError):  # like the reference: a cached call without a kv_cache object is an error
+        generate(model, start.cuda(), max_new_tokens=2, use_cache=True)
 
 
 @pytest.mark.parametrize("name", ["decoder_rope_gqa", "decoder_rope_mha"])

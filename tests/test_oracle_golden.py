@@ -153,3 +153,102 @@ def test_rope_matches_closed_form():
     th = p * 10000 ** (-2 * j / 8)
     want = q[0, 0, p, j] * torch.cos(torch.tensor(th)) - q[0, 0, p, j + 4] * torch.sin(torch.tensor(th))
     assert abs(float(qr[0, 0, p, j] - want)) < 1e-5
+
+
+# ---- real-width fixtures (tests/golden/make_golden_real.py): weights rebuilt from the seeded recipe ----
+def _real_fixture(name, shapes_from):
+    from tests.conftest import real_state_dict
+    fx = load_fixture(name)
+    return fx, real_state_dict(shapes_from(fx.meta), fx.meta["weight_seed"])
+
+
+def _encoder_shapes(m, lm_head=False):
+    H, V, kv = m["hidden_size"], m["vocab_size"], m["num_key_value_heads"] * (m["hidden_size"] // m["num_attention_heads"])
+    s = {"word_embeddings.weight": (V, H)}
+    for i in range(m["num_hidden_layers"]):
+        p = f"all_layer.{i}."
+        s.update({p + "attention.query.weight": (H, H), p + "attention.query.bias": (H,),
+                  p + "attention.key.weight": (kv, H), p + "attention.key.bias": (kv,),
+                  p + "attention.value.weight": (kv, H), p + "attention.value.bias": (kv,),
+                  p + "attention.out.dense.weight": (H, H), p + "attention.out.dense.bias": (H,),
+                  p + "attention.out.layernorm.weight": (H,), p + "attention.out.layernorm.bias": (H,),
+                  p + "feed_forward.intermediate.weight": (4 * H, H), p + "feed_forward.intermediate.bias": (4 * H,),
+                  p + "feed_forward.out.weight": (H, 4 * H), p + "feed_forward.out.bias": (H,),
+                  p + "feed_forward.layernorm.weight": (H,), p + "feed_forward.layernorm.bias": (H,)})
+    if lm_head:
+        s.update({"lm_head.dense.weight": (H, H), "lm_head.dense.bias": (H,), "lm_head.layer_norm.weight": (H,),
+                  "lm_head.layer_norm.bias": (H,), "lm_head.decoder.weight": (V, H), "lm_head.bias": (V,),
+                  "lm_head.decoder.bias": (V,)})
+    return s
+
+
+def test_real_width_encoder_forward_and_grads():
+    """C1 shape (8 x 128, H 768, 12 / 4 heads): the oracle against the reference's outputs and gradients."""
+    fx, sd = _real_fixture("encoder_real_rope_gqa", _encoder_shapes)
+    m = fx.meta
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ids, mask = fx.inputs["input_ids"], fx.inputs["attention_mask"]
+    out = O.encoder_forward(sd, fx.cfg(), ids, mask, m["pos"], m["attn"])
+    assert rel_l2(out[:, ::8], fx.outputs["logits_rows"]) <= FWD_TOL
+    cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(m["cotangent_seed"])) * mask[..., None]
+    (out * cot).sum().backward()
+    n = 0
+    for k, g in fx.outputs.items():
+        if not k.startswith("grad::"):
+            continue
+        name = k[6:]
+        got = sd[name].grad
+        assert abs(float(got.norm()) - m["grad_norms"][name]) <= 1e-4 * max(m["grad_norms"][name], 1e-3), name
+        if name == "word_embeddings.weight":
+            got = got[fx.inputs["emb_rows"]]
+        elif got.dim() == 2:
+            got = got[:64, :64]
+        assert rel_l2(got, g, floor=1e-4) <= 5 * GRAD_TOL, name
+        n += 1
+    assert n >= 17
+
+
+def test_real_width_decoder_prefill_decode_generate():
+    """200-token causal prefill + 3 decode steps through the static cache + greedy generate at H 768."""
+    fx, sd = _real_fixture("decoder_real_rope_gqa", lambda m: _encoder_shapes(m, lm_head=True))
+    m, cfg = fx.meta, fx.cfg()
+    prompt = fx.inputs["prompt"]
+    B, P = prompt.shape
+    N = m["new_tokens"]
+    cache = O.StaticCacheOneOracle(cfg.num_hidden_layers, B, cfg.kv_heads("gqa"), P + N, cfg.head_dim)
+    h, logits = O.decoder_forward(sd, cfg, prompt, torch.ones(B, P, dtype=torch.long), "rope", "gqa", cache, 0)
+    assert rel_l2(logits[:, -1], fx.outputs["prefill_last_logits"]) <= FWD_TOL
+    assert rel_l2(h[:, ::25], fx.outputs["prefill_hidden_rows"]) <= FWD_TOL
+    steps = []
+    for t in range(3):
+        _, lg = O.decoder_forward(sd, cfg, fx.inputs["decode_tokens"][:, t:t + 1], None, "rope", "gqa", cache, P + t)
+        steps.append(lg)
+    assert rel_l2(torch.cat(steps, 1), fx.outputs["decode_logits"]) <= FWD_TOL
+    assert rel_l2(cache.key_cache[0][:, :, ::16], fx.outputs["key_cache_l0_s16"]) <= FWD_TOL
+    assert rel_l2(cache.value_cache[0][:, :, ::16], fx.outputs["value_cache_l0_s16"]) <= FWD_TOL
+    ids = O.decoder_generate(sd, cfg, prompt, torch.ones(B, P, dtype=torch.long), max_len=N, pos_type="rope",
+                             attention_type="gqa", cache_kind="static")
+    ref = fx.outputs["generate"]
+    for i, mg in enumerate(m["generate_margins"]):  # fp32 vs fp32: identical wherever the margin is not rounding noise
+        if mg <= 1e-4:
+            break
+        assert torch.equal(ids[:, P + i], ref[:, P + i]), (i, mg)
+
+
+def test_philox_known_answers_and_dropout_mask():
+    """Philox4x32-10 against the Random123 known-answer vectors; the keep mask has the stated rate and depends on every
+    coordinate of its identity (seed, offset, step)."""
+    import numpy as np
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert tuple(int(x) for x in got) == want
+    a = O.dropout_keep_mask(256, 768, 0.1, 99, 1, 0)
+    assert abs(float(a.float().mean()) - 0.9) < 3e-3
+    for other in (O.dropout_keep_mask(256, 768, 0.1, 100, 1, 0), O.dropout_keep_mask(256, 768, 0.1, 99, 2, 0),
+                  O.dropout_keep_mask(256, 768, 0.1, 99, 1, 1)):
+        assert 0.1 < float((a != other).float().mean()) < 0.25  # independent masks differ on ~2 p (1 - p) of the elements
+    assert torch.equal(a, O.dropout_keep_mask(256, 768, 0.1, 99, 1, 0))
+    assert bool(O.dropout_keep_mask(8, 64, 0.0, 5, 0, 0).all())

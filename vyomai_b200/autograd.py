@@ -43,15 +43,16 @@ def attention_block_fn(mod, x2d: torch.Tensor, B: int, S: int, mask: MaskSpec, r
     w_qkv, b_qkv = F.pack_linears(lin)
     attn, _ = F.attention_core(x2d, B, S, w_qkv, b_qkv, mod.num_attention_heads, mod._kv_heads, mask, rope, kv,
                                decode_no_mask, pos0=start_pos)
-    y, _ = F.self_output(attn, x2d, dense, ln)
+    y, _ = F.self_output(attn, x2d, dense, ln, dropout=F.dropout_state(mod.out, mod.out.dropout.p))
     return y
 
 
-def self_output_fn(attn2d: torch.Tensor, residual2d: torch.Tensor, dense: nn.Linear, ln: nn.LayerNorm) -> torch.Tensor:
+def self_output_fn(attn2d: torch.Tensor, residual2d: torch.Tensor, dense: nn.Linear, ln: nn.LayerNorm,
+                   dropout=None) -> torch.Tensor:
     if _needs_grad(attn2d, residual2d, dense.weight, ln.weight):
         from .autograd_train import SelfOutputFn
-        return SelfOutputFn.apply(attn2d, residual2d, dense.weight, dense.bias, ln.weight, ln.bias, ln.eps)
-    y, _ = F.self_output(attn2d, residual2d, dense, ln)
+        return SelfOutputFn.apply(attn2d, residual2d, dense.weight, dense.bias, ln.weight, ln.bias, ln.eps, dropout)
+    y, _ = F.self_output(attn2d, residual2d, dense, ln, dropout=dropout)
     return y
 
 
@@ -59,9 +60,9 @@ def feed_forward_fn(mod, h2d: torch.Tensor, input2d: torch.Tensor) -> torch.Tens
     inter, out, ln = mod.intermediate, mod.out, mod.layernorm
     if _needs_grad(h2d, input2d, inter.weight, out.weight, ln.weight):
         from .autograd_train import FeedForwardFn
-        return FeedForwardFn.apply(mod._act_name, ln.eps, h2d, input2d, inter.weight, inter.bias, out.weight, out.bias,
-                                   ln.weight, ln.bias)
-    y, _ = F.feed_forward(h2d, input2d, inter, out, ln, act=mod._act_name)
+        return FeedForwardFn.apply(mod._act_name, ln.eps, F.dropout_state(mod, mod.dropout.p), h2d, input2d, inter.weight,
+                                   inter.bias, out.weight, out.bias, ln.weight, ln.bias)
+    y, _ = F.feed_forward(h2d, input2d, inter, out, ln, act=mod._act_name, dropout=F.dropout_state(mod, mod.dropout.p))
     return y
 
 
@@ -82,13 +83,15 @@ def lm_head_loss_fn(mod, h2d: torch.Tensor, labels: torch.Tensor, ignore_index: 
 
 
 def embed_fn(ids: torch.Tensor, table: torch.Tensor, pos_table: Optional[torch.Tensor], pos_row_off: int,
-             tokens_per_seq: int, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
+             tokens_per_seq: int, extra: Optional[torch.Tensor] = None, padding_idx: Optional[int] = None,
+             pos_padding_idx: Optional[int] = None) -> torch.Tensor:
     """hidden rows [B * (tokens_per_seq + (extra is not None)), H] = table[ids] (+ position rows), with an
-    optional leading row per sequence copied from `extra` [B, H] (the captioner's image vector)."""
+    optional leading row per sequence copied from `extra` [B, H] (the captioner's image vector). `padding_idx` /
+    `pos_padding_idx`: rows of the word / learned-position tables that nn.Embedding(padding_idx=...) keeps gradient-free."""
     from .autograd_train import EmbedFn
     if _needs_grad(table, pos_table, extra):
-        return EmbedFn.apply(ids, table, pos_table, pos_row_off, tokens_per_seq, extra)
-    return EmbedFn.forward(_NoCtx(), ids, table, pos_table, pos_row_off, tokens_per_seq, extra)
+        return EmbedFn.apply(ids, table, pos_table, pos_row_off, tokens_per_seq, extra, padding_idx, pos_padding_idx)
+    return EmbedFn.forward(_NoCtx(), ids, table, pos_table, pos_row_off, tokens_per_seq, extra, padding_idx, pos_padding_idx)
 
 
 class _NoCtx:

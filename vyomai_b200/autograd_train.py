@@ -79,27 +79,34 @@ def _emit_bgrad(p: Optional[torch.Tensor], dy2d: torch.Tensor) -> Optional[torch
 
 
 def _ln_bwd(dy: torch.Tensor, s: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean, rstd,
-            bias: Optional[torch.Tensor] = None):
+            bias: Optional[torch.Tensor] = None, dropout=None):
     """LayerNorm backward. Returns (ds, d_gamma, d_beta, d_bias); `bias` is the bias of the Linear whose output was
-    normalised (its gradient = column sums of ds, produced by the same kernels). With trainer-owned gradient buffers
-    the parameter gradients are accumulated in place by the reduce kernel and None is returned for them."""
+    normalised (its gradient = column sums of that Linear's output gradient, produced by the same kernels). With
+    trainer-owned gradient buffers the parameter gradients are accumulated in place by the reduce kernel and None is
+    returned for them. With `dropout` (the forward's DropoutState) ds is the pair (gradient of the pre-norm sum = of the
+    residual, gradient of the dropped Linear output)."""
     direct = _direct(gamma) and _direct(beta) and gamma.grad.dtype == beta.grad.dtype
     if direct and (bias is None or (_direct(bias) and bias.grad.dtype == gamma.grad.dtype)):
         over = _overwrite(gamma) and _overwrite(beta) and (bias is None or _overwrite(bias))
         if not over and (_overwrite(gamma) or _overwrite(beta) or _overwrite(bias)):
             raise RuntimeError("a LayerNorm's weight / bias and the preceding Linear's bias must share the gradient write mode")
         ds = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out=gamma.grad, dbeta_out=beta.grad,
-                                   dbias_out=bias.grad if bias is not None else None, accumulate=not over)[0]
+                                   dbias_out=bias.grad if bias is not None else None, accumulate=not over, dropout=dropout)[0]
         _ready(gamma)
         _ready(beta)
         if bias is not None:
             _ready(bias)
         return ds, None, None, None
     if bias is not None:
-        ds, dgamma, dbeta, dbias = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, want_dbias=True)
+        ds, dgamma, dbeta, dbias = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, want_dbias=True, dropout=dropout)
         return ds, dgamma.to(gamma.dtype), dbeta.to(beta.dtype), dbias.to(bias.dtype)
-    ds, dgamma, dbeta = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd)
+    ds, dgamma, dbeta = ops.add_layernorm_bwd(dy, s, gamma, mean, rstd, dropout=dropout)
     return ds, dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None
+
+
+def _split_ds(ds):
+    """(gradient of the residual, gradient of the Linear output) from _ln_bwd's first result."""
+    return ds if isinstance(ds, tuple) else (ds, ds)
 
 
 def _packed_grads(params) -> Optional[torch.Tensor]:
@@ -128,7 +135,8 @@ class AttentionBlockFn(torch.autograd.Function):
         attn, saved = F.attention_core(x2d, B, S, w_qkv, b_qkv, mod.num_attention_heads, mod._kv_heads, mask, rope,
                                        None, False, need_lse=True, pos0=start_pos)
         q, k, v, lse = saved
-        y, (s, mean, rstd) = F.self_output(attn, x2d, dense, ln, save=True)
+        ctx.drop = F.dropout_state(mod.out, mod.out.dropout.p)
+        y, (s, mean, rstd) = F.self_output(attn, x2d, dense, ln, save=True, dropout=ctx.drop)
         ctx.mod, ctx.B, ctx.S, ctx.mask, ctx.rope, ctx.start_pos = mod, B, S, mask, rope, start_pos
         ctx.n_w = len(lin)
         ctx.has_qkv_bias = lin[0].bias is not None
@@ -145,9 +153,10 @@ class AttentionBlockFn(torch.autograd.Function):
         w_qkv, _ = F.pack_linears(lin)
         Hq, Hkv, d = mod.num_attention_heads, mod._kv_heads, F.HEAD_DIM
         dy = dy.contiguous()
-        ds, dgamma, dbeta, d_bo = _ln_bwd(dy, s, ln.weight, ln.bias, mean, rstd, bias=dense.bias)
-        d_wo = _emit_wgrad(dense.weight, ds, attn)
-        d_attn = _dgrad(ds, dense.weight, out_dtype=torch.bfloat16)  # bf16: MMA operand of the attention backward
+        ds, dgamma, dbeta, d_bo = _ln_bwd(dy, s, ln.weight, ln.bias, mean, rstd, bias=dense.bias, dropout=ctx.drop)
+        ds, dxo = _split_ds(ds)  # residual gradient, gradient of dense(attn) (the dropped branch)
+        d_wo = _emit_wgrad(dense.weight, dxo, attn)
+        d_attn = _dgrad(dxo, dense.weight, out_dtype=torch.bfloat16)  # bf16: MMA operand of the attention backward
         dqkv = torch.empty((B * S, (Hq + 2 * Hkv) * d), device=dy.device, dtype=x2d.dtype)
         cos = sin = None
         rope_pos0 = 0
@@ -197,9 +206,14 @@ class SelfOutputFn(torch.autograd.Function):
     """y = LN(dense(attn) + residual) (AttentionSelfOutput used stand-alone)."""
 
     @staticmethod
-    def forward(ctx, attn2d, residual2d, w, b, gamma, beta, eps):
-        s = F._lin(attn2d, w, b, addend=residual2d)
-        y, _, mean, rstd = ops.add_layernorm(s, None, gamma, beta, eps, save_stats=True)
+    def forward(ctx, attn2d, residual2d, w, b, gamma, beta, eps, dropout=None):
+        if dropout is None:
+            s = F._lin(attn2d, w, b, addend=residual2d)
+            y, _, mean, rstd = ops.add_layernorm(s, None, gamma, beta, eps, save_stats=True)
+        else:
+            y, s, mean, rstd = ops.add_layernorm(F._lin(attn2d, w, b), residual2d.contiguous(), gamma, beta, eps, save_stats=True,
+                                                 save_sum=True, dropout=dropout)
+        ctx.drop = dropout
         ctx.has_bias = b is not None
         ctx.save_for_backward(attn2d, w, gamma, s, mean, rstd)
         ctx.bdt = b.dtype if b is not None else None
@@ -208,22 +222,28 @@ class SelfOutputFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         attn2d, w, gamma, s, mean, rstd = ctx.saved_tensors
-        ds, dgamma, dbeta = ops.add_layernorm_bwd(dy.contiguous(), s, gamma, mean, rstd)
-        d_w = _wgrad(ds, attn2d, w)
-        d_b = ops.colsum(ds, out_dtype=ctx.bdt) if ctx.has_bias else None
-        d_attn = _dgrad(ds, w)
-        return d_attn, ds, d_w, d_b, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None
+        ds, dgamma, dbeta = ops.add_layernorm_bwd(dy.contiguous(), s, gamma, mean, rstd, dropout=ctx.drop)
+        ds, dxo = _split_ds(ds)
+        d_w = _wgrad(dxo, attn2d, w)
+        d_b = ops.colsum(dxo, out_dtype=ctx.bdt) if ctx.has_bias else None
+        d_attn = _dgrad(dxo, w)
+        return d_attn, ds, d_w, d_b, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None
 
 
 class FeedForwardFn(torch.autograd.Function):
     """y = LN(W2 act(W1 h + b1) + b2 + input)."""
 
     @staticmethod
-    def forward(ctx, act, eps, h2d, input2d, w1, b1, w2, b2, gamma, beta):
+    def forward(ctx, act, eps, dropout, h2d, input2d, w1, b1, w2, b2, gamma, beta):
         z = torch.empty((h2d.shape[0], w1.shape[0]), device=h2d.device, dtype=h2d.dtype)
         a = F._lin(h2d, w1, b1, act=act, aux=z)
-        s = F._lin(a, w2, b2, addend=input2d)
-        y, _, mean, rstd = ops.add_layernorm(s, None, gamma, beta, eps, save_stats=True)
+        if dropout is None:
+            s = F._lin(a, w2, b2, addend=input2d)
+            y, _, mean, rstd = ops.add_layernorm(s, None, gamma, beta, eps, save_stats=True)
+        else:
+            y, s, mean, rstd = ops.add_layernorm(F._lin(a, w2, b2), input2d.contiguous(), gamma, beta, eps, save_stats=True,
+                                                 save_sum=True, dropout=dropout)
+        ctx.drop = dropout
         ctx.act = act
         ctx.params = (w1, b1, w2, b2, gamma, beta)  # the Parameter objects (direct-gradient attributes live on them)
         ctx.save_for_backward(h2d, z, a, s, mean, rstd)
@@ -233,13 +253,14 @@ class FeedForwardFn(torch.autograd.Function):
     def backward(ctx, dy):
         h2d, z, a, s, mean, rstd = ctx.saved_tensors
         w1, b1, w2, b2, gamma, beta = ctx.params
-        ds, dgamma, dbeta, d_b2 = _ln_bwd(dy.contiguous(), s, gamma, beta, mean, rstd, bias=b2)
-        d_w2 = _emit_wgrad(w2, ds, a)
-        dz = _dgrad(ds, w2, act="d" + ctx.act, aux=z)  # (dS W2) * act'(z) in the dgrad epilogue
+        ds, dgamma, dbeta, d_b2 = _ln_bwd(dy.contiguous(), s, gamma, beta, mean, rstd, bias=b2, dropout=ctx.drop)
+        ds, dxo = _split_ds(ds)  # gradient of input_tensor, gradient of the second Linear's output
+        d_w2 = _emit_wgrad(w2, dxo, a)
+        dz = _dgrad(dxo, w2, act="d" + ctx.act, aux=z)  # (dS W2) * act'(z) in the dgrad epilogue
         d_w1 = _emit_wgrad(w1, dz, h2d)
         d_b1 = _emit_bgrad(b1, dz)
         dh = _dgrad(dz, w1)
-        return None, None, dh, ds, d_w1, d_b1, d_w2, d_b2, dgamma, dbeta
+        return None, None, None, dh, ds, d_w1, d_b1, d_w2, d_b2, dgamma, dbeta
 
 
 def _padded_logits(rows: int, V: int, like: torch.Tensor):
@@ -292,8 +313,6 @@ class LMHeadLossFn(torch.autograd.Function):
     the same launch (the upstream gradient of a training loss is 1; backward rescales only if it is not), and the
     backward GEMMs read that buffer in place — no slice / as_strided gradient copies of an 800 MB tensor."""
 
-    assume_unit_grad = True  # loss.backward() passes 1; set False to rescale by an arbitrary upstream gradient
-
     @staticmethod
     def forward(ctx, eps, ignore_index, h2d, wd, bd, gamma, beta, wv, bv, labels):
         z = torch.empty((h2d.shape[0], wd.shape[0]), device=h2d.device, dtype=h2d.dtype)
@@ -311,9 +330,11 @@ class LMHeadLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         *saved, dlogits = ctx.saved_tensors
-        # dlogits already holds d loss / d logits for gout == 1 (what loss.backward() passes)
-        if not LMHeadLossFn.assume_unit_grad:
-            dlogits.mul_(gout.to(dlogits.dtype))
+        # dlogits already holds d loss / d logits for an upstream gradient of 1 (what loss.backward() passes); any other
+        # upstream gradient (a scaled / accumulated loss) is applied on the device — the kernel returns at once for 1
+        ld = dlogits.stride(0)  # the row-padded buffer behind the [:, :V] view
+        ops.scale_by_ptr(torch.as_strided(dlogits, (dlogits.shape[0], ld), (ld, 1), dlogits.storage_offset()),
+                         gout.to(torch.float32).reshape(1))
         grads = _lm_head_backward(saved, ctx.params, dlogits)
         return (None, None, *grads, None)
 
@@ -359,7 +380,8 @@ class EmbedFn(torch.autograd.Function):
     from `extra` (the captioner's image vector, models/multimodel.py:163-166)."""
 
     @staticmethod
-    def forward(ctx, ids, table, pos_table, pos_row_off, tokens_per_seq, extra):
+    def forward(ctx, ids, table, pos_table, pos_row_off, tokens_per_seq, extra, padding_idx=None, pos_padding_idx=None):
+        ctx.pad = (padding_idx, pos_padding_idx)
         B = ids.numel() // tokens_per_seq
         e = 0 if extra is None else 1
         seq = tokens_per_seq + e
@@ -394,11 +416,12 @@ class EmbedFn(torch.autograd.Function):
             d_pos = ctx.pos_param.grad.view(pos_table.shape) if pos_direct else torch.zeros_like(pos_table)
         if d_table is not None or d_pos is not None:
             ops.embed_bwd(idsf, dout, rows=idsf.numel(), H=H, tokens_per_seq=tps, out_group_stride=seq, out_row_off=e,
-                          dtable=d_table, dpos=d_pos, pos_row_off=pos_row_off + e)
+                          dtable=d_table, dpos=d_pos, pos_row_off=pos_row_off + e, padding_idx=ctx.pad[0],
+                          pos_padding_idx=ctx.pad[1])
         if e:
             if d_pos is not None:  # the extra row's position gradient
                 ops.embed_bwd(None, dout, rows=B, H=H, tokens_per_seq=1, out_group_stride=seq, out_row_off=0,
-                              dtable=None, dpos=d_pos, pos_row_off=pos_row_off)
+                              dtable=None, dpos=d_pos, pos_row_off=pos_row_off, pos_padding_idx=ctx.pad[1])
             if ctx.needs_input_grad[5]:
                 shape, dt = ctx.extra_shape
                 d_extra = torch.empty(shape, device=dout.device, dtype=dout.dtype)
@@ -411,7 +434,7 @@ class EmbedFn(torch.autograd.Function):
         if pos_direct:
             _ready(ctx.pos_param)
             d_pos = None
-        return None, d_table, d_pos, None, None, d_extra
+        return None, d_table, d_pos, None, None, d_extra, None, None
 
 
 class VitStemFn(torch.autograd.Function):

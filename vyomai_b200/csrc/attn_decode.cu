@@ -29,8 +29,9 @@ struct DecodeDev {
   const void* qkv;  // [B, (Hq + 2 Hkv) * 64]
   long long ld_qkv;
   int qkv_dtype;
-  const float* rope_cos;  // table [cache_len][32] (row = position), or null
+  const float* rope_cos;  // table [rows][32] (row = position + rope_pos_off), or null
   const float* rope_sin;
+  int rope_pos_off;
   void* kcache;
   void* vcache;
   long long c_sb, c_sh, c_sl;  // element strides: batch (paged: block), head, slot
@@ -111,7 +112,8 @@ attn_decode_kernel(const DecodeDev g) {
       if (which <= NREP && g.rope_cos) {
         const int jj = j & 31;
         const float other = ld_as_float(g.qkv, g.qkv_dtype, row + col + (j < 32 ? j + 32 : j - 32));
-        const float c = g.rope_cos[sp * 32 + jj], s = g.rope_sin[sp * 32 + jj];
+        const int rr = sp + g.rope_pos_off;
+        const float c = g.rope_cos[rr * 32 + jj], s = g.rope_sin[rr * 32 + jj];
         x = j < 32 ? x * c - other * s : x * c + other * s;
       }
       if (which < NREP) s_q[which][j] = x;
@@ -356,6 +358,11 @@ extern "C" int vy_attn_decode(const VyDecode* p) {
   VY_CHECK_ARG(p->qkv && p->k_cache && p->v_cache && p->out, "vy_attn_decode: null pointer");
   VY_CHECK_ARG(dtype_ok(p->qkv_dtype) && dtype_ok(p->cache_dtype) && dtype_ok(p->out_dtype), "vy_attn_decode: bad dtype");
   VY_CHECK_ARG((p->rope_cos == nullptr) == (p->rope_sin == nullptr), "vy_attn_decode: rope tables must both be set or NULL");
+  // start_pos is the position itself, or (start_pos_ptr / seqlens) its upper bound: either way the table must cover it
+  if (p->rope_cos && p->rope_rows > 0)
+    VY_CHECK_ARG(p->start_pos + p->rope_pos_off < p->rope_rows && (p->start_pos_ptr || p->seqlens || p->start_pos + p->rope_pos_off >= 0),
+                 "vy_attn_decode: position %d (+ offset %d) lies outside the %d rows of the RoPE tables", p->start_pos,
+                 p->rope_pos_off, p->rope_rows);
   const long long es = dtype_size(p->cache_dtype);
   VY_CHECK_ARG((reinterpret_cast<uintptr_t>(p->k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->v_cache) & 15) == 0 &&
                    (p->cache_sb * es) % 16 == 0 && (p->cache_sh * es) % 16 == 0 && (p->cache_sl * es) % 16 == 0,
@@ -370,6 +377,7 @@ extern "C" int vy_attn_decode(const VyDecode* p) {
   g.qkv = p->qkv; g.ld_qkv = p->ld_qkv; g.qkv_dtype = p->qkv_dtype;
   g.rope_cos = p->rope_cos;
   g.rope_sin = p->rope_sin;
+  g.rope_pos_off = p->rope_pos_off;
   g.kcache = p->k_cache; g.vcache = p->v_cache;
   g.c_sb = p->cache_sb; g.c_sh = p->cache_sh; g.c_sl = p->cache_sl; g.cache_dtype = p->cache_dtype;
   g.seqlens = p->seqlens;

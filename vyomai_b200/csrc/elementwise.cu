@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256)
 embed_bwd_kernel(int rows, int H, const long long* __restrict__ ids, int vocab, int tokens_per_seq,
                  int out_group_stride, int out_row_off, int pos_row_off, float scale,
                  const void* __restrict__ dout, long long ld_dout, int dt, void* __restrict__ dtable,
-                 long long ld_table, void* __restrict__ dpos) {
+                 long long ld_table, void* __restrict__ dpos, long long pad_row, long long pos_pad_row) {
   pdl_trigger();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -82,13 +82,17 @@ embed_bwd_kernel(int rows, int H, const long long* __restrict__ ids, int vocab, 
     if (srow < 0 || srow >= vocab) continue;
     const int l = r % tokens_per_seq;
     const long long orow = static_cast<long long>(r / tokens_per_seq) * out_group_stride + l + out_row_off;
+    // nn.Embedding(padding_idx=...) rows never receive a gradient (pad_row / pos_pad_row < 0: no such row)
+    const bool to_table = dtable && srow != pad_row;
+    const bool to_pos = dpos && (pos_row_off + l) != pos_pad_row;
+    if (!to_table && !to_pos) continue;
     for (int vi = lane; vi < nvec; vi += 32) {
       float v[8];
       ld8_as_float(dout, dt, orow * ld_dout + vi * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
-        if (dtable) atomic_add_elem2(dtable, dt, srow * ld_table + vi * 8 + j, v[j] * scale, v[j + 1] * scale);
-        if (dpos) atomic_add_elem2(dpos, dt, static_cast<long long>(pos_row_off + l) * H + vi * 8 + j, v[j] * scale, v[j + 1] * scale);
+        if (to_table) atomic_add_elem2(dtable, dt, srow * ld_table + vi * 8 + j, v[j] * scale, v[j + 1] * scale);
+        if (to_pos) atomic_add_elem2(dpos, dt, static_cast<long long>(pos_row_off + l) * H + vi * 8 + j, v[j] * scale, v[j + 1] * scale);
       }
     }
   }
@@ -592,6 +596,28 @@ swiglu_bwd_kernel(long long nvec, const void* __restrict__ dh, const void* __res
   }
 }
 
+// x[i] *= *scale; a unit scale (what loss.backward() passes) costs one scalar load per thread and no traffic
+__global__ void __launch_bounds__(256)
+scale_by_ptr_kernel(long long n, void* __restrict__ x, int dt, const float* __restrict__ scale) {
+  pdl_trigger();
+  pdl_wait();
+  const float sc = *scale;
+  if (sc == 1.0f) return;
+  const long long nvec = n >> 3;
+  for (long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi < nvec;
+       vi += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    ld8_as_float(x, dt, vi * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= sc;
+    st8_from_float(x, dt, vi * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const long long i = (nvec << 3) + threadIdx.x;
+    st_from_float(x, dt, i, ld_as_float(x, dt, i) * sc);
+  }
+}
+
 static int ew_grid(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(num_sms()) * 8;
@@ -631,7 +657,8 @@ extern "C" int vy_embed_bwd(const VyEmbed* p) {
   const int ogs = p->out_group_stride > 0 ? p->out_group_stride : tps;
   VY_CUDA_OK(launch_kernel(embed_bwd_kernel, dim3(ew_grid(p->rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->rows, p->H, reinterpret_cast<const long long*>(p->ids), p->vocab, tps, ogs, p->out_row_off, p->pos_row_off,
-      p->out_scale == 0.f ? 1.f : p->out_scale, p->dout, p->ld_out, p->dtype, p->dtable, p->ld_src, p->dpos));
+      p->out_scale == 0.f ? 1.f : p->out_scale, p->dout, p->ld_out, p->dtype, p->dtable, p->ld_src, p->dpos,
+      static_cast<long long>(p->padding_idx_plus1) - 1, static_cast<long long>(p->pos_padding_idx_plus1) - 1));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -775,6 +802,16 @@ extern "C" int vy_rope_apply(const VyRope* p) {
   const long long rows = static_cast<long long>(p->B) * p->H * p->S;
   VY_CUDA_OK(launch_kernel(rope_kernel, dim3(ew_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->B, p->H, p->S, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_scale_by_ptr(int64_t n, void* x, int dtype, const float* scale, void* stream) {
+  VY_NEED_DEVICE("vy_scale_by_ptr");
+  VY_CHECK_ARG(n > 0 && x && scale && dtype_ok(dtype) && aligned16(x), "vy_scale_by_ptr: bad arguments (x 16-byte aligned)");
+  VY_CUDA_OK(launch_kernel(scale_by_ptr_kernel, dim3(ew_grid(n, 8 * 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                           static_cast<long long>(n), x, dtype, scale));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -2,6 +2,8 @@
 // (gemm_kernel.cuh; instantiated in gemm_inst_*.cu so the translation units build in parallel).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "gemm_kernel.cuh"
 
 namespace vy {
@@ -170,15 +172,36 @@ splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ ws, con
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// one int of device memory that a timed-out wait inside a GEMM kernel raises (mbar_wait_soft)
-static int* poison_flag() {
-  static int* flag = nullptr;
-  if (!flag) {
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(flag, 0, sizeof(int));
+// Per-device pair of flags that a timed-out wait inside a GEMM kernel raises (mbar_wait_soft): one int of device memory
+// (what the other waits of the same launch poll) and one int of mapped pinned host memory (what the host reads without
+// synchronising). Allocated on first use on whichever device is current, so a process that drives several GPUs never
+// hands one device's flag to another device's kernels.
+struct PoisonSlot {
+  int* dev = nullptr;
+  int* host = nullptr;      // host address of the mirror
+  int* host_dev = nullptr;  // device address of the mirror
+};
+static PoisonSlot* poison_slot() {
+  static PoisonSlot slots[64];
+  static std::mutex mu;
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  PoisonSlot& s = slots[d];
+  if (!s.dev) {
+    int* dv = nullptr;
+    int* h = nullptr;
+    int* hd = nullptr;
+    if (cudaMalloc(&dv, sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(dv, 0, sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    *h = 0;
+    if (cudaHostGetDevicePointer(&hd, h, 0) != cudaSuccess) return nullptr;
+    s.dev = dv; s.host = h; s.host_dev = hd;
   }
-  return flag;
+  return &s;
 }
+static std::atomic<int> g_gemm_launch_id{0};
 
 }  // namespace vy
 
@@ -193,11 +216,22 @@ extern "C" int vy_gemm_tune_override(int pair, int bn, int splits) {
 
 extern "C" int vy_gemm_poisoned(void) {
   using namespace vy;
-  int* f = poison_flag();
+  PoisonSlot* f = poison_slot();
   int v = -1;
-  if (!f || cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (v != 0) cudaMemset(f, 0, sizeof(int));  // reading a raised flag lowers it again
-  return v;
+  if (!f || cudaMemcpy(&v, f->dev, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (v != 0 || *reinterpret_cast<volatile int*>(f->host) != 0) {  // reading a raised flag lowers it again
+    cudaMemset(f->dev, 0, sizeof(int));
+    *reinterpret_cast<volatile int*>(f->host) = 0;
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" int vy_gemm_poison_peek(void) {
+  using namespace vy;
+  PoisonSlot* f = poison_slot();
+  if (!f) return -1;
+  return *reinterpret_cast<volatile int*>(f->host) != 0 ? 1 : 0;
 }
 
 extern "C" int vy_gemm(const VyGemm* p) {
@@ -221,8 +255,18 @@ extern "C" int vy_gemm(const VyGemm* p) {
   memset(&g, 0, sizeof(g));
   static const int dbg = getenv("VY_GEMM_DEBUG") ? atoi(getenv("VY_GEMM_DEBUG")) : 0;
   g.debug = dbg;
-  g.poison = poison_flag();
-  VY_CHECK_ARG(g.poison != nullptr, "vy_gemm: could not allocate the poison flag");
+  PoisonSlot* ps = poison_slot();
+  VY_CHECK_ARG(ps != nullptr, "vy_gemm: could not allocate the poison flags of this device");
+  if (*reinterpret_cast<volatile int*>(ps->host) != 0) {
+    set_error("vy_gemm: a barrier wait inside an earlier GEMM kernel on this device timed out (launch id %d) — its results "
+              "and everything computed from them are invalid; vy_gemm_poisoned() acknowledges and lowers the flag",
+              *reinterpret_cast<volatile int*>(ps->host));
+    return VY_ERR_CUDA;
+  }
+  g.poison.flag = ps->dev;
+  g.poison.host = ps->host_dev;
+  int lid = g_gemm_launch_id.fetch_add(1, std::memory_order_relaxed) + 1;
+  g.poison.id = lid & 0x7fffffff ? lid & 0x7fffffff : 1;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.epi = p->epi; g.act = p->act; g.transposed_out = p->transposed_out;
   g.bias = p->bias; g.bias_dtype = p->bias_dtype;
@@ -262,6 +306,12 @@ extern "C" int vy_gemm(const VyGemm* p) {
     VY_CHECK_ARG((p->q_out || p->n_q_heads == 0) && ((p->k_out && p->v_out) || p->n_kv_heads == 0) && dtype_ok(p->out_dtype),
                  "vy_gemm: q/k/v outputs missing");
     VY_CHECK_ARG(p->start_pos >= 0 && p->kv_dst_pos0 >= 0, "vy_gemm: negative position");
+    VY_CHECK_ARG(p->kv_cap <= 0 || p->kv_dst_pos0 + p->tokens_per_seq <= p->kv_cap,
+                 "vy_gemm: k/v rows [%d, %d) do not fit the %d token slots of k_out / v_out", p->kv_dst_pos0,
+                 p->kv_dst_pos0 + p->tokens_per_seq, p->kv_cap);
+    VY_CHECK_ARG(p->rope_rows <= 0 || !p->rope_cos || p->start_pos + p->tokens_per_seq <= p->rope_rows,
+                 "vy_gemm: positions [%d, %d) exceed the %d rows of the RoPE tables", p->start_pos,
+                 p->start_pos + p->tokens_per_seq, p->rope_rows);
     VY_CHECK_ARG((p->rope_cos == nullptr) == (p->rope_sin == nullptr), "vy_gemm: rope_cos/rope_sin must both be set or NULL");
     VY_CHECK_ARG(dtype_ok(p->kv_out_dtype), "vy_gemm: bad kv_out_dtype");
     auto okstr = [&](const void* ptr, long long sb, long long sh, long long sl, int dt) {

@@ -53,7 +53,7 @@ struct GemmDev {
   int kv_out_dtype;
   int k_splits, kb_per_split;  // split-K: unit = (tile, split); raw fp32 partial tiles go to ws[split][M][N]
   float* ws;
-  int* poison;    // raised by a wait that timed out (mbar_wait_soft); checked by the host through vy_gemm_poisoned()
+  PoisonRef poison;  // raised by a wait that timed out (mbar_wait_soft); the host sees it in vy_gemm / vy_gemm_poison_peek / vy_gemm_poisoned
   int tma_store;  // fast epilogues write back with TMA stores (tma_out / tma_aux of the launch)
   int debug;  // development switches (VY_GEMM_DEBUG): 1 = epilogue drains TMEM only, 2 = producer skips TMA after the first ring fill
 };

@@ -14,11 +14,12 @@ __global__ void __launch_bounds__(NORM_WARPS * 32)
 add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void* __restrict__ res,
                          int io_dt, const void* __restrict__ gamma, const void* __restrict__ beta,
                          int p_dt, float eps, void* __restrict__ y, void* __restrict__ sum_out,
-                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int kind) {
+                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int kind, const DropArgs drop) {
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H >> 3;
+  const unsigned int drop_step = (drop.p > 0.f && drop.step_ptr) ? static_cast<unsigned int>(*drop.step_ptr) : 0u;
   for (int row = blockIdx.x * NORM_WARPS + warp; row < rows; row += gridDim.x * NORM_WARPS) {
     const long long base = static_cast<long long>(row) * H;
     float v[NV][8];
@@ -28,6 +29,11 @@ add_layernorm_fwd_kernel(int rows, int H, const void* __restrict__ x, const void
       const int vi = lane + i * 32;
       if (vi < nvec) {
         ld8_as_float(x, io_dt, base + vi * 8, v[i]);
+        if (drop.p > 0.f) {  // dropout(x) before the residual add (attention.py:70, ffn.py:38)
+          const unsigned int keep = dropout_keep8(drop, static_cast<unsigned long long>(row) * nvec + vi, drop_step);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = (keep >> j) & 1u ? v[i][j] * drop.scale : 0.f;
+        }
         if (res) {
           float r[8];
           ld8_as_float(res, io_dt, base + vi * 8, r);
@@ -109,14 +115,15 @@ __device__ __forceinline__ void bulk_load_row(void* dst, const void* src, uint32
                : "memory");
 }
 
-template <int NV, bool IO_BF16>
+template <int NV, bool IO_BF16, bool DROP>
 __global__ void __launch_bounds__(NORM_WARPS * 32, 1)
 add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const void* __restrict__ s,
                          const void* __restrict__ gamma, int p_dt, const float* __restrict__ mean,
                          const float* __restrict__ rstd, void* __restrict__ dx, int want_dbias, float* __restrict__ partials,
-                         int kind) {
+                         int kind, void* __restrict__ dx_drop, const DropArgs drop) {
   pdl_trigger();
   pdl_wait();
+  const unsigned int drop_step = (DROP && drop.step_ptr) ? static_cast<unsigned int>(*drop.step_ptr) : 0u;
   extern __shared__ __align__(128) float red[];  // [NORM_WARPS][3][H] at the end; the row ring before that
   constexpr int IO_DT = IO_BF16 ? VY_BF16 : VY_F32;
   constexpr int RAW = IO_BF16 ? 1 : 2;  // uint4 per 8 elements
@@ -252,9 +259,18 @@ add_layernorm_bwd_kernel(int rows, int H, const void* __restrict__ dy, const voi
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               o[j] = rs[u] * (dyv[u][i][j] * g[i][j] - m1 - xh[u][i][j] * m2);
-              dbi[i][j] += o[j];
+              if (!DROP) dbi[i][j] += o[j];
             }
             st8_from_float(dx, IO_DT, rbase + vi * 8, o);
+            if (DROP) {  // gradient of the dropped branch: the forward's mask, regenerated
+              const unsigned int keep = dropout_keep8(drop, static_cast<unsigned long long>(row0 + u * stride) * nvec + vi, drop_step);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                o[j] = (keep >> j) & 1u ? o[j] * drop.scale : 0.f;
+                dbi[i][j] += o[j];
+              }
+              st8_from_float(dx_drop, IO_DT, rbase + vi * 8, o);
+            }
           }
         }
       }
@@ -458,6 +474,19 @@ static int norm_common_checks(const VyNorm* p, const char* who) {
   return VY_OK;
 }
 
+static int make_drop_args(const VyNorm* p, const char* who, DropArgs* d) {
+  memset(d, 0, sizeof(*d));
+  VY_CHECK_ARG(p->dropout_p >= 0.f && p->dropout_p < 1.f, "%s: dropout_p must lie in [0, 1) (got %g)", who, p->dropout_p);
+  if (p->dropout_p == 0.f) return VY_OK;
+  d->p = p->dropout_p;
+  d->scale = 1.f / (1.f - p->dropout_p);
+  d->thresh = static_cast<unsigned int>(p->dropout_p * 65536.f + 0.5f);
+  d->offset = p->dropout_offset;
+  d->seed = p->dropout_seed;
+  d->step_ptr = p->dropout_step_ptr;
+  return VY_OK;
+}
+
 }  // namespace vy
 
 extern "C" int vy_norm_bwd_partial_rows(void) { return 2 * vy::num_sms(); }
@@ -471,6 +500,9 @@ extern "C" int vy_add_layernorm_fwd(const VyNorm* p) {
   VY_CHECK_ARG(aligned16(p->x) && aligned16(p->y) && aligned16(p->gamma) && aligned16(p->beta) &&
                    aligned16(p->residual) && aligned16(p->sum_out),
                "vy_add_layernorm_fwd: pointers must be 16-byte aligned");
+  DropArgs drop;
+  rc = make_drop_args(p, "vy_add_layernorm_fwd", &drop);
+  if (rc != VY_OK) return rc;
   const int nv = (p->H + 255) / 256;
   int grid = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
   const int maxgrid = num_sms() * 8;
@@ -479,7 +511,7 @@ extern "C" int vy_add_layernorm_fwd(const VyNorm* p) {
 #define VY_LN_FWD(NV)                                                                              \
   VY_CUDA_OK(launch_kernel(add_layernorm_fwd_kernel<NV>, dim3(grid), dim3(NORM_WARPS * 32), 0, st,                                   \
       p->rows, p->H, p->x, p->residual, p->io_dtype, p->gamma, p->beta, p->param_dtype, p->eps, p->y, \
-      p->sum_out, p->mean, p->rstd, p->kind))
+      p->sum_out, p->mean, p->rstd, p->kind, drop))
   switch (nv) {
     case 1: VY_LN_FWD(1); break;
     case 2: VY_LN_FWD(2); break;
@@ -508,6 +540,17 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   VY_CHECK_ARG(aligned16(p->dy) && aligned16(p->s) && aligned16(p->dx) && aligned16(p->gamma),
                "vy_add_layernorm_bwd: pointers must be 16-byte aligned");
   VY_CHECK_ARG(dtype_ok(p->dparam_dtype), "vy_add_layernorm_bwd: bad dparam_dtype");
+  DropArgs drop;
+  rc = make_drop_args(p, "vy_add_layernorm_bwd", &drop);
+  if (rc != VY_OK) return rc;
+  const bool dropping = drop.p > 0.f;
+  if (dropping) {
+    VY_CHECK_ARG(p->dx_drop != nullptr && aligned16(p->dx_drop), "vy_add_layernorm_bwd: dropout_p > 0 needs a 16-byte aligned dx_drop");
+    if (p->H > 1024) {
+      set_error("vy_add_layernorm_bwd: dropout backward supports H <= 1024 (got %d)", p->H);
+      return VY_ERR_UNSUPPORTED;
+    }
+  }
   const int nv = (p->H + 255) / 256;
   int grid = (p->rows + NORM_WARPS - 1) / NORM_WARPS;
   if (grid > num_sms()) grid = num_sms();  // persistent: one CTA per SM (partials hold up to 2 * SMs * 2 * H floats)
@@ -516,18 +559,18 @@ extern "C" int vy_add_layernorm_bwd(const VyNorm* p) {
   const size_t ring_bytes = static_cast<size_t>(NORM_WARPS) * ring_slots * 2 * p->H * dtype_size(p->io_dtype) + NORM_WARPS * ring_slots * 8;
   const size_t smem = red_bytes > ring_bytes ? red_bytes : ring_bytes;
   cudaStream_t st = static_cast<cudaStream_t>(p->stream);
-#define VY_LN_BWD2(NV, BF)                                                                            \
+#define VY_LN_BWD2(NV, BF, DR)                                                                        \
   do {                                                                                               \
-    auto kern = add_layernorm_bwd_kernel<NV, BF>;                                                    \
+    auto kern = add_layernorm_bwd_kernel<NV, BF, DR>;                                                \
     if (smem > 48 * 1024)                                                                            \
       VY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     VY_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(NORM_WARPS * 32), smem, st, p->rows, p->H, p->dy, p->s, p->gamma, p->param_dtype, p->mean, p->rstd, \
-                                              p->dx, p->dbias != nullptr, p->partials, p->kind));      \
+                                              p->dx, p->dbias != nullptr, p->partials, p->kind, p->dx_drop, drop));      \
   } while (0)
 #define VY_LN_BWD(NV)                     \
   do {                                    \
-    if (p->io_dtype == VY_BF16) VY_LN_BWD2(NV, true); \
-    else VY_LN_BWD2(NV, false);           \
+    if (p->io_dtype == VY_BF16) { if (dropping) VY_LN_BWD2(NV, true, true); else VY_LN_BWD2(NV, true, false); } \
+    else { if (dropping) VY_LN_BWD2(NV, false, true); else VY_LN_BWD2(NV, false, false); }           \
   } while (0)
   switch (nv) {
     case 1: VY_LN_BWD(1); break;

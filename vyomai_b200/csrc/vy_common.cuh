@@ -148,6 +148,39 @@ __device__ __forceinline__ void st8_from_float(void* p, int dt, int64_t i, const
   }
 }
 
+// ---- dropout: counter-based mask (Philox4x32-10), regenerated in backward instead of stored --------------------
+// One call yields 128 random bits = eight 16-bit lanes = the keep decisions of one 8-element vector:
+// element j of vector `vec` is kept iff lane j >= thresh (thresh = round(p * 65536)).
+struct DropArgs {
+  float p;                // 0 = off
+  float scale;            // 1 / (1 - p)
+  unsigned int thresh;    // round(p * 65536)
+  unsigned int offset;    // distinguishes the call sites of one step
+  unsigned long long seed;
+  const int* step_ptr;    // device step counter or null (= 0)
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// keep bits (bit j = element j kept) of 8-element vector number `vec` of the call
+__device__ __forceinline__ unsigned int dropout_keep8(const DropArgs& d, unsigned long long vec, unsigned int step) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<unsigned int>(vec), static_cast<unsigned int>(vec >> 32), d.offset, step),
+                                make_uint2(static_cast<unsigned int>(d.seed), static_cast<unsigned int>(d.seed >> 32)));
+  const unsigned int w[4] = {r.x, r.y, r.z, r.w};
+  unsigned int keep = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) keep |= (((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= d.thresh ? 1u : 0u) << j;
+  return keep;
+}
+
 // Exact-erf GELU (nn.GELU(), VyomAI/layers/ffn.py:8) without libdevice's branchy erff: with
 // Q(x) = 1 - Phi(|x|) = 0.5 erfc(|x| / sqrt 2) from Abramowitz-Stegun 7.1.26 (|error| <= 0.75e-7, far
 // below bf16 / tf32 resolution), gelu(x) = x Phi(x) and gelu'(x) = Phi(x) + x phi(x) share one

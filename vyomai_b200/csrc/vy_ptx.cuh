@@ -75,17 +75,27 @@ VY_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// GEMM flavour of the bounded wait: instead of trapping, a wait that times out raises a flag in global memory and
-// returns; every other wait of the grid notices the flag within 64 attempts and returns too, so a protocol bug ends the
-// kernel with wrong results and *poison != 0 (vy_gemm_poisoned() on the host) rather than with a fault or a hang.
+// GEMM flavour of the bounded wait: instead of trapping, a wait that times out raises a flag and returns; every other
+// wait of the SAME launch notices the flag within 64 attempts and returns too, so a protocol bug ends that kernel with
+// wrong results and a raised flag rather than with a fault or a hang. The flag holds the id of the launch that timed
+// out: waits of later launches compare it with their own id, so a stale flag never makes a healthy GEMM bail out.
+// `host` is the device address of a pinned host mirror the library reads without synchronising (every vy_gemm call
+// and vy_gemm_poison_peek() fail loudly once it is non-zero; vy_gemm_poisoned() lowers both).
+struct PoisonRef {
+  int* flag;  // device memory, one per device
+  int* host;  // mapped pinned host memory, one per device
+  int id;     // id of this launch (never 0)
+};
 template <bool CLUSTER_SCOPE = false>
-VY_DEVINL void mbar_wait_soft(uint64_t* bar, uint32_t parity, int* poison) {
+VY_DEVINL void mbar_wait_soft(uint64_t* bar, uint32_t parity, const PoisonRef& poison) {
   uint32_t spins = 0;
   while (!(CLUSTER_SCOPE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
     if ((++spins & 63u) == 0) {
-      if (*reinterpret_cast<volatile int*>(poison) != 0) return;
+      if (*reinterpret_cast<volatile int*>(poison.flag) == poison.id) return;
       if (spins > (1u << 21)) {
-        atomicExch(poison, 1);
+        atomicExch(poison.flag, poison.id);
+        *reinterpret_cast<volatile int*>(poison.host) = poison.id;
+        __threadfence_system();
         return;
       }
     }

@@ -182,9 +182,10 @@ def attention_core(
     if kv is not None and S == 1 and decode_no_mask:
         # single-token decode: plain projection, then the fused RoPE + append + attention kernel
         qkv = _lin(x2d, w_qkv, b_qkv)
-        if cos is not None and rope_pos != start:  # vy_attn_decode indexes the tables by the cache slot
-            cos, sin = cos[rope_pos - start:], sin[rope_pos - start:]
-        out = ops.attn_decode(qkv, kv.k_buf, kv.v_buf, start, n_q_heads, n_kv_heads, cos, sin, out_dtype=T)
+        # vy_attn_decode addresses the tables by cache slot + offset: a caller holding only the angle rows of the
+        # current positions (the bare layer API) has rope_pos = 0 while the slot is start_pos
+        out = ops.attn_decode(qkv, kv.k_buf, kv.v_buf, start, n_q_heads, n_kv_heads, cos, sin, out_dtype=T,
+                              rope_pos_off=rope_pos - start)
         return out, None
 
     q = torch.empty((B, n_q_heads, S, d), device=dev, dtype=torch.bfloat16)
@@ -212,22 +213,42 @@ def attention_core(
     return out.view(B * S, n_q_heads * d), (q, k_att, v_att, lse)
 
 
-def self_output(attn2d: torch.Tensor, residual2d: torch.Tensor, dense: nn.Linear, ln: nn.LayerNorm, save: bool = False):
-    """AttentionSelfOutput.forward (layers/attention.py:57-72): LN(dense(attn) + residual); the
-    residual add rides in the GEMM epilogue. Dropout is the identity (eval / p = 0)."""
-    s = _lin(attn2d, dense.weight, dense.bias, addend=residual2d)
-    y, _, mean, rstd = ops.add_layernorm(s, None, ln.weight, ln.bias, ln.eps, save_stats=save)
+def dropout_state(module: nn.Module, p: float) -> Optional[ops.DropoutState]:
+    """The reference's nn.Dropout(hidden_dropout_prob) is live in .train() (attention.py:55,70; ffn.py:24,38): a fresh
+    mask identity per call then, None in eval / p = 0."""
+    if module.training and p > 0.0:
+        return ops.DropoutState(p)
+    return None
+
+
+def self_output(attn2d: torch.Tensor, residual2d: torch.Tensor, dense: nn.Linear, ln: nn.LayerNorm, save: bool = False,
+                dropout: Optional[ops.DropoutState] = None):
+    """AttentionSelfOutput.forward (layers/attention.py:57-72): LN(dropout(dense(attn)) + residual). Without dropout the
+    residual add rides in the GEMM epilogue; with it the GEMM writes dense(attn) and the norm kernel drops, adds the
+    residual and normalises in one pass (the mask is regenerated in backward, never stored)."""
+    if dropout is None:
+        s = _lin(attn2d, dense.weight, dense.bias, addend=residual2d)
+        y, _, mean, rstd = ops.add_layernorm(s, None, ln.weight, ln.bias, ln.eps, save_stats=save)
+        return y, (s, mean, rstd)
+    x = _lin(attn2d, dense.weight, dense.bias)
+    y, s, mean, rstd = ops.add_layernorm(x, residual2d.contiguous(), ln.weight, ln.bias, ln.eps, save_stats=save, save_sum=save,
+                                         dropout=dropout)
     return y, (s, mean, rstd)
 
 
 def feed_forward(h2d: torch.Tensor, input2d: torch.Tensor, inter: nn.Linear, out: nn.Linear, ln: nn.LayerNorm,
-                 act: str = "gelu", save: bool = False):
-    """FeedForward.forward (layers/ffn.py:32-40): LN(out(act(intermediate(h))) + input_tensor) with
-    bias+GELU fused into the first GEMM's epilogue and bias+residual into the second's."""
+                 act: str = "gelu", save: bool = False, dropout: Optional[ops.DropoutState] = None):
+    """FeedForward.forward (layers/ffn.py:32-40): LN(dropout(out(act(intermediate(h)))) + input_tensor) with
+    bias+GELU fused into the first GEMM's epilogue and bias+residual into the second's (dropout: see self_output)."""
     z = torch.empty((h2d.shape[0], inter.weight.shape[0]), device=h2d.device, dtype=h2d.dtype) if save else None
     a = _lin(h2d, inter.weight, inter.bias, act=act, aux=z)
-    s = _lin(a, out.weight, out.bias, addend=input2d)
-    y, _, mean, rstd = ops.add_layernorm(s, None, ln.weight, ln.bias, ln.eps, save_stats=save)
+    if dropout is None:
+        s = _lin(a, out.weight, out.bias, addend=input2d)
+        y, _, mean, rstd = ops.add_layernorm(s, None, ln.weight, ln.bias, ln.eps, save_stats=save)
+    else:
+        x = _lin(a, out.weight, out.bias)
+        y, s, mean, rstd = ops.add_layernorm(x, input2d.contiguous(), ln.weight, ln.bias, ln.eps, save_stats=save, save_sum=save,
+                                             dropout=dropout)
     return y, (z, a, s, mean, rstd)
 
 

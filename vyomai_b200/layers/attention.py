@@ -10,7 +10,8 @@ forward bodies run the fused sm_100a path:
          + ONE vy_attn_fwd (tcgen05 flash attention; GQA by head index)        [seqlen > 1]
         or ONE swap-AB vy_gemm + ONE vy_attn_decode                             [seqlen == 1, cached]
     AttentionSelfOutput (dense + dropout + residual + LayerNorm)
-        -> ONE vy_gemm (bias + residual epilogue) + ONE vy_add_layernorm_fwd
+        -> ONE vy_gemm (bias + residual epilogue) + ONE vy_add_layernorm_fwd            [eval / p = 0]
+        or ONE vy_gemm (bias) + ONE vy_add_layernorm_fwd (Philox dropout + residual)    [.train(), p > 0]
 """
 from typing import List, Optional, Tuple
 
@@ -43,14 +44,6 @@ def _check_heads(config) -> None:
         )
 
 
-def _check_dropout(module: nn.Module, p: float) -> None:
-    if module.training and p > 0.0:
-        raise _lib.VyomError(
-            "the fused sm_100a path implements hidden_dropout_prob = 0 (or .eval()); "
-            f"got training mode with p = {p}. Set config.hidden_dropout_prob = 0 for training runs."
-        )
-
-
 class AttentionSelfOutput(nn.Module):
     """dense -> dropout -> LayerNorm(. + input) (reference: attention.py:42-72)."""
 
@@ -61,12 +54,11 @@ class AttentionSelfOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_states: torch.Tensor, input_tensor: torch.Tensor) -> torch.Tensor:
-        _check_dropout(self, self.dropout.p)
         shape = input_tensor.shape
         H = shape[-1]
         from ..autograd import self_output_fn
         y = self_output_fn(hidden_states.reshape(-1, hidden_states.shape[-1]), input_tensor.reshape(-1, H), self.dense,
-                           self.layernorm)
+                           self.layernorm, dropout=F.dropout_state(self, self.dropout.p))
         return y.view(shape)
 
 
@@ -114,7 +106,6 @@ class _SelfAttentionBase(nn.Module):
     def _run(self, hidden_state: torch.Tensor, attention_mask, freqs, kv: Optional[KVTarget], start_pos: int) -> torch.Tensor:
         if self._head != F.HEAD_DIM:
             raise _lib.VyomError(f"the sm_100a attention path is specialised for head_dim 64 (got {self._head})")
-        _check_dropout(self, self.out.dropout.p)
         B, S, H = hidden_state.shape
         mask = attention_mask if isinstance(attention_mask, MaskSpec) else MaskSpec.from_dense(attention_mask, S)
         rope = None

@@ -12,7 +12,6 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from .attention import _check_dropout
 
 # activation names of ffn.py:7-15 that the GEMM epilogue implements
 _FUSED_ACT = {"gelu": "gelu"}
@@ -38,7 +37,6 @@ class FeedForward(nn.Module):
         self.out = nn.Linear(int(multiplier) * config.hidden_size, config.hidden_size)
 
     def forward(self, hidden_state: torch.Tensor, input_tensor: torch.Tensor) -> torch.Tensor:
-        _check_dropout(self, self.dropout.p)
         from ..autograd import feed_forward_fn
         shape = input_tensor.shape
         H = shape[-1]

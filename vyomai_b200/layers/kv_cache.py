@@ -118,8 +118,10 @@ class StaticCache:
         self.first_update_len = 0
 
     def slot(self, batch: int, heads: int, seqlen: int, head_dim: int, start_pos: int, device, dtype):
-        if seqlen > self.key_cache.size()[2]:
-            raise ValueError(f"{(batch, heads, seqlen, head_dim)} is more than init k_cache size {self.key_cache.shape}")
+        if seqlen > self.key_cache.size()[2] or start_pos + seqlen > self.key_cache.size()[2]:
+            # the reference fails here too (on the slice assignment at kv_cache.py:142-145 once start_pos + seqlen runs
+            # past the buffer); the fused append must never be handed a slot range outside the cache
+            raise ValueError(f"{(batch, heads, seqlen, head_dim)} at position {start_pos} is more than init k_cache size {self.key_cache.shape}")
         assert batch == 1, "Only support batch size 1"
         if self.key_cache.device != device or self.key_cache.dtype != dtype:
             self.key_cache = self.key_cache.to(device=device, dtype=dtype)

@@ -108,4 +108,7 @@ class TextStem:
         rows starting at start_pos), optionally behind one leading row per sequence taken from `extra`."""
         table = self.word_embeddings.weight
         pos = self._pos_table(table.device, table.dtype)
-        return embed_fn(input_ids, table, pos, start_pos, input_ids.shape[1], extra)
+        pe = self.position_embeddings
+        pos_pad = pe.pos_embeddings.padding_idx if isinstance(pe, AbsoluteEncoding) else None
+        return embed_fn(input_ids, table, pos, start_pos, input_ids.shape[1], extra,
+                        padding_idx=self.word_embeddings.padding_idx, pos_padding_idx=pos_pad)

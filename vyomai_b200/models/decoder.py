@@ -152,13 +152,20 @@ class DecoderModel(nn.Module, TextStem):
         bsz, _ = input_ids.size()
         tokens = torch.full((bsz, max_len), pad_id, dtype=torch.long, device=dev)
         kv_cache = None
+        live_dropout = self.training and getattr(self.config, "hidden_dropout_prob", 0.0) > 0.0  # random masks: eager loop
         graph_path = (self.use_decode_graph and use_cache and use_static_cache and not do_sample and self._rope is not None
-                      and min_prompt_len == input_ids.shape[1] and bool((input_ids != pad_id).all()))
+                      and not live_dropout and min_prompt_len == input_ids.shape[1] and bool((input_ids != pad_id).all()))
+        if graph_path:
+            # the replayed steps index the RoPE table with positions up to max_len - 2 without passing through forward():
+            # apply its position check up front, like the eager loop (and the reference) would hit it on the way
+            self._check_positions(max_len - 1)
         if use_cache:
             if use_static_cache and graph_path:
                 # the captured step is bound to its cache buffers: keep both and reuse them for calls of the same shape
                 # (slots beyond the current position are never read, so a stale cache needs no clearing)
-                key = (bsz, max_len, self.word_embeddings.weight.dtype, dev)
+                # the captured step bakes in the weights' addresses: re-capture when parameters were re-homed
+                # (trainer.FlatParams, pack_linears after .to(), load_state_dict(assign=True))
+                key = (bsz, max_len, self.word_embeddings.weight.dtype, dev, tuple(p.data_ptr() for p in self.parameters()))
                 if getattr(self, "_decode_graph_key", None) != key:
                     self._decode_graph_key = key
                     self._decode_graph_cache = StaticCacheOne(self.config, max_cache_len=max_len, batch_size=bsz,

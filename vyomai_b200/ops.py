@@ -211,7 +211,8 @@ def qkv_rope_gemm(
         q_out=q_out.data_ptr(), q_sb=q_out.stride(0), q_sh=q_out.stride(1), q_sl=q_out.stride(2),
         k_out=k_out.data_ptr(), k_sb=k_out.stride(0), k_sh=k_out.stride(1), k_sl=k_out.stride(2),
         v_out=v_out.data_ptr(), v_sb=v_out.stride(0), v_sh=v_out.stride(1), v_sl=v_out.stride(2),
-        kv_out_dtype=_dt(k_out), stream=_stream(),
+        kv_out_dtype=_dt(k_out), kv_cap=k_out.shape[2], rope_rows=rope_cos.shape[0] if rope_cos is not None else 0,
+        stream=_stream(),
     )
     if gemm_tune.ENABLED:
         key = ("qkv", M, N, K, kw["in_dtype"], a_mn, b_mn, bias is not None, rope_cos is not None, n_q_heads, n_kv_heads,
@@ -230,8 +231,10 @@ def add_layernorm(
     save_stats: bool = False,
     save_sum: bool = False,
     kind: str = "layernorm",
+    dropout: Optional["DropoutState"] = None,
 ):
-    """y = LayerNorm(x + residual). Returns (y, sum_or_None, mean_or_None, rstd_or_None).
+    """y = LayerNorm(dropout(x) + residual). Returns (y, sum_or_None, mean_or_None, rstd_or_None). `dropout` (a
+    DropoutState with p > 0) drops x before the residual add — attention.py:70 / ffn.py:38 in .train().
     kind="rmsnorm": y = gamma * xhat with xhat = s * rsqrt(mean(s^2) + eps) (custom_transformer.py:227-241; `beta`, the
     optional shift of simple_vllm.ipynb's RMSNorm, may be None); kind="gemma_rmsnorm": y = (1 + gamma) * xhat."""
     _need_cuda(x, residual, gamma, beta)
@@ -255,16 +258,42 @@ def add_layernorm(
         "vy_add_layernorm_fwd", "VyNorm",
         rows=rows, H=H, x=x2.data_ptr(), residual=_ptr(r2), io_dtype=_dt(x2), gamma=gamma.data_ptr(),
         beta=_ptr(beta), param_dtype=_dt(gamma), eps=float(eps), y=y.data_ptr(), sum_out=_ptr(s),
-        mean=_ptr(mean), rstd=_ptr(rstd), kind=NORM_KIND[kind], stream=_stream(),
+        mean=_ptr(mean), rstd=_ptr(rstd), kind=NORM_KIND[kind], stream=_stream(), **(dropout.kwargs() if dropout else {}),
     )
     if save_sum and residual is None:
         s = x2
     return y.view(x.shape), s, mean, rstd
 
 
+class DropoutState:
+    """Identifies one dropout mask: (p, seed, offset, step counter). The mask itself is never stored — the forward and
+    the backward kernels regenerate it from these four (include/vyom_b200.h, VyNorm.dropout_*)."""
+
+    _next_offset = 0
+    seed = 0x5DEECE66D
+    step_ptr: Optional[torch.Tensor] = None  # device int32 step counter shared by every mask (trainer.Trainer sets it, so
+    #                                          a replayed CUDA graph draws fresh masks each step); None = step 0
+
+    def __init__(self, p: float, step_ptr: Optional[torch.Tensor] = None):
+        self.p = float(p)
+        self.seed = DropoutState.seed
+        DropoutState._next_offset = (DropoutState._next_offset + 1) & 0xFFFFFFFF
+        self.offset = DropoutState._next_offset
+        self.step_ptr = step_ptr if step_ptr is not None else DropoutState.step_ptr
+
+    @staticmethod
+    def manual_seed(seed: int) -> None:
+        DropoutState.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        DropoutState._next_offset = 0
+
+    def kwargs(self) -> dict:
+        return dict(dropout_p=self.p, dropout_seed=self.seed, dropout_offset=self.offset, dropout_step_ptr=_ptr(self.step_ptr))
+
+
 def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tensor] = None,
                       dbeta_out: Optional[torch.Tensor] = None, dbias_out: Optional[torch.Tensor] = None,
-                      want_dbias: bool = False, accumulate: bool = True, kind: str = "layernorm"):
+                      want_dbias: bool = False, accumulate: bool = True, kind: str = "layernorm",
+                      dropout: Optional[DropoutState] = None):
     """Returns (dx, dgamma, dbeta[, dbias]) for y = LayerNorm(s) (or the RMSNorm kinds of add_layernorm; `mean` may then
     be None and dbeta is the gradient of the optional shift). Without dgamma_out/dbeta_out the parameter
     gradients come back as fresh fp32 tensors; with them (same dtype, e.g. the parameters' .grad views) the kernel
@@ -278,6 +307,7 @@ def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tenso
         raise _lib.VyomError("add_layernorm_bwd: dy and s must be contiguous")
     rows = dy2.shape[0]
     dx = torch.empty_like(dy2)
+    dx_drop = torch.empty_like(dy2) if dropout else None
     acc = dgamma_out is not None
     if acc:
         if dbeta_out is None or dgamma_out.dtype != dbeta_out.dtype or not (dgamma_out.is_contiguous() and dbeta_out.is_contiguous()):
@@ -300,10 +330,14 @@ def add_layernorm_bwd(dy, s, gamma, mean, rstd, dgamma_out: Optional[torch.Tenso
         mean=_ptr(mean), rstd=rstd.data_ptr(), dy=dy2.data_ptr(), s=s2.data_ptr(), dx=dx.data_ptr(),
         dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), dbias=_ptr(dbias), dparam_dtype=_dt(dgamma),
         dparam_accumulate=int(acc and accumulate), partials=partials.data_ptr(), kind=NORM_KIND[kind], stream=_stream(),
+        dx_drop=_ptr(dx_drop), **(dropout.kwargs() if dropout else {}),
     )
+    # with dropout: dx is the gradient of the pre-norm sum (= of the residual), dx_drop that of the dropped input x
+    # (and dbias its column sums); returned as a pair in dx's place
+    dx_ret = dx.view(dy.shape) if not dropout else (dx.view(dy.shape), dx_drop.view(dy.shape))
     if want_dbias or dbias_out is not None:
-        return dx.view(dy.shape), dgamma, dbeta, dbias
-    return dx.view(dy.shape), dgamma, dbeta
+        return dx_ret, dgamma, dbeta, dbias
+    return dx_ret, dgamma, dbeta
 
 
 def attn_fwd(
@@ -375,8 +409,10 @@ def attn_decode(
     start_pos_dev: Optional[torch.Tensor] = None,
     seqlens: Optional[torch.Tensor] = None,
     block_table: Optional[torch.Tensor] = None,
+    rope_pos_off: int = 0,
 ) -> torch.Tensor:
-    """Single-token attention with fused RoPE and kv-cache append. `seqlens` (int32 [B], device) gives every row its
+    """Single-token attention with fused RoPE and kv-cache append. The new token's angles are row
+    (position + rope_pos_off) of the tables (0 when row 0 is position 0). `seqlens` (int32 [B], device) gives every row its
     own context length (continuous batching; negative = idle slot); `block_table` (int32 [B, max_blocks], device) makes
     the caches paged pools [num_blocks, block_size, Hkv, 64] (Examples/simple_vllm.ipynb) — `start_pos` is then the
     largest context length of the batch. With `start_pos_dev` (int32 [1] on the device) the
@@ -414,7 +450,8 @@ def attn_decode(
         "vy_attn_decode", "VyDecode",
         B=B, n_q_heads=n_q_heads, n_kv_heads=n_kv_heads, head_dim=D, start_pos=start_pos,
         cache_len=cache_len, qkv=qkv.data_ptr(), ld_qkv=qkv.stride(0), qkv_dtype=_dt(qkv),
-        rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin), k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),
+        rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin), rope_pos_off=rope_pos_off,
+        rope_rows=rope_cos.shape[0] if rope_cos is not None else 0, k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),
         cache_sb=c_sb, cache_sh=c_sh, cache_sl=c_sl, cache_dtype=_dt(k_cache),
         seqlens=_ptr(seqlens), block_table=_ptr(block_table),
         max_blocks_per_seq=block_table.shape[1] if paged else 0, block_size=block_size,
@@ -465,14 +502,19 @@ def embed(ids: Optional[torch.Tensor], src: torch.Tensor, *, out: torch.Tensor, 
 
 def embed_bwd(ids: Optional[torch.Tensor], dout: torch.Tensor, *, rows: int, H: int, tokens_per_seq: int,
               out_group_stride: int = 0, out_row_off: int = 0, dtable: Optional[torch.Tensor] = None,
-              dpos: Optional[torch.Tensor] = None, pos_row_off: int = 0, out_scale: float = 1.0) -> None:
+              dpos: Optional[torch.Tensor] = None, pos_row_off: int = 0, out_scale: float = 1.0,
+              padding_idx: Optional[int] = None, pos_padding_idx: Optional[int] = None) -> None:
+    """Scatter-add of `dout` rows into the table / position gradients. `padding_idx` / `pos_padding_idx`: the table /
+    position row that nn.Embedding(padding_idx=...) never updates (skipped here too)."""
     _need_cuda(ids, dout, dtable, dpos)
     _lib.call(
         "vy_embed_bwd", "VyEmbed",
         rows=rows, H=H, ids=_ptr(ids), dtype=_dt(dout), vocab=dtable.shape[0] if dtable is not None else rows,
         tokens_per_seq=tokens_per_seq, out_group_stride=out_group_stride, out_row_off=out_row_off,
         pos_row_off=pos_row_off, out_scale=float(out_scale), ld_out=dout.stride(0), dout=dout.data_ptr(),
-        dtable=_ptr(dtable), ld_src=dtable.stride(0) if dtable is not None else 0, dpos=_ptr(dpos), stream=_stream(),
+        dtable=_ptr(dtable), ld_src=dtable.stride(0) if dtable is not None else 0, dpos=_ptr(dpos),
+        padding_idx_plus1=0 if padding_idx is None else padding_idx + 1,
+        pos_padding_idx_plus1=0 if pos_padding_idx is None else pos_padding_idx + 1, stream=_stream(),
     )
 
 
@@ -581,6 +623,17 @@ def act_bwd(dy: torch.Tensor, z: torch.Tensor, act: str = "gelu") -> torch.Tenso
     _lib.check(_lib.lib().vy_act_bwd(dy.numel(), dy.data_ptr(), z.data_ptr(), _dt(dy), ACT[act], out.data_ptr(), _stream()),
                "vy_act_bwd")
     return out
+
+
+def scale_by_ptr(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """x *= scale (fp32 device scalar) in place; free when the scalar is 1."""
+    _need_cuda(x, scale)
+    if scale.dtype != torch.float32 or scale.numel() != 1:
+        raise _lib.VyomError("scale_by_ptr: scale must be one float32 element on the device")
+    if not x.is_contiguous():
+        raise _lib.VyomError("scale_by_ptr: x must be contiguous")
+    _lib.check(_lib.lib().vy_scale_by_ptr(x.numel(), x.data_ptr(), _dt(x), scale.data_ptr(), _stream()), "vy_scale_by_ptr")
+    return x
 
 
 def swiglu_bwd(dh: torch.Tensor, z: torch.Tensor) -> torch.Tensor:

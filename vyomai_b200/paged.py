@@ -98,6 +98,9 @@ class ContinuousBatchEngine:
 
     def add_sequence(self, prompt_ids: List[int], max_gen_len: int = 128) -> int:
         """Queues a request; it becomes active when the pool has blocks for its prompt."""
+        # every position the sequence can reach must have a row in the model's position / RoPE tables: the decode kernel
+        # indexes them without passing through DecoderModel.forward's own check
+        self.model._check_positions(len(prompt_ids) + max_gen_len)
         sid = next(self.id_gen)
         self.waiting_room.append({"sid": sid, "prompt_ids": list(prompt_ids), "max_gen_len": max_gen_len})
         return sid

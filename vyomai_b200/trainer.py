@@ -169,6 +169,7 @@ class Trainer:
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
         self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        ops.DropoutState.step_ptr = self.step_dev  # dropout masks follow the device step counter (fresh per graph replay)
         self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
         per = max(1, int(bucket_mb * 1024 * 1024 / self.fp.grad.element_size()))
@@ -263,7 +264,16 @@ class Trainer:
         self._ready_ids = set()
         self.exchange.begin_step()
 
+    def _check_gemm_health(self) -> None:
+        """A GEMM whose barrier wait timed out finishes with undefined results and raises a per-device flag; its host
+        mirror is read here without synchronising, so a corrupted step stops the run instead of training on."""
+        from . import _lib
+        if _lib.lib().vy_gemm_poison_peek() != 0:
+            raise _lib.VyomError("a barrier wait inside a vy_gemm kernel timed out on this device: the parameters updated since "
+                                 "then are invalid (vy_gemm_poisoned() acknowledges the flag)")
+
     def optimizer_step(self) -> None:
+        self._check_gemm_health()
         self.exchange.finish()
         self.step_count += 1
         self.step_dev.add_(1)  # device-side step counter: the whole step can live in a replayed CUDA graph
@@ -325,6 +335,7 @@ class Trainer:
         for dst, src in zip(self._static_in, (pixel_values, input_ids, attention_mask, labels_full)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        self._check_gemm_health()  # the replayed kernels make no host-side vy_gemm call that would notice the flag
         self._graph.replay()
         self.replayed_kernels += self.graph_kernels
         return self._static_loss
