@@ -431,6 +431,67 @@ VY_API int vy_attn_decode(const VyDecode* p);
 VY_API int vy_attn_decode_splits(int B, int n_kv_heads, int start_pos);
 
 /* ------------------------------------------------------------------------------------------
+ * vy_decode_step — ONE kernel launch per generated token for DecoderModel (bf16): the body of the reference's greedy
+ * loop (VyomAI/models/decoder.py:470-513 -> forward :324-374 -> DecoderLayer.forward :222-250 -> LMHead :267-275 ->
+ * topk(1) :489-496) with a single-token input and a whole-model static kv-cache (layers/kv_cache.py:255-361):
+ *   x = word_embeddings[tok] (+ position_embeddings[pos]);  per layer: q|k|v projection, RoPE at `pos`, cache append at
+ *   slot `pos`, attention over slots [0, pos] WITHOUT a mask (quirk Q3), LN(dense(.) + x), LN(W2 gelu(W1 .) + x) (the FFN
+ *   residual is the layer input, quirk Q2);  logits = decoder(LN(gelu(dense(x)))); next = first index of the row maximum.
+ * Persistent: one CTA per SM, stages separated by grid-wide barriers, weights and cache streamed from HBM once, every
+ * intermediate kept in an L2-resident scratch (`workspace`). On return (stream order) tok[b] holds the next token,
+ * tokens_out[b][pos + 1] too (if given), and *pos has been incremented — so a captured CUDA graph of this ONE launch
+ * replays the whole greedy loop. Constraints: bf16 weights / caches, batch <= 32, head_dim 64, H = 64 * n_q_heads a
+ * multiple of 256 (<= 1024), ffn a multiple of 256 (<= 4096). q|k|v weights / biases of a layer are one packed matrix
+ * [ (n_q + 2 n_kv) * 64, H ] (rows q | k | v). `workspace`: vy_decode_step_workspace_bytes() bytes, 256-byte aligned,
+ * ZEROED once by the caller before first use (it holds the barrier counters) and private to one stream.
+ * vy_decode_step_status(workspace): 0, or 1 if a grid barrier of some earlier step timed out (results invalid).
+ * ------------------------------------------------------------------------------------------ */
+#define VY_DECODE_MAX_LAYERS 24
+
+typedef struct VyDecodeLayer {
+  const void* w_qkv; const void* b_qkv;   /* attention.{query,key,value}.{weight,bias} packed (bias may be NULL) */
+  const void* w_o;   const void* b_o;     /* attention.out.dense */
+  const void* ln1_g; const void* ln1_b;   /* attention.out.layernorm */
+  const void* w_1;   const void* b_1;     /* feed_forward.intermediate */
+  const void* w_2;   const void* b_2;     /* feed_forward.out */
+  const void* ln2_g; const void* ln2_b;   /* feed_forward.layernorm */
+  void* k_cache;     void* v_cache;       /* this layer's [B', n_kv, cache_len, 64] bf16 caches */
+} VyDecodeLayer;
+
+typedef struct VyDecodeStep {
+  int32_t B, H, n_q_heads, n_kv_heads, head_dim, ffn, vocab, n_layers;
+  const VyDecodeLayer* layers;  /* HOST array of n_layers entries */
+  const void* emb;              /* word_embeddings.weight [vocab, H] */
+  const void* pos_table;        /* learned / sinusoidal position rows [>= cache_len, H], or NULL (RoPE models) */
+  const float* rope_cos;        /* fp32 [rope_rows][32] or NULL */
+  const float* rope_sin;
+  int32_t rope_rows;
+  const void* w_d; const void* b_d;             /* lm_head.dense */
+  const void* ln_head_g; const void* ln_head_b; /* lm_head.layer_norm */
+  const void* w_v; const void* b_v;             /* lm_head.decoder [vocab, H], lm_head.bias */
+  float eps_layer, eps_head;
+  int32_t cache_len;
+  int64_t cache_sb, cache_sh, cache_sl;  /* element strides of the caches: batch, head, slot */
+  int32_t pos_bound;            /* upper bound of *pos over the life of this launch description (sizes the kv-split) */
+  int32_t* pos;                 /* device: position / cache slot of the token being fed; incremented by the step */
+  int64_t* tok;                 /* device [B]: in = token fed to this step, out = the greedy next token */
+  int64_t* tokens_out;          /* optional device [B][ld_tokens]: next token also stored at column pos + 1 */
+  int64_t ld_tokens;
+  void* logits;                 /* optional device bf16 [B][ld_logits]: the step's logits */
+  int64_t ld_logits;
+  void* workspace;
+  int64_t workspace_bytes;
+  int64_t* trace;               /* optional device [2 * (5 * n_layers + 2) + 1] (development, tools/decode_bench.py --trace):
+                                   %globaltimer (ns) of CTA 0 at launch [0], when it reaches grid barrier k [1 + 2k] and when
+                                   that barrier opens [2 + 2k] — a step's time stage by stage, own work vs waiting */
+  void* stream;
+} VyDecodeStep;
+
+VY_API int vy_decode_step(const VyDecodeStep* p);
+VY_API int64_t vy_decode_step_workspace_bytes(int B, int H, int n_q_heads, int n_kv_heads, int ffn);
+VY_API int vy_decode_step_status(const void* workspace);
+
+/* ------------------------------------------------------------------------------------------
  * vy_embed_fwd / vy_embed_bwd — row gather with fused positional add, scale and row remap.
  * replaces nn.Embedding lookup + "hidden_state + pos_info" at VyomAI/models/encoder.py:146-152,
  * models/decoder.py:343-350, models/multimodel.py:162-180 (the captioner writes its text rows

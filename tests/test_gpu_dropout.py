@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 def test_dropout_add_layernorm_matches_oracle_given_the_mask(rows, H, p, dtype, tol):
     from vyomai_b200 import ops
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(rows, H, generator=g).to(dtype).float() + 3.0  # offset: no element is (near) zero, so the mask can be read off
+    x = torch.randn(rows, H, generator=g).to(dtype).float() + 10.0  # offset: no element is near zero, so the mask can be read off
     r = torch.randn(rows, H, generator=g).to(dtype).float()
     gam = torch.randn(H, generator=g).to(dtype).float()
     bet = torch.randn(H, generator=g).to(dtype).float()
@@ -32,8 +32,8 @@ def test_dropout_add_layernorm_matches_oracle_given_the_mask(rows, H, p, dtype, 
     y, s, mean, rstd = ops.add_layernorm(x.to(dtype).cuda(), r.to(dtype).cuda(), gam.to(dtype).cuda(), bet.to(dtype).cuda(), 1e-5,
                                          save_stats=True, save_sum=True, dropout=st)
     keep = O.dropout_keep_mask(rows, H, p, st.seed, st.offset, 7)
-    kept_by_kernel = ((s.float().cpu() - r).abs() > 0.5)  # dropped elements leave exactly the residual
-    assert torch.equal(kept_by_kernel, keep)                # integer work: bit-exact
+    kept_by_kernel = ((s.float().cpu() - r).abs() > 2.0)  # dropped elements leave exactly the residual
+    assert int((kept_by_kernel != keep).sum()) == 0         # integer work: bit-exact
     assert abs(float(keep.float().mean()) - (1 - p)) < 4e-3
     s_ref = torch.where(keep, x / (1 - p), torch.zeros_like(x)) + r
     assert rel_l2(s.float().cpu(), s_ref) <= tol
@@ -47,16 +47,16 @@ def test_dropout_add_layernorm_matches_oracle_given_the_mask(rows, H, p, dtype, 
     dx_ref = torch.where(keep, sref.grad / (1 - p), torch.zeros_like(x))                                  # d x: the forward's mask again
     assert torch.equal(dx.float().cpu() != 0, keep & (ds.float().cpu() != 0))
     assert rel_l2(dx.float().cpu(), dx_ref) <= (2 * tol if dtype == torch.bfloat16 else 2e-5)
-    assert rel_l2(dbias.cpu(), dx.float().cpu().sum(0)) <= 2e-5
+    assert rel_l2(dbias.cpu(), dx_ref.sum(0)) <= (2e-5 if dtype == torch.float32 else 2e-3)
     # another call site (offset) or another step draws another mask
     st2 = ops.DropoutState(p, step_ptr=step)
     _, s2, _, _ = ops.add_layernorm(x.to(dtype).cuda(), r.to(dtype).cuda(), gam.to(dtype).cuda(), bet.to(dtype).cuda(), 1e-5,
                                     save_sum=True, dropout=st2)
-    assert not torch.equal((s2.float().cpu() - r).abs() > 0.5, keep)
+    assert not torch.equal((s2.float().cpu() - r).abs() > 2.0, keep)
     step.add_(1)
     _, s3, _, _ = ops.add_layernorm(x.to(dtype).cuda(), r.to(dtype).cuda(), gam.to(dtype).cuda(), bet.to(dtype).cuda(), 1e-5,
                                     save_sum=True, dropout=st)
-    assert torch.equal((s3.float().cpu() - r).abs() > 0.5, O.dropout_keep_mask(rows, H, p, st.seed, st.offset, 8))
+    assert torch.equal((s3.float().cpu() - r).abs() > 2.0, O.dropout_keep_mask(rows, H, p, st.seed, st.offset, 8))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--prefill", type=int, default=512)
     ap.add_argument("--decode", type=int, default=256)
+    ap.add_argument("--trace", action="store_true", help="stage-by-stage %globaltimer trace of one fused decode step (stderr)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     cfg = Cfg()
@@ -103,6 +104,29 @@ def main():
         evs.sort(key=lambda e: e.time_range.start)
         for e in evs:
             print(f"  {e.device_time_total:8.1f}  {e.name[:100]}", file=sys.stderr)
+    if args.trace and getattr(g, "fused", None) is not None:
+        from vyomai_b200 import decode_step
+        L = args.layers
+        nb = 5 * L + 2
+        tr = torch.zeros(2 * nb + 1, dtype=torch.int64, device=dev)
+        tok = g.tok.clone()
+        pos = torch.full((1,), P + N // 2, dtype=torch.int32, device=dev)
+        st = decode_step.FusedDecodeStep(model, g.cache, B, tok, pos, None, pos_bound=g.cache.key_cache[0].shape[2] - 1, trace=tr)
+        for _ in range(3):
+            pos.fill_(P + N // 2)
+            st.launch()
+        torch.cuda.synchronize()
+        t = tr.cpu().tolist()
+        names = []
+        for l in range(L):
+            names += [f"L{l}.qkv", f"L{l}.attn", f"L{l}.out", f"L{l}.ffn1", f"L{l}.ffn2"]
+        names += ["lm.dense", "lm.vocab+argmax"]
+        print(f"fused step trace (CTA 0): total {(t[2 * nb] - t[0]) / 1e3:.1f} us", file=sys.stderr)
+        prev = t[0]
+        for k, nm in enumerate(names):
+            own, wait = t[1 + 2 * k] - prev, t[2 + 2 * k] - t[1 + 2 * k]
+            print(f"  {nm:16s} own {own / 1e3:7.2f} us   wait+barrier {wait / 1e3:7.2f} us", file=sys.stderr)
+            prev = t[2 + 2 * k]
     res = {
         "workload": f"decoder_clm_L{args.layers}_{args.attn}_B{B}_prefill{P}_decode{N}_bf16_staticcache",
         "prefill_tok_per_s": B * P / (pre_ms / 1e3), "prefill_ms": pre_ms,

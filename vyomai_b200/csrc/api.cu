@@ -180,6 +180,8 @@ int vy_abi_sizeof(const char* name) {
   VY_SZ(VyXent);
   VY_SZ(VyAdamW);
   VY_SZ(VyRope);
+  VY_SZ(VyDecodeLayer);
+  VY_SZ(VyDecodeStep);
 #undef VY_SZ
   return -1;
 }

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import torch
 
+from . import decode_step
 from . import functional as F
 from . import ops
 
@@ -24,9 +25,17 @@ class GreedyDecodeGraph:
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)             # cache slot / position of that token
         self.tokens = torch.zeros((batch, max_len), dtype=torch.long, device=dev)
         self.graph = None
+        # the whole step as ONE persistent kernel (csrc/decode_step.cu) when the model fits its constraints
+        self.fused = None
+        if decode_step.supported(model, kv_cache, batch):
+            self.fused = decode_step.FusedDecodeStep(model, kv_cache, batch, self.tok, self.pos, self.tokens,
+                                                     pos_bound=kv_cache.key_cache[0].shape[2] - 1)
 
     # one decode step on the static buffers (eager or under capture)
     def _step(self) -> None:
+        if self.fused is not None:
+            self.fused.launch()
+            return
         m = self.model
         B = self.B
         T = m.word_embeddings.weight.dtype
@@ -73,3 +82,5 @@ class GreedyDecodeGraph:
             self.capture()
         for _ in range(steps):
             self.graph.replay()
+        if self.fused is not None:
+            self.fused.check()
