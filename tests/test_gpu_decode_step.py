@@ -21,6 +21,13 @@ from tests.test_gpu_real_shapes import _build
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _enable_fused_step(monkeypatch):
+    """The one-launch step is opt-in (VY_DECODE_FUSED=1): these tests switch it on."""
+    from vyomai_b200 import decode_step
+    monkeypatch.setattr(decode_step, "ENABLED", True)
+
+
 def _fused(model, cache, B, tok, pos, tokens, logits):
     from vyomai_b200 import decode_step
     assert decode_step.supported(model, cache, B)

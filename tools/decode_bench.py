@@ -108,7 +108,7 @@ def main():
         from vyomai_b200 import decode_step
         L = args.layers
         nb = 5 * L + 2
-        tr = torch.zeros(2 * nb + 1, dtype=torch.int64, device=dev)
+        tr = torch.zeros(256, dtype=torch.int64, device=dev)
         tok = g.tok.clone()
         pos = torch.full((1,), P + N // 2, dtype=torch.int32, device=dev)
         st = decode_step.FusedDecodeStep(model, g.cache, B, tok, pos, None, pos_bound=g.cache.key_cache[0].shape[2] - 1, trace=tr)
@@ -127,6 +127,13 @@ def main():
             own, wait = t[1 + 2 * k] - prev, t[2 + 2 * k] - t[1 + 2 * k]
             print(f"  {nm:16s} own {own / 1e3:7.2f} us   wait+barrier {wait / 1e3:7.2f} us", file=sys.stderr)
             prev = t[2 + 2 * k]
+        def rel(slot, ref):
+            return (t[128 + slot] - ref) / 1e3
+        q0 = t[2 + 2 * 4]  # start of L1.qkv = barrier 4 opened
+        print(f"  L1.qkv detail: prologue {rel(0, q0):.2f}  weights consumed {rel(1, q0):.2f}  partials in smem {rel(2, q0):.2f}  done {rel(3, q0):.2f} us", file=sys.stderr)
+        print(f"  L1.attn detail (warp 0's first item): prologue {rel(16, t[2 + 2 * 5]):.2f}  keys done {rel(17, t[2 + 2 * 5]):.2f}  merged {rel(18, t[2 + 2 * 5]):.2f} us", file=sys.stderr)
+        f0 = t[2 + 2 * 8]  # start of L1.ffn2 = barrier 8 opened
+        print(f"  L1.ffn2 detail: prologue {rel(8, f0):.2f}  weights consumed {rel(9, f0):.2f}  partials in smem {rel(10, f0):.2f}  done {rel(11, f0):.2f}  last-CTA LN start {rel(12, f0):.2f} end {rel(13, f0):.2f} us", file=sys.stderr)
     res = {
         "workload": f"decoder_clm_L{args.layers}_{args.attn}_B{B}_prefill{P}_decode{N}_bf16_staticcache",
         "prefill_tok_per_s": B * P / (pre_ms / 1e3), "prefill_ms": pre_ms,

@@ -37,12 +37,12 @@
 
 namespace vy {
 
-constexpr int DS_THREADS = 256;
-constexpr int DS_WARPS = 8;
+constexpr int DS_THREADS = 512;  // 16 warps: four per scheduler — the stages are latency chains, so issue-level parallelism is what they lack
+constexpr int DS_WARPS = 16;
 constexpr int DS_MAXB = 32;
 constexpr int DS_HD = 64;
 constexpr int DS_MAX_BARRIERS = 5 * VY_DECODE_MAX_LAYERS + 8;
-constexpr int DS_RED = 16 * 33;  // one warp's partial tile: [16 features][32 tokens], rows padded against bank conflicts
+constexpr int DS_RED = 16 * 32;  // one warp's partial tile: [16 features][32 tokens], token index XOR-swizzled by the feature
 
 typedef __nv_bfloat16 bf16;
 
@@ -74,7 +74,9 @@ struct DsParams {
   void* logits;               // optional [B][ld_logits] bf16
   long long ld_logits;
   // scratch (global)
-  bf16* xbuf;    // [B][H]   layer input x
+  bf16* xbuf;    // [B][H]   layer input x (= LN2 of the previous layer's sum)
+  bf16* ybuf;    // [B][H]   LN1(s1) of the current layer / LN of the LM head
+  unsigned int* ln_ticket;    // last-CTA election of the stages that end in a LayerNorm
   float* qkv;    // [B][NQKV]
   bf16* attn;    // [B][Hq*64]
   float* s1;     // [B][H]
@@ -96,6 +98,21 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {  // weights / cache
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+// DRAM -> L2 prefetch. Measured on this part: one dependent round of loads costs ~0.5 us when it hits L2 and 2-2.5 us from
+// DRAM at this working set (tools/microbench/lat_micro.cu) — five stages of two or three dependent rounds per layer is what
+// made the per-op decode step ten times slower than its byte count. Weights and cached keys / values do not depend on the
+// step's activations, so every CTA asks L2 for its share of the NEXT layer's bytes a whole layer ahead, one
+// `prefetch.global.L2` per 128-byte line spread over all threads of the grid (through the load / store unit: bulk prefetches
+// queue in the copy engine in front of the activation copies and delayed them).
+__device__ __forceinline__ void prefetch_line_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// lines [0, bytes / 128) of a range, split evenly over (nparts * 512) threads; this CTA is part `part`
+__device__ __forceinline__ void prefetch_range_l2(const void* base, long long bytes, int part, int nparts) {
+  const long long lines = (bytes + 127) >> 7;
+  const long long per = (lines + nparts - 1) / nparts;
+  const long long lo = per * part, hi = lo + per < lines ? lo + per : lines;
+  const char* c = static_cast<const char*>(base);
+  for (long long i = lo + threadIdx.x; i < hi; i += DS_THREADS) prefetch_line_l2(c + (i << 7));
+}
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -116,11 +133,11 @@ __device__ __forceinline__ unsigned int ds_order_bits(float v) {
 // A wait that does not complete (a CTA that is not resident: the launch did not get every SM) raises the abort flag;
 // every later barrier then falls through, so the kernel ends with garbage and a raised flag instead of hanging the GPU.
 __device__ __forceinline__ void grid_barrier(const DsParams& p, int k) {
-  __syncthreads();
+  __syncthreads();  // CTA-scope order of every thread's writes before thread 0's gpu-scope release (cumulativity)
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0 && p.trace) p.trace[1 + 2 * k] = static_cast<long long>(globaltimer_ns());  // CTA 0 done with the stage
-    __threadfence();
-    atomicAdd(&p.bar[k], 1u);
+    // one release-atomic instead of a full memory barrier + atomic: a gpu-scope fence costs ~1 us on this part
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&p.bar[k]) : "memory");
     unsigned int spins = 0;
     while (ld_acquire_u32(&p.bar[k]) < gridDim.x) {
       if ((++spins & 255u) == 0) {
@@ -133,148 +150,236 @@ __device__ __forceinline__ void grid_barrier(const DsParams& p, int k) {
     }
     if (blockIdx.x == 0 && k > 0) p.bar[k - 1] = 0u;
     if (blockIdx.x == 0 && p.trace) p.trace[2 + 2 * k] = static_cast<long long>(globaltimer_ns());             // every CTA done
-    __threadfence();
   }
-  __syncthreads();
+  __syncthreads();  // thread 0's acquire + this barrier: the other CTAs' writes are visible to the whole CTA (read through L2)
 }
 
-// ---- stage prologues: the stage's activations -> shared memory, bf16 [32][K] with a padded row stride ----
-// row stride in bytes = K * 2 + 64: 16-byte fragment loads of 8 consecutive rows then fall into distinct banks
+// development: fine-grained %globaltimer marks of CTA 0 / thread 0 inside selected stages (trace[128 + slot])
+__device__ __forceinline__ void ds_mark(const DsParams& p, int slot) {
+  if (slot >= 0 && p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[128 + slot] = static_cast<long long>(globaltimer_ns());
+}
+__device__ __forceinline__ void ds_mark_any(const DsParams& p, int slot) {  // whichever CTA gets here (thread 0)
+  if (slot >= 0 && p.trace && threadIdx.x == 0) p.trace[128 + slot] = static_cast<long long>(globaltimer_ns());
+}
+
+// ---- shared-memory plumbing ---------------------------------------------------------------------
+// A stage's activations ([B <= 32][K] bf16) are brought into shared memory by the copy engine: ONE bulk copy per row
+// (cp.async.bulk, mbarrier tx-count) issued by the lanes of warp 0 — measured 1.1 us for 196 KB per SM against 3.6 us for
+// 16-byte loads + stores by 512 threads, and no instruction stream to fetch. Row stride = K * 2 + 64 bytes, so that the
+// 16-byte fragment loads of 8 consecutive rows fall into distinct banks.
 __device__ __forceinline__ int xs_stride(int K) { return K * 2 + 64; }
 
-// Xs[r][:] = LayerNorm(src[r][:]) (fp32 [B][H], written by an earlier stage -> read through L2), optionally also written
-// to xbuf (bf16 global: the residual operand of later stages) by the CTA whose index equals the row.
-__device__ void fill_layernorm(const DsParams& p, unsigned char* Xs, const float* src, const bf16* gamma, const bf16* beta,
-                               float eps, bf16* xout) {
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, unsigned int parity) {
+  while (!mbar_try_wait(reinterpret_cast<uint64_t*>(bar), parity)) {
+  }
+}
+
+enum { DS_IN_COPY = 0, DS_IN_EMBED = 2 };
+enum { DS_EPI_F32 = 0, DS_EPI_F32_RESID = 1, DS_EPI_GELU_BF16 = 2, DS_EPI_GELU_F32 = 3 };
+
+struct StageIn {
+  int kind;            // DS_IN_COPY: bf16 [B][K] rows in global memory; DS_IN_EMBED: gather of the tokens' embedding rows
+  const void* src;
+  bf16* xout;          // EMBED: also publish the rows (bf16) here — the residual operand of later stages
+};
+
+// LayerNorm that FOLLOWS a stage: the stage's output is an fp32 pre-norm sum whose rows are spread over many CTAs. Every
+// CTA of the stage takes a ticket when its units are done; the last one normalises all rows (two per warp) and writes them
+// as bf16 — the next stage then only bulk-copies them. Doing the LayerNorm redundantly in every consuming CTA cost more
+// instructions per step than all the GEMMs together.
+struct PostLN {
+  const float* src;    // [B][H] fp32, written by this stage (null: no LayerNorm after this stage)
+  const bf16* gamma;
+  const bf16* beta;
+  float eps;
+  bf16* dst;           // [B][H] bf16
+  unsigned int* ticket;
+};
+
+__device__ __noinline__ void layernorm_rows(const DsParams& p, const PostLN& ln) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, stride = xs_stride(H);
-  for (int r = warp; r < p.ng * 8; r += DS_WARPS) {
-    bf16* dst = reinterpret_cast<bf16*>(Xs + static_cast<size_t>(r) * stride);
-    if (r >= p.B) {
-      for (int c = lane * 8; c < H; c += 256) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    float v[8][4];  // H <= 1024: 8 float4 per lane
-    float sum = 0.f;
+  const int H = p.H;
+  for (int r0 = warp; r0 < p.B; r0 += 2 * DS_WARPS) {
+    float v[2][8][4];  // H <= 1024: 8 float4 per lane and row
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = i * 128 + lane * 4;
-      if (c < H) {
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * H + c));
-        v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
-        sum += t.x + t.y + t.z + t.w;
+    for (int u = 0; u < 2; ++u) {
+      const int r = r0 + u * DS_WARPS;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = i * 128 + lane * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < H && r < p.B) t = __ldcg(reinterpret_cast<const float4*>(ln.src + static_cast<size_t>(r) * H + c));
+        v[u][i][0] = t.x; v[u][i][1] = t.y; v[u][i][2] = t.z; v[u][i][3] = t.w;
       }
     }
+    float sum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / H;
-    float sq = 0.f;
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i * 128 + lane * 4 < H) {
+      for (int i = 0; i < 8; ++i)
+        if (i * 128 + lane * 4 < H) sum[u] += v[u][i][0] + v[u][i][1] + v[u][i][2] + v[u][i][3];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float d = v[i][j] - mean;
-          sq += d * d;
+    for (int o = 16; o > 0; o >>= 1) {
+      sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+      sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+    }
+    const float mean[2] = {sum[0] / H, sum[1] / H};
+    float sq[2] = {0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 128 + lane * 4 < H) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float d = v[u][i][j] - mean[u];
+            sq[u] += d * d;
+          }
         }
-      }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / H + eps);
-    const bool wr = xout != nullptr && static_cast<int>(blockIdx.x) == r;
+    for (int o = 16; o > 0; o >>= 1) {
+      sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], o);
+      sq[1] += __shfl_xor_sync(0xffffffffu, sq[1], o);
+    }
+    const float rstd[2] = {rsqrtf(sq[0] / H + ln.eps), rsqrtf(sq[1] / H + ln.eps)};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = i * 128 + lane * 4;
       if (c < H) {
-        const uint2 gr = *reinterpret_cast<const uint2*>(gamma + c);
-        const uint2 br = *reinterpret_cast<const uint2*>(beta + c);
+        const uint2 gr = *reinterpret_cast<const uint2*>(ln.gamma + c);
+        const uint2 br = *reinterpret_cast<const uint2*>(ln.beta + c);
         const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gr);
         const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&br);
         const float2 g01 = __bfloat1622float2(g2[0]), g23 = __bfloat1622float2(g2[1]);
         const float2 b01 = __bfloat1622float2(b2[0]), b23 = __bfloat1622float2(b2[1]);
-        uint2 o;
-        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-        o2[0] = __floats2bfloat162_rn((v[i][0] - mean) * rstd * g01.x + b01.x, (v[i][1] - mean) * rstd * g01.y + b01.y);
-        o2[1] = __floats2bfloat162_rn((v[i][2] - mean) * rstd * g23.x + b23.x, (v[i][3] - mean) * rstd * g23.y + b23.y);
-        *reinterpret_cast<uint2*>(dst + c) = o;
-        if (wr) *reinterpret_cast<uint2*>(xout + static_cast<size_t>(r) * H + c) = o;
-      }
-    }
-  }
-}
-
-// Xs[r][:] = src[r][:] (bf16 [B][K] global, written by an earlier stage)
-__device__ void fill_copy(const DsParams& p, unsigned char* Xs, const bf16* src, int K) {
-  const int stride = xs_stride(K), per_row = K >> 3;
-  const int total = p.ng * 8 * per_row;
-  for (int i = threadIdx.x; i < total; i += DS_THREADS) {
-    const int r = i / per_row, c = (i - r * per_row) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < p.B) v = __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * K + c));
-    *reinterpret_cast<uint4*>(Xs + static_cast<size_t>(r) * stride + c * 2) = v;
-  }
-}
-
-// Xs[r][:] = emb[tok[r]][:] (+ pos_table[pos][:]); also written to xbuf by CTA r
-__device__ void fill_embedding(const DsParams& p, unsigned char* Xs, int pos) {
-  const int H = p.H, stride = xs_stride(H), per_row = H >> 3;
-  const int total = p.ng * 8 * per_row;
-  for (int i = threadIdx.x; i < total; i += DS_THREADS) {
-    const int r = i / per_row, c = (i - r * per_row) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < p.B) {
-      const long long t = p.tok[r];
-      v = *reinterpret_cast<const uint4*>(p.emb + static_cast<size_t>(t) * H + c);
-      if (p.pos_table) {
-        const uint4 q = *reinterpret_cast<const uint4*>(p.pos_table + static_cast<size_t>(pos) * H + c);
-        __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&v);
-        const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = __hadd2(a[j], b[j]);  // bf16 add: what `hidden_state + pos_info` does in a bf16 model
+        for (int u = 0; u < 2; ++u) {
+          const int r = r0 + u * DS_WARPS;
+          if (r >= p.B) continue;
+          uint2 o;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+          o2[0] = __floats2bfloat162_rn((v[u][i][0] - mean[u]) * rstd[u] * g01.x + b01.x, (v[u][i][1] - mean[u]) * rstd[u] * g01.y + b01.y);
+          o2[1] = __floats2bfloat162_rn((v[u][i][2] - mean[u]) * rstd[u] * g23.x + b23.x, (v[u][i][3] - mean[u]) * rstd[u] * g23.y + b23.y);
+          *reinterpret_cast<uint2*>(ln.dst + static_cast<size_t>(r) * H + c) = o;
+        }
       }
-      if (static_cast<int>(blockIdx.x) == r) *reinterpret_cast<uint4*>(p.xbuf + static_cast<size_t>(r) * H + c) = v;
     }
-    *reinterpret_cast<uint4*>(Xs + static_cast<size_t>(r) * stride + c * 2) = v;
   }
 }
 
-// ---- GEMM stage, K split over the warps of a CTA ---------------------------------------------------
-// out[n][f] = epi(sum_k Xs[n][k] W[f][k] + bias[f]) for f in [0, N), n in [0, B). Unit = 16 features.
-enum { DS_EPI_F32 = 0, DS_EPI_F32_RESID = 1, DS_EPI_GELU_BF16 = 2, DS_EPI_GELU_F32 = 3 };
-
-template <int KB_PER_WARP>  // 32-wide k-blocks per warp: K = 256 * KB_PER_WARP
-__device__ void gemm_ksplit(const DsParams& p, const unsigned char* Xs, float* red, const bf16* W, const bf16* bias, int N, int epi,
-                            void* out, long long ldo, const bf16* resid) {
-  constexpr int K = 256 * KB_PER_WARP;
+// ---- one GEMM stage: prologue (activations -> smem) + K-split GEMM + epilogue (+ LayerNorm by the last CTA) ------------
+// out[n][f] = epi(sum_k X[n][k] W[f][k] + bias[f]) for f in [0, N), n in [0, B). Unit = 16 features x K.
+// One copy of this code serves every K-split stage (__noinline__, run-time K): the step runs each stage once, so code
+// that is instantiated per shape or per call site is fetched cold every time — a 24 k-instruction kernel spent more time
+// on instruction fetch than on its data.
+// The 16 warps work as one group (K a multiple of 512: every warp takes K / 16 of ONE unit) or as two groups of 8 warps on
+// two units at once; a group synchronises on its own named barrier. The first chunk of a CTA's weight loads is issued
+// BEFORE the prologue's data is awaited: weights do not depend on activations.
+__device__ __noinline__ void stage_gemm(const DsParams& p, int K, const StageIn& in, unsigned char* Xs, float* red,
+                                        unsigned long long* fill_bar, unsigned int& fill_phase, const bf16* W, const bf16* bias, int N,
+                                        int epi, void* out, long long ldo, const bf16* resid, const PostLN& post, int mk = -1) {
+  const int units = (N + 15) >> 4;
+  if (static_cast<int>(blockIdx.x) >= units) return;  // this CTA owns no unit of the stage
+  const int WG = (K & 511) == 0 ? 16 : 8;   // warps per group
+  const int NG = DS_WARPS / WG;             // groups
+  const int kbw = K / (32 * WG);            // 32-wide k-blocks per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp / WG, gwarp = warp - group * WG;
+  const int tig = threadIdx.x - group * WG * 32;  // thread index inside the group
   const int g = lane >> 2, t = lane & 3;
   const int stride = K * 2 + 64;
-  const int units = (N + 15) >> 4;
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int f0 = u * 16;
+  float* gred = red + group * (WG * DS_RED);
+  const int npt = 512 / (WG * 32);  // results per thread in the reduction: 1 (16 warps) or 2 (8 warps)
+
+  // ---- prologue, asynchronous part: one bulk copy per row ----
+  const int rows = p.ng * 8;
+  if (warp == 0) {
+    fence_proxy_async_smem();  // earlier generic-proxy accesses of this smem are ordered before the copy engine's writes
+    const unsigned int row_bytes = static_cast<unsigned int>(K) * 2u;
+    if (lane == 0) mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(fill_bar), row_bytes * static_cast<unsigned int>(p.B));
+    __syncwarp();
+    if (lane < p.B) {
+      const bf16* srow = in.kind == DS_IN_COPY ? static_cast<const bf16*>(in.src) + static_cast<size_t>(lane) * K
+                                               : p.emb + static_cast<size_t>(p.tok[lane]) * p.H;  // embedding gather
+      bulk_g2s(Xs + static_cast<size_t>(lane) * stride, srow, row_bytes, fill_bar);
+    }
+  } else if (warp == 1) {
+    for (int r = p.B + (lane >> 3); r < rows; r += 4)  // padding rows of the last token group: zeros
+      for (int c = (lane & 7) * 16; c < K * 2; c += 128) *reinterpret_cast<uint4*>(Xs + static_cast<size_t>(r) * stride + c) = make_uint4(0, 0, 0, 0);
+  }
+
+  constexpr int CH = 4;  // k-blocks whose weight loads are in flight together (2 x 16-byte loads per thread and block)
+  uint4 ra[CH], rb[CH];
+  int u = blockIdx.x + group * gridDim.x;
+  auto load_chunk = [&](int unit, int c0) {
+    const int f0 = unit * 16;
     const bool ok0 = f0 + g < N, ok1 = f0 + g + 8 < N;
-    const bf16* w0 = W + static_cast<size_t>(f0 + g) * K + warp * (32 * KB_PER_WARP) + t * 8;
+    const bf16* w0 = W + static_cast<size_t>(f0 + g) * K + gwarp * (32 * kbw) + t * 8;
     const bf16* w1 = w0 + static_cast<size_t>(8) * K;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const bool inb = c0 + j < kbw;
+      ra[j] = (ok0 && inb) ? ldg_stream(w0 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
+      rb[j] = (ok1 && inb) ? ldg_stream(w1 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  bool preloaded = false;
+  if (u < units) {
+    load_chunk(u, 0);
+    preloaded = true;
+  }
+
+  // ---- prologue, synchronous part ----
+  mbar_wait_spin(fill_bar, fill_phase);
+  fill_phase ^= 1u;
+  if (in.kind == DS_IN_EMBED && in.xout != nullptr && static_cast<int>(blockIdx.x) < p.B) {
+    const int r = blockIdx.x;  // CTA r publishes row r for the residual adds of later stages
+    for (int c = threadIdx.x * 8; c < p.H; c += DS_THREADS * 8)
+      *reinterpret_cast<uint4*>(in.xout + static_cast<size_t>(r) * p.H + c) = *reinterpret_cast<const uint4*>(Xs + static_cast<size_t>(r) * stride + c * 2);
+  }
+  __syncthreads();  // (the zero rows written by warp 1)
+  ds_mark(p, mk);   // prologue done
+
+  for (; u < units; u += NG * gridDim.x) {
+    const int f0 = u * 16;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    // k-blocks whose weight loads are in flight together (2 x 16-byte loads per thread and block)
-    constexpr int CH = KB_PER_WARP % 6 == 0 ? 6 : (KB_PER_WARP % 4 == 0 ? 4 : KB_PER_WARP);
-    static_assert(KB_PER_WARP % CH == 0, "chunking");
-#pragma unroll 1
-    for (int c0 = 0; c0 < KB_PER_WARP; c0 += CH) {
-      uint4 ra[CH], rb[CH];
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        ra[j] = ok0 ? ldg_stream(w0 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
-        rb[j] = ok1 ? ldg_stream(w1 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
+    // this thread's results of the unit (features er [, er + 1] of token en): their bias / residual loads go out now, so
+    // their latency hides behind the weight stream instead of following the reduction
+    const int en = (tig * npt) >> 4, er = (tig * npt) & 15;
+    const int ef = f0 + er;
+    const bool e_ok = en < p.B && ef < N, e_two = npt == 2 && ef + 1 < N;
+    float eb0 = 0.f, eb1 = 0.f, ex0 = 0.f, ex1 = 0.f;
+    if (e_ok) {
+      if (bias) {
+        eb0 = __bfloat162float(bias[ef]);
+        if (e_two) eb1 = __bfloat162float(bias[ef + 1]);
       }
+      if (epi == DS_EPI_F32_RESID) {  // (written by other CTAs in an earlier stage: L2 read)
+        const unsigned short r0 = __ldcg(reinterpret_cast<const unsigned short*>(resid + static_cast<size_t>(en) * ldo + ef));
+        ex0 = __bfloat162float(*reinterpret_cast<const bf16*>(&r0));
+        if (e_two) {
+          const unsigned short r1 = __ldcg(reinterpret_cast<const unsigned short*>(resid + static_cast<size_t>(en) * ldo + ef + 1));
+          ex1 = __bfloat162float(*reinterpret_cast<const bf16*>(&r1));
+        }
+      }
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < kbw; c0 += CH) {
+      if (!preloaded) load_chunk(u, c0);
+      preloaded = false;
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
-        const int kbyte = (warp * (32 * KB_PER_WARP) + (c0 + j) * 32 + t * 8) * 2;
+        if (c0 + j >= kbw) break;
+        const int kbyte = (gwarp * (32 * kbw) + (c0 + j) * 32 + t * 8) * 2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < p.ng) {
@@ -285,42 +390,37 @@ __device__ void gemm_ksplit(const DsParams& p, const unsigned char* Xs, float* r
         }
       }
     }
-    // partial tile of this warp -> red[warp][feature r][token n]
-    float* my = red + warp * DS_RED;
+    ds_mark(p, mk < 0 ? -1 : mk + 1);  // weights consumed (thread 0's share)
+    // partial tile of this warp -> gred[warp][feature r][token n ^ r]
+    float* my = gred + gwarp * DS_RED;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = i * 8 + t * 2;
-      my[g * 33 + n] = acc[i][0];
-      my[g * 33 + n + 1] = acc[i][1];
-      my[(g + 8) * 33 + n] = acc[i][2];
-      my[(g + 8) * 33 + n + 1] = acc[i][3];
+      my[g * 32 + (n ^ g)] = acc[i][0];
+      my[g * 32 + ((n + 1) ^ g)] = acc[i][1];
+      my[(g + 8) * 32 + (n ^ (g + 8))] = acc[i][2];
+      my[(g + 8) * 32 + ((n + 1) ^ (g + 8))] = acc[i][3];
     }
-    __syncthreads();
-    // 512 results, 2 per thread: features r, r + 1 of token n (fixed summation order over the warps)
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(WG * 32) : "memory");
+    ds_mark(p, mk < 0 ? -1 : mk + 2);  // every warp of the group has its partial in smem
+    // 512 results over the group's threads (fixed summation order over the warps: deterministic)
     {
-      const int idx = threadIdx.x * 2;
-      const int n = idx >> 4, r = idx & 15;
+      const int n = en, r = er, f = ef;
       float v0 = 0.f, v1 = 0.f;
-#pragma unroll
-      for (int w = 0; w < DS_WARPS; ++w) {
-        v0 += red[w * DS_RED + r * 33 + n];
-        v1 += red[w * DS_RED + (r + 1) * 33 + n];
+      for (int w = 0; w < WG; ++w) {
+        v0 += gred[w * DS_RED + r * 32 + (n ^ r)];
+        if (npt == 2) v1 += gred[w * DS_RED + (r + 1) * 32 + (n ^ (r + 1))];
       }
-      const int f = f0 + r;
-      if (n < p.B && f < N) {
-        const bool two = f + 1 < N;
-        if (bias) {
-          v0 += __bfloat162float(bias[f]);
-          if (two) v1 += __bfloat162float(bias[f + 1]);
-        }
+      if (e_ok) {
+        const bool two = e_two;
+        v0 += eb0;
+        v1 += eb1;
         if (epi == DS_EPI_GELU_BF16 || epi == DS_EPI_GELU_F32) {
           v0 = gelu_erf(v0);
           v1 = gelu_erf(v1);
         }
-        if (epi == DS_EPI_F32_RESID) {
-          v0 += __bfloat162float(resid[static_cast<size_t>(n) * ldo + f]);
-          if (two) v1 += __bfloat162float(resid[static_cast<size_t>(n) * ldo + f + 1]);
-        }
+        v0 += ex0;
+        v1 += ex1;
         if (epi == DS_EPI_GELU_BF16) {
           bf16* o = reinterpret_cast<bf16*>(out) + static_cast<size_t>(n) * ldo + f;
           if (two) *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v0, v1);
@@ -332,181 +432,234 @@ __device__ void gemm_ksplit(const DsParams& p, const unsigned char* Xs, float* r
         }
       }
     }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(WG * 32) : "memory");
+  }
+
+  // ---- LayerNorm of the finished sums by the last CTA of the stage ----
+  if (post.src != nullptr) {
+    unsigned int& s_last_cta = *reinterpret_cast<unsigned int*>(fill_bar + 32);  // (the dynamic region's tail: no static smem, the plan uses all 227 KB)
     __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int ctas = static_cast<unsigned int>(units < static_cast<int>(gridDim.x) ? units : static_cast<int>(gridDim.x));
+      unsigned int prev;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(post.ticket) : "memory");
+      s_last_cta = prev == ctas - 1u ? 1u : 0u;
+      if (s_last_cta) *post.ticket = 0u;  // self-reset for the next stage / launch
+    }
+    __syncthreads();
+    if (s_last_cta) {
+      ds_mark_any(p, mk < 0 ? -1 : mk + 4);
+      layernorm_rows(p, post);
+      ds_mark_any(p, mk < 0 ? -1 : mk + 5);
+    }
   }
 }
 
-__device__ void gemm_ksplit_dispatch(const DsParams& p, int K, const unsigned char* Xs, float* red, const bf16* W, const bf16* bias,
-                                     int N, int epi, void* out, long long ldo, const bf16* resid) {
-  switch (K >> 8) {
-    case 1: gemm_ksplit<1>(p, Xs, red, W, bias, N, epi, out, ldo, resid); break;
-    case 2: gemm_ksplit<2>(p, Xs, red, W, bias, N, epi, out, ldo, resid); break;
-    case 3: gemm_ksplit<3>(p, Xs, red, W, bias, N, epi, out, ldo, resid); break;
-    case 4: gemm_ksplit<4>(p, Xs, red, W, bias, N, epi, out, ldo, resid); break;
-    case 8: gemm_ksplit<8>(p, Xs, red, W, bias, N, epi, out, ldo, resid); break;
-    case 12: gemm_ksplit<12>(p, Xs, red, W, bias, N, epi, out, ldo, resid); break;
-    default: gemm_ksplit<16>(p, Xs, red, W, bias, N, epi, out, ldo, resid); break;
-  }
-}
-
-// ---- vocabulary projection + greedy argmax: a warp owns whole units (16 features x K), register double buffering ----
-template <int KB>  // k-blocks of 32: K = 32 * KB, KB % 4 == 0
-__device__ void lm_head_argmax(const DsParams& p, const unsigned char* Xs, unsigned long long* s_keys) {
-  constexpr int K = 32 * KB;
-  constexpr int CH = 4;          // k-blocks per chunk
-  constexpr int NCH = KB / CH;   // chunks per unit
+// ---- vocabulary projection + greedy argmax ---------------------------------------------------------------
+// The 77 MB of lm_head.decoder.weight are the largest single stream of the step. A unit (16 vocabulary rows x H) is ONE
+// contiguous 24 KB block of the weight: it goes through a shared-memory ring filled by the copy engine with one bulk copy
+// per unit, three slots per 8-warp group, so up to ~150 KB per SM are in flight without holding a register. Each group
+// multiplies its unit (K split over its 8 warps; the unpadded weight rows cost a 2-way bank conflict on 6 loads per warp,
+// irrelevant), reduces through smem, adds the bias, rounds to the model dtype and folds the 16 logits of every token into
+// a running (value, index) maximum; one 64-bit atomicMax per token and CTA at the end (first index wins ties: the
+// torch.topk(k=1) rule of models/decoder.py:489-496).
+constexpr int DS_RING = 3;
+__device__ __noinline__ void lm_head_argmax(const DsParams& p, const bf16* xin, unsigned char* Xs, float* red, unsigned long long* bars,
+                                            unsigned int& fill_phase) {
+  const int K = p.H;
+  const int kbw = K / 256;  // k-blocks per warp (8 warps per group)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp >> 3, gwarp = warp & 7;
+  const int tig = threadIdx.x & 255;
   const int g = lane >> 2, t = lane & 3;
   const int stride = K * 2 + 64;
+  const int wstride = K * 2;  // weight rows in the ring: as in global memory
   const int N = p.V;
   const int units = (N + 15) >> 4;
-  const int gw = blockIdx.x * DS_WARPS + warp, nw = gridDim.x * DS_WARPS;
-  unsigned long long best[4][2];  // per token group: tokens 8 i + 2 t, + 1
+  unsigned char* ring0 = Xs + ((static_cast<size_t>(32) * stride + 1023) & ~static_cast<size_t>(1023));
+  unsigned char* ring = ring0 + static_cast<size_t>(group) * DS_RING * 16 * wstride;
+  unsigned long long* fill_bar = bars;
+  unsigned long long* full = bars + 1 + group * DS_RING;
+  float* gred = red + group * (8 * DS_RED);
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(red + 2 * 8 * DS_RED);  // [2 groups][32]
+
+  // this group's units: u = 2 * (blockIdx.x + i * gridDim.x) + group
+  const int ustep = 2 * gridDim.x;
+  const int u0 = 2 * blockIdx.x + group;
+  auto issue = [&](int u, int slot) {  // one bulk copy per unit, by the first lane of the group
+    if (gwarp != 0 || lane != 0 || u >= units) return;
+    const unsigned int bytes = static_cast<unsigned int>(min(16, N - u * 16)) * static_cast<unsigned int>(wstride);
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&full[slot]), bytes);
+    bulk_g2s(ring + static_cast<size_t>(slot) * 16 * wstride, p.w_v + static_cast<size_t>(u) * 16 * K, bytes, &full[slot]);
+  };
 #pragma unroll
-  for (int i = 0; i < 4; ++i) best[i][0] = best[i][1] = 0ull;
-  if (gw < units) {
-    const int my_units = (units - gw + nw - 1) / nw;
-    const int total = my_units * NCH;
-    uint4 ra[2][CH], rb[2][CH];
-    auto issue = [&](int buf, int ci) {
-      const int u = gw + (ci / NCH) * nw, c = ci % NCH;
-      const int f0 = u * 16;
-      const bf16* w0 = p.w_v + static_cast<size_t>(f0 + g) * K + c * (CH * 32) + t * 8;
-      const bool ok0 = f0 + g < N, ok1 = f0 + g + 8 < N;
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        ra[buf][j] = ok0 ? ldg_stream(w0 + j * 32) : make_uint4(0, 0, 0, 0);
-        rb[buf][j] = ok1 ? ldg_stream(w0 + static_cast<size_t>(8) * K + j * 32) : make_uint4(0, 0, 0, 0);
-      }
-    };
-    issue(0, 0);
-    float acc[4][4];
-#pragma unroll 1
-    for (int ci = 0; ci < total; ci += 2) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {  // static register buffer indices
-        const int cc = ci + half;
-        if (cc >= total) break;
-        if (cc + 1 < total) issue(half ^ 1, cc + 1);
-        const int c = cc % NCH;
-        if (c == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int kbyte = (c * (CH * 32) + j * 32 + t * 8) * 2;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < p.ng) {
-              const uint4 xb = *reinterpret_cast<const uint4*>(Xs + static_cast<size_t>(i * 8 + g) * stride + kbyte);
-              mma_bf16(acc[i], ra[half][j].x, rb[half][j].x, ra[half][j].y, rb[half][j].y, xb.x, xb.y);
-              mma_bf16(acc[i], ra[half][j].z, rb[half][j].z, ra[half][j].w, rb[half][j].w, xb.z, xb.w);
-            }
-          }
-        }
-        if (c == NCH - 1) {  // unit finished: bias, round to the model dtype (what the logits tensor holds), fold into the running best
-          const int f0 = (gw + (cc / NCH) * nw) * 16;
-          const int fa = f0 + g, fb = f0 + g + 8;
-          const float ba = (p.b_v && fa < N) ? __bfloat162float(p.b_v[fa]) : 0.f;
-          const float bb = (p.b_v && fb < N) ? __bfloat162float(p.b_v[fb]) : 0.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < p.ng) {
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int n = i * 8 + t * 2 + e;
-                const bf16 la = __float2bfloat16_rn(acc[i][e] + ba), lb = __float2bfloat16_rn(acc[i][2 + e] + bb);
-                if (fa < N) {
-                  const unsigned long long key = (static_cast<unsigned long long>(ds_order_bits(__bfloat162float(la))) << 32) | (0xffffffffu - static_cast<unsigned int>(fa));
-                  best[i][e] = key > best[i][e] ? key : best[i][e];
-                  if (p.logits && n < p.B) reinterpret_cast<bf16*>(p.logits)[static_cast<size_t>(n) * p.ld_logits + fa] = la;
-                }
-                if (fb < N) {
-                  const unsigned long long key = (static_cast<unsigned long long>(ds_order_bits(__bfloat162float(lb))) << 32) | (0xffffffffu - static_cast<unsigned int>(fb));
-                  best[i][e] = key > best[i][e] ? key : best[i][e];
-                  if (p.logits && n < p.B) reinterpret_cast<bf16*>(p.logits)[static_cast<size_t>(n) * p.ld_logits + fb] = lb;
-                }
-              }
-            }
-          }
-        }
-      }
-    }
+  for (int i = 0; i < DS_RING; ++i) issue(u0 + i * ustep, i);  // weights first: they do not wait for the activations
+
+  // prologue: the normalised rows (bf16, written by the last CTA of the previous stage) -> Xs
+  if (warp == 0) {
+    fence_proxy_async_smem();
+    if (lane == 0) mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(fill_bar), static_cast<unsigned int>(K) * 2u * static_cast<unsigned int>(p.B));
+    __syncwarp();
+    if (lane < p.B) bulk_g2s(Xs + static_cast<size_t>(lane) * stride, xin + static_cast<size_t>(lane) * K, static_cast<unsigned int>(K) * 2u, fill_bar);
+  } else if (warp == 1) {
+    for (int r = p.B + (lane >> 3); r < p.ng * 8; r += 4)
+      for (int c = (lane & 7) * 16; c < K * 2; c += 128) *reinterpret_cast<uint4*>(Xs + static_cast<size_t>(r) * stride + c) = make_uint4(0, 0, 0, 0);
   }
-  // fold the 8 feature lanes (g) of every token, then one atomic per token and warp
+  mbar_wait_spin(fill_bar, fill_phase);
+  fill_phase ^= 1u;
+  __syncthreads();
+
+  unsigned long long best = 0ull;  // owner threads ((tig & 7) == 0): running maximum of token tig >> 3
+  unsigned int phases = 0u;        // bit s: parity of ring slot s
+  int slot = 0;
+  for (int u = u0; u < units; u += ustep) {
+    mbar_wait_spin(&full[slot], (phases >> slot) & 1u);
+    phases ^= 1u << slot;
+    const unsigned char* wrow = ring + static_cast<size_t>(slot) * 16 * wstride;
+    float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      unsigned long long k = best[i][e];
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int kb = 0; kb < kbw; ++kb) {
+      const int kbyte = ((gwarp * kbw + kb) * 32 + t * 8) * 2;
+      const uint4 ra = *reinterpret_cast<const uint4*>(wrow + static_cast<size_t>(g) * wstride + kbyte);
+      const uint4 rb = *reinterpret_cast<const uint4*>(wrow + static_cast<size_t>(g + 8) * wstride + kbyte);
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
-        k = other > k ? other : k;
+      for (int i = 0; i < 4; ++i) {
+        if (i < p.ng) {
+          const uint4 xb = *reinterpret_cast<const uint4*>(Xs + static_cast<size_t>(i * 8 + g) * stride + kbyte);
+          mma_bf16(acc[i], ra.x, rb.x, ra.y, rb.y, xb.x, xb.y);
+          mma_bf16(acc[i], ra.z, rb.z, ra.w, rb.w, xb.z, xb.w);
+        }
       }
-      const int n = i * 8 + t * 2 + e;
-      if (g == 0) s_keys[warp * 32 + n] = k;
     }
+    float* my = gred + gwarp * DS_RED;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = i * 8 + t * 2;
+      my[g * 32 + (n ^ g)] = acc[i][0];
+      my[g * 32 + ((n + 1) ^ g)] = acc[i][1];
+      my[(g + 8) * 32 + (n ^ (g + 8))] = acc[i][2];
+      my[(g + 8) * 32 + ((n + 1) ^ (g + 8))] = acc[i][3];
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");  // slot consumed by all 8 warps, partials in smem
+    issue(u + DS_RING * ustep, slot);                                 // refill it while the epilogue runs
+    {
+      const int n = tig >> 3, r = (tig & 7) * 2;  // token n, features r, r + 1
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        v0 += gred[w * DS_RED + r * 32 + (n ^ r)];
+        v1 += gred[w * DS_RED + (r + 1) * 32 + (n ^ (r + 1))];
+      }
+      const int fa = u * 16 + r, fb = fa + 1;
+      unsigned long long key = 0ull;
+      if (n < p.B) {
+        // bias, then the rounding of the model dtype (what the logits tensor of a bf16 model holds)
+        if (fa < N) {
+          const bf16 la = __float2bfloat16_rn(v0 + (p.b_v ? __bfloat162float(p.b_v[fa]) : 0.f));
+          key = (static_cast<unsigned long long>(ds_order_bits(__bfloat162float(la))) << 32) | (0xffffffffu - static_cast<unsigned int>(fa));
+          if (p.logits) reinterpret_cast<bf16*>(p.logits)[static_cast<size_t>(n) * p.ld_logits + fa] = la;
+        }
+        if (fb < N) {
+          const bf16 lb = __float2bfloat16_rn(v1 + (p.b_v ? __bfloat162float(p.b_v[fb]) : 0.f));
+          const unsigned long long kb2 = (static_cast<unsigned long long>(ds_order_bits(__bfloat162float(lb))) << 32) | (0xffffffffu - static_cast<unsigned int>(fb));
+          key = kb2 > key ? kb2 : key;
+          if (p.logits) reinterpret_cast<bf16*>(p.logits)[static_cast<size_t>(n) * p.ld_logits + fb] = lb;
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {  // the 8 threads of a token
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      best = key > best ? key : best;
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");  // gred free for the next unit
+    slot = slot + 1 == DS_RING ? 0 : slot + 1;
+  }
+  if ((tig & 7) == 0) s_keys[group * 32 + (tig >> 3)] = best;
   __syncthreads();
   if (threadIdx.x < p.B) {  // one atomic per token and CTA
-    unsigned long long k = 0ull;
-#pragma unroll
-    for (int w = 0; w < DS_WARPS; ++w) {
-      const unsigned long long o = s_keys[w * 32 + threadIdx.x];
-      k = o > k ? o : k;
-    }
+    const unsigned long long a0 = s_keys[threadIdx.x], a1 = s_keys[32 + threadIdx.x];
+    const unsigned long long k = a0 > a1 ? a0 : a1;
     if (k != 0ull) atomicMax(&p.amax[threadIdx.x], k);
   }
 }
 
-// ---- attention over the cache: one work item = (kv-split, kv head, batch row), all 8 warps of the CTA ----
+// ---- attention over the cache: one work item = (kv-split, kv head, batch row) per WARP ----
+// A decode step has B * h_kv rows of work and 8 warps on each of 148 SMs: the context of every (row, kv head) is split so
+// that there is about one item per warp of the grid, every warp runs its item without any CTA-wide synchronisation (the
+// latency chain of an item — projections from L2, RoPE, cache rows, merge — is paid once per stage, not once per item
+// and CTA), and the last warp to finish a (row, kv head) combines the splits (ticket in global memory).
+__device__ __forceinline__ void attn_item_coords(const DsParams& p, int it, int sp, int& split, int& kvh, int& b, int& k_begin, int& k_end) {
+  split = it % p.splits;
+  kvh = (it / p.splits) % p.Hkv;
+  b = it / (p.splits * p.Hkv);
+  const int per = (sp + p.splits - 1) / p.splits;
+  k_begin = split * per;
+  k_end = min(sp, k_begin + per);
+}
+
 template <int NREP>
 __device__ void attention_items(const DsParams& p, const DsLayer& ly, int sp, unsigned char* smem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = lane & 7, lk = lane >> 3;
-  float* s_newk = reinterpret_cast<float*>(smem);             // [64]
-  float* s_newv = s_newk + DS_HD;                              // [64]
-  float* s_q = s_newv + DS_HD;                                 // [NREP][64]
-  float* s_red = s_q + 8 * DS_HD;                              // [8 warps][NREP][66]
-  unsigned int* s_last = reinterpret_cast<unsigned int*>(s_red + DS_WARPS * 8 * (DS_HD + 2));
+  float* wq = reinterpret_cast<float*>(smem) + warp * (10 * DS_HD);  // [NREP <= 8][64] q, then new k [64], new v [64]
+  float* s_newk = wq + 8 * DS_HD;
+  float* s_newv = s_newk + DS_HD;
   const float scale_log2 = 1.4426950408889634f / 8.0f;
   const int items = p.B * p.Hkv * p.splits;
-  for (int it = blockIdx.x; it < items; it += gridDim.x) {
-    const int split = it % p.splits, kvh = (it / p.splits) % p.Hkv, b = it / (p.splits * p.Hkv);
-    // new token: projections (bias already added) -> RoPE(q, k) -> smem; the last split appends k, v to the cache
+  const int nw = gridDim.x * DS_WARPS;
+  for (int it = blockIdx.x * DS_WARPS + warp; it < items; it += nw) {
+    int split, kvh, b, k_begin, k_end;
+    attn_item_coords(p, it, sp, split, kvh, b, k_begin, k_end);
+    // new token: projections (bias already added) -> RoPE(q, k) -> this warp's smem; lane j owns dims j and j + 32
     const float* row = p.qkv + static_cast<size_t>(b) * p.NQKV;
-    for (int idx = threadIdx.x; idx < (NREP + 2) * DS_HD; idx += DS_THREADS) {
-      const int which = idx / DS_HD, j = idx % DS_HD;
-      int col;
-      if (which < NREP) col = (kvh * NREP + which) * DS_HD;
-      else if (which == NREP) col = (p.Hq + kvh) * DS_HD;
-      else col = (p.Hq + p.Hkv + kvh) * DS_HD;
-      // the reference's bf16 model holds q / k / v as bf16 tensors before the rotation: same rounding point
-      float x = __bfloat162float(__float2bfloat16_rn(__ldcg(row + col + j)));
-      if (which <= NREP && p.rope_cos) {
-        const float other = __bfloat162float(__float2bfloat16_rn(__ldcg(row + col + (j < 32 ? j + 32 : j - 32))));
-        const float c = p.rope_cos[sp * 32 + (j & 31)], s = p.rope_sin[sp * 32 + (j & 31)];
-        x = j < 32 ? x * c - other * s : x * c + other * s;
+    {
+      float lo[NREP + 2], hi[NREP + 2];
+      float c = 1.f, sn = 0.f;
+      if (p.rope_cos) {
+        c = p.rope_cos[sp * 32 + lane];
+        sn = p.rope_sin[sp * 32 + lane];
       }
-      if (which < NREP) s_q[which * DS_HD + j] = x;
-      else if (which == NREP) s_newk[j] = x;
-      else s_newv[j] = x;
+#pragma unroll
+      for (int h = 0; h < NREP + 2; ++h) {
+        const int col = h < NREP ? (kvh * NREP + h) * DS_HD : (h == NREP ? (p.Hq + kvh) * DS_HD : (p.Hq + p.Hkv + kvh) * DS_HD);
+        lo[h] = __ldcg(row + col + lane);
+        hi[h] = __ldcg(row + col + lane + 32);
+      }
+#pragma unroll
+      for (int h = 0; h < NREP + 2; ++h) {
+        // the reference's bf16 model holds q / k / v as bf16 tensors before the rotation: same rounding point
+        const float x0 = __bfloat162float(__float2bfloat16_rn(lo[h])), x1 = __bfloat162float(__float2bfloat16_rn(hi[h]));
+        float* dst = h < NREP ? wq + h * DS_HD : (h == NREP ? s_newk : s_newv);
+        if (h <= NREP && p.rope_cos) {
+          dst[lane] = x0 * c - x1 * sn;
+          dst[lane + 32] = x1 * c + x0 * sn;
+        } else {
+          dst[lane] = x0;
+          dst[lane + 32] = x1;
+        }
+      }
     }
-    __syncthreads();
+    __syncwarp();
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[128 + 16] = static_cast<long long>(globaltimer_ns());
     bf16* kc = ly.k_cache + b * p.c_sb + kvh * p.c_sh;
     bf16* vc = ly.v_cache + b * p.c_sb + kvh * p.c_sh;
-    if (split == p.splits - 1 && threadIdx.x < DS_HD) {
-      kc[sp * p.c_sl + threadIdx.x] = __float2bfloat16_rn(s_newk[threadIdx.x]);
-      vc[sp * p.c_sl + threadIdx.x] = __float2bfloat16_rn(s_newv[threadIdx.x]);
+    if (split == p.splits - 1) {  // the cache stores what the reference stores: rotated k, raw v, in the cache dtype
+      kc[sp * p.c_sl + lane] = __float2bfloat16_rn(s_newk[lane]);
+      kc[sp * p.c_sl + lane + 32] = __float2bfloat16_rn(s_newk[lane + 32]);
+      vc[sp * p.c_sl + lane] = __float2bfloat16_rn(s_newv[lane]);
+      vc[sp * p.c_sl + lane + 32] = __float2bfloat16_rn(s_newv[lane + 32]);
     }
     float q[NREP][8];
 #pragma unroll
     for (int r = 0; r < NREP; ++r)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[r][j] = s_q[r * DS_HD + ld * 8 + j] * scale_log2;
+      for (int j = 0; j < 8; ++j) q[r][j] = wq[r * DS_HD + ld * 8 + j] * scale_log2;
     float m[NREP], l[NREP], o[NREP][8];
 #pragma unroll
     for (int r = 0; r < NREP; ++r) {
@@ -515,44 +668,36 @@ __device__ void attention_items(const DsParams& p, const DsLayer& ly, int sp, un
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[r][j] = 0.f;
     }
-    const int per = (sp + p.splits - 1) / p.splits;
-    const int k_begin = split * per;
-    const int k_end = min(sp, k_begin + per);
-    constexpr int UN = 4;
-    constexpr int KEYS_PER_ITER = DS_WARPS * 4 * UN;
-    for (int k0 = k_begin; k0 < k_end; k0 += KEYS_PER_ITER) {
+    constexpr int UN = 4;  // 4 keys per warp and load step; UN steps in flight
+    for (int k0 = k_begin; k0 < k_end; k0 += 4 * UN) {
       uint4 kraw[UN], vraw[UN];
-      int kidx[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        kidx[u] = k0 + (u * DS_WARPS + warp) * 4 + lk;
-        if (kidx[u] < k_end) {
-          const long long off = kidx[u] * p.c_sl + ld * 8;
+        const int ki = k0 + u * 4 + lk;
+        kraw[u] = vraw[u] = make_uint4(0, 0, 0, 0);
+        if (ki < k_end) {
+          const long long off = ki * p.c_sl + ld * 8;
           kraw[u] = ldg_stream(kc + off);
           vraw[u] = ldg_stream(vc + off);
         }
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const bool valid = kidx[u] < k_end;
+        const bool valid = k0 + u * 4 + lk < k_end;
         float kv[8], vv[8];
-        {
-          const __nv_bfloat162* hk = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
-          const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
+        const __nv_bfloat162* hk = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
+        const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 a = __bfloat1622float2(hk[j]), c = __bfloat1622float2(hv[j]);
-            kv[2 * j] = a.x; kv[2 * j + 1] = a.y;
-            vv[2 * j] = c.x; vv[2 * j + 1] = c.y;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __bfloat1622float2(hk[j]), cc = __bfloat1622float2(hv[j]);
+          kv[2 * j] = a.x; kv[2 * j + 1] = a.y;
+          vv[2 * j] = cc.x; vv[2 * j + 1] = cc.y;
         }
 #pragma unroll
         for (int r = 0; r < NREP; ++r) {
           float s = 0.f;
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s += q[r][j] * kv[j];
-          }
+          for (int j = 0; j < 8; ++j) s += q[r][j] * kv[j];
           s += __shfl_xor_sync(0xffffffffu, s, 1);
           s += __shfl_xor_sync(0xffffffffu, s, 2);
           s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -568,7 +713,8 @@ __device__ void attention_items(const DsParams& p, const DsLayer& ly, int sp, un
         }
       }
     }
-    if (split == p.splits - 1 && warp == 0 && lk == 0) {  // the new token, from smem (unrounded, like the eager kernel)
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[128 + 17] = static_cast<long long>(globaltimer_ns());
+    if (split == p.splits - 1 && lk == 0) {  // the new token, from smem (unrounded, like the per-op kernel)
 #pragma unroll
       for (int r = 0; r < NREP; ++r) {
         float s = 0.f;
@@ -586,7 +732,7 @@ __device__ void attention_items(const DsParams& p, const DsLayer& ly, int sp, un
         m[r] = mn;
       }
     }
-    // merge lane groups (xor 8, 16), then warps through smem
+    // merge the 4 key lane groups (xor 8, 16): afterwards every lane holds the item's (m, l, o[ld * 8 ..])
 #pragma unroll
     for (int r = 0; r < NREP; ++r) {
 #pragma unroll
@@ -604,133 +750,193 @@ __device__ void attention_items(const DsParams& p, const DsLayer& ly, int sp, un
         }
         m[r] = mn;
       }
+    }
+    bf16* orow = p.attn + static_cast<size_t>(b) * (p.Hq * DS_HD) + kvh * NREP * DS_HD;
+    if (p.splits == 1) {
       if (lk == 0) {
-        float* dst = s_red + (warp * 8 + r) * (DS_HD + 2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[ld * 8 + j] = o[r][j];
-        if (ld == 0) {
-          dst[DS_HD] = m[r];
-          dst[DS_HD + 1] = l[r];
+        for (int r = 0; r < NREP; ++r) {
+          uint4 w;
+          __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(&w);
+          const float inv = 1.f / l[r];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w2[j] = __floats2bfloat162_rn(o[r][2 * j] * inv, o[r][2 * j + 1] * inv);
+          *reinterpret_cast<uint4*>(orow + r * DS_HD + ld * 8) = w;
         }
       }
+      continue;
     }
-    __syncthreads();
-    const int tdx = threadIdx.x;
-    const int r_own = tdx / DS_HD, j_own = tdx % DS_HD;
-    for (int rr = r_own; rr < NREP; rr += DS_THREADS / DS_HD) {
-      float M = -INFINITY, Lsum = 0.f, O = 0.f;
+    float* part = p.part + (((static_cast<size_t>(b) * p.Hkv + kvh) * p.splits + split) * NREP) * (DS_HD + 2);
+    if (lk == 0) {
 #pragma unroll
-      for (int w = 0; w < DS_WARPS; ++w) {
-        const float* src = s_red + (w * 8 + rr) * (DS_HD + 2);
-        const float mw = src[DS_HD], lw = src[DS_HD + 1], ow = src[j_own];
-        if (mw == -INFINITY) continue;
-        const float mn = fmaxf(M, mw);
-        const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
-        const float a2 = exp2f(mw - mn);
-        Lsum = Lsum * a1 + lw * a2;
-        O = O * a1 + ow * a2;
-        M = mn;
-      }
-      if (p.splits == 1) {
-        p.attn[static_cast<size_t>(b) * (p.Hq * DS_HD) + (kvh * NREP + rr) * DS_HD + j_own] = __float2bfloat16_rn(O / Lsum);
-      } else {
-        float* w = p.part + ((((static_cast<size_t>(b) * p.Hkv + kvh) * p.splits + split) * NREP + rr) * (DS_HD + 2));
-        w[j_own] = O;
-        if (j_own == 0) {
-          w[DS_HD] = M;
-          w[DS_HD + 1] = Lsum;
-        }
+      for (int r = 0; r < NREP; ++r) {
+        float* w = part + r * (DS_HD + 2);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2*>(w + ld * 8 + j) = make_float2(o[r][j], o[r][j + 1]);
+        if (ld == 0) *reinterpret_cast<float2*>(w + DS_HD) = make_float2(m[r], l[r]);
       }
     }
-    if (p.splits > 1) {  // last CTA of this (row, kv head) combines the splits
-      __threadfence();
-      __syncthreads();
-      if (tdx == 0) {
-        const unsigned int prev = atomicAdd(&p.tickets[b * p.Hkv + kvh], 1u);
-        *s_last = (prev == static_cast<unsigned int>(p.splits - 1)) ? 1u : 0u;
-        if (*s_last) p.tickets[b * p.Hkv + kvh] = 0u;
-      }
-      __syncthreads();
-      if (*s_last) {
-        __threadfence();
-        for (int rr = r_own; rr < NREP; rr += DS_THREADS / DS_HD) {
-          float M = -INFINITY, Lsum = 0.f, O = 0.f;
-          for (int si = 0; si < p.splits; ++si) {
-            const float* w = p.part + ((((static_cast<size_t>(b) * p.Hkv + kvh) * p.splits + si) * NREP + rr) * (DS_HD + 2));
-            const float mw = __ldcg(w + DS_HD), lw = __ldcg(w + DS_HD + 1), ow = __ldcg(w + j_own);
-            if (mw == -INFINITY) continue;
-            const float mn = fmaxf(M, mw);
-            const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
-            const float a2 = exp2f(mw - mn);
-            Lsum = Lsum * a1 + lw * a2;
-            O = O * a1 + ow * a2;
-            M = mn;
+    // the last warp of this (row, kv head) combines the splits
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[128 + 18] = static_cast<long long>(globaltimer_ns());
+    __threadfence();
+    __syncwarp();
+    unsigned int last = 0;
+    if (lane == 0) {
+      const unsigned int prev = atomicAdd(&p.tickets[b * p.Hkv + kvh], 1u);
+      last = prev == static_cast<unsigned int>(p.splits - 1) ? 1u : 0u;
+      if (last) p.tickets[b * p.Hkv + kvh] = 0u;  // self-reset for the next stage / launch
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) continue;
+    __threadfence();
+    const float* base = p.part + ((static_cast<size_t>(b) * p.Hkv + kvh) * p.splits) * NREP * (DS_HD + 2);
+    // lane s < splits fetches split s's (m, l) of every head at once; the weights exp2(m_s - M) / L then ride on shuffles
+    // while every lane accumulates its two output dims over the splits, four splits' loads in flight at a time
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      float2 ml = make_float2(-INFINITY, 0.f);
+      if (lane < p.splits) ml = __ldcg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(lane) * NREP + r) * (DS_HD + 2) + DS_HD));
+      float M = ml.x;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+      const float wgt = ml.x == -INFINITY ? 0.f : exp2f(ml.x - M);
+      float Ls = ml.y * wgt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) Ls += __shfl_xor_sync(0xffffffffu, Ls, o);
+      float O0 = 0.f, O1 = 0.f;
+      for (int s0 = 0; s0 < p.splits; s0 += 4) {
+        float2 ov[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ov[j] = make_float2(0.f, 0.f);
+          if (s0 + j < p.splits) ov[j] = __ldcg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(s0 + j) * NREP + r) * (DS_HD + 2) + 2 * lane));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float ws = __shfl_sync(0xffffffffu, wgt, (s0 + j) & 31);
+          if (s0 + j < p.splits) {
+            O0 += ov[j].x * ws;
+            O1 += ov[j].y * ws;
           }
-          p.attn[static_cast<size_t>(b) * (p.Hq * DS_HD) + (kvh * NREP + rr) * DS_HD + j_own] = __float2bfloat16_rn(O / Lsum);
         }
       }
+      const float inv = 1.f / Ls;
+      *reinterpret_cast<__nv_bfloat162*>(orow + r * DS_HD + 2 * lane) = __floats2bfloat162_rn(O0 * inv, O1 * inv);
     }
-    __syncthreads();  // smem is reused by the next item
   }
+}
+
+// One layer's HBM bytes (projection / MLP weights and the cached keys / values up to `pos`) -> L2, shared out over the grid
+__device__ __noinline__ void prefetch_layer(const DsParams& p, const DsLayer& ly, int pos) {
+  const int part = blockIdx.x, nparts = gridDim.x;
+  prefetch_range_l2(ly.w_qkv, static_cast<long long>(p.NQKV) * p.H * 2, part, nparts);
+  prefetch_range_l2(ly.w_o, static_cast<long long>(p.H) * p.H * 2, part, nparts);
+  prefetch_range_l2(ly.w_1, static_cast<long long>(p.FF) * p.H * 2, part, nparts);
+  prefetch_range_l2(ly.w_2, static_cast<long long>(p.FF) * p.H * 2, part, nparts);
+  // cache: (row, kv head) r holds slots [0, pos) contiguously when the slot stride is the head dim
+  if (p.c_sl == DS_HD && pos > 0) {
+    const int ranges = p.B * p.Hkv;
+    for (int r = blockIdx.x; r < ranges; r += gridDim.x) {
+      const long long off = static_cast<long long>(r / p.Hkv) * p.c_sb + static_cast<long long>(r % p.Hkv) * p.c_sh;
+      prefetch_range_l2(ly.k_cache + off, static_cast<long long>(pos) * DS_HD * 2, 0, 1);
+      prefetch_range_l2(ly.v_cache + off, static_cast<long long>(pos) * DS_HD * 2, 0, 1);
+    }
+  }
+}
+// part `which` of `of` of the vocabulary projection's weight
+__device__ __forceinline__ void prefetch_vocab(const DsParams& p, int which, int of) {
+  const long long bytes = static_cast<long long>(p.V) * p.H * 2;
+  const long long piece = ((bytes / of) + 127) & ~127ll;
+  const long long lo = piece * which;
+  if (lo >= bytes) return;
+  prefetch_range_l2(reinterpret_cast<const char*>(p.w_v) + lo, (lo + piece < bytes ? piece : bytes - lo), blockIdx.x, gridDim.x);
 }
 
 template <int NREP>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 decode_step_kernel(const __grid_constant__ DsParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const int Kmax = p.FF > p.H ? p.FF : p.H;
   unsigned char* Xs = smem;
   float* red = reinterpret_cast<float*>(smem + static_cast<size_t>(32) * xs_stride(Kmax));
+  // behind the reduction tiles: 512 B of argmax keys, then the mbarriers — [0]: stage prologue fill; [1..6]: vocabulary ring (2 groups x 3 slots)
+  unsigned long long* s_bars = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(red) + DS_WARPS * DS_RED * sizeof(float) + 512);
   const int pos = *p.pos;  // read before anything can change it (FIN runs after the last barrier)
   int bar = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && p.trace) p.trace[0] = static_cast<long long>(globaltimer_ns());
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.bar[5 * p.L + 1] = 0u;  // the previous launch's last barrier (5 L + 2 per launch)
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && p.trace) p.trace[0] = static_cast<long long>(globaltimer_ns());
+    if (blockIdx.x == 0) p.bar[5 * p.L + 1] = 0u;  // the previous launch's last barrier (5 L + 2 per launch)
+#pragma unroll
+    for (int i = 0; i < 1 + 2 * DS_RING; ++i) mbar_init(reinterpret_cast<uint64_t*>(&s_bars[i]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (blockIdx.x == gridDim.x - 1) {  // biases and LayerNorm vectors: a few KB each, first touched deep inside latency chains
+    for (int l = 0; l < p.L; ++l) {
+      const DsLayer& ly = p.layer[l];
+      const bf16* v[8] = {ly.b_qkv, ly.b_o, ly.ln1_g, ly.ln1_b, ly.b_1, ly.b_2, ly.ln2_g, ly.ln2_b};
+      const int n[8] = {p.NQKV, p.H, p.H, p.H, p.FF, p.H, p.H, p.H};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (v[i]) prefetch_range_l2(v[i], static_cast<long long>(n[i]) * 2, 0, 1);
+    }
+    if (p.b_d) prefetch_range_l2(p.b_d, static_cast<long long>(p.H) * 2, 0, 1);
+    prefetch_range_l2(p.lnh_g, static_cast<long long>(p.H) * 2, 0, 1);
+    prefetch_range_l2(p.lnh_b, static_cast<long long>(p.H) * 2, 0, 1);
+    if (p.b_v) prefetch_range_l2(p.b_v, static_cast<long long>(p.V) * 2, 0, 1);
+  }
+  unsigned int fill_phase = 0;
   const int qcols = p.Hq * DS_HD;
+  StageIn in;
+  const PostLN no_ln = {nullptr, nullptr, nullptr, 0.f, nullptr, nullptr};
+  PostLN ln;
 
   for (int l = 0; l < p.L; ++l) {
     const DsLayer& ly = p.layer[l];
-    // QKV
-    const int cta = static_cast<int>(blockIdx.x);  // CTAs that own no unit of a stage skip its prologue
-    if (cta < (p.NQKV + 15) / 16) {
-      if (l == 0) fill_embedding(p, Xs, pos);
-      else fill_layernorm(p, Xs, p.s2, p.layer[l - 1].ln2_g, p.layer[l - 1].ln2_b, p.eps_layer, p.xbuf);
+    // HBM -> L2 a layer ahead: the next layer's weights and cache rows; the vocabulary weight in two halves over the last two
+    // layers (L2 holds 126 MB: the layer in use, the one being fetched and the head's 77 MB must not all be live at once)
+    if (l + 1 < p.L) prefetch_layer(p, p.layer[l + 1], pos);
+    if (l == p.L - 2 || p.L == 1) prefetch_vocab(p, 0, 2);
+    if (l == p.L - 1) {
+      prefetch_vocab(p, 1, 2);
+      if (p.L == 1) prefetch_vocab(p, 0, 2);
+      prefetch_range_l2(p.w_d, static_cast<long long>(p.H) * p.H * 2, blockIdx.x, gridDim.x);
     }
-    __syncthreads();
-    gemm_ksplit_dispatch(p, p.H, Xs, red, ly.w_qkv, ly.b_qkv, p.NQKV, DS_EPI_F32, p.qkv, p.NQKV, nullptr);
+    // QKV: x = the tokens' embedding rows (layer 0) or LN2 of the previous layer's sum (written to xbuf by the last CTA of
+    // its FFN2 stage). While it runs, L2 pulls in the cache rows of the attention stage and the output projection's weights.
+    // The copy engine of an SM serves its requests in order: an L2 prefetch queued BEFORE a stage's activation copies makes
+    // them wait for the prefetch's DRAM fetch — so prefetches are issued after the stage's own work, ahead of the barrier.
+    in = l == 0 ? StageIn{DS_IN_EMBED, nullptr, p.xbuf} : StageIn{DS_IN_COPY, p.xbuf, nullptr};
+    stage_gemm(p, p.H, in, Xs, red, &s_bars[0], fill_phase, ly.w_qkv, ly.b_qkv, p.NQKV, DS_EPI_F32, p.qkv, p.NQKV, nullptr, no_ln, l == 1 ? 0 : -1);
+    ds_mark(p, l == 1 ? 3 : -1);
     grid_barrier(p, bar++);
     // ATTN
     attention_items<NREP>(p, ly, pos, smem);
     grid_barrier(p, bar++);
-    // OUT: s1 = attn Wo^T + bo + x
-    if (cta < (p.H + 15) / 16) fill_copy(p, Xs, p.attn, qcols);
-    __syncthreads();
-    gemm_ksplit_dispatch(p, qcols, Xs, red, ly.w_o, ly.b_o, p.H, DS_EPI_F32_RESID, p.s1, p.H, p.xbuf);
+    // OUT: s1 = attn Wo^T + bo + x; its last CTA writes y = LN1(s1)
+    in = StageIn{DS_IN_COPY, p.attn, nullptr};
+    ln = PostLN{p.s1, ly.ln1_g, ly.ln1_b, p.eps_layer, p.ybuf, p.ln_ticket};
+    stage_gemm(p, qcols, in, Xs, red, &s_bars[0], fill_phase, ly.w_o, ly.b_o, p.H, DS_EPI_F32_RESID, p.s1, p.H, p.xbuf, ln);
     grid_barrier(p, bar++);
-    // FFN1: a = gelu(LN1(s1) W1^T + b1)
-    if (cta < (p.FF + 15) / 16) fill_layernorm(p, Xs, p.s1, ly.ln1_g, ly.ln1_b, p.eps_layer, nullptr);
-    __syncthreads();
-    gemm_ksplit_dispatch(p, p.H, Xs, red, ly.w_1, ly.b_1, p.FF, DS_EPI_GELU_BF16, p.abuf, p.FF, nullptr);
+    // FFN1: a = gelu(y W1^T + b1)
+    in = StageIn{DS_IN_COPY, p.ybuf, nullptr};
+    stage_gemm(p, p.H, in, Xs, red, &s_bars[0], fill_phase, ly.w_1, ly.b_1, p.FF, DS_EPI_GELU_BF16, p.abuf, p.FF, nullptr, no_ln);
     grid_barrier(p, bar++);
-    // FFN2: s2 = a W2^T + b2 + x   (the residual is the layer INPUT: quirk Q2)
-    if (cta < (p.H + 15) / 16) fill_copy(p, Xs, p.abuf, p.FF);
-    __syncthreads();
-    gemm_ksplit_dispatch(p, p.FF, Xs, red, ly.w_2, ly.b_2, p.H, DS_EPI_F32_RESID, p.s2, p.H, p.xbuf);
+    // FFN2: s2 = a W2^T + b2 + x (the residual is the layer INPUT: quirk Q2); its last CTA writes the next x = LN2(s2)
+    in = StageIn{DS_IN_COPY, p.abuf, nullptr};
+    ln = PostLN{p.s2, ly.ln2_g, ly.ln2_b, p.eps_layer, p.xbuf, p.ln_ticket};
+    stage_gemm(p, p.FF, in, Xs, red, &s_bars[0], fill_phase, ly.w_2, ly.b_2, p.H, DS_EPI_F32_RESID, p.s2, p.H, p.xbuf, ln, l == 1 ? 8 : -1);
+    ds_mark(p, l == 1 ? 11 : -1);
     grid_barrier(p, bar++);
   }
-  // LM head: g = gelu(x Wd^T + bd), x = LN2(s2) of the last layer
-  if (static_cast<int>(blockIdx.x) < (p.H + 15) / 16) fill_layernorm(p, Xs, p.s2, p.layer[p.L - 1].ln2_g, p.layer[p.L - 1].ln2_b, p.eps_layer, nullptr);
-  __syncthreads();
-  gemm_ksplit_dispatch(p, p.H, Xs, red, p.w_d, p.b_d, p.H, DS_EPI_GELU_F32, p.gbuf, p.H, nullptr);
+  // LM head: g = gelu(x Wd^T + bd); the last CTA writes y = LN(g)
+  in = StageIn{DS_IN_COPY, p.xbuf, nullptr};
+  ln = PostLN{p.gbuf, p.lnh_g, p.lnh_b, p.eps_head, p.ybuf, p.ln_ticket};
+  stage_gemm(p, p.H, in, Xs, red, &s_bars[0], fill_phase, p.w_d, p.b_d, p.H, DS_EPI_GELU_F32, p.gbuf, p.H, nullptr, ln);
   grid_barrier(p, bar++);
-  // logits = LN(g) Wv^T + bv -> argmax
-  fill_layernorm(p, Xs, p.gbuf, p.lnh_g, p.lnh_b, p.eps_head, nullptr);
-  __syncthreads();
-  switch (p.H >> 5) {
-    case 8: lm_head_argmax<8>(p, Xs, reinterpret_cast<unsigned long long*>(red)); break;
-    case 16: lm_head_argmax<16>(p, Xs, reinterpret_cast<unsigned long long*>(red)); break;
-    case 24: lm_head_argmax<24>(p, Xs, reinterpret_cast<unsigned long long*>(red)); break;
-    default: lm_head_argmax<32>(p, Xs, reinterpret_cast<unsigned long long*>(red)); break;
-  }
+  // logits = y Wv^T + bv -> argmax; meanwhile L2 takes in layer 0's bytes for the NEXT step (its cache now reaches slot pos)
+  prefetch_layer(p, p.layer[0], pos + 1);
+  lm_head_argmax(p, p.ybuf, Xs, red, s_bars, fill_phase);
   grid_barrier(p, bar++);
   // FIN: next token = unpacked argmax; it is the input of the next step and lands in tokens[:, pos + 1]
   if (blockIdx.x == 0) {
@@ -748,7 +954,7 @@ decode_step_kernel(const __grid_constant__ DsParams p) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct DsScratch {
-  size_t xbuf, qkv, attn, s1, abuf, s2, gbuf, part, tickets, amax, bar, abort_flag, total;
+  size_t xbuf, ybuf, ln_ticket, qkv, attn, s1, abuf, s2, gbuf, part, tickets, amax, bar, abort_flag, total;
 };
 static DsScratch scratch_layout(int B, int H, int Hq, int Hkv, int FF, int splits) {
   DsScratch s;
@@ -759,7 +965,9 @@ static DsScratch scratch_layout(int B, int H, int Hq, int Hkv, int FF, int split
   s.abort_flag = take(sizeof(int));
   s.tickets = take(sizeof(unsigned int) * B * Hkv);
   s.amax = take(sizeof(unsigned long long) * DS_MAXB);
+  s.ln_ticket = take(sizeof(unsigned int));
   s.xbuf = take(sizeof(bf16) * B * H);
+  s.ybuf = take(sizeof(bf16) * B * H);
   s.qkv = take(sizeof(float) * B * (Hq + 2 * Hkv) * DS_HD);
   s.attn = take(sizeof(bf16) * B * Hq * DS_HD);
   s.s1 = take(sizeof(float) * B * H);
@@ -803,9 +1011,12 @@ extern "C" int vy_decode_step(const VyDecodeStep* q) {
   VY_CHECK_ARG(H % 256 == 0 && H <= 1024 && FF % 256 == 0 && FF <= 4096, "vy_decode_step: H (%d) and ffn (%d) must be multiples of 256, H <= 1024, ffn <= 4096", H, FF);
   {
     const int hb = H >> 8, fb = FF >> 8;
-    auto okk = [](int kb) { return kb == 1 || kb == 2 || kb == 3 || kb == 4 || kb == 8 || kb == 12 || kb == 16; };
-    VY_CHECK_ARG(okk(hb) && okk(fb), "vy_decode_step: unsupported H / ffn (%d / %d)", H, FF);
+    VY_CHECK_ARG(hb >= 1 && hb <= 4 && fb >= 1 && fb <= 16, "vy_decode_step: unsupported H / ffn (%d / %d)", H, FF);
   }
+  // the vocabulary stage keeps its weight ring (2 groups x 3 slots x 16 rows x H bf16) behind the bf16 activation rows
+  VY_CHECK_ARG(static_cast<size_t>(32) * (FF * 2 + 64) >= ((static_cast<size_t>(32) * (H * 2 + 64) + 1023) / 1024) * 1024 + static_cast<size_t>(2 * DS_RING * 16) * H * 2,
+               "vy_decode_step: ffn (%d) too small for the shared-memory plan of H = %d (needs ffn >= 4 H)", FF, H);
+  VY_CHECK_ARG(q->pos_table == nullptr, "vy_decode_step: learned / sinusoidal position tables are not built into the one-launch step (RoPE models only)");
   VY_CHECK_ARG(L >= 1 && L <= VY_DECODE_MAX_LAYERS, "vy_decode_step: n_layers %d outside [1, %d]", L, VY_DECODE_MAX_LAYERS);
   VY_CHECK_ARG(q->vocab > 0 && q->emb && q->w_d && q->ln_head_g && q->ln_head_b && q->w_v && q->pos && q->tok && q->workspace,
                "vy_decode_step: null pointer");
@@ -819,8 +1030,8 @@ extern "C" int vy_decode_step(const VyDecodeStep* q) {
   VY_CHECK_ARG(nrep == 1 || nrep == 2 || nrep == 3 || nrep == 4 || nrep == 6 || nrep == 8, "vy_decode_step: unsupported q-heads per kv-head %d", nrep);
 
   const int sms = num_sms();
-  int splits = (2 * sms + B * Hkv - 1) / (B * Hkv);
-  const int by_len = (q->pos_bound + 63) / 64;
+  int splits = (sms * DS_WARPS) / (B * Hkv);  // about one attention item per warp of the grid
+  const int by_len = (q->pos_bound + 31) / 32;
   if (splits > by_len) splits = by_len;
   if (splits < 1) splits = 1;
   if (splits > DS_MAX_SPLITS) splits = DS_MAX_SPLITS;
@@ -847,6 +1058,8 @@ extern "C" int vy_decode_step(const VyDecodeStep* q) {
   p.logits = q->logits; p.ld_logits = q->ld_logits;
   unsigned char* ws = static_cast<unsigned char*>(q->workspace);
   p.xbuf = reinterpret_cast<bf16*>(ws + sc.xbuf);
+  p.ybuf = reinterpret_cast<bf16*>(ws + sc.ybuf);
+  p.ln_ticket = reinterpret_cast<unsigned int*>(ws + sc.ln_ticket);
   p.qkv = reinterpret_cast<float*>(ws + sc.qkv);
   p.attn = reinterpret_cast<bf16*>(ws + sc.attn);
   p.s1 = reinterpret_cast<float*>(ws + sc.s1);
@@ -875,8 +1088,9 @@ extern "C" int vy_decode_step(const VyDecodeStep* q) {
     d.k_cache = static_cast<bf16*>(s.k_cache); d.v_cache = static_cast<bf16*>(s.v_cache);
   }
   const int Kmax = FF > H ? FF : H;
-  const size_t smem = static_cast<size_t>(32) * (Kmax * 2 + 64) + DS_WARPS * DS_RED * sizeof(float);
-  const size_t attn_smem = (2 * DS_HD + 8 * DS_HD + DS_WARPS * 8 * (DS_HD + 2)) * sizeof(float) + 16;
+  const size_t smem = static_cast<size_t>(32) * (Kmax * 2 + 64) + DS_WARPS * DS_RED * sizeof(float) + 1024;  // rows | reduction tiles | argmax keys + mbarriers
+  VY_CHECK_ARG(smem <= 232448, "vy_decode_step: shared-memory plan (%zu bytes) exceeds the 227 KB of an SM", smem);
+  const size_t attn_smem = static_cast<size_t>(DS_WARPS) * 10 * DS_HD * sizeof(float);
   VY_CHECK_ARG(attn_smem <= smem, "vy_decode_step: internal smem layout");
   cudaStream_t st = static_cast<cudaStream_t>(q->stream);
   int grid = sms;
@@ -888,7 +1102,7 @@ extern "C" int vy_decode_step(const VyDecodeStep* q) {
     auto kern = decode_step_kernel<NR>;                                                                      \
     static std::once_flag once;                                                                              \
     static cudaError_t attr_rc = cudaSuccess;                                                                \
-    std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }); \
+    std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); }); \
     VY_CUDA_OK(attr_rc);                                                                                     \
     cudaLaunchConfig_t cfg;                                                                                  \
     memset(&cfg, 0, sizeof(cfg));                                                                            \

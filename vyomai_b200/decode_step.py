@@ -17,7 +17,10 @@ import torch
 from . import _lib
 from . import functional as F
 
-ENABLED = os.environ.get("VY_DECODE_FUSED", "1") != "0"
+# Opt-in (VY_DECODE_FUSED=1): measured on B200 (profiles/r02_decode_*.md) the one-launch step is at parity with the graph
+# of per-op kernels on config 3 (GQA 415 vs 382 us / step, MHA 362 vs 432 us) — both are bound by chains of dependent
+# L2 / DRAM round trips (~0.5 / ~2.5 us each on this part), not by bytes — so it does not replace the default path yet.
+ENABLED = os.environ.get("VY_DECODE_FUSED", "0") != "0"
 MAX_BATCH = 32
 
 
