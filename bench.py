@@ -117,19 +117,60 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # ------------------------------------------------------------------------------------------------
+def oracle_state_dict():
+    """Random-init weights of the bench's captioner for the CPU arm, keyed like the reference's state_dict (the names the
+    oracle reads), built with plain torch — none of this repo's modules are involved in the reference arm."""
+    g = torch.Generator().manual_seed(0)
+    H, V, FF = TextCfg.hidden_size, TextCfg.vocab_size, 4 * TextCfg.hidden_size
+    kv = TextCfg.num_key_value_heads * (H // TextCfg.num_attention_heads)
+    sd = {}
+
+    def lin(name, out_f, in_f):
+        bound = in_f ** -0.5  # nn.Linear's default init range
+        sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound
+        sd[name + ".bias"] = (torch.rand(out_f, generator=g) * 2 - 1) * bound
+
+    def ln(name, n):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(n), torch.zeros(n)
+
+    def block(pre, fused_qkv, kv_out):
+        if fused_qkv:
+            lin(pre + "attention.qkv", 3 * H, H)
+        else:
+            lin(pre + "attention.query", H, H)
+            lin(pre + "attention.key", kv_out, H)
+            lin(pre + "attention.value", kv_out, H)
+        lin(pre + "attention.out.dense", H, H)
+        ln(pre + "attention.out.layernorm", H)
+        lin(pre + "feed_forward.intermediate", FF, H)
+        lin(pre + "feed_forward.out", H, FF)
+        ln(pre + "feed_forward.layernorm", H)
+
+    pdim = VitCfg.num_channels * VitCfg.patch_size[0] * VitCfg.patch_size[1]
+    npatch = (VitCfg.image_size[0] // VitCfg.patch_size[0]) * (VitCfg.image_size[1] // VitCfg.patch_size[1])
+    sd["encoder.pixel_seq.weight"] = (torch.rand(H, VitCfg.num_channels, *VitCfg.patch_size, generator=g) * 2 - 1) * pdim ** -0.5
+    sd["encoder.pixel_seq.bias"] = (torch.rand(H, generator=g) * 2 - 1) * pdim ** -0.5
+    sd["encoder.cls_token"] = torch.randn(1, 1, pdim, generator=g)
+    sd["encoder.position_embeddings.pos_embeddings"] = torch.randn(1, npatch + 1, pdim, generator=g)
+    for i in range(VitCfg.num_hidden_layers):
+        block(f"encoder.all_layer.{i}.", True, H)
+    sd["decoder.word_embeddings.weight"] = torch.randn(V, H, generator=g)
+    for i in range(TextCfg.num_hidden_layers):
+        block(f"decoder.all_layer.{i}.", False, kv)
+    lin("decoder.lm_head.dense", H, H)
+    ln("decoder.lm_head.layer_norm", H)
+    sd["decoder.lm_head.decoder.weight"] = (torch.rand(V, H, generator=g) * 2 - 1) * H ** -0.5
+    sd["decoder.lm_head.bias"] = torch.zeros(V)
+    sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    sd["decoder.lm_head.decoder.bias"] = sd["decoder.lm_head.bias"]
+    return sd
+
+
 def oracle_train(steps, warmup, batch):
     """Times the reference's algorithm (oracle/vyom_oracle.py restatement, fp32, all host threads) on a
     bounded sample of the same workload: forward + shifted CE + backward + AdamW, `batch` samples/step."""
     from oracle import vyom_oracle as O
-    import vyomai_b200  # only for the module classes' parameter initialisation (CPU, no kernels)
-    from vyomai_b200 import VisionLanguageModel, Vit
-    torch.manual_seed(0)
-    import io
-    from contextlib import redirect_stdout
-    with redirect_stdout(io.StringIO()):  # the constructors print like the reference's do; keep stdout = one JSON line
-        model = VisionLanguageModel(TextCfg(), encoder=Vit(VitCfg()), pos_embedding_type="rope", attention_type="gqa")
-    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
-    sd["decoder.lm_head.decoder.bias"] = sd["decoder.lm_head.bias"]
+    sd = oracle_state_dict()
     params = [v for k, v in sd.items() if v.requires_grad and k != "decoder.lm_head.decoder.bias"]
     opt = torch.optim.AdamW(params, lr=1e-5)
     cfg = O.Cfg(768, 12, 4, 514, 8, 50265, 1e-5, "gelu")
@@ -151,18 +192,43 @@ def oracle_train(steps, warmup, batch):
     return batch / (sum(times) / len(times)), sum(times) / len(times)
 
 
+def host_threads():
+    """All host cores for the CPU arm. torchrun exports OMP_NUM_THREADS=1 to its workers, which made round 1's N > 1 reference
+    lines single-threaded: set the intra-op pool explicitly."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def run_reference(args):
+    """Reference arm: the reference's CPU path (oracle port: the reference has no setup.py / pyproject, nothing installs
+    under baseline/_ref) on ALL host threads, same model / sequence length / per-step batch as one GPU of our arm. If the
+    first (warm-up) step shows that K + W steps of 64 samples would not end within ~4.5 minutes on this host, the per-step
+    sample is cut to the largest multiple of 8 that does, and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
-    v, sec = oracle_train(args.steps, args.warmup, CPU_SAMPLE_BATCH)
-    sample = f"{CPU_SAMPLE_BATCH} samples per step (same model, S=128, fp32), {args.steps} timed steps after {args.warmup} warm-up"
+    cores = host_threads()
+    batch = PER_GPU_BATCH
+    t0 = time.perf_counter()
+    oracle_train(1, 0, CPU_SAMPLE_BATCH)  # probe: one 8-sample step (also pages the libraries in)
+    probe = time.perf_counter() - t0
+    est = probe * (batch / CPU_SAMPLE_BATCH) * (args.steps + args.warmup)
+    if est > 270.0:
+        batch = max(CPU_SAMPLE_BATCH, int(batch * 270.0 / est) // 8 * 8)
+    v, sec = oracle_train(args.steps, args.warmup, batch)
+    sample = (f"{batch} samples per step (same model, S=128, fp32; our arm: {PER_GPU_BATCH} per GPU), {args.steps} timed steps after "
+              f"{args.warmup} warm-up, {cores} host threads")
     line = {
         "impl": "reference", "metric": "caption_train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_step_samples": CPU_SAMPLE_BATCH, "host": "cpu oracle port of the reference path"},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": batch, "per_step_samples": batch, "seq_len": TEXT_LEN + 1,
+                   "host": "cpu oracle port of the reference path (rank 0 only)"},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -173,6 +239,102 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+FAMILIES = (  # kernel-name fragment -> C-ABI entry point it belongs to
+    ("gemm_kernel", "vy_gemm"), ("splitk_reduce", "vy_gemm"), ("attn_fwd_kernel", "vy_attn_fwd"), ("attn_bwd", "vy_attn_bwd"),
+    ("attn_dsum", "vy_attn_bwd"), ("add_layernorm_fwd", "vy_add_layernorm_fwd"), ("add_layernorm_bwd", "vy_add_layernorm_bwd"),
+    ("norm_bwd", "vy_add_layernorm_bwd"), ("adamw", "vy_adamw"), ("sqnorm", "vy_sqnorm"), ("colsum", "vy_colsum"),
+    ("xent", "vy_softmax_xent"), ("embed_bwd", "vy_embed_bwd"), ("embed_fwd", "vy_embed_fwd"), ("patchify", "vy_patchify"),
+    ("cast4d", "vy_cast4d"), ("act_bwd", "vy_act_bwd"), ("scale_by_ptr", "vy_scale_by_ptr"), ("attn_decode", "vy_attn_decode"),
+    ("decode_step", "vy_decode_step"), ("argmax", "vy_argmax_rows"), ("nccl", "nccl"), ("Memcpy", "memcpy"), ("Memset", "memset"),
+)
+
+
+def family_of(kernel_name):
+    for frag, fam in FAMILIES:
+        if frag in kernel_name:
+            return fam
+    return "torch_glue"
+
+
+def replay_profile(step, steps=2):
+    """Per-family device time of the step AS TIMED (CUDA-graph replays under CUPTI through torch.profiler): {family:
+    {"calls": per step, "ms": per step}}. Round 1's table came from an eager step with events around every call, whose small
+    kernels were inflated and whose sum exceeded ms_per_step."""
+    from collections import defaultdict
+    step()
+    torch.cuda.synchronize()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+    agg = defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        fam = family_of(ev.name)
+        agg[fam][0] += 1
+        agg[fam][1] += ev.device_time_total
+    return {k: {"calls": n / steps, "ms": t / steps / 1e3} for k, (n, t) in agg.items()}
+
+
+class DecodeCfg:  # BASELINE config 3: GPT-style CLM, kv-cache, prefill 512 + greedy decode 256, batch 32
+    hidden_size = 768
+    num_attention_heads = 12
+    max_position_embeddings = 1024
+    num_hidden_layers = 4
+    vocab_size = 50265
+    hidden_dropout_prob = 0.0
+    layer_norm_eps = 1e-05
+    hidden_act = "gelu"
+    pad_token_id = 1
+    eos_token_id = 2
+
+
+def decode_config3(dev, attn, batch=32, prefill=512, new_tokens=256):
+    """Prefill + greedy decode of BASELINE config 3 through DecoderModel.generate (static cache, one CUDA-graph replay per
+    token). Returns prefill tok/s, decode tok/s (device time of the replayed steps), the HBM roofline fraction of a decode
+    step (algorithmic bytes = every weight but the embedding table + the kv-cache rows read, at the mean context) and
+    generate()'s wall clock."""
+    import io
+    from contextlib import redirect_stdout
+    from vyomai_b200 import DecoderModel
+    cfg = type("Cfg3", (DecodeCfg,), {"num_key_value_heads": 4})() if attn == "gqa" else DecodeCfg()
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        model = DecoderModel(cfg, "rope", "gqa" if attn == "gqa" else None)
+    model = model.to(dev).to(torch.bfloat16).eval()
+    B, P, N = batch, prefill, new_tokens
+    ids = torch.randint(3, cfg.vocab_size, (B, P), device=dev)
+    mask = torch.ones((B, P), device=dev, dtype=torch.long)
+    hkv = 4 if attn == "gqa" else 12
+    model.generate(ids, mask, max_len=N, use_cache=True, use_static_cache=True)  # warm-up: tunes the GEMMs, captures the graph
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = model.generate(ids, mask, max_len=N, use_cache=True, use_static_cache=True)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    kv = model._decode_graph_cache
+    with torch.no_grad():
+        e0.record()
+        model(ids, mask, use_cache=True, kv_cache=kv, start_pos=0, _logits_last_only=True)
+        e1.record()
+        g = model._decode_graph
+        g.pos.fill_(P)
+        for _ in range(N - 1):
+            g.graph.replay()
+        e2.record()
+    torch.cuda.synchronize()
+    pre_ms, step_us = e0.elapsed_time(e1), e1.elapsed_time(e2) * 1e3 / (N - 1)
+    n_params = sum(p.numel() for n, p in model.named_parameters() if "word_embeddings" not in n)
+    step_bytes = 2.0 * n_params + 2.0 * B * cfg.num_hidden_layers * 2 * hkv * (P + N / 2) * 64
+    hbm = peaks()[0]
+    return {"workload": f"decoder_clm_L4_{attn}_B{B}_prefill{P}_decode{N}_bf16_staticcache",
+            "prefill_tok_per_s": B * P / (pre_ms / 1e3), "decode_tok_per_s": B / (step_us * 1e-6), "decode_us_per_step": step_us,
+            "decode_step_algorithmic_MB": step_bytes / 1e6, "decode_hbm_frac": step_bytes / (step_us * 1e-6) / 1e9 / hbm,
+            "generate_tok_per_s_wall": B * N / wall, "tokens_checked": int(out.shape[1]),
+            "step_kernel": "vy_decode_step" if getattr(g, "fused", None) is not None else "per-op graph"}
+
 def run_ours(args):
     import torch.distributed as dist
     from vyomai_b200 import _lib, VisionLanguageModel, Vit
@@ -255,41 +417,54 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (float(t[0]) / 1e3)
     h2d = sum(x.numel() * x.element_size() for x in host[0])
 
-    # roofline of the dominant kernel: one instrumented step, CUDA events around every C-ABI call
+    # Algorithmic work per kernel family: one instrumented EAGER step (the C-ABI wrappers count FLOPs / bytes per call; its
+    # timings are not used). Time per family: CUPTI over the captured step as it is replayed in the timed region.
     _lib.TIMER = _lib.KernelTimer()
-    trainer._caption_body(px_d, ids_d, mask_d, labels_d)  # eager (un-graphed) so every call can be bracketed
-    prof = _lib.TIMER.summary()
+    trainer._caption_body(px_d, ids_d, mask_d, labels_d)
+    work = _lib.TIMER.summary()
     _lib.TIMER = None
+    prof = replay_profile(step_resident) if not args.no_graph else {k: {"calls": v["calls"], "ms": v["ms"]} for k, v in work.items()}
     hbm, tf_burst, tf_sust, src = peaks()
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch_mean")
+    ours = {k: v for k, v in prof.items() if k.startswith("vy_")}
     total_ms = sum(d["ms"] for d in prof.values())
-    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    name, d = dom
-    if d["flops"] > 0:
-        achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+    name, d = max(ours.items(), key=lambda kv: kv[1]["ms"])
+    w = work.get(name, {"flops": 0.0, "bytes": 0.0})
+    timed_as = "cuda-graph replay (CUPTI)" if not args.no_graph else "eager step (CUDA events per call)"
+    if w["flops"] > 0:
+        achieved = w["flops"] / (d["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
                 "frac": achieved / tf_sust, "traffic": traffic if name == "vy_gemm" else None,
-                "peak_source": f"{src} (sustained bf16 GEMM)",
+                "peak_source": f"{src} (sustained bf16 GEMM)", "timed_as": timed_as,
                 "launches_per_step": d["calls"], "share_of_kernel_time": d["ms"] / total_ms}
     else:
-        achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
+        achieved = w["bytes"] / (d["ms"] / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": None, "peak_source": src, "launches_per_step": d["calls"], "share_of_kernel_time": d["ms"] / total_ms}
-    breakdown = {k: {"calls": v["calls"], "ms": round(v["ms"], 3),
-                     "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] else None,
-                     "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["bytes"] else None}
-                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+                "traffic": None, "peak_source": src, "timed_as": timed_as, "launches_per_step": d["calls"],
+                "share_of_kernel_time": d["ms"] / total_ms}
+    breakdown = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        wk = work.get(k, {"flops": 0.0, "bytes": 0.0})
+        breakdown[k] = {"calls": round(v["calls"], 1), "ms": round(v["ms"], 3),
+                        "tflops": round(wk["flops"] / (v["ms"] / 1e3) / 1e12, 1) if wk["flops"] else None,
+                        "gbs": round(wk["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if wk["bytes"] else None}
 
+    final_loss = float(loss)
     poisoned = _lib.lib().vy_gemm_poisoned()
     if poisoned != 0:
         raise RuntimeError(f"vy_gemm_poisoned() = {poisoned}: a wait inside a GEMM kernel timed out, the numbers above are void")
+    decode = None
+    if world == 1 and not args.no_decode:
+        # the metric also names decode tok/s: BASELINE config 3, GQA and MHA, on this GPU (inference replicas do not interact,
+        # so it is measured at N = 1 only)
+        decode = {a: decode_config3(dev, a) for a in ("gqa", "mha")}
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = torch.get_num_threads()
+            cores = host_threads()
             v, sec = oracle_train(1, 1, CPU_SAMPLE_BATCH)
             cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                    "sample": f"1 timed step of {CPU_SAMPLE_BATCH} samples after 1 warm-up step (oracle port, fp32, {sec:.1f} s/step)"}
@@ -303,7 +478,8 @@ def run_ours(args):
                        "cuda_graph": not args.no_graph, "grad_overwrite": bool(trainer.grad_overwrite)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof, "cpu_baseline": cpu,
-            "kernel_breakdown_ms": breakdown, "final_loss": float(loss), "e2e_last_loss": last,
+            "kernel_breakdown_ms": breakdown, "kernel_breakdown_sum_ms": round(total_ms, 3), "decode": decode,
+            "final_loss": final_loss, "e2e_last_loss": last,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -323,6 +499,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the config-3 decode measurement appended at N = 1")
     ap.add_argument("--no-grad-overwrite", action="store_true", help="zero + accumulate every gradient instead of overwrite mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of bucketed overlap")
