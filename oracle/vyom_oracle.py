@@ -591,3 +591,88 @@ def dropout_keep_mask(rows: int, H: int, p: float, seed: int, offset: int, step:
 def dropout_add_layer_norm(x: Tensor, residual: Tensor, keep: Tensor, p: float, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
     """LN(dropout(x) + residual) with a given keep mask (attention.py:70-71, ffn.py:38-39)."""
     return layer_norm(torch.where(keep, x / (1.0 - p), torch.zeros_like(x)) + residual, gamma, beta, eps)
+
+
+# ----------------------------------------------------------------------------------------------
+# seq2seq: cross-attention and the BART-style decoder around it (models/encoder_decoder.py, layers/attention.py:382-573)
+# ----------------------------------------------------------------------------------------------
+def cross_attention(sd: SD, pre: str, x: Tensor, enc: Tensor, enc_mask: Optional[Tensor], cfg: Cfg,
+                    attention_type: Optional[str], kv_store: Optional[dict] = None) -> Tensor:
+    """EncoderDecoderAttention[Gqa].forward (layers/attention.py:409-470, 513-573): q from the decoder stream, k / v from the
+    encoder states — computed once and kept when a cache is attached (`len(cache) == 0` decides, :445-462) — no RoPE (the
+    call is commented out in the reference), additive encoder key-padding mask, then AttentionSelfOutput."""
+    d = cfg.head_dim
+    q = split_heads(linear(x, sd[pre + "query.weight"], sd.get(pre + "query.bias")), d)
+    if kv_store is not None and "k" in kv_store:
+        k, v = kv_store["k"], kv_store["v"]
+    else:
+        k = split_heads(linear(enc, sd[pre + "key.weight"], sd.get(pre + "key.bias")), d)
+        v = split_heads(linear(enc, sd[pre + "value.weight"], sd.get(pre + "value.bias")), d)
+        if kv_store is not None:
+            kv_store["k"], kv_store["v"] = k, v
+    n_rep = q.shape[1] // k.shape[1]
+    out = merge_heads(sdpa(q, repeat_kv(k, n_rep), repeat_kv(v, n_rep), enc_mask))
+    return attention_self_output(sd, pre + "out.", out, x, cfg.layer_norm_eps)
+
+
+def seq2seq_decoder_forward(sd: SD, cfg: Cfg, input_ids: Tensor, attention_mask: Optional[Tensor], enc: Tensor,
+                            enc_mask: Optional[Tensor], pos_type="absolute", attention_type=None, cache=None,
+                            cross_store: Optional[list] = None, start_pos: int = 0, pre: str = "decoder.") -> Tensor:
+    """Seq2SeqDecoderModel.forward (models/encoder_decoder.py:157-212) with Seq2SeqDecoderLayer.forward (:57-87):
+    self-attention (causal x padding, per-layer cache) -> cross-attention -> FeedForward with the LAYER INPUT as residual."""
+    h = sd[pre + "word_embeddings.weight"][input_ids]
+    bsz, seqlen = input_ids.shape
+    add, freqs = _positions(sd, pre, cfg, pos_type, start_pos, seqlen, h.dtype)
+    if add is not None:
+        h = h + add
+    mask = decoder_mask(bsz, seqlen, attention_mask, start_pos, h.dtype) if seqlen > 1 else None
+    for i in range(cfg.num_hidden_layers):
+        p = f"{pre}all_layer.{i}."
+        a = self_attention(sd, p + "attention.", h, mask, freqs, cfg, attention_type, cache=cache, layer_idx=i, start_pos=start_pos)
+        c = cross_attention(sd, p + "cross_attention.", a, enc, enc_mask, cfg, attention_type,
+                            None if cross_store is None else cross_store[i])
+        h = feed_forward(sd, p + "feed_forward.", c, h, cfg)
+    return h
+
+
+def seq2seq_lm_head(sd: SD, h: Tensor, eps: float, pre: str = "lm_head.") -> Tensor:
+    """LMHead of the seq2seq model (models/encoder_decoder.py:90-113): vocab(LN(gelu(dense(h))))."""
+    x = gelu_erf(linear(h, sd[pre + "dense.weight"], sd[pre + "dense.bias"]))
+    x = layer_norm(x, sd[pre + "layer_norm.weight"], sd[pre + "layer_norm.bias"], eps)
+    return linear(x, sd[pre + "vocab.weight"], sd[pre + "bias"])
+
+
+def seq2seq_forward(sd: SD, enc_cfg: Cfg, dec_cfg: Cfg, input_ids: Optional[Tensor], attention_mask: Optional[Tensor],
+                    decoder_input_ids: Tensor, decoder_attention_mask: Optional[Tensor], enc_pos="absolute", enc_attn=None,
+                    dec_pos="absolute", dec_attn=None, encoder_output: Optional[Tensor] = None, cache=None, cross_store=None,
+                    start_pos: int = 0) -> Tuple[Tensor, Tensor]:
+    """EncoderDecoderModel.forward (models/encoder_decoder.py:305-343). Returns (logits, encoder_output)."""
+    if encoder_output is None:
+        encoder_output = encoder_forward(sd, enc_cfg, input_ids, attention_mask, enc_pos, enc_attn, pre="encoder.")
+    if attention_mask is None:
+        attention_mask = torch.ones(encoder_output.shape[:2])
+    enc_mask = encoder_mask(attention_mask, encoder_output.dtype)
+    h = seq2seq_decoder_forward(sd, dec_cfg, decoder_input_ids, decoder_attention_mask, encoder_output, enc_mask, dec_pos,
+                                dec_attn, cache, cross_store, start_pos)
+    return seq2seq_lm_head(sd, h, dec_cfg.layer_norm_eps), encoder_output
+
+
+def seq2seq_generate(sd, enc_cfg, dec_cfg, encoder_output: Tensor, encoder_attention_mask: Optional[Tensor], decoder_start: Tensor,
+                     max_new_tokens: int, dec_pos="absolute", dec_attn=None, use_cache: bool = False) -> Tensor:
+    """generate_seq2seq, greedy (generation_utils.py:54-125)."""
+    idx = decoder_start
+    idx_next = idx
+    index = 0
+    cache = DynamicCacheOneOracle(dec_cfg.num_hidden_layers) if use_cache else None
+    cross = [dict() for _ in range(dec_cfg.num_hidden_layers)] if use_cache else None
+    for _ in range(max_new_tokens):
+        if use_cache:
+            logits, _ = seq2seq_forward(sd, enc_cfg, dec_cfg, None, encoder_attention_mask, idx_next, None, dec_pos=dec_pos,
+                                        dec_attn=dec_attn, encoder_output=encoder_output, cache=cache, cross_store=cross, start_pos=index)
+        else:
+            logits, _ = seq2seq_forward(sd, enc_cfg, dec_cfg, None, encoder_attention_mask, idx, None, dec_pos=dec_pos,
+                                        dec_attn=dec_attn, encoder_output=encoder_output)
+        idx_next = torch.topk(torch.softmax(logits[:, -1], dim=-1), k=1, dim=-1)[1]
+        idx = torch.cat((idx, idx_next), dim=1)
+        index = idx.shape[1] - 1
+    return idx

@@ -179,8 +179,11 @@ def test_vyomai_import_name_is_a_drop_in_for_the_hot_path():
     assert D2 is vyomai_b200.DecoderModel and C2 is vyomai_b200.EncoderConfig
     cfg = EncoderConfig()
     assert (cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size) == (768, 12, 50265)  # reference defaults (utils.py:90-100)
+    from VyomAI import DoraLinear, EncoderDecoderModel, LoraLinear, Seq2SeqDecoderModel, generate_seq2seq  # noqa: F401  (round 2)
+    from VyomAI.models.encoder_decoder import EncoderDecoderModel as E2
+    assert E2 is vyomai_b200.EncoderDecoderModel
     with pytest.raises(ImportError):
-        from VyomAI import LoraLinear  # noqa: F401
+        from VyomAI import ModelForCausalLM  # noqa: F401
     with pytest.raises(ImportError):
         VyomAI.speculative_generate
 

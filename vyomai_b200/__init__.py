@@ -9,5 +9,7 @@ from .models.encoder import EncoderModel, EncoderForMaskedLM  # noqa: F401
 from .models.decoder import DecoderModel  # noqa: F401
 from .models.vision_encoder import Vit  # noqa: F401
 from .models.multimodel import VisionLanguageModel  # noqa: F401
-from .generation_utils import generate, generate_multimodel  # noqa: F401
+from .models.encoder_decoder import EncoderDecoderModel, Seq2SeqDecoderModel  # noqa: F401
+from .layers.adapters import DoraLinear, LoraLinear  # noqa: F401
+from .generation_utils import generate, generate_multimodel, generate_seq2seq  # noqa: F401
 from .paged import ContinuousBatchEngine, PagedKVManager, SequenceState  # noqa: F401  (Examples/simple_vllm.ipynb)

@@ -47,6 +47,29 @@ def attention_block_fn(mod, x2d: torch.Tensor, B: int, S: int, mask: MaskSpec, r
     return y
 
 
+def cross_attention_block_fn(mod, x2d: torch.Tensor, B: int, Sq: int, enc2d: Optional[torch.Tensor], Skv: int, mask: MaskSpec,
+                             cached_kv=None) -> torch.Tensor:
+    """EncoderDecoderAttention[Gqa].forward: LN(dense(cross_attention(x, enc)) + x)."""
+    dense, ln = mod.out.dense, mod.out.layernorm
+    drop = F.dropout_state(mod.out, mod.out.dropout.p)
+    if cached_kv is None and _needs_grad(x2d, enc2d, mod.query.weight, mod.key.weight, dense.weight, ln.weight):
+        from .autograd_train import CrossAttentionBlockFn
+        return CrossAttentionBlockFn.apply(mod, B, Sq, Skv, mask, drop, x2d, enc2d, mod.query.weight, mod.query.bias, mod.key.weight,
+                                           mod.key.bias, mod.value.weight, mod.value.bias, dense.weight, dense.bias, ln.weight, ln.bias)
+    attn, _ = F.cross_attention_core(x2d, B, Sq, enc2d, Skv, mod.query, mod.key, mod.value, mod.num_attention_heads, mod._kv_heads,
+                                     mask, cached_kv)
+    y, _ = F.self_output(attn, x2d, dense, ln, dropout=drop)
+    return y
+
+
+def linear_fn(x2d: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """y = x W^T + b on vy_gemm, differentiable (plain nn.Linear semantics for callers outside the fused blocks)."""
+    if _needs_grad(x2d, w, b):
+        from .autograd_train import LinearFn
+        return LinearFn.apply(x2d, w, b)
+    return F._lin(x2d, w, b)
+
+
 def self_output_fn(attn2d: torch.Tensor, residual2d: torch.Tensor, dense: nn.Linear, ln: nn.LayerNorm,
                    dropout=None) -> torch.Tensor:
     if _needs_grad(attn2d, residual2d, dense.weight, ln.weight):

@@ -202,6 +202,65 @@ class AttentionBlockFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *grads)
 
 
+class CrossAttentionBlockFn(torch.autograd.Function):
+    """y = LN(dropout(dense(attention(q(x), k(enc), v(enc)))) + x) — cross-attention (layers/attention.py:382-573). Inputs
+    after the non-tensor arguments: x2d, enc2d, Wq, bq, Wk, bk, Wv, bv, Wo, bo, ln.weight, ln.bias."""
+
+    @staticmethod
+    def forward(ctx, mod, B, Sq, Skv, mask, drop, x2d, enc2d, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta):
+        attn, (q, k, v, lse) = F.cross_attention_core(x2d, B, Sq, enc2d, Skv, mod.query, mod.key, mod.value, mod.num_attention_heads,
+                                                       mod._kv_heads, mask, None, need_lse=True)
+        y, (s, mean, rstd) = F.self_output(attn, x2d, mod.out.dense, mod.out.layernorm, save=True, dropout=drop)
+        ctx.mod, ctx.B, ctx.Sq, ctx.Skv, ctx.mask, ctx.drop = mod, B, Sq, Skv, mask, drop
+        ctx.save_for_backward(x2d, enc2d, q, k, v, attn, lse, s, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, enc2d, q, k, v, attn, lse, s, mean, rstd = ctx.saved_tensors
+        mod, B, Sq, Skv, mask = ctx.mod, ctx.B, ctx.Sq, ctx.Skv, ctx.mask
+        dense, ln = mod.out.dense, mod.out.layernorm
+        Hq, Hkv, d = mod.num_attention_heads, mod._kv_heads, F.HEAD_DIM
+        ds, dgamma, dbeta, d_bo = _ln_bwd(dy.contiguous(), s, ln.weight, ln.bias, mean, rstd, bias=dense.bias, dropout=ctx.drop)
+        ds, dxo = _split_ds(ds)
+        d_wo = _emit_wgrad(dense.weight, dxo, attn)
+        d_attn = _dgrad(dxo, dense.weight, out_dtype=torch.bfloat16)
+        dq = torch.empty((B * Sq, Hq * d), device=dy.device, dtype=x2d.dtype)
+        dkv = torch.empty((B * Skv, 2 * Hkv * d), device=dy.device, dtype=x2d.dtype)
+        ops.attn_bwd(q, k, v, attn, d_attn, lse, causal=False, q_pos0=0, key_padding_mask=mask.key_padding, rope_cos=None,
+                     rope_sin=None, dq=dq, dk=dkv[:, : Hkv * d], dv=dkv[:, Hkv * d:])
+        dx = _dgrad(dq, mod.query.weight, addend=ds)  # + the residual branch
+        w_kv, _ = F.pack_linears([mod.key, mod.value])
+        d_enc = _dgrad(dkv, w_kv)
+        d_wq = _wgrad(dq, x2d, mod.query.weight)
+        d_wkv = _wgrad(dkv, enc2d, w_kv)
+        n = Hkv * d
+        d_bq = _bgrad(dq, mod.query.bias)
+        d_bkv = _bgrad(dkv, mod.key.bias)
+        d_bk = d_bkv[:n] if d_bkv is not None else None
+        d_bv = d_bkv[n:] if d_bkv is not None else None
+        return (None, None, None, None, None, None, dx, d_enc, d_wq, d_bq, d_wkv[:n], d_bk, d_wkv[n:], d_bv, d_wo, d_bo, dgamma, dbeta)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (nn.Linear) on vy_gemm with its dgrad / wgrad / bias-gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, b):
+        ctx.save_for_backward(x2d, w)
+        ctx.bdt = None if b is None else b.dtype
+        return F._lin(x2d, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = _dgrad(dy, w) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(dy, x2d, w) if ctx.needs_input_grad[1] else None
+        db = ops.colsum(dy, out_dtype=ctx.bdt) if (ctx.bdt is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
 class SelfOutputFn(torch.autograd.Function):
     """y = LN(dense(attn) + residual) (AttentionSelfOutput used stand-alone)."""
 

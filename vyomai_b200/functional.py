@@ -213,6 +213,37 @@ def attention_core(
     return out.view(B * S, n_q_heads * d), (q, k_att, v_att, lse)
 
 
+def project_kv(enc2d: torch.Tensor, B: int, Skv: int, key: nn.Linear, value: nn.Linear, n_kv_heads: int):
+    """k / v projections of the encoder states as [B, h_kv, Skv, 64] bf16 (one GEMM over the packed key | value weights)."""
+    w_kv, b_kv = pack_linears([key, value])
+    k = torch.empty((B, n_kv_heads, Skv, HEAD_DIM), device=enc2d.device, dtype=torch.bfloat16)
+    v = torch.empty((B, n_kv_heads, Skv, HEAD_DIM), device=enc2d.device, dtype=torch.bfloat16)
+    ops.qkv_rope_gemm(enc2d, w_kv, b_kv, tokens_per_seq=Skv, start_pos=0, n_q_heads=0, n_kv_heads=n_kv_heads, head_dim=HEAD_DIM,
+                      rope_cos=None, rope_sin=None, q_out=None, k_out=k, v_out=v)
+    return k, v
+
+
+def cross_attention_core(x2d: torch.Tensor, B: int, Sq: int, enc2d: Optional[torch.Tensor], Skv: int, query: nn.Linear,
+                         key: nn.Linear, value: nn.Linear, n_q_heads: int, n_kv_heads: int, mask: MaskSpec,
+                         cached_kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, need_lse: bool = False):
+    """Cross-attention core (layers/attention.py:431-468, 535-571): q from the decoder stream, k / v from the encoder
+    states (or from the cache that holds them after the first generation step), no RoPE (the reference leaves it commented
+    out), key-padding mask of the ENCODER sequence, GQA by head index. Returns (attn [B*Sq, Hq*64], (q, k, v, lse))."""
+    dev = x2d.device
+    d = HEAD_DIM
+    q = torch.empty((B, n_q_heads, Sq, d), device=dev, dtype=torch.bfloat16)
+    ops.qkv_rope_gemm(x2d, query.weight, query.bias, tokens_per_seq=Sq, start_pos=0, n_q_heads=n_q_heads, n_kv_heads=0,
+                      head_dim=d, rope_cos=None, rope_sin=None, q_out=q, k_out=None, v_out=None)
+    if cached_kv is not None:
+        k, v = cached_kv
+        if k.dtype != torch.bfloat16:
+            k, v = ops.cast4d(k, torch.bfloat16), ops.cast4d(v, torch.bfloat16)
+    else:
+        k, v = project_kv(enc2d, B, Skv, key, value, n_kv_heads)
+    out, lse = ops.attn_fwd(q, k, v, causal=False, q_pos0=0, key_padding_mask=mask.key_padding, out_dtype=x2d.dtype, need_lse=need_lse)
+    return out.view(B * Sq, n_q_heads * d), (q, k, v, lse)
+
+
 def dropout_state(module: nn.Module, p: float) -> Optional[ops.DropoutState]:
     """The reference's nn.Dropout(hidden_dropout_prob) is live in .train() (attention.py:55,70; ffn.py:24,38): a fresh
     mask identity per call then, None in eval / p = 0."""

@@ -37,6 +37,28 @@ def generate(model: nn.Module, tokenize_text: torch.Tensor, max_new_tokens: Opti
     return idx
 
 
+def generate_seq2seq(model: nn.Module, encoder_output: torch.Tensor, encoder_attention_mask: torch.Tensor, decoder_start: torch.Tensor,
+                     max_new_tokens: Optional[int] = 5, temperature: Optional[float] = 1.0, do_sample: Optional[bool] = False,
+                     top_k: Optional[int] = 10, use_cache: Optional[bool] = False) -> torch.Tensor:
+    """reference: generation_utils.py:54-125 (the cached step feeds only the newest token at start_pos = len - 1: the model
+    already holds the earlier ones in its self-attention caches, and the encoder's k / v in the cross-attention caches)"""
+    idx = decoder_start
+    idx_next = idx
+    index = 0
+    for _ in range(max_new_tokens):
+        with torch.no_grad():
+            if use_cache:
+                logits = model(encoder_output=encoder_output, attention_mask=encoder_attention_mask, decoder_input_ids=idx_next,
+                               use_cache=use_cache, start_pos=index).logits
+            else:
+                logits = model(encoder_output=encoder_output, attention_mask=encoder_attention_mask, decoder_input_ids=idx,
+                               use_cache=use_cache).logits
+        idx_next = _pick(logits[:, -1], temperature, do_sample).to(idx.device)
+        idx = torch.cat((idx, idx_next), dim=1)
+        index = idx.size()[1] - 1
+    return idx
+
+
 def generate_multimodel(model: nn.Module, encoder_output: torch.Tensor, encoder_attention_mask: torch.Tensor,
                         decoder_start: torch.Tensor, max_new_tokens=24, temperature=1.0, do_sample=False, top_k=10,
                         use_cache=False) -> torch.Tensor:

@@ -237,3 +237,82 @@ class SharedCacheDecoderAttentionGqa(_SharedCacheDecoderAttentionBase):
     def __init__(self, config, layer_idx: int) -> None:
         super().__init__()
         self._setup(config, layer_idx, gqa=True)
+
+
+class _CrossAttentionBase(nn.Module):
+    """Cross-attention of the seq2seq decoder (reference: attention.py:382-573): queries from the decoder stream, keys /
+    values from the encoder states, computed once per generation and then read back from the per-layer cache
+    (`len(cache) == 0` decides, :445-462); no RoPE; the mask is the ENCODER's key-padding mask."""
+
+    def _setup(self, config, layer_idx: int, gqa: bool) -> None:
+        _check_heads(config)
+        self.layer_idx = layer_idx
+        self.attention_bias = getattr(config, "attention_bias", True)
+        self.num_attention_heads = config.num_attention_heads
+        head = int(config.hidden_size // config.num_attention_heads)
+        if gqa:
+            self.head_dim = head
+            self.is_casual = True
+            self.num_key_value_heads = getattr(config, "num_key_value_heads", 4)
+            self.num_key_value_groups = self.num_attention_heads // max(self.num_key_value_heads, 1)
+            if self.num_attention_heads % self.num_key_value_heads != 0 or self.num_attention_heads < self.num_key_value_heads:
+                raise ValueError(
+                    f"num_key_value_heads {self.num_key_value_heads }  should be less than equal num_attention_heads {config.num_attention_heads} and  multiple of num_attention_heads {config.num_attention_heads} "
+                )
+            kv_out = self.num_key_value_heads * head
+        else:
+            self.head_size = head
+            kv_out = config.hidden_size
+        self._head = head
+        self._kv_heads = self.num_key_value_heads if gqa else self.num_attention_heads
+        self.flash = True
+        self.query = nn.Linear(config.hidden_size, config.hidden_size, bias=self.attention_bias)
+        self.key = nn.Linear(config.hidden_size, kv_out, bias=self.attention_bias)
+        self.value = nn.Linear(config.hidden_size, kv_out, bias=self.attention_bias)
+        self.out = AttentionSelfOutput(config=config, bias=self.attention_bias)
+
+    def forward(self, hidden_state: torch.Tensor, encoder_hidden_state: torch.Tensor, encoder_attention_mask: torch.Tensor,
+                freqs: Optional[torch.Tensor] = None, use_cache: Optional[bool] = False) -> torch.Tensor:
+        if self._head != F.HEAD_DIM:
+            raise _lib.VyomError(f"the sm_100a attention path is specialised for head_dim 64 (got {self._head})")
+        B, Sq, H = hidden_state.shape
+        mask = encoder_attention_mask if isinstance(encoder_attention_mask, MaskSpec) else MaskSpec.from_dense(encoder_attention_mask, 1)
+        if mask.causal:
+            raise _lib.VyomError("cross-attention takes the encoder's key-padding mask, not a causal one")
+        from ..autograd import cross_attention_block_fn
+        x2d = hidden_state.reshape(B * Sq, H)
+        cached = None
+        enc2d, Skv = None, 0
+        if use_cache:
+            cache = getattr(self, "cache", None)
+            if cache is None:
+                raise ValueError("use_cache is True please enable model._setup_cache() to use kv-cache")
+            if len(cache) != 0:
+                cached = cache.get()
+                Skv = cached[0].shape[2]
+        if cached is None:
+            Skv = encoder_hidden_state.shape[1]
+            enc2d = encoder_hidden_state.reshape(B * Skv, H).to(hidden_state.dtype)
+        if use_cache and cached is None:
+            # first cached step: project k / v once and keep them (they do not change during generation)
+            with torch.no_grad():
+                k, v = F.project_kv(enc2d, B, Skv, self.key, self.value, self._kv_heads)
+            cached = self.cache.update(k, v)
+        y = cross_attention_block_fn(self, x2d, B, Sq, enc2d, Skv, mask, cached)
+        return y.view(B, Sq, H)
+
+
+class EncoderDecoderAttention(_CrossAttentionBase):
+    """reference: attention.py:382-470"""
+
+    def __init__(self, config, layer_idx: int) -> None:
+        super().__init__()
+        self._setup(config, layer_idx, gqa=False)
+
+
+class EncoderDecoderAttentionGqa(_CrossAttentionBase):
+    """reference: attention.py:473-573"""
+
+    def __init__(self, config, layer_idx: int) -> None:
+        super().__init__()
+        self._setup(config, layer_idx, gqa=True)

@@ -180,25 +180,34 @@ def qkv_rope_gemm(
     head_dim: int,
     rope_cos: Optional[torch.Tensor],
     rope_sin: Optional[torch.Tensor],
-    q_out: torch.Tensor,
-    k_out: torch.Tensor,
-    v_out: torch.Tensor,
+    q_out: Optional[torch.Tensor],
+    k_out: Optional[torch.Tensor],
+    v_out: Optional[torch.Tensor],
     kv_dst_pos0: Optional[int] = None,
 ) -> None:
     """Fused q/k/v projection: bias + in-register RoPE + "b l (h d) -> b h l d" scatter + kv-cache
     append. q_out/k_out/v_out are 4-D [B, heads, tokens, head_dim] tensors (any batch/head/token
-    strides, head_dim contiguous); k/v rows land at token index start_pos + l.
+    strides, head_dim contiguous); k/v rows land at token index start_pos + l. With n_kv_heads == 0 only q is projected
+    (k_out / v_out None), with n_q_heads == 0 only k and v — the two halves of cross-attention, whose queries and keys come
+    from different sequences (layers/attention.py:431-451).
     """
     _need_cuda(x, w, bias, rope_cos, rope_sin, q_out, k_out, v_out)
     M, K = x.shape
     N = w.shape[0]
     a_mn, lda = _major(x, "qkv x")
     b_mn, ldb = _major(w, "qkv w")
+    if (n_q_heads > 0 and q_out is None) or (n_kv_heads > 0 and (k_out is None or v_out is None)):
+        raise _lib.VyomError("qkv_rope_gemm: missing output tensor")
     for t in (q_out, k_out, v_out):
-        if t.dim() != 4 or t.stride(3) != 1:
+        if t is not None and (t.dim() != 4 or t.stride(3) != 1):
             raise _lib.VyomError("qkv_rope_gemm: outputs must be [B,h,S,d] with contiguous d")
-    if k_out.dtype != v_out.dtype:
+    if k_out is not None and k_out.dtype != v_out.dtype:
         raise _lib.VyomError("qkv_rope_gemm: k_out and v_out must share a dtype")
+    ref_out = q_out if q_out is not None else k_out
+    if q_out is None:
+        q_out = k_out  # placeholders for the struct's strides / dtype (never written when the head count is 0)
+    if k_out is None:
+        k_out = v_out = q_out
     if rope_cos is not None and (rope_cos.dtype != torch.float32 or not rope_cos.is_contiguous()):
         raise _lib.VyomError("qkv_rope_gemm: rope tables must be contiguous float32")
     kw = dict(
@@ -211,13 +220,14 @@ def qkv_rope_gemm(
         q_out=q_out.data_ptr(), q_sb=q_out.stride(0), q_sh=q_out.stride(1), q_sl=q_out.stride(2),
         k_out=k_out.data_ptr(), k_sb=k_out.stride(0), k_sh=k_out.stride(1), k_sl=k_out.stride(2),
         v_out=v_out.data_ptr(), v_sb=v_out.stride(0), v_sh=v_out.stride(1), v_sl=v_out.stride(2),
-        kv_out_dtype=_dt(k_out), kv_cap=k_out.shape[2], rope_rows=rope_cos.shape[0] if rope_cos is not None else 0,
+        kv_out_dtype=_dt(k_out), kv_cap=k_out.shape[2] if n_kv_heads > 0 else 0, rope_rows=rope_cos.shape[0] if rope_cos is not None else 0,
         stream=_stream(),
     )
     if gemm_tune.ENABLED:
         key = ("qkv", M, N, K, kw["in_dtype"], a_mn, b_mn, bias is not None, rope_cos is not None, n_q_heads, n_kv_heads,
                tokens_per_seq, q_out.dtype, k_out.dtype)
-        kw.update(gemm_tune.hints(key, kw, [("q_out", q_out), ("k_out", k_out), ("v_out", v_out)], x.device))
+        written = ([("q_out", q_out)] if n_q_heads > 0 else []) + ([("k_out", k_out), ("v_out", v_out)] if n_kv_heads > 0 else [])
+        kw.update(gemm_tune.hints(key, kw, written, x.device))
     _lib.call("vy_gemm", "VyGemm", **kw)
 
 
