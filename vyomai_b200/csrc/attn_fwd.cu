@@ -172,6 +172,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       const int kv0 = j * AT_BN;
       // key-padding bits of this tile: bit i of kb[k] <-> key kv0 + 4 i + k
       uint32_t kb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      // Visibility of the tile's keys for this row in "prefix form": keys [0, vis_end) are visible, [vis_end, tile_valid)
+      // are masked (finite score: quirk Q4), [tile_valid, 128) lie beyond Skv. Right padding, no padding and the causal
+      // bound are all prefixes, so the per-element mask logic (bit extraction, two compares, two selects — it made the
+      // softmax warps issue-bound at ~33 instructions per score) collapses to a comparison of the column index with a
+      // per-row register; anything else (left padding) takes the general per-element path.
+      const int tile_valid = min(AT_BN, g.Skv - kv0);
+      int vis_end = tile_valid;
+      bool prefix = true;
       if (g.kpm) {
         uint32_t w = 0;
         const int kbase = kv0 + lane * 4;
@@ -181,28 +189,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
           if (kbase + k < g.Skv && kp[kbase + k]) w |= 1u << k;
 #pragma unroll
         for (int k = 0; k < 4; ++k) kb[k] = __ballot_sync(0xffffffffu, (w >> k) & 1u);
+        const int cnt = __popc(kb[0]) + __popc(kb[1]) + __popc(kb[2]) + __popc(kb[3]);
+        uint32_t expect = 0;  // this lane's 4 keys if the visible ones were exactly the first cnt of the tile
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane * 4 + k < cnt) expect |= 1u << k;
+        prefix = __ballot_sync(0xffffffffu, expect != w) == 0u;
+        vis_end = min(vis_end, cnt);
       }
-      auto score = [&](uint32_t raw, int c) -> float {
-        const int key = kv0 + c;
-        float t = __uint_as_float(raw) * g.scale_log2;
-        const bool vis = ((kb[c & 3] >> (c >> 2)) & 1u) && (!g.causal || key <= qpos);
-        t = vis ? t : AT_MASKED;
-        return key < g.Skv ? t : -INFINITY;
-      };
+      if (g.causal) vis_end = min(vis_end, max(qpos - kv0 + 1, 0));
+      // tcgen05.ld is warp-collective: the chunk classification below must be warp-uniform, so it uses the smallest and
+      // the largest vis_end of the warp's 32 rows (they differ only on the causal diagonal)
+      const int vmin = __reduce_min_sync(0xffffffffu, vis_end), vmax = __reduce_max_sync(0xffffffffu, vis_end);
 
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
       float mx = m;
+      if (prefix) {
+        // pass 1: row max of the visible raw scores (the scale is positive: applied once to the maximum)
+        float rmax = -INFINITY;
 #pragma unroll 1
-      for (int c4 = 0; c4 < AT_BN / 32; ++c4) {
-        uint32_t raw[32];
-        tmem_ld_x32(tmem_S + lane_off + c4 * 32, raw);
-        tmem_ld_wait();
+        for (int c4 = 0; c4 < AT_BN / 32; ++c4) {
+          if (c4 * 32 >= vmax) break;
+          uint32_t raw[32];
+          tmem_ld_x32(tmem_S + lane_off + c4 * 32, raw);
+          tmem_ld_wait();
+          if (c4 * 32 + 32 <= vmin) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, score(raw[i], c4 * 32 + i));
+            for (int i = 0; i < 32; ++i) rmax = fmaxf(rmax, __uint_as_float(raw[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c4 * 32 + i < vis_end) rmax = fmaxf(rmax, __uint_as_float(raw[i]));
+          }
+        }
+        mx = fmaxf(mx, rmax * g.scale_log2);
+        if (vis_end < tile_valid) mx = fmaxf(mx, AT_MASKED);
+      } else {
+        auto score = [&](uint32_t raw, int c) -> float {
+          const int key = kv0 + c;
+          float t = __uint_as_float(raw) * g.scale_log2;
+          const bool vis = ((kb[c & 3] >> (c >> 2)) & 1u) && (!g.causal || key <= qpos);
+          t = vis ? t : AT_MASKED;
+          return key < g.Skv ? t : -INFINITY;
+        };
+#pragma unroll 1
+        for (int c4 = 0; c4 < AT_BN / 32; ++c4) {
+          uint32_t raw[32];
+          tmem_ld_x32(tmem_S + lane_off + c4 * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, score(raw[i], c4 * 32 + i));
+        }
       }
-      const float alpha = exp2f(m - mx);  // m = -inf on the first tile -> 0
+      const float alpha = vy_ex2_approx(m - mx);  // m = -inf on the first tile -> 0
       m = mx;
       // fold in the previous tile's P V (already complete: the tensor pipe runs in issue order)
       if (j > 0) {
@@ -221,19 +261,65 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       for (int i = 0; i < AT_D; ++i) acc[i] *= alpha;
       l *= alpha;
       // pass 2: p = exp2(t - m), row sum, bf16 P into swizzled smem (K-major, two 64-key atoms)
+      const float pm = vy_ex2_approx(AT_MASKED - m);  // weight of a masked key: 0, or 1 when the row has seen no visible key
 #pragma unroll 1
       for (int c4 = 0; c4 < AT_BN / 32; ++c4) {
-        uint32_t raw[32];
-        tmem_ld_x32(tmem_S + lane_off + c4 * 32, raw);
-        tmem_ld_wait();
         uint32_t packed[16];
+        if (prefix && c4 * 32 >= vmax) {
+          // whole chunk masked or beyond Skv for every row of the warp: constant weights, no TMEM read
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(score(raw[2 * i], c4 * 32 + 2 * i) - m);
-          const float p1 = exp2f(score(raw[2 * i + 1], c4 * 32 + 2 * i + 1) - m);
-          l += p0 + p1;
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-          packed[i] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = c4 * 32 + 2 * i < tile_valid ? pm : 0.f;
+            const float p1 = c4 * 32 + 2 * i + 1 < tile_valid ? pm : 0.f;
+            l += p0 + p1;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+            packed[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        } else {
+          uint32_t raw[32];
+          tmem_ld_x32(tmem_S + lane_off + c4 * 32, raw);
+          tmem_ld_wait();
+          if (prefix && c4 * 32 + 32 <= vmin) {
+            // whole chunk visible for every row of the warp: one FFMA + one MUFU per score
+            const float nm = -m;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = vy_ex2_approx(fmaf(__uint_as_float(raw[2 * i]), g.scale_log2, nm));
+              const float p1 = vy_ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), g.scale_log2, nm));
+              l += p0 + p1;
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+              packed[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          } else if (prefix) {
+            const float nm = -m;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c0 = c4 * 32 + 2 * i;
+              float p0 = vy_ex2_approx(fmaf(__uint_as_float(raw[2 * i]), g.scale_log2, nm));
+              float p1 = vy_ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), g.scale_log2, nm));
+              p0 = c0 < vis_end ? p0 : (c0 < tile_valid ? pm : 0.f);
+              p1 = c0 + 1 < vis_end ? p1 : (c0 + 1 < tile_valid ? pm : 0.f);
+              l += p0 + p1;
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+              packed[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = c4 * 32 + 2 * i + e;
+                const int key = kv0 + c;
+                const bool vis = ((kb[c & 3] >> (c >> 2)) & 1u) && (!g.causal || key <= qpos);
+                const float t = vis ? __uint_as_float(raw[2 * i + e]) * g.scale_log2 : AT_MASKED;
+                p[e] = key < g.Skv ? vy_ex2_approx(t - m) : 0.f;
+              }
+              l += p[0] + p[1];
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(p[0], p[1]);
+              packed[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          }
         }
         // 32 columns = 4 chunks of 16 B; atom = 64 columns
         const int atom = c4 >> 1;

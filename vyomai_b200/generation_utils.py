@@ -15,7 +15,9 @@ def _pick(logits_last: torch.Tensor, temperature: float, do_sample: bool) -> tor
     if do_sample:
         probs = torch.softmax(logits_last.float() / temperature, dim=-1)
         return torch.multinomial(probs, num_samples=1)
-    return ops.argmax_rows(logits_last)[:, None]
+    if not logits_last.is_cuda:  # a caller working with CPU tensors got its logits back on the CPU (models/_common.ensure_cuda)
+        logits_last = logits_last.cuda()
+    return ops.argmax_rows(logits_last.contiguous())[:, None]
 
 
 def generate(model: nn.Module, tokenize_text: torch.Tensor, max_new_tokens: Optional[int] = 3,
