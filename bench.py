@@ -356,7 +356,8 @@ def run_ours(args):
         model = VisionLanguageModel(TextCfg(), encoder=Vit(VitCfg()), pos_embedding_type="rope", attention_type="gqa")
     model = model.to(dev).to(torch.bfloat16).train()
     trainer = Trainer(model, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, use_graph=not args.no_graph,
-                      grad_overwrite=not args.no_grad_overwrite, overlap=not args.no_overlap, bucket_mb=args.bucket_mb)
+                      grad_overwrite=not args.no_grad_overwrite, overlap=not args.no_overlap, bucket_mb=args.bucket_mb,
+                      dp_mode=args.dp_mode)
 
     B = PER_GPU_BATCH
     host = [synth_batch(B, 17 + 1000 * rank + i, True) for i in range(2)]
@@ -473,7 +474,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "seq_len": TEXT_LEN + 1,
-                       "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2",
+                       "parallelism": f"dp{world}", "dp_step": trainer.dp_mode, "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2",
                        "dropout": 0.0, "optimizer": "AdamW fp32 master + clip 1.0",
                        "cuda_graph": not args.no_graph, "grad_overwrite": bool(trainer.grad_overwrite)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -503,6 +504,8 @@ def main():
     ap.add_argument("--no-grad-overwrite", action="store_true", help="zero + accumulate every gradient instead of overwrite mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of bucketed overlap")
+    ap.add_argument("--dp-mode", default=None, choices=["p2p", "nccl"],
+                    help="N > 1: p2p = sharded optimizer step over NVLink peer memory (default), nccl = bucketed all-reduce + full AdamW")
     ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient bucket size of the overlapped all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

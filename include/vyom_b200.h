@@ -622,6 +622,57 @@ typedef struct VyAdamW {
 
 VY_API int vy_adamw(const VyAdamW* p);
 
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel optimizer step over NVLink peer memory (one node, <= 8 ranks) — replaces, for the notebooks' training loop
+ * (Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1 main(): DDP gradient all-reduce + clip_grad_norm_(1.0) +
+ * AdamW on every rank), the pair "all-reduce the whole gradient, run the whole optimizer everywhere" by a sharded step
+ * whose kernels read and write the other ranks' buffers directly:
+ *   vy_dp_barrier       device-side rendezvous of the ranks (flags in symmetric memory, generation counted; capturable);
+ *   vy_dp_reduce_shard  gshard[i - lo] = sum_r grad_r[i] for i in [lo, hi) (peer loads, rank order, fp32) and the shard's
+ *                       sum of squares written to slot [rank] of every rank's `scalars`;
+ *   vy_dp_adamw_shard   after a barrier: clip coefficient from the N published partial norms (the norm is that of the MEAN
+ *                       gradient, like clip_grad_norm_ on DDP-averaged gradients), torch.optim.AdamW semantics on the shard
+ *                       with fp32 master weights / moments that exist for the shard only, new parameters stored into EVERY
+ *                       rank's parameter buffer; after one more barrier all ranks hold bit-identical parameters.
+ * All pointer tables are HOST arrays of `world` device pointers that are valid on the calling rank's device (peer-mapped:
+ * cudaIpc / CUDA VMM, e.g. torch.distributed._symmetric_memory). flags: uint32 [world] per rank, zero-initialised; scalars:
+ * float [world] per rank; epoch: local device uint32 (zero-initialised); error_flag: local device int32, raised when a
+ * barrier wait times out (a rank that never arrives) instead of hanging the GPU. */
+typedef struct VyDpGroup {
+  int32_t world, rank;
+  void* const* grads;      /* [world] flat gradient buffers (dtype of the model), or NULL for a barrier-only group */
+  void* const* params;     /* [world] flat parameter buffers */
+  uint32_t* const* flags;  /* [world] barrier flags */
+  float* const* scalars;   /* [world] scalar slots */
+  uint32_t* epoch;
+  int32_t* error_flag;
+} VyDpGroup;
+
+typedef struct VyDpReduce {
+  int64_t lo, hi;   /* this rank's shard of the flat buffers, in elements, multiples of 8 */
+  int32_t dtype;    /* of the gradient buffers */
+  float* gshard;    /* out: fp32 [hi - lo] summed gradient */
+  float* sq_local;  /* out: device scalar, sum of squares of gshard */
+  void* stream;
+} VyDpReduce;
+
+typedef struct VyDpAdamW {
+  int64_t lo, hi;
+  int32_t param_dtype;
+  const float* gshard;
+  float* exp_avg;     /* fp32 [hi - lo] */
+  float* exp_avg_sq;  /* fp32 [hi - lo] */
+  float* master;      /* fp32 [hi - lo] master copy of the shard, or NULL (fp32 parameters) */
+  float lr, beta1, beta2, eps, weight_decay, max_grad_norm; /* max_grad_norm <= 0: no clipping */
+  int32_t step;
+  const int32_t* step_ptr; /* optional device step counter (captured CUDA graphs) */
+  void* stream;
+} VyDpAdamW;
+
+VY_API int vy_dp_barrier(const VyDpGroup* g, void* stream);
+VY_API int vy_dp_reduce_shard(const VyDpGroup* g, const VyDpReduce* p);
+VY_API int vy_dp_adamw_shard(const VyDpGroup* g, const VyDpAdamW* p);
+
 #ifdef __cplusplus
 }
 #endif

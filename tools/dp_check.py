@@ -35,11 +35,16 @@ def main():
     with redirect_stdout(io.StringIO()):
         base = VisionLanguageModel(T(), encoder=Vit(Vc()), pos_embedding_type="rope", attention_type="gqa")
     base = base.to(dev).to(torch.bfloat16).train()
-    models = [base, copy.deepcopy(base), copy.deepcopy(base)]
+    models = [base, copy.deepcopy(base), copy.deepcopy(base), copy.deepcopy(base)]
+    w_init = None
     # tiny buckets (64 KB) so that many boundaries fall inside the model; overlap on / off
-    trainers = [Trainer(models[0], lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, use_graph=False, bucket_mb=0.0625, overlap=True),
-                Trainer(models[1], lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, use_graph=False, bucket_mb=0.0625, overlap=False),
-                Trainer(models[2], lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, use_graph=False, bucket_mb=0.0625, overlap=False)]
+    trainers = [Trainer(models[0], lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, use_graph=False, bucket_mb=0.0625, overlap=True, dp_mode="nccl"),
+                Trainer(models[1], lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, use_graph=False, bucket_mb=0.0625, overlap=False, dp_mode="nccl"),
+                Trainer(models[2], lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, use_graph=False, bucket_mb=0.0625, overlap=False, dp_mode="nccl"),
+                # the peer-memory sharded step (dp_shard.py): no NCCL in the step, fp32 gradient sum
+                Trainer(models[3], lr=1e-3, weight_decay=0.01, max_grad_norm=1.0, use_graph=False, dp_mode="p2p")]
+    assert trainers[3].dp_mode == "p2p", f"symmetric memory unavailable: dp_mode {trainers[3].dp_mode}"
+    w_init = trainers[1].fp.flat.float().clone()
     g = torch.Generator().manual_seed(100 + rank)
     ok = True
     for step in range(3):
@@ -80,7 +85,20 @@ def main():
         lock = torch.equal(ref, trainers[0].fp.flat)
         if rank == 1:
             print(f"   [rank 1] step {step}: parameters equal to rank 0's: {lock}", flush=True)
-        ok &= same and lock
+        # sharded peer-memory step: replicas bit-identical; against the NCCL path the only difference is the gradient sum's
+        # rounding (fp32 here, bf16 inside NCCL), so the UPDATE so far must agree closely
+        ref3 = trainers[3].fp.flat.clone()
+        dist.broadcast(ref3, src=0)
+        lock3 = torch.equal(ref3, trainers[3].fp.flat)
+        trainers[3].shard.check()
+        up_n, up_p = trainers[1].fp.flat.float() - w_init, trainers[3].fp.flat.float() - w_init
+        rel = float((up_p - up_n).norm() / up_n.norm())
+        cos = float(torch.nn.functional.cosine_similarity(up_p, up_n, dim=0))
+        p2p_ok = lock3 and cos > 0.98 and abs(losses[3] - losses[1]) < 0.02
+        if rank == 0:
+            print(f"step {step}: peer-memory sharded step: loss {losses[3]:.5f}; replicas bit-identical: {lock3}; update vs NCCL path: "
+                  f"rel l2 {rel:.3e}, cosine {cos:.5f}", flush=True)
+        ok &= same and lock and p2p_ok
         if rank == 0:
             print(f"step {step}: loss overlap {losses[0]:.5f} / single all-reduce {losses[1]:.5f}; parameters identical to the "
                   f"non-overlapped run: {same} (max diff {d_ab:.3e} in {n_ab} elements; two non-overlapped runs differ by {d_bc:.3e} in {n_bc}); ranks in lock step: {lock}; buckets {len(trainers[0].exchange.buckets)}; "

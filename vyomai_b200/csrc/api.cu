@@ -182,6 +182,9 @@ int vy_abi_sizeof(const char* name) {
   VY_SZ(VyRope);
   VY_SZ(VyDecodeLayer);
   VY_SZ(VyDecodeStep);
+  VY_SZ(VyDpGroup);
+  VY_SZ(VyDpReduce);
+  VY_SZ(VyDpAdamW);
 #undef VY_SZ
   return -1;
 }

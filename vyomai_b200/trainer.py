@@ -54,7 +54,9 @@ class FlatParams:
 
     ALIGN = 8  # elements; keeps every tensor 16-byte aligned for bf16 and fp32
 
-    def __init__(self, model: nn.Module):
+    def __init__(self, model: nn.Module, alloc=None):
+        """`alloc(numel, dtype) -> zero-filled 1-D tensor` places the two buffers (default: ordinary device memory; the
+        peer-memory data-parallel step passes a symmetric-memory allocator)."""
         params = _param_order(model)
         dtypes = {p.dtype for p in params}
         if len(dtypes) != 1:
@@ -69,8 +71,12 @@ class FlatParams:
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
         self.zero_ranges = None  # None: zero_grad clears everything; else the [start, end) slices it must clear
-        self.flat = torch.zeros(off, device=dev, dtype=self.dtype)
-        self.grad = torch.zeros(off, device=dev, dtype=self.dtype)
+        if alloc is None:
+            self.flat = torch.zeros(off, device=dev, dtype=self.dtype)
+            self.grad = torch.zeros(off, device=dev, dtype=self.dtype)
+        else:
+            self.flat = alloc(off, self.dtype)
+            self.grad = alloc(off, self.dtype)
         for p, o in zip(params, self.offsets):
             view = self.flat[o:o + p.numel()].view(p.shape)
             view.copy_(p.data)
@@ -99,14 +105,15 @@ class GradExchange:
     stream so they overlap the rest of backward. Works with any torch.distributed backend (NCCL on
     the B200 box, gloo in the CPU tests)."""
 
-    def __init__(self, flat_grad: torch.Tensor, bucket_elems: int, param_starts: Optional[List[int]] = None):
-        """`param_starts`: offsets at which parameters begin in the flat buffer. Bucket boundaries then snap to them (a
+    def __init__(self, flat_grad: torch.Tensor, bucket_elems: int, param_starts: Optional[List[int]] = None, enabled: bool = True):
+        """`enabled=False`: the gradients are exchanged elsewhere (dp_shard.ShardedStep) and every call here is a no-op.
+        `param_starts`: offsets at which parameters begin in the flat buffer. Bucket boundaries then snap to them (a
         bucket = whole parameters, at least `bucket_elems` elements unless a single parameter is larger), so that
         "every parameter that starts in the bucket is ready" means every element of the bucket has been written — with
         free-running boundaries the tail of a parameter lying in the next bucket would be reduced before backward has
         produced it."""
         self.grad = flat_grad
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size() if enabled and dist.is_available() and dist.is_initialized() else 1
         self.buckets: List[Tuple[int, int]] = []
         cuts = sorted(set(param_starts)) if param_starts else None
         end = flat_grad.numel()
@@ -154,27 +161,55 @@ class Trainer:
 
     def __init__(self, model: nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, bucket_mb: float = 64.0, overlap: bool = True, use_graph: bool = False,
-                 grad_overwrite: bool = True):
+                 grad_overwrite: bool = True, dp_mode: Optional[str] = None):
+        """dp_mode (world size > 1): "p2p" — the sharded optimizer step over NVLink peer memory (dp_shard.py: no NCCL kernel
+        in the step, optimizer state and its traffic divided by the world size); "nccl" — bucketed, overlapped NCCL
+        all-reduce + the full AdamW on every rank. Default: p2p when symmetric memory is available (VY_DP_MODE overrides)."""
         self.model = model
         self.use_graph = use_graph
         self._graph = None
         self._graph_key = None
         self.graph_kernels = 0       # kernels of this library inside the captured step
         self.replayed_kernels = 0    # ... launched so far through graph replays (vy_launch_count only sees eager calls)
-        self.fp = FlatParams(model)
+        from . import dp_shard
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if dp_mode is None:
+            dp_mode = os.environ.get("VY_DP_MODE", "p2p")
+        self.dp_mode = dp_mode if (world > 1 and dp_mode == "p2p" and dp_shard.available()) else ("nccl" if world > 1 else "single")
+        self.shard = None
+        if self.dp_mode == "p2p":
+            dev0 = next(model.parameters()).device
+            alloc = dp_shard.SymmetricAllocator(dev0)
+            ptrs = {}
+
+            def symm_zeros(numel, dtype):
+                t, pp = alloc.zeros(numel, dtype)
+                ptrs[t.data_ptr()] = pp
+                return t
+
+            self.fp = FlatParams(model, alloc=symm_zeros)
+            self.shard = dp_shard.ShardedStep.from_process_group(
+                alloc, self.fp.flat, ptrs[self.fp.flat.data_ptr()], self.fp.grad, ptrs[self.fp.grad.data_ptr()],
+                lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+            overlap = False
+        else:
+            self.fp = FlatParams(model)
         n = self.fp.numel
         dev = self.fp.flat.device
-        self.master = self.fp.flat.to(torch.float32).clone() if self.fp.dtype != torch.float32 else None
-        self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        if self.shard is None:
+            self.master = self.fp.flat.to(torch.float32).clone() if self.fp.dtype != torch.float32 else None
+            self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
+            self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        else:  # optimizer state exists for this rank's shard only (dp_shard.ShardedStep)
+            self.master = self.exp_avg = self.exp_avg_sq = None
         self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         ops.DropoutState.step_ptr = self.step_dev  # dropout masks follow the device step counter (fresh per graph replay)
         self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
         per = max(1, int(bucket_mb * 1024 * 1024 / self.fp.grad.element_size()))
-        self.exchange = GradExchange(self.fp.grad, per, param_starts=list(self.fp.offsets))
-        self.world = self.exchange.world
+        self.exchange = GradExchange(self.fp.grad, per, param_starts=list(self.fp.offsets), enabled=self.shard is None)
+        self.world = world
         self.overlap = overlap and self.world > 1
         self._pending: Dict[int, int] = {}
         self._ready_ids: Set[int] = set()
@@ -274,6 +309,11 @@ class Trainer:
 
     def optimizer_step(self) -> None:
         self._check_gemm_health()
+        if self.shard is not None:
+            self.step_count += 1
+            self.step_dev.add_(1)
+            self.shard.step(self.step_count, self.step_dev)
+            return
         self.exchange.finish()
         self.step_count += 1
         self.step_dev.add_(1)  # device-side step counter: the whole step can live in a replayed CUDA graph
