@@ -63,6 +63,10 @@ VY_API int vy_version(void);
 VY_API const char* vy_last_error(void);
 /* number of kernels this library has launched from the calling process (all threads) */
 VY_API int64_t vy_launch_count(void);
+/* Programmatic dependent launch of this library's kernels (each one triggers its dependents at entry and waits for its
+ * predecessor before touching global memory): on != 0 enables, 0 disables, negative returns to the process default (the
+ * VY_PDL environment variable, off). Returns the previous override (-1 = none). Affects launches made after the call. */
+VY_API int vy_set_pdl(int on);
 /* 1 if the current device is sm_100 (B200), else 0 */
 VY_API int vy_device_ok(void);
 /* sizeof() of the parameter struct called `name` ("VyGemm", ...) as compiled into the library, or -1;
@@ -429,6 +433,10 @@ typedef struct VyDecode {
 
 VY_API int vy_attn_decode(const VyDecode* p);
 VY_API int vy_attn_decode_splits(int B, int n_kv_heads, int start_pos);
+/* kv-splits vy_attn_decode will use for `p` when p->splits == 0 (so that the caller can size workspace: B * n_kv * splits *
+ * n_rep * 66 floats, and tickets: B * n_kv). bf16 caches with contiguous slots (cache_sl == 64, no block table) take the
+ * copy-engine kernel, whose split policy differs from vy_attn_decode_splits' (which the other layouts keep). */
+VY_API int vy_attn_decode_plan(const VyDecode* p);
 
 /* ------------------------------------------------------------------------------------------
  * vy_decode_step — ONE kernel launch per generated token for DecoderModel (bf16): the body of the reference's greedy

@@ -147,7 +147,10 @@ def test_attn_bwd_vs_oracle(case):
 
 @pytest.mark.parametrize("cdt,tol", [(torch.bfloat16, 8e-3), (torch.float32, 2e-5)])
 @pytest.mark.parametrize("case", [(32, 12, 12, 640, 768, 0), (32, 12, 4, 513, 768, 0), (3, 12, 4, 0, 16, 0),
-                                  (2, 12, 12, 5, 16, 1), (1, 8, 1, 300, 384, 0), (4, 12, 4, 100, 128, 3)],
+                                  (2, 12, 12, 5, 16, 1), (1, 8, 1, 300, 384, 0), (4, 12, 4, 100, 128, 3),
+                                  # long contexts: the bf16 copy-engine kernel refills its 3-stage ring (16 / 6 chunks per CTA)
+                                  (2, 12, 4, 2000, 2048, 1), (2, 12, 12, 1500, 1536, 2), (2, 12, 2, 700, 768, 0),
+                                  (3, 8, 4, 129, 256, 0), (2, 16, 4, 128, 256, 1), (1, 12, 4, 1, 8, 0)],
                          ids=lambda c: "B%d_h%d_%d_pos%d_len%d_split%d" % c)
 def test_attn_decode_vs_oracle(case, cdt, tol):
     """Single-token decode: RoPE of q / k at `start`, append to the cache, unmasked attention over [0, start] (quirk Q3).

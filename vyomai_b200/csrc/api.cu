@@ -21,10 +21,22 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Programmatic dependent launch: VY_PDL in the environment is the process default (off: no gain inside the captured TRAINING
+// step, whose kernels are long), vy_set_pdl() overrides it at run time (the captured DECODE step turns it on: ~30 kernels of
+// 4-20 us each, -21 us per step measured, profiles/r02_decode_attn_ab.txt).
+static std::atomic<int> g_pdl_override{-1};
 bool pdl_enabled() {
-  static const bool on = getenv("VY_PDL") && atoi(getenv("VY_PDL")) != 0;  // measured: no gain inside the captured step, so opt-in
-  return on;
+  static const bool env_on = getenv("VY_PDL") && atoi(getenv("VY_PDL")) != 0;
+  const int o = g_pdl_override.load(std::memory_order_relaxed);
+  return o < 0 ? env_on : o != 0;
 }
+
+}  // namespace vy
+extern "C" int vy_set_pdl(int on) {
+  const int prev = vy::g_pdl_override.exchange(on < 0 ? -1 : (on ? 1 : 0));
+  return prev;
+}
+namespace vy {
 
 int num_sms() {
   static int cached[64] = {0};

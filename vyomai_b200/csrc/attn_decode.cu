@@ -47,6 +47,12 @@ struct DecodeDev {
   unsigned int* tickets;  // [B * Hkv], zero on entry, self-resetting
 };
 
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <typename TC>
 __device__ __forceinline__ void load_row8(const TC* p, float (&v)[8]);
 template <>
@@ -66,6 +72,101 @@ __device__ __forceinline__ void load_row8<float>(const float* p, float (&v)[8]) 
   float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// Merges the per-lane-group online-softmax states (m, l, o[8]) of one CTA — lane groups (shuffles), warps (smem), kv-splits
+// (fp32 workspace + last-CTA ticket) — and writes the attention output of the NREP query heads of (b, kvh).
+template <int NREP, int NWARPS>
+__device__ __forceinline__ void decode_finish(const DecodeDev& g, float (&m)[NREP], float (&l)[NREP], float (&o)[NREP][8],
+                                              float (*s_red)[DEC_MAX_REP][HD + 2], int split, int kvh, int b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = lane & 7, lk = lane >> 3;
+  // ---- merge the 4 lane groups of each warp (xor 8, 16) ----
+#pragma unroll
+  for (int r = 0; r < NREP; ++r) {
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m[r], off);
+      const float l2 = __shfl_xor_sync(0xffffffffu, l[r], off);
+      const float mn = fmaxf(m[r], m2);
+      const float a1 = (m[r] == -INFINITY) ? 0.f : exp2f(m[r] - mn);
+      const float a2 = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
+      l[r] = l[r] * a1 + l2 * a2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o2 = __shfl_xor_sync(0xffffffffu, o[r][j], off);
+        o[r][j] = o[r][j] * a1 + o2 * a2;
+      }
+      m[r] = mn;
+    }
+    if (lk == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[warp][r][ld * 8 + j] = o[r][j];
+      if (ld == 0) {
+        s_red[warp][r][HD] = m[r];
+        s_red[warp][r][HD + 1] = l[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- merge warps; thread t < NREP*64 owns (head r, dim j) ----
+  const int t = threadIdx.x;
+  float M = -INFINITY, L = 0.f, O = 0.f;
+  const int r_own = t / HD, j_own = t % HD;
+  for (int rr = r_own; rr < NREP; rr += (NWARPS * 32) / HD) {
+    M = -INFINITY; L = 0.f; O = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      const float mw = s_red[w][rr][HD], lw = s_red[w][rr][HD + 1], ow = s_red[w][rr][j_own];
+      if (mw == -INFINITY) continue;
+      const float mn = fmaxf(M, mw);
+      const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
+      const float a2 = exp2f(mw - mn);
+      L = L * a1 + lw * a2;
+      O = O * a1 + ow * a2;
+      M = mn;
+    }
+    if (g.splits == 1) {
+      st_from_float(g.out, g.out_dtype, static_cast<long long>(b) * g.ld_out + (kvh * NREP + rr) * HD + j_own, O / L);
+    } else {
+      float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + split) * NREP + rr) * (HD + 2));
+      w[j_own] = O;
+      if (j_own == 0) {
+        w[HD] = M;
+        w[HD + 1] = L;
+      }
+    }
+  }
+  if (g.splits == 1) return;
+
+  // ---- last CTA of this (b, kv head) combines the splits ----
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int prev = atomicAdd(&g.tickets[b * g.Hkv + kvh], 1u);
+    s_last = (prev == static_cast<unsigned int>(g.splits - 1)) ? 1u : 0u;
+    if (s_last) g.tickets[b * g.Hkv + kvh] = 0u;  // self-reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int rr = r_own; rr < NREP; rr += (NWARPS * 32) / HD) {
+    M = -INFINITY; L = 0.f; O = 0.f;
+    for (int si = 0; si < g.splits; ++si) {
+      const float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + si) * NREP + rr) * (HD + 2));
+      const float mw = __ldcg(w + HD), lw = __ldcg(w + HD + 1), ow = __ldcg(w + j_own);
+      if (mw == -INFINITY) continue;
+      const float mn = fmaxf(M, mw);
+      const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
+      const float a2 = exp2f(mw - mn);
+      L = L * a1 + lw * a2;
+      O = O * a1 + ow * a2;
+      M = mn;
+    }
+    st_from_float(g.out, g.out_dtype, static_cast<long long>(b) * g.ld_out + (kvh * NREP + rr) * HD + j_own, O / L);
+  }
 }
 
 template <typename TC, int NREP, int NWARPS>
@@ -209,91 +310,216 @@ attn_decode_kernel(const DecodeDev g) {
     }
   }
 
-  // ---- merge the 4 lane groups of each warp (xor 8, 16) ----
+  decode_finish<NREP, NWARPS>(g, m, l, o, s_red, split, kvh, b);
+}
+
+// ---- copy-engine variant: bf16 cache with contiguous slots (slot stride = 64 elements, no block table) ----
+// The key / value rows of one (batch row, kv head) are then ONE contiguous range, so the whole slice of a CTA is requested
+// from HBM up front with bulk copies (cp.async.bulk -> shared memory, mbarrier tx-count) instead of 16-byte loads issued
+// loop iteration by loop iteration: a 16 KB chunk = 128 keys, `stages` chunks of K and of V in flight per CTA (all of a
+// C3-sized context at once), consumed in order and refilled while later chunks are still arriving. The LDG version keeps
+// 128 B per thread in flight and pays one HBM round trip per 128 keys (ncu: 722 GB/s, long_scoreboard-bound).
+constexpr int TD_CHUNK = 128;                       // keys per chunk
+constexpr int TD_CHUNK_BYTES = TD_CHUNK * HD * 2;   // 16 KB of bf16
+constexpr int TD_WARPS = 8;
+constexpr int TD_MAX_STAGES = 6;
+
+template <int NREP>
+__global__ void __launch_bounds__(TD_WARPS * 32)
+attn_decode_tma_kernel(const DecodeDev g, const int stages) {
+  extern __shared__ __align__(128) unsigned char td_smem[];  // [stages][K chunk | V chunk]
+  __shared__ __align__(8) uint64_t s_full[TD_MAX_STAGES];
+  __shared__ __align__(8) uint64_t s_empty[TD_MAX_STAGES];
+  __shared__ float s_newk[HD];
+  __shared__ float s_newv[HD];
+  __shared__ float s_q[DEC_MAX_REP][HD];
+  pdl_trigger();
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = lane & 7, lk = lane >> 3;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], TD_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  const int sp = g.seqlens ? g.seqlens[b] : (g.start_pos_ptr ? *g.start_pos_ptr : g.start_pos);
+  if (sp < 0) return;  // an idle batch slot
+  const __nv_bfloat16* kc = reinterpret_cast<const __nv_bfloat16*>(g.kcache) + b * g.c_sb + kvh * g.c_sh;
+  const __nv_bfloat16* vc = reinterpret_cast<const __nv_bfloat16*>(g.vcache) + b * g.c_sb + kvh * g.c_sh;
+  // cached slots [0, sp) are split evenly; the new token comes from smem (last split), as in the LDG kernel
+  const int per = (sp + g.splits - 1) / g.splits;
+  const int k_begin = split * per;
+  const int k_end = min(sp, k_begin + per);
+  const int nchunks = k_end > k_begin ? (k_end - k_begin + TD_CHUNK - 1) / TD_CHUNK : 0;
+  auto issue = [&](int c) {  // one thread: request chunk c of K and V
+    const int st = c % stages;
+    const int key0 = k_begin + c * TD_CHUNK;
+    const unsigned int bytes = static_cast<unsigned int>(min(TD_CHUNK, k_end - key0)) * (HD * 2);
+    unsigned char* dst = td_smem + static_cast<size_t>(st) * (2 * TD_CHUNK_BYTES);
+    mbar_arrive_expect_tx(&s_full[st], 2 * bytes);
+    bulk_g2s(dst, kc + static_cast<long long>(key0) * HD, bytes, &s_full[st]);
+    bulk_g2s(dst + TD_CHUNK_BYTES, vc + static_cast<long long>(key0) * HD, bytes, &s_full[st]);
+  };
+  if (threadIdx.x == 0) {
+    const int n0 = min(nchunks, stages);
+    for (int c = 0; c < n0; ++c) issue(c);
+  }
+
+  // ---- new token (while the copies fly): bias-added projections -> RoPE(q, k) -> smem; append k, v to the cache ----
+  {
+    const long long row = static_cast<long long>(b) * g.ld_qkv;
+    for (int idx = threadIdx.x; idx < (NREP + 2) * HD; idx += blockDim.x) {
+      const int which = idx / HD;  // 0..NREP-1: q heads, NREP: k, NREP+1: v
+      const int j = idx % HD;
+      int col;
+      if (which < NREP) col = (kvh * NREP + which) * HD;
+      else if (which == NREP) col = (g.Hq + kvh) * HD;
+      else col = (g.Hq + g.Hkv + kvh) * HD;
+      float x = ld_as_float(g.qkv, g.qkv_dtype, row + col + j);
+      if (which <= NREP && g.rope_cos) {
+        const int jj = j & 31;
+        const float other = ld_as_float(g.qkv, g.qkv_dtype, row + col + (j < 32 ? j + 32 : j - 32));
+        const int rr = sp + g.rope_pos_off;
+        const float c = g.rope_cos[rr * 32 + jj], sn = g.rope_sin[rr * 32 + jj];
+        x = j < 32 ? x * c - other * sn : x * c + other * sn;
+      }
+      if (which < NREP) s_q[which][j] = x;
+      else if (which == NREP) s_newk[j] = x;
+      else s_newv[j] = x;
+    }
+  }
+  __syncthreads();
+  if (split == g.splits - 1 && threadIdx.x < HD) {
+    __nv_bfloat16* kw = reinterpret_cast<__nv_bfloat16*>(g.kcache) + b * g.c_sb + kvh * g.c_sh + static_cast<long long>(sp) * HD;
+    __nv_bfloat16* vw = reinterpret_cast<__nv_bfloat16*>(g.vcache) + b * g.c_sb + kvh * g.c_sh + static_cast<long long>(sp) * HD;
+    kw[threadIdx.x] = __float2bfloat16(s_newk[threadIdx.x]);
+    vw[threadIdx.x] = __float2bfloat16(s_newv[threadIdx.x]);
+  }
+
+  float q[NREP][8];
+#pragma unroll
+  for (int r = 0; r < NREP; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[r][j] = s_q[r][ld * 8 + j] * g.scale_log2;
+  float m[NREP], l[NREP], o[NREP][8];
 #pragma unroll
   for (int r = 0; r < NREP; ++r) {
+    m[r] = -INFINITY;
+    l[r] = 0.f;
 #pragma unroll
-    for (int off = 8; off <= 16; off <<= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, m[r], off);
-      const float l2 = __shfl_xor_sync(0xffffffffu, l[r], off);
-      const float mn = fmaxf(m[r], m2);
-      const float a1 = (m[r] == -INFINITY) ? 0.f : exp2f(m[r] - mn);
-      const float a2 = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
-      l[r] = l[r] * a1 + l2 * a2;
+    for (int j = 0; j < 8; ++j) o[r][j] = 0.f;
+  }
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % stages;
+    const unsigned int parity = static_cast<unsigned int>(c / stages) & 1u;
+    mbar_wait(&s_full[st], parity);
+    const int keys = min(TD_CHUNK, k_end - (k_begin + c * TD_CHUNK));
+    const unsigned char* kt = td_smem + static_cast<size_t>(st) * (2 * TD_CHUNK_BYTES);
+    const unsigned char* vt = kt + TD_CHUNK_BYTES;
+    // key (u * 8 + warp) * 4 + lk: a partly filled chunk is still spread over all warps
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float o2 = __shfl_xor_sync(0xffffffffu, o[r][j], off);
-        o[r][j] = o[r][j] * a1 + o2 * a2;
+    for (int u = 0; u < TD_CHUNK / (TD_WARPS * 4); ++u) {
+      const int kidx = (u * TD_WARPS + warp) * 4 + lk;
+      const bool valid = kidx < keys;
+      float kv[8], vv[8];
+      if (valid) {
+        const uint4 kr = *reinterpret_cast<const uint4*>(kt + kidx * (HD * 2) + ld * 16);
+        const uint4 vr = *reinterpret_cast<const uint4*>(vt + kidx * (HD * 2) + ld * 16);
+        const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kr);
+        const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&vr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __bfloat1622float2(kh[k]), bb = __bfloat1622float2(vh[k]);
+          kv[2 * k] = a.x; kv[2 * k + 1] = a.y;
+          vv[2 * k] = bb.x; vv[2 * k + 1] = bb.y;
+        }
       }
+#pragma unroll
+      for (int r = 0; r < NREP; ++r) {
+        float sc = 0.f;
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sc += q[r][j] * kv[j];
+        }
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+        if (valid) {
+          const float mn = fmaxf(m[r], sc);
+          const float a = exp2f(m[r] - mn);
+          const float pp = exp2f(sc - mn);
+          l[r] = l[r] * a + pp;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[r][j] = o[r][j] * a + pp * vv[j];
+          m[r] = mn;
+        }
+      }
+    }
+    if (c + stages < nchunks) {  // the stage is needed again: hand it back, thread 0 refills it once every warp has
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (threadIdx.x == 0) {
+        mbar_wait(&s_empty[st], parity);
+        issue(c + stages);
+      }
+    }
+  }
+  // the new token
+  if (split == g.splits - 1 && warp == 0 && lk == 0) {
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      float sc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sc += q[r][j] * s_newk[ld * 8 + j];
+      sc += __shfl_xor_sync(0x000000ffu, sc, 1);
+      sc += __shfl_xor_sync(0x000000ffu, sc, 2);
+      sc += __shfl_xor_sync(0x000000ffu, sc, 4);
+      const float mn = fmaxf(m[r], sc);
+      const float a = exp2f(m[r] - mn);
+      const float pp = exp2f(sc - mn);
+      l[r] = l[r] * a + pp;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[r][j] = o[r][j] * a + pp * s_newv[ld * 8 + j];
       m[r] = mn;
     }
-    if (lk == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s_red[warp][r][ld * 8 + j] = o[r][j];
-      if (ld == 0) {
-        s_red[warp][r][HD] = m[r];
-        s_red[warp][r][HD + 1] = l[r];
-      }
-    }
   }
+  // every requested chunk has landed and been consumed: the ring now holds the warps' partial results (16.9 KB)
   __syncthreads();
+  float (*s_red)[DEC_MAX_REP][HD + 2] = reinterpret_cast<float (*)[DEC_MAX_REP][HD + 2]>(td_smem);
+  decode_finish<NREP, TD_WARPS>(g, m, l, o, s_red, split, kvh, b);
+}
 
-  // ---- merge warps; thread t < NREP*64 owns (head r, dim j) ----
-  const int t = threadIdx.x;
-  float M = -INFINITY, L = 0.f, O = 0.f;
-  const int r_own = t / HD, j_own = t % HD;
-  for (int rr = r_own; rr < NREP; rr += (NWARPS * 32) / HD) {
-    M = -INFINITY; L = 0.f; O = 0.f;
-#pragma unroll
-    for (int w = 0; w < NWARPS; ++w) {
-      const float mw = s_red[w][rr][HD], lw = s_red[w][rr][HD + 1], ow = s_red[w][rr][j_own];
-      if (mw == -INFINITY) continue;
-      const float mn = fmaxf(M, mw);
-      const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
-      const float a2 = exp2f(mw - mn);
-      L = L * a1 + lw * a2;
-      O = O * a1 + ow * a2;
-      M = mn;
-    }
-    if (g.splits == 1) {
-      st_from_float(g.out, g.out_dtype, static_cast<long long>(b) * g.ld_out + (kvh * NREP + rr) * HD + j_own, O / L);
-    } else {
-      float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + split) * NREP + rr) * (HD + 2));
-      w[j_own] = O;
-      if (j_own == 0) {
-        w[HD] = M;
-        w[HD + 1] = L;
-      }
-    }
+template <int NREP>
+static int launch_decode_tma_r(const DecodeDev& g, int stages, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(stages) * 2 * TD_CHUNK_BYTES;
+  static bool attr_done[64] = {};  // per device: the limit is an attribute of the function in that device's context
+  int dev = 0;
+  VY_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_done[dev]) {
+    VY_CUDA_OK(cudaFuncSetAttribute(attn_decode_tma_kernel<NREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_MAX_STAGES * 2 * TD_CHUNK_BYTES));
+    attr_done[dev] = true;
   }
-  if (g.splits == 1) return;
-
-  // ---- last CTA of this (b, kv head) combines the splits ----
-  __shared__ unsigned int s_last;
-  __threadfence();
-  __syncthreads();
-  if (t == 0) {
-    const unsigned int prev = atomicAdd(&g.tickets[b * g.Hkv + kvh], 1u);
-    s_last = (prev == static_cast<unsigned int>(g.splits - 1)) ? 1u : 0u;
-    if (s_last) g.tickets[b * g.Hkv + kvh] = 0u;  // self-reset for the next launch
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int rr = r_own; rr < NREP; rr += (NWARPS * 32) / HD) {
-    M = -INFINITY; L = 0.f; O = 0.f;
-    for (int si = 0; si < g.splits; ++si) {
-      const float* w = g.ws + ((((static_cast<long long>(b) * g.Hkv + kvh) * g.splits + si) * NREP + rr) * (HD + 2));
-      const float mw = __ldcg(w + HD), lw = __ldcg(w + HD + 1), ow = __ldcg(w + j_own);
-      if (mw == -INFINITY) continue;
-      const float mn = fmaxf(M, mw);
-      const float a1 = (M == -INFINITY) ? 0.f : exp2f(M - mn);
-      const float a2 = exp2f(mw - mn);
-      L = L * a1 + lw * a2;
-      O = O * a1 + ow * a2;
-      M = mn;
-    }
-    st_from_float(g.out, g.out_dtype, static_cast<long long>(b) * g.ld_out + (kvh * NREP + rr) * HD + j_own, O / L);
+  VY_CUDA_OK(launch_kernel(attn_decode_tma_kernel<NREP>, dim3(g.splits, g.Hkv, g.B), dim3(TD_WARPS * 32), smem, st, g, stages));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+static int launch_decode_tma(const DecodeDev& g, int stages, cudaStream_t st) {
+  switch (g.n_rep) {
+    case 1: return launch_decode_tma_r<1>(g, stages, st);
+    case 2: return launch_decode_tma_r<2>(g, stages, st);
+    case 3: return launch_decode_tma_r<3>(g, stages, st);
+    case 4: return launch_decode_tma_r<4>(g, stages, st);
+    case 6: return launch_decode_tma_r<6>(g, stages, st);
+    case 8: return launch_decode_tma_r<8>(g, stages, st);
+    default:
+      set_error("vy_attn_decode: unsupported q-heads per kv-head %d (1,2,3,4,6,8)", g.n_rep);
+      return VY_ERR_UNSUPPORTED;
   }
 }
 
@@ -339,6 +565,43 @@ extern "C" int vy_attn_decode_splits(int B, int Hkv, int start_pos) {
   return splits;
 }
 
+// The copy-engine kernel serves bf16 caches whose slots are contiguous per (row, kv head) and unpaged.
+static bool decode_tma_ok(const VyDecode* p) {
+  static const bool off = getenv("VY_DECODE_ATTN_LDG") && atoi(getenv("VY_DECODE_ATTN_LDG")) != 0;  // development: A/B against the LDG kernel
+  return !off && p->cache_dtype == VY_BF16 && p->block_table == nullptr && p->cache_sl == 64 && p->head_dim == 64;
+}
+// splits / stages of the copy-engine kernel for a context of at most `ctx` cached slots: <= 3 stages (96 KB) lets two CTAs share an
+// SM, so aim for ~2 CTAs per SM; a CTA whose slice is <= 3 chunks then has its whole slice in flight from the start.
+static void decode_tma_plan(int B, int Hkv, int ctx, int* splits, int* stages) {
+  static const int f_splits = getenv("VY_DECODE_TMA_SPLITS") ? atoi(getenv("VY_DECODE_TMA_SPLITS")) : 0;
+  static const int f_stages = getenv("VY_DECODE_TMA_STAGES") ? atoi(getenv("VY_DECODE_TMA_STAGES")) : 0;
+  const int items = B * Hkv, sms = vy::num_sms();
+  const int chunks = ctx > 0 ? (ctx + vy::TD_CHUNK - 1) / vy::TD_CHUNK : 1;
+  // measured on config 3 (profiles/r02_decode_attn_ab.txt): once the (row, kv head) pairs alone cover 3/4 of the SMs a split only
+  // adds the workspace round trip (GQA 128 pairs: 355 us/step unsplit or 2-way, 377 3-way; MHA 384 pairs: 381 unsplit, 399 2-way)
+  int sp = 4 * items >= 3 * sms ? 1 : (2 * sms + items - 1) / items;
+  if (sp > chunks) sp = chunks;
+  if (sp > 32) sp = 32;
+  if (sp < 1) sp = 1;
+  if (f_splits > 0) sp = f_splits > chunks ? chunks : f_splits;
+  const int per_chunks = ((ctx + sp - 1) / sp + vy::TD_CHUNK - 1) / vy::TD_CHUNK;
+  int st = per_chunks < 3 ? (per_chunks < 1 ? 1 : per_chunks) : 3;
+  if (static_cast<long long>(items) * sp <= sms && per_chunks > 3) st = per_chunks < vy::TD_MAX_STAGES ? per_chunks : vy::TD_MAX_STAGES;  // one CTA per SM anyway
+  if (f_stages > 0) st = f_stages > vy::TD_MAX_STAGES ? vy::TD_MAX_STAGES : f_stages;
+  *splits = sp;
+  *stages = st;
+}
+
+extern "C" int vy_attn_decode_plan(const VyDecode* p) {
+  if (!p || p->B <= 0 || p->n_kv_heads <= 0) return 1;
+  if (decode_tma_ok(p)) {
+    int sp, st;
+    decode_tma_plan(p->B, p->n_kv_heads, p->start_pos, &sp, &st);
+    return sp;
+  }
+  return vy_attn_decode_splits(p->B, p->n_kv_heads, p->start_pos);
+}
+
 extern "C" int vy_attn_decode(const VyDecode* p) {
   using namespace vy;
   VY_CHECK_ARG(p != nullptr, "vy_attn_decode: null params");
@@ -367,7 +630,17 @@ extern "C" int vy_attn_decode(const VyDecode* p) {
   VY_CHECK_ARG((reinterpret_cast<uintptr_t>(p->k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->v_cache) & 15) == 0 &&
                    (p->cache_sb * es) % 16 == 0 && (p->cache_sh * es) % 16 == 0 && (p->cache_sl * es) % 16 == 0,
                "vy_attn_decode: cache pointers/strides must keep 16-byte alignment");
-  int splits = p->splits > 0 ? p->splits : vy_attn_decode_splits(p->B, p->n_kv_heads, p->start_pos);
+  const bool tma = decode_tma_ok(p);
+  int splits = p->splits > 0 ? p->splits : vy_attn_decode_plan(p);
+  int stages = 0;
+  if (tma) {
+    int sp0;
+    decode_tma_plan(p->B, p->n_kv_heads, p->start_pos, &sp0, &stages);
+    if (splits != sp0) {  // the caller pinned another split: size the ring for its slice
+      const int per_chunks = ((p->start_pos + splits - 1) / splits + TD_CHUNK - 1) / TD_CHUNK;
+      stages = per_chunks < 1 ? 1 : (per_chunks > 3 ? 3 : per_chunks);
+    }
+  }
   if (splits > 1) VY_CHECK_ARG(p->workspace && p->tickets, "vy_attn_decode: split-kv needs workspace and tickets");
 
   DecodeDev g;
@@ -390,6 +663,7 @@ extern "C" int vy_attn_decode(const VyDecode* p) {
   g.scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
   g.ws = p->workspace; g.tickets = reinterpret_cast<unsigned int*>(p->tickets);
   cudaStream_t st = static_cast<cudaStream_t>(p->stream);
+  if (tma) return launch_decode_tma(g, stages, st);
   if (p->cache_dtype == VY_BF16) return launch_decode<__nv_bfloat16>(g, st);
   return launch_decode<float>(g, st);
 }

@@ -8,9 +8,11 @@ once and replayed; the host only enqueues replays and looks at the eos flags eve
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
-from . import decode_step
+from . import _lib, decode_step
 from . import functional as F
 from . import ops
 
@@ -68,8 +70,16 @@ class GreedyDecodeGraph:
         self.pos.copy_(pos0)
         self.tok.copy_(tok0)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
-            self._step()
+        # the step is a chain of ~30 short kernels: programmatic dependent launch lets each one's prologue overlap its
+        # predecessor's tail (-21 us per step, profiles/r02_decode_attn_ab.txt). VY_DECODE_PDL=0 keeps plain stream order.
+        pdl = os.environ.get("VY_DECODE_PDL", "1") != "0"
+        prev = _lib.lib().vy_set_pdl(1) if pdl else None
+        try:
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self._step()
+        finally:
+            if pdl:
+                _lib.lib().vy_set_pdl(prev)
         self.pos.copy_(pos0)
         self.tok.copy_(tok0)
 

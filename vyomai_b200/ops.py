@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import ctypes
+
 import torch
 
 from . import _lib, gemm_tune
@@ -449,15 +451,7 @@ def attn_decode(
         c_sb, c_sh, c_sl = k_cache.stride(0), k_cache.stride(1), k_cache.stride(2)
     if out is None:
         out = torch.empty((B, n_q_heads * D), device=qkv.device, dtype=out_dtype or qkv.dtype)
-    L = _lib.lib()
-    if splits <= 0:
-        splits = L.vy_attn_decode_splits(B, n_kv_heads, start_pos)
-    ws = tk = None
-    if splits > 1:
-        ws = torch.empty(B * n_kv_heads * splits * (n_q_heads // n_kv_heads) * 66, device=qkv.device, dtype=torch.float32)
-        tk = _tickets(qkv.device, B * n_kv_heads)
-    _lib.call(
-        "vy_attn_decode", "VyDecode",
+    kw = dict(
         B=B, n_q_heads=n_q_heads, n_kv_heads=n_kv_heads, head_dim=D, start_pos=start_pos,
         cache_len=cache_len, qkv=qkv.data_ptr(), ld_qkv=qkv.stride(0), qkv_dtype=_dt(qkv),
         rope_cos=_ptr(rope_cos), rope_sin=_ptr(rope_sin), rope_pos_off=rope_pos_off,
@@ -465,9 +459,19 @@ def attn_decode(
         cache_sb=c_sb, cache_sh=c_sh, cache_sl=c_sl, cache_dtype=_dt(k_cache),
         seqlens=_ptr(seqlens), block_table=_ptr(block_table),
         max_blocks_per_seq=block_table.shape[1] if paged else 0, block_size=block_size,
-        out=out.data_ptr(), ld_out=out.stride(0), out_dtype=_dt(out), splits=splits, workspace=_ptr(ws),
-        tickets=_ptr(tk), start_pos_ptr=_ptr(start_pos_dev), stream=_stream(),
+        out=out.data_ptr(), ld_out=out.stride(0), out_dtype=_dt(out), start_pos_ptr=_ptr(start_pos_dev), stream=_stream(),
     )
+    if splits <= 0:  # the library's own choice for this layout (copy-engine kernel or LDG kernel)
+        st = _lib.STRUCTS["VyDecode"]()
+        for k, v in kw.items():
+            if v is not None:
+                setattr(st, k, v)
+        splits = _lib.lib().vy_attn_decode_plan(ctypes.byref(st))
+    ws = tk = None
+    if splits > 1:
+        ws = torch.empty(B * n_kv_heads * splits * (n_q_heads // n_kv_heads) * 66, device=qkv.device, dtype=torch.float32)
+        tk = _tickets(qkv.device, B * n_kv_heads)
+    _lib.call("vy_attn_decode", "VyDecode", splits=splits, workspace=_ptr(ws), tickets=_ptr(tk), **kw)
     return out
 
 
