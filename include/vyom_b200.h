@@ -110,6 +110,11 @@ VY_API int vy_abi_sizeof(const char* name);
  * "b l (h d) -> b h l d" rearrange (attention.py:118-120) and the kv-cache append
  * (kv_cache.py:355-359) are fused into the projection. k/v rows are written at token index
  * kv_dst_pos0 + l (= start_pos for a cache, 0 for a fresh buffer); q rows at l.
+ *
+ * Small batches (transposed_out, N <= 32 activation rows, bf16, K-major operands, K / s a multiple of 128 and <= 768 for
+ * some s <= 8, act NONE / GELU_*, no aux / addend2 / row remaps) do not use the tensor-memory kernel at
+ * all: csrc/gemm_skinny.cu streams the weights once through 150-400 CTAs (16 features x K / s each, mma.sync, partial sums
+ * combined through the shared memory of a thread-block cluster). VY_GEMM_SKINNY=0 in the environment disables it.
  * ------------------------------------------------------------------------------------------ */
 typedef struct VyGemm {
   int32_t M, N, K;
@@ -177,10 +182,18 @@ typedef struct VyGemm {
   int32_t hint_bn;      /* 32, 64, 128, 192 or 256 */
   int32_t hint_splits;  /* K splits, 1..8 */
 
+  /* Non-zero: the K-major weight operand (A in the swap-AB / transposed_out form) is not written by any kernel still in
+   * flight on this stream. The small-batch kernel (N <= 32 activation rows, bf16) then requests the weights BEFORE it
+   * waits for its predecessor under programmatic dependent launch (vy_set_pdl). Leave 0 when an optimizer step may
+   * immediately precede the call. */
+  int32_t weights_static;
+
   void* stream;
 } VyGemm;
 
 VY_API int vy_gemm(const VyGemm* p);
+/* 1 if vy_gemm would serve `p` with the small-batch weight-streaming kernel (tiling hints do not apply to it), else 0 */
+VY_API int vy_gemm_is_small_batch(const VyGemm* p);
 /* Self-check of the GEMM kernels' barrier protocol: a wait inside a kernel that times out raises a device flag instead
  * of faulting, and the launch finishes with undefined results. Returns the flag (0 = every vy_gemm so far ran its
  * protocol to completion, 1 = some launch did not, -1 = the flag could not be read); a raised flag is lowered by the

@@ -347,6 +347,37 @@ def test_gemm_epilogues_vs_oracle(dtype, tol):
     assert bool((outb.view(Bn, P + 1, Hd)[:, 0] == 0).all())
 
 
+@pytest.mark.parametrize("case", [(32, 768, 768), (32, 1280, 768), (32, 3072, 768), (32, 768, 3072), (32, 50265, 768), (1, 768, 768),
+                                  (7, 1000, 256), (17, 40, 128), (24, 2048, 2048), (9, 776, 1536)],
+                         ids=lambda c: "n%d_F%d_K%d" % c)
+def test_small_batch_gemm_vs_oracle(case):
+    """The weight-streaming kernel behind swap-AB vy_gemm calls with <= 32 activation rows (csrc/gemm_skinny.cu): bias, both
+    GELUs, residual addend, bf16 / fp32 outputs, out_scale, strided output, feature counts that are no multiple of 16 — against
+    the oracle's linear / gelu, and bit-for-bit run to run (cluster reduction in fixed rank order)."""
+    import ctypes
+    from vyomai_b200 import _lib, ops
+    n, F, K = case
+    dt = torch.bfloat16
+    x, w, bias, res = _randn((n, K), 40, dt), _randn((F, K), 41, dt, K ** -0.5), _randn((F,), 42, dt), _randn((n, F), 43, dt)
+    xd, wd, bd, rd = (t.to(dt).to(DEV) for t in (x, w, bias, res))
+    z = O.linear(x, w, bias)
+    with torch.no_grad():
+        o1 = ops.gemm(xd, wd, bias=bd, swap_ab=True, out_dtype=torch.float32)
+        assert rel_l2(o1.cpu(), z) <= 2e-3
+        o2 = ops.gemm(xd, wd, bias=bd, act="gelu", addend=rd, swap_ab=True)
+        assert rel_l2(o2.float().cpu(), O.gelu_erf(z) + res) <= 6e-3
+        o3 = ops.gemm(xd, wd, act="gelu_tanh", swap_ab=True, out_dtype=torch.float32, out_scale=0.5)
+        assert rel_l2(o3.cpu(), 0.5 * O.gelu_tanh(O.linear(x, w, None))) <= 2e-3
+        wide = torch.full((n, F + 24), 7.0, device=DEV, dtype=torch.float32)  # strided output: columns beyond F untouched
+        ops.gemm(xd, wd, bias=bd, addend=res.to(DEV), swap_ab=True, out=wide[:, :F])
+        assert rel_l2(wide[:, :F].cpu(), z + res) <= 2e-3 and bool((wide[:, F:] == 7.0).all())
+        assert torch.equal(o1, ops.gemm(xd, wd, bias=bd, swap_ab=True, out_dtype=torch.float32))
+    # this call is served by the small-batch kernel (not the tensor-memory tiles)
+    st = _lib.STRUCTS["VyGemm"]()
+    st.M, st.N, st.K, st.in_dtype, st.transposed_out = F, n, K, _lib.CONSTS["VY_BF16"], 1
+    assert _lib.lib().vy_gemm_is_small_batch(ctypes.byref(st)) == 1
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_apply_rotary_pos_emb_public_helper(dtype):
     """The stand-alone apply_rotary_pos_emb(q, k, freqs) of layers/positional_embeddings.py (vy_rope_apply) against the

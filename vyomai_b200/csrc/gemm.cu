@@ -214,6 +214,11 @@ extern "C" int vy_gemm_tune_override(int pair, int bn, int splits) {
   return VY_OK;
 }
 
+namespace vy {
+bool skinny_applicable(const VyGemm* p);  // gemm_skinny.cu
+int launch_skinny(const VyGemm* p);
+}  // namespace vy
+
 extern "C" int vy_gemm_poisoned(void) {
   using namespace vy;
   PoisonSlot* f = poison_slot();
@@ -334,6 +339,10 @@ extern "C" int vy_gemm(const VyGemm* p) {
     set_error("vy_gemm: unknown epilogue %d", p->epi);
     return VY_ERR_INVALID_ARG;
   }
+
+  // at most 32 activation rows against a K-major weight (the projections of a decode step): weight-streaming kernel of
+  // gemm_skinny.cu instead of 128-row tcgen05 tiles
+  if (skinny_applicable(p)) return launch_skinny(p);
 
   // TMA-store write-back for the fast (all-bf16, 16-byte aligned, no row remap) epilogues; VY_GEMM_TMA_STORE=0 keeps st.global
   static const bool tma_store_on = !(getenv("VY_GEMM_TMA_STORE") && atoi(getenv("VY_GEMM_TMA_STORE")) == 0);

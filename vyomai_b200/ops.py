@@ -80,6 +80,17 @@ def _splitk_workspace(device: torch.device) -> torch.Tensor:
     return t
 
 
+def _small_batch(kw: dict) -> bool:
+    """True when vy_gemm will route this call to the small-batch weight-streaming kernel (nothing to tune there)."""
+    if not kw.get("transposed_out") or kw["N"] > 32:
+        return False
+    st = _lib.STRUCTS["VyGemm"]()
+    for k, v in kw.items():
+        if v is not None:
+            setattr(st, k, v)
+    return bool(_lib.lib().vy_gemm_is_small_batch(ctypes.byref(st)))
+
+
 def gemm(
     a: torch.Tensor,
     b: torch.Tensor,
@@ -158,9 +169,10 @@ def gemm(
         kw.update(M=M, N=N, K=K, A=a.data_ptr(), lda=lda, a_mn_major=a_mn, B=b.data_ptr(), ldb=ldb,
                   b_mn_major=b_mn, transposed_out=0)
     else:
+        # inference (no autograd): nothing in flight writes the weights, so the small-batch kernel may prefetch them under PDL
         kw.update(M=N, N=M, K=K, A=b.data_ptr(), lda=ldb, a_mn_major=b_mn, B=a.data_ptr(), ldb=lda,
-                  b_mn_major=a_mn, transposed_out=1)
-    if gemm_tune.ENABLED:
+                  b_mn_major=a_mn, transposed_out=1, weights_static=0 if torch.is_grad_enabled() else 1)
+    if gemm_tune.ENABLED and not _small_batch(kw):
         key = ("gemm", kw["M"], kw["N"], K, kw["in_dtype"], kw["a_mn_major"], kw["b_mn_major"], kw["transposed_out"], act,
                bias is not None, addend is not None, addend is not None and addend.data_ptr() == out.data_ptr(),
                addend2 is not None, aux is not None, out.dtype, allow_split_k, out_row_group, addend_row_mod, out_scale != 1.0)
