@@ -214,6 +214,9 @@ bool skinny_applicable(const VyGemm* p) {
   if (p->epi != VY_EPI_LINEAR || p->in_dtype != VY_BF16 || !p->transposed_out || p->a_mn_major || p->b_mn_major) return false;
   if (p->N > 32 || p->aux || p->addend2 || p->addend_row_mod || p->out_row_group) return false;
   if (p->act != VY_ACT_NONE && p->act != VY_ACT_GELU_ERF && p->act != VY_ACT_GELU_TANH) return false;
+  // one wave of small CTAs is the whole point; a vocabulary-sized F (3142 feature blocks) would run ~4 latency-bound waves of
+  // them and measured 2x slower than the 128-row tensor-memory tiles, which stream 77 MB at 3.5 TB/s
+  if ((p->M + 15) / 16 > 4 * num_sms()) return false;
   return skinny_ksplit(p->M, p->K) > 0;
 }
 
