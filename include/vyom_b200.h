@@ -383,6 +383,16 @@ VY_API int vy_act_bwd(int64_t n, const void* dy, const void* z, int dtype, int a
  * written (loss.backward() passes 1, a scaled or accumulated loss does not). */
 VY_API int vy_scale_by_ptr(int64_t n, void* x, int dtype, const float* scale, void* stream);
 
+/* vy_slot_merge_fwd / _bwd — `inputs_embeds.masked_scatter(input_ids == image_token_index, image_features)` of the notebook-II
+ * captioner (Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1, VisionLanguageModel.forward) and its autograd:
+ *   fwd: out[r, :] = slot[r] >= 0 ? b[slot[r], :] : a[r, :]         (a: word-embedding rows, b: image-feature rows)
+ *   bwd: da[r, :] = slot[r] >= 0 ? 0 : dout[r, :];   db[slot[r], :] = dout[r, :]     (da or db may be NULL)
+ * slot[r] is the running count of image tokens before row r (masked_scatter consumes source rows in row-major order) or
+ * -1; every b row is used at most once, rows of db no slot points at are left untouched (zero them first). All buffers
+ * are row-contiguous [rows or n_b, H]; H * sizeof(dtype) % 16 == 0. */
+VY_API int vy_slot_merge_fwd(int rows, int H, int dtype, const void* a, const void* b, const int32_t* slot, void* out, void* stream);
+VY_API int vy_slot_merge_bwd(int rows, int H, int dtype, const void* dout, const int32_t* slot, void* da, void* db, void* stream);
+
 /* vy_swiglu_bwd — gradient of h[r, j] = silu(z[r, 2j]) * z[r, 2j+1] w.r.t. the interleaved pre-activations:
  * dz[r, 2j] = dh[r, j] * z[r, 2j+1] * silu'(z[r, 2j]), dz[r, 2j+1] = dh[r, j] * silu(z[r, 2j]); dz then feeds the
  * ordinary dgrad / wgrad GEMMs against the interleaved weight. dh [rows, I], z / dz [rows, 2 I], contiguous, I % 8 == 0. */

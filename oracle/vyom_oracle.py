@@ -676,3 +676,64 @@ def seq2seq_generate(sd, enc_cfg, dec_cfg, encoder_output: Tensor, encoder_atten
         idx = torch.cat((idx, idx_next), dim=1)
         index = idx.shape[1] - 1
     return idx
+
+
+# ---------------------------------------------------------------------------------------------
+# Image-slot captioner (Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1: "Multimodal-II")
+# ---------------------------------------------------------------------------------------------
+def slot_update_causal_mask(attention_mask: Tensor, seqlen: int, cache_position: Tensor, is_training: bool, dtype) -> Tensor:
+    """`_update_causal_mask` of the notebook: a (seqlen, T) sheet of finfo.min, T = attention_mask.shape[-1]; for seqlen > 1
+    its upper triangle only (training) or its first seqlen columns cleared (inference: "attend to the whole prefix"); then
+    multiplied by [column > cache_position[row]]; then every column whose attention_mask is 0 is set to finfo.min wherever
+    the sheet was 0. Returns (B, 1, seqlen, T)."""
+    mn = torch.finfo(dtype).min
+    T = attention_mask.shape[-1]
+    sheet = torch.full((seqlen, T), mn, dtype=dtype)
+    if seqlen != 1:
+        if is_training:
+            sheet = torch.triu(sheet, diagonal=1)
+        else:
+            sheet[:, :seqlen] = 0.0
+    sheet = sheet * (torch.arange(T) > cache_position.reshape(-1, 1))
+    sheet = sheet[None, None].expand(attention_mask.shape[0], 1, -1, -1).clone()
+    pad = (sheet + attention_mask[:, None, None, :].to(dtype)) == 0
+    return sheet.masked_fill(pad, mn)
+
+
+def slot_vlm_forward(sd: SD, cfg: Cfg, image_features: Optional[Tensor], input_ids: Tensor, attention_mask: Tensor,
+                     is_training: bool, image_token_index: int = 128001, attention_type=None, cache=None,
+                     start_pos: int = 0) -> Tensor:
+    """VisionLanguageModel.forward of the notebook (cell 1): word embeddings, `masked_scatter` of the image-feature rows into
+    the `<image>` positions (source rows consumed in row-major order over the batch), the mask above, RoPE decoder layers
+    (positions start_pos..), LM head `vocab(LN(gelu(dense(h))))`. `image_features` [B, n, H] = encoder(...).last_hidden_state,
+    None on cached single-token steps."""
+    h = sd["decoder.word_embeddings.weight"][input_ids]
+    bsz, seqlen = input_ids.shape
+    if image_features is not None:
+        is_img = input_ids == image_token_index
+        src = image_features.reshape(-1, image_features.shape[-1]).to(h.dtype)
+        n = int(is_img.sum())
+        assert n <= src.shape[0], "masked_scatter: source shorter than the mask"
+        h = h.clone()
+        h[is_img] = src[:n]
+        cache_position = torch.arange(seqlen)
+    else:
+        cache_position = torch.arange(seqlen) if is_training else torch.arange(start_pos, start_pos + seqlen)
+    mask = slot_update_causal_mask(attention_mask, seqlen, cache_position, is_training, h.dtype)
+    freqs = rope_freqs(cfg.max_position_embeddings, cfg.head_dim)[:, start_pos:start_pos + seqlen]
+    for i in range(cfg.num_hidden_layers):
+        # (the attention slices the mask to the keys it actually has: attention_mask[:, :, :, :k.shape[-2]])
+        skv = start_pos + seqlen if cache is not None else seqlen
+        h = transformer_layer(sd, f"decoder.all_layer.{i}.", h, mask[..., :skv], freqs, cfg, attention_type, cache=cache,
+                              layer_idx=i, start_pos=start_pos)
+    return seq2seq_lm_head(sd, h, cfg.layer_norm_eps)
+
+
+def slot_loss(logits: Tensor, input_ids: Tensor, attention_mask: Tensor, pad_token_id: int, image_token_index: int = 128001) -> Tensor:
+    """main() + loss_fn of the notebook: labels = input_ids with `<image>` and pad ids set to -100; logits[:, :-1] against
+    labels[:, 1:] at the positions where attention_mask[:, 1:] != 0; CrossEntropyLoss(ignore_index=-100) mean."""
+    labels = input_ids.masked_fill(input_ids == image_token_index, -100)
+    labels = torch.where(input_ids == pad_token_id, torch.full_like(labels, -100), labels)
+    sl, lb = logits[:, :-1], labels[:, 1:]
+    sel = attention_mask[:, 1:] != 0
+    return torch.nn.functional.cross_entropy(sl[sel].float(), lb[sel], ignore_index=-100)

@@ -9,6 +9,7 @@ from .models.encoder import EncoderModel, EncoderForMaskedLM  # noqa: F401
 from .models.decoder import DecoderModel  # noqa: F401
 from .models.vision_encoder import Vit  # noqa: F401
 from .models.multimodel import VisionLanguageModel  # noqa: F401
+from .models.multimodel_slots import ImageSlotVisionLanguageModel, slot_caption_labels  # noqa: F401  (notebook-II captioner)
 from .models.encoder_decoder import EncoderDecoderModel, Seq2SeqDecoderModel  # noqa: F401
 from .layers.adapters import DoraLinear, LoraLinear  # noqa: F401
 from .generation_utils import generate, generate_multimodel, generate_seq2seq  # noqa: F401

@@ -117,6 +117,30 @@ def embed_fn(ids: torch.Tensor, table: torch.Tensor, pos_table: Optional[torch.T
     return EmbedFn.forward(_NoCtx(), ids, table, pos_table, pos_row_off, tokens_per_seq, extra, padding_idx, pos_padding_idx)
 
 
+class SlotMergeFn(torch.autograd.Function):
+    """rows = where(slot >= 0, image_rows[slot], word_rows): the masked_scatter of image features into the <image> token
+    positions (Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1, VisionLanguageModel.forward). Gradients: the word
+    rows get dout with the image positions zeroed (masked_scatter overwrote them), the image rows get their dout rows."""
+
+    @staticmethod
+    def forward(ctx, word_rows, image_rows, slot):
+        ctx.save_for_backward(slot)
+        ctx.n_img = image_rows.shape[0]
+        return ops.slot_merge(word_rows.contiguous(), image_rows.contiguous(), slot)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (slot,) = ctx.saved_tensors
+        da, db = ops.slot_merge_bwd(dout.contiguous(), slot, ctx.n_img, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return da, db, None
+
+
+def slot_merge_fn(word_rows: torch.Tensor, image_rows: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
+    if _needs_grad(word_rows, image_rows):
+        return SlotMergeFn.apply(word_rows, image_rows, slot)
+    return ops.slot_merge(word_rows.contiguous(), image_rows.contiguous(), slot)
+
+
 class _NoCtx:
     """Stand-in ctx so a Function's forward can be reused on the no-grad path without autograd."""
 

@@ -527,6 +527,28 @@ adamw_kernel(long long n, void* __restrict__ p, int p_dt, const void* __restrict
   }
 }
 
+// ---- image-slot merge (the notebook-II captioner): rows whose slot index is >= 0 come from `b`, the others from `a` ----
+// fwd: out[r] = slot[r] >= 0 ? b[slot[r]] : a[r].   bwd: da[r] = slot[r] >= 0 ? 0 : dout[r];  db[slot[r]] = dout[r].
+// One 16-byte vector per thread; rows are H elements (H % 8 == 0 for bf16, % 4 for fp32), all buffers row-contiguous.
+__global__ void __launch_bounds__(256)
+slot_merge_kernel(int rows, int vec_per_row, const uint4* __restrict__ a, const uint4* __restrict__ b, const int* __restrict__ slot,
+                  uint4* __restrict__ out, uint4* __restrict__ da, uint4* __restrict__ db, int backward) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = static_cast<long long>(rows) * vec_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / vec_per_row), c = static_cast<int>(i - static_cast<long long>(r) * vec_per_row);
+    const int sl = slot[r];
+    if (!backward) {
+      out[i] = sl >= 0 ? b[static_cast<long long>(sl) * vec_per_row + c] : a[i];
+    } else {
+      const uint4 g = a[i];  // (a = dout)
+      if (da) da[i] = sl >= 0 ? make_uint4(0, 0, 0, 0) : g;
+      if (db && sl >= 0) db[static_cast<long long>(sl) * vec_per_row + c] = g;
+    }
+  }
+}
+
 // stand-alone half-split RoPE: one warp per (b, h, l) row, lane j <-> pair (j, j + 32)
 __global__ void __launch_bounds__(256)
 rope_kernel(int B, int H, int S, const void* __restrict__ x, long long xsb, long long xsh, long long xsl, int dt,
@@ -812,6 +834,34 @@ extern "C" int vy_scale_by_ptr(int64_t n, void* x, int dtype, const float* scale
   VY_CHECK_ARG(n > 0 && x && scale && dtype_ok(dtype) && aligned16(x), "vy_scale_by_ptr: bad arguments (x 16-byte aligned)");
   VY_CUDA_OK(launch_kernel(scale_by_ptr_kernel, dim3(ew_grid(n, 8 * 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
                            static_cast<long long>(n), x, dtype, scale));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_slot_merge_fwd(int rows, int H, int dtype, const void* a, const void* b, const int32_t* slot, void* out, void* stream) {
+  VY_NEED_DEVICE("vy_slot_merge_fwd");
+  VY_CHECK_ARG(rows > 0 && H > 0 && dtype_ok(dtype) && a && b && slot && out && aligned16(a) && aligned16(b) && aligned16(out) &&
+                   (static_cast<long long>(H) * dtype_size(dtype)) % 16 == 0,
+               "vy_slot_merge_fwd: bad arguments (row bytes and pointers must be multiples of 16)");
+  const int vpr = static_cast<int>(static_cast<long long>(H) * dtype_size(dtype) / 16);
+  VY_CUDA_OK(launch_kernel(slot_merge_kernel, dim3(ew_grid(static_cast<long long>(rows) * vpr, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, vpr,
+                           static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<const int*>(slot), static_cast<uint4*>(out),
+                           static_cast<uint4*>(nullptr), static_cast<uint4*>(nullptr), 0));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_slot_merge_bwd(int rows, int H, int dtype, const void* dout, const int32_t* slot, void* da, void* db, void* stream) {
+  VY_NEED_DEVICE("vy_slot_merge_bwd");
+  VY_CHECK_ARG(rows > 0 && H > 0 && dtype_ok(dtype) && dout && slot && (da || db) && aligned16(dout) && aligned16(da) && aligned16(db) &&
+                   (static_cast<long long>(H) * dtype_size(dtype)) % 16 == 0,
+               "vy_slot_merge_bwd: bad arguments (row bytes and pointers must be multiples of 16)");
+  const int vpr = static_cast<int>(static_cast<long long>(H) * dtype_size(dtype) / 16);
+  VY_CUDA_OK(launch_kernel(slot_merge_kernel, dim3(ew_grid(static_cast<long long>(rows) * vpr, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, vpr,
+                           static_cast<const uint4*>(dout), static_cast<const uint4*>(nullptr), static_cast<const int*>(slot),
+                           static_cast<uint4*>(nullptr), static_cast<uint4*>(da), static_cast<uint4*>(db), 1));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -72,6 +72,11 @@ class LMHead(nn.Module):
         logits = lm_head_fn(self, hidden_state.reshape(-1, shape[-1]))
         return logits.view(*shape[:-1], logits.shape[-1])
 
+    def loss(self, hidden_state: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+        """Token cross-entropy of self(hidden) against `labels` (one per hidden row) with the head and the loss fused."""
+        from ..autograd import lm_head_loss_fn
+        return lm_head_loss_fn(self, hidden_state.reshape(-1, hidden_state.shape[-1]), labels, ignore_index)
+
 
 class Seq2SeqDecoderModel(nn.Module, TextStem):
     """Seq2Seq decoder model (reference: models/encoder_decoder.py:116-278)"""

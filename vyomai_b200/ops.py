@@ -662,6 +662,33 @@ def scale_by_ptr(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def slot_merge(a: torch.Tensor, b: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
+    """out[r] = b[slot[r]] where slot[r] >= 0, else a[r] (masked_scatter of image-feature rows into embedding rows)."""
+    _need_cuda(a, b, slot)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1] or a.dtype != b.dtype or not (a.is_contiguous() and b.is_contiguous()):
+        raise _lib.VyomError("slot_merge: a [rows, H] and b [n, H] must be contiguous 2-D tensors of one dtype")
+    if slot.dtype != torch.int32 or not slot.is_contiguous() or slot.numel() != a.shape[0]:
+        raise _lib.VyomError("slot_merge: slot must be a contiguous int32 tensor with one entry per row of a")
+    out = torch.empty_like(a)
+    _lib.check(_lib.lib().vy_slot_merge_fwd(a.shape[0], a.shape[1], _dt(a), a.data_ptr(), b.data_ptr(), slot.data_ptr(), out.data_ptr(),
+                                           _stream()), "vy_slot_merge_fwd")
+    return out
+
+
+def slot_merge_bwd(dout: torch.Tensor, slot: torch.Tensor, n_b: int, need_a: bool = True, need_b: bool = True):
+    """(da, db) for slot_merge: da = dout with the slot rows zeroed, db[slot[r]] = dout[r] (rows no slot points at are zero)."""
+    _need_cuda(dout, slot)
+    if dout.dim() != 2 or not dout.is_contiguous():
+        raise _lib.VyomError("slot_merge_bwd: dout must be a contiguous 2-D tensor")
+    da = torch.empty_like(dout) if need_a else None
+    db = torch.zeros((n_b, dout.shape[1]), device=dout.device, dtype=dout.dtype) if need_b else None
+    if da is None and db is None:
+        return None, None
+    _lib.check(_lib.lib().vy_slot_merge_bwd(dout.shape[0], dout.shape[1], _dt(dout), dout.data_ptr(), slot.data_ptr(), _ptr(da), _ptr(db),
+                                           _stream()), "vy_slot_merge_bwd")
+    return da, db
+
+
 def swiglu_bwd(dh: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     """dz for h = silu(z[:, 0::2]) * z[:, 1::2] (the act="swiglu" epilogue of gemm): dh [rows, I], z [rows, 2 I]."""
     _need_cuda(dh, z)

@@ -237,6 +237,7 @@ class Trainer:
         checks the "exactly once" premise on the first step by poisoning the buffer."""
         from .layers.ffn import FeedForward
         from .models._common import LMHead
+        from .models.encoder_decoder import LMHead as LMHeadVocab  # same head, projection named `vocab`
         marked = set()
 
         def mark(*ps):
@@ -253,7 +254,7 @@ class Trainer:
             elif isinstance(mod, FeedForward):
                 mark(mod.intermediate.weight, mod.intermediate.bias, mod.out.weight, mod.out.bias, mod.layernorm.weight,
                      mod.layernorm.bias)
-            elif isinstance(mod, LMHead):
+            elif isinstance(mod, (LMHead, LMHeadVocab)):
                 mark(mod.dense.weight, mod.dense.bias, mod.layer_norm.weight, mod.layer_norm.bias, mod.decoder.weight, mod.bias)
         ranges = []
         for p, o in zip(self.fp.params, self.fp.offsets):
