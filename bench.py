@@ -72,6 +72,42 @@ def synth_batch(batch, seed, pin):
     return pixels, ids, mask
 
 
+# ---- second workload: the notebook-II form of the captioner (Examples/vyom-ai-accelerate-multimodel-2t4.ipynb cell 1) ----
+# ViT-base (12 layers) -> all 197 tokens scattered into the <image> slots of a 248-token sequence ([bos, <Caption>] + 197 x
+# <image> + caption + eos, right-padded), 8-layer RoPE decoder with the DeBERTa-v3-base widths the notebook takes its config
+# from (768 / 12 heads MHA / 3072, vocab 128100 + <image>, LayerNorm eps 1e-7), causal x padding mask, AdamW + clip 1.0.
+SLOTS_WORKLOAD = "captioner_II_train_vit224p16L12_197img_in_248tok_dec768L8mha_rope_rpad"
+SLOTS_SEQ, SLOTS_IMG, SLOTS_BATCH, SLOTS_IMAGE_TOKEN = 248, 197, 32, 128001
+
+
+class SlotTextCfg(TextCfg):
+    num_key_value_heads = None
+    vocab_size = 128101
+    layer_norm_eps = 1e-07
+    pad_token_id = 0
+
+
+class SlotVitCfg(VitCfg):
+    num_hidden_layers = 12
+
+
+def synth_slot_batch(batch, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    pixels = torch.rand((batch, 3, 224, 224), generator=g)
+    n_text = SLOTS_SEQ - 2 - SLOTS_IMG  # 49 caption positions incl. eos
+    ids = torch.full((batch, SLOTS_SEQ), SlotTextCfg.pad_token_id, dtype=torch.long)
+    ids[:, 0], ids[:, 1] = 1, 5
+    ids[:, 2:2 + SLOTS_IMG] = SLOTS_IMAGE_TOKEN
+    text = torch.randint(6, 128000, (batch, n_text), generator=g)
+    lens = torch.randint(8, n_text + 1, (batch,), generator=g)
+    keep = torch.arange(n_text)[None, :] < lens[:, None]
+    ids[:, 2 + SLOTS_IMG:] = torch.where(keep, text, torch.full_like(text, SlotTextCfg.pad_token_id))
+    mask = (ids != SlotTextCfg.pad_token_id).long()
+    if pin:
+        pixels, ids, mask = pixels.pin_memory(), ids.pin_memory(), mask.pin_memory()
+    return pixels, ids, mask
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
 
@@ -117,12 +153,12 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # ------------------------------------------------------------------------------------------------
-def oracle_state_dict():
+def oracle_state_dict(TextCfg=TextCfg, VitCfg=VitCfg, head="decoder.lm_head.", head_proj="decoder"):
     """Random-init weights of the bench's captioner for the CPU arm, keyed like the reference's state_dict (the names the
     oracle reads), built with plain torch — none of this repo's modules are involved in the reference arm."""
     g = torch.Generator().manual_seed(0)
     H, V, FF = TextCfg.hidden_size, TextCfg.vocab_size, 4 * TextCfg.hidden_size
-    kv = TextCfg.num_key_value_heads * (H // TextCfg.num_attention_heads)
+    kv = (TextCfg.num_key_value_heads or TextCfg.num_attention_heads) * (H // TextCfg.num_attention_heads)
     sd = {}
 
     def lin(name, out_f, in_f):
@@ -157,12 +193,12 @@ def oracle_state_dict():
     sd["decoder.word_embeddings.weight"] = torch.randn(V, H, generator=g)
     for i in range(TextCfg.num_hidden_layers):
         block(f"decoder.all_layer.{i}.", False, kv)
-    lin("decoder.lm_head.dense", H, H)
-    ln("decoder.lm_head.layer_norm", H)
-    sd["decoder.lm_head.decoder.weight"] = (torch.rand(V, H, generator=g) * 2 - 1) * H ** -0.5
-    sd["decoder.lm_head.bias"] = torch.zeros(V)
+    lin(head + "dense", H, H)
+    ln(head + "layer_norm", H)
+    sd[head + head_proj + ".weight"] = (torch.rand(V, H, generator=g) * 2 - 1) * H ** -0.5
+    sd[head + "bias"] = torch.zeros(V)
     sd = {k: v.requires_grad_(True) for k, v in sd.items()}
-    sd["decoder.lm_head.decoder.bias"] = sd["decoder.lm_head.bias"]
+    sd[head + head_proj + ".bias"] = sd[head + "bias"]
     return sd
 
 
@@ -183,6 +219,31 @@ def oracle_train(steps, warmup, batch):
         opt.zero_grad(set_to_none=True)
         logits = O.vlm_forward(sd, cfg, vcfg, px, ids, mask, "rope", "gqa")
         loss = O.cross_entropy_shifted(logits[:, 1:], labels)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return batch / (sum(times) / len(times)), sum(times) / len(times)
+
+
+def oracle_train_slots(steps, warmup, batch):
+    """The same for the notebook-II form: oracle ViT (all 197 tokens) -> slot_vlm_forward (training mask) -> slot_loss -> AdamW."""
+    from oracle import vyom_oracle as O
+    sd = oracle_state_dict(SlotTextCfg, SlotVitCfg, head="lm_head.", head_proj="vocab")
+    params = [v for k, v in sd.items() if v.requires_grad and k != "lm_head.vocab.bias"]
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.0)
+    cfg = O.Cfg(768, 12, None, 514, 8, SlotTextCfg.vocab_size, 1e-7, "gelu")
+    vcfg = O.Cfg(768, 12, None, 514, 12, 0, 1e-5, "gelu", (224, 224), (16, 16), 3)
+    times = []
+    for it in range(warmup + steps):
+        px, ids, mask = synth_slot_batch(batch, 2000 + it, False)
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        feats = O.vit_forward(sd, vcfg, px, pre="encoder.")
+        logits = O.slot_vlm_forward(sd, cfg, feats, ids, mask, True, SLOTS_IMAGE_TOKEN)
+        loss = O.slot_loss(logits, ids, mask, SlotTextCfg.pad_token_id, SLOTS_IMAGE_TOKEN)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
@@ -213,21 +274,26 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_threads()
-    batch = PER_GPU_BATCH
+    slots = args.workload == "slots"
+    train = oracle_train_slots if slots else oracle_train
+    ours_batch = SLOTS_BATCH if slots else PER_GPU_BATCH
+    probe_n = 2 if slots else CPU_SAMPLE_BATCH
+    batch = ours_batch
     t0 = time.perf_counter()
-    oracle_train(1, 0, CPU_SAMPLE_BATCH)  # probe: one 8-sample step (also pages the libraries in)
+    train(1, 0, probe_n)  # probe: one small step (also pages the libraries in)
     probe = time.perf_counter() - t0
-    est = probe * (batch / CPU_SAMPLE_BATCH) * (args.steps + args.warmup)
+    est = probe * (batch / probe_n) * (args.steps + args.warmup)
     if est > 270.0:
-        batch = max(CPU_SAMPLE_BATCH, int(batch * 270.0 / est) // 8 * 8)
-    v, sec = oracle_train(args.steps, args.warmup, batch)
-    sample = (f"{batch} samples per step (same model, S=128, fp32; our arm: {PER_GPU_BATCH} per GPU), {args.steps} timed steps after "
+        batch = max(probe_n, int(batch * 270.0 / est) // probe_n * probe_n)
+    v, sec = train(args.steps, args.warmup, batch)
+    sample = (f"{batch} samples per step (same model, S={SLOTS_SEQ if slots else TEXT_LEN + 1}, fp32; our arm: {ours_batch} per GPU), {args.steps} timed steps after "
               f"{args.warmup} warm-up, {cores} host threads")
     line = {
         "impl": "reference", "metric": "caption_train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": batch, "per_step_samples": batch, "seq_len": TEXT_LEN + 1,
+        "config": {"workload": SLOTS_WORKLOAD if slots else WORKLOAD, "per_gpu_batch": batch, "per_step_samples": batch,
+                   "seq_len": SLOTS_SEQ if slots else TEXT_LEN + 1,
                    "host": "cpu oracle port of the reference path (rank 0 only)"},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -316,6 +382,7 @@ def decode_config3(dev, attn, batch=32, prefill=512, new_tokens=256):
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     kv = model._decode_graph_cache
     with torch.no_grad():
+        model(ids, mask, use_cache=True, kv_cache=kv, start_pos=0, _logits_last_only=True)  # (one-time tuning / lazy module loads)
         e0.record()
         model(ids, mask, use_cache=True, kv_cache=kv, start_pos=0, _logits_last_only=True)
         e1.record()
@@ -335,10 +402,69 @@ def decode_config3(dev, attn, batch=32, prefill=512, new_tokens=256):
             "generate_tok_per_s_wall": B * N / wall, "tokens_checked": int(out.shape[1]),
             "step_kernel": "vy_decode_step" if getattr(g, "fused", None) is not None else "per-op graph"}
 
+def build_package_model():
+    from vyomai_b200 import VisionLanguageModel, Vit
+    return VisionLanguageModel(TextCfg(), encoder=Vit(VitCfg()), pos_embedding_type="rope", attention_type="gqa")
+
+
+def build_slots_model():
+    from vyomai_b200 import ImageSlotVisionLanguageModel, Vit
+    return ImageSlotVisionLanguageModel(Vit(SlotVitCfg()), SlotTextCfg(), decoder_pos_embedding_type="rope")
+
+
+def slots_labels(ids, mask):
+    from vyomai_b200 import slot_caption_labels
+    return slot_caption_labels(ids, mask, SlotTextCfg.pad_token_id, SLOTS_IMAGE_TOKEN)
+
+
+def workload_of(name):
+    from vyomai_b200.trainer import caption_labels
+    if name == "slots":
+        return {"name": SLOTS_WORKLOAD, "batch": SLOTS_BATCH, "seq": SLOTS_SEQ, "synth": synth_slot_batch, "build": build_slots_model,
+                "labels": slots_labels, "wd": 0.0}
+    return {"name": WORKLOAD, "batch": PER_GPU_BATCH, "seq": TEXT_LEN + 1, "synth": synth_batch, "build": build_package_model,
+            "labels": caption_labels, "wd": 0.01}
+
+
+def measure_slots(dev, steps, warmup):
+    """The notebook-II workload on one GPU, appended to the default line: resident-input training steps (CUDA-graph replays)
+    timed with CUDA events, and the oracle port of the same step on the host cores (2 samples per step)."""
+    import io
+    from contextlib import redirect_stdout
+    from vyomai_b200.trainer import Trainer
+    wl = workload_of("slots")
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        model = wl["build"]()
+    model = model.to(dev).to(torch.bfloat16).train()
+    tr = Trainer(model, lr=1e-5, weight_decay=wl["wd"], max_grad_norm=1.0, use_graph=True)
+    px, ids, mask = [t.to(dev) for t in wl["synth"](wl["batch"], 23, False)]
+    labels = wl["labels"](ids, mask)
+    for _ in range(max(warmup, 3)):
+        loss = tr.caption_step(px, ids, mask, labels)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.caption_step(px, ids, mask, labels)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    cores = host_threads()
+    v, sec = oracle_train_slots(1, 1, 2)
+    n_params = sum(p.numel() for p in model.parameters())
+    return {"workload": wl["name"], "per_gpu_batch": wl["batch"], "seq_len": wl["seq"], "image_tokens": SLOTS_IMG, "ms_per_step": ms,
+            "samples_per_s": wl["batch"] / (ms / 1e3), "tokens_per_s": wl["batch"] * wl["seq"] / (ms / 1e3), "params_M": round(n_params / 1e6, 1),
+            "final_loss": float(loss), "grad_overwrite": bool(tr.grad_overwrite), "kernels_per_step": tr.graph_kernels,
+            "cpu_port": {"value": v, "unit": "samples/s", "cores": cores, "sample": f"1 timed step of 2 samples after 1 warm-up ({sec:.1f} s/step)"}}
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from vyomai_b200 import _lib, VisionLanguageModel, Vit
-    from vyomai_b200.trainer import HostPrefetcher, Trainer, caption_labels
+    from vyomai_b200 import _lib
+    from vyomai_b200.trainer import HostPrefetcher, Trainer
+    wl = workload_of(args.workload)
+    caption_labels = wl["labels"]
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -353,14 +479,14 @@ def run_ours(args):
     import io
     from contextlib import redirect_stdout
     with redirect_stdout(io.StringIO()):
-        model = VisionLanguageModel(TextCfg(), encoder=Vit(VitCfg()), pos_embedding_type="rope", attention_type="gqa")
+        model = wl["build"]()
     model = model.to(dev).to(torch.bfloat16).train()
-    trainer = Trainer(model, lr=1e-5, weight_decay=0.01, max_grad_norm=1.0, use_graph=not args.no_graph,
+    trainer = Trainer(model, lr=1e-5, weight_decay=wl["wd"], max_grad_norm=1.0, use_graph=not args.no_graph,
                       grad_overwrite=not args.no_grad_overwrite, overlap=not args.no_overlap, bucket_mb=args.bucket_mb,
                       dp_mode=args.dp_mode)
 
-    B = PER_GPU_BATCH
-    host = [synth_batch(B, 17 + 1000 * rank + i, True) for i in range(2)]
+    B = wl["batch"]
+    host = [wl["synth"](B, 17 + 1000 * rank + i, True) for i in range(2)]
     px_d, ids_d, mask_d = [t.to(dev) for t in host[0]]
     labels_d = caption_labels(ids_d, mask_d)
 
@@ -462,24 +588,28 @@ def run_ours(args):
         # the metric also names decode tok/s: BASELINE config 3, GQA and MHA, on this GPU (inference replicas do not interact,
         # so it is measured at N = 1 only)
         decode = {a: decode_config3(dev, a) for a in ("gqa", "mha")}
+    slots = None
+    if world == 1 and args.workload == "package" and not args.no_slots:
+        slots = measure_slots(dev, args.steps, args.warmup)  # BASELINE configs[3] in its notebook-II form, same GPU
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = host_threads()
-            v, sec = oracle_train(1, 1, CPU_SAMPLE_BATCH)
+            nb = CPU_SAMPLE_BATCH if args.workload == "package" else 2
+            v, sec = (oracle_train if args.workload == "package" else oracle_train_slots)(1, 1, nb)
             cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                   "sample": f"1 timed step of {CPU_SAMPLE_BATCH} samples after 1 warm-up step (oracle port, fp32, {sec:.1f} s/step)"}
+                   "sample": f"1 timed step of {nb} samples after 1 warm-up step (oracle port, fp32, {sec:.1f} s/step)"}
         line = {
             "metric": "caption_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "seq_len": TEXT_LEN + 1,
+            "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "seq_len": wl["seq"],
                        "parallelism": f"dp{world}", "dp_step": trainer.dp_mode, "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2",
                        "dropout": 0.0, "optimizer": "AdamW fp32 master + clip 1.0",
                        "cuda_graph": not args.no_graph, "grad_overwrite": bool(trainer.grad_overwrite)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof, "cpu_baseline": cpu,
-            "kernel_breakdown_ms": breakdown, "kernel_breakdown_sum_ms": round(total_ms, 3), "decode": decode,
+            "kernel_breakdown_ms": breakdown, "kernel_breakdown_sum_ms": round(total_ms, 3), "decode": decode, "notebook_II": slots,
             "final_loss": final_loss, "e2e_last_loss": last,
         }
         print(json.dumps(line), flush=True)
@@ -500,6 +630,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="package", choices=["package", "slots"],
+                    help="package: VisionLanguageModel of the reference package (1 image token + 127 text, the headline since round 1); "
+                         "slots: the notebook-II form (197 image tokens in a 248-token sequence)")
+    ap.add_argument("--no-slots", action="store_true", help="skip the notebook-II measurement appended at N = 1")
     ap.add_argument("--no-decode", action="store_true", help="skip the config-3 decode measurement appended at N = 1")
     ap.add_argument("--no-grad-overwrite", action="store_true", help="zero + accumulate every gradient instead of overwrite mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
