@@ -421,13 +421,17 @@ attn_decode_tma_kernel(const DecodeDev g, const int stages) {
     const int keys = min(TD_CHUNK, k_end - (k_begin + c * TD_CHUNK));
     const unsigned char* kt = td_smem + static_cast<size_t>(st) * (2 * TD_CHUNK_BYTES);
     const unsigned char* vt = kt + TD_CHUNK_BYTES;
-    // key (u * 8 + warp) * 4 + lk: a partly filled chunk is still spread over all warps
+    // key (u * 8 + warp) * 4 + lk: a partly filled chunk is still spread over all warps. The 4 keys a lane group sees per
+    // chunk are scored first (independent dot products and shuffles), then folded into the running softmax with ONE rescale
+    // per head — a per-key online update is a chain of dependent ex2 / FMA that two warps per scheduler cannot hide.
+    constexpr int KU = TD_CHUNK / (TD_WARPS * 4);
+    float kvk[KU][8], vvk[KU][8];
+    bool valid[KU];
 #pragma unroll
-    for (int u = 0; u < TD_CHUNK / (TD_WARPS * 4); ++u) {
+    for (int u = 0; u < KU; ++u) {
       const int kidx = (u * TD_WARPS + warp) * 4 + lk;
-      const bool valid = kidx < keys;
-      float kv[8], vv[8];
-      if (valid) {
+      valid[u] = kidx < keys;
+      if (valid[u]) {
         const uint4 kr = *reinterpret_cast<const uint4*>(kt + kidx * (HD * 2) + ld * 16);
         const uint4 vr = *reinterpret_cast<const uint4*>(vt + kidx * (HD * 2) + ld * 16);
         const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kr);
@@ -435,29 +439,51 @@ attn_decode_tma_kernel(const DecodeDev g, const int stages) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 a = __bfloat1622float2(kh[k]), bb = __bfloat1622float2(vh[k]);
-          kv[2 * k] = a.x; kv[2 * k + 1] = a.y;
-          vv[2 * k] = bb.x; vv[2 * k + 1] = bb.y;
+          kvk[u][2 * k] = a.x; kvk[u][2 * k + 1] = a.y;
+          vvk[u][2 * k] = bb.x; vvk[u][2 * k + 1] = bb.y;
         }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) kvk[u][k] = vvk[u][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NREP; ++r) {
+      float sc[KU];
+#pragma unroll
+      for (int u = 0; u < KU; ++u) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += q[r][j] * kvk[u][j];
+        sc[u] = t;
       }
 #pragma unroll
-      for (int r = 0; r < NREP; ++r) {
-        float sc = 0.f;
-        if (valid) {
+      for (int u = 0; u < KU; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 1);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) sc += q[r][j] * kv[j];
-        }
-        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-        if (valid) {
-          const float mn = fmaxf(m[r], sc);
-          const float a = exp2f(m[r] - mn);
-          const float pp = exp2f(sc - mn);
-          l[r] = l[r] * a + pp;
+      for (int u = 0; u < KU; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 2);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[r][j] = o[r][j] * a + pp * vv[j];
-          m[r] = mn;
+      for (int u = 0; u < KU; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 4);
+      float mn = m[r];
+#pragma unroll
+      for (int u = 0; u < KU; ++u)
+        if (valid[u]) mn = fmaxf(mn, sc[u]);
+      if (mn != -INFINITY) {  // (-inf: this lane group has not seen a key yet)
+        const float a = exp2f(m[r] - mn);
+        float pp[KU], psum = 0.f;
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+          pp[u] = valid[u] ? exp2f(sc[u] - mn) : 0.f;
+          psum += pp[u];
         }
+        l[r] = l[r] * a + psum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float acc = o[r][j] * a;
+#pragma unroll
+          for (int u = 0; u < KU; ++u) acc += pp[u] * vvk[u][j];
+          o[r][j] = acc;
+        }
+        m[r] = mn;
       }
     }
     if (c + stages < nchunks) {  // the stage is needed again: hand it back, thread 0 refills it once every warp has

@@ -191,7 +191,8 @@ gemm_skinny_kernel(const SkinnyDev p) {
 // possible splits take the one that brings the CTA count closest to ~2 per SM without exceeding 8 CTAs per cluster.
 static int skinny_ksplit(int F, int K) {
   const int units = (F + 15) / 16;
-  const int target = 2 * num_sms();
+  static const int target_env = getenv("VY_SKINNY_CTAS") ? atoi(getenv("VY_SKINNY_CTAS")) : 0;  // development: sweep
+  const int target = target_env > 0 ? target_env : num_sms();
   int best = 0;
   long long best_score = -(1LL << 60);
   for (int s = 1; s <= 8; ++s) {
