@@ -459,6 +459,126 @@ def measure_slots(dev, steps, warmup):
             "cpu_port": {"value": v, "unit": "samples/s", "cores": cores, "sample": f"1 timed step of 2 samples after 1 warm-up ({sec:.1f} s/step)"}}
 
 
+def _timed_graph(fn, iters=20):
+    """Device time per call of `fn` replayed from a CUDA graph (3 eager warm-up calls on a side stream first)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    for _ in range(3):
+        graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def measure_configs_1_2(dev):
+    """BASELINE configs[0] and [1] on this GPU with the oracle port timed beside them on the host cores:
+    C1 = EncoderModel (default EncoderConfig, RoPE + GQA kv4), 8 x 128 right-padded tokens, forward + backward of (out . G).sum();
+    C2 = Vit 224 / patch 16 (4 layers) + Linear(768, 6) on the CLS row, batch 64, forward. FLOPs: SURVEY.md §8(d)."""
+    import io
+    from contextlib import redirect_stdout
+    from oracle import vyom_oracle as O
+    from vyomai_b200 import EncoderConfig, EncoderModel, Vit
+    tf_sust = peaks()[2]
+    out = {}
+    cores = host_threads()
+    # ---- C1 ----
+    cfg = type("C1", (), dict(vars(EncoderConfig()), num_key_value_heads=4, hidden_dropout_prob=0.0))()
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        enc = EncoderModel(cfg, pos_embedding_type="rope", attention_type="gqa")
+    enc = enc.to(dev).to(torch.bfloat16).train()
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, cfg.vocab_size, (8, 128), generator=g)
+    lens = torch.randint(16, 129, (8,), generator=g)
+    lens[0] = 128
+    mask = (torch.arange(128)[None, :] < lens[:, None]).long()
+    cot = torch.randn(8, 128, cfg.hidden_size, generator=g) * mask[..., None]
+    ids_d, mask_d, cot_d = ids.to(dev), mask.to(dev), cot.to(dev).to(torch.bfloat16)
+
+    def c1_step():
+        for p in enc.parameters():
+            p.grad = None
+        (enc(ids_d, mask_d).logits * cot_d).sum().backward()
+
+    try:
+        ms, how = _timed_graph(c1_step), "cuda-graph replay"
+    except Exception as e:  # capture refused: time eager launches instead and say so
+        torch.cuda.synchronize()
+        for _ in range(3):
+            c1_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            c1_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms, how = e0.elapsed_time(e1) / 20, f"eager launches (graph capture failed: {type(e).__name__})"
+    sd = {k: v.detach().float().cpu().requires_grad_(v.dtype.is_floating_point) for k, v in enc.state_dict().items()}
+    ocfg = O.Cfg(cfg.hidden_size, cfg.num_attention_heads, 4, cfg.max_position_embeddings, cfg.num_hidden_layers, cfg.vocab_size,
+                 cfg.layer_norm_eps, cfg.hidden_act)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for v in sd.values():
+            v.grad = None
+        (O.encoder_forward(sd, ocfg, ids, mask, "rope", "gqa") * cot).sum().backward()
+        ts.append(time.perf_counter() - t0)
+    cpu_s = min(ts[1:])
+    out["C1_encoder_8x128_fwd_bwd"] = {"ms_per_step": ms, "samples_per_s": 8 / (ms / 1e3), "tflops": 159.0 / ms, "frac_of_sustained_bf16": 159.0 / ms / tf_sust,
+                                      "algorithmic_gflop_per_step": 159.0, "timed_as": how, "dtype": "bf16",
+                                      "cpu_port": {"samples_per_s": 8 / cpu_s, "cores": cores, "dtype": "f32", "sample": "best of 2 steps after 1 warm-up"}}
+    del enc
+    # ---- C2 ----
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        vit = Vit(VitCfg())
+    head = torch.nn.Linear(768, 6)
+    vit, head = vit.to(dev).to(torch.bfloat16).eval(), head.to(dev).to(torch.bfloat16)
+    px = torch.rand(64, 3, 224, 224, generator=g)
+    px_d = px.to(dev).to(torch.bfloat16)
+
+    def c2_step():
+        with torch.no_grad():
+            return head(vit(pixel_values=px_d).logits[:, 0])
+
+    try:
+        ms2, how2 = _timed_graph(c2_step), "cuda-graph replay"
+    except Exception as e:
+        torch.cuda.synchronize()
+        for _ in range(3):
+            c2_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            c2_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms2, how2 = e0.elapsed_time(e1) / 20, f"eager launches (graph capture failed: {type(e).__name__})"
+    vsd = {k: v.detach().float().cpu() for k, v in vit.state_dict().items()}
+    vcfg = O.Cfg(768, 12, None, 514, VitCfg.num_hidden_layers, 0, 1e-5, "gelu", (224, 224), (16, 16), 3)
+    with torch.no_grad():
+        O.vit_forward(vsd, vcfg, px[:8])
+        t0 = time.perf_counter()
+        O.vit_forward(vsd, vcfg, px[:16])
+        cpu2 = time.perf_counter() - t0
+    out["C2_vit224p16_L4_b64_fwd"] = {"ms_per_step": ms2, "images_per_s": 64 / (ms2 / 1e3), "tflops": 759.0 / ms2, "frac_of_sustained_bf16": 759.0 / ms2 / tf_sust,
+                                     "algorithmic_gflop_per_step": 759.0, "timed_as": how2, "dtype": "bf16",
+                                     "cpu_port": {"images_per_s": 16 / cpu2, "cores": cores, "dtype": "f32", "sample": "one 16-image forward after an 8-image warm-up"}}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from vyomai_b200 import _lib
@@ -588,6 +708,9 @@ def run_ours(args):
         # the metric also names decode tok/s: BASELINE config 3, GQA and MHA, on this GPU (inference replicas do not interact,
         # so it is measured at N = 1 only)
         decode = {a: decode_config3(dev, a) for a in ("gqa", "mha")}
+    small = None
+    if world == 1 and args.workload == "package" and not args.no_configs_1_2:
+        small = measure_configs_1_2(dev)  # BASELINE configs[0], [1]
     slots = None
     if world == 1 and args.workload == "package" and not args.no_slots:
         slots = measure_slots(dev, args.steps, args.warmup)  # BASELINE configs[3] in its notebook-II form, same GPU
@@ -609,7 +732,7 @@ def run_ours(args):
                        "cuda_graph": not args.no_graph, "grad_overwrite": bool(trainer.grad_overwrite)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof, "cpu_baseline": cpu,
-            "kernel_breakdown_ms": breakdown, "kernel_breakdown_sum_ms": round(total_ms, 3), "decode": decode, "notebook_II": slots,
+            "kernel_breakdown_ms": breakdown, "kernel_breakdown_sum_ms": round(total_ms, 3), "decode": decode, "notebook_II": slots, "configs_1_2": small,
             "final_loss": final_loss, "e2e_last_loss": last,
         }
         print(json.dumps(line), flush=True)
@@ -633,6 +756,7 @@ def main():
     ap.add_argument("--workload", default="package", choices=["package", "slots"],
                     help="package: VisionLanguageModel of the reference package (1 image token + 127 text, the headline since round 1); "
                          "slots: the notebook-II form (197 image tokens in a 248-token sequence)")
+    ap.add_argument("--no-configs-1-2", action="store_true", help="skip the encoder (C1) / ViT (C2) measurements appended at N = 1")
     ap.add_argument("--no-slots", action="store_true", help="skip the notebook-II measurement appended at N = 1")
     ap.add_argument("--no-decode", action="store_true", help="skip the config-3 decode measurement appended at N = 1")
     ap.add_argument("--no-grad-overwrite", action="store_true", help="zero + accumulate every gradient instead of overwrite mode")

@@ -54,7 +54,8 @@ enum {
   VY_ACT_GELU_TANH = 2,
   VY_ACT_DGELU_ERF = 3,
   VY_ACT_DGELU_TANH = 4,
-  VY_ACT_SWIGLU = 5 /* gated MLP: see VyGemm.act */
+  VY_ACT_SWIGLU = 5, /* gated MLP: see VyGemm.act */
+  VY_ACT_GEGLU_TANH = 6 /* same layout and rules as VY_ACT_SWIGLU with out = gelu_tanh(gate) * up (GemmaMLP, Examples/paligemma.ipynb cell 11) */
 };
 
 enum { VY_EPI_LINEAR = 0, VY_EPI_QKV_ROPE = 1 };
@@ -111,8 +112,7 @@ VY_API int vy_abi_sizeof(const char* name);
  * (kv_cache.py:355-359) are fused into the projection. k/v rows are written at token index
  * kv_dst_pos0 + l (= start_pos for a cache, 0 for a fresh buffer); q rows at l.
  *
- * Small batches (transposed_out, N <= 32 activation rows, bf16, K-major operands, K / s a multiple of 128 and <= 768 for
- * some s <= 8, act NONE / GELU_*, no aux / addend2 / row remaps) do not use the tensor-memory kernel at
+ * Small batches (transposed_out, N <= 32 activation rows, bf16, K-major operands, K / s a multiple of 128 for some s <= 8, at most ~9.4k output features, act NONE / GELU_*, no aux / addend2 / row remaps) do not use the tensor-memory kernel at
  * all: csrc/gemm_skinny.cu streams the weights once through 150-400 CTAs (16 features x K / s each, mma.sync, partial sums
  * combined through the shared memory of a thread-block cluster). VY_GEMM_SKINNY=0 in the environment disables it.
  * ------------------------------------------------------------------------------------------ */
@@ -286,6 +286,11 @@ VY_API int vy_norm_bwd_partial_rows(void);
  * k <= q_pos0 + l; models/decoder.py:376-419). Masked scores behave like "+ finfo.min": a row with
  * no visible key returns the mean of v over ALL Skv keys.
  * lse (optional, fp32 [B, n_q_heads, Sq]) receives log2-domain logsumexp for vy_attn_bwd.
+ * head_dim 64 runs on the tensor-memory kernel described above. Any other head_dim that is a multiple of 8 up to 256
+ * (SigLIP 72, Gemma 256: Examples/paligemma.ipynb cells 9, 12) and every call with a prefix-LM mask runs on a second,
+ * mma.sync-based forward kernel (csrc/attn_fwd_mma.cu; "64" in the layout notes above reads head_dim, the scale is
+ * 1/sqrt(head_dim)); at Sq == 1 it packs the query heads of a kv group into one tile (MQA / GQA decode over a cache).
+ * vy_attn_bwd exists for head_dim 64 only.
  * ------------------------------------------------------------------------------------------ */
 typedef struct VyAttn {
   int32_t B, n_q_heads, n_kv_heads, head_dim;
@@ -304,6 +309,10 @@ typedef struct VyAttn {
   int64_t o_sb, o_sl;
   int32_t out_dtype;
   float* lse;
+  /* PREFIX_LM mask (with causal != 0): int32 [B], key k is visible to query l iff k <= q_pos0 + l OR k < prefix_len[b] — the
+   * training mask of Examples/paligemma.ipynb cell 17 `_update_causal_mask` (image + prompt tokens attend to each other in
+   * both directions, the suffix is causal). NULL = plain causal. */
+  const int32_t* prefix_len;
   void* stream;
 } VyAttn;
 
@@ -357,7 +366,8 @@ VY_API int vy_attn_bwd(const VyAttnBwd* p);
 
 /* vy_rope_apply — stand-alone half-split RoPE for the public apply_rotary_pos_emb(q, k, freqs)
  * helper (layers/positional_embeddings.py:155-182): out[b,h,l,:] = rotate(x[b,h,l,:], angle row
- * pos0 + l). cos/sin are fp32 [rows][32]; inverse = 1 applies the transpose rotation. head_dim 64. */
+ * pos0 + l). cos/sin are fp32 [rows][head_dim / 2]; inverse = 1 applies the transpose rotation. Any even head_dim (64 in the
+ * package's models, 256 in the Gemma decoder of Examples/paligemma.ipynb cell 11, whose `out` is the kv-cache slot itself). */
 typedef struct VyRope {
   int32_t B, H, S, head_dim;
   const void* x;
@@ -572,6 +582,8 @@ typedef struct VyPatchify {
   int32_t in_dtype;
   void* out;
   int32_t out_dtype;
+  int64_t ld_out; /* row stride of out in elements; 0 = C * patch_h * patch_w. A wider stride pads each patch row (columns beyond the
+                   * patch are left untouched) — SigLIP's 14 x 14 patches give 588 columns, which vy_gemm needs padded to 592 */
   void* stream;
 } VyPatchify;
 

@@ -380,6 +380,10 @@ static int make_qkv_map(CUtensorMap* out, const void* base, int S, int H, int B,
 
 }  // namespace vy
 
+namespace vy {
+int attn_fwd_mma(const VyAttn* p);  // attn_fwd_mma.cu
+}
+
 extern "C" int vy_attn_fwd(const VyAttn* p) {
   using namespace vy;
   VY_CHECK_ARG(p != nullptr, "vy_attn_fwd: null params");
@@ -387,12 +391,15 @@ extern "C" int vy_attn_fwd(const VyAttn* p) {
     set_error("vy_attn_fwd: no sm_100 device (there is no CPU fallback)");
     return VY_ERR_NO_DEVICE;
   }
-  VY_CHECK_ARG(p->head_dim == 64, "vy_attn_fwd: head_dim must be 64 (got %d)", p->head_dim);
   VY_CHECK_ARG(p->qkv_dtype == VY_BF16, "vy_attn_fwd: q/k/v must be bf16 (fp32 models hand bf16 operands to the tensor cores)");
   VY_CHECK_ARG(p->B > 0 && p->Sq > 0 && p->Skv > 0 && p->n_q_heads > 0 && p->n_kv_heads > 0 &&
                    p->n_q_heads % p->n_kv_heads == 0,
                "vy_attn_fwd: bad shape");
   VY_CHECK_ARG(p->q && p->k && p->v && p->out && dtype_ok(p->out_dtype), "vy_attn_fwd: null pointer / bad out dtype");
+  if (p->causal) VY_CHECK_ARG(p->q_pos0 >= 0, "vy_attn_fwd: negative q_pos0");
+  // head dims other than 64 and the prefix-LM mask: the mma.sync kernel (attn_fwd_mma.cu); VY_ATTN_MMA=1 sends everything there
+  static const bool force_mma = getenv("VY_ATTN_MMA") && atoi(getenv("VY_ATTN_MMA")) != 0;
+  if (p->head_dim != 64 || (p->causal && p->prefix_len) || force_mma) return attn_fwd_mma(p);
   auto ok16 = [](const void* ptr, long long a, long long b_, long long c) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (a * 2) % 16 == 0 && (b_ * 2) % 16 == 0 && (c * 2) % 16 == 0;
   };

@@ -103,11 +103,12 @@ embed_bwd_kernel(int rows, int H, const long long* __restrict__ ids, int vocab, 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __restrict__ px, int in_dt,
-                void* __restrict__ out, int out_dt, int vec) {
+                void* __restrict__ out, int out_dt, int vec, long long ld_out) {
   pdl_trigger();
   pdl_wait();
   const int gw = Ww / pw, gh = Hh / ph;
   const int K = C * ph * pw;
+  if (ld_out <= 0) ld_out = K;
   const long long total = static_cast<long long>(B) * gh * gw * K;
   if (vec) {
     // 8 consecutive outputs = 8 consecutive pixels of one patch row (pw % 8 == 0): one 16/32-byte load and store
@@ -124,7 +125,7 @@ patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __rest
       const long long src = ((static_cast<long long>(b) * C + c) * Hh + (r * ph + ii)) * Ww + (s * pw + j);
       float x[8];
       ld8_as_float(px, in_dt, src, x);
-      st8_from_float(out, out_dt, i, x);
+      st8_from_float(out, out_dt, prow * ld_out + kk, x);
     }
     return;
   }
@@ -137,7 +138,7 @@ patchify_kernel(int B, int C, int Hh, int Ww, int ph, int pw, const void* __rest
     const int b = static_cast<int>(prow / (static_cast<long long>(gw) * gh));
     const int j = kk % pw, ii = (kk / pw) % ph, c = kk / (pw * ph);
     const long long src = ((static_cast<long long>(b) * C + c) * Hh + (r * ph + ii)) * Ww + (s * pw + j);
-    st_from_float(out, out_dt, i, ld_as_float(px, in_dt, src));
+    st_from_float(out, out_dt, prow * ld_out + kk, ld_as_float(px, in_dt, src));
   }
 }
 
@@ -549,9 +550,9 @@ slot_merge_kernel(int rows, int vec_per_row, const uint4* __restrict__ a, const 
   }
 }
 
-// stand-alone half-split RoPE: one warp per (b, h, l) row, lane j <-> pair (j, j + 32)
+// stand-alone half-split RoPE: one warp per (b, h, l) row, lane j (+ 32, ...) <-> pair (j, j + D / 2)
 __global__ void __launch_bounds__(256)
-rope_kernel(int B, int H, int S, const void* __restrict__ x, long long xsb, long long xsh, long long xsl, int dt,
+rope_kernel(int B, int H, int S, int D, const void* __restrict__ x, long long xsb, long long xsh, long long xsl, int dt,
             const float* __restrict__ cs, const float* __restrict__ sn, int pos0, int inverse, void* __restrict__ out,
             long long osb, long long osh, long long osl) {
   pdl_trigger();
@@ -565,12 +566,15 @@ rope_kernel(int B, int H, int S, const void* __restrict__ x, long long xsb, long
     const int h = static_cast<int>((r / S) % H);
     const int b = static_cast<int>(r / (static_cast<long long>(S) * H));
     const long long xi = b * xsb + h * xsh + l * xsl, oi = b * osb + h * osh + l * osl;
-    const float a = ld_as_float(x, dt, xi + lane), bb = ld_as_float(x, dt, xi + lane + 32);
-    const float c = cs[static_cast<long long>(pos0 + l) * 32 + lane];
-    float s = sn[static_cast<long long>(pos0 + l) * 32 + lane];
-    if (inverse) s = -s;
-    st_from_float(out, dt, oi + lane, a * c - bb * s);
-    st_from_float(out, dt, oi + lane + 32, bb * c + a * s);
+    const int half = D >> 1;
+    for (int j = lane; j < half; j += 32) {
+      const float a = ld_as_float(x, dt, xi + j), bb = ld_as_float(x, dt, xi + j + half);
+      const float c = cs[static_cast<long long>(pos0 + l) * half + j];
+      float s = sn[static_cast<long long>(pos0 + l) * half + j];
+      if (inverse) s = -s;
+      st_from_float(out, dt, oi + j, a * c - bb * s);
+      st_from_float(out, dt, oi + j + half, bb * c + a * s);
+    }
   }
 }
 
@@ -693,10 +697,13 @@ extern "C" int vy_patchify(const VyPatchify* p) {
                "vy_patchify: image dimensions must be divisible by the patch size");
   VY_CHECK_ARG(p->pixels && p->out && dtype_ok(p->in_dtype) && dtype_ok(p->out_dtype), "vy_patchify: null pointer / bad dtype");
   const long long total = static_cast<long long>(p->B) * p->C * p->H * p->W;
-  const int vec = (p->patch_w % 8 == 0 && p->W % 8 == 0 && aligned16(p->pixels) && aligned16(p->out)) ? 1 : 0;
+  const long long Kp = static_cast<long long>(p->C) * p->patch_h * p->patch_w;
+  VY_CHECK_ARG(p->ld_out == 0 || p->ld_out >= Kp, "vy_patchify: ld_out %lld is smaller than a patch row (%lld)", (long long)p->ld_out, Kp);
+  const int vec = (p->patch_w % 8 == 0 && p->W % 8 == 0 && aligned16(p->pixels) && aligned16(p->out) &&
+                   (p->ld_out == 0 || (p->ld_out * static_cast<long long>(dtype_size(p->out_dtype))) % 16 == 0)) ? 1 : 0;
   VY_CUDA_OK(launch_kernel(patchify_kernel, dim3(ew_grid(vec ? total / 8 : total, 1024)), dim3(256), 0,
                            static_cast<cudaStream_t>(p->stream), p->B, p->C, p->H, p->W, p->patch_h, p->patch_w, p->pixels,
-                           p->in_dtype, p->out, p->out_dtype, vec));
+                           p->in_dtype, p->out, p->out_dtype, vec, static_cast<long long>(p->ld_out)));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
@@ -819,11 +826,11 @@ extern "C" int vy_adamw(const VyAdamW* p) {
 extern "C" int vy_rope_apply(const VyRope* p) {
   VY_CHECK_ARG(p != nullptr, "vy_rope_apply: null params");
   VY_NEED_DEVICE("vy_rope_apply");
-  VY_CHECK_ARG(p->head_dim == 64, "vy_rope_apply: head_dim must be 64 (got %d)", p->head_dim);
+  VY_CHECK_ARG(p->head_dim >= 2 && (p->head_dim & 1) == 0, "vy_rope_apply: head_dim must be even (got %d)", p->head_dim);
   VY_CHECK_ARG(p->B > 0 && p->H > 0 && p->S > 0 && p->x && p->out && p->cos && p->sin && dtype_ok(p->dtype), "vy_rope_apply: bad arguments");
   const long long rows = static_cast<long long>(p->B) * p->H * p->S;
   VY_CUDA_OK(launch_kernel(rope_kernel, dim3(ew_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
-      p->B, p->H, p->S, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl));
+      p->B, p->H, p->S, p->head_dim, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

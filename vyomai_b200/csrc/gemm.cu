@@ -246,6 +246,15 @@ extern "C" int vy_gemm(const VyGemm* p) {
     set_error("vy_gemm: no sm_100 device (there is no CPU fallback)");
     return VY_ERR_NO_DEVICE;
   }
+  // GeGLU = the gated epilogue with gelu_tanh on the gate (Examples/paligemma.ipynb cell 11 GemmaMLP): same code path as SwiGLU
+  VyGemm gated_copy;
+  int gate_act = 0;
+  if (p->act == VY_ACT_GEGLU_TANH) {
+    gated_copy = *p;
+    gated_copy.act = VY_ACT_SWIGLU;
+    p = &gated_copy;
+    gate_act = 1;
+  }
   VY_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "vy_gemm: bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
   VY_CHECK_ARG(dtype_ok(p->in_dtype), "vy_gemm: bad in_dtype %d", p->in_dtype);
   VY_CHECK_ARG(p->A && p->B, "vy_gemm: null operand");
@@ -274,6 +283,7 @@ extern "C" int vy_gemm(const VyGemm* p) {
   g.poison.id = lid & 0x7fffffff ? lid & 0x7fffffff : 1;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.epi = p->epi; g.act = p->act; g.transposed_out = p->transposed_out;
+  g.gate_act = gate_act;
   g.bias = p->bias; g.bias_dtype = p->bias_dtype;
   g.addend = p->addend; g.ld_addend = p->ld_addend; g.addend_dtype = p->addend_dtype;
   g.addend_row_mod = p->addend_row_mod; g.addend_row_off = p->addend_row_off;

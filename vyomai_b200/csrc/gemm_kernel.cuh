@@ -24,6 +24,7 @@ namespace vy {
 struct GemmDev {
   int M, N, K;
   int epi, act, transposed_out;
+  int gate_act;  // VY_ACT_SWIGLU family: 0 = silu(gate) * up, 1 = gelu_tanh(gate) * up (GeGLU)
   const void* bias;
   int bias_dtype;
   const void* addend;
@@ -166,6 +167,8 @@ __device__ __forceinline__ uint4 staged_slot(const uint8_t* stage, int lane, int
 // Epilogue bodies. Warp (q = TMEM lane quarter, half) owns accumulator rows [32q, 32q + 32) and, of
 // the tile's BN columns, the half [half * BN/2, (half + 1) * BN/2); thread <-> accumulator row.
 // --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gate_fn(float x, int gate_act) { return gate_act ? gelu_tanh(x) : x / (1.f + __expf(-x)); }
+
 // general per-thread handling of one 32-column chunk: any dtype mix / alignment, ragged N edge
 static __device__ __noinline__ void epilogue_chunk_general(const GemmDev& g, const uint32_t* raw, const float* bs, int grow,
                                                     long long orow, long long arow, int gcol0, int lim) {
@@ -189,7 +192,7 @@ static __device__ __noinline__ void epilogue_chunk_general(const GemmDev& g, con
           st8_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + gcol0 + j4 * 16 + 8, hi);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = x[2 * j] / (1.f + __expf(-x[2 * j])) * x[2 * j + 1] * scale;
+        for (int j = 0; j < 8; ++j) h[j] = gate_fn(x[2 * j], g.gate_act) * x[2 * j + 1] * scale;
         st8_from_float(g.out, g.out_dtype, obase + j4 * 8, h);
       }
     } else {
@@ -199,7 +202,7 @@ static __device__ __noinline__ void epilogue_chunk_general(const GemmDev& g, con
           st_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + gcol0 + j, a);
           st_from_float(g.aux, g.aux_dtype, static_cast<long long>(grow) * g.ld_aux + gcol0 + j + 1, b);
         }
-        st_from_float(g.out, g.out_dtype, obase + (j >> 1), a / (1.f + __expf(-a)) * b * scale);
+        st_from_float(g.out, g.out_dtype, obase + (j >> 1), gate_fn(a, g.gate_act) * b * scale);
       }
     }
     return;
@@ -571,7 +574,7 @@ __device__ __forceinline__ void epilogue_swiglu_fast(const GemmDev& g, uint32_t 
         for (int j = 0; j < 8; ++j) {
           const float gte = __uint_as_float(raw[jj * 16 + 2 * j]) + (j < 4 ? b0[2 * j] : b1[2 * j - 8]);
           const float up = __uint_as_float(raw[jj * 16 + 2 * j + 1]) + (j < 4 ? b0[2 * j + 1] : b1[2 * j - 7]);
-          h[j] = gte / (1.f + __expf(-gte)) * up * scale;
+          h[j] = gate_fn(gte, g.gate_act) * up * scale;
         }
         *reinterpret_cast<uint4*>(srow + (((cc * 2 + jj) ^ sw) << 4)) =
             make_uint4(pack2_bf16(h[0], h[1]), pack2_bf16(h[2], h[3]), pack2_bf16(h[4], h[5]), pack2_bf16(h[6], h[7]));

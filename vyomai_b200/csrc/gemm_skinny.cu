@@ -20,7 +20,7 @@ namespace vy {
 
 constexpr int SK_WARPS = 4;
 constexpr int SK_THREADS = SK_WARPS * 32;
-constexpr int SK_MAX_KB = 6;   // 32-wide k-blocks per warp: K / ksplit <= 4 * 6 * 32 = 768
+constexpr int SK_MAX_KB = 6;   // 32-wide k-blocks a warp has in flight at once (12 x 16-byte loads per thread)
 constexpr int SK_TILE = 16 * 33;  // [16 features][32 tokens] fp32, padded rows
 
 struct SkinnyDev {
@@ -83,35 +83,39 @@ gemm_skinny_kernel(const SkinnyDev p) {
   const __nv_bfloat16* w0 = p.W + static_cast<long long>(f0 + g) * p.ldw + k0;
   const __nv_bfloat16* w1 = w0 + 8 * p.ldw;
   uint4 ra[SK_MAX_KB], rb[SK_MAX_KB];
-  auto load_w = [&]() {
+  auto load_w = [&](int c0) {  // k-blocks [c0, c0 + SK_MAX_KB) of this warp
 #pragma unroll
     for (int j = 0; j < SK_MAX_KB; ++j) {
-      ra[j] = (ok0 && j < kbw) ? sk_ldg_stream(w0 + j * 32) : make_uint4(0, 0, 0, 0);
-      rb[j] = (ok1 && j < kbw) ? sk_ldg_stream(w1 + j * 32) : make_uint4(0, 0, 0, 0);
+      ra[j] = (ok0 && c0 + j < kbw) ? sk_ldg_stream(w0 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
+      rb[j] = (ok1 && c0 + j < kbw) ? sk_ldg_stream(w1 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
     }
   };
-  if (p.static_w) load_w();  // before the predecessor is awaited: the whole weight matrix is in flight across the grid
+  if (p.static_w) load_w(0);  // before the predecessor is awaited: (the first chunk of) the whole weight matrix is in flight
   pdl_wait();
-  if (!p.static_w) load_w();
+  if (!p.static_w) load_w(0);
 
   float acc[NG][4];
 #pragma unroll
   for (int i = 0; i < NG; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < kbw; c0 += SK_MAX_KB) {
+    if (c0 > 0) load_w(c0);
 #pragma unroll
-  for (int j = 0; j < SK_MAX_KB; ++j) {
-    if (j < kbw) {
-      uint4 xb[NG];
+    for (int j = 0; j < SK_MAX_KB; ++j) {
+      if (c0 + j < kbw) {
+        uint4 xb[NG];
 #pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        const int n = i * 8 + g;
-        xb[i] = n < p.n_tok ? __ldcg(reinterpret_cast<const uint4*>(p.X + static_cast<long long>(n) * p.ldx + k0 + j * 32)) : make_uint4(0, 0, 0, 0);
-      }
+        for (int i = 0; i < NG; ++i) {
+          const int n = i * 8 + g;
+          xb[i] = n < p.n_tok ? __ldcg(reinterpret_cast<const uint4*>(p.X + static_cast<long long>(n) * p.ldx + k0 + (c0 + j) * 32)) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        sk_mma(acc[i], ra[j].x, rb[j].x, ra[j].y, rb[j].y, xb[i].x, xb[i].y);
-        sk_mma(acc[i], ra[j].z, rb[j].z, ra[j].w, rb[j].w, xb[i].z, xb[i].w);
+        for (int i = 0; i < NG; ++i) {
+          sk_mma(acc[i], ra[j].x, rb[j].x, ra[j].y, rb[j].y, xb[i].x, xb[i].y);
+          sk_mma(acc[i], ra[j].z, rb[j].z, ra[j].w, rb[j].w, xb[i].z, xb[i].w);
+        }
       }
     }
   }
@@ -192,15 +196,22 @@ gemm_skinny_kernel(const SkinnyDev p) {
 static int skinny_ksplit(int F, int K) {
   const int units = (F + 15) / 16;
   static const int target_env = getenv("VY_SKINNY_CTAS") ? atoi(getenv("VY_SKINNY_CTAS")) : 0;  // development: sweep
-  const int target = target_env > 0 ? target_env : num_sms();
+  // one CTA per SM is enough while the whole matrix is a few MB (latency-bound; measured on the 768-wide decode step:
+  // profiles/r02_decode_skinny_sweep_*.txt); tens of MB (the 2048 x 16384 Gemma projections) need several resident CTAs per
+  // SM to keep enough loads in flight
+  long long mb3 = static_cast<long long>(F) * K * 2 / (3 << 20);
+  if (mb3 < 1) mb3 = 1;
+  if (mb3 > 4) mb3 = 4;
+  const int target = target_env > 0 ? target_env : num_sms() * static_cast<int>(mb3);
   int best = 0;
   long long best_score = -(1LL << 60);
   for (int s = 1; s <= 8; ++s) {
     if (K % s) continue;
     const int kc = K / s;
-    if (kc % (SK_WARPS * 32) || kc > SK_WARPS * SK_MAX_KB * 32) continue;
+    if (kc % (SK_WARPS * 32)) continue;
     const long long ctas = static_cast<long long>(units) * s;
-    const long long score = ctas <= target ? ctas : target - (ctas - target) / 4;  // more CTAs up to the target, then mildly worse
+    long long score = ctas <= target ? ctas : target - (ctas - target) / 4;  // more CTAs up to the target, then mildly worse
+    if (kc > SK_WARPS * SK_MAX_KB * 32) score -= num_sms() / 4;  // a second dependent round of weight loads per warp
     if (score > best_score) {
       best_score = score;
       best = s;

@@ -24,6 +24,7 @@ ACT = {
     "none": C["VY_ACT_NONE"],
     "gelu": C["VY_ACT_GELU_ERF"],
     "swiglu": C["VY_ACT_SWIGLU"],
+    "geglu_tanh": C["VY_ACT_GEGLU_TANH"],
     "gelu_erf": C["VY_ACT_GELU_ERF"],
     "gelu_tanh": C["VY_ACT_GELU_TANH"],
     "dgelu": C["VY_ACT_DGELU_ERF"],
@@ -129,9 +130,9 @@ def gemm(
         rows = M if out_row_group == 0 else None
         if rows is None:
             raise _lib.VyomError("gemm: pass `out` when using a row-group remap")
-        out = torch.empty((M, N // 2 if act == "swiglu" else N), device=a.device, dtype=odt)
-    if act == "swiglu" and (swap_ab or N % 2 or out.shape[-1] != N // 2):
-        raise _lib.VyomError("gemm: act='swiglu' takes interleaved gate/up rows (even N), writes N / 2 columns, no swap_ab")
+        out = torch.empty((M, N // 2 if act in ("swiglu", "geglu_tanh") else N), device=a.device, dtype=odt)
+    if act in ("swiglu", "geglu_tanh") and (swap_ab or N % 2 or out.shape[-1] != N // 2):
+        raise _lib.VyomError("gemm: act='swiglu' / 'geglu_tanh' takes interleaved gate/up rows (even N), writes N / 2 columns, no swap_ab")
     if out.stride(-1) != 1:
         raise _lib.VyomError("gemm: out must be row-major")
     a_mn, lda = _major(a, "gemm a")
@@ -176,7 +177,7 @@ def gemm(
         key = ("gemm", kw["M"], kw["N"], K, kw["in_dtype"], kw["a_mn_major"], kw["b_mn_major"], kw["transposed_out"], act,
                bias is not None, addend is not None, addend is not None and addend.data_ptr() == out.data_ptr(),
                addend2 is not None, aux is not None, out.dtype, allow_split_k, out_row_group, addend_row_mod, out_scale != 1.0)
-        saves_aux = aux is not None and act in ("gelu", "gelu_tanh", "swiglu")
+        saves_aux = aux is not None and act in ("gelu", "gelu_tanh", "swiglu", "geglu_tanh")
         kw.update(gemm_tune.hints(key, kw, [("out", out), ("aux", aux if saves_aux else None)], a.device))
     _lib.call("vy_gemm", "VyGemm", **kw)
     return out
@@ -375,10 +376,14 @@ def attn_fwd(
     out: Optional[torch.Tensor] = None,
     out_dtype: Optional[torch.dtype] = None,
     need_lse: bool = False,
+    prefix_len: Optional[torch.Tensor] = None,
 ):
-    """Flash attention forward. q [B,Hq,Sq,64], k/v [B,Hkv,Skv,64] (bf16, any batch/head/token
-    strides). Returns (out [B,Sq,Hq*64], lse [B,Hq,Sq] or None)."""
-    _need_cuda(q, k, v, key_padding_mask, out)
+    """Flash attention forward. q [B,Hq,Sq,D], k/v [B,Hkv,Skv,D] (bf16, any batch/head/token strides; D = 64 on the
+    tensor-memory kernel, any multiple of 8 up to 256 on the mma.sync one). `prefix_len` (int32 [B], with causal): keys below
+    it are visible to every query (prefix-LM). Returns (out [B,Sq,Hq*D], lse [B,Hq,Sq] or None)."""
+    _need_cuda(q, k, v, key_padding_mask, out, prefix_len)
+    if prefix_len is not None and (prefix_len.dtype != torch.int32 or not prefix_len.is_contiguous() or prefix_len.numel() != q.shape[0]):
+        raise _lib.VyomError("attn_fwd: prefix_len must be a contiguous int32 tensor with one entry per batch row")
     B, Hq, Sq, D = q.shape
     _, Hkv, Skv, _ = k.shape
     for t in (q, k, v):
@@ -401,7 +406,7 @@ def attn_fwd(
         causal=int(causal), q_pos0=q_pos0, key_padding_mask=_ptr(kpm),
         kpm_stride=kpm.stride(0) if kpm is not None else 0,
         out=out.data_ptr(), o_sb=out.stride(0), o_sl=out.stride(1), out_dtype=_dt(out), lse=_ptr(lse),
-        stream=_stream(),
+        prefix_len=_ptr(prefix_len), stream=_stream(),
     )
     return out, lse
 
@@ -544,16 +549,20 @@ def embed_bwd(ids: Optional[torch.Tensor], dout: torch.Tensor, *, rows: int, H: 
     )
 
 
-def patchify(pixels: torch.Tensor, patch: Tuple[int, int], dtype: torch.dtype) -> torch.Tensor:
-    """NCHW pixels -> [B * nP, C*ph*pw] patch rows in `dtype`."""
+def patchify(pixels: torch.Tensor, patch: Tuple[int, int], dtype: torch.dtype, pad_to: int = 1) -> torch.Tensor:
+    """NCHW pixels -> [B * nP, C*ph*pw] patch rows in `dtype`. pad_to > 1: rows are zero-padded to a multiple of `pad_to`
+    columns (a K the GEMM can take: 16-byte rows)."""
     _need_cuda(pixels)
     if not pixels.is_contiguous():
         raise _lib.VyomError("patchify: pixels must be contiguous NCHW")
     B, Cc, Hh, Ww = pixels.shape
     ph, pw = patch
-    out = torch.empty((B * (Hh // ph) * (Ww // pw), Cc * ph * pw), device=pixels.device, dtype=dtype)
+    K = Cc * ph * pw
+    Kp = (K + pad_to - 1) // pad_to * pad_to
+    rows = B * (Hh // ph) * (Ww // pw)
+    out = torch.empty((rows, K), device=pixels.device, dtype=dtype) if Kp == K else torch.zeros((rows, Kp), device=pixels.device, dtype=dtype)
     _lib.call("vy_patchify", "VyPatchify", B=B, C=Cc, H=Hh, W=Ww, patch_h=ph, patch_w=pw, pixels=pixels.data_ptr(),
-              in_dtype=_dt(pixels), out=out.data_ptr(), out_dtype=_dt(out), stream=_stream())
+              in_dtype=_dt(pixels), out=out.data_ptr(), out_dtype=_dt(out), ld_out=Kp if Kp != K else 0, stream=_stream())
     return out
 
 
