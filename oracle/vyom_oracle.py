@@ -737,3 +737,116 @@ def slot_loss(logits: Tensor, input_ids: Tensor, attention_mask: Tensor, pad_tok
     sl, lb = logits[:, :-1], labels[:, 1:]
     sel = attention_mask[:, 1:] != 0
     return torch.nn.functional.cross_entropy(sl[sel].float(), lb[sel], ignore_index=-100)
+
+# ---------------------------------------------------------------------------------------------
+# PaliGemma-scale scratch model (Examples/paligemma.ipynb cells 9-17, 28, 30): SigLIP tower + projector + Gemma decoder
+# ---------------------------------------------------------------------------------------------
+def siglip_forward(sd: SD, pre: str, pixels: Tensor, patch: int, n_layers: int, n_heads: int, eps: float) -> Tensor:
+    """SiglipVisionTransformer.forward (cell 9): stride == kernel conv patch embedding + learned positions, pre-norm layers
+    `x += attn(LN1(x)); x += fc2(gelu_tanh(fc1(LN2(x))))` with un-masked attention of scale head_dim^-0.5 (softmax in fp32),
+    then post_layernorm. `pre` ends with "vision_model."."""
+    w = sd[pre + "embeddings.patch_embedding.weight"]
+    x = torch.nn.functional.conv2d(pixels, w, sd[pre + "embeddings.patch_embedding.bias"], stride=patch)
+    x = x.flatten(2).transpose(1, 2)  # "b d h w -> b (h w) d"
+    x = x + sd[pre + "embeddings.position_embedding.weight"][None, : x.shape[1]]
+    H = x.shape[-1]
+    d = H // n_heads
+    for i in range(n_layers):
+        lp = f"{pre}encoder.layers.{i}."
+        h = layer_norm(x, sd[lp + "layer_norm1.weight"], sd[lp + "layer_norm1.bias"], eps)
+        q = split_heads(linear(h, sd[lp + "self_attn.q_proj.weight"], sd[lp + "self_attn.q_proj.bias"]), d)
+        k = split_heads(linear(h, sd[lp + "self_attn.k_proj.weight"], sd[lp + "self_attn.k_proj.bias"]), d)
+        v = split_heads(linear(h, sd[lp + "self_attn.v_proj.weight"], sd[lp + "self_attn.v_proj.bias"]), d)
+        a = merge_heads(sdpa(q, k, v, None))
+        x = x + linear(a, sd[lp + "self_attn.out_proj.weight"], sd[lp + "self_attn.out_proj.bias"])
+        h = layer_norm(x, sd[lp + "layer_norm2.weight"], sd[lp + "layer_norm2.bias"], eps)
+        h = gelu_tanh(linear(h, sd[lp + "mlp.fc1.weight"], sd[lp + "mlp.fc1.bias"]))
+        x = x + linear(h, sd[lp + "mlp.fc2.weight"], sd[lp + "mlp.fc2.bias"])
+    return layer_norm(x, sd[pre + "post_layernorm.weight"], sd[pre + "post_layernorm.bias"], eps)
+
+
+def gemma_rope(q: Tensor, k: Tensor, position_ids: Tensor, theta: float) -> Tuple[Tensor, Tensor]:
+    """GemmaRotaryEmbedding + apply_rotary_pos_emb (cell 11): inv_freq_i = theta^(-2i/d); angle = position * inv_freq; half-split
+    rotation x*cos + rotate_half(x)*sin, cos / sin cast to x.dtype. position_ids: (B, S)."""
+    d = q.shape[-1]
+    inv = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
+    ang = position_ids[:, :, None].float() * inv[None, None, :]
+    emb = torch.cat([ang, ang], dim=-1)
+    cos, sin = emb.cos().to(q.dtype)[:, None], emb.sin().to(q.dtype)[:, None]
+    return q * cos + rotate_half(q) * sin, k * cos + rotate_half(k) * sin
+
+
+def paligemma_mask(attention_mask: Tensor, seqlen: int, target: int, cache_position: Tensor, dtype,
+                   token_type_ids: Optional[Tensor] = None) -> Tensor:
+    """_update_causal_mask (cell 17) with a static cache of `target` slots: the sheet of slot_update_causal_mask (training =
+    upper triangle, inference = first seqlen columns cleared), x [column > cache_position[row]], padding columns of the
+    first attention_mask.shape[-1] set to finfo.min; in training the columns whose token_type_ids == 0 (image + prompt, and
+    — as written — pads) are then cleared for every row (prefix-LM)."""
+    mn = torch.finfo(dtype).min
+    is_training = token_type_ids is not None
+    sheet = torch.full((seqlen, target), mn, dtype=dtype)
+    if seqlen != 1:
+        if is_training:
+            sheet = torch.triu(sheet, diagonal=1)
+        else:
+            sheet[:, :seqlen] = 0.0
+    sheet = sheet * (torch.arange(target) > cache_position.reshape(-1, 1))
+    sheet = sheet[None, None].expand(attention_mask.shape[0], 1, -1, -1).clone()
+    ml = attention_mask.shape[-1]
+    pad = (sheet[..., :ml] + attention_mask[:, None, None, :].to(dtype)) == 0
+    sheet[..., :ml] = sheet[..., :ml].masked_fill(pad, mn)
+    if is_training:
+        sheet[..., :ml] = sheet[..., :ml].masked_fill(token_type_ids[:, None, None, :] == 0, 0)
+    return sheet
+
+
+def gemma_layers(sd: SD, pre: str, h: Tensor, mask: Tensor, position_ids: Tensor, n_layers: int, n_heads: int, n_kv: int, head_dim: int,
+                 eps: float, theta: float, cache=None, cache_position: Optional[Tensor] = None) -> Tensor:
+    """GemmaModel.forward after the embedding (cells 12, 13, 15): hidden * sqrt(H) (in the hidden dtype), pre-norm layers with
+    (1 + w) RMSNorm, bias-free q/k/v/o, RoPE, static kv-cache (k_out[:, :, cache_position] = k; attention over ALL its slots
+    under `mask`), GeGLU MLP down(gelu_tanh(gate(x)) * up(x)), final norm. `pre` ends with "model."."""
+    H = h.shape[-1]
+    h = h * torch.tensor(H ** 0.5, dtype=h.dtype)
+    for i in range(n_layers):
+        lp = f"{pre}layers.{i}."
+        x = rms_norm(h, sd[lp + "input_layernorm.weight"], eps, gemma=True)
+        q = split_heads(linear(x, sd[lp + "self_attn.q_proj.weight"], None), head_dim)
+        k = split_heads(linear(x, sd[lp + "self_attn.k_proj.weight"], None), head_dim)
+        v = split_heads(linear(x, sd[lp + "self_attn.v_proj.weight"], None), head_dim)
+        q, k = gemma_rope(q, k, position_ids, theta)
+        if cache is not None:
+            cache[0][i][:, :, cache_position] = k
+            cache[1][i][:, :, cache_position] = v
+            k, v = cache[0][i], cache[1][i]
+        kk, vv = repeat_kv(k, n_heads // n_kv), repeat_kv(v, n_heads // n_kv)
+        a = merge_heads(sdpa(q, kk, vv, mask[..., : kk.shape[-2]]))
+        h = h + linear(a, sd[lp + "self_attn.o_proj.weight"], None)
+        x = rms_norm(h, sd[lp + "post_attention_layernorm.weight"], eps, gemma=True)
+        g = gelu_tanh(linear(x, sd[lp + "mlp.gate_proj.weight"], None)) * linear(x, sd[lp + "mlp.up_proj.weight"], None)
+        h = h + linear(g, sd[lp + "mlp.down_proj.weight"], None)
+    return rms_norm(h, sd[pre + "norm.weight"], eps, gemma=True)
+
+
+def paligemma_forward(sd: SD, cfg: dict, input_ids: Tensor, pixels: Optional[Tensor], attention_mask: Tensor, cache=None,
+                      seen: int = 0, cache_len: Optional[int] = None, token_type_ids: Optional[Tensor] = None) -> Tensor:
+    """PaliGemmaForConditionalGeneration.forward (cell 17): embeddings, image features = projector(SigLIP(pixels)) / sqrt(H)
+    scattered into the image-token positions, 1-indexed positions (cache_position + 1), the mask above, Gemma, tied-or-not
+    lm_head (no bias). cfg: dict of the scalar hyper-parameters (see tests/golden/make_golden_paligemma.py). `cache` =
+    (key_list, value_list) of zero tensors [B, n_kv, cache_len, head_dim]; `seen` = tokens already in it."""
+    t, v = cfg["text"], cfg["vision"]
+    emb = sd["language_model.model.embed_tokens.weight"][input_ids]
+    bsz, seqlen = input_ids.shape
+    cache_position = torch.arange(seen, seen + seqlen)
+    position_ids = (cache_position + 1)[None].expand(bsz, -1)
+    if pixels is not None:
+        feats = siglip_forward(sd, "vision_tower.vision_model.", pixels, v["patch_size"], v["num_hidden_layers"], v["num_attention_heads"],
+                               v["layer_norm_eps"])
+        feats = linear(feats, sd["multi_modal_projector.linear.weight"], sd["multi_modal_projector.linear.bias"]) / (cfg["hidden_size"] ** 0.5)
+        is_img = input_ids == cfg["image_token_index"]
+        emb = emb.clone()
+        emb[is_img] = feats.reshape(-1, feats.shape[-1]).to(emb.dtype)[: int(is_img.sum())]
+    target = cache_len if cache is not None else attention_mask.shape[-1]
+    mask = paligemma_mask(attention_mask, seqlen, target, cache_position, emb.dtype, token_type_ids)
+    h = gemma_layers(sd, "language_model.model.", emb, mask, position_ids, t["num_hidden_layers"], t["num_attention_heads"],
+                     t["num_key_value_heads"], t["head_dim"], t["rms_norm_eps"], t["rope_theta"], cache, cache_position)
+    return linear(h, sd["language_model.lm_head.weight"], None)

@@ -649,6 +649,22 @@ def rope_apply(x: torch.Tensor, freqs: torch.Tensor, inverse: bool = False) -> t
     return out
 
 
+def rope_into(x: torch.Tensor, out: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, pos0: int, inverse: bool = False) -> torch.Tensor:
+    """Half-split RoPE of x [B, h, S, D] (any batch / head / token strides, D contiguous and even) written to `out` (same shape,
+    its own strides — e.g. a kv-cache slot range; out may be x itself). cos / sin: fp32 [rows, D / 2] tables, row pos0 + l is
+    used for token l."""
+    _need_cuda(x, out, cos, sin)
+    B, Hh, S, D = x.shape
+    if x.stride(3) != 1 or out.stride(3) != 1 or tuple(out.shape) != tuple(x.shape) or out.dtype != x.dtype:
+        raise _lib.VyomError("rope_into: x and out must share shape and dtype with a contiguous head_dim")
+    if cos.dtype != torch.float32 or cos.shape[1] != D // 2 or not cos.is_contiguous() or not sin.is_contiguous() or cos.shape[0] < pos0 + S:
+        raise _lib.VyomError("rope_into: cos / sin must be contiguous fp32 [>= pos0 + S, D / 2] tables")
+    _lib.call("vy_rope_apply", "VyRope", B=B, H=Hh, S=S, head_dim=D, x=x.data_ptr(), x_sb=x.stride(0), x_sh=x.stride(1),
+              x_sl=x.stride(2), dtype=_dt(x), cos=cos.data_ptr(), sin=sin.data_ptr(), pos0=pos0, inverse=int(inverse),
+              out=out.data_ptr(), o_sb=out.stride(0), o_sh=out.stride(1), o_sl=out.stride(2), stream=_stream())
+    return out
+
+
 def act_bwd(dy: torch.Tensor, z: torch.Tensor, act: str = "gelu") -> torch.Tensor:
     """dy * act'(z), elementwise (contiguous, same dtype)."""
     _need_cuda(dy, z)
