@@ -579,6 +579,124 @@ def measure_configs_1_2(dev):
     return out
 
 
+C5_VISION = dict(hidden_size=1152, intermediate_size=4304, num_hidden_layers=27, num_attention_heads=16, num_channels=3, image_size=224,
+                 patch_size=14, layer_norm_eps=1e-6)
+C5_TEXT = dict(vocab_size=257216, hidden_size=2048, intermediate_size=16384, num_hidden_layers=18, num_attention_heads=8,
+               num_key_value_heads=1, head_dim=256, max_position_embeddings=8192, rms_norm_eps=1e-6, rope_theta=10000.0)
+
+
+def measure_config5(dev, batches=(1, 32), new_tokens=50, cpu=True):
+    """BASELINE configs[4]: PaliGemma-scale scratch model (SigLIP 27 x 1152 / 14-pixel patches + Gemma 18 x 2048, 8 q heads,
+    1 kv head of 256, GeGLU 16384, vocab 257216, tied head), random init, bf16: prefill of 256 image + 8 text tokens, then
+    `new_tokens` greedy tokens through a 384-slot static cache — the procedure of Examples/paligemma.ipynb cell 30.
+    HBM floor per decoded token: every weight once (5.02 GB incl. the tied table as lm_head) + the kv rows."""
+    from vyomai_b200.models.paligemma import PaliGemmaConfig, PaliGemmaForConditionalGeneration, StaticCache
+    out = {"workload": "paligemma_scale_siglip27x1152_gemma18x2048_mqa256_prefill264_decode%d_bf16_staticcache384" % new_tokens}
+    try:
+        cfg = PaliGemmaConfig(vision_config=dict(C5_VISION), text_config=dict(C5_TEXT), image_token_index=257152, vocab_size=257216,
+                              projection_dim=2048, hidden_size=2048, pad_token_id=0)
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            with torch.device(dev):
+                torch.manual_seed(0)
+                model = PaliGemmaForConditionalGeneration(cfg)
+        finally:
+            torch.set_default_dtype(old)
+        model.tie_weights()
+        model.eval()
+        with torch.no_grad():
+            for n, p in model.named_parameters():  # N(0, 0.02) like a scratch init; norms near identity
+                if p.dim() >= 2:
+                    p.normal_(0.0, 0.02)
+        n_params = sum(p.numel() for p in model.parameters())
+        lm_params = sum(p.numel() for n, p in model.language_model.named_parameters())
+        out["params_B"] = round(n_params / 1e9, 3)
+        hbm = peaks()[0]
+        g = torch.Generator().manual_seed(5)
+        for B in batches:
+            ids = torch.cat([torch.full((B, 256), 257152, dtype=torch.long), torch.randint(2, 250000, (B, 8), generator=g)], dim=1).to(dev)
+            mask = torch.ones((B, 264), dtype=torch.long, device=dev)
+            px = torch.rand((B, 3, 224, 224), generator=g).to(dev).to(torch.bfloat16)
+
+            def run(n_new):
+                cache = StaticCache(cfg.text_config, batch_size=B, device=dev, dtype=torch.bfloat16, max_cache_len=384)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                cur, cm = ids, mask
+                ev[0].record()
+                o = model(input_ids=cur, pixel_values=px, attention_mask=cm, past_key_values=cache, use_cache=True, logits_last_only=True)
+                from vyomai_b200 import ops
+                nxt = ops.argmax_rows(o.logits[:, -1]).view(B, 1)
+                ev[1].record()
+                for _ in range(n_new - 1):
+                    cm = torch.cat([cm, torch.ones((B, 1), device=dev, dtype=cm.dtype)], dim=-1)
+                    o = model(input_ids=nxt, pixel_values=None, attention_mask=cm, past_key_values=cache, use_cache=True, logits_last_only=True)
+                    nxt = ops.argmax_rows(o.logits[:, -1]).view(B, 1)
+                ev[2].record()
+                torch.cuda.synchronize()
+                return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]) / (n_new - 1)
+
+            run(4)  # warm-up: weight packing, GEMM tuning, lazy module loads
+            pre_ms, step_ms = run(new_tokens)
+            kv_bytes = 2.0 * B * 18 * 2 * 1 * (264 + new_tokens / 2) * 256
+            step_bytes = 2.0 * lm_params + kv_bytes  # (tied table counted once: it is read as the lm_head)
+            out[f"B{B}"] = {"prefill_ms": pre_ms, "prefill_tok_per_s": B * 264 / (pre_ms / 1e3), "decode_ms_per_step": step_ms,
+                            "decode_tok_per_s": B / (step_ms / 1e3), "decode_step_algorithmic_GB": step_bytes / 1e9,
+                            "decode_hbm_frac": step_bytes / (step_ms / 1e3) / 1e9 / hbm, "timed_as": "eager launches, CUDA events"}
+        del model
+        torch.cuda.empty_cache()
+    except Exception as e:  # the headline line must still be printed
+        out["error"] = f"{type(e).__name__}: {str(e)[:300]}"
+        return out
+    if cpu:
+        try:
+            import psutil
+            if psutil.virtual_memory().available < 48e9:
+                out["cpu_port"] = {"skipped": "less than 48 GB of free host memory for the fp32 weights (11.7 GB) and activations"}
+                return out
+            from oracle import vyom_oracle as O
+            cores = host_threads()
+            t0 = time.perf_counter()
+            sd = {}
+            gg = torch.Generator().manual_seed(1)
+
+            def w(name, *shape):
+                sd[name] = torch.empty(shape).normal_(0.0, 0.02, generator=gg)
+
+            t = C5_TEXT
+            w("language_model.model.embed_tokens.weight", t["vocab_size"], t["hidden_size"])
+            sd["language_model.lm_head.weight"] = sd["language_model.model.embed_tokens.weight"]
+            for i in range(t["num_hidden_layers"]):
+                lp = f"language_model.model.layers.{i}."
+                w(lp + "self_attn.q_proj.weight", 2048, 2048); w(lp + "self_attn.k_proj.weight", 256, 2048)
+                w(lp + "self_attn.v_proj.weight", 256, 2048); w(lp + "self_attn.o_proj.weight", 2048, 2048)
+                w(lp + "mlp.gate_proj.weight", 16384, 2048); w(lp + "mlp.up_proj.weight", 16384, 2048); w(lp + "mlp.down_proj.weight", 2048, 16384)
+                sd[lp + "input_layernorm.weight"] = torch.zeros(2048); sd[lp + "post_attention_layernorm.weight"] = torch.zeros(2048)
+            sd["language_model.model.norm.weight"] = torch.zeros(2048)
+            build_s = time.perf_counter() - t0
+            cfgd = {"hidden_size": 2048, "image_token_index": 257152, "text": t, "vision": C5_VISION}
+            ids = torch.randint(2, 250000, (1, 264), generator=gg)  # text-only prompt of the same length: the decode steps are what is timed
+            mask = torch.ones(1, 264, dtype=torch.long)
+            cache = ([torch.zeros(1, 1, 384, 256) for _ in range(18)], [torch.zeros(1, 1, 384, 256) for _ in range(18)])
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                lg = O.paligemma_forward(sd, cfgd, ids, None, mask, cache=cache, seen=0, cache_len=384)
+                pre_s = time.perf_counter() - t0
+                nxt = lg[:, -1].argmax(-1, keepdim=True)
+                ts = []
+                for s in range(3):
+                    mask = torch.cat([mask, torch.ones(1, 1, dtype=mask.dtype)], -1)
+                    t0 = time.perf_counter()
+                    lg = O.paligemma_forward(sd, cfgd, nxt, None, mask, cache=cache, seen=264 + s, cache_len=384)
+                    ts.append(time.perf_counter() - t0)
+                    nxt = lg[:, -1].argmax(-1, keepdim=True)
+            out["cpu_port"] = {"decode_tok_per_s": 1.0 / min(ts), "prefill_tok_per_s": 264 / pre_s, "cores": cores, "dtype": "f32", "batch": 1,
+                               "sample": f"Gemma decoder only (text prompt of 264 tokens), 3 decode steps, best; weights built in {build_s:.0f} s"}
+        except Exception as e:
+            out["cpu_port"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from vyomai_b200 import _lib
@@ -711,6 +829,9 @@ def run_ours(args):
     small = None
     if world == 1 and args.workload == "package" and not args.no_configs_1_2:
         small = measure_configs_1_2(dev)  # BASELINE configs[0], [1]
+    c5 = None
+    if world == 1 and args.workload == "package" and not args.no_config5:
+        c5 = measure_config5(dev, cpu=not args.no_cpu_baseline)  # BASELINE configs[4]
     slots = None
     if world == 1 and args.workload == "package" and not args.no_slots:
         slots = measure_slots(dev, args.steps, args.warmup)  # BASELINE configs[3] in its notebook-II form, same GPU
@@ -732,7 +853,7 @@ def run_ours(args):
                        "cuda_graph": not args.no_graph, "grad_overwrite": bool(trainer.grad_overwrite)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof, "cpu_baseline": cpu,
-            "kernel_breakdown_ms": breakdown, "kernel_breakdown_sum_ms": round(total_ms, 3), "decode": decode, "notebook_II": slots, "configs_1_2": small,
+            "kernel_breakdown_ms": breakdown, "kernel_breakdown_sum_ms": round(total_ms, 3), "decode": decode, "notebook_II": slots, "configs_1_2": small, "config_5": c5,
             "final_loss": final_loss, "e2e_last_loss": last,
         }
         print(json.dumps(line), flush=True)
@@ -757,6 +878,7 @@ def main():
                     help="package: VisionLanguageModel of the reference package (1 image token + 127 text, the headline since round 1); "
                          "slots: the notebook-II form (197 image tokens in a 248-token sequence)")
     ap.add_argument("--no-configs-1-2", action="store_true", help="skip the encoder (C1) / ViT (C2) measurements appended at N = 1")
+    ap.add_argument("--no-config5", action="store_true", help="skip the PaliGemma-scale prefill + decode measurement appended at N = 1")
     ap.add_argument("--no-slots", action="store_true", help="skip the notebook-II measurement appended at N = 1")
     ap.add_argument("--no-decode", action="store_true", help="skip the config-3 decode measurement appended at N = 1")
     ap.add_argument("--no-grad-overwrite", action="store_true", help="zero + accumulate every gradient instead of overwrite mode")

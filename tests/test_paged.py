@@ -130,15 +130,21 @@ def test_paged_decode_kernel_matches_oracle_and_contiguous_mode(dtype, tol, bs, 
         o1 = ops.attn_decode(qkv[b:b + 1].to(dev), kcd[b:b + 1], vcd[b:b + 1], ctx[b], Hq, Hkv, cos.to(dev), sin.to(dev),
                              out_dtype=torch.float32)
         assert float((o1[0] - out[b]).abs().max()) < 1e-4 * max(1.0, float(out[b].abs().max())), b
-    # the call the notebook makes, when flash-attn runs here
-    try:
-        from flash_attn import flash_attn_with_kvcache
-        fa = flash_attn_with_kvcache(qr.to(dev).to(torch.bfloat16).unsqueeze(1), kp.to(torch.bfloat16), vp.to(torch.bfloat16),
-                                     cache_seqlens=seq + 1, block_table=table.to(dev), causal=True)
-        fa_err = float((fa.float().reshape(B, -1).cpu() - ref).norm() / ref.norm())
-        assert fa_err < 2e-2, fa_err  # flash-attn computes in bf16
-    except (ImportError, RuntimeError) as e:  # not built for this GPU: the oracle comparison above stands alone
-        print("flash_attn_with_kvcache not usable here:", str(e)[:100])
+    # The call the notebook makes (Examples/simple_vllm.ipynb cell 2: flash_attn_with_kvcache over the block table) — an
+    # implementation independent of this repo and of the oracle. flash-attn 2.8 pages by multiples of 256 slots, so the pin
+    # runs in the block-size-256 cases; it is mandatory there whenever the package imports (no except around the call).
+    if bs % 256 == 0:
+        try:
+            from flash_attn import flash_attn_with_kvcache
+        except ImportError:
+            flash_attn_with_kvcache = None
+        if flash_attn_with_kvcache is not None:
+            fa = flash_attn_with_kvcache(qr.to(dev).to(torch.bfloat16).unsqueeze(1), kp.to(torch.bfloat16), vp.to(torch.bfloat16),
+                                         cache_seqlens=seq + 1, block_table=table.to(dev), causal=True)
+            fa_err = float((fa.float().reshape(B, -1).cpu() - ref).norm() / ref.norm())
+            ours_vs_fa = float((fa.float().reshape(B, -1) - out).norm() / out.norm())
+            assert fa_err < 2e-2 and ours_vs_fa < 2e-2, (fa_err, ours_vs_fa)  # flash-attn computes in bf16
+            print(f"paged decode pinned by flash_attn_with_kvcache: oracle vs flash-attn {fa_err:.2e}, kernel vs flash-attn {ours_vs_fa:.2e}")
 
 
 @pytest.mark.gpu
