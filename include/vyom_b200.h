@@ -313,6 +313,9 @@ typedef struct VyAttn {
    * training mask of Examples/paligemma.ipynb cell 17 `_update_causal_mask` (image + prompt tokens attend to each other in
    * both directions, the suffix is causal). NULL = plain causal. */
   const int32_t* prefix_len;
+  /* Device-side position (mma.sync kernel only; NULL = off): the keys are [0, min(Skv, *pos_ptr + Sq)) and q_pos0 = *pos_ptr —
+   * Skv is then the capacity of the cache the k / v pointers address, so one captured graph serves every decode step. */
+  const int32_t* pos_ptr;
   void* stream;
 } VyAttn;
 
@@ -378,6 +381,11 @@ typedef struct VyRope {
   int32_t pos0, inverse;
   void* out;
   int64_t o_sb, o_sh, o_sl;
+  /* Device-side position (all optional, zero = off) so that ONE captured CUDA graph serves every decode step:
+   * pos_ptr: int32 scalar added to pos0; out_follows_pos: token l is written at out token index l + *pos_ptr (out = base of a
+   * kv-cache: the append); copy_only: no rotation, a plain strided copy (values go into the cache unrotated). */
+  const int32_t* pos_ptr;
+  int32_t out_follows_pos, copy_only;
   void* stream;
 } VyRope;
 

@@ -196,5 +196,44 @@ def test_paligemma_model_matches_the_notebook():
         assert int(got[0, s]) == int(ref_ids[0, s]), (s, got.tolist(), ref_ids.tolist())
         n_ok += 1
     print(f"paligemma greedy ids equal to the notebook's for {n_ok}/{ref_ids.shape[1]} steps (margins {[round(x, 3) for x in m['generate_margins']]})")
+    # the CUDA-graph path (default, device-side position, split packed-head attention) against the notebook-style eager loop
+    eager = paligemma_generate(model, ids[row:row + 1, :L], px[row:row + 1], mask[row:row + 1, :L], max_tokens_to_generate=ref_ids.shape[1],
+                               max_cache_len=m["cache_len"], use_graph=False)
+    for s, mg in enumerate(m["generate_margins"]):
+        if mg < 0.2:
+            break
+        assert int(eager[0, s]) == int(ref_ids[0, s]) == int(got[0, s])
     gb = paligemma_generate(model, ids, px, mask, max_tokens_to_generate=3, max_cache_len=m["cache_len"])
-    assert list(gb.shape) == [3, 3]
+    ge = paligemma_generate(model, ids, px, mask, max_tokens_to_generate=3, max_cache_len=m["cache_len"], use_graph=False)
+    assert list(gb.shape) == [3, 3] and torch.equal(gb[:, 0], ge[:, 0])  # (the prefill token: identical code path)
+
+
+@pytest.mark.gpu
+def test_paligemma_graph_decode_step_matches_eager_step_logits():
+    """One replayed step of PaliGemmaDecodeGraph against the eager single-token forward on copies of the same cache: the token
+    chosen, the cache row written at the device-side position, and nothing else touched."""
+    import copy
+    from vyomai_b200 import ops
+    from vyomai_b200.models.paligemma import PaliGemmaDecodeGraph, StaticCache
+    fx = load_fixture(NAME)
+    m = fx.meta
+    model, cfg = _build(fx)
+    ids, mask, px = fx.inputs["input_ids"].cuda(), fx.inputs["attention_mask"].cuda(), fx.inputs["pixel_values"].cuda().bfloat16()
+    B, S0 = ids.shape
+    cache = StaticCache(cfg.text_config, batch_size=B, device="cuda", dtype=torch.bfloat16, max_cache_len=m["cache_len"])
+    o = model(input_ids=ids, pixel_values=px, attention_mask=mask, past_key_values=cache, use_cache=True, logits_last_only=True)
+    first = ops.argmax_rows(o.logits[:, -1])
+    cache2 = copy.deepcopy(cache)
+    am = torch.cat([mask, torch.ones(B, 1, dtype=mask.dtype, device="cuda")], -1)
+    e = model(input_ids=first.view(B, 1), attention_mask=am, past_key_values=cache2, use_cache=True, logits_last_only=True)
+    want = ops.argmax_rows(e.logits[:, -1])
+    g = PaliGemmaDecodeGraph(model, cache, mask)
+    out = torch.empty((B, 2), dtype=torch.long, device="cuda")
+    g.run(first, S0, 1, out)
+    top2 = e.logits[:, -1].float().topk(2, -1).values
+    sure = (top2[:, 0] - top2[:, 1]) > 0.1
+    assert torch.equal(out[sure, 0], want[sure])
+    for li in range(len(cache.key_cache)):
+        assert rel_l2(cache.key_cache[li][:, :, :S0 + 1].float().cpu(), cache2.key_cache[li][:, :, :S0 + 1].float().cpu()) <= 1e-2
+        assert rel_l2(cache.value_cache[li][:, :, :S0 + 1].float().cpu(), cache2.value_cache[li][:, :, :S0 + 1].float().cpu()) <= 1e-2
+        assert float(cache.key_cache[li][:, :, S0 + 1:].abs().max()) == 0.0

@@ -399,7 +399,7 @@ extern "C" int vy_attn_fwd(const VyAttn* p) {
   if (p->causal) VY_CHECK_ARG(p->q_pos0 >= 0, "vy_attn_fwd: negative q_pos0");
   // head dims other than 64 and the prefix-LM mask: the mma.sync kernel (attn_fwd_mma.cu); VY_ATTN_MMA=1 sends everything there
   static const bool force_mma = getenv("VY_ATTN_MMA") && atoi(getenv("VY_ATTN_MMA")) != 0;
-  if (p->head_dim != 64 || (p->causal && p->prefix_len) || force_mma) return attn_fwd_mma(p);
+  if (p->head_dim != 64 || (p->causal && p->prefix_len) || p->pos_ptr || force_mma) return attn_fwd_mma(p);
   auto ok16 = [](const void* ptr, long long a, long long b_, long long c) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (a * 2) % 16 == 0 && (b_ * 2) % 16 == 0 && (c * 2) % 16 == 0;
   };

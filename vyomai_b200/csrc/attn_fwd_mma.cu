@@ -32,13 +32,22 @@ struct AttnMmaDev {
   const unsigned char* kpm;
   long long kpm_stride;
   const int* prefix_len;
+  const int* pos_ptr;
   void* out;
   long long o_sb, o_sl;
   int out_dt;
   float* lse;
   float scale_log2;
   int pack_heads;  // Sq == 1: tile row r = query head kvh * n_rep + r
+  int splits;      // pack_heads only: the key blocks are divided over gridDim.x CTAs, combined by the last one to finish
 };
+
+// split-key decode: partial (o[D], m, l) per (batch row, kv head, split, query head of the group) + a ticket per (row, kv head).
+// Library-owned scratch (like the norm / squared-norm partials): calls that split must not run concurrently on two streams.
+constexpr int AM_WS_FLOATS = 1 << 20;
+constexpr int AM_MAX_TICKETS = 4096;
+__device__ float am_ws[AM_WS_FLOATS];
+__device__ unsigned int am_tickets[AM_MAX_TICKETS];
 
 __device__ __forceinline__ void am_ldmatrix_x4(unsigned (&r)[4], unsigned addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -60,7 +69,7 @@ __device__ __forceinline__ unsigned am_pack(float lo, float hi) {
 // the 8 row addresses of an ldmatrix fall into distinct 16-byte bank groups.
 template <int DP>
 __global__ void __launch_bounds__(AM_WARPS * 32)
-attn_fwd_mma_kernel(const AttnMmaDev g) {
+attn_fwd_mma_kernel(AttnMmaDev g) {
   extern __shared__ __align__(16) unsigned char am_smem[];
   constexpr int ROWB = DP * 2 + 16;
   unsigned char* sQ = am_smem;
@@ -68,6 +77,11 @@ attn_fwd_mma_kernel(const AttnMmaDev g) {
   unsigned char* sV = sK + AM_BN * ROWB;
   pdl_trigger();
   pdl_wait();
+  if (g.pos_ptr) {  // device-side position: keys [0, pos + Sq) of a cache with Skv slots
+    const int pos = *g.pos_ptr;
+    g.q_pos0 = pos;
+    g.Skv = min(g.Skv, pos + g.Sq);
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
   const int b = blockIdx.z;
@@ -109,7 +123,14 @@ attn_fwd_mma_kernel(const AttnMmaDev g) {
   const __nv_bfloat16* vbase = g.v + static_cast<long long>(b) * g.v_sb + static_cast<long long>(kvh) * g.v_sh;
 
   const int n_blocks = (g.Skv + AM_BN - 1) / AM_BN;
-  for (int kb = 0; kb < n_blocks; ++kb) {
+  int kb_lo = 0, kb_hi = n_blocks;
+  if (g.splits > 1) {  // this CTA's share of the key blocks (possibly empty)
+    const int per = (n_blocks + g.splits - 1) / g.splits;
+    kb_lo = min(n_blocks, static_cast<int>(blockIdx.x) * per);
+    kb_hi = min(n_blocks, kb_lo + per);
+    __syncthreads();  // Q stored (the loop's first barrier may not run)
+  }
+  for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int k0 = kb * AM_BN;
     __syncthreads();  // previous block's K / V fully consumed (and, first time, Q stored)
     for (int i = threadIdx.x; i < AM_BN * (DP / 8); i += blockDim.x) {
@@ -219,6 +240,57 @@ attn_fwd_mma_kernel(const AttnMmaDev g) {
     }
   }
 
+  if (g.splits > 1) {
+    // ---- partial results -> scratch; the last CTA of this (batch row, kv head) combines them in split order ----
+    const long long slot0 = (static_cast<long long>(b) * g.Hkv + kvh) * g.splits;
+    const int stride = g.D + 2;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int r = warp * 16 + gq + e * 8;
+      if (r >= rows_valid) continue;
+      float* w = am_ws + ((slot0 + blockIdx.x) * g.n_rep + r) * stride;
+#pragma unroll
+      for (int i = 0; i < DP / 8; ++i) {
+        const int d = i * 8 + tq * 2;
+        if (d < g.D) {
+          w[d] = o_acc[i][2 * e];
+          w[d + 1] = o_acc[i][2 * e + 1];
+        }
+      }
+      if (tq == 0) {
+        w[g.D] = m_run[e];
+        w[g.D + 1] = l_run[e];
+      }
+    }
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(&am_tickets[b * g.Hkv + kvh], 1u);
+      s_last = prev == static_cast<unsigned int>(g.splits - 1) ? 1u : 0u;
+      if (s_last) am_tickets[b * g.Hkv + kvh] = 0u;  // self-reset for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int idx = threadIdx.x; idx < g.n_rep * g.D; idx += blockDim.x) {
+      const int r = idx / g.D, d = idx - r * g.D;
+      float M = -INFINITY;
+      for (int sp = 0; sp < g.splits; ++sp) M = fmaxf(M, __ldcg(am_ws + ((slot0 + sp) * g.n_rep + r) * stride + g.D));
+      float L = 0.f, O = 0.f;
+      for (int sp = 0; sp < g.splits; ++sp) {
+        const float* w = am_ws + ((slot0 + sp) * g.n_rep + r) * stride;
+        const float ms = __ldcg(w + g.D);
+        if (ms == -INFINITY) continue;  // an empty share
+        const float a = exp2f(ms - M);
+        L += __ldcg(w + g.D + 1) * a;
+        O += __ldcg(w + d) * a;
+      }
+      st_from_float(g.out, g.out_dt, static_cast<long long>(b) * g.o_sb + static_cast<long long>(h_blk + r) * g.D + d, O / L);
+    }
+    return;
+  }
+
   // ---- epilogue: O / l -> out[b, l, h * D + d] ----
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
@@ -257,7 +329,7 @@ static int launch_attn_mma(const AttnMmaDev& g, cudaStream_t st) {
     VY_CUDA_OK(cudaFuncSetAttribute(attn_fwd_mma_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_done[dev] = true;
   }
-  const dim3 grid(g.pack_heads ? 1 : (g.Sq + AM_BM - 1) / AM_BM, g.pack_heads ? g.Hkv : g.Hq, g.B);
+  const dim3 grid(g.pack_heads ? g.splits : (g.Sq + AM_BM - 1) / AM_BM, g.pack_heads ? g.Hkv : g.Hq, g.B);
   VY_CUDA_OK(launch_kernel(attn_fwd_mma_kernel<DP>, grid, dim3(AM_WARPS * 32), smem, st, g));
   VY_LAUNCH_OK();
   count_launch();
@@ -282,12 +354,23 @@ int attn_fwd_mma(const VyAttn* p) {
   g.v = static_cast<const __nv_bfloat16*>(p->v); g.v_sb = p->v_sb; g.v_sh = p->v_sh; g.v_sl = p->v_sl;
   g.causal = p->causal; g.q_pos0 = p->q_pos0; g.kpm = p->key_padding_mask; g.kpm_stride = p->kpm_stride;
   g.prefix_len = p->causal ? p->prefix_len : nullptr;
+  g.pos_ptr = p->pos_ptr;
   g.out = p->out; g.o_sb = p->o_sb; g.o_sl = p->o_sl; g.out_dt = p->out_dtype; g.lse = p->lse;
   g.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p->head_dim));
   // single-token decode of a grouped model: the group's query heads share one tile (a causal mask is vacuous at Sq == 1
   // only when the query sits at the end of the keys, which is what q_pos0 + 1 == Skv says)
-  g.pack_heads = (p->Sq == 1 && g.n_rep > 1 && g.n_rep <= AM_BM && (!p->causal || p->q_pos0 + 1 >= p->Skv)) ? 1 : 0;
+  g.pack_heads = (p->Sq == 1 && g.n_rep > 1 && g.n_rep <= AM_BM && (!p->causal || p->pos_ptr || p->q_pos0 + 1 >= p->Skv)) ? 1 : 0;
   if (g.pack_heads) g.causal = 0;
+  g.splits = 1;
+  if (g.pack_heads && !p->lse) {
+    // few (row, kv head) pairs: one CTA each would stream the whole context alone (65 us per Gemma layer at batch 1)
+    const int pairs = p->B * p->n_kv_heads, blocks = (p->Skv + AM_BN - 1) / AM_BN;
+    int sp = pairs >= num_sms() ? 1 : (num_sms() + pairs - 1) / pairs;
+    if (sp > blocks) sp = blocks;
+    if (sp > 16) sp = 16;
+    const long long need = static_cast<long long>(pairs) * sp * g.n_rep * (p->head_dim + 2);
+    if (sp > 1 && need <= AM_WS_FLOATS && pairs <= AM_MAX_TICKETS) g.splits = sp;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(p->stream);
   const int dp = (p->head_dim + 15) / 16 * 16;
   if (dp <= 64) return launch_attn_mma<64>(g, st);

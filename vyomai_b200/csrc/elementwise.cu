@@ -554,9 +554,12 @@ slot_merge_kernel(int rows, int vec_per_row, const uint4* __restrict__ a, const 
 __global__ void __launch_bounds__(256)
 rope_kernel(int B, int H, int S, int D, const void* __restrict__ x, long long xsb, long long xsh, long long xsl, int dt,
             const float* __restrict__ cs, const float* __restrict__ sn, int pos0, int inverse, void* __restrict__ out,
-            long long osb, long long osh, long long osl) {
+            long long osb, long long osh, long long osl, const int* __restrict__ pos_ptr, int out_follows_pos, int copy_only) {
   pdl_trigger();
   pdl_wait();
+  const int pos_dev = pos_ptr ? *pos_ptr : 0;  // device-side position: one captured graph serves every decode step
+  pos0 += pos_dev;
+  const long long out_shift = out_follows_pos ? static_cast<long long>(pos_dev) * osl : 0;
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -565,8 +568,12 @@ rope_kernel(int B, int H, int S, int D, const void* __restrict__ x, long long xs
     const int l = static_cast<int>(r % S);
     const int h = static_cast<int>((r / S) % H);
     const int b = static_cast<int>(r / (static_cast<long long>(S) * H));
-    const long long xi = b * xsb + h * xsh + l * xsl, oi = b * osb + h * osh + l * osl;
+    const long long xi = b * xsb + h * xsh + l * xsl, oi = b * osb + h * osh + l * osl + out_shift;
     const int half = D >> 1;
+    if (copy_only) {  // (values: appended to the cache unrotated)
+      for (int j = lane; j < D; j += 32) st_from_float(out, dt, oi + j, ld_as_float(x, dt, xi + j));
+      continue;
+    }
     for (int j = lane; j < half; j += 32) {
       const float a = ld_as_float(x, dt, xi + j), bb = ld_as_float(x, dt, xi + j + half);
       const float c = cs[static_cast<long long>(pos0 + l) * half + j];
@@ -827,10 +834,10 @@ extern "C" int vy_rope_apply(const VyRope* p) {
   VY_CHECK_ARG(p != nullptr, "vy_rope_apply: null params");
   VY_NEED_DEVICE("vy_rope_apply");
   VY_CHECK_ARG(p->head_dim >= 2 && (p->head_dim & 1) == 0, "vy_rope_apply: head_dim must be even (got %d)", p->head_dim);
-  VY_CHECK_ARG(p->B > 0 && p->H > 0 && p->S > 0 && p->x && p->out && p->cos && p->sin && dtype_ok(p->dtype), "vy_rope_apply: bad arguments");
+  VY_CHECK_ARG(p->B > 0 && p->H > 0 && p->S > 0 && p->x && p->out && (p->copy_only || (p->cos && p->sin)) && dtype_ok(p->dtype), "vy_rope_apply: bad arguments");
   const long long rows = static_cast<long long>(p->B) * p->H * p->S;
   VY_CUDA_OK(launch_kernel(rope_kernel, dim3(ew_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
-      p->B, p->H, p->S, p->head_dim, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl));
+      p->B, p->H, p->S, p->head_dim, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl, p->pos_ptr, p->out_follows_pos, p->copy_only));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -321,22 +321,37 @@ class GemmaModel(nn.Module):
         self.norm = GemmaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self._rope = _RopeTable(config.head_dim, config.rope_theta)
 
-    def run_layers(self, h: torch.Tensor, B: int, S: int, start: int, key_padding: Optional[torch.Tensor], cache: Optional[StaticCache],
+    def run_layers(self, h: torch.Tensor, B: int, S: int, start, key_padding: Optional[torch.Tensor], cache: Optional[StaticCache],
                    prefix_visible: bool) -> torch.Tensor:
         """h: [B * S, H] embeddings already multiplied by sqrt(H). Tokens sit at cache slots [start, start + S), positions
-        start + 1 .. . Without a cache (plain forward) K / V are the new rows themselves."""
+        start + 1 .. . Without a cache (plain forward) K / V are the new rows themselves. `start` may be a device int32 scalar
+        (S == 1, with a cache): RoPE row, cache slot and the attention's key range then follow it on the device, so the
+        captured step can be replayed for every token (PaliGemmaDecodeGraph)."""
         cfg = self.config
         T = h.dtype
         nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
-        cos, sin = self._rope.get(start + S + 1, h.device, T)
+        on_dev = torch.is_tensor(start)
+        pos_dev = start if on_dev else None
+        if on_dev:
+            if S != 1 or cache is None:
+                raise ValueError("a device-side position serves single-token steps over a cache")
+            start = 0
+            cos, sin = self._rope.get(cache.max_cache_len + 2, h.device, T)
+        else:
+            cos, sin = self._rope.get(start + S + 1, h.device, T)
         for li, layer in enumerate(self.layers):
             att = layer.self_attn
             x, _, _, _ = ops.add_layernorm(h, None, layer.input_layernorm.weight, None, layer.input_layernorm.eps, kind="gemma_rmsnorm")
             qkv = _lin(x, _packed(att, ("q_proj", "k_proj", "v_proj"), "weight"), _packed(att, ("q_proj", "k_proj", "v_proj"), "bias"))
             v4 = qkv.view(B, S, nh + 2 * nkv, hd).permute(0, 2, 1, 3)  # [B, heads, S, hd] view of the packed projection
             q, k_new, v_new = v4[:, :nh], v4[:, nh:nh + nkv], v4[:, nh + nkv:]
-            ops.rope_into(q, q, cos, sin, start + 1)
-            if cache is not None:
+            ops.rope_into(q, q, cos, sin, start + 1, pos_dev=pos_dev)
+            if on_dev:
+                kc, vc = cache.key_cache[li], cache.value_cache[li]
+                ops.rope_into(k_new, kc[:B, :, 0:1], cos, sin, 1, pos_dev=pos_dev, out_follows_pos=True)
+                ops.rope_into(v_new, vc[:B, :, 0:1], None, None, 0, pos_dev=pos_dev, out_follows_pos=True, copy_only=True)
+                k_att, v_att = kc[:B], vc[:B]  # every slot of the cache; the kernel stops at the device-side position
+            elif cache is not None:
                 kc, vc = cache.key_cache[li], cache.value_cache[li]
                 ops.rope_into(k_new, kc[:B, :, start:start + S], cos, sin, start + 1)
                 ops.cast4d(v_new, vc.dtype, out=vc[:B, :, start:start + S])
@@ -346,7 +361,8 @@ class GemmaModel(nn.Module):
                 k_att, v_att = k_new, v_new
             # inference (cell 17 _update_causal_mask): a multi-token call sees its whole prefix, a single token everything
             # before it — both are "no causal mask" over [0, start + S); padding columns stay masked
-            a, _ = ops.attn_fwd(q, k_att, v_att, causal=not prefix_visible, q_pos0=start, key_padding_mask=key_padding, out_dtype=T)
+            a, _ = ops.attn_fwd(q, k_att, v_att, causal=not prefix_visible, q_pos0=start, key_padding_mask=key_padding, out_dtype=T,
+                                pos_dev=pos_dev)
             h = _lin(a.view(B * S, nh * hd), att.o_proj.weight, att.o_proj.bias, addend=h)
             x, _, _, _ = ops.add_layernorm(h, None, layer.post_attention_layernorm.weight, None, layer.post_attention_layernorm.eps,
                                            kind="gemma_rmsnorm")
@@ -463,18 +479,102 @@ class PaliGemmaForConditionalGeneration(nn.Module):
                                        image_hidden_states=None if image_features is None else image_features / (H ** 0.5))
 
 
+class PaliGemmaDecodeGraph:
+    """One CUDA-graph replay per generated token: the single-token step (embedding * sqrt(H), 18 x [RMSNorm, q|k|v, RoPE + cache
+    append at the DEVICE-side position, packed-head attention over the cache, o_proj, RMSNorm, GeGLU, down_proj], final norm,
+    lm_head, argmax, position increment) is captured once after the prefill and replayed — an eager step is ~230 launches whose
+    host cost exceeds their device time. Programmatic dependent launch is on during the capture, as for DecoderModel's graph."""
+
+    def __init__(self, model: "PaliGemmaForConditionalGeneration", cache: StaticCache, prefill_mask: torch.Tensor):
+        self.model, self.cache = model, cache
+        dev = cache.key_cache[0].device
+        B, S0 = prefill_mask.shape
+        self.B = B
+        self.tok = torch.zeros(B, dtype=torch.long, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.kpm = torch.ones((B, cache.max_cache_len), dtype=torch.uint8, device=dev)  # generated tokens are never padding
+        self.kpm[:, :S0] = (prefill_mask != 0).to(torch.uint8)
+        self.graph = None
+
+    def _step(self) -> None:
+        lm = self.model.language_model
+        H = lm.model.config.hidden_size
+        table = lm.model.embed_tokens.weight
+        rows = torch.empty((self.B, H), device=table.device, dtype=table.dtype)
+        ops.embed(self.tok, table, out=rows, tokens_per_seq=1, out_group_stride=1, out_scale=math.sqrt(H))
+        h = lm.model.run_layers(rows, self.B, 1, self.pos, self.kpm, self.cache, prefix_visible=True)
+        V = lm.lm_head.weight.shape[0]
+        buf = torch.empty((self.B, (V + 7) // 8 * 8), device=table.device, dtype=h.dtype)
+        logits = _lin(h, lm.lm_head.weight, None, out=buf[:, :V])
+        ops.argmax_rows(logits, out=self.tok)
+        self.pos.add_(1)
+
+    def capture(self) -> None:
+        import os
+        pos0, tok0 = self.pos.clone(), self.tok.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            self._step()  # warm-up (packs weights, loads modules); the slot it writes is rewritten by the first real step
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.pos.copy_(pos0)
+        self.tok.copy_(tok0)
+        self.graph = torch.cuda.CUDAGraph()
+        pdl = os.environ.get("VY_DECODE_PDL", "1") != "0"
+        prev = _lib.lib().vy_set_pdl(1) if pdl else None
+        try:
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self._step()
+        finally:
+            if pdl:
+                _lib.lib().vy_set_pdl(prev)
+        self.pos.copy_(pos0)
+        self.tok.copy_(tok0)
+
+    def run(self, first_token: torch.Tensor, start: int, steps: int, out: torch.Tensor) -> None:
+        """Feeds `first_token` [B] (not yet in the cache; it goes to slot `start`) and generates `steps` more tokens into
+        out[:, 0:steps]."""
+        if start + steps > self.cache.max_cache_len:
+            raise ValueError(f"{start + steps} tokens do not fit the {self.cache.max_cache_len} slots of the cache")
+        self.tok.copy_(first_token.view(-1))
+        self.pos.fill_(start)
+        if self.graph is None:
+            self.capture()
+        for i in range(steps):
+            self.graph.replay()
+            out[:, i].copy_(self.tok)
+        self.cache._seen = start + steps
+
+
 @torch.no_grad()
 def paligemma_generate(model: PaliGemmaForConditionalGeneration, input_ids, pixel_values, attention_mask, max_tokens_to_generate: int = 50,
-                       max_cache_len: int = 384, stop_token: Optional[int] = None) -> torch.Tensor:
+                       max_cache_len: int = 384, stop_token: Optional[int] = None, use_graph: bool = True) -> torch.Tensor:
     """Greedy generation, the procedure of the notebook's `test_inference` (cell 30) for any batch size: StaticCache of
     `max_cache_len` slots, prefill, then one token per step with the attention mask grown by a column of ones. Returns the
-    generated ids [B, n]; with `stop_token` it stops once every row has produced it (one host sync per step, like the
-    reference's `.item()`)."""
+    generated ids [B, n]. Without `stop_token` (or with use_graph) the single-token steps are CUDA-graph replays
+    (PaliGemmaDecodeGraph) and rows that have produced `stop_token` are cut afterwards; use_graph=False runs the notebook's
+    eager loop with its one host sync per step."""
     dev = next(model.parameters()).device
     dt = next(model.parameters()).dtype
     input_ids, pixel_values, attention_mask = input_ids.to(dev), pixel_values.to(dev), attention_mask.to(dev)
-    B = input_ids.shape[0]
+    B, S0 = input_ids.shape
     cache = StaticCache(model.config.text_config, batch_size=B, device=dev, dtype=dt, max_cache_len=max_cache_len)
+    if use_graph:
+        out = model(input_ids=input_ids, pixel_values=pixel_values, attention_mask=attention_mask, past_key_values=cache, use_cache=True,
+                    logits_last_only=True)
+        first = ops.argmax_rows(out.logits[:, -1])
+        toks = torch.empty((B, max_tokens_to_generate), dtype=torch.long, device=dev)
+        toks[:, 0] = first
+        if max_tokens_to_generate > 1:
+            g = PaliGemmaDecodeGraph(model, cache, attention_mask)
+            g.run(first, S0, max_tokens_to_generate - 1, toks[:, 1:])
+        if stop_token is not None:  # the reference stops at the stop token: nothing after it is reported
+            hit = (toks == stop_token).int().cumsum(1)
+            keep = (hit == 0) | ((hit == 1) & (toks == stop_token))
+            n = int(keep.any(0).sum())
+            toks = toks[:, :n]
+        return toks
     toks = []
     done = torch.zeros(B, dtype=torch.bool, device=dev)
     for _ in range(max_tokens_to_generate):

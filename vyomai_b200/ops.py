@@ -377,11 +377,12 @@ def attn_fwd(
     out_dtype: Optional[torch.dtype] = None,
     need_lse: bool = False,
     prefix_len: Optional[torch.Tensor] = None,
+    pos_dev: Optional[torch.Tensor] = None,
 ):
     """Flash attention forward. q [B,Hq,Sq,D], k/v [B,Hkv,Skv,D] (bf16, any batch/head/token strides; D = 64 on the
     tensor-memory kernel, any multiple of 8 up to 256 on the mma.sync one). `prefix_len` (int32 [B], with causal): keys below
     it are visible to every query (prefix-LM). Returns (out [B,Sq,Hq*D], lse [B,Hq,Sq] or None)."""
-    _need_cuda(q, k, v, key_padding_mask, out, prefix_len)
+    _need_cuda(q, k, v, key_padding_mask, out, prefix_len, pos_dev)
     if prefix_len is not None and (prefix_len.dtype != torch.int32 or not prefix_len.is_contiguous() or prefix_len.numel() != q.shape[0]):
         raise _lib.VyomError("attn_fwd: prefix_len must be a contiguous int32 tensor with one entry per batch row")
     B, Hq, Sq, D = q.shape
@@ -406,7 +407,7 @@ def attn_fwd(
         causal=int(causal), q_pos0=q_pos0, key_padding_mask=_ptr(kpm),
         kpm_stride=kpm.stride(0) if kpm is not None else 0,
         out=out.data_ptr(), o_sb=out.stride(0), o_sl=out.stride(1), out_dtype=_dt(out), lse=_ptr(lse),
-        prefix_len=_ptr(prefix_len), stream=_stream(),
+        prefix_len=_ptr(prefix_len), pos_ptr=_ptr(pos_dev), stream=_stream(),
     )
     return out, lse
 
@@ -649,19 +650,23 @@ def rope_apply(x: torch.Tensor, freqs: torch.Tensor, inverse: bool = False) -> t
     return out
 
 
-def rope_into(x: torch.Tensor, out: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, pos0: int, inverse: bool = False) -> torch.Tensor:
+def rope_into(x: torch.Tensor, out: torch.Tensor, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], pos0: int, inverse: bool = False,
+              pos_dev: Optional[torch.Tensor] = None, out_follows_pos: bool = False, copy_only: bool = False) -> torch.Tensor:
     """Half-split RoPE of x [B, h, S, D] (any batch / head / token strides, D contiguous and even) written to `out` (same shape,
     its own strides — e.g. a kv-cache slot range; out may be x itself). cos / sin: fp32 [rows, D / 2] tables, row pos0 + l is
-    used for token l."""
-    _need_cuda(x, out, cos, sin)
+    used for token l. `pos_dev` (device int32 scalar) is added to pos0 on the device; with out_follows_pos the rows land at
+    out token index l + pos_dev (out = the base of a kv-cache); copy_only skips the rotation (values)."""
+    _need_cuda(x, out, cos, sin, pos_dev)
     B, Hh, S, D = x.shape
     if x.stride(3) != 1 or out.stride(3) != 1 or tuple(out.shape) != tuple(x.shape) or out.dtype != x.dtype:
         raise _lib.VyomError("rope_into: x and out must share shape and dtype with a contiguous head_dim")
-    if cos.dtype != torch.float32 or cos.shape[1] != D // 2 or not cos.is_contiguous() or not sin.is_contiguous() or cos.shape[0] < pos0 + S:
+    if not copy_only and (cos.dtype != torch.float32 or cos.shape[1] != D // 2 or not cos.is_contiguous() or not sin.is_contiguous()
+                          or cos.shape[0] < pos0 + S):
         raise _lib.VyomError("rope_into: cos / sin must be contiguous fp32 [>= pos0 + S, D / 2] tables")
     _lib.call("vy_rope_apply", "VyRope", B=B, H=Hh, S=S, head_dim=D, x=x.data_ptr(), x_sb=x.stride(0), x_sh=x.stride(1),
-              x_sl=x.stride(2), dtype=_dt(x), cos=cos.data_ptr(), sin=sin.data_ptr(), pos0=pos0, inverse=int(inverse),
-              out=out.data_ptr(), o_sb=out.stride(0), o_sh=out.stride(1), o_sl=out.stride(2), stream=_stream())
+              x_sl=x.stride(2), dtype=_dt(x), cos=_ptr(cos), sin=_ptr(sin), pos0=pos0, inverse=int(inverse),
+              out=out.data_ptr(), o_sb=out.stride(0), o_sh=out.stride(1), o_sl=out.stride(2), pos_ptr=_ptr(pos_dev),
+              out_follows_pos=int(out_follows_pos), copy_only=int(copy_only), stream=_stream())
     return out
 
 
