@@ -133,15 +133,30 @@ attn_fwd_mma_kernel(AttnMmaDev g) {
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int k0 = kb * AM_BN;
     __syncthreads();  // previous block's K / V fully consumed (and, first time, Q stored)
-    for (int i = threadIdx.x; i < AM_BN * (DP / 8); i += blockDim.x) {
-      const int r = i / (DP / 8), c = i - r * (DP / 8);
-      uint4 kvv = make_uint4(0, 0, 0, 0), vvv = make_uint4(0, 0, 0, 0);
-      if (k0 + r < g.Skv && c < vec_per_row) {
-        kvv = *reinterpret_cast<const uint4*>(kbase + static_cast<long long>(k0 + r) * g.k_sl + c * 8);
-        vvv = *reinterpret_cast<const uint4*>(vbase + static_cast<long long>(k0 + r) * g.v_sl + c * 8);
+    // 4 row-vectors of K and of V per thread in flight (8 independent 16-byte loads) before the first shared-memory store
+    constexpr int KV_VECS = AM_BN * (DP / 8);
+    for (int i0 = threadIdx.x; i0 < KV_VECS; i0 += 4 * AM_WARPS * 32) {
+      uint4 kvv[4], vvv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * AM_WARPS * 32;
+        const int r = i / (DP / 8), c = i - r * (DP / 8);
+        kvv[u] = make_uint4(0, 0, 0, 0);
+        vvv[u] = make_uint4(0, 0, 0, 0);
+        if (i < KV_VECS && k0 + r < g.Skv && c < vec_per_row) {
+          kvv[u] = *reinterpret_cast<const uint4*>(kbase + static_cast<long long>(k0 + r) * g.k_sl + c * 8);
+          vvv[u] = *reinterpret_cast<const uint4*>(vbase + static_cast<long long>(k0 + r) * g.v_sl + c * 8);
+        }
       }
-      *reinterpret_cast<uint4*>(sK + r * ROWB + c * 16) = kvv;
-      *reinterpret_cast<uint4*>(sV + r * ROWB + c * 16) = vvv;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * AM_WARPS * 32;
+        const int r = i / (DP / 8), c = i - r * (DP / 8);
+        if (i < KV_VECS) {
+          *reinterpret_cast<uint4*>(sK + r * ROWB + c * 16) = kvv[u];
+          *reinterpret_cast<uint4*>(sV + r * ROWB + c * 16) = vvv[u];
+        }
+      }
     }
     __syncthreads();
 
@@ -273,20 +288,42 @@ attn_fwd_mma_kernel(AttnMmaDev g) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int idx = threadIdx.x; idx < g.n_rep * g.D; idx += blockDim.x) {
-      const int r = idx / g.D, d = idx - r * g.D;
-      float M = -INFINITY;
-      for (int sp = 0; sp < g.splits; ++sp) M = fmaxf(M, __ldcg(am_ws + ((slot0 + sp) * g.n_rep + r) * stride + g.D));
-      float L = 0.f, O = 0.f;
-      for (int sp = 0; sp < g.splits; ++sp) {
-        const float* w = am_ws + ((slot0 + sp) * g.n_rep + r) * stride;
-        const float ms = __ldcg(w + g.D);
-        if (ms == -INFINITY) continue;  // an empty share
-        const float a = exp2f(ms - M);
-        L += __ldcg(w + g.D + 1) * a;
-        O += __ldcg(w + d) * a;
+    // one (query head, 4 dims) item per thread and pass; all loads of an item are independent and issued together
+    constexpr int MAXS = 16;
+    for (int idx = threadIdx.x; idx < g.n_rep * (g.D >> 2); idx += blockDim.x) {
+      const int r = idx / (g.D >> 2), d = (idx - r * (g.D >> 2)) << 2;
+      float ms[MAXS], ls[MAXS];
+      float4 os[MAXS];
+#pragma unroll
+      for (int sp = 0; sp < MAXS; ++sp) {
+        if (sp < g.splits) {
+          const float* w = am_ws + ((slot0 + sp) * g.n_rep + r) * stride;
+          ms[sp] = __ldcg(w + g.D);
+          ls[sp] = __ldcg(w + g.D + 1);
+          os[sp] = make_float4(__ldcg(w + d), __ldcg(w + d + 1), __ldcg(w + d + 2), __ldcg(w + d + 3));
+        } else {
+          ms[sp] = -INFINITY;
+          ls[sp] = 0.f;
+          os[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      st_from_float(g.out, g.out_dt, static_cast<long long>(b) * g.o_sb + static_cast<long long>(h_blk + r) * g.D + d, O / L);
+      float M = -INFINITY;
+#pragma unroll
+      for (int sp = 0; sp < MAXS; ++sp) M = fmaxf(M, ms[sp]);
+      float L = 0.f;
+      float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int sp = 0; sp < MAXS; ++sp) {
+        const float a = ms[sp] == -INFINITY ? 0.f : exp2f(ms[sp] - M);  // (an empty share has weight 0)
+        L += ls[sp] * a;
+        O.x += os[sp].x * a; O.y += os[sp].y * a; O.z += os[sp].z * a; O.w += os[sp].w * a;
+      }
+      const float inv = 1.f / L;
+      const long long ob = static_cast<long long>(b) * g.o_sb + static_cast<long long>(h_blk + r) * g.D + d;
+      st_from_float(g.out, g.out_dt, ob, O.x * inv);
+      st_from_float(g.out, g.out_dt, ob + 1, O.y * inv);
+      st_from_float(g.out, g.out_dt, ob + 2, O.z * inv);
+      st_from_float(g.out, g.out_dt, ob + 3, O.w * inv);
     }
     return;
   }

@@ -91,6 +91,14 @@ gemm_skinny_kernel(const SkinnyDev p) {
     }
   };
   if (p.static_w) load_w(0);  // before the predecessor is awaited: (the first chunk of) the whole weight matrix is in flight
+  if (kbw > SK_MAX_KB && t == 0) {
+    // long K (the 2048 x 16384 projection): the later chunks' loads are issued only after the earlier chunks' MMAs, one DRAM
+    // round trip each; request their lines into L2 now (128 B = two k-blocks of one row), so those loads become L2 hits
+    for (int c = SK_MAX_KB; c < kbw; c += 2) {
+      if (ok0) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + c * 32));
+      if (ok1) asm volatile("prefetch.global.L2 [%0];" ::"l"(w1 + c * 32));
+    }
+  }
   pdl_wait();
   if (!p.static_w) load_w(0);
 
