@@ -48,3 +48,7 @@ tot = sum(v[1] for v in agg.values())
 print(f"B={B}: {tot / N / 1e3:.3f} ms of kernel time per decode step (graph replay, PDL: kernels overlap, per-kernel times include waiting)")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
     print(f"{t / N:9.1f} us/step  {n / N:6.1f} calls  {t / n:8.1f} us/call  {k}")
+sk = sorted(ev.device_time_total for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "skinny" in ev.name)
+n = len(sk) // 3
+print("small-batch GEMM calls, us (sorted thirds = q|k|v / o_proj / down_proj by size):",
+      [round(sum(sk[i * n:(i + 1) * n]) / max(1, n), 1) for i in range(3)], "min", round(sk[0], 1), "max", round(sk[-1], 1))

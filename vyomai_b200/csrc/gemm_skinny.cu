@@ -82,34 +82,25 @@ gemm_skinny_kernel(const SkinnyDev p) {
   const bool ok0 = f0 + g < p.F, ok1 = f0 + g + 8 < p.F;
   const __nv_bfloat16* w0 = p.W + static_cast<long long>(f0 + g) * p.ldw + k0;
   const __nv_bfloat16* w1 = w0 + 8 * p.ldw;
-  uint4 ra[SK_MAX_KB], rb[SK_MAX_KB];
-  auto load_w = [&](int c0) {  // k-blocks [c0, c0 + SK_MAX_KB) of this warp
+  // two register buffers of SK_MAX_KB k-blocks: the loads of chunk c + 1 are issued before the MMAs of chunk c
+  uint4 ra[SK_MAX_KB], rb[SK_MAX_KB], ra2[SK_MAX_KB], rb2[SK_MAX_KB];
+  auto load_w = [&](uint4 (&wa)[SK_MAX_KB], uint4 (&wb)[SK_MAX_KB], int c0) {  // k-blocks [c0, c0 + SK_MAX_KB) of this warp
 #pragma unroll
     for (int j = 0; j < SK_MAX_KB; ++j) {
-      ra[j] = (ok0 && c0 + j < kbw) ? sk_ldg_stream(w0 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
-      rb[j] = (ok1 && c0 + j < kbw) ? sk_ldg_stream(w1 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
+      wa[j] = (ok0 && c0 + j < kbw) ? sk_ldg_stream(w0 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
+      wb[j] = (ok1 && c0 + j < kbw) ? sk_ldg_stream(w1 + (c0 + j) * 32) : make_uint4(0, 0, 0, 0);
     }
   };
-  if (p.static_w) load_w(0);  // before the predecessor is awaited: (the first chunk of) the whole weight matrix is in flight
-  if (kbw > SK_MAX_KB && t == 0) {
-    // long K (the 2048 x 16384 projection): the later chunks' loads are issued only after the earlier chunks' MMAs, one DRAM
-    // round trip each; request their lines into L2 now (128 B = two k-blocks of one row), so those loads become L2 hits
-    for (int c = SK_MAX_KB; c < kbw; c += 2) {
-      if (ok0) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + c * 32));
-      if (ok1) asm volatile("prefetch.global.L2 [%0];" ::"l"(w1 + c * 32));
-    }
-  }
+  if (p.static_w) load_w(ra, rb, 0);  // before the predecessor is awaited: (the first chunk of) the whole weight matrix is in flight
   pdl_wait();
-  if (!p.static_w) load_w(0);
+  if (!p.static_w) load_w(ra, rb, 0);
 
   float acc[NG][4];
 #pragma unroll
   for (int i = 0; i < NG; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < kbw; c0 += SK_MAX_KB) {
-    if (c0 > 0) load_w(c0);
+  auto compute = [&](const uint4 (&wa)[SK_MAX_KB], const uint4 (&wb)[SK_MAX_KB], int c0) {
 #pragma unroll
     for (int j = 0; j < SK_MAX_KB; ++j) {
       if (c0 + j < kbw) {
@@ -121,11 +112,18 @@ gemm_skinny_kernel(const SkinnyDev p) {
         }
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
-          sk_mma(acc[i], ra[j].x, rb[j].x, ra[j].y, rb[j].y, xb[i].x, xb[i].y);
-          sk_mma(acc[i], ra[j].z, rb[j].z, ra[j].w, rb[j].w, xb[i].z, xb[i].w);
+          sk_mma(acc[i], wa[j].x, wb[j].x, wa[j].y, wb[j].y, xb[i].x, xb[i].y);
+          sk_mma(acc[i], wa[j].z, wb[j].z, wa[j].w, wb[j].w, xb[i].z, xb[i].w);
         }
       }
     }
+  };
+#pragma unroll 1
+  for (int c0 = 0; c0 < kbw; c0 += 2 * SK_MAX_KB) {
+    if (c0 + SK_MAX_KB < kbw) load_w(ra2, rb2, c0 + SK_MAX_KB);
+    compute(ra, rb, c0);
+    if (c0 + 2 * SK_MAX_KB < kbw) load_w(ra, rb, c0 + 2 * SK_MAX_KB);
+    if (c0 + SK_MAX_KB < kbw) compute(ra2, rb2, c0 + SK_MAX_KB);
   }
   // this warp's partial tile: [feature][token]
   float* my = s_part[warp];
