@@ -797,9 +797,11 @@ def run_ours(args):
     prof = replay_profile(step_resident) if not args.no_graph else {k: {"calls": v["calls"], "ms": v["ms"]} for k, v in work.items()}
     hbm, tf_burst, tf_sust, src = peaks()
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_mean")
+    for tname in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):  # r02: mean over two whole steps (350 launches); r01: 6 launches
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch_mean")
+            break
     ours = {k: v for k, v in prof.items() if k.startswith("vy_")}
     total_ms = sum(d["ms"] for d in prof.values())
     name, d = max(ours.items(), key=lambda kv: kv[1]["ms"])
