@@ -66,7 +66,9 @@ VY_API const char* vy_last_error(void);
 VY_API int64_t vy_launch_count(void);
 /* Programmatic dependent launch of this library's kernels (each one triggers its dependents at entry and waits for its
  * predecessor before touching global memory): on != 0 enables, 0 disables, negative returns to the process default (the
- * VY_PDL environment variable, off). Returns the previous override (-1 = none). Affects launches made after the call. */
+ * VY_PDL environment variable, off). Returns the previous override (-1 = none). Affects launches made after the call, by
+ * every thread of the process: meant to bracket a CUDA-graph capture (vyomai_b200/decode_graph.py), not to be toggled
+ * around individual calls while other threads launch. */
 VY_API int vy_set_pdl(int on);
 /* 1 if the current device is sm_100 (B200), else 0 */
 VY_API int vy_device_ok(void);
@@ -290,7 +292,9 @@ VY_API int vy_norm_bwd_partial_rows(void);
  * (SigLIP 72, Gemma 256: Examples/paligemma.ipynb cells 9, 12) and every call with a prefix-LM mask runs on a second,
  * mma.sync-based forward kernel (csrc/attn_fwd_mma.cu; "64" in the layout notes above reads head_dim, the scale is
  * 1/sqrt(head_dim)); at Sq == 1 it packs the query heads of a kv group into one tile (MQA / GQA decode over a cache).
- * vy_attn_bwd exists for head_dim 64 only.
+ * vy_attn_bwd exists for head_dim 64 only. The packed-head decode form splits the keys over several CTAs when there are few
+ * (row, kv head) pairs and combines them through a library-owned scratch buffer: such calls must not run concurrently on two
+ * streams of one device (like vy_sqnorm / vy_add_layernorm_bwd's partials).
  * ------------------------------------------------------------------------------------------ */
 typedef struct VyAttn {
   int32_t B, n_q_heads, n_kv_heads, head_dim;
@@ -407,9 +411,10 @@ VY_API int vy_scale_by_ptr(int64_t n, void* x, int dtype, const float* scale, vo
  *   bwd: da[r, :] = slot[r] >= 0 ? 0 : dout[r, :];   db[slot[r], :] = dout[r, :]     (da or db may be NULL)
  * slot[r] is the running count of image tokens before row r (masked_scatter consumes source rows in row-major order) or
  * -1; every b row is used at most once, rows of db no slot points at are left untouched (zero them first). All buffers
- * are row-contiguous [rows or n_b, H]; H * sizeof(dtype) % 16 == 0. */
-VY_API int vy_slot_merge_fwd(int rows, int H, int dtype, const void* a, const void* b, const int32_t* slot, void* out, void* stream);
-VY_API int vy_slot_merge_bwd(int rows, int H, int dtype, const void* dout, const int32_t* slot, void* da, void* db, void* stream);
+ * are row-contiguous [rows or n_b, H]; H * sizeof(dtype) % 16 == 0. A slot index >= n_b (more image positions than source
+ * rows: the reference raises) is treated as -1, so b / db are never addressed out of bounds. */
+VY_API int vy_slot_merge_fwd(int rows, int H, int dtype, const void* a, const void* b, int n_b, const int32_t* slot, void* out, void* stream);
+VY_API int vy_slot_merge_bwd(int rows, int H, int dtype, const void* dout, const int32_t* slot, void* da, void* db, int n_b, void* stream);
 
 /* vy_swiglu_bwd — gradient of h[r, j] = silu(z[r, 2j]) * z[r, 2j+1] w.r.t. the interleaved pre-activations:
  * dz[r, 2j] = dh[r, j] * z[r, 2j+1] * silu'(z[r, 2j]), dz[r, 2j+1] = dh[r, j] * silu(z[r, 2j]); dz then feeds the

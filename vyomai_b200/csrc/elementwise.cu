@@ -533,13 +533,14 @@ adamw_kernel(long long n, void* __restrict__ p, int p_dt, const void* __restrict
 // One 16-byte vector per thread; rows are H elements (H % 8 == 0 for bf16, % 4 for fp32), all buffers row-contiguous.
 __global__ void __launch_bounds__(256)
 slot_merge_kernel(int rows, int vec_per_row, const uint4* __restrict__ a, const uint4* __restrict__ b, const int* __restrict__ slot,
-                  uint4* __restrict__ out, uint4* __restrict__ da, uint4* __restrict__ db, int backward) {
+                  uint4* __restrict__ out, uint4* __restrict__ da, uint4* __restrict__ db, int backward, int n_b) {
   pdl_trigger();
   pdl_wait();
   const long long total = static_cast<long long>(rows) * vec_per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / vec_per_row), c = static_cast<int>(i - static_cast<long long>(r) * vec_per_row);
-    const int sl = slot[r];
+    int sl = slot[r];
+    if (sl >= n_b) sl = -1;  // more <image> positions than source rows (the reference's masked_scatter raises; the host checks): never read past b
     if (!backward) {
       out[i] = sl >= 0 ? b[static_cast<long long>(sl) * vec_per_row + c] : a[i];
     } else {
@@ -853,29 +854,29 @@ extern "C" int vy_scale_by_ptr(int64_t n, void* x, int dtype, const float* scale
   return VY_OK;
 }
 
-extern "C" int vy_slot_merge_fwd(int rows, int H, int dtype, const void* a, const void* b, const int32_t* slot, void* out, void* stream) {
+extern "C" int vy_slot_merge_fwd(int rows, int H, int dtype, const void* a, const void* b, int n_b, const int32_t* slot, void* out, void* stream) {
   VY_NEED_DEVICE("vy_slot_merge_fwd");
-  VY_CHECK_ARG(rows > 0 && H > 0 && dtype_ok(dtype) && a && b && slot && out && aligned16(a) && aligned16(b) && aligned16(out) &&
+  VY_CHECK_ARG(rows > 0 && H > 0 && n_b >= 0 && dtype_ok(dtype) && a && b && slot && out && aligned16(a) && aligned16(b) && aligned16(out) &&
                    (static_cast<long long>(H) * dtype_size(dtype)) % 16 == 0,
                "vy_slot_merge_fwd: bad arguments (row bytes and pointers must be multiples of 16)");
   const int vpr = static_cast<int>(static_cast<long long>(H) * dtype_size(dtype) / 16);
   VY_CUDA_OK(launch_kernel(slot_merge_kernel, dim3(ew_grid(static_cast<long long>(rows) * vpr, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, vpr,
                            static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<const int*>(slot), static_cast<uint4*>(out),
-                           static_cast<uint4*>(nullptr), static_cast<uint4*>(nullptr), 0));
+                           static_cast<uint4*>(nullptr), static_cast<uint4*>(nullptr), 0, n_b));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;
 }
 
-extern "C" int vy_slot_merge_bwd(int rows, int H, int dtype, const void* dout, const int32_t* slot, void* da, void* db, void* stream) {
+extern "C" int vy_slot_merge_bwd(int rows, int H, int dtype, const void* dout, const int32_t* slot, void* da, void* db, int n_b, void* stream) {
   VY_NEED_DEVICE("vy_slot_merge_bwd");
-  VY_CHECK_ARG(rows > 0 && H > 0 && dtype_ok(dtype) && dout && slot && (da || db) && aligned16(dout) && aligned16(da) && aligned16(db) &&
+  VY_CHECK_ARG(rows > 0 && H > 0 && n_b >= 0 && dtype_ok(dtype) && dout && slot && (da || db) && aligned16(dout) && aligned16(da) && aligned16(db) &&
                    (static_cast<long long>(H) * dtype_size(dtype)) % 16 == 0,
                "vy_slot_merge_bwd: bad arguments (row bytes and pointers must be multiples of 16)");
   const int vpr = static_cast<int>(static_cast<long long>(H) * dtype_size(dtype) / 16);
   VY_CUDA_OK(launch_kernel(slot_merge_kernel, dim3(ew_grid(static_cast<long long>(rows) * vpr, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, vpr,
                            static_cast<const uint4*>(dout), static_cast<const uint4*>(nullptr), static_cast<const int*>(slot),
-                           static_cast<uint4*>(nullptr), static_cast<uint4*>(da), static_cast<uint4*>(db), 1));
+                           static_cast<uint4*>(nullptr), static_cast<uint4*>(da), static_cast<uint4*>(db), 1, n_b));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -700,7 +700,7 @@ def slot_merge(a: torch.Tensor, b: torch.Tensor, slot: torch.Tensor) -> torch.Te
     if slot.dtype != torch.int32 or not slot.is_contiguous() or slot.numel() != a.shape[0]:
         raise _lib.VyomError("slot_merge: slot must be a contiguous int32 tensor with one entry per row of a")
     out = torch.empty_like(a)
-    _lib.check(_lib.lib().vy_slot_merge_fwd(a.shape[0], a.shape[1], _dt(a), a.data_ptr(), b.data_ptr(), slot.data_ptr(), out.data_ptr(),
+    _lib.check(_lib.lib().vy_slot_merge_fwd(a.shape[0], a.shape[1], _dt(a), a.data_ptr(), b.data_ptr(), b.shape[0], slot.data_ptr(), out.data_ptr(),
                                            _stream()), "vy_slot_merge_fwd")
     return out
 
@@ -715,7 +715,7 @@ def slot_merge_bwd(dout: torch.Tensor, slot: torch.Tensor, n_b: int, need_a: boo
     if da is None and db is None:
         return None, None
     _lib.check(_lib.lib().vy_slot_merge_bwd(dout.shape[0], dout.shape[1], _dt(dout), dout.data_ptr(), slot.data_ptr(), _ptr(da), _ptr(db),
-                                           _stream()), "vy_slot_merge_bwd")
+                                           n_b, _stream()), "vy_slot_merge_bwd")
     return da, db
 
 

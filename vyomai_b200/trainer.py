@@ -311,6 +311,8 @@ class Trainer:
     def optimizer_step(self) -> None:
         self._check_gemm_health()
         if self.shard is not None:
+            if self.step_count % 64 == 63:  # a device-side barrier that timed out left the replicas inconsistent: stop
+                self.shard.check()           # (one host sync every 64 steps)
             self.step_count += 1
             self.step_dev.add_(1)
             self.shard.step(self.step_count, self.step_dev)
@@ -377,6 +379,9 @@ class Trainer:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._check_gemm_health()  # the replayed kernels make no host-side vy_gemm call that would notice the flag
+        self._replays = getattr(self, "_replays", 0) + 1
+        if self.shard is not None and self._replays % 64 == 0:
+            self.shard.check()
         self._graph.replay()
         self.replayed_kernels += self.graph_kernels
         return self._static_loss
