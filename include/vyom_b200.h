@@ -395,6 +395,30 @@ typedef struct VyRope {
 
 VY_API int vy_rope_apply(const VyRope* p);
 
+/* vy_rope_append — apply_rotary_pos_emb(q, k) + StaticCache.update(k, v) of a PACKED q|k|v projection in one launch
+ * (Examples/paligemma.ipynb cell 12 GemmaAttention.forward + cell 28): `qkv` is addressed as [B, n_q + 2 n_kv, S, head_dim]
+ * through (sb, sh, sl); query heads are rotated in place, key heads rotated into k_cache, value heads copied into v_cache
+ * ([B, n_kv, slots, head_dim] through c_sb, c_sh, c_sl) at slot slot0 + l; token l uses table row pos0 + l (PaliGemma: slot + 1).
+ * pos_ptr (device int32, optional) is added to both pos0 and slot0, so a captured graph serves every decode step; cache_slots /
+ * rope_rows (0 = unchecked) bound the host-known part. cos / sin: fp32 [rows][head_dim / 2]. */
+typedef struct VyRopeAppend {
+  int32_t B, S, n_q_heads, n_kv_heads, head_dim;
+  void* qkv;
+  int64_t sb, sh, sl;
+  int32_t dtype; /* of qkv and the caches */
+  const float* cos;
+  const float* sin;
+  int32_t pos0, slot0;
+  const int32_t* pos_ptr;
+  void* k_cache;
+  void* v_cache;
+  int64_t c_sb, c_sh, c_sl;
+  int32_t cache_slots, rope_rows;
+  void* stream;
+} VyRopeAppend;
+
+VY_API int vy_rope_append(const VyRopeAppend* p);
+
 /* vy_act_bwd — out[i] = dy[i] * act'(z[i]) (act = VY_ACT_GELU_ERF / VY_ACT_GELU_TANH): the GELU
  * backward of the LM head (models/decoder.py:269), whose upstream gradient comes out of a LayerNorm
  * backward rather than a GEMM (inside the FFN the same factor rides in the dgrad GEMM epilogue). */

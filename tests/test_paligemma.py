@@ -127,6 +127,21 @@ def test_rope_256_geglu_and_padded_patches_vs_oracle():
     ops.rope_into(x.bfloat16().cuda(), cache[:, :, start:start + S], cos, sin, start + 1)
     assert rel_l2(cache[:, :, start:start + S].float().cpu(), want) <= 4e-3
     assert float(cache[:, :, :start].abs().max()) == 0.0 and float(cache[:, :, start + S:].abs().max()) == 0.0
+    # the same as ONE launch over a packed q|k|v projection: q rotated in place, k rotated into the cache, v copied into it
+    nq, nkv, S2 = 4, 1, 3
+    packed = _r((B, S2, (nq + 2 * nkv) * D), 11).bfloat16().cuda()
+    v4 = packed.view(B, S2, nq + 2 * nkv, D).permute(0, 2, 1, 3)
+    ref4 = v4.float().cpu().clone()
+    pos2 = (torch.arange(start, start + S2) + 1)[None].expand(B, -1)
+    q_want, k_want = O.gemma_rope(ref4[:, :nq], ref4[:, nq:nq + nkv], pos2, 10000.0)
+    kc2 = torch.zeros(B + 1, nkv, 32, D, dtype=torch.bfloat16, device="cuda")
+    vc2 = torch.zeros_like(kc2)
+    posd = torch.tensor([start], dtype=torch.int32, device="cuda")
+    ops.rope_append(v4, nq, nkv, kc2, vc2, cos, sin, 1, 0, pos_dev=posd)  # host part 1 / 0, the rest from the device scalar
+    assert rel_l2(v4[:, :nq].float().cpu(), q_want) <= 4e-3
+    assert rel_l2(kc2[:B, :, start:start + S2].float().cpu(), k_want) <= 4e-3
+    assert torch.equal(vc2[:B, :, start:start + S2].float().cpu(), ref4[:, nq + nkv:])
+    assert float(kc2[B].abs().max()) == 0.0 and float(kc2[:, :, :start].abs().max()) == 0.0 and float(vc2[:, :, start + S2:].abs().max()) == 0.0
     # GeGLU: gelu_tanh(x Wg^T) * (x Wu^T) from ONE GEMM over interleaved gate / up rows
     M, H, inter = 300, 256, 512
     xx, wg, wu = _r((M, H), 6), _r((inter, H), 7, H ** -0.5), _r((inter, H), 8, H ** -0.5)

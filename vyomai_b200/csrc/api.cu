@@ -192,6 +192,7 @@ int vy_abi_sizeof(const char* name) {
   VY_SZ(VyXent);
   VY_SZ(VyAdamW);
   VY_SZ(VyRope);
+  VY_SZ(VyRopeAppend);
   VY_SZ(VyDecodeLayer);
   VY_SZ(VyDecodeStep);
   VY_SZ(VyDpGroup);

@@ -586,6 +586,45 @@ rope_kernel(int B, int H, int S, int D, const void* __restrict__ x, long long xs
   }
 }
 
+// RoPE + kv-cache append of a packed q|k|v projection in ONE launch (PaliGemma-scale decoder: three launches per layer before):
+// head h of the [B, n_q + 2 n_kv, S, D] view is rotated in place (query), rotated into the key cache, or copied into the value
+// cache at slot slot0 (+ *pos_ptr) + l. One warp per (b, h, l) row.
+__global__ void __launch_bounds__(256)
+rope_append_kernel(int B, int n_q, int n_kv, int S, int D, void* __restrict__ qkv, long long sb, long long sh, long long sl, int dt,
+                   const float* __restrict__ cs, const float* __restrict__ sn, int pos0, int slot0, const int* __restrict__ pos_ptr,
+                   void* __restrict__ kc, void* __restrict__ vc, long long c_sb, long long c_sh, long long c_sl) {
+  pdl_trigger();
+  pdl_wait();
+  const int pos_dev = pos_ptr ? *pos_ptr : 0;
+  pos0 += pos_dev;
+  slot0 += pos_dev;
+  const int Hh = n_q + 2 * n_kv;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long rows = static_cast<long long>(B) * Hh * S;
+  const int half = D >> 1;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const int l = static_cast<int>(r % S);
+    const int h = static_cast<int>((r / S) % Hh);
+    const int b = static_cast<int>(r / (static_cast<long long>(S) * Hh));
+    const long long xi = b * sb + h * sh + l * sl;
+    if (h >= n_q + n_kv) {  // value: plain copy into the cache
+      const long long oi = b * c_sb + (h - n_q - n_kv) * c_sh + static_cast<long long>(slot0 + l) * c_sl;
+      for (int j = lane; j < D; j += 32) st_from_float(vc, dt, oi + j, ld_as_float(qkv, dt, xi + j));
+      continue;
+    }
+    void* out = h < n_q ? qkv : kc;
+    const long long oi = h < n_q ? xi : b * c_sb + (h - n_q) * c_sh + static_cast<long long>(slot0 + l) * c_sl;
+    for (int j = lane; j < half; j += 32) {
+      const float a = ld_as_float(qkv, dt, xi + j), bb = ld_as_float(qkv, dt, xi + j + half);
+      const float c = cs[static_cast<long long>(pos0 + l) * half + j], s = sn[static_cast<long long>(pos0 + l) * half + j];
+      st_from_float(out, dt, oi + j, a * c - bb * s);
+      st_from_float(out, dt, oi + j + half, bb * c + a * s);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(long long n, const void* __restrict__ dy, const void* __restrict__ z, int dt, int act, void* __restrict__ out) {
   pdl_trigger();
@@ -839,6 +878,25 @@ extern "C" int vy_rope_apply(const VyRope* p) {
   const long long rows = static_cast<long long>(p->B) * p->H * p->S;
   VY_CUDA_OK(launch_kernel(rope_kernel, dim3(ew_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->B, p->H, p->S, p->head_dim, p->x, p->x_sb, p->x_sh, p->x_sl, p->dtype, p->cos, p->sin, p->pos0, p->inverse, p->out, p->o_sb, p->o_sh, p->o_sl, p->pos_ptr, p->out_follows_pos, p->copy_only));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
+
+extern "C" int vy_rope_append(const VyRopeAppend* p) {
+  VY_CHECK_ARG(p != nullptr, "vy_rope_append: null params");
+  VY_NEED_DEVICE("vy_rope_append");
+  VY_CHECK_ARG(p->B > 0 && p->S > 0 && p->n_q_heads >= 0 && p->n_kv_heads > 0 && p->head_dim >= 2 && (p->head_dim & 1) == 0,
+               "vy_rope_append: bad shape");
+  VY_CHECK_ARG(p->qkv && p->cos && p->sin && p->k_cache && p->v_cache && dtype_ok(p->dtype), "vy_rope_append: null pointer / bad dtype");
+  VY_CHECK_ARG(p->pos0 >= 0 && p->slot0 >= 0 && (p->cache_slots <= 0 || p->pos_ptr || p->slot0 + p->S <= p->cache_slots),
+               "vy_rope_append: slots [%d, %d) do not fit the %d slots of the cache", p->slot0, p->slot0 + p->S, p->cache_slots);
+  VY_CHECK_ARG(p->rope_rows <= 0 || p->pos_ptr || p->pos0 + p->S <= p->rope_rows, "vy_rope_append: positions [%d, %d) exceed the %d rows of the tables",
+               p->pos0, p->pos0 + p->S, p->rope_rows);
+  const long long rows = static_cast<long long>(p->B) * (p->n_q_heads + 2 * p->n_kv_heads) * p->S;
+  VY_CUDA_OK(launch_kernel(rope_append_kernel, dim3(ew_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(p->stream), p->B, p->n_q_heads,
+                           p->n_kv_heads, p->S, p->head_dim, p->qkv, p->sb, p->sh, p->sl, p->dtype, p->cos, p->sin, p->pos0, p->slot0, p->pos_ptr,
+                           p->k_cache, p->v_cache, p->c_sb, p->c_sh, p->c_sl));
   VY_LAUNCH_OK();
   count_launch();
   return VY_OK;

@@ -31,7 +31,38 @@ def available() -> bool:
         importlib.import_module("torch.distributed._symmetric_memory")
     except Exception:
         return False
-    return dist.get_backend() == "nccl"
+    if dist.get_backend() != "nccl":
+        return False
+    return _probe()
+
+
+_PROBE = None
+
+
+def _probe() -> bool:
+    """Collective, once per process: can every rank allocate and rendezvous a small symmetric buffer? All ranks get the same
+    answer (MIN over ranks), so the trainers agree on the data-parallel mode; a failure (no peer access, allocator not
+    supported) selects the NCCL all-reduce path and says so on stderr."""
+    global _PROBE
+    if _PROBE is not None:
+        return _PROBE
+    import sys
+    import torch.distributed._symmetric_memory as symm
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ok, why = 1, ""
+    try:
+        t = symm.empty(64, dtype=torch.float32, device=dev)
+        h = symm.rendezvous(t, dist.group.WORLD)
+        ok = 1 if len(h.buffer_ptrs) == dist.get_world_size() else 0
+    except Exception as e:  # noqa: BLE001
+        ok, why = 0, f"{type(e).__name__}: {str(e)[:200]}"
+    flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    _PROBE = bool(int(flag.item()))
+    if not _PROBE and dist.get_rank() == 0:
+        print(f"[vyomai_b200] symmetric memory unavailable ({why or 'on another rank'}): data-parallel step falls back to the NCCL "
+              "all-reduce path", file=sys.stderr, flush=True)
+    return _PROBE
 
 
 class SymmetricAllocator:

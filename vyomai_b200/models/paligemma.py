@@ -345,18 +345,15 @@ class GemmaModel(nn.Module):
             qkv = _lin(x, _packed(att, ("q_proj", "k_proj", "v_proj"), "weight"), _packed(att, ("q_proj", "k_proj", "v_proj"), "bias"))
             v4 = qkv.view(B, S, nh + 2 * nkv, hd).permute(0, 2, 1, 3)  # [B, heads, S, hd] view of the packed projection
             q, k_new, v_new = v4[:, :nh], v4[:, nh:nh + nkv], v4[:, nh + nkv:]
-            ops.rope_into(q, q, cos, sin, start + 1, pos_dev=pos_dev)
-            if on_dev:
+            if cache is not None:  # RoPE(q) in place, RoPE(k) and v straight into the cache: one launch
                 kc, vc = cache.key_cache[li], cache.value_cache[li]
-                ops.rope_into(k_new, kc[:B, :, 0:1], cos, sin, 1, pos_dev=pos_dev, out_follows_pos=True)
-                ops.rope_into(v_new, vc[:B, :, 0:1], None, None, 0, pos_dev=pos_dev, out_follows_pos=True, copy_only=True)
-                k_att, v_att = kc[:B], vc[:B]  # every slot of the cache; the kernel stops at the device-side position
-            elif cache is not None:
-                kc, vc = cache.key_cache[li], cache.value_cache[li]
-                ops.rope_into(k_new, kc[:B, :, start:start + S], cos, sin, start + 1)
-                ops.cast4d(v_new, vc.dtype, out=vc[:B, :, start:start + S])
-                k_att, v_att = kc[:B, :, :start + S], vc[:B, :, :start + S]
+                ops.rope_append(v4, nh, nkv, kc, vc, cos, sin, start + 1, start, pos_dev=pos_dev)
+                if on_dev:
+                    k_att, v_att = kc[:B], vc[:B]  # every slot of the cache; the kernel stops at the device-side position
+                else:
+                    k_att, v_att = kc[:B, :, :start + S], vc[:B, :, :start + S]
             else:
+                ops.rope_into(q, q, cos, sin, start + 1)
                 ops.rope_into(k_new, k_new, cos, sin, start + 1)
                 k_att, v_att = k_new, v_new
             # inference (cell 17 _update_causal_mask): a multi-token call sees its whole prefix, a single token everything

@@ -670,6 +670,26 @@ def rope_into(x: torch.Tensor, out: torch.Tensor, cos: Optional[torch.Tensor], s
     return out
 
 
+def rope_append(qkv4: torch.Tensor, n_q_heads: int, n_kv_heads: int, k_cache: torch.Tensor, v_cache: torch.Tensor, cos: torch.Tensor,
+                sin: torch.Tensor, pos0: int, slot0: int, pos_dev: Optional[torch.Tensor] = None) -> None:
+    """RoPE of the query heads (in place) and key heads (into k_cache) and the value copy (into v_cache) of a packed projection
+    viewed as [B, n_q + 2 n_kv, S, D]; caches [>= B, n_kv, slots, D]; token l -> table row pos0 + l, cache slot slot0 + l (both
+    + pos_dev on the device)."""
+    _need_cuda(qkv4, k_cache, v_cache, cos, sin, pos_dev)
+    B, Hh, S, D = qkv4.shape
+    if Hh != n_q_heads + 2 * n_kv_heads or qkv4.stride(3) != 1 or k_cache.stride(3) != 1 or k_cache.stride() != v_cache.stride():
+        raise _lib.VyomError("rope_append: qkv must be [B, n_q + 2 n_kv, S, D] with contiguous D; k / v caches must share strides")
+    if k_cache.dtype != qkv4.dtype or v_cache.dtype != qkv4.dtype or k_cache.shape[1] != n_kv_heads or k_cache.shape[3] != D:
+        raise _lib.VyomError("rope_append: caches must be [B', n_kv, slots, D] in the projection's dtype")
+    if cos.dtype != torch.float32 or cos.shape[1] != D // 2 or not cos.is_contiguous() or not sin.is_contiguous():
+        raise _lib.VyomError("rope_append: cos / sin must be contiguous fp32 [rows, D / 2] tables")
+    _lib.call("vy_rope_append", "VyRopeAppend", B=B, S=S, n_q_heads=n_q_heads, n_kv_heads=n_kv_heads, head_dim=D, qkv=qkv4.data_ptr(),
+              sb=qkv4.stride(0), sh=qkv4.stride(1), sl=qkv4.stride(2), dtype=_dt(qkv4), cos=cos.data_ptr(), sin=sin.data_ptr(),
+              pos0=pos0, slot0=slot0, pos_ptr=_ptr(pos_dev), k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),
+              c_sb=k_cache.stride(0), c_sh=k_cache.stride(1), c_sl=k_cache.stride(2), cache_slots=k_cache.shape[2],
+              rope_rows=cos.shape[0], stream=_stream())
+
+
 def act_bwd(dy: torch.Tensor, z: torch.Tensor, act: str = "gelu") -> torch.Tensor:
     """dy * act'(z), elementwise (contiguous, same dtype)."""
     _need_cuda(dy, z)
