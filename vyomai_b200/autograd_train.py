@@ -68,11 +68,22 @@ def _emit_wgrad(p: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor) -> Optio
     return _wgrad(dy2d, x2d, p).view(p.shape)
 
 
-def _emit_bgrad(p: Optional[torch.Tensor], dy2d: torch.Tensor) -> Optional[torch.Tensor]:
+def _side_ok(p) -> bool:
+    """Side-stream column sums need a consumer that joins before it reads the gradient: the trainer's optimizer step does
+    (Trainer.optimizer_step); the NCCL bucket hooks fire at `_ready`, i.e. too early, so that mode keeps the main stream."""
+    return getattr(p, "_vy_side_bgrad", False)
+
+
+def _emit_bgrad(p: Optional[torch.Tensor], dy2d: torch.Tensor, after=None) -> Optional[torch.Tensor]:
+    """`after`: ops.side_fork_point() taken when dy2d was complete — the sum then runs on the side stream (the caller joins
+    before it returns)."""
     if p is None:
         return None
     if _direct(p):
-        ops.colsum(dy2d, out=p.grad, accumulate=not _overwrite(p))
+        if after is not None and _side_ok(p):
+            ops.colsum_side(after, dy2d, out=p.grad, accumulate=not _overwrite(p))
+        else:
+            ops.colsum(dy2d, out=p.grad, accumulate=not _overwrite(p))
         _ready(p)
         return None
     return ops.colsum(dy2d, out_dtype=p.dtype)
@@ -166,6 +177,7 @@ class AttentionBlockFn(torch.autograd.Function):
         ops.attn_bwd(q, k, v, attn, d_attn, lse, causal=mask.causal, q_pos0=mask.q_pos0, key_padding_mask=mask.key_padding,
                      rope_cos=cos, rope_sin=sin, rope_pos0=rope_pos0, dq=dqkv[:, : Hq * d],
                      dk=dqkv[:, Hq * d:(Hq + Hkv) * d], dv=dqkv[:, (Hq + Hkv) * d:])
+        fork = ops.side_fork_point()
         dx = _dgrad(dqkv, w_qkv, addend=ds)  # + the residual branch of LN(dense(.) + x)
         grads = [dx]
         gw = _packed_grads([l.weight for l in lin])
@@ -184,7 +196,11 @@ class AttentionBlockFn(torch.autograd.Function):
         if ctx.has_qkv_bias:
             gb = _packed_grads([l.bias for l in lin])
             if gb is not None:
-                ops.colsum(dqkv, out=gb, accumulate=not all(_overwrite(l.bias) for l in lin))
+                acc = not all(_overwrite(l.bias) for l in lin)
+                if fork is not None and all(_side_ok(l.bias) for l in lin):
+                    ops.colsum_side(fork, dqkv, out=gb, accumulate=acc)
+                else:
+                    ops.colsum(dqkv, out=gb, accumulate=acc)
                 for l in lin:
                     _ready(l.bias)
                     grads.append(None)
@@ -199,6 +215,7 @@ class AttentionBlockFn(torch.autograd.Function):
         if ctx.has_dense_bias:
             grads.append(d_bo)
         grads += [dgamma, dbeta]
+        ops.side_join()
         return (None, None, None, None, None, None, *grads)
 
 
@@ -316,9 +333,11 @@ class FeedForwardFn(torch.autograd.Function):
         ds, dxo = _split_ds(ds)  # gradient of input_tensor, gradient of the second Linear's output
         d_w2 = _emit_wgrad(w2, dxo, a)
         dz = _dgrad(dxo, w2, act="d" + ctx.act, aux=z)  # (dS W2) * act'(z) in the dgrad epilogue
+        fork = ops.side_fork_point()
         d_w1 = _emit_wgrad(w1, dz, h2d)
-        d_b1 = _emit_bgrad(b1, dz)
+        d_b1 = _emit_bgrad(b1, dz, after=fork)  # column sums of dz under the weight-gradient GEMM
         dh = _dgrad(dz, w1)
+        ops.side_join()
         return None, None, None, dh, ds, d_w1, d_b1, d_w2, d_b2, dgamma, dbeta
 
 
@@ -332,14 +351,16 @@ def _padded_logits(rows: int, V: int, like: torch.Tensor):
 def _lm_head_backward(ctx_saved, params, dlogits):
     h2d, z, a, n, mean, rstd = ctx_saved
     wd, bd, gamma, beta, wv, bv = params
+    fork = ops.side_fork_point()
     d_wv = _emit_wgrad(wv, dlogits, n)
-    d_bv = _emit_bgrad(bv, dlogits)
+    d_bv = _emit_bgrad(bv, dlogits, after=fork)  # 0.8 GB of dlogits summed under the 0.5 ms vocabulary wgrad GEMM
     dn = _dgrad(dlogits, wv)
     da, dgamma, dbeta, _ = _ln_bwd(dn, a, gamma, beta, mean, rstd)
     dz = ops.act_bwd(da, z, "gelu")
     d_wd = _emit_wgrad(wd, dz, h2d)
     d_bd = _emit_bgrad(bd, dz)
     dh = _dgrad(dz, wd)
+    ops.side_join()
     return dh, d_wd, d_bd, dgamma, dbeta, d_wv, d_bv
 
 

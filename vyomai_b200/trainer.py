@@ -225,6 +225,10 @@ class Trainer:
                 self._bucket_size[b] += 1
                 p._vy_grad_ready = self._on_grad
                 p.register_post_accumulate_grad_hook(self._on_grad)
+        if not self.overlap:  # (the overlapped NCCL exchange launches a bucket at `_ready`, before a side-stream sum would be done)
+            for p in self.fp.params:
+                if p.dim() == 1:
+                    p._vy_side_bgrad = True
         self.grad_overwrite = False
         if grad_overwrite:
             self._enable_grad_overwrite()
@@ -309,6 +313,7 @@ class Trainer:
                                  "then are invalid (vy_gemm_poisoned() acknowledges the flag)")
 
     def optimizer_step(self) -> None:
+        ops.side_join()  # bias-gradient column sums still running on the side stream
         self._check_gemm_health()
         if self.shard is not None:
             if self.step_count % 64 == 63:  # a device-side barrier that timed out left the replicas inconsistent: stop
