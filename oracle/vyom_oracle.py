@@ -850,3 +850,31 @@ def paligemma_forward(sd: SD, cfg: dict, input_ids: Tensor, pixels: Optional[Ten
     h = gemma_layers(sd, "language_model.model.", emb, mask, position_ids, t["num_hidden_layers"], t["num_attention_heads"],
                      t["num_key_value_heads"], t["head_dim"], t["rms_norm_eps"], t["rope_theta"], cache, cache_position)
     return linear(h, sd["language_model.lm_head.weight"], None)
+
+# ---------------------------------------------------------------------------------------------
+# RMSNorm / SwiGLU / RoPE decoder (VyomAI/models/custom_transformer.py: ModelForCausalLM)
+# ---------------------------------------------------------------------------------------------
+def custom_lm_forward(sd: SD, cfg: dict, input_ids: Tensor, attention_mask: Optional[Tensor] = None) -> Tensor:
+    """ModelForCausalLM.forward without a cache (custom_transformer.py:426-497, 636-678): embed_tokens; per layer
+    `h += o_proj(attn(RMSNorm(h)))`, `h += down(silu(gate(x)) * up(x))` with x = RMSNorm(h) (:257-292); q / k / v carry a bias, o_proj
+    does not (:173-176); RoPE with 0-based positions, inv_freq = theta^(-2i/d), cos / sin cast to the activation dtype (:99-123,
+    352-363); causal x key-padding additive mask of finfo.min (:498-604); final RMSNorm; lm_head (tied to embed_tokens unless the
+    state dict says otherwise). cfg: the Config fields as a dict (+ head_dim)."""
+    h = sd["model.embed_tokens.weight"][input_ids]  # (the live copy: ModelForCausalLM.forward runs `self.model`, :610,648)
+    bsz, seqlen = input_ids.shape
+    nh, nkv, d = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["head_dim"]
+    pos = torch.arange(seqlen)[None].expand(bsz, -1)
+    mask = decoder_mask(bsz, seqlen, attention_mask, 0, h.dtype)
+    for i in range(cfg["num_hidden_layers"]):
+        lp = f"model.layers.{i}."
+        x = rms_norm(h, sd[lp + "input_layernorm.weight"], cfg["rms_norm_eps"])
+        q = split_heads(linear(x, sd[lp + "self_attn.q_proj.weight"], sd[lp + "self_attn.q_proj.bias"]), d)
+        k = split_heads(linear(x, sd[lp + "self_attn.k_proj.weight"], sd[lp + "self_attn.k_proj.bias"]), d)
+        v = split_heads(linear(x, sd[lp + "self_attn.v_proj.weight"], sd[lp + "self_attn.v_proj.bias"]), d)
+        q, k = gemma_rope(q, k, pos, cfg["rope_theta"])
+        a = merge_heads(sdpa(q, repeat_kv(k, nh // nkv), repeat_kv(v, nh // nkv), mask))
+        h = h + linear(a, sd[lp + "self_attn.o_proj.weight"], None)
+        x = rms_norm(h, sd[lp + "post_attention_layernorm.weight"], cfg["rms_norm_eps"])
+        h = h + gated_mlp(x, sd[lp + "mlp.gate_proj.weight"], sd[lp + "mlp.up_proj.weight"], sd[lp + "mlp.down_proj.weight"])
+    h = rms_norm(h, sd["model.norm.weight"], cfg["rms_norm_eps"])
+    return linear(h, sd.get("lm_head.weight", sd["model.embed_tokens.weight"]), None)

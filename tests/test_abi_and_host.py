@@ -182,8 +182,11 @@ def test_vyomai_import_name_is_a_drop_in_for_the_hot_path():
     from VyomAI import DoraLinear, EncoderDecoderModel, LoraLinear, Seq2SeqDecoderModel, generate_seq2seq  # noqa: F401  (round 2)
     from VyomAI.models.encoder_decoder import EncoderDecoderModel as E2
     assert E2 is vyomai_b200.EncoderDecoderModel
+    from VyomAI import ModelForCausalLM  # noqa: F401  (inference path of models/custom_transformer.py)
+    from VyomAI.models.custom_transformer import Config as HfStyleConfig
+    assert HfStyleConfig(hidden_size=256, num_attention_heads=2).head_dim == 128
     with pytest.raises(ImportError):
-        from VyomAI import ModelForCausalLM  # noqa: F401
+        from VyomAI import TopKProcessor  # noqa: F401
     with pytest.raises(ImportError):
         VyomAI.speculative_generate
 

@@ -310,7 +310,17 @@ class _RopeTable:
         return self.cos, self.sin
 
 
+def _norm_eps(norm: nn.Module) -> float:
+    return norm.eps if hasattr(norm, "eps") else norm.variance_epsilon
+
+
 class GemmaModel(nn.Module):
+    # what distinguishes this decoder from the other pre-norm / RoPE / gated-MLP decoder of the reference
+    # (models/custom_transformer.py), which runs through the same run_layers: norm kind, gate activation, first position
+    _norm_kind = "gemma_rmsnorm"   # (1 + w) * xhat
+    _mlp_act = "geglu_tanh"        # gelu_tanh(gate) * up
+    _pos_off = 1                   # PaliGemma positions are 1-indexed (cell 17)
+
     def __init__(self, config: GemmaConfig):
         super().__init__()
         self.padding_idx = config.pad_token_id
@@ -341,31 +351,31 @@ class GemmaModel(nn.Module):
             cos, sin = self._rope.get(start + S + 1, h.device, T)
         for li, layer in enumerate(self.layers):
             att = layer.self_attn
-            x, _, _, _ = ops.add_layernorm(h, None, layer.input_layernorm.weight, None, layer.input_layernorm.eps, kind="gemma_rmsnorm")
+            x, _, _, _ = ops.add_layernorm(h, None, layer.input_layernorm.weight, None, _norm_eps(layer.input_layernorm), kind=self._norm_kind)
             qkv = _lin(x, _packed(att, ("q_proj", "k_proj", "v_proj"), "weight"), _packed(att, ("q_proj", "k_proj", "v_proj"), "bias"))
             v4 = qkv.view(B, S, nh + 2 * nkv, hd).permute(0, 2, 1, 3)  # [B, heads, S, hd] view of the packed projection
             q, k_new, v_new = v4[:, :nh], v4[:, nh:nh + nkv], v4[:, nh + nkv:]
             if cache is not None:  # RoPE(q) in place, RoPE(k) and v straight into the cache: one launch
                 kc, vc = cache.key_cache[li], cache.value_cache[li]
-                ops.rope_append(v4, nh, nkv, kc, vc, cos, sin, start + 1, start, pos_dev=pos_dev)
+                ops.rope_append(v4, nh, nkv, kc, vc, cos, sin, start + self._pos_off, start, pos_dev=pos_dev)
                 if on_dev:
                     k_att, v_att = kc[:B], vc[:B]  # every slot of the cache; the kernel stops at the device-side position
                 else:
                     k_att, v_att = kc[:B, :, :start + S], vc[:B, :, :start + S]
             else:
-                ops.rope_into(q, q, cos, sin, start + 1)
-                ops.rope_into(k_new, k_new, cos, sin, start + 1)
+                ops.rope_into(q, q, cos, sin, start + self._pos_off)
+                ops.rope_into(k_new, k_new, cos, sin, start + self._pos_off)
                 k_att, v_att = k_new, v_new
             # inference (cell 17 _update_causal_mask): a multi-token call sees its whole prefix, a single token everything
             # before it — both are "no causal mask" over [0, start + S); padding columns stay masked
             a, _ = ops.attn_fwd(q, k_att, v_att, causal=not prefix_visible, q_pos0=start, key_padding_mask=key_padding, out_dtype=T,
                                 pos_dev=pos_dev)
             h = _lin(a.view(B * S, nh * hd), att.o_proj.weight, att.o_proj.bias, addend=h)
-            x, _, _, _ = ops.add_layernorm(h, None, layer.post_attention_layernorm.weight, None, layer.post_attention_layernorm.eps,
-                                           kind="gemma_rmsnorm")
-            g = ops.gemm(x, _interleaved_gate_up(layer.mlp), act="geglu_tanh")
+            x, _, _, _ = ops.add_layernorm(h, None, layer.post_attention_layernorm.weight, None, _norm_eps(layer.post_attention_layernorm),
+                                           kind=self._norm_kind)
+            g = ops.gemm(x, _interleaved_gate_up(layer.mlp), act=self._mlp_act)
             h = _lin(g, layer.mlp.down_proj.weight, None, addend=h)
-        y, _, _, _ = ops.add_layernorm(h, None, self.norm.weight, None, self.norm.eps, kind="gemma_rmsnorm")
+        y, _, _, _ = ops.add_layernorm(h, None, self.norm.weight, None, _norm_eps(self.norm), kind=self._norm_kind)
         return y
 
 
@@ -482,8 +492,12 @@ class PaliGemmaDecodeGraph:
     lm_head, argmax, position increment) is captured once after the prefill and replayed — an eager step is ~230 launches whose
     host cost exceeds their device time. Programmatic dependent launch is on during the capture, as for DecoderModel's graph."""
 
-    def __init__(self, model: "PaliGemmaForConditionalGeneration", cache: StaticCache, prefill_mask: torch.Tensor):
+    def __init__(self, model, cache: StaticCache, prefill_mask: torch.Tensor):
+        """`model`: PaliGemmaForConditionalGeneration, or any object whose `language_model` (or itself) has `.model` (embed_tokens,
+        run_layers) and `.lm_head` — models/custom_transformer.ModelForCausalLM reuses this class."""
         self.model, self.cache = model, cache
+        self.lm = getattr(model, "language_model", model)
+        self.embed_scale = getattr(self.lm, "embed_scale", None)
         dev = cache.key_cache[0].device
         B, S0 = prefill_mask.shape
         self.B = B
@@ -494,11 +508,12 @@ class PaliGemmaDecodeGraph:
         self.graph = None
 
     def _step(self) -> None:
-        lm = self.model.language_model
+        lm = self.lm
         H = lm.model.config.hidden_size
         table = lm.model.embed_tokens.weight
         rows = torch.empty((self.B, H), device=table.device, dtype=table.dtype)
-        ops.embed(self.tok, table, out=rows, tokens_per_seq=1, out_group_stride=1, out_scale=math.sqrt(H))
+        ops.embed(self.tok, table, out=rows, tokens_per_seq=1, out_group_stride=1,
+                  out_scale=math.sqrt(H) if self.embed_scale is None else self.embed_scale)
         h = lm.model.run_layers(rows, self.B, 1, self.pos, self.kpm, self.cache, prefix_visible=True)
         V = lm.lm_head.weight.shape[0]
         buf = torch.empty((self.B, (V + 7) // 8 * 8), device=table.device, dtype=h.dtype)
