@@ -613,6 +613,9 @@ static void decode_tma_plan(int B, int Hkv, int ctx, int* splits, int* stages) {
   const int per_chunks = ((ctx + sp - 1) / sp + vy::TD_CHUNK - 1) / vy::TD_CHUNK;
   int st = per_chunks < 3 ? (per_chunks < 1 ? 1 : per_chunks) : 3;
   if (static_cast<long long>(items) * sp <= sms && per_chunks > 3) st = per_chunks < vy::TD_MAX_STAGES ? per_chunks : vy::TD_MAX_STAGES;  // one CTA per SM anyway
+  // 3-stage rings (96 KB) put two CTAs on an SM, 2-stage rings (64 KB) three: when the CTAs need more than two per SM but fit
+  // three, one wave of 2-stage CTAs beats a full wave plus a thin second one (MHA config 3: 384 CTAs, 252.6 -> 236.8 us/step)
+  if (st == 3 && static_cast<long long>(items) * sp > 2LL * sms && static_cast<long long>(items) * sp <= 3LL * sms) st = 2;
   if (f_stages > 0) st = f_stages > vy::TD_MAX_STAGES ? vy::TD_MAX_STAGES : f_stages;
   *splits = sp;
   *stages = st;
