@@ -630,6 +630,11 @@ VY_API int vy_patchify(const VyPatchify* p);
  * torch.topk(k=1) rule of VyomAI/models/decoder.py:489-496 and generation_utils.py:179-189
  * (argmax of softmax(logits) == argmax of logits). out is int64 [rows]. */
 VY_API int vy_argmax_rows(int rows, int V, const void* x, int64_t ld, int dtype, int64_t* out, void* stream);
+/* The same plus the greedy loop's bookkeeping (models/decoder.py:489-500) in the same launch sequence: out[r] = argmax, then
+ * *pos += 1 and, when `tokens` is given, tokens[r * tokens_ld + *pos] = out[r] (skipped when *pos falls outside
+ * [0, tokens_cols)). rows <= 1024. pos is a device int32 scalar: the tail of a captured single-token decode step. */
+VY_API int vy_argmax_advance(int rows, int V, const void* x, int64_t ld, int dtype, int64_t* out, int32_t* pos, int64_t* tokens, int64_t tokens_ld,
+                             int tokens_cols, void* stream);
 
 /* vy_colsum — out[c] (+)= scale * sum_r x[r, c]: the bias gradient of every nn.Linear on the path.
  * workspace: vy_colsum_workspace_floats(cols) floats. */

@@ -236,6 +236,25 @@ argmax_unpack_kernel(int rows, unsigned long long* __restrict__ out) {
   reinterpret_cast<long long*>(out)[r] = idx;
 }
 
+// unpack + the greedy loop's bookkeeping in one launch (one CTA, rows <= 1024): tok[r] = argmax index, *pos += 1,
+// tokens[r][*pos] = tok[r] — the tail of a captured decode step (decoder.py:489-500: append the token, advance cur_pos)
+__global__ void __launch_bounds__(1024)
+argmax_advance_kernel(int rows, unsigned long long* __restrict__ out, int* __restrict__ pos, long long* __restrict__ tokens, long long tokens_ld,
+                      int tokens_cols) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = threadIdx.x;
+  const int np = *pos + 1;
+  if (r < rows) {
+    const unsigned long long key = out[r];
+    const long long idx = key == 0ull ? 0ll : static_cast<long long>(0xffffffffu - static_cast<unsigned int>(key & 0xffffffffull));
+    reinterpret_cast<long long*>(out)[r] = idx;
+    if (tokens && np >= 0 && np < tokens_cols) tokens[r * tokens_ld + np] = idx;
+  }
+  __syncthreads();  // every thread has read *pos
+  if (r == 0) *pos = np;
+}
+
 // ------------------------------------------------------------------------------------------
 // column sums (bias gradients): stage 1 partial sums over row chunks, stage 2 final reduce
 // ------------------------------------------------------------------------------------------
@@ -773,6 +792,30 @@ extern "C" int vy_argmax_rows(int rows, int V, const void* x, int64_t ld, int dt
   VY_LAUNCH_OK();
   VY_CUDA_OK(launch_kernel(argmax_unpack_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, rows,
                            reinterpret_cast<unsigned long long*>(out)));
+  VY_LAUNCH_OK();
+  count_launch(2);
+  return VY_OK;
+}
+
+extern "C" int vy_argmax_advance(int rows, int V, const void* x, int64_t ld, int dtype, int64_t* out, int32_t* pos, int64_t* tokens, int64_t tokens_ld,
+                                 int tokens_cols, void* stream) {
+  VY_NEED_DEVICE("vy_argmax_advance");
+  VY_CHECK_ARG(rows > 0 && rows <= 1024 && V > 0 && x && out && pos && dtype_ok(dtype) && (!tokens || (tokens_ld >= tokens_cols && tokens_cols > 0)),
+               "vy_argmax_advance: bad arguments (rows <= 1024)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int slices = (2 * num_sms() + rows - 1) / rows;  // ~2 CTAs per SM over all rows
+  const int max_slices = (V + 2047) / 2048;         // at least 2048 columns per slice
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  int per = (V + slices - 1) / slices;
+  per = (per + 7) / 8 * 8;  // slices start on 16-byte boundaries of a bf16 row
+  slices = (V + per - 1) / per;
+  VY_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(int64_t) * rows, st));
+  VY_CUDA_OK(launch_kernel(argmax_rows_kernel, dim3(slices, rows), dim3(256), 0, st, rows, V, per, x, ld, dtype,
+                           reinterpret_cast<unsigned long long*>(out)));
+  VY_LAUNCH_OK();
+  VY_CUDA_OK(launch_kernel(argmax_advance_kernel, dim3(1), dim3(1024), 0, st, rows, reinterpret_cast<unsigned long long*>(out), static_cast<int*>(pos),
+                           reinterpret_cast<long long*>(tokens), static_cast<long long>(tokens_ld), tokens_cols));
   VY_LAUNCH_OK();
   count_launch(2);
   return VY_OK;

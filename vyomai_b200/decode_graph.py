@@ -55,9 +55,7 @@ class GreedyDecodeGraph:
             x, _ = F.feed_forward(y, x, ff.intermediate, ff.out, ff.layernorm, act=ff._act_name)
         head = m.lm_head
         logits, _ = F.lm_head(x, head.dense, head.layer_norm, head.decoder.weight, head.bias)
-        ops.argmax_rows(logits, out=self.tok)
-        self.pos.add_(1)
-        self.tokens.scatter_(1, self.pos.to(torch.long).expand(B, 1), self.tok.view(B, 1))
+        ops.argmax_advance(logits, self.tok, self.pos, self.tokens)  # tok = argmax; pos += 1; tokens[:, pos] = tok
 
     def capture(self) -> None:
         side = torch.cuda.Stream()

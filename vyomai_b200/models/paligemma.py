@@ -518,8 +518,7 @@ class PaliGemmaDecodeGraph:
         V = lm.lm_head.weight.shape[0]
         buf = torch.empty((self.B, (V + 7) // 8 * 8), device=table.device, dtype=h.dtype)
         logits = _lin(h, lm.lm_head.weight, None, out=buf[:, :V])
-        ops.argmax_rows(logits, out=self.tok)
-        self.pos.add_(1)
+        ops.argmax_advance(logits, self.tok, self.pos)  # tok = argmax; pos += 1
 
     def capture(self) -> None:
         import os

@@ -580,6 +580,20 @@ def argmax_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
+def argmax_advance(x: torch.Tensor, out: torch.Tensor, pos: torch.Tensor, tokens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """argmax_rows into `out`, then pos += 1 (device int32 scalar) and tokens[:, pos] = out (tokens: [rows, n] int64, unit inner
+    stride) — one launch sequence for the tail of a captured greedy step."""
+    _need_cuda(x, out, pos, tokens)
+    if out.dtype != torch.int64 or not out.is_contiguous() or out.numel() != x.shape[0] or pos.dtype != torch.int32 or pos.numel() != 1:
+        raise _lib.VyomError("argmax_advance: out must be contiguous int64 [rows], pos one int32 element")
+    if tokens is not None and (tokens.dtype != torch.int64 or tokens.dim() != 2 or tokens.stride(1) != 1 or tokens.shape[0] != x.shape[0]):
+        raise _lib.VyomError("argmax_advance: tokens must be int64 [rows, n] with a unit inner stride")
+    _lib.check(_lib.lib().vy_argmax_advance(x.shape[0], x.shape[1], x.data_ptr(), x.stride(0), _dt(x), out.data_ptr(), pos.data_ptr(),
+                                           _ptr(tokens), tokens.stride(0) if tokens is not None else 0,
+                                           tokens.shape[1] if tokens is not None else 0, _stream()), "vy_argmax_advance")
+    return out
+
+
 def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
            accumulate: bool = False, scale: float = 1.0) -> torch.Tensor:
     """out[c] (+)= sum_r x[r, c] (bias gradients)."""
