@@ -348,7 +348,9 @@ def test_gemm_epilogues_vs_oracle(dtype, tol):
 
 
 @pytest.mark.parametrize("case", [(32, 768, 768), (32, 1280, 768), (32, 3072, 768), (32, 768, 3072), (32, 50265, 768), (1, 768, 768),
-                                  (7, 1000, 256), (17, 40, 128), (24, 2048, 2048), (9, 776, 1536)],
+                                  (7, 1000, 256), (17, 40, 128), (24, 2048, 2048), (9, 776, 1536),
+                                  # the PaliGemma-scale projections: long K (6 double-buffered chunks per warp, 4-CTA clusters), 1 and 32 rows
+                                  (1, 2048, 16384), (32, 2048, 16384), (1, 2560, 2048)],
                          ids=lambda c: "n%d_F%d_K%d" % c)
 def test_small_batch_gemm_vs_oracle(case):
     """The weight-streaming kernel behind swap-AB vy_gemm calls with <= 32 activation rows (csrc/gemm_skinny.cu): bias, both

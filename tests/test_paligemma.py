@@ -252,3 +252,73 @@ def test_paligemma_graph_decode_step_matches_eager_step_logits():
         assert rel_l2(cache.key_cache[li][:, :, :S0 + 1].float().cpu(), cache2.key_cache[li][:, :, :S0 + 1].float().cpu()) <= 1e-2
         assert rel_l2(cache.value_cache[li][:, :, :S0 + 1].float().cpu(), cache2.value_cache[li][:, :, :S0 + 1].float().cpu()) <= 1e-2
         assert float(cache.key_cache[li][:, :, S0 + 1:].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_paligemma_real_width_layers_vs_oracle():
+    """The REAL layer widths of config 5 (SigLIP 1152 / 16 heads of 72 / MLP 4304 / 14-pixel patches of a 224 image; Gemma 2048 /
+    8 query heads + 1 kv head of 256 / GeGLU 16384) with two layers each and a 32 000-token vocabulary, so that the kernels run
+    the shapes of the benchmark (K = 16384 small-batch GEMM, 1-row gated GEMM, 256-wide packed-head decode tile split over keys,
+    592-column patch rows) — against the CPU oracle on the same seeded bf16-representable weights: image features, the last-position
+    prefill logits and three teacher-forced cached steps (eager and CUDA-graph), greedy choice where the oracle's margin allows."""
+    from vyomai_b200 import ops
+    from vyomai_b200.models.paligemma import PaliGemmaConfig, PaliGemmaDecodeGraph, PaliGemmaForConditionalGeneration, StaticCache
+    vis = dict(hidden_size=1152, intermediate_size=4304, num_hidden_layers=2, num_attention_heads=16, num_channels=3, image_size=224,
+               patch_size=14, layer_norm_eps=1e-6)
+    txt = dict(vocab_size=32000, hidden_size=2048, intermediate_size=16384, num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=1,
+               head_dim=256, max_position_embeddings=512, rms_norm_eps=1e-6, rope_theta=10000.0)
+    meta = {"hidden_size": 2048, "image_token_index": 31999, "vision": vis, "text": txt}
+    cfg = PaliGemmaConfig(vision_config=dict(vis), text_config=dict(txt), image_token_index=31999, vocab_size=32000, projection_dim=2048,
+                          hidden_size=2048, pad_token_id=0)
+    torch.manual_seed(5)
+    model = PaliGemmaForConditionalGeneration(cfg)
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("layernorm.weight") or n.endswith("model.norm.weight"):
+                p.copy_((0.1 * torch.randn(p.shape, generator=g)).bfloat16().float())
+            elif p.dim() >= 2:
+                p.copy_((0.02 * torch.randn(p.shape, generator=g)).bfloat16().float())
+            else:
+                p.copy_((0.02 * torch.randn(p.shape, generator=g) + (1.0 if "layer_norm" in n or "post_layernorm" in n else 0.0) * (".weight" in n)).bfloat16().float())
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().to(torch.bfloat16).eval()
+    B, n_img, n_txt = 2, 256, 6
+    ids = torch.cat([torch.full((B, n_img), 31999, dtype=torch.long), torch.randint(1, 31000, (B, n_txt), generator=g)], dim=1)
+    mask = torch.ones(B, n_img + n_txt, dtype=torch.long)
+    mask[1, -2:] = 0  # a right-padded row
+    ids[1, -2:] = 0
+    px = torch.rand(B, 3, 224, 224, generator=g).bfloat16().float()
+    TOLB = 2e-2
+    with torch.no_grad():
+        feats = O.siglip_forward(sd, "vision_tower.vision_model.", px, 14, 2, 16, 1e-6)
+    got_f = model.vision_tower(px.cuda().bfloat16()).last_hidden_state
+    assert rel_l2(got_f.float().cpu(), feats) <= TOLB
+    S0, CL = n_img + n_txt, 320
+    ocache = ([torch.zeros(B, 1, CL, 256) for _ in range(2)], [torch.zeros(B, 1, CL, 256) for _ in range(2)])
+    with torch.no_grad():
+        ref0 = O.paligemma_forward(sd, meta, ids, px, mask, cache=ocache, seen=0, cache_len=CL)[:, -1]
+    cache = StaticCache(cfg.text_config, batch_size=B, device="cuda", dtype=torch.bfloat16, max_cache_len=CL)
+    out = model(input_ids=ids.cuda(), pixel_values=px.cuda().bfloat16(), attention_mask=mask.cuda(), past_key_values=cache, use_cache=True,
+                logits_last_only=True)
+    assert rel_l2(out.logits[:, -1].float().cpu()[:1], ref0[:1]) <= TOLB  # (row 1 ends in padding: its last position is a pad query)
+    graph = PaliGemmaDecodeGraph(model, cache, mask.cuda())
+    cur = ref0.argmax(-1)  # teacher forcing on the oracle's own choices
+    am = mask
+    toks = torch.empty((B, 1), dtype=torch.long, device="cuda")
+    for s in range(3):
+        am = torch.cat([am, torch.ones(B, 1, dtype=am.dtype)], -1)
+        with torch.no_grad():
+            ref = O.paligemma_forward(sd, meta, cur.view(B, 1), None, am, cache=ocache, seen=S0 + s, cache_len=CL)[:, -1]
+        if s < 2:  # eager cached step
+            o = model(input_ids=cur.view(B, 1).cuda(), attention_mask=am.cuda(), past_key_values=cache, use_cache=True, logits_last_only=True)
+            assert rel_l2(o.logits[:, -1].float().cpu(), ref) <= TOLB, s
+        else:      # the same step as one CUDA-graph replay: compare the choice it makes where the oracle is sure
+            graph.run(cur.cuda(), S0 + s, 1, toks)
+            top2 = ref.topk(2, -1).values
+            sure = (top2[:, 0] - top2[:, 1]) > 0.15
+            assert torch.equal(toks[:, 0].cpu()[sure], ref.argmax(-1)[sure])
+        cur = ref.argmax(-1)
+    for li in range(2):
+        assert rel_l2(cache.key_cache[li][:, :, :S0 + 3].float().cpu(), ocache[0][li][:, :, :S0 + 3]) <= TOLB
+        assert float(cache.key_cache[li][:, :, S0 + 3:].abs().max()) == 0.0
