@@ -343,3 +343,17 @@ def test_gemm_tuner_picks_by_measurement_redirects_written_buffers_and_persists(
     monkeypatch.setattr(T, "_time", lambda k, device, runs=3: 50.0 if "hint_bn" not in k else 49.5)
     assert T.hints(("sig", 2), kw, [("out", out)], torch.device("cpu")) == {}
     T.clear()
+
+
+def test_sharded_step_host_logic():
+    """dp_shard: shards are contiguous, 8-element aligned, cover the flat buffer exactly once for every world size; without an
+    initialised NCCL process group the peer-memory mode reports itself unavailable (the trainer then uses the NCCL / single path)."""
+    from vyomai_b200 import dp_shard
+    for n in (8 * 1, 8 * 1000, 8 * 12345, 8 * 20_000_001):
+        for world in range(1, 9):
+            edges = [dp_shard.shard_bounds(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (lo, hi), (lo2, _hi2) in zip(edges, edges[1:]):
+                assert hi == lo2 and lo % 8 == 0 and hi % 8 == 0 and lo <= hi
+    assert dp_shard.available() is False  # no CUDA device / no process group here
+    assert dp_shard.MAX_WORLD == 8
