@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VY_ABI_VERSION 6
+#define VY_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define VY_API __attribute__((visibility("default")))
@@ -641,6 +641,10 @@ VY_API int vy_argmax_advance(int rows, int V, const void* x, int64_t ld, int dty
 VY_API int vy_colsum(int rows, int cols, const void* x, int64_t ld, int dtype, void* out, int out_dtype,
                      int accumulate, float scale, float* workspace, void* stream);
 VY_API int vy_colsum_workspace_floats(int cols);
+/* Second stage of a two-stage column sum on its own: out[c] (+)= scale * (*scale_ptr if given) * sum_k part[k * part_ld + c],
+ * k < chunks, added in index order. Used for the partial sums vy_softmax_xent leaves in VyXent.colsum_part. */
+VY_API int vy_colsum_finish(int cols, int chunks, const float* part, int64_t part_ld, void* out, int out_dtype, int accumulate,
+                            float scale, const float* scale_ptr, void* stream);
 
 /* vy_cast4d — strided 4-D copy with dtype conversion (inner dim contiguous on both sides), e.g.
  * an fp32 StaticCacheOne prefix (layers/kv_cache.py:295-312) to the bf16 attention operands. */
@@ -673,10 +677,17 @@ typedef struct VyXent {
   float grad_scale;
   float* loss_rows; /* [rows] or NULL */
   int32_t write_grad;
+  /* Optional, with write_grad: [vy_xent_colsum_chunks(rows, V, dtype)][V rounded up to 8] fp32; needs ld % 8 == 0 and
+   * ld >= V rounded up to 8 (columns V .. of the logits rows are then written with zeros). The column sums of the written gradient
+   * (the bias gradient of the vocabulary projection, models/decoder.py:267-275 `self.decoder` of LMHead) are then taken in
+   * the same pass as per-CTA partial sums, to be added up by vy_colsum_finish: the [rows, V] gradient is not re-read. */
+  float* colsum_part;
   void* stream;
 } VyXent;
 
 VY_API int vy_softmax_xent(const VyXent* p);
+/* Rows of VyXent.colsum_part for this shape; 0 = the fused column sums are not available (needs bf16, V <= 57344). */
+VY_API int vy_xent_colsum_chunks(int rows, int V, int dtype);
 
 /* vy_sqnorm — *out += sum(g^2) over a flat gradient buffer (out must be zeroed by the caller);
  * vy_adamw — fused AdamW over a flat parameter buffer (torch.optim.AdamW semantics: decoupled

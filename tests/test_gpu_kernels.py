@@ -462,3 +462,82 @@ def test_decode_through_the_bare_layer_api_with_a_freqs_slice():
         got1 = att(x[:, 5:].to(DEV), None, freqs=freqs[:, 5:6], use_cache=True, start_pos=5)
     assert rel_l2(got0.cpu(), ref0) <= 6e-3
     assert rel_l2(got1.cpu(), ref1) <= 6e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# softmax cross-entropy with the vocabulary bias gradient (column sums of the written gradient) taken in the same pass
+# ---------------------------------------------------------------------------------------------
+XENT_COLSUM_CASES = [
+    # rows, V, row stride, ignored rows
+    (300, 50272, 50272, "some"),   # the captioner's vocabulary: 7 vectors per thread, the last one partly populated
+    (37, 1000, 1024, "some"),      # fewer rows than CTAs, padded rows, one vector per thread for 125 threads
+    (160, 8192, 8192, "none"),
+    (129, 50265, 50272, "some"),   # bench.py's vocabulary: the last vector holds one column and seven padding lanes
+    (40, 1003, 1008, "none"),
+    (150, 57344, 57344, "all"),    # the widest vocabulary the fused path takes; every row ignored -> zeros
+]
+
+
+@pytest.mark.parametrize("rows,V,ld,ignored", XENT_COLSUM_CASES)
+def test_softmax_xent_with_fused_column_sums(rows, V, ld, ignored):
+    """vy_softmax_xent(colsum_part) + vy_colsum_finish against the oracle's loss (cross_entropy_shifted's formula:
+    logsumexp - picked logit, ignore_index rows dropped) and autograd's gradients of it: row losses, the gradient written
+    over the logits, and its column sums (the LM head's bias gradient) — also against the two-kernel path (vy_softmax_xent
+    without colsum_part, then vy_colsum). Tolerances: losses 2e-5 (fp32 math on the same bf16 logits), gradient 4e-3 rel-L2
+    (bf16 storage), column sums 2e-3 rel-L2 of the oracle's fp32 sums (the fused sums add unrounded fp32 terms)."""
+    from vyomai_b200 import ops
+    g = _gen(1234 + rows)
+    x = (torch.randn(rows, V, generator=g) * 2.5).to(torch.bfloat16)
+    labels = torch.randint(0, V, (rows,), generator=g)
+    if ignored == "some":
+        labels[::5] = -100
+        labels[rows - 1] = -100
+    elif ignored == "all":
+        labels[:] = -100
+    gs = 1.0 / max(1, int((labels != -100).sum()))
+    xr = x.float().requires_grad_(True)
+    keep = labels != -100
+    lse = torch.logsumexp(xr, dim=-1)
+    picked = xr.gather(1, labels.clamp(min=0)[:, None])[:, 0]
+    ref_rows = (lse - picked) * keep
+    (ref_rows.sum() * gs).backward()
+    ref_grad, ref_bias = xr.grad, xr.grad.sum(0)
+
+    def device_logits():
+        buf = torch.full((rows, ld), float("nan"), dtype=torch.bfloat16, device=DEV)  # padding columns hold garbage
+        buf[:, :V] = x.to(DEV)
+        return buf[:, :V]
+
+    lg = device_logits()
+    part = ops.xent_colsum_part(lg)
+    assert part is not None and part.shape[1] == V
+    inv = torch.tensor([gs], dtype=torch.float32, device=DEV)
+    loss_rows = ops.softmax_xent(lg, labels.to(DEV), ignore_index=-100, grad_scale_ptr=inv, write_grad=True, colsum_part=part)
+    two = torch.tensor([2.0], dtype=torch.float32, device=DEV)
+    bias = ops.colsum_finish(part, out_dtype=torch.float32)
+    bias2 = ops.colsum_finish(part, out=bias.clone(), accumulate=True, scale_ptr=two)  # b + 2 b
+    torch.cuda.synchronize()
+    assert torch.allclose(loss_rows.cpu(), ref_rows.detach(), rtol=2e-5, atol=2e-5)
+    if ignored == "all":
+        assert not lg.any() and not bias.any()
+        return
+    assert rel_l2(lg.float().cpu(), ref_grad) <= 4e-3
+    assert not lg[~keep.to(DEV)].any()
+    pad = torch.as_strided(lg, (rows, (V + 7) // 8 * 8), (ld, 1), lg.storage_offset())[:, V:]
+    assert not pad.any()  # the lanes of a last partial vector beyond V are written with zeros
+    assert rel_l2(bias.cpu(), ref_bias) <= 2e-3
+    assert torch.allclose(bias2, 3.0 * bias, rtol=1e-6, atol=0.0)
+    # the two-kernel path on the same inputs
+    lg2 = device_logits()
+    loss_rows2 = ops.softmax_xent(lg2, labels.to(DEV), ignore_index=-100, grad_scale_ptr=inv, write_grad=True)
+    bias_sep = ops.colsum(lg2, out_dtype=torch.float32)
+    assert torch.allclose(loss_rows2, loss_rows, rtol=2e-5, atol=2e-5)
+    assert rel_l2(lg.float(), lg2.float()) <= 4e-3
+    assert rel_l2(bias, bias_sep) <= 4e-3
+
+
+def test_fused_column_sums_are_declined_outside_their_shapes():
+    from vyomai_b200 import ops
+    assert ops.xent_colsum_part(torch.zeros(4, 1000, device=DEV)) is None                          # fp32 logits
+    assert ops.xent_colsum_part(torch.zeros(4, 1004, device=DEV, dtype=torch.bfloat16)) is None    # rows do not cover V rounded up to 8
+    assert ops.xent_colsum_part(torch.zeros(4, 57352, device=DEV, dtype=torch.bfloat16)) is None   # wider than the accumulators

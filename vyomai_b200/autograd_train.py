@@ -348,12 +348,22 @@ def _padded_logits(rows: int, V: int, like: torch.Tensor):
     return buf[:, :V]
 
 
-def _lm_head_backward(ctx_saved, params, dlogits):
+def _lm_head_backward(ctx_saved, params, dlogits, bias_part=None, gout=None):
+    """`bias_part`: the per-CTA column sums of dlogits vy_softmax_xent took while writing it (for an upstream gradient of 1;
+    `gout`, a device scalar, rescales them) — the 0.8 GB gradient is then not read a third time for the bias."""
     h2d, z, a, n, mean, rstd = ctx_saved
     wd, bd, gamma, beta, wv, bv = params
     fork = ops.side_fork_point()
     d_wv = _emit_wgrad(wv, dlogits, n)
-    d_bv = _emit_bgrad(bv, dlogits, after=fork)  # 0.8 GB of dlogits summed under the 0.5 ms vocabulary wgrad GEMM
+    if bv is not None and bias_part is not None:
+        if _direct(bv):
+            ops.colsum_finish(bias_part, out=bv.grad, accumulate=not _overwrite(bv), scale_ptr=gout)
+            _ready(bv)
+            d_bv = None
+        else:
+            d_bv = ops.colsum_finish(bias_part, out_dtype=bv.dtype, scale_ptr=gout)
+    else:
+        d_bv = _emit_bgrad(bv, dlogits, after=fork)  # 0.8 GB of dlogits summed under the 0.5 ms vocabulary wgrad GEMM
     dn = _dgrad(dlogits, wv)
     da, dgamma, dbeta, _ = _ln_bwd(dn, a, gamma, beta, mean, rstd)
     dz = ops.act_bwd(da, z, "gelu")
@@ -402,20 +412,24 @@ class LMHeadLossFn(torch.autograd.Function):
         labels = labels.reshape(-1).contiguous()
         n_valid = (labels != ignore_index).sum().clamp(min=1).to(torch.float32)
         inv = (1.0 / n_valid).reshape(1)
-        loss_rows = ops.softmax_xent(logits, labels, ignore_index=ignore_index, grad_scale_ptr=inv, write_grad=True)
+        part = ops.xent_colsum_part(logits) if (bv is not None and ctx.needs_input_grad[8]) else None
+        loss_rows = ops.softmax_xent(logits, labels, ignore_index=ignore_index, grad_scale_ptr=inv, write_grad=True, colsum_part=part)
         ctx.params = (wd, bd, gamma, beta, wv, bv)
-        ctx.save_for_backward(h2d, z, a, n, mean, rstd, logits)
+        ctx.has_part = part is not None
+        ctx.save_for_backward(h2d, z, a, n, mean, rstd, logits, *([part] if part is not None else []))
         return loss_rows.sum() * inv[0]
 
     @staticmethod
     def backward(ctx, gout):
-        *saved, dlogits = ctx.saved_tensors
+        saved = list(ctx.saved_tensors)
+        part = saved.pop() if ctx.has_part else None
+        dlogits = saved.pop()
         # dlogits already holds d loss / d logits for an upstream gradient of 1 (what loss.backward() passes); any other
         # upstream gradient (a scaled / accumulated loss) is applied on the device — the kernel returns at once for 1
         ld = dlogits.stride(0)  # the row-padded buffer behind the [:, :V] view
-        ops.scale_by_ptr(torch.as_strided(dlogits, (dlogits.shape[0], ld), (ld, 1), dlogits.storage_offset()),
-                         gout.to(torch.float32).reshape(1))
-        grads = _lm_head_backward(saved, ctx.params, dlogits)
+        g32 = gout.to(torch.float32).reshape(1)
+        ops.scale_by_ptr(torch.as_strided(dlogits, (dlogits.shape[0], ld), (ld, 1), dlogits.storage_offset()), g32)
+        grads = _lm_head_backward(saved, ctx.params, dlogits, bias_part=part, gout=g32)
         return (None, None, *grads, None)
 
 

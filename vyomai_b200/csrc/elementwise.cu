@@ -305,15 +305,15 @@ colsum_partial_kernel(int R, int Cn, const void* __restrict__ x, long long ld, i
   }
 }
 __global__ void __launch_bounds__(128)
-colsum_final_kernel(int Cn, int chunks, const float* __restrict__ part, void* __restrict__ out, int out_dt, int accumulate,
-                    float scale) {
+colsum_final_kernel(int Cn, int chunks, const float* __restrict__ part, long long pld, void* __restrict__ out, int out_dt, int accumulate,
+                    float scale, const float* __restrict__ scale_ptr) {
   pdl_trigger();
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
   float a = 0.f;
-  for (int k = 0; k < chunks; ++k) a += part[static_cast<long long>(k) * Cn + c];
-  a *= scale;
+  for (int k = 0; k < chunks; ++k) a += part[static_cast<long long>(k) * pld + c];
+  a *= scale_ptr ? scale * *scale_ptr : scale;
   if (accumulate) a += ld_as_float(out, out_dt, c);
   st_from_float(out, out_dt, c, a);
 }
@@ -429,6 +429,157 @@ xent_kernel(int rows, int V, void* __restrict__ logits, long long ld, int dt, co
     for (int c = nvec * 8 + threadIdx.x; c < V; c += blockDim.x) {
       const float pr = __expf(ld_as_float(logits, dt, base + c) - mx) * inv;
       st_from_float(logits, dt, base + c, (pr - (c == lab ? 1.f : 0.f)) * gs);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The same loss with the column sums of the written gradient (= the vocabulary projection's bias gradient) taken in
+// the same pass, so the [rows, V] gradient is not read again for them (824 MB at the captioner's shape). One persistent
+// 1024-thread CTA per SM walks rows b, b + G, ...: thread t owns the 8-column vectors t, t + 1024, ... of every row
+//   * the row lives in registers as raw bf16 (<= 7 x 16 B per thread), read from HBM exactly once;
+//   * per-column fp32 accumulators live in shared memory (V x 4 B <= 224 KB, two float4 planes so that consecutive
+//     lanes touch consecutive 16-byte words) and are private to their owning thread: no atomics, fixed order;
+//   * the next row's vectors are requested as soon as the current row's vector has been consumed in the last pass.
+// The CTA's sums go to part[b][V]; colsum_final_kernel adds the G partials in index order (deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int XC_THREADS = 1024, XC_MAXC = 7;
+__device__ __forceinline__ void bf16x8_to_float(const uint4& raw, float (&x)[8]) {
+  const unsigned int u[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    x[2 * k] = __uint_as_float(u[k] << 16);
+    x[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+  }
+}
+__global__ void __launch_bounds__(XC_THREADS, 1)
+xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const long long* __restrict__ labels,
+                   long long ignore_index, const float* __restrict__ grad_scale_ptr, float grad_scale,
+                   float* __restrict__ loss_rows, float* __restrict__ part) {
+  pdl_trigger();
+  extern __shared__ float4 xc_acc[];  // [2][nvec]
+  __shared__ float s_mx[32], s_sum[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int nvec = (V + 7) >> 3;  // the row stride covers whole vectors; a last partial vector's lanes >= V are padding
+  const int tail = V & 7;
+  constexpr float LOG2E = 1.4426950408889634f;
+  for (int i = t; i < 2 * nvec; i += XC_THREADS) xc_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();
+  __syncthreads();
+  const float gs = grad_scale_ptr ? *grad_scale_ptr * grad_scale : grad_scale;
+  uint4 raw[XC_MAXC];
+  int r = blockIdx.x;
+  if (r < rows) {
+    const uint4* src = reinterpret_cast<const uint4*>(logits + static_cast<long long>(r) * ld);
+#pragma unroll
+    for (int k = 0; k < XC_MAXC; ++k)
+      if (t + k * XC_THREADS < nvec) raw[k] = src[t + k * XC_THREADS];
+  }
+  for (; r < rows; r += gridDim.x) {
+    __nv_bfloat16* row = logits + static_cast<long long>(r) * ld;
+    const int rn = r + gridDim.x;
+    const uint4* nxt = reinterpret_cast<const uint4*>(logits + static_cast<long long>(rn) * ld);
+    const bool more = rn < rows;
+    const long long lab = labels[r];
+    if (!(lab != ignore_index && lab >= 0 && lab < V)) {  // CTA-uniform
+      if (t == 0 && loss_rows) loss_rows[r] = 0.f;
+#pragma unroll
+      for (int k = 0; k < XC_MAXC; ++k) {
+        const int vi = t + k * XC_THREADS;
+        if (vi < nvec) {
+          reinterpret_cast<uint4*>(row)[vi] = make_uint4(0u, 0u, 0u, 0u);
+          if (more) raw[k] = nxt[vi];
+        }
+      }
+      continue;
+    }
+    if (tail) {  // padding lanes read as -inf: they add 0 to the sums and receive a zero gradient
+#pragma unroll
+      for (int k = 0; k < XC_MAXC; ++k)
+        if (t + k * XC_THREADS == nvec - 1) {
+          unsigned int* u = reinterpret_cast<unsigned int*>(&raw[k]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (2 * q >= tail) u[q] = (u[q] & 0xffff0000u) | 0xff80u;
+            if (2 * q + 1 >= tail) u[q] = (u[q] & 0x0000ffffu) | 0xff800000u;
+          }
+        }
+    }
+    float x_lab = 0.f;
+    if (t == 0) x_lab = __bfloat162float(row[lab]);  // read before the last pass (behind two barriers) overwrites it
+    // pass 1: row maximum
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < XC_MAXC; ++k)
+      if (t + k * XC_THREADS < nvec) {
+        float x[8];
+        bf16x8_to_float(raw[k], x);
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]))));
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_mx[w] = mx;
+    __syncthreads();
+    mx = s_mx[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float mb = -mx * LOG2E;
+    // pass 2: sum of exp(x - max)
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < XC_MAXC; ++k)
+      if (t + k * XC_THREADS < nvec) {
+        float x[8];
+        bf16x8_to_float(raw[k], x);
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += vy_ex2_approx(fmaf(x[j], LOG2E, mb));
+        sum += a;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_sum[w] = sum;
+    __syncthreads();
+    sum = s_sum[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (t == 0 && loss_rows) loss_rows[r] = mx + __logf(sum) - x_lab;
+    // pass 3: gradient written over the logits, column sums, next row requested
+    const float sc = gs / sum;
+    const int lab_vi = static_cast<int>(lab >> 3), lab_j = static_cast<int>(lab & 7);
+#pragma unroll
+    for (int k = 0; k < XC_MAXC; ++k) {
+      const int vi = t + k * XC_THREADS;
+      if (vi < nvec) {
+        float x[8];
+        bf16x8_to_float(raw[k], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = vy_ex2_approx(fmaf(x[j], LOG2E, mb)) * sc;
+        if (vi == lab_vi) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] -= (j == lab_j ? gs : 0.f);
+        }
+        if (more) raw[k] = nxt[vi];
+        float4 a0 = xc_acc[vi], a1 = xc_acc[nvec + vi];
+        a0.x += x[0]; a0.y += x[1]; a0.z += x[2]; a0.w += x[3];
+        a1.x += x[4]; a1.y += x[5]; a1.z += x[6]; a1.w += x[7];
+        xc_acc[vi] = a0;
+        xc_acc[nvec + vi] = a1;
+        uint4 o;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+        reinterpret_cast<uint4*>(row)[vi] = o;
+      }
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(part + static_cast<long long>(blockIdx.x) * nvec * 8);  // rows of nvec * 8 floats
+#pragma unroll
+  for (int k = 0; k < XC_MAXC; ++k) {
+    const int vi = t + k * XC_THREADS;
+    if (vi < nvec) {
+      dst[2 * vi] = xc_acc[vi];
+      dst[2 * vi + 1] = xc_acc[nvec + vi];
     }
   }
 }
@@ -835,14 +986,31 @@ extern "C" int vy_colsum(int rows, int cols, const void* x, int64_t ld, int dtyp
   const int vec_ok = (aligned16(x) && (ld * static_cast<long long>(dtype_size(dtype))) % 16 == 0) ? 1 : 0;
   VY_CUDA_OK(launch_kernel(colsum_partial_kernel, dim3(grid), dim3(256), 0, st, rows, cols, x, ld, dtype, workspace, vec_ok));
   VY_LAUNCH_OK();
-  VY_CUDA_OK(launch_kernel(colsum_final_kernel, dim3((cols + 127) / 128), dim3(128), 0, st, cols, chunks, workspace, out, out_dtype, accumulate,
-                                                           scale == 0.f ? 1.f : scale));
+  VY_CUDA_OK(launch_kernel(colsum_final_kernel, dim3((cols + 127) / 128), dim3(128), 0, st, cols, chunks, workspace, static_cast<long long>(cols), out, out_dtype, accumulate,
+                                                           scale == 0.f ? 1.f : scale, static_cast<const float*>(nullptr)));
   VY_LAUNCH_OK();
   count_launch(2);
   return VY_OK;
 }
 
 extern "C" int vy_colsum_workspace_floats(int cols) { return CS_CHUNKS * cols; }
+
+extern "C" int vy_xent_colsum_chunks(int rows, int V, int dtype) {
+  if (rows <= 0 || V <= 0 || dtype != VY_BF16 || (V + 7) / 8 > XC_MAXC * XC_THREADS) return 0;
+  const int sms = num_sms();
+  return rows < sms ? rows : sms;
+}
+
+extern "C" int vy_colsum_finish(int cols, int chunks, const float* part, int64_t part_ld, void* out, int out_dtype, int accumulate,
+                                float scale, const float* scale_ptr, void* stream) {
+  VY_NEED_DEVICE("vy_colsum_finish");
+  VY_CHECK_ARG(cols > 0 && chunks > 0 && part && part_ld >= cols && out && dtype_ok(out_dtype), "vy_colsum_finish: bad arguments");
+  VY_CUDA_OK(launch_kernel(colsum_final_kernel, dim3((cols + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), cols, chunks, part,
+                           static_cast<long long>(part_ld), out, out_dtype, accumulate, scale == 0.f ? 1.f : scale, scale_ptr));
+  VY_LAUNCH_OK();
+  count_launch();
+  return VY_OK;
+}
 
 extern "C" int vy_cast4d(const VyCast4d* p) {
   VY_CHECK_ARG(p != nullptr, "vy_cast4d: null params");
@@ -867,6 +1035,25 @@ extern "C" int vy_softmax_xent(const VyXent* p) {
   VY_CHECK_ARG(p != nullptr, "vy_softmax_xent: null params");
   VY_NEED_DEVICE("vy_softmax_xent");
   VY_CHECK_ARG(p->rows > 0 && p->V > 0 && p->logits && p->labels && dtype_ok(p->dtype), "vy_softmax_xent: bad arguments");
+  if (p->colsum_part) {  // fused column sums: one persistent CTA per SM (see xent_colsum_kernel)
+    const int chunks = vy_xent_colsum_chunks(p->rows, p->V, p->dtype);
+    const int nvec = (p->V + 7) / 8;
+    VY_CHECK_ARG(chunks > 0 && p->write_grad && aligned16(p->logits) && p->ld % 8 == 0 && p->ld >= nvec * 8 && aligned16(p->colsum_part),
+                 "vy_softmax_xent: colsum_part needs write_grad, bf16 logits whose row stride is a multiple of 8 elements covering "
+                 "V rounded up to 8, and vy_xent_colsum_chunks() > 0");
+    const size_t smem = static_cast<size_t>(nvec) * 32;
+    static bool attr_set = false;  // per process; the limit is a property of the function on every device of one kind
+    if (!attr_set) {
+      VY_CUDA_OK(cudaFuncSetAttribute(xent_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XC_MAXC * XC_THREADS * 32));
+      attr_set = true;
+    }
+    VY_CUDA_OK(launch_kernel(xent_colsum_kernel, dim3(chunks), dim3(XC_THREADS), smem, static_cast<cudaStream_t>(p->stream), p->rows, p->V,
+                             static_cast<__nv_bfloat16*>(p->logits), static_cast<long long>(p->ld), reinterpret_cast<const long long*>(p->labels),
+                             static_cast<long long>(p->ignore_index), p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->colsum_part));
+    VY_LAUNCH_OK();
+    count_launch();
+    return VY_OK;
+  }
   VY_CUDA_OK(launch_kernel(xent_kernel, dim3(p->rows), dim3(256), 0, static_cast<cudaStream_t>(p->stream), 
       p->rows, p->V, p->logits, p->ld, p->dtype, reinterpret_cast<const long long*>(p->labels), p->ignore_index,
       p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->write_grad,

@@ -609,15 +609,40 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, out_dtype: Optio
 
 
 def softmax_xent(logits: torch.Tensor, labels: torch.Tensor, *, ignore_index: int = -100, grad_scale: float = 1.0,
-                 grad_scale_ptr: Optional[torch.Tensor] = None, write_grad: bool = True) -> torch.Tensor:
-    """Per-row cross-entropy (fp32 [rows]); overwrites `logits` with d loss/d logits when write_grad."""
-    _need_cuda(logits, labels, grad_scale_ptr)
+                 grad_scale_ptr: Optional[torch.Tensor] = None, write_grad: bool = True, colsum_part: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-row cross-entropy (fp32 [rows]); overwrites `logits` with d loss/d logits when write_grad. `colsum_part`
+    (xent_colsum_part(logits)): the written gradient's column sums are left there as partial sums for colsum_finish."""
+    _need_cuda(logits, labels, grad_scale_ptr, colsum_part)
     rows, V = logits.shape
     loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
     _lib.call("vy_softmax_xent", "VyXent", rows=rows, V=V, logits=logits.data_ptr(), ld=logits.stride(0), dtype=_dt(logits),
               labels=labels.data_ptr(), ignore_index=ignore_index, grad_scale_ptr=_ptr(grad_scale_ptr),
-              grad_scale=float(grad_scale), loss_rows=loss.data_ptr(), write_grad=int(write_grad), stream=_stream())
+              grad_scale=float(grad_scale), loss_rows=loss.data_ptr(), write_grad=int(write_grad), colsum_part=_ptr(colsum_part),
+              stream=_stream())
     return loss
+
+
+def xent_colsum_part(logits: torch.Tensor) -> Optional[torch.Tensor]:
+    """The fp32 [chunks, V] buffer softmax_xent(colsum_part=...) fills for these logits, or None when the fused column
+    sums do not cover the shape / dtype (the caller then sums the gradient with `colsum`)."""
+    rows, V = logits.shape
+    Vp = (V + 7) // 8 * 8  # a last partial vector of a row is read and written whole: the row stride must cover it
+    if logits.dtype != torch.bfloat16 or logits.stride(1) != 1 or logits.stride(0) % 8 or logits.stride(0) < Vp or logits.data_ptr() % 16:
+        return None
+    chunks = _lib.lib().vy_xent_colsum_chunks(rows, V, _dt(logits))
+    return torch.empty((chunks, Vp), device=logits.device, dtype=torch.float32)[:, :V] if chunks > 0 else None
+
+
+def colsum_finish(part: torch.Tensor, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                  accumulate: bool = False, scale: float = 1.0, scale_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] (+)= scale * (*scale_ptr) * sum_k part[k, c], k in index order."""
+    _need_cuda(part, out, scale_ptr)
+    chunks, Cn = part.shape
+    if out is None:
+        out = torch.empty(Cn, device=part.device, dtype=out_dtype or torch.float32)
+    _lib.check(_lib.lib().vy_colsum_finish(Cn, chunks, part.data_ptr(), part.stride(0), out.data_ptr(), _dt(out), int(accumulate), float(scale),
+                                           _ptr(scale_ptr), _stream()), "vy_colsum_finish")
+    return out
 
 
 def attn_bwd(q, k, v, o, dout, lse, *, causal: bool, q_pos0: int, key_padding_mask, rope_cos, rope_sin,
