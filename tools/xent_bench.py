@@ -1,7 +1,10 @@
 """Times vy_softmax_xent at the captioner's shape (rows x V bf16 logits, padded rows): the two-kernel form (loss + gradient,
 then vy_colsum of the gradient) against the fused form (column sums taken in the same pass). CUDA events, L2 flushed by the
 0.8 GB working set itself. Usage: python tools/xent_bench.py [rows] [V] [iters]"""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 

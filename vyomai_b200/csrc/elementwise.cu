@@ -2,6 +2,8 @@
 // patch extraction, greedy argmax, column sums (bias gradients), strided casts, fused
 // softmax-cross-entropy, fused AdamW with global-norm clipping. All vectorised to 16-byte
 // accesses where the layout allows; grid sizes are multiples of the SM count.
+#include <type_traits>
+
 #include "vy_common.cuh"
 #include "vy_ptx.cuh"
 
@@ -443,7 +445,7 @@ xent_kernel(int rows, int V, void* __restrict__ logits, long long ld, int dt, co
 //   * the next row's vectors are requested as soon as the current row's vector has been consumed in the last pass.
 // The CTA's sums go to part[b][V]; colsum_final_kernel adds the G partials in index order (deterministic).
 // ------------------------------------------------------------------------------------------
-constexpr int XC_THREADS = 1024, XC_MAXC = 7;
+constexpr int XC_THREADS = 1024, XC_MAXC = 7, XC_HALF = 4;
 __device__ __forceinline__ void bf16x8_to_float(const uint4& raw, float (&x)[8]) {
   const unsigned int u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -452,6 +454,8 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& raw, float (&x)[8])
     x[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
   }
 }
+// NFULL: vectors k < NFULL of a thread exist for every thread (V >= NFULL * 8192) and are processed without bounds tests.
+template <int NFULL>
 __global__ void __launch_bounds__(XC_THREADS, 1)
 xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const long long* __restrict__ labels,
                    long long ignore_index, const float* __restrict__ grad_scale_ptr, float grad_scale,
@@ -463,17 +467,33 @@ xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const l
   const int nvec = (V + 7) >> 3;  // the row stride covers whole vectors; a last partial vector's lanes >= V are padding
   const int tail = V & 7;
   constexpr float LOG2E = 1.4426950408889634f;
+#define XC_HAS(k) ((k) < NFULL || t + (k) * XC_THREADS < nvec)
+// The passes unpack the same registers; without this the compiler keeps the unpacked fp32 values of one pass alive for the
+// next (56 more registers than there are) and spills them.
+#define XC_OPAQUE()                                                                                        \
+  _Pragma("unroll") for (int k_ = 0; k_ < XC_MAXC; ++k_)                                                  \
+      asm volatile("" : "+r"(raw[k_].x), "+r"(raw[k_].y), "+r"(raw[k_].z), "+r"(raw[k_].w))
   for (int i = t; i < 2 * nvec; i += XC_THREADS) xc_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   pdl_wait();
   __syncthreads();
   const float gs = grad_scale_ptr ? *grad_scale_ptr * grad_scale : grad_scale;
   uint4 raw[XC_MAXC];
   int r = blockIdx.x;
+  // Rows are asked into L2 two iterations ahead (one 128-byte line per thread, no register and no scoreboard involved), so
+  // the register loads of the next row, issued in two batches inside the last pass, find them there (~0.5 us instead of a
+  // 2 us DRAM round, measured in tools/microbench) and anything that has to wait behind them waits that long at most.
+  auto ask_l2 = [&](int rr) {
+    if (rr < rows) {
+      const char* b = reinterpret_cast<const char*>(logits + static_cast<long long>(rr) * ld);
+      if (t * 8 < nvec) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + t * 128));  // nvec <= 7168: at most 896 lines
+    }
+  };
   if (r < rows) {
     const uint4* src = reinterpret_cast<const uint4*>(logits + static_cast<long long>(r) * ld);
 #pragma unroll
     for (int k = 0; k < XC_MAXC; ++k)
-      if (t + k * XC_THREADS < nvec) raw[k] = src[t + k * XC_THREADS];
+      if (XC_HAS(k)) raw[k] = src[t + k * XC_THREADS];
+    ask_l2(r + gridDim.x);
   }
   for (; r < rows; r += gridDim.x) {
     __nv_bfloat16* row = logits + static_cast<long long>(r) * ld;
@@ -481,18 +501,24 @@ xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const l
     const uint4* nxt = reinterpret_cast<const uint4*>(logits + static_cast<long long>(rn) * ld);
     const bool more = rn < rows;
     const long long lab = labels[r];
+    ask_l2(rn + gridDim.x);
     if (!(lab != ignore_index && lab >= 0 && lab < V)) {  // CTA-uniform
       if (t == 0 && loss_rows) loss_rows[r] = 0.f;
 #pragma unroll
-      for (int k = 0; k < XC_MAXC; ++k) {
-        const int vi = t + k * XC_THREADS;
-        if (vi < nvec) {
+      for (int k = 0; k < XC_MAXC; ++k)
+        if (XC_HAS(k)) {
+          const int vi = t + k * XC_THREADS;
           reinterpret_cast<uint4*>(row)[vi] = make_uint4(0u, 0u, 0u, 0u);
           if (more) raw[k] = nxt[vi];
         }
-      }
       continue;
     }
+    // the thread that holds the label's column reads its logit now and corrects that one element after the last pass
+    // (softmax - onehot), so the passes themselves carry no per-element label test
+    const int lab_vi = static_cast<int>(lab >> 3);
+    const bool own = t == (lab_vi & (XC_THREADS - 1));
+    float x_lab = 0.f;
+    if (own) x_lab = __bfloat162float(row[lab]);
     if (tail) {  // padding lanes read as -inf: they add 0 to the sums and receive a zero gradient
 #pragma unroll
       for (int k = 0; k < XC_MAXC; ++k)
@@ -505,17 +531,16 @@ xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const l
           }
         }
     }
-    float x_lab = 0.f;
-    if (t == 0) x_lab = __bfloat162float(row[lab]);  // read before the last pass (behind two barriers) overwrites it
-    // pass 1: row maximum
-    float mx = -INFINITY;
+    // pass 1: row maximum on the packed values
+    unsigned int pm = 0xff80ff80u;
 #pragma unroll
     for (int k = 0; k < XC_MAXC; ++k)
-      if (t + k * XC_THREADS < nvec) {
-        float x[8];
-        bf16x8_to_float(raw[k], x);
-        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]))));
+      if (XC_HAS(k)) {
+        const unsigned int u[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) asm("max.bf16x2 %0, %0, %1;" : "+r"(pm) : "r"(u[q]));
       }
+    float mx = fmaxf(__uint_as_float(pm << 16), __uint_as_float(pm & 0xffff0000u));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) s_mx[w] = mx;
@@ -524,11 +549,12 @@ xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const l
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const float mb = -mx * LOG2E;
+    XC_OPAQUE();
     // pass 2: sum of exp(x - max)
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < XC_MAXC; ++k)
-      if (t + k * XC_THREADS < nvec) {
+      if (XC_HAS(k)) {
         float x[8];
         bf16x8_to_float(raw[k], x);
         float a = 0.f;
@@ -543,45 +569,71 @@ xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const l
     sum = s_sum[lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (t == 0 && loss_rows) loss_rows[r] = mx + __logf(sum) - x_lab;
-    // pass 3: gradient written over the logits, column sums, next row requested
+    // pass 3: softmax * scale written over the logits, column sums, next row requested. A positive scale is folded into the
+    // exponent (one multiply per element less); anything else (<= 0, non-finite) is multiplied in.
+    XC_OPAQUE();
     const float sc = gs / sum;
-    const int lab_vi = static_cast<int>(lab >> 3), lab_j = static_cast<int>(lab & 7);
+    const bool fold = sc > 0.f && sc < INFINITY;
+    const float mb3 = fold ? mb + __log2f(sc) : mb;
+    const float mul = fold ? 1.f : sc;
+    auto pass3 = [&](auto folded) {
 #pragma unroll
-    for (int k = 0; k < XC_MAXC; ++k) {
-      const int vi = t + k * XC_THREADS;
-      if (vi < nvec) {
-        float x[8];
-        bf16x8_to_float(raw[k], x);
+      for (int k = 0; k < XC_MAXC; ++k) {
+        if (XC_HAS(k)) {
+          const int vi = t + k * XC_THREADS;
+          const unsigned int u[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+          unsigned int o[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = vy_ex2_approx(fmaf(x[j], LOG2E, mb)) * sc;
-        if (vi == lab_vi) {
+          for (int h = 0; h < 2; ++h) {  // four columns at a time: fewer values alive than registers left
+            float x[4] = {__uint_as_float(u[2 * h] << 16), __uint_as_float(u[2 * h] & 0xffff0000u),
+                          __uint_as_float(u[2 * h + 1] << 16), __uint_as_float(u[2 * h + 1] & 0xffff0000u)};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] -= (j == lab_j ? gs : 0.f);
+            for (int j = 0; j < 4; ++j) {
+              x[j] = vy_ex2_approx(fmaf(x[j], LOG2E, mb3));
+              if (!decltype(folded)::value) x[j] *= mul;
+            }
+            float4 a = xc_acc[h * nvec + vi];
+            a.x += x[0]; a.y += x[1]; a.z += x[2]; a.w += x[3];
+            xc_acc[h * nvec + vi] = a;
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+            o[2 * h] = *reinterpret_cast<const unsigned int*>(&p0);
+            o[2 * h + 1] = *reinterpret_cast<const unsigned int*>(&p1);
+          }
+          reinterpret_cast<uint4*>(row)[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+          asm volatile("" ::: "memory");  // one vector at a time: interleaving the bodies costs more registers than there are
         }
-        if (more) raw[k] = nxt[vi];
-        float4 a0 = xc_acc[vi], a1 = xc_acc[nvec + vi];
-        a0.x += x[0]; a0.y += x[1]; a0.z += x[2]; a0.w += x[3];
-        a1.x += x[4]; a1.y += x[5]; a1.z += x[6]; a1.w += x[7];
-        xc_acc[vi] = a0;
-        xc_acc[nvec + vi] = a1;
-        uint4 o;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+        if (k == XC_HALF - 1 && more) {  // the first vectors are consumed: their registers take the next row's
 #pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
-        reinterpret_cast<uint4*>(row)[vi] = o;
+          for (int kk = 0; kk < XC_HALF; ++kk)
+            if (XC_HAS(kk)) raw[kk] = nxt[t + kk * XC_THREADS];
+        }
       }
+      if (more) {
+#pragma unroll
+        for (int kk = XC_HALF; kk < XC_MAXC; ++kk)
+          if (XC_HAS(kk)) raw[kk] = nxt[t + kk * XC_THREADS];
+      }
+    };
+    if (fold) pass3(std::true_type{});
+    else pass3(std::false_type{});
+    if (own) {  // this thread wrote the label's vector above: same-thread order makes the corrections land after it
+      const float g = vy_ex2_approx(fmaf(x_lab, LOG2E, mb3)) * mul - gs;
+      row[lab] = __float2bfloat16_rn(g);
+      const int lab_j = static_cast<int>(lab & 7);
+      reinterpret_cast<float*>(xc_acc)[(static_cast<long long>(lab_j >> 2) * nvec + lab_vi) * 4 + (lab_j & 3)] -= gs;
+      if (loss_rows) loss_rows[r] = mx + __logf(sum) - x_lab;
     }
   }
   float4* dst = reinterpret_cast<float4*>(part + static_cast<long long>(blockIdx.x) * nvec * 8);  // rows of nvec * 8 floats
 #pragma unroll
-  for (int k = 0; k < XC_MAXC; ++k) {
-    const int vi = t + k * XC_THREADS;
-    if (vi < nvec) {
+  for (int k = 0; k < XC_MAXC; ++k)
+    if (XC_HAS(k)) {
+      const int vi = t + k * XC_THREADS;
       dst[2 * vi] = xc_acc[vi];
       dst[2 * vi + 1] = xc_acc[nvec + vi];
     }
-  }
+#undef XC_HAS
+#undef XC_OPAQUE
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1042,14 +1094,15 @@ extern "C" int vy_softmax_xent(const VyXent* p) {
                  "vy_softmax_xent: colsum_part needs write_grad, bf16 logits whose row stride is a multiple of 8 elements covering "
                  "V rounded up to 8, and vy_xent_colsum_chunks() > 0");
     const size_t smem = static_cast<size_t>(nvec) * 32;
-    static bool attr_set = false;  // per process; the limit is a property of the function on every device of one kind
-    if (!attr_set) {
-      VY_CUDA_OK(cudaFuncSetAttribute(xent_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XC_MAXC * XC_THREADS * 32));
-      attr_set = true;
-    }
-    VY_CUDA_OK(launch_kernel(xent_colsum_kernel, dim3(chunks), dim3(XC_THREADS), smem, static_cast<cudaStream_t>(p->stream), p->rows, p->V,
-                             static_cast<__nv_bfloat16*>(p->logits), static_cast<long long>(p->ld), reinterpret_cast<const long long*>(p->labels),
-                             static_cast<long long>(p->ignore_index), p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->colsum_part));
+    auto go = [&](auto kern) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XC_MAXC * XC_THREADS * 32);
+      if (e != cudaSuccess) return e;
+      return launch_kernel(kern, dim3(chunks), dim3(XC_THREADS), smem, static_cast<cudaStream_t>(p->stream), p->rows, p->V,
+                           static_cast<__nv_bfloat16*>(p->logits), static_cast<long long>(p->ld), reinterpret_cast<const long long*>(p->labels),
+                           static_cast<long long>(p->ignore_index), p->grad_scale_ptr, p->grad_scale, p->loss_rows, p->colsum_part);
+    };
+    const int nfull = nvec / XC_THREADS;  // vectors every thread owns
+    VY_CUDA_OK(nfull >= 6 ? go(xent_colsum_kernel<6>) : nfull >= 3 ? go(xent_colsum_kernel<3>) : go(xent_colsum_kernel<0>));
     VY_LAUNCH_OK();
     count_launch();
     return VY_OK;
