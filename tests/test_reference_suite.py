@@ -5,6 +5,8 @@ baseline/_ref/tests/ is an untouched copy of /root/reference/tests made by `__gr
 sys.path, so `from VyomAI import ...` resolves to the B200-native package. These tests assert shapes and the agreement of
 the no-cache / dynamic / static generation paths; numerical parity is pinned elsewhere (golden fixtures).
 They build their models in .train() with hidden_dropout_prob = 0.1, on the CPU in test_vision_encoder.py — both must work.
+The run is seeded through tests/ref_seed_plugin.py (see its docstring: the files' chained-equality assertion on greedy ids of
+randomly initialised models is not stable under near ties); the test files themselves are not touched.
 """
 import os
 import subprocess
@@ -29,7 +31,7 @@ def test_reference_test_file_passes_unchanged(fname):
     probe = subprocess.run([sys.executable, "-c", "import VyomAI, os; print(os.path.dirname(VyomAI.__file__))"], cwd=ROOT, env=env,
                            capture_output=True, text=True)
     assert probe.stdout.strip() == os.path.join(ROOT, "VyomAI"), probe.stdout + probe.stderr  # our import name, not the copy
-    r = subprocess.run([sys.executable, "-m", "pytest", path, "-q", "-x", "-p", "no:cacheprovider", "--import-mode=importlib",
+    r = subprocess.run([sys.executable, "-m", "pytest", path, "-q", "-x", "-p", "no:cacheprovider", "-p", "tests.ref_seed_plugin", "--import-mode=importlib",
                         "--rootdir", REF_TESTS, "-c", os.devnull], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
