@@ -592,21 +592,25 @@ xent_colsum_kernel(int rows, int V, __nv_bfloat16* logits, long long ld, const l
       if (XC_HAS(k)) {
         const int vi = t + k * XC_THREADS;
         const unsigned int u[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+        float4 a0 = xc_acc[vi], a1 = xc_acc[nvec + vi];  // both accumulator words requested before the arithmetic
+        float x[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[q]));
+          x[2 * q] = f.x * sc;
+          x[2 * q + 1] = f.y * sc;
+        }
+        a0.x += x[0]; a0.y += x[1]; a0.z += x[2]; a0.w += x[3];
+        a1.x += x[4]; a1.y += x[5]; a1.z += x[6]; a1.w += x[7];
+        xc_acc[vi] = a0;
+        xc_acc[nvec + vi] = a1;
         unsigned int o[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // four columns at a time: fewer values alive than registers left
-          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u[2 * h]));
-          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u[2 * h + 1]));
-          const float x0 = lo.x * sc, x1 = lo.y * sc, x2 = hi.x * sc, x3 = hi.y * sc;
-          float4 a = xc_acc[h * nvec + vi];
-          a.x += x0; a.y += x1; a.z += x2; a.w += x3;
-          xc_acc[h * nvec + vi] = a;
-          const __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
-          o[2 * h] = *reinterpret_cast<const unsigned int*>(&p0);
-          o[2 * h + 1] = *reinterpret_cast<const unsigned int*>(&p1);
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+          o[q] = *reinterpret_cast<const unsigned int*>(&pk);
         }
         reinterpret_cast<uint4*>(row)[vi] = make_uint4(o[0], o[1], o[2], o[3]);
-        asm volatile("" ::: "memory");  // one vector at a time: interleaving the bodies costs more registers than there are
       }
       if (k == XC_HALF - 1 && more) {  // the first vectors are consumed: their registers take the next row's
 #pragma unroll
