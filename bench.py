@@ -305,14 +305,14 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
-FAMILIES = (  # kernel-name fragment -> C-ABI entry point it belongs to
+FAMILIES = (  # kernel-name fragment -> C-ABI entry point it belongs to (first match wins)
+    ("dp_barrier", "vy_dp_barrier (includes the wait for the peers)"), ("dp_reduce", "vy_dp_reduce_shard"), ("dp_adamw", "vy_dp_adamw_shard"),
     ("gemm_kernel", "vy_gemm"), ("splitk_reduce", "vy_gemm"), ("attn_fwd_kernel", "vy_attn_fwd"), ("attn_bwd", "vy_attn_bwd"),
     ("attn_dsum", "vy_attn_bwd"), ("add_layernorm_fwd", "vy_add_layernorm_fwd"), ("add_layernorm_bwd", "vy_add_layernorm_bwd"),
     ("norm_bwd", "vy_add_layernorm_bwd"), ("adamw", "vy_adamw"), ("sqnorm", "vy_sqnorm"), ("xent", "vy_softmax_xent"),
     ("colsum", "vy_colsum"), ("embed_bwd", "vy_embed_bwd"), ("embed_fwd", "vy_embed_fwd"), ("patchify", "vy_patchify"),
     ("cast4d", "vy_cast4d"), ("act_bwd", "vy_act_bwd"), ("scale_by_ptr", "vy_scale_by_ptr"), ("attn_decode", "vy_attn_decode"),
-    ("decode_step", "vy_decode_step"), ("argmax", "vy_argmax_rows"), ("dp_barrier", "vy_dp_barrier (includes the wait for the peers)"),
-    ("dp_reduce", "vy_dp_reduce_shard"), ("dp_adamw", "vy_dp_adamw_shard"), ("nccl", "nccl"), ("Memcpy", "memcpy"), ("Memset", "memset"),
+    ("decode_step", "vy_decode_step"), ("argmax", "vy_argmax_rows"), ("nccl", "nccl"), ("Memcpy", "memcpy"), ("Memset", "memset"),
 )
 
 
