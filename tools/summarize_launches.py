@@ -37,7 +37,7 @@ def main():
     out.append(f"| **total** | {sum(a[0] for a in agg.values())} | {total / 1e3:.1f} | | 100% |")
     text = "\n".join(out) + "\n"
     if len(sys.argv) > 2:
-        open(sys.argv[2], "a").write(text)
+        open(sys.argv[2], "w").write(text)
     print(text)
 
 
