@@ -663,8 +663,22 @@ sqnorm_kernel(long long n, const void* __restrict__ g, int dt, float* __restrict
   __shared__ bool s_last;
   float a = 0.f;
   const long long nvec = n >> 3;
-  for (long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; vi < nvec;
-       vi += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long vi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  {  // four 16-byte loads in flight per thread (ncu: one at a time left the kernel latency-bound at 3.9 of 6.5 TB/s)
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (; vi + 3 * stride < nvec; vi += 4 * stride) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ld8_as_float(g, dt, (vi + u * stride) * 8, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a4[u] += v[u][j] * v[u][j];
+    }
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+  }
+  for (; vi < nvec; vi += stride) {
     float v[8];
     ld8_as_float(g, dt, vi * 8, v);
 #pragma unroll
