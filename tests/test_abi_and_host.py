@@ -357,3 +357,22 @@ def test_sharded_step_host_logic():
                 assert hi == lo2 and lo % 8 == 0 and hi % 8 == 0 and lo <= hi
     assert dp_shard.available() is False  # no CUDA device / no process group here
     assert dp_shard.MAX_WORLD == 8
+
+
+def test_bench_kernel_families_map_kernel_names_to_their_entry_points():
+    """bench.py's kernel table: first match wins, so the specific fragments must come before the generic ones (the fused
+    cross-entropy kernel is not a column sum, the sharded optimizer kernel is not vy_adamw) and the data-parallel barrier — a
+    wait, not work — is recognisable by its family name (bench.py leaves it out of the roofline's dominant-kernel choice)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("vy_bench_for_test", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    f = bench.family_of
+    assert f("void vy::xent_colsum_kernel<6>(int, int, __nv_bfloat16*, ...)") == "vy_softmax_xent"
+    assert f("vy::xent_kernel(int, int, void*, ...)") == "vy_softmax_xent"
+    assert f("vy::colsum_partial_kernel(int, int, ...)") == "vy_colsum" and f("vy::colsum_final_kernel(...)") == "vy_colsum"
+    assert f("vy::adamw_kernel(long long, ...)") == "vy_adamw" and f("vy::dp_adamw_kernel(...)") == "vy_dp_adamw_shard"
+    assert f("vy::dp_barrier_kernel(...)").startswith("vy_dp_barrier") and f("vy::dp_reduce_kernel(...)") == "vy_dp_reduce_shard"
+    assert f("void vy::gemm_kernel<__nv_bfloat16, 256, true, true, true, false>(...)") == "vy_gemm"
+    assert f("at::native::vectorized_elementwise_kernel<4, ...>") == "torch_glue"
